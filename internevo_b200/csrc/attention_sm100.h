@@ -1,0 +1,36 @@
+// Host API of the sm_100a flash-attention kernels (varlen, causal, GQA; bf16 in / fp32 softmax).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+struct AttnDesc {
+    const void* q = nullptr;  // [T, H, D]   strides in elements (q_stride_t, q_stride_h, 1)
+    const void* k = nullptr;  // [T, Hkv, D]
+    const void* v = nullptr;  // [T, Hkv, D]
+    void* o = nullptr;        // [T, H, D] contiguous
+    float* lse = nullptr;     // [H, T] natural-log LSE (scaled scores)
+    int T = 0, H = 0, Hkv = 0, D = 0;
+    int64_t q_stride_t = 0, q_stride_h = 0, k_stride_t = 0, k_stride_h = 0, v_stride_t = 0, v_stride_h = 0;
+    const int* cu_seqlens = nullptr;  // [num_seqs + 1]
+    int num_seqs = 0, max_seqlen = 0;
+    float scale = 1.f;
+    int causal = 1;
+};
+
+struct AttnBwdDesc {
+    AttnDesc f;
+    const void* dout = nullptr;  // [T, H, D] contiguous
+    void* dq = nullptr;          // [T, H, D]
+    void* dk = nullptr;          // [T, Hkv, D]
+    void* dv = nullptr;          // [T, Hkv, D]
+    int64_t dq_stride_t = 0, dq_stride_h = 0, dk_stride_t = 0, dk_stride_h = 0, dv_stride_t = 0, dv_stride_h = 0;
+    float* delta = nullptr;   // [H, T] scratch: rowsum(dO * O)
+    float* dq_acc = nullptr;  // [T, H, D] fp32 scratch (zero-initialised by the caller)
+};
+
+int attn_fwd(const AttnDesc& d, cudaStream_t s);
+int attn_bwd(const AttnBwdDesc& d, cudaStream_t s);
+
+}  // namespace b200

@@ -1,0 +1,303 @@
+// torch op registrations for the sm_100a kernels (namespace torch.ops.b200). Thin: shape checks + raw launches on the
+// current stream; allocation and autograd live in python (internevo_b200/ops).
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/library.h>
+
+#include "attention_sm100.h"
+#include "comm_kernels.h"
+#include "elementwise.h"
+#include "gemm_sm100.h"
+
+using at::Tensor;
+using c10::optional;
+
+namespace {
+
+inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+inline const void* optptr(const optional<Tensor>& t) { return t.has_value() ? t->data_ptr() : nullptr; }
+
+#define CHECK_RC(rc, what) TORCH_CHECK((rc) == 0, what, " failed with code ", (rc))
+#define CHECK_BF16(t) TORCH_CHECK((t).is_cuda() && (t).scalar_type() == at::kBFloat16, #t " must be a CUDA bf16 tensor")
+
+// D[M,N] (+)= A * B^T.  a: [M,K] (a_mn=false) or [K,M] (a_mn=true); b: [N,K] (b_mn=false) or [K,N] (b_mn=true)
+void gemm(const Tensor& a, const Tensor& b, Tensor& out, bool a_mn, bool b_mn, const optional<Tensor>& bias,
+          int64_t flags, const optional<Tensor>& h, int64_t force_bn, int64_t max_ctas) {
+    CHECK_BF16(a);
+    CHECK_BF16(b);
+    TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && out.dim() == 2, "gemm expects 2-D tensors");
+    TORCH_CHECK(a.stride(1) == 1 && b.stride(1) == 1 && out.stride(1) == 1, "innermost dim must be contiguous");
+    c10::cuda::CUDAGuard guard(a.device());
+    b200::GemmDesc g;
+    g.M = a_mn ? a.size(1) : a.size(0);
+    g.K = a_mn ? a.size(0) : a.size(1);
+    g.N = b_mn ? b.size(1) : b.size(0);
+    const int64_t kb = b_mn ? b.size(0) : b.size(1);
+    TORCH_CHECK(kb == g.K, "gemm: K mismatch ", kb, " vs ", g.K);
+    TORCH_CHECK(out.size(0) == g.M && out.size(1) == g.N, "gemm: bad output shape");
+    TORCH_CHECK(g.N % 8 == 0 && g.K % 8 == 0, "gemm: N and K must be multiples of 8");
+    TORCH_CHECK(a.stride(0) % 8 == 0 && b.stride(0) % 8 == 0, "gemm: row strides must be multiples of 8 elements");
+    TORCH_CHECK((reinterpret_cast<uintptr_t>(a.data_ptr()) & 15) == 0 && (reinterpret_cast<uintptr_t>(b.data_ptr()) & 15) == 0,
+                "gemm: operands must be 16-byte aligned");
+    if (a_mn) TORCH_CHECK(g.M % 8 == 0, "gemm: M must be a multiple of 8 for MN-major A");
+    const bool f32 = flags & b200::GEMM_OUT_F32;
+    TORCH_CHECK(out.scalar_type() == (f32 ? at::kFloat : at::kBFloat16), "gemm: output dtype/flag mismatch");
+    TORCH_CHECK(out.stride(0) % (f32 ? 4 : 8) == 0, "gemm: output row stride alignment");
+    g.A = a.data_ptr(); g.lda = a.stride(0); g.a_mn_major = a_mn;
+    g.B = b.data_ptr(); g.ldb = b.stride(0); g.b_mn_major = b_mn;
+    g.D = out.data_ptr(); g.ldd = out.stride(0);
+    g.bias = optptr(bias);
+    if (bias.has_value()) { CHECK_BF16(*bias); TORCH_CHECK(bias->numel() == g.N, "gemm: bias size"); }
+    if (flags & b200::GEMM_SWIGLU) {
+        TORCH_CHECK(h.has_value() && h->scalar_type() == at::kBFloat16 && h->size(0) == g.M && h->size(1) == g.N / 2 &&
+                        h->stride(1) == 1 && h->stride(0) % 8 == 0 && g.N % 16 == 0,
+                    "gemm: bad swiglu output");
+        g.H = h->data_ptr(); g.ldh = h->stride(0);
+    }
+    g.flags = static_cast<int>(flags);
+    g.force_bn = static_cast<int>(force_bn);
+    g.max_ctas = static_cast<int>(max_ctas);
+    CHECK_RC(b200::gemm_bf16(g, cur_stream()), "b200::gemm");
+}
+
+void rmsnorm_fwd(const Tensor& x, const optional<Tensor>& res_in, const Tensor& w, Tensor& y,
+                 const optional<Tensor>& res_out, const optional<Tensor>& rstd, double eps) {
+    CHECK_BF16(x); CHECK_BF16(w); CHECK_BF16(y);
+    TORCH_CHECK(x.is_contiguous() && y.is_contiguous() && w.is_contiguous(), "rmsnorm: contiguous tensors required");
+    c10::cuda::CUDAGuard guard(x.device());
+    const int H = x.size(-1);
+    const int rows = x.numel() / H;
+    CHECK_RC(b200::rmsnorm_fwd(x.data_ptr(), optptr(res_in), w.data_ptr(), y.data_ptr(),
+                               res_out.has_value() ? res_out->data_ptr() : nullptr,
+                               rstd.has_value() ? rstd->data_ptr<float>() : nullptr, rows, H, (float)eps, cur_stream()),
+             "b200::rmsnorm_fwd");
+}
+
+int64_t rmsnorm_bwd_blocks(int64_t rows) { return b200::rmsnorm_bwd_blocks((int)rows); }
+
+void rmsnorm_bwd(const Tensor& dy, const Tensor& res, const Tensor& w, const Tensor& rstd, const optional<Tensor>& dres,
+                 Tensor& dx, Tensor& dw_partial, Tensor& dw, bool accumulate) {
+    CHECK_BF16(dy); CHECK_BF16(res); CHECK_BF16(w); CHECK_BF16(dx);
+    TORCH_CHECK(dy.is_contiguous() && res.is_contiguous() && dx.is_contiguous(), "rmsnorm_bwd: contiguous required");
+    c10::cuda::CUDAGuard guard(dy.device());
+    const int H = dy.size(-1);
+    const int rows = dy.numel() / H;
+    TORCH_CHECK(dw_partial.numel() >= (int64_t)b200::rmsnorm_bwd_blocks(rows) * H, "rmsnorm_bwd: partial buffer too small");
+    const bool f32 = dw.scalar_type() == at::kFloat;
+    CHECK_RC(b200::rmsnorm_bwd(dy.data_ptr(), res.data_ptr(), w.data_ptr(), rstd.data_ptr<float>(), optptr(dres),
+                               dx.data_ptr(), dw_partial.data_ptr<float>(), f32 ? dw.data_ptr<float>() : nullptr,
+                               f32 ? nullptr : dw.data_ptr(), accumulate, rows, H, cur_stream()),
+             "b200::rmsnorm_bwd");
+}
+
+// x: [T, heads, D] view with contiguous (heads, D) and token stride x.stride(0)
+void rope(Tensor& x, const optional<Tensor>& pos, const Tensor& cos_t, const Tensor& sin_t, int64_t group,
+          int64_t rot_per_group, bool conj, bool interleaved) {
+    CHECK_BF16(x);
+    TORCH_CHECK(x.dim() == 3 && x.stride(2) == 1 && x.stride(1) == x.size(2), "rope: x must be [T, heads, D] with dense heads");
+    TORCH_CHECK(cos_t.scalar_type() == at::kFloat && cos_t.is_contiguous() && sin_t.is_contiguous(), "rope: tables fp32");
+    if (pos.has_value()) TORCH_CHECK(pos->scalar_type() == at::kInt && pos->is_contiguous(), "rope: pos must be int32");
+    c10::cuda::CUDAGuard guard(x.device());
+    CHECK_RC(b200::rope_inplace(x.data_ptr(), pos.has_value() ? pos->data_ptr<int>() : nullptr, cos_t.data_ptr<float>(),
+                                sin_t.data_ptr<float>(), x.size(0), x.size(1), x.size(2), x.stride(0), group,
+                                rot_per_group, conj, interleaved, cur_stream()),
+             "b200::rope");
+}
+
+void swiglu_fwd(const Tensor& gu, Tensor& h) {
+    CHECK_BF16(gu); CHECK_BF16(h);
+    TORCH_CHECK(gu.is_contiguous() && h.is_contiguous() && gu.numel() == 2 * h.numel(), "swiglu_fwd: shapes");
+    c10::cuda::CUDAGuard guard(gu.device());
+    const int64_t F = h.size(-1);
+    CHECK_RC(b200::swiglu_fwd(gu.data_ptr(), h.data_ptr(), h.numel() / F, F, cur_stream()), "b200::swiglu_fwd");
+}
+void swiglu_bwd(const Tensor& dh, const Tensor& gu, Tensor& dgu) {
+    CHECK_BF16(dh); CHECK_BF16(gu); CHECK_BF16(dgu);
+    TORCH_CHECK(dh.is_contiguous() && gu.is_contiguous() && dgu.is_contiguous(), "swiglu_bwd: contiguous");
+    c10::cuda::CUDAGuard guard(gu.device());
+    const int64_t F = dh.size(-1);
+    CHECK_RC(b200::swiglu_bwd(dh.data_ptr(), gu.data_ptr(), dgu.data_ptr(), dh.numel() / F, F, cur_stream()),
+             "b200::swiglu_bwd");
+}
+
+void ce_fwd(const Tensor& logits, const Tensor& labels, int64_t vocab_start, Tensor& out_max, Tensor& out_sum,
+            Tensor& out_sumx, Tensor& out_tgt) {
+    CHECK_BF16(logits);
+    TORCH_CHECK(logits.dim() == 2 && logits.stride(1) == 1 && labels.scalar_type() == at::kLong && labels.is_contiguous(),
+                "ce_fwd: logits [rows, V] bf16, labels int64");
+    c10::cuda::CUDAGuard guard(logits.device());
+    CHECK_RC(b200::ce_fwd(logits.data_ptr(), logits.stride(0), labels.data_ptr<int64_t>(), logits.size(0), logits.size(1),
+                          vocab_start, out_max.data_ptr<float>(), out_sum.data_ptr<float>(), out_sumx.data_ptr<float>(),
+                          out_tgt.data_ptr<float>(), cur_stream()),
+             "b200::ce_fwd");
+}
+void ce_bwd(Tensor& logits, const Tensor& labels, const Tensor& lse, const Tensor& gscale, int64_t vocab_start,
+            double smoothing, int64_t total_classes, int64_t ignore_index) {
+    CHECK_BF16(logits);
+    c10::cuda::CUDAGuard guard(logits.device());
+    CHECK_RC(b200::ce_bwd(logits.data_ptr(), logits.stride(0), labels.data_ptr<int64_t>(), lse.data_ptr<float>(),
+                          gscale.data_ptr<float>(), logits.size(0), logits.size(1), vocab_start, (float)smoothing,
+                          total_classes, ignore_index, cur_stream()),
+             "b200::ce_bwd");
+}
+
+void adamw(Tensor& p, Tensor& m, Tensor& v, const Tensor& g, const optional<Tensor>& p_lp, double lr, double beta1,
+           double beta2, double eps, double wd, double bc1, double bc2, const optional<Tensor>& scalars) {
+    TORCH_CHECK(p.scalar_type() == at::kFloat && m.scalar_type() == at::kFloat && v.scalar_type() == at::kFloat,
+                "adamw: fp32 state required");
+    TORCH_CHECK(p.is_contiguous() && m.is_contiguous() && v.is_contiguous() && g.is_contiguous(), "adamw: contiguous");
+    TORCH_CHECK(g.numel() == p.numel(), "adamw: grad size");
+    const bool gbf = g.scalar_type() == at::kBFloat16;
+    TORCH_CHECK(gbf || g.scalar_type() == at::kFloat, "adamw: grad must be bf16 or fp32");
+    c10::cuda::CUDAGuard guard(p.device());
+    CHECK_RC(b200::adamw_step(p.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(), g.data_ptr(), gbf,
+                              p_lp.has_value() ? p_lp->data_ptr() : nullptr, p.numel(), (float)lr, (float)beta1,
+                              (float)beta2, (float)eps, (float)wd, (float)bc1, (float)bc2,
+                              scalars.has_value() ? scalars->data_ptr<float>() : nullptr, cur_stream()),
+             "b200::adamw");
+}
+
+void sumsq(const Tensor& g, Tensor& out) {
+    TORCH_CHECK(g.is_contiguous() && out.scalar_type() == at::kFloat, "sumsq: contiguous input, fp32 output");
+    const bool gbf = g.scalar_type() == at::kBFloat16;
+    TORCH_CHECK(gbf || g.scalar_type() == at::kFloat, "sumsq: bf16 or fp32");
+    c10::cuda::CUDAGuard guard(g.device());
+    CHECK_RC(b200::sumsq(g.data_ptr(), gbf, g.numel(), out.data_ptr<float>(), cur_stream()), "b200::sumsq");
+}
+void clip_scalars(const Tensor& sumsq_in, Tensor& scalars, double loss_scale, double clip) {
+    c10::cuda::CUDAGuard guard(scalars.device());
+    CHECK_RC(b200::clip_scalars(sumsq_in.data_ptr<float>(), scalars.data_ptr<float>(), (float)loss_scale, (float)clip,
+                                cur_stream()),
+             "b200::clip_scalars");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// attention
+// ---------------------------------------------------------------------------------------------------------------
+void attn_fwd(const Tensor& q, const Tensor& k, const Tensor& v, Tensor& out, Tensor& lse, const Tensor& cu_seqlens,
+              int64_t max_seqlen, double scale, bool causal) {
+    CHECK_BF16(q); CHECK_BF16(k); CHECK_BF16(v); CHECK_BF16(out);
+    TORCH_CHECK(q.dim() == 3 && k.dim() == 3 && v.dim() == 3, "attn: q [T,H,D], k/v [T,Hkv,D]");
+    TORCH_CHECK(q.stride(2) == 1 && k.stride(2) == 1 && v.stride(2) == 1 && out.is_contiguous(), "attn: strides");
+    TORCH_CHECK(cu_seqlens.scalar_type() == at::kInt && cu_seqlens.is_contiguous(), "attn: cu_seqlens int32");
+    c10::cuda::CUDAGuard guard(q.device());
+    b200::AttnDesc d;
+    d.q = q.data_ptr(); d.k = k.data_ptr(); d.v = v.data_ptr(); d.o = out.data_ptr(); d.lse = lse.data_ptr<float>();
+    d.T = q.size(0); d.H = q.size(1); d.Hkv = k.size(1); d.D = q.size(2);
+    d.q_stride_t = q.stride(0); d.q_stride_h = q.stride(1);
+    d.k_stride_t = k.stride(0); d.k_stride_h = k.stride(1);
+    d.v_stride_t = v.stride(0); d.v_stride_h = v.stride(1);
+    d.cu_seqlens = cu_seqlens.data_ptr<int>(); d.num_seqs = cu_seqlens.numel() - 1; d.max_seqlen = max_seqlen;
+    d.scale = (float)scale; d.causal = causal;
+    CHECK_RC(b200::attn_fwd(d, cur_stream()), "b200::attn_fwd");
+}
+
+void attn_bwd(const Tensor& dout, const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& out, const Tensor& lse,
+              Tensor& dq, Tensor& dk, Tensor& dv, Tensor& delta, Tensor& dq_acc, const Tensor& cu_seqlens,
+              int64_t max_seqlen, double scale, bool causal) {
+    CHECK_BF16(q); CHECK_BF16(k); CHECK_BF16(v); CHECK_BF16(dout);
+    c10::cuda::CUDAGuard guard(q.device());
+    b200::AttnBwdDesc d;
+    d.f.q = q.data_ptr(); d.f.k = k.data_ptr(); d.f.v = v.data_ptr(); d.f.o = const_cast<void*>(out.data_ptr());
+    d.f.lse = const_cast<float*>(lse.data_ptr<float>());
+    d.f.T = q.size(0); d.f.H = q.size(1); d.f.Hkv = k.size(1); d.f.D = q.size(2);
+    d.f.q_stride_t = q.stride(0); d.f.q_stride_h = q.stride(1);
+    d.f.k_stride_t = k.stride(0); d.f.k_stride_h = k.stride(1);
+    d.f.v_stride_t = v.stride(0); d.f.v_stride_h = v.stride(1);
+    d.f.cu_seqlens = cu_seqlens.data_ptr<int>(); d.f.num_seqs = cu_seqlens.numel() - 1; d.f.max_seqlen = max_seqlen;
+    d.f.scale = (float)scale; d.f.causal = causal;
+    TORCH_CHECK(dout.is_contiguous() && out.is_contiguous(), "attn_bwd: dout/out contiguous");
+    TORCH_CHECK(dq.stride(2) == 1 && dk.stride(2) == 1 && dv.stride(2) == 1, "attn_bwd: grads last dim contiguous");
+    d.dout = dout.data_ptr();
+    d.dq = dq.data_ptr(); d.dq_stride_t = dq.stride(0); d.dq_stride_h = dq.stride(1);
+    d.dk = dk.data_ptr(); d.dk_stride_t = dk.stride(0); d.dk_stride_h = dk.stride(1);
+    d.dv = dv.data_ptr(); d.dv_stride_t = dv.stride(0); d.dv_stride_h = dv.stride(1);
+    d.delta = delta.data_ptr<float>();
+    d.dq_acc = dq_acc.data_ptr<float>();
+    CHECK_RC(b200::attn_bwd(d, cur_stream()), "b200::attn_bwd");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// peer-memory communication kernels (pointers come from the symmetric heap, see internevo_b200/parallel/symm.py)
+// ---------------------------------------------------------------------------------------------------------------
+void symm_barrier(int64_t flags_ptrs, int64_t rank, int64_t world, int64_t epoch) {
+    CHECK_RC(b200::symm_barrier(reinterpret_cast<uint32_t* const*>(flags_ptrs), rank, world, (uint32_t)epoch, cur_stream()),
+             "b200::symm_barrier");
+}
+
+void reduce_scatter_adam(int64_t grad_ptrs, int64_t param_ptrs, int64_t flags_ptrs, int64_t rank, int64_t world,
+                         int64_t epoch, int64_t shard_off, int64_t shard_n, Tensor& p, Tensor& m, Tensor& v,
+                         const Tensor& scalars, double lr, double beta1, double beta2, double eps, double wd, double bc1,
+                         double bc2, double grad_div, int64_t phase) {
+    c10::cuda::CUDAGuard guard(p.device());
+    b200::RsAdamDesc d;
+    d.grad_ptrs = reinterpret_cast<void* const*>(grad_ptrs);
+    d.param_ptrs = reinterpret_cast<void* const*>(param_ptrs);
+    d.flags_ptrs = reinterpret_cast<uint32_t* const*>(flags_ptrs);
+    d.rank = rank; d.world = world; d.epoch = (uint32_t)epoch;
+    d.shard_off = shard_off; d.shard_n = shard_n;
+    d.p = p.data_ptr<float>(); d.m = m.data_ptr<float>(); d.v = v.data_ptr<float>();
+    d.scalars = scalars.data_ptr<float>();
+    d.lr = lr; d.beta1 = beta1; d.beta2 = beta2; d.eps = eps; d.wd = wd; d.bc1 = bc1; d.bc2 = bc2; d.grad_div = grad_div;
+    d.phase = phase;
+    CHECK_RC(b200::reduce_scatter_adam(d, cur_stream()), "b200::reduce_scatter_adam");
+}
+
+void gemm_rs(const Tensor& a, const Tensor& b, int64_t out_ptrs, int64_t flags_ptrs, int64_t rank, int64_t world,
+             int64_t epoch, bool b_mn, Tensor& scratch, Tensor& out_local, int64_t mode) {
+    CHECK_BF16(a); CHECK_BF16(b);
+    c10::cuda::CUDAGuard guard(a.device());
+    b200::GemmCommDesc d;
+    d.g.M = a.size(0); d.g.K = a.size(1); d.g.N = b_mn ? b.size(1) : b.size(0);
+    d.g.A = a.data_ptr(); d.g.lda = a.stride(0); d.g.a_mn_major = 0;
+    d.g.B = b.data_ptr(); d.g.ldb = b.stride(0); d.g.b_mn_major = b_mn;
+    d.g.D = scratch.data_ptr(); d.g.ldd = scratch.stride(0);
+    d.peer_ptrs = reinterpret_cast<void* const*>(out_ptrs);
+    d.flags_ptrs = reinterpret_cast<uint32_t* const*>(flags_ptrs);
+    d.rank = rank; d.world = world; d.epoch = (uint32_t)epoch; d.mode = mode;
+    d.out_local = out_local.data_ptr(); d.ld_out = out_local.stride(0);
+    CHECK_RC(b200::gemm_reduce_scatter(d, cur_stream()), "b200::gemm_rs");
+}
+
+void ag_gemm(int64_t a_ptrs, int64_t flags_ptrs, int64_t rank, int64_t world, int64_t epoch, int64_t m_local, int64_t k,
+             int64_t lda, const Tensor& b, bool b_mn, Tensor& out, int64_t flags, const optional<Tensor>& h,
+             const optional<Tensor>& gathered) {
+    CHECK_BF16(b);
+    c10::cuda::CUDAGuard guard(b.device());
+    b200::GemmCommDesc d;
+    d.g.M = m_local * world; d.g.K = k; d.g.N = b_mn ? b.size(1) : b.size(0);
+    d.g.lda = lda; d.g.a_mn_major = 0;
+    d.g.B = b.data_ptr(); d.g.ldb = b.stride(0); d.g.b_mn_major = b_mn;
+    d.g.D = out.data_ptr(); d.g.ldd = out.stride(0);
+    d.g.flags = flags;
+    if (h.has_value()) { d.g.H = h->data_ptr(); d.g.ldh = h->stride(0); }
+    d.peer_ptrs = reinterpret_cast<void* const*>(a_ptrs);
+    d.flags_ptrs = reinterpret_cast<uint32_t* const*>(flags_ptrs);
+    d.rank = rank; d.world = world; d.epoch = (uint32_t)epoch; d.m_local = m_local;
+    d.out_local = gathered.has_value() ? gathered->data_ptr() : nullptr;
+    d.ld_out = gathered.has_value() ? gathered->stride(0) : 0;
+    CHECK_RC(b200::allgather_gemm(d, cur_stream()), "b200::ag_gemm");
+}
+
+}  // namespace
+
+TORCH_LIBRARY(b200, m) {
+    m.def("gemm(Tensor a, Tensor b, Tensor(a!) out, bool a_mn, bool b_mn, Tensor? bias, int flags, Tensor? h, int force_bn, int max_ctas) -> ()", &gemm);
+    m.def("rmsnorm_fwd(Tensor x, Tensor? res_in, Tensor w, Tensor(a!) y, Tensor? res_out, Tensor? rstd, float eps) -> ()", &rmsnorm_fwd);
+    m.def("rmsnorm_bwd_blocks(int rows) -> int", &rmsnorm_bwd_blocks);
+    m.def("rmsnorm_bwd(Tensor dy, Tensor res, Tensor w, Tensor rstd, Tensor? dres, Tensor(a!) dx, Tensor(b!) dw_partial, Tensor(c!) dw, bool accumulate) -> ()", &rmsnorm_bwd);
+    m.def("rope(Tensor(a!) x, Tensor? pos, Tensor cos_t, Tensor sin_t, int group, int rot_per_group, bool conj, bool interleaved) -> ()", &rope);
+    m.def("swiglu_fwd(Tensor gu, Tensor(a!) h) -> ()", &swiglu_fwd);
+    m.def("swiglu_bwd(Tensor dh, Tensor gu, Tensor(a!) dgu) -> ()", &swiglu_bwd);
+    m.def("ce_fwd(Tensor logits, Tensor labels, int vocab_start, Tensor(a!) out_max, Tensor(b!) out_sum, Tensor(c!) out_sumx, Tensor(d!) out_tgt) -> ()", &ce_fwd);
+    m.def("ce_bwd(Tensor(a!) logits, Tensor labels, Tensor lse, Tensor gscale, int vocab_start, float smoothing, int total_classes, int ignore_index) -> ()", &ce_bwd);
+    m.def("adamw(Tensor(a!) p, Tensor(b!) m, Tensor(c!) v, Tensor g, Tensor? p_lp, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2, Tensor? scalars) -> ()", &adamw);
+    m.def("sumsq(Tensor g, Tensor(a!) out) -> ()", &sumsq);
+    m.def("clip_scalars(Tensor sumsq_in, Tensor(a!) scalars, float loss_scale, float clip) -> ()", &clip_scalars);
+    m.def("attn_fwd(Tensor q, Tensor k, Tensor v, Tensor(a!) out, Tensor(b!) lse, Tensor cu_seqlens, int max_seqlen, float scale, bool causal) -> ()", &attn_fwd);
+    m.def("attn_bwd(Tensor dout, Tensor q, Tensor k, Tensor v, Tensor out, Tensor lse, Tensor(a!) dq, Tensor(b!) dk, Tensor(c!) dv, Tensor(d!) delta, Tensor(e!) dq_acc, Tensor cu_seqlens, int max_seqlen, float scale, bool causal) -> ()", &attn_bwd);
+    m.def("symm_barrier(int flags_ptrs, int rank, int world, int epoch) -> ()", &symm_barrier);
+    m.def("reduce_scatter_adam(int grad_ptrs, int param_ptrs, int flags_ptrs, int rank, int world, int epoch, int shard_off, int shard_n, Tensor(a!) p, Tensor(b!) m, Tensor(c!) v, Tensor scalars, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2, float grad_div, int phase) -> ()", &reduce_scatter_adam);
+    m.def("gemm_rs(Tensor a, Tensor b, int out_ptrs, int flags_ptrs, int rank, int world, int epoch, bool b_mn, Tensor(a!) scratch, Tensor(b!) out_local, int mode) -> ()", &gemm_rs);
+    m.def("ag_gemm(int a_ptrs, int flags_ptrs, int rank, int world, int epoch, int m_local, int k, int lda, Tensor b, bool b_mn, Tensor(a!) out, int flags, Tensor? h, Tensor? gathered) -> ()", &ag_gemm);
+}

@@ -1,0 +1,42 @@
+// Host API of the peer-memory (NVLink / NVSwitch) kernels: barrier over symmetric flags, fused
+// reduce-scatter + AdamW + all-gather for Hybrid-ZeRO, GEMM->reduce-scatter and all-gather->GEMM for tensor parallel.
+// Pointer tables (`*_ptrs`) are device arrays of `world` peer-mapped base pointers (see parallel/symm.py).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gemm_sm100.h"
+
+namespace b200 {
+
+int symm_barrier(uint32_t* const* flags_ptrs, int rank, int world, uint32_t epoch, cudaStream_t s);
+
+struct RsAdamDesc {
+    void* const* grad_ptrs = nullptr;    // per-rank bf16 gradient arena (same layout on every rank)
+    void* const* param_ptrs = nullptr;   // per-rank bf16 parameter arena
+    uint32_t* const* flags_ptrs = nullptr;
+    int rank = 0, world = 1;
+    uint32_t epoch = 0;
+    int64_t shard_off = 0, shard_n = 0;  // this rank's owned slice [shard_off, shard_off + shard_n) of the arena
+    float *p = nullptr, *m = nullptr, *v = nullptr;  // fp32 master / moments of the owned slice
+    float* scalars = nullptr;  // [0] grad multiplier, [1] overflow flag, [2] norm, [3] local sum of squares
+    double lr = 0, beta1 = 0.9, beta2 = 0.95, eps = 1e-8, wd = 0, bc1 = 1, bc2 = 1, grad_div = 1;
+    int phase = 0;  // 0: reduce owned slice (peer loads) -> fp32 grad in `m`-sized scratch + sumsq ; 1: adam + multicast params
+};
+int reduce_scatter_adam(const RsAdamDesc& d, cudaStream_t s);
+
+struct GemmCommDesc {
+    GemmDesc g;
+    void* const* peer_ptrs = nullptr;
+    uint32_t* const* flags_ptrs = nullptr;
+    int rank = 0, world = 1;
+    uint32_t epoch = 0;
+    int mode = 0;          // gemm_rs: 0 = reduce-scatter rows, 1 = all-reduce
+    int64_t m_local = 0;   // ag_gemm: rows contributed by each rank
+    void* out_local = nullptr;
+    int64_t ld_out = 0;
+};
+int gemm_reduce_scatter(const GemmCommDesc& d, cudaStream_t s);
+int allgather_gemm(const GemmCommDesc& d, cudaStream_t s);
+
+}  // namespace b200

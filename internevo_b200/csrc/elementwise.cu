@@ -1,0 +1,564 @@
+// Bandwidth-bound sm_100a kernels: fused residual-add + RMSNorm (fwd/bwd), in-place RoPE on the packed InternLM2 qkv
+// layout, SwiGLU (fwd/bwd, interleaved gate/up), vocab-parallel cross-entropy (online LSE fwd, in-place bwd),
+// fused AdamW (unscale + clip + update + bf16 cast-back) and flat L2-norm.  All use 128-bit accesses and fp32 math.
+//
+// Reference kernels replaced: apex cuApplyRMSNorm / cuComputeGradInput (third_party/apex/csrc/layer_norm_cuda_kernel.cu),
+// rotary_emb.apply_rotary (third_party/flash-attention/csrc/rotary/rotary_cuda.cu), the jit-scripted Silu
+// (internlm/model/utils.py:684-688), xentropy_cuda_lib (third_party/flash-attention/csrc/xentropy/xentropy_kernel.cu),
+// ATen fused AdamW + the flatten/cast/unscale glue (internlm/solver/optimizer/hybrid_zero_optim.py:740-797) and
+// apex multi_tensor_l2norm.
+#include "elementwise.h"
+
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "sm100_ptx.cuh"
+
+namespace b200 {
+
+// ----------------------------------------------------------------------------------------------------------------
+// helpers
+// ----------------------------------------------------------------------------------------------------------------
+B200_DEVICE float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+B200_DEVICE float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+template <int THREADS>
+B200_DEVICE float block_sum(float v, float* red) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    float t = (l < THREADS / 32) ? red[l] : 0.f;
+    return warp_sum(t);
+}
+template <int THREADS>
+B200_DEVICE float block_max(float v, float* red) {
+    v = warp_max(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    float t = (l < THREADS / 32) ? red[l] : -INFINITY;
+    return warp_max(t);
+}
+B200_DEVICE void unpack8(const uint4& u, float (&f)[8]) {
+    float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+B200_DEVICE uint4 pack8(const float (&f)[8]) {
+    uint4 u;
+    u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]); u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+    return u;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// RMSNorm: one CTA (256 threads) per row, row cached in registers (H <= 256*8*MAXV)
+// ----------------------------------------------------------------------------------------------------------------
+static constexpr int RN_THREADS = 256;
+static constexpr int RN_MAXV = 4;  // up to 8192 columns
+
+// res_out = x (+ res_in);  y = res_out * rstd * w
+__global__ void __launch_bounds__(RN_THREADS) rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                 const __nv_bfloat16* __restrict__ res_in,
+                                                                 const __nv_bfloat16* __restrict__ w,
+                                                                 __nv_bfloat16* __restrict__ y,
+                                                                 __nv_bfloat16* __restrict__ res_out,
+                                                                 float* __restrict__ rstd_out, int rows, int H,
+                                                                 float eps) {
+    __shared__ float red[32];
+    const int nvec = H / 8;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const uint4* xr = reinterpret_cast<const uint4*>(x + (int64_t)row * H);
+        const uint4* rr = res_in ? reinterpret_cast<const uint4*>(res_in + (int64_t)row * H) : nullptr;
+        float v[RN_MAXV][8];
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < RN_MAXV; ++i) {
+            const int idx = threadIdx.x + i * RN_THREADS;
+            if (idx < nvec) {
+                unpack8(xr[idx], v[i]);
+                if (rr) {
+                    float r[8];
+                    unpack8(rr[idx], r);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[i][j] += r[j];
+                }
+                if (res_out) {
+                    uint4 o = pack8(v[i]);
+                    reinterpret_cast<uint4*>(res_out + (int64_t)row * H)[idx] = o;
+                    unpack8(o, v[i]);  // normalise the bf16-rounded residual, as the unfused composition would
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ss += v[i][j] * v[i][j];
+            }
+        }
+        ss = block_sum<RN_THREADS>(ss, red);
+        const float rstd = rsqrtf(ss / H + eps);
+        if (threadIdx.x == 0 && rstd_out) rstd_out[row] = rstd;
+#pragma unroll
+        for (int i = 0; i < RN_MAXV; ++i) {
+            const int idx = threadIdx.x + i * RN_THREADS;
+            if (idx < nvec) {
+                float wv[8], o[8];
+                unpack8(reinterpret_cast<const uint4*>(w)[idx], wv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = v[i][j] * rstd * wv[j];
+                reinterpret_cast<uint4*>(y + (int64_t)row * H)[idx] = pack8(o);
+            }
+        }
+    }
+}
+
+// dx = rstd * (dy*w - xhat * mean(dy*w*xhat)) (+ dres);  dw_partial[block] += dy * xhat
+__global__ void __launch_bounds__(RN_THREADS) rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                                 const __nv_bfloat16* __restrict__ res,
+                                                                 const __nv_bfloat16* __restrict__ w,
+                                                                 const float* __restrict__ rstd_in,
+                                                                 const __nv_bfloat16* __restrict__ dres,
+                                                                 __nv_bfloat16* __restrict__ dx,
+                                                                 float* __restrict__ dw_partial, int rows, int H) {
+    __shared__ float red[32];
+    const int nvec = H / 8;
+    float dwacc[RN_MAXV][8];
+    float wv[RN_MAXV][8];
+#pragma unroll
+    for (int i = 0; i < RN_MAXV; ++i) {
+        const int idx = threadIdx.x + i * RN_THREADS;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dwacc[i][j] = 0.f;
+        if (idx < nvec) unpack8(reinterpret_cast<const uint4*>(w)[idx], wv[i]);
+    }
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const float rstd = rstd_in[row];
+        float g[RN_MAXV][8], xh[RN_MAXV][8];
+        float dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < RN_MAXV; ++i) {
+            const int idx = threadIdx.x + i * RN_THREADS;
+            if (idx < nvec) {
+                unpack8(reinterpret_cast<const uint4*>(dy + (int64_t)row * H)[idx], g[i]);
+                unpack8(reinterpret_cast<const uint4*>(res + (int64_t)row * H)[idx], xh[i]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    xh[i][j] *= rstd;
+                    dwacc[i][j] += g[i][j] * xh[i][j];
+                    g[i][j] *= wv[i][j];
+                    dot += g[i][j] * xh[i][j];
+                }
+            }
+        }
+        dot = block_sum<RN_THREADS>(dot, red) / H;
+#pragma unroll
+        for (int i = 0; i < RN_MAXV; ++i) {
+            const int idx = threadIdx.x + i * RN_THREADS;
+            if (idx < nvec) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - xh[i][j] * dot);
+                if (dres) {
+                    float r[8];
+                    unpack8(reinterpret_cast<const uint4*>(dres + (int64_t)row * H)[idx], r);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] += r[j];
+                }
+                reinterpret_cast<uint4*>(dx + (int64_t)row * H)[idx] = pack8(o);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < RN_MAXV; ++i) {
+        const int idx = threadIdx.x + i * RN_THREADS;
+        if (idx < nvec) {
+            float* p = dw_partial + (int64_t)blockIdx.x * H + idx * 8;
+            reinterpret_cast<float4*>(p)[0] = make_float4(dwacc[i][0], dwacc[i][1], dwacc[i][2], dwacc[i][3]);
+            reinterpret_cast<float4*>(p)[1] = make_float4(dwacc[i][4], dwacc[i][5], dwacc[i][6], dwacc[i][7]);
+        }
+    }
+}
+
+// dw[c] (+)= sum_b partial[b, c]
+__global__ void colsum_kernel(const float* __restrict__ partial, float* __restrict__ out_f32,
+                              __nv_bfloat16* __restrict__ out_bf16, int nblocks, int H, int accumulate) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= H) return;
+    float s = 0.f;
+    for (int b = 0; b < nblocks; ++b) s += partial[(int64_t)b * H + c];
+    if (out_f32) out_f32[c] = accumulate ? out_f32[c] + s : s;
+    if (out_bf16) out_bf16[c] = __float2bfloat16_rn(accumulate ? __bfloat162float(out_bf16[c]) + s : s);
+}
+
+int rmsnorm_fwd(const void* x, const void* res_in, const void* w, void* y, void* res_out, float* rstd, int rows, int H,
+                float eps, cudaStream_t s) {
+    if (H % 8 != 0 || H > RN_THREADS * 8 * RN_MAXV) return -1;
+    const int grid = rows < 148 * 8 ? rows : 148 * 8;
+    rmsnorm_fwd_kernel<<<grid, RN_THREADS, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res_in,
+                                                   (const __nv_bfloat16*)w, (__nv_bfloat16*)y, (__nv_bfloat16*)res_out,
+                                                   rstd, rows, H, eps);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int rmsnorm_bwd_blocks(int rows) { return rows < 148 * 4 ? rows : 148 * 4; }
+
+int rmsnorm_bwd(const void* dy, const void* res, const void* w, const float* rstd, const void* dres, void* dx,
+                float* dw_partial, float* dw_f32, void* dw_bf16, int accumulate, int rows, int H, cudaStream_t s) {
+    if (H % 8 != 0 || H > RN_THREADS * 8 * RN_MAXV) return -1;
+    const int grid = rmsnorm_bwd_blocks(rows);
+    rmsnorm_bwd_kernel<<<grid, RN_THREADS, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)res,
+                                                   (const __nv_bfloat16*)w, rstd, (const __nv_bfloat16*)dres,
+                                                   (__nv_bfloat16*)dx, dw_partial, rows, H);
+    colsum_kernel<<<(H + 255) / 256, 256, 0, s>>>(dw_partial, dw_f32, (__nv_bfloat16*)dw_bf16, grid, H, accumulate);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// RoPE, in place, on x viewed as [T, nheads_total, D] where only heads with (head % group) < rot_per_group rotate
+// (InternLM2 packed wqkv "(h gs d)": group = q_per_kv + 2, rot_per_group = q_per_kv + 1 -> q and k rotate, v not).
+// Non-interleaved (GPT-NeoX halves) or interleaved pairs.  cos/sin tables are [max_pos, D/2] fp32.
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void rope_kernel(__nv_bfloat16* __restrict__ x, const int* __restrict__ pos, const float* __restrict__ cos_t,
+                            const float* __restrict__ sin_t, int T, int heads, int D, int64_t stride_t, int group,
+                            int rot_per_group, float sign, int interleaved) {
+    // one warp per (token, head); each lane handles D/64 chunks of (4 + 4) elements
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= (int64_t)T * heads) return;
+    const int t = gw / heads, h = gw % heads;
+    if ((h % group) >= rot_per_group) return;
+    const int p = pos ? pos[t] : t;
+    __nv_bfloat16* xp = x + (int64_t)t * stride_t + (int64_t)h * D;
+    const float* c = cos_t + (int64_t)p * (D / 2);
+    const float* s = sin_t + (int64_t)p * (D / 2);
+    const int half = D / 2;
+    if (!interleaved) {
+        for (int i = lane * 4; i < half; i += 128) {
+            uint2 a = *reinterpret_cast<uint2*>(xp + i);
+            uint2 b = *reinterpret_cast<uint2*>(xp + half + i);
+            float4 cc = *reinterpret_cast<const float4*>(c + i);
+            float4 ss = *reinterpret_cast<const float4*>(s + i);
+            float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), b0 = unpack_bf16(b.x), b1 = unpack_bf16(b.y);
+            ss.x *= sign; ss.y *= sign; ss.z *= sign; ss.w *= sign;
+            uint2 oa, ob;
+            oa.x = pack_bf16(a0.x * cc.x - b0.x * ss.x, a0.y * cc.y - b0.y * ss.y);
+            oa.y = pack_bf16(a1.x * cc.z - b1.x * ss.z, a1.y * cc.w - b1.y * ss.w);
+            ob.x = pack_bf16(a0.x * ss.x + b0.x * cc.x, a0.y * ss.y + b0.y * cc.y);
+            ob.y = pack_bf16(a1.x * ss.z + b1.x * cc.z, a1.y * ss.w + b1.y * cc.w);
+            *reinterpret_cast<uint2*>(xp + i) = oa;
+            *reinterpret_cast<uint2*>(xp + half + i) = ob;
+        }
+    } else {
+        for (int i = lane * 4; i < half; i += 128) {  // 4 pairs = 8 elements
+            uint4 a = *reinterpret_cast<uint4*>(xp + 2 * i);
+            float4 cc = *reinterpret_cast<const float4*>(c + i);
+            float4 ss = *reinterpret_cast<const float4*>(s + i);
+            ss.x *= sign; ss.y *= sign; ss.z *= sign; ss.w *= sign;
+            float2 p0 = unpack_bf16(a.x), p1 = unpack_bf16(a.y), p2 = unpack_bf16(a.z), p3 = unpack_bf16(a.w);
+            uint4 o;
+            o.x = pack_bf16(p0.x * cc.x - p0.y * ss.x, p0.x * ss.x + p0.y * cc.x);
+            o.y = pack_bf16(p1.x * cc.y - p1.y * ss.y, p1.x * ss.y + p1.y * cc.y);
+            o.z = pack_bf16(p2.x * cc.z - p2.y * ss.z, p2.x * ss.z + p2.y * cc.z);
+            o.w = pack_bf16(p3.x * cc.w - p3.y * ss.w, p3.x * ss.w + p3.y * cc.w);
+            *reinterpret_cast<uint4*>(xp + 2 * i) = o;
+        }
+    }
+}
+
+int rope_inplace(void* x, const int* pos, const float* cos_t, const float* sin_t, int T, int heads, int D,
+                 int64_t stride_t, int group, int rot_per_group, int conj, int interleaved, cudaStream_t s) {
+    if (D % 8 != 0) return -1;
+    const int64_t warps = (int64_t)T * heads;
+    const int threads = 256;
+    const int64_t blocks = (warps * 32 + threads - 1) / threads;
+    rope_kernel<<<(unsigned)blocks, threads, 0, s>>>((__nv_bfloat16*)x, pos, cos_t, sin_t, T, heads, D, stride_t, group,
+                                                     rot_per_group, conj ? -1.f : 1.f, interleaved);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// SwiGLU on interleaved (gate, up) columns: gu [rows, 2F] -> h [rows, F];  bwd: dgu from dh, gu
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void swiglu_fwd_kernel(const uint4* __restrict__ gu, uint2* __restrict__ h, int64_t nvec) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        float f[8];
+        unpack8(gu[i], f);
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = f[2 * j] / (1.f + __expf(-f[2 * j])) * f[2 * j + 1];
+        uint2 r;
+        r.x = pack_bf16(o[0], o[1]); r.y = pack_bf16(o[2], o[3]);
+        h[i] = r;
+    }
+}
+__global__ void swiglu_bwd_kernel(const uint2* __restrict__ dh, const uint4* __restrict__ gu, uint4* __restrict__ dgu,
+                                  int64_t nvec) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        float f[8], o[8];
+        unpack8(gu[i], f);
+        uint2 d = dh[i];
+        float2 d0 = unpack_bf16(d.x), d1 = unpack_bf16(d.y);
+        const float dv[4] = {d0.x, d0.y, d1.x, d1.y};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float g = f[2 * j], u = f[2 * j + 1];
+            const float sg = 1.f / (1.f + __expf(-g));
+            o[2 * j] = dv[j] * u * sg * (1.f + g * (1.f - sg));
+            o[2 * j + 1] = dv[j] * g * sg;
+        }
+        dgu[i] = pack8(o);
+    }
+}
+int swiglu_fwd(const void* gu, void* h, int64_t rows, int64_t F, cudaStream_t s) {
+    if (F % 4 != 0) return -1;
+    const int64_t nvec = rows * F / 4;
+    const int blocks = (int)((nvec + 255) / 256 < 148 * 16 ? (nvec + 255) / 256 : 148 * 16);
+    swiglu_fwd_kernel<<<blocks, 256, 0, s>>>((const uint4*)gu, (uint2*)h, nvec);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+int swiglu_bwd(const void* dh, const void* gu, void* dgu, int64_t rows, int64_t F, cudaStream_t s) {
+    if (F % 4 != 0) return -1;
+    const int64_t nvec = rows * F / 4;
+    const int blocks = (int)((nvec + 255) / 256 < 148 * 16 ? (nvec + 255) / 256 : 148 * 16);
+    swiglu_bwd_kernel<<<blocks, 256, 0, s>>>((const uint2*)dh, (const uint4*)gu, (uint4*)dgu, nvec);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Cross entropy over (a vocab shard of) bf16 logits [rows, V], row stride ld.
+//   fwd: per row online (max, sum exp(x - max), sum x, logit[target]) in ONE pass
+//   bwd: logits <- gscale[row] * (exp(x - lse) * (1 - 0) - (1-eps)*onehot - eps/Vtotal)   in place
+// ----------------------------------------------------------------------------------------------------------------
+static constexpr int CE_THREADS = 512;
+
+__global__ void __launch_bounds__(CE_THREADS) ce_fwd_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld,
+                                                            const int64_t* __restrict__ labels, int V, int vocab_start,
+                                                            float* __restrict__ out_max, float* __restrict__ out_sum,
+                                                            float* __restrict__ out_sumx, float* __restrict__ out_tgt) {
+    __shared__ float red[32];
+    const int row = blockIdx.x;
+    const __nv_bfloat16* x = logits + (int64_t)row * ld;
+    const int nvec = V / 8;
+    float m = -INFINITY, s = 0.f, sx = 0.f;
+    for (int i = threadIdx.x; i < nvec; i += CE_THREADS) {
+        float f[8];
+        unpack8(ld_nc_v4(x + i * 8), f);
+        float lm = f[0];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) lm = fmaxf(lm, f[j]);
+        const float nm = fmaxf(m, lm);
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc += __expf(f[j] - nm); sx += f[j]; }
+        s = s * __expf(m - nm) + acc;
+        m = nm;
+    }
+    for (int i = nvec * 8 + threadIdx.x; i < V; i += CE_THREADS) {  // tail
+        const float f = __bfloat162float(x[i]);
+        const float nm = fmaxf(m, f);
+        s = s * __expf(m - nm) + __expf(f - nm);
+        m = nm;
+        sx += f;
+    }
+    const float gm = block_max<CE_THREADS>(m, red);
+    s = (m == -INFINITY) ? 0.f : s * __expf(m - gm);
+    s = block_sum<CE_THREADS>(s, red);
+    sx = block_sum<CE_THREADS>(sx, red);
+    if (threadIdx.x == 0) {
+        out_max[row] = gm;
+        out_sum[row] = s;
+        out_sumx[row] = sx;
+        const int64_t t = labels[row] - vocab_start;
+        out_tgt[row] = (t >= 0 && t < V) ? __bfloat162float(x[t]) : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(CE_THREADS) ce_bwd_kernel(__nv_bfloat16* __restrict__ logits, int64_t ld,
+                                                            const int64_t* __restrict__ labels,
+                                                            const float* __restrict__ lse,
+                                                            const float* __restrict__ gscale, int V, int vocab_start,
+                                                            float smoothing, int total_classes, int ignore_index) {
+    const int row = blockIdx.x;
+    __nv_bfloat16* x = logits + (int64_t)row * ld;
+    const int64_t label = labels[row];
+    const float g = (label == ignore_index) ? 0.f : gscale[row];
+    const float l = lse[row];
+    const int64_t t = label - vocab_start;
+    const float sm = smoothing / total_classes;
+    const int nvec = V / 8;
+    for (int i = threadIdx.x; i < nvec; i += CE_THREADS) {
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(x + i * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float p = __expf(f[j] - l) - sm;
+            if (i * 8 + j == t) p -= (1.f - smoothing);
+            f[j] = g * p;
+        }
+        *reinterpret_cast<uint4*>(x + i * 8) = pack8(f);
+    }
+    for (int i = nvec * 8 + threadIdx.x; i < V; i += CE_THREADS) {
+        float p = __expf(__bfloat162float(x[i]) - l) - sm;
+        if (i == t) p -= (1.f - smoothing);
+        x[i] = __float2bfloat16_rn(g * p);
+    }
+}
+
+int ce_fwd(const void* logits, int64_t ld, const int64_t* labels, int rows, int V, int vocab_start, float* out_max,
+           float* out_sum, float* out_sumx, float* out_tgt, cudaStream_t s) {
+    if (ld % 8 != 0) return -1;
+    ce_fwd_kernel<<<rows, CE_THREADS, 0, s>>>((const __nv_bfloat16*)logits, ld, labels, V, vocab_start, out_max, out_sum,
+                                              out_sumx, out_tgt);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+int ce_bwd(void* logits, int64_t ld, const int64_t* labels, const float* lse, const float* gscale, int rows, int V,
+           int vocab_start, float smoothing, int total_classes, int ignore_index, cudaStream_t s) {
+    if (ld % 8 != 0) return -1;
+    ce_bwd_kernel<<<rows, CE_THREADS, 0, s>>>((__nv_bfloat16*)logits, ld, labels, lse, gscale, V, vocab_start, smoothing,
+                                              total_classes, ignore_index);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Fused AdamW on a flat shard: g (bf16 or fp32) -> unscale/clip -> m, v, p (fp32) -> bf16 copy of p.
+// `scalars` lives on the device so the step needs no host sync: [0] = combined grad multiplier (1/(loss_scale*clip)),
+// [1] = skip flag (non-zero => overflow, leave everything untouched).
+// ----------------------------------------------------------------------------------------------------------------
+template <typename G>
+__global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                             const G* __restrict__ g, __nv_bfloat16* __restrict__ p_lp, int64_t n, float lr, float beta1,
+                             float beta2, float eps, float wd, float bc1, float bc2, const float* __restrict__ scalars) {
+    const float mult = scalars ? scalars[0] : 1.f;
+    if (scalars && scalars[1] != 0.f) return;
+    const int64_t n4 = n / 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 pv = reinterpret_cast<float4*>(p)[i];
+        float4 mv = reinterpret_cast<float4*>(m)[i];
+        float4 vv = reinterpret_cast<float4*>(v)[i];
+        float gv[4];
+        if constexpr (sizeof(G) == 2) {
+            uint2 u = reinterpret_cast<const uint2*>(g)[i];
+            float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+            gv[0] = a.x; gv[1] = a.y; gv[2] = b.x; gv[3] = b.y;
+        } else {
+            float4 u = reinterpret_cast<const float4*>(g)[i];
+            gv[0] = u.x; gv[1] = u.y; gv[2] = u.z; gv[3] = u.w;
+        }
+        float* pp = reinterpret_cast<float*>(&pv);
+        float* mp = reinterpret_cast<float*>(&mv);
+        float* vp = reinterpret_cast<float*>(&vv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float gg = gv[j] * mult;
+            mp[j] = beta1 * mp[j] + (1.f - beta1) * gg;
+            vp[j] = beta2 * vp[j] + (1.f - beta2) * gg * gg;
+            const float mh = mp[j] / bc1;
+            const float vh = vp[j] / bc2;
+            pp[j] = pp[j] * (1.f - lr * wd) - lr * mh / (sqrtf(vh) + eps);
+        }
+        reinterpret_cast<float4*>(p)[i] = pv;
+        reinterpret_cast<float4*>(m)[i] = mv;
+        reinterpret_cast<float4*>(v)[i] = vv;
+        if (p_lp) {
+            uint2 o;
+            o.x = pack_bf16(pp[0], pp[1]); o.y = pack_bf16(pp[2], pp[3]);
+            reinterpret_cast<uint2*>(p_lp)[i] = o;
+        }
+    }
+    // tail (n not a multiple of 4)
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const int64_t i = n4 * 4 + threadIdx.x;
+        float gg;
+        if constexpr (sizeof(G) == 2) gg = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(g)[i]) * mult;
+        else gg = reinterpret_cast<const float*>(g)[i] * mult;
+        const float mm = beta1 * m[i] + (1.f - beta1) * gg;
+        const float vv = beta2 * v[i] + (1.f - beta2) * gg * gg;
+        m[i] = mm; v[i] = vv;
+        const float np = p[i] * (1.f - lr * wd) - lr * (mm / bc1) / (sqrtf(vv / bc2) + eps);
+        p[i] = np;
+        if (p_lp) p_lp[i] = __float2bfloat16_rn(np);
+    }
+}
+
+int adamw_step(float* p, float* m, float* v, const void* g, int g_is_bf16, void* p_lp, int64_t n, float lr, float beta1,
+               float beta2, float eps, float wd, float bc1, float bc2, const float* scalars, cudaStream_t s) {
+    if (n == 0) return 0;
+    const int64_t want = (n / 4 + 255) / 256;
+    const int blocks = (int)(want < 148 * 8 ? (want > 0 ? want : 1) : 148 * 8);
+    if (g_is_bf16)
+        adamw_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(p, m, v, (const __nv_bfloat16*)g, (__nv_bfloat16*)p_lp, n, lr,
+                                                           beta1, beta2, eps, wd, bc1, bc2, scalars);
+    else
+        adamw_kernel<float><<<blocks, 256, 0, s>>>(p, m, v, (const float*)g, (__nv_bfloat16*)p_lp, n, lr, beta1, beta2,
+                                                   eps, wd, bc1, bc2, scalars);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// sum of squares of a flat buffer (bf16 or fp32) accumulated into *out (atomicAdd, fp32). inf/nan propagate.
+// ----------------------------------------------------------------------------------------------------------------
+template <typename G>
+__global__ void sumsq_kernel(const G* __restrict__ g, int64_t n, float* __restrict__ out) {
+    __shared__ float red[32];
+    float acc = 0.f;
+    constexpr int VEC = 16 / sizeof(G);
+    const int64_t nv = n / VEC;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+        uint4 u = ld_nc_v4(reinterpret_cast<const uint4*>(g) + i);
+        if constexpr (sizeof(G) == 2) {
+            float f[8];
+            unpack8(u, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc += f[j] * f[j];
+        } else {
+            const float* f = reinterpret_cast<const float*>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc += f[j] * f[j];
+        }
+    }
+    if (blockIdx.x == 0) {
+        for (int64_t i = nv * VEC + threadIdx.x; i < n; i += blockDim.x) {
+            float f;
+            if constexpr (sizeof(G) == 2) f = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(g)[i]);
+            else f = reinterpret_cast<const float*>(g)[i];
+            acc += f * f;
+        }
+    }
+    acc = block_sum<256>(acc, red);
+    if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+int sumsq(const void* g, int is_bf16, int64_t n, float* out, cudaStream_t s) {
+    if (n == 0) return 0;
+    const int64_t want = (n / 8 + 255) / 256;
+    const int blocks = (int)(want < 148 * 4 ? (want > 0 ? want : 1) : 148 * 4);
+    if (is_bf16) sumsq_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)g, n, out);
+    else sumsq_kernel<float><<<blocks, 256, 0, s>>>((const float*)g, n, out);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// scalars[0] = 1 / (loss_scale * max(1, norm/clip)) ; scalars[1] = overflow flag; scalars[2] = norm (unscaled)
+__global__ void clip_scalars_kernel(const float* __restrict__ sumsq_in, float* __restrict__ scalars, float loss_scale,
+                                    float clip) {
+    const float ss = *sumsq_in;
+    const bool bad = !(ss == ss) || isinf(ss);
+    const float norm = sqrtf(ss) / loss_scale;
+    float mult = 1.f / loss_scale;
+    if (clip > 0.f) {
+        const float c = norm / clip;
+        if (c > 1.f) mult /= c;
+    }
+    scalars[0] = bad ? 0.f : mult;
+    scalars[1] = bad ? 1.f : 0.f;
+    scalars[2] = bad ? -1.f : norm;
+}
+int clip_scalars(const float* sumsq_in, float* scalars, float loss_scale, float clip, cudaStream_t s) {
+    clip_scalars_kernel<<<1, 1, 0, s>>>(sumsq_in, scalars, loss_scale, clip);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+}  // namespace b200

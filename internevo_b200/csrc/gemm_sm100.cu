@@ -1,0 +1,416 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> smem ring -> tcgen05.mma (fp32 accumulators in TMEM,
+// double-buffered) -> tcgen05.ld epilogue with fused bias / accumulate / SwiGLU / fp32-out.
+//
+//   D[M,N] (+)= A[M,K] * B[N,K]^T        (both operands may be K-major or MN-major in memory, so the same kernel
+//                                          serves forward  Y = X W^T   (A K-major, B K-major),
+//                                                 dgrad    dX = dY W   (A K-major, B MN-major),
+//                                                 wgrad    dW = dY^T X (A MN-major, B MN-major))
+//
+// This replaces the cuBLAS / cublasLt calls of the reference (F.linear + fused_dense_lib.linear_bias_wgrad,
+// reference internlm/model/utils.py:228-586) and is the building block of the fused compute+collective kernels.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue.
+#include "gemm_sm100.h"
+
+#include <cstdio>
+#include <mutex>
+#include <unordered_map>
+
+#include "sm100_ptx.cuh"
+
+namespace b200 {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B atom row
+static constexpr int UMMA_K = 16;
+static constexpr int NUM_THREADS = 192;
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct GemmKernelArgs {
+    int M, N, K;
+    void* D;
+    int64_t ldd;
+    const __nv_bfloat16* bias;
+    void* H;
+    int64_t ldh;
+    int flags;
+    int a_mn, b_mn;
+    int tiles_m, tiles_n;
+};
+
+B200_DEVICE void tile_coords(int tile, int tiles_m, int tiles_n, int& m, int& n) {
+    constexpr int GROUP_M = 8;
+    const int per_group = GROUP_M * tiles_n;
+    const int g = tile / per_group;
+    const int first_m = g * GROUP_M;
+    const int gsize = min(tiles_m - first_m, GROUP_M);
+    const int r = tile - g * per_group;
+    m = first_m + r % gsize;
+    n = r / gsize;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmKernelArgs args) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + STAGES;
+    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = args.tiles_m * args.tiles_n;
+    const int num_kb = (args.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<1>(tmem_base_smem, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int tm, tn;
+                tile_coords(tile, args.tiles_m, args.tiles_n, tm, tn);
+                const int m0 = tm * BM, n0 = tn * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
+                    uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
+                    const int k0 = kb * BK;
+                    if (!args.a_mn) {
+                        tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BM / 64; ++j)
+                            tma_load_2d(sa + j * (BK * 128), &tmap_a, &full_bar[stage], m0 + j * 64, k0);
+                    }
+                    if (!args.b_mn) {
+                        tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j)
+                            tma_load_2d(sb + j * (BK * 128), &tmap_b, &full_bar[stage], n0 + j * 64, k0);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_f16(BM, BN, args.a_mn, args.b_mn);
+            // K-major: 8-row groups are 1024 B apart, advance 32 B per UMMA_K.
+            // MN-major: 64-element column blocks are BK*128 B apart (LBO), 8-k groups 1024 B apart, advance 2048 B.
+            const uint32_t a_lbo = args.a_mn ? BK * 128 : 16, b_lbo = args.b_mn ? BK * 128 : 16;
+            const uint32_t a_kstep = args.a_mn ? (UMMA_K * 128) : (UMMA_K * 2);
+            const uint32_t b_kstep = args.b_mn ? (UMMA_K * 128) : (UMMA_K * 2);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem_a + stage * Cfg::A_BYTES);
+                    const uint32_t sb = smem_u32(smem_b + stage * Cfg::B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t da = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
+                        const uint64_t db = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
+                        umma_f16_ss<1>(d_tmem, da, db, idesc, (kb | k) != 0);
+                    }
+                    umma_commit<1>(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit<1>(&tmem_full[acc]);  // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const bool out_f32 = args.flags & GEMM_OUT_F32;
+        const bool accumulate = args.flags & GEMM_ACCUMULATE;
+        const bool swiglu = args.flags & GEMM_SWIGLU;
+        const bool no_store_d = args.flags & GEMM_SKIP_D;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int tm, tn;
+            tile_coords(tile, args.tiles_m, args.tiles_n, tm, tn);
+            const int row = tm * BM + q * 32 + lane;
+            const int n0 = tn * BN;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(taddr + c, r);
+                tmem_ld_wait();
+                const int col = n0 + c;
+                if (row < args.M && col < args.N) {
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                    const int ncols = min(32, args.N - col);  // multiple of 8 (host asserts N % 8 == 0)
+                    if (args.bias != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            if (i < ncols) {
+                                uint4 b = *reinterpret_cast<const uint4*>(args.bias + col + i);
+                                float2 b0 = unpack_bf16(b.x), b1 = unpack_bf16(b.y), b2 = unpack_bf16(b.z),
+                                       b3 = unpack_bf16(b.w);
+                                v[i] += b0.x; v[i + 1] += b0.y; v[i + 2] += b1.x; v[i + 3] += b1.y;
+                                v[i + 4] += b2.x; v[i + 5] += b2.y; v[i + 6] += b3.x; v[i + 7] += b3.y;
+                            }
+                        }
+                    }
+                    if (out_f32) {
+                        float* d = reinterpret_cast<float*>(args.D) + static_cast<int64_t>(row) * args.ldd + col;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            if (i < ncols) {
+                                float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                                if (accumulate) {
+                                    float4 p = *reinterpret_cast<float4*>(d + i);
+                                    o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+                                }
+                                *reinterpret_cast<float4*>(d + i) = o;
+                            }
+                        }
+                    } else {
+                        __nv_bfloat16* d =
+                            reinterpret_cast<__nv_bfloat16*>(args.D) + static_cast<int64_t>(row) * args.ldd + col;
+                        if (!no_store_d) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 8) {
+                                if (i < ncols) {
+                                    if (accumulate) {
+                                        uint4 p = *reinterpret_cast<uint4*>(d + i);
+                                        float2 p0 = unpack_bf16(p.x), p1 = unpack_bf16(p.y), p2 = unpack_bf16(p.z),
+                                               p3 = unpack_bf16(p.w);
+                                        v[i] += p0.x; v[i + 1] += p0.y; v[i + 2] += p1.x; v[i + 3] += p1.y;
+                                        v[i + 4] += p2.x; v[i + 5] += p2.y; v[i + 6] += p3.x; v[i + 7] += p3.y;
+                                    }
+                                    uint4 o;
+                                    o.x = pack_bf16(v[i], v[i + 1]);
+                                    o.y = pack_bf16(v[i + 2], v[i + 3]);
+                                    o.z = pack_bf16(v[i + 4], v[i + 5]);
+                                    o.w = pack_bf16(v[i + 6], v[i + 7]);
+                                    *reinterpret_cast<uint4*>(d + i) = o;
+                                }
+                            }
+                        }
+                        if (swiglu) {
+                            // columns are interleaved (gate, up) pairs; h = silu(gate) * up, computed on the
+                            // bf16-rounded values so that backward (which reads the stored gate/up) matches
+                            __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(args.H) +
+                                               static_cast<int64_t>(row) * args.ldh + (col >> 1);
+#pragma unroll
+                            for (int i = 0; i < 32; i += 16) {
+                                if (i < ncols) {
+                                    float hv[8];
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        float g = __bfloat162float(__float2bfloat16_rn(v[i + 2 * j]));
+                                        float u = __bfloat162float(__float2bfloat16_rn(v[i + 2 * j + 1]));
+                                        hv[j] = g / (1.f + __expf(-g)) * u;
+                                    }
+                                    uint4 o;
+                                    o.x = pack_bf16(hv[0], hv[1]);
+                                    o.y = pack_bf16(hv[2], hv[3]);
+                                    o.z = pack_bf16(hv[4], hv[5]);
+                                    o.w = pack_bf16(hv[6], hv[7]);
+                                    *reinterpret_cast<uint4*>(h + (i >> 1)) = o;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<1>(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || p == nullptr) {
+            fprintf(stderr, "[b200] cannot resolve cuTensorMapEncodeTiled: %s\n", cudaGetErrorString(e));
+            fn = nullptr;
+        } else {
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        }
+    });
+    return fn;
+}
+
+// 2D bf16 tensor map: `inner` contiguous elements, `outer` rows with `ld` elements stride, 128B swizzle
+// Driver-API calls need a context bound to the calling thread; autograd worker threads may not have one yet
+// (the runtime binds the primary context lazily), so make sure before encoding a tensor map.
+static void ensure_context() {
+    using CtxGetFn = CUresult (*)(CUcontext*);
+    static CtxGetFn get_ctx = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuCtxGetCurrent", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            get_ctx = reinterpret_cast<CtxGetFn>(p);
+    });
+    CUcontext ctx = nullptr;
+    if (get_ctx == nullptr || get_ctx(&ctx) != CUDA_SUCCESS || ctx == nullptr) cudaFree(0);
+}
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                      uint32_t box_inner, uint32_t box_outer) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return -1;
+    ensure_context();
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {ld_elems * 2};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "[b200] cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%llu outer=%llu ld=%llu box=%ux%u\n",
+                (int)r, ptr, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld_elems,
+                box_inner, box_outer);
+        return -2;
+    }
+    return 0;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return g_num_sms;
+}
+
+template <int BN>
+static int launch(const GemmDesc& g, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    CUtensorMap ta, tb;
+    int rc;
+    // A: logical [M, K]
+    if (!g.a_mn_major) rc = make_tmap_2d_bf16(&ta, g.A, g.K, g.M, g.lda, BK, BM);
+    else               rc = make_tmap_2d_bf16(&ta, g.A, g.M, g.K, g.lda, 64, BK);
+    if (rc) return rc;
+    // B: logical [N, K]
+    if (!g.b_mn_major) rc = make_tmap_2d_bf16(&tb, g.B, g.K, g.N, g.ldb, BK, BN);
+    else               rc = make_tmap_2d_bf16(&tb, g.B, g.N, g.K, g.ldb, 64, BK);
+    if (rc) return rc;
+
+    GemmKernelArgs a;
+    a.M = g.M; a.N = g.N; a.K = g.K;
+    a.D = g.D; a.ldd = g.ldd;
+    a.bias = reinterpret_cast<const __nv_bfloat16*>(g.bias);
+    a.H = g.H; a.ldh = g.ldh;
+    a.flags = g.flags;
+    a.a_mn = g.a_mn_major; a.b_mn = g.b_mn_major;
+    a.tiles_m = (g.M + BM - 1) / BM;
+    a.tiles_n = (g.N + BN - 1) / BN;
+    const int tiles = a.tiles_m * a.tiles_n;
+    int sms = g.max_ctas > 0 ? g.max_ctas : num_sms();
+    const int grid = tiles < sms ? tiles : sms;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) {
+            fprintf(stderr, "[b200] cudaFuncSetAttribute(smem=%d) failed: %s\n", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+            return -3;
+        }
+        attr_set = true;
+    }
+    gemm_bf16_kernel<BN><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        fprintf(stderr, "[b200] gemm launch failed: %s\n", cudaGetErrorString(e));
+        return -4;
+    }
+    return 0;
+}
+
+int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
+    if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
+    // pick the narrower tile when the 256-wide grid would leave SMs idle
+    const int tiles256 = ((g.M + BM - 1) / BM) * ((g.N + 255) / 256);
+    const bool use128 = g.force_bn == 128 || (g.force_bn == 0 && tiles256 < num_sms());
+    return use128 ? launch<128>(g, stream) : launch<256>(g, stream);
+}
+
+}  // namespace b200

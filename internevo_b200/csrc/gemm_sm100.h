@@ -1,0 +1,39 @@
+// Host API of the sm_100a tcgen05 GEMM family (no torch dependency).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+enum GemmFlags : int {
+    GEMM_OUT_F32 = 1,      // D is fp32 (default bf16)
+    GEMM_ACCUMULATE = 2,   // D += A*B^T (reads the previous D)
+    GEMM_SWIGLU = 4,       // columns of D are interleaved (gate, up); also write H[:, j] = silu(gate_j) * up_j
+    GEMM_SKIP_D = 8,       // with GEMM_SWIGLU: do not materialise D
+};
+
+struct GemmDesc {
+    int M = 0, N = 0, K = 0;
+    const void* A = nullptr;  // bf16; K-major: [M, K] with row stride lda; MN-major: [K, M] with row stride lda
+    int64_t lda = 0;
+    int a_mn_major = 0;
+    const void* B = nullptr;  // bf16; K-major: [N, K] with row stride ldb; MN-major: [K, N] with row stride ldb
+    int64_t ldb = 0;
+    int b_mn_major = 0;
+    void* D = nullptr;  // [M, N] row stride ldd, bf16 or fp32
+    int64_t ldd = 0;
+    const void* bias = nullptr;  // bf16 [N] or null
+    void* H = nullptr;           // bf16 [M, N/2] (GEMM_SWIGLU)
+    int64_t ldh = 0;
+    int flags = 0;
+    int force_bn = 0;   // 0 = auto, 128 or 256
+    int max_ctas = 0;   // 0 = all SMs; otherwise cap the persistent grid (leave SMs for a concurrent comm kernel)
+};
+
+int gemm_bf16(const GemmDesc& g, cudaStream_t stream);
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                      uint32_t box_inner, uint32_t box_outer);
+
+}  // namespace b200

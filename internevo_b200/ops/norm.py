@@ -1,0 +1,106 @@
+"""Fused residual-add + RMSNorm (forward and backward are one kernel each).
+
+Replaces apex ``MixedFusedRMSNorm`` / ``RMSNormTorch`` (reference ``internlm/model/ops/norm.py:10-46``,
+``internlm/model/utils.py:662-675``) and the separate ``dropout(h) + residual`` elementwise pass of the block
+(reference ``internlm/model/modeling_internlm2.py:697-707``).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib
+from .gemm import _bump
+
+
+def rmsnorm_ref(x: torch.Tensor, weight: torch.Tensor, eps: float) -> torch.Tensor:
+    xf = x.float()
+    y = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)
+    return (y * weight.float()).to(weight.dtype if weight.dtype != torch.float32 or x.dtype == torch.float32 else x.dtype)
+
+
+class _AddRMSNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, residual, weight, eps):
+        # returns (y, new_residual); new_residual = x + residual (or x itself when residual is None)
+        H = x.shape[-1]
+        xc = x.contiguous()
+        rows = xc.numel() // H
+        y = torch.empty_like(xc)
+        rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+        if residual is not None:
+            res_out = torch.empty_like(xc)
+            torch.ops.b200.rmsnorm_fwd(xc, residual.contiguous(), weight, y, res_out, rstd, eps)
+        else:
+            res_out = xc
+            torch.ops.b200.rmsnorm_fwd(xc, None, weight, y, None, rstd, eps)
+        _bump()
+        ctx.save_for_backward(res_out, weight, rstd)
+        ctx.has_res = residual is not None
+        return y, res_out
+
+    @staticmethod
+    def backward(ctx, dy, dres_out):
+        res, weight, rstd = ctx.saved_tensors
+        H = res.shape[-1]
+        rows = res.numel() // H
+        dy = dy.contiguous()
+        dx = torch.empty_like(res)
+        nblk = torch.ops.b200.rmsnorm_bwd_blocks(rows)
+        partial = torch.empty(nblk * H, device=res.device, dtype=torch.float32)
+        buf = getattr(weight, "grad_buf", None)
+        if buf is not None:
+            fresh = not getattr(weight, "grad_ready", False)
+            torch.ops.b200.rmsnorm_bwd(dy, res, weight, rstd, dres_out.contiguous() if dres_out is not None else None,
+                                       dx, partial, buf, not fresh)
+            weight.grad_ready = True
+            hook = getattr(weight, "grad_hook", None)
+            if hook is not None:
+                hook(weight)
+            dw = None
+        else:
+            dw = torch.empty_like(weight)
+            torch.ops.b200.rmsnorm_bwd(dy, res, weight, rstd, dres_out.contiguous() if dres_out is not None else None,
+                                       dx, partial, dw, False)
+        _bump(2)
+        # d(new_residual)/dx = d(new_residual)/d(residual) = identity: both inputs receive the same gradient
+        return dx, (dx if ctx.has_res else None), dw, None
+
+
+def add_rmsnorm(
+    x: torch.Tensor, residual: Optional[torch.Tensor], weight: torch.Tensor, eps: float
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``new_res = x + residual``; ``y = RMSNorm(new_res) * weight``.  Returns ``(y, new_res)``."""
+    H = x.shape[-1]
+    if (
+        _lib.use_native(x, weight)
+        and x.dtype == torch.bfloat16
+        and weight.dtype == torch.bfloat16
+        and H % 8 == 0
+        and H <= 8192
+    ):
+        return _AddRMSNormFn.apply(x, residual, weight, eps)
+    new_res = x if residual is None else x + residual
+    return rmsnorm_ref(new_res, weight, eps).to(x.dtype), new_res
+
+
+class RMSNorm(nn.Module):
+    """RMSNorm with learnable scale.  ``forward(x)`` or ``forward(x, residual) -> (y, new_residual)``."""
+
+    def __init__(self, hidden_size: int, eps: float = 1e-5, device=None, dtype=None):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(hidden_size, device=device, dtype=dtype))
+
+    def reset_parameters(self):
+        nn.init.ones_(self.weight)
+
+    def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None):
+        if residual is None:
+            return add_rmsnorm(x, None, self.weight, self.eps)[0]
+        return add_rmsnorm(x, residual, self.weight, self.eps)
+
+    def extra_repr(self):
+        return f"{tuple(self.weight.shape)}, eps={self.eps}"

@@ -1,0 +1,319 @@
+"""GPU numerics + speed check for the hand-written kernels (run under gpurun; each section in its own process).
+
+    python tools/kernel_check.py gemm        # correctness sweep of the tcgen05 GEMM, all operand layouts / epilogues
+    python tools/kernel_check.py gemm_perf   # TFLOP/s vs torch.matmul (cuBLAS) on the model's shapes
+    python tools/kernel_check.py elementwise # RMSNorm / RoPE / SwiGLU / CE / AdamW / sumsq vs fp32 PyTorch
+    python tools/kernel_check.py attn        # flash attention fwd/bwd vs fp32 reference
+"""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch
+
+import internevo_b200.ops as ops
+from internevo_b200.ops import _lib
+
+dev = "cuda"
+
+
+def err_report(name, got, ref, tol):
+    got, ref = got.float(), ref.float()
+    diff = (got - ref).abs()
+    denom = ref.abs().max().clamp_min(1e-6)
+    rel = (diff.max() / denom).item()
+    ok = rel < tol and not torch.isnan(got).any().item()
+    print(f"  [{'OK ' if ok else 'BAD'}] {name}: max_abs={diff.max().item():.4e} rel_to_max={rel:.3e} (tol {tol})", flush=True)
+    if not ok and got.dim() == 2:
+        # localise the damage: error per 32x32 block, coarse map
+        M, N = got.shape
+        bm, bn = max(1, M // 8), max(1, N // 8)
+        grid = diff[: bm * 8, : bn * 8].reshape(8, bm, 8, bn).amax(dim=(1, 3))
+        print("    coarse error map (8x8 blocks):")
+        for r in grid.tolist():
+            print("     ", " ".join(f"{v:9.2e}" for v in r))
+        bad = (diff > tol * denom).nonzero()
+        print("    first bad idx:", bad[:5].tolist(), "got", [got[i, j].item() for i, j in bad[:5].tolist()],
+              "ref", [ref[i, j].item() for i, j in bad[:5].tolist()])
+    return ok
+
+
+def check_gemm():
+    torch.manual_seed(0)
+    allok = True
+    shapes = [(128, 256, 64), (128, 128, 64), (128, 256, 256), (256, 512, 512), (384, 768, 1024), (1000, 520, 264),
+              (4096, 4096, 4096), (333, 46272 // 8, 512)]
+    for (M, N, K) in shapes:
+        a = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
+        b = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
+        ref = a.float() @ b.float().t()
+        for bn in (256, 128):
+            out = ops.matmul(a, b, force_bn=bn)
+            allok &= err_report(f"NT  {M}x{N}x{K} bn{bn}", out, ref, 1e-2)
+        if M % 8 == 0:
+            bt = b.t().contiguous()  # [K, N]
+            out = ops.matmul(a, bt, b_mn=True)
+            allok &= err_report(f"NN  {M}x{N}x{K} (B MN-major)", out, ref, 1e-2)
+            at = a.t().contiguous()  # [K, M]
+            out = ops.matmul(at, bt, a_mn=True, b_mn=True)
+            allok &= err_report(f"TN  {M}x{N}x{K} (A,B MN-major)", out, ref, 1e-2)
+            out = ops.matmul(at, b, a_mn=True)
+            allok &= err_report(f"TT  {M}x{N}x{K} (A MN-major)", out, ref, 1e-2)
+    # epilogues
+    M, N, K = 512, 1024, 512
+    a = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
+    b = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
+    bias = torch.randn(N, device=dev, dtype=torch.bfloat16)
+    ref = a.float() @ b.float().t()
+    allok &= err_report("bias", ops.matmul(a, b, bias=bias), ref + bias.float(), 1e-2)
+    allok &= err_report("fp32 out", ops.matmul(a, b, out_dtype=torch.float32), ref, 1e-3)
+    acc = torch.randn(M, N, device=dev, dtype=torch.float32)
+    acc0 = acc.clone()
+    ops.matmul(a, b, out=acc, accumulate=True)
+    allok &= err_report("fp32 accumulate", acc, ref + acc0, 1e-3)
+    accb = torch.randn(M, N, device=dev, dtype=torch.bfloat16)
+    accb0 = accb.clone()
+    ops.matmul(a, b, out=accb, accumulate=True)
+    allok &= err_report("bf16 accumulate", accb, ref + accb0.float(), 1e-2)
+    gu, h = ops.matmul_swiglu(a, b)
+    allok &= err_report("swiglu gu", gu, ref, 1e-2)
+    g, u = gu[:, 0::2].float(), gu[:, 1::2].float()
+    allok &= err_report("swiglu h", h, torch.nn.functional.silu(g) * u, 1e-2)
+    # autograd linear
+    x = torch.randn(256, 512, device=dev, dtype=torch.bfloat16, requires_grad=True)
+    w = torch.randn(384, 512, device=dev, dtype=torch.bfloat16, requires_grad=True)
+    y = ops.linear(x, w)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    allok &= err_report("linear fwd", y, x.float() @ w.float().t(), 1e-2)
+    allok &= err_report("linear dx", x.grad, dy.float() @ w.float(), 1e-2)
+    allok &= err_report("linear dw", w.grad, dy.float().t() @ x.float(), 1e-2)
+    print("GEMM_ALL_OK" if allok else "GEMM_HAS_FAILURES", flush=True)
+    return allok
+
+
+def timeit(fn, iters=20, warmup=3, flush=None):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        times.append(s.elapsed_time(e))
+    times.sort()
+    return times[len(times) // 2]
+
+
+def gemm_perf():
+    res = []
+    flush = torch.empty(256 * 1024 * 1024, device=dev, dtype=torch.uint8)
+    T, h, F, V = 4096, 4096, 14336, 92544
+    cases = [
+        ("8192^3 NT", 8192, 8192, 8192, False, False),
+        ("wqkv fwd  NT", T, 6144, h, False, False),
+        ("wo   fwd  NT", T, h, h, False, False),
+        ("w13  fwd  NT", T, 2 * F, h, False, False),
+        ("w2   fwd  NT", T, h, F, False, False),
+        ("head fwd  NT", T, V, h, False, False),
+        ("w13 dgrad NN", T, h, 2 * F, False, True),
+        ("w2  dgrad NN", T, F, h, False, True),
+        ("w13 wgrad TN", 2 * F, h, T, True, True),
+        ("w2  wgrad TN", h, F, T, True, True),
+        ("head wgrad TN", V, h, T, True, True),
+    ]
+    for name, M, N, K, a_mn, b_mn in cases:
+        a = torch.randn((K, M) if a_mn else (M, K), device=dev, dtype=torch.bfloat16)
+        b = torch.randn((K, N) if b_mn else (N, K), device=dev, dtype=torch.bfloat16)
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        A = a.t() if a_mn else a
+        Bt = b if b_mn else b.t()
+        row = {"case": name, "M": M, "N": N, "K": K}
+        for bn in (256, 128):
+            try:
+                ms = timeit(lambda: ops.matmul(a, b, a_mn=a_mn, b_mn=b_mn, out=out, force_bn=bn), flush=flush)
+                row[f"ours_bn{bn}_tflops"] = round(2 * M * N * K / ms / 1e9, 1)
+            except Exception as e:  # noqa
+                row[f"ours_bn{bn}_tflops"] = f"ERR {e}"
+        ms = timeit(lambda: torch.matmul(A, Bt, out=out), flush=flush)
+        row["cublas_tflops"] = round(2 * M * N * K / ms / 1e9, 1)
+        print(json.dumps(row), flush=True)
+        res.append(row)
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(res, open("gpurun_out/gemm_perf.json", "w"), indent=1)
+
+
+def check_elementwise():
+    torch.manual_seed(0)
+    ok = True
+    T, H = 1000, 4096
+    x = torch.randn(T, H, device=dev, dtype=torch.bfloat16, requires_grad=True)
+    r = torch.randn(T, H, device=dev, dtype=torch.bfloat16, requires_grad=True)
+    w = (torch.rand(H, device=dev) + 0.5).to(torch.bfloat16).requires_grad_(True)
+    y, nr = ops.add_rmsnorm(x, r, w, 1e-5)
+    nr_ref = (x.float() + r.float()).to(torch.bfloat16).float()
+    y_ref = nr_ref * torch.rsqrt(nr_ref.pow(2).mean(-1, keepdim=True) + 1e-5) * w.float()
+    ok &= err_report("rmsnorm y", y, y_ref, 1e-2)
+    ok &= err_report("rmsnorm res", nr, nr_ref, 1e-2)
+    dy, dnr = torch.randn_like(y), torch.randn_like(nr)
+    torch.autograd.backward([y, nr], [dy, dnr])
+    xf = x.detach().float().requires_grad_(True)
+    rf = r.detach().float().requires_grad_(True)
+    wf = w.detach().float().requires_grad_(True)
+    nrf = xf + rf
+    yf = nrf * torch.rsqrt(nrf.pow(2).mean(-1, keepdim=True) + 1e-5) * wf
+    torch.autograd.backward([yf, nrf], [dy.float(), dnr.float()])
+    ok &= err_report("rmsnorm dx", x.grad, xf.grad, 2e-2)
+    ok &= err_report("rmsnorm dres", r.grad, rf.grad, 2e-2)
+    ok &= err_report("rmsnorm dw", w.grad, wf.grad, 2e-2)
+
+    # RoPE on packed qkv [T, Hkv*(q_per_kv+2), D]
+    Hkv, qpk, D = 8, 4, 128
+    qkv = torch.randn(T, Hkv * (qpk + 2), D, device=dev, dtype=torch.bfloat16)
+    pos = torch.randint(0, 4096, (T,), device=dev, dtype=torch.int32)
+    tabs = ops.RotaryTables(D, 1e6)
+    cos, sin = tabs.get(4096, dev)
+    from internevo_b200.ops.rope import _rope_ref
+    ref = _rope_ref(qkv.clone(), pos, cos, sin, qpk + 2, qpk + 1, False, False)
+    got = ops.rope_(qkv.clone(), pos, cos, sin, qpk + 2, qpk + 1, False, False)
+    ok &= err_report("rope packed", got.flatten(1), ref.flatten(1), 1e-2)
+    back = ops.rope_(got.clone(), pos, cos, sin, qpk + 2, qpk + 1, True, False)
+    ok &= err_report("rope conj roundtrip", back.flatten(1), qkv.flatten(1), 2e-2)
+    ref = _rope_ref(qkv.clone(), pos, cos, sin, 1, 1, False, True)
+    got = ops.rope_(qkv.clone(), pos, cos, sin, 1, 1, False, True)
+    ok &= err_report("rope interleaved", got.flatten(1), ref.flatten(1), 1e-2)
+
+    # SwiGLU
+    gu = torch.randn(T, 2 * 1024, device=dev, dtype=torch.bfloat16, requires_grad=True)
+    hh = ops.swiglu_interleaved(gu)
+    dh = torch.randn_like(hh)
+    hh.backward(dh)
+    gf = gu.detach().float().requires_grad_(True)
+    hf = torch.nn.functional.silu(gf[:, 0::2]) * gf[:, 1::2]
+    hf.backward(dh.float())
+    ok &= err_report("swiglu fwd", hh, hf, 1e-2)
+    ok &= err_report("swiglu bwd", gu.grad, gf.grad, 1e-2)
+
+    # cross entropy
+    V = 92544
+    logits = (torch.randn(512, V, device=dev) * 2).to(torch.bfloat16).requires_grad_(True)
+    labels = torch.randint(0, V, (512,), device=dev)
+    labels[::7] = -100
+    for sm in (0.0, 0.1):
+        lg = logits.detach().clone().requires_grad_(True)
+        loss = ops.cross_entropy(lg, labels, label_smoothing=sm, inplace_backward=False)
+        loss.sum().backward()
+        lf = logits.detach().float().requires_grad_(True)
+        lref = torch.nn.functional.cross_entropy(lf, labels, reduction="none", label_smoothing=sm, ignore_index=-100)
+        lref.sum().backward()
+        ok &= err_report(f"ce loss sm={sm}", loss[None], lref[None], 1e-3)
+        ok &= err_report(f"ce grad sm={sm}", lg.grad, lf.grad, 2e-2)
+
+    # adam + sumsq
+    n = 1_000_003
+    p = torch.randn(n, device=dev)
+    m = torch.zeros(n, device=dev)
+    v = torch.zeros(n, device=dev)
+    g = torch.randn(n, device=dev).to(torch.bfloat16)
+    plp = torch.empty(n, device=dev, dtype=torch.bfloat16)
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pr], lr=1e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1)
+    ss = torch.zeros(1, device=dev)
+    ops.sumsq_(g, ss)
+    ok &= err_report("sumsq", ss[None], g.float().pow(2).sum()[None, None], 1e-4)
+    scal = torch.zeros(4, device=dev)
+    ops.clip_scalars_(ss, scal, 1.0, 1.0)
+    norm = g.float().norm().item()
+    print("   scalars", scal.tolist(), "expected mult", 1.0 / norm, "norm", norm)
+    for step in (1, 2, 3):
+        ops.adamw_(p, m, v, g, plp, 1e-3, 0.9, 0.95, 1e-8, 0.1, step, scal)
+        pr.grad = g.float() * (1.0 / norm)
+        opt.step()
+    ok &= err_report("adamw p", p[None], pr.detach()[None], 1e-5)
+    ok &= err_report("adamw p_lp", plp[None], pr.detach()[None], 1e-2)
+    print("ELEMENTWISE_ALL_OK" if ok else "ELEMENTWISE_HAS_FAILURES", flush=True)
+
+    # bandwidth numbers
+    flush = torch.empty(256 * 1024 * 1024, device=dev, dtype=torch.uint8)
+    T = 16384
+    x = torch.randn(T, H, device=dev, dtype=torch.bfloat16)
+    r = torch.randn(T, H, device=dev, dtype=torch.bfloat16)
+    wq = torch.ones(H, device=dev, dtype=torch.bfloat16)
+    ms = timeit(lambda: ops.add_rmsnorm(x, r, wq, 1e-5), flush=flush)
+    print(f"  rmsnorm fwd {T}x{H}: {ms:.3f} ms  {4 * T * H * 2 / ms / 1e6:.0f} GB/s")
+    lg = torch.randn(4096, V, device=dev, dtype=torch.bfloat16)
+    lb = torch.randint(0, V, (4096,), device=dev)
+    st = torch.empty(4, 4096, device=dev)
+    ms = timeit(lambda: torch.ops.b200.ce_fwd(lg, lb, 0, st[0], st[1], st[2], st[3]), flush=flush)
+    print(f"  ce fwd 4096x{V}: {ms:.3f} ms  {4096 * V * 2 / ms / 1e6:.0f} GB/s")
+    n = 256 * 1024 * 1024
+    p = torch.zeros(n, device=dev); m = torch.zeros(n, device=dev); v = torch.zeros(n, device=dev)
+    g = torch.zeros(n, device=dev, dtype=torch.bfloat16); plp = torch.empty(n, device=dev, dtype=torch.bfloat16)
+    ms = timeit(lambda: ops.adamw_(p, m, v, g, plp, 1e-3, 0.9, 0.95, 1e-8, 0.1, 1, None))
+    print(f"  adamw {n}: {ms:.3f} ms  {n * 28 / ms / 1e6:.0f} GB/s")
+    return ok
+
+
+def check_attn():
+    from internevo_b200.ops.attention import attention_ref, flash_attention_varlen
+
+    torch.manual_seed(0)
+    ok = True
+    for (seqs, H, Hkv, D) in [([128], 2, 2, 128), ([256, 384], 4, 2, 128), ([1000, 24, 513], 8, 2, 128), ([4096], 8, 2, 128)]:
+        T = sum(seqs)
+        cu = torch.tensor([0] + list(torch.tensor(seqs).cumsum(0)), device=dev, dtype=torch.int32)
+        q = torch.randn(T, H, D, device=dev, dtype=torch.bfloat16, requires_grad=True)
+        k = torch.randn(T, Hkv, D, device=dev, dtype=torch.bfloat16, requires_grad=True)
+        v = torch.randn(T, Hkv, D, device=dev, dtype=torch.bfloat16, requires_grad=True)
+        out = flash_attention_varlen(q, k, v, cu, max(seqs), causal=True)
+        dout = torch.randn_like(out)
+        out.backward(dout)
+        qf, kf, vf = [t.detach().float().requires_grad_(True) for t in (q, k, v)]
+        ref = attention_ref(qf, kf, vf, cu, causal=True)
+        ref.backward(dout.float())
+        ok &= err_report(f"attn fwd {seqs} H{H}/{Hkv}", out.flatten(1), ref.flatten(1), 2e-2)
+        ok &= err_report("attn dq", q.grad.flatten(1), qf.grad.flatten(1), 3e-2)
+        ok &= err_report("attn dk", k.grad.flatten(1), kf.grad.flatten(1), 3e-2)
+        ok &= err_report("attn dv", v.grad.flatten(1), vf.grad.flatten(1), 3e-2)
+    print("ATTN_ALL_OK" if ok else "ATTN_HAS_FAILURES", flush=True)
+    # speed: 7B shape, T=4096 one sequence and 16k
+    for S in (4096, 16384):
+        H, Hkv, D = 32, 8, 128
+        cu = torch.tensor([0, S], device=dev, dtype=torch.int32)
+        q = torch.randn(S, H, D, device=dev, dtype=torch.bfloat16, requires_grad=True)
+        k = torch.randn(S, Hkv, D, device=dev, dtype=torch.bfloat16, requires_grad=True)
+        v = torch.randn(S, Hkv, D, device=dev, dtype=torch.bfloat16, requires_grad=True)
+        ms = timeit(lambda: flash_attention_varlen(q, k, v, cu, S, causal=True))
+        fl = 4 * S * S * H * D / 2
+        print(f"  attn fwd S={S}: {ms:.3f} ms {fl / ms / 1e9:.0f} TFLOP/s (causal flops)")
+        out = flash_attention_varlen(q, k, v, cu, S, causal=True)
+        dout = torch.randn_like(out)
+        ms = timeit(lambda: out.backward(dout, retain_graph=True))
+        print(f"  attn bwd S={S}: {ms:.3f} ms {2.5 * fl / ms / 1e9:.0f} TFLOP/s")
+        try:
+            from flash_attn import flash_attn_varlen_func
+            ms = timeit(lambda: flash_attn_varlen_func(q, k, v, cu, cu, S, S, causal=True))
+            print(f"  flash_attn lib fwd S={S}: {ms:.3f} ms {fl / ms / 1e9:.0f} TFLOP/s")
+        except Exception as e:  # noqa
+            print("  flash_attn lib unavailable:", repr(e)[:200])
+    return ok
+
+
+if __name__ == "__main__":
+    what = sys.argv[1]
+    assert torch.cuda.is_available(), "needs a GPU"
+    assert _lib.available()
+    print("device", torch.cuda.get_device_name(0), "section", what, flush=True)
+    t0 = time.time()
+    fn = {"gemm": check_gemm, "gemm_perf": gemm_perf, "elementwise": check_elementwise, "attn": check_attn}[what]
+    r = fn()
+    print(f"section {what} done in {time.time() - t0:.1f}s", flush=True)
+    sys.exit(0 if r in (None, True) else 1)
