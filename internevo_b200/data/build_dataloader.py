@@ -1,0 +1,101 @@
+"""Train / validation dataloader construction (reference ``internlm/data/build_dataloader.py:88-158``)."""
+from __future__ import annotations
+
+from functools import partial
+
+import torch
+from torch.utils.data import ConcatDataset, DataLoader
+
+from internevo_b200.core.context import ParallelMode
+from internevo_b200.core.context import global_context as gpc
+from internevo_b200.utils.logger import get_logger
+from internevo_b200.utils.parallel import is_using_isp
+
+from .batch_sampler import StaticBatchSampler, get_dpsampler_dataloader
+from .collaters import jsonl_ds_collate_fn, packed_collate_fn
+from .datasets import (
+    JsonlDataset,
+    PackedDatasetWithCut,
+    PackedDatasetWithoutCuSeqlen,
+    RandomDataset,
+    get_packed_dataset_without_short_length,
+)
+
+logger = get_logger(__file__)
+
+
+def _dp_rank_size():
+    mode = ParallelMode.WEIGHT_DATA if is_using_isp() else ParallelMode.DATA
+    # ISP shards the sequence over the TENSOR group: ranks of one TP group consume the same samples
+    if is_using_isp():
+        return gpc.get_local_rank(ParallelMode.DATA), gpc.get_world_size(ParallelMode.DATA)
+    return gpc.get_local_rank(mode), gpc.get_world_size(mode)
+
+
+def get_tokenized_train_loader_items(data_cfg):
+    if data_cfg.get("train_folder", None) is None:
+        train_ds = RandomDataset(num_samples=data_cfg.get("num_random_samples", 100000),
+                                 max_len=data_cfg.seq_len, fixed_seqlen=data_cfg.fixed_random_dataset_seqlen)
+        if data_cfg.pack_sample_into_one:
+            train_ds = PackedDatasetWithoutCuSeqlen(train_ds, max_length_per_sample=data_cfg.seq_len,
+                                                    packed_length=data_cfg.packed_length)
+        else:
+            train_ds = PackedDatasetWithCut(train_ds, max_length_per_sample=data_cfg.seq_len,
+                                            packed_length=data_cfg.packed_length)
+    else:
+        train_ds = get_packed_dataset_without_short_length(
+            folder=data_cfg.train_folder, packed_length=data_cfg.packed_length, max_length_per_sample=data_cfg.seq_len,
+            show_progress=gpc.is_rank_for_log(), min_length=data_cfg.get("min_length", 0),
+            min_length_dict=data_cfg.get("min_length_dict", None), pack_sample_into_one=data_cfg.pack_sample_into_one,
+        )
+    rank, size = _dp_rank_size()
+    train_sampler = StaticBatchSampler(
+        train_ds.datasets if isinstance(train_ds, ConcatDataset) else [train_ds],
+        batch_size=data_cfg.micro_num, rampup_batch_size=data_cfg.rampup_batch_size, micro_bsz=data_cfg.micro_bsz,
+        seed=1024, drop_last=True, data_rank=rank, data_world_size=size,
+    )
+    train_collate_fn = partial(packed_collate_fn, packed_length=data_cfg.packed_length)
+    return train_ds, train_sampler, train_collate_fn
+
+
+def get_tokenized_valid_loader_items(data_cfg):
+    if not data_cfg.get("valid_folder", None):
+        valid_ds = RandomDataset(num_samples=gpc.get_world_size(ParallelMode.DATA) * 500, max_len=data_cfg.seq_len)
+    else:
+        valid_ds = JsonlDataset(data_cfg.valid_folder, min_length=0) if data_cfg.valid_folder.endswith(".bin") else None
+        if valid_ds is None:
+            import os
+
+            files = sorted(os.path.join(r, f) for r, _, fs in os.walk(data_cfg.valid_folder) for f in fs
+                           if f.endswith(".bin"))
+            valid_ds = ConcatDataset([JsonlDataset(f, min_length=0) for f in files])
+    return valid_ds, partial(jsonl_ds_collate_fn, max_length_per_sample=data_cfg.seq_len)
+
+
+def build_train_loader_with_data_type():
+    """→ ``(train_dataloader, dataset_types)``; only ``data.type == "tokenized"`` exists in this snapshot."""
+    data_cfg = gpc.config.data
+    assert data_cfg.type == "tokenized", f"unsupported data type {data_cfg.type}"
+    train_ds, train_sampler, train_collate_fn = get_tokenized_train_loader_items(data_cfg)
+    dataset_types = list(["en", "cn", "code"])
+    train_dl = DataLoader(
+        dataset=train_ds, batch_sampler=train_sampler, num_workers=data_cfg.get("num_worker", 0),
+        pin_memory=torch.cuda.is_available(), collate_fn=train_collate_fn,
+        persistent_workers=data_cfg.get("num_worker", 0) > 0,
+    )
+    return train_dl, dataset_types
+
+
+def build_valid_loader_with_data_type():
+    data_cfg = gpc.config.data
+    assert data_cfg.type == "tokenized"
+    valid_ds, valid_collate_fn = get_tokenized_valid_loader_items(data_cfg)
+    if valid_ds is None:
+        return None
+    bsz = data_cfg.valid_micro_num * data_cfg.micro_bsz
+    n = min(len(valid_ds), bsz)
+    if n < bsz and gpc.is_rank_for_log():
+        logger.info(f"validation set smaller than one batch: using {n}")
+    dl = get_dpsampler_dataloader(valid_ds, shuffle=False, num_workers=0, batch_size=bsz, collate_fn=valid_collate_fn,
+                                  drop_last=True)
+    return {"val": dl} if not isinstance(dl, dict) else dl

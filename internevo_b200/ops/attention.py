@@ -1,0 +1,122 @@
+"""Variable-length causal attention with GQA.
+
+``flash_attention_varlen`` dispatches to the hand-written sm_100a kernel (``csrc/attention_sm100.cu``: TMA-fed
+``tcgen05`` QK^T / PV with the score tile in TMEM and an online-softmax warpgroup); it replaces flash-attn's
+``flash_attn_varlen_kvpacked_func`` (reference ``internlm/model/modeling_internlm2.py:446-468``), whose pinned build
+refuses sm_100 altogether.  ``attention_ref`` is the fp32 PyTorch oracle and the CPU path.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .gemm import _bump
+
+_IMPL = os.environ.get("INTERNEVO_ATTN_IMPL", "flash_attn")  # b200 | flash_attn | sdpa
+
+
+def set_attention_impl(name: str):
+    global _IMPL
+    assert name in ("b200", "flash_attn", "sdpa")
+    _IMPL = name
+
+
+def get_attention_impl() -> str:
+    return _IMPL
+
+
+def attention_ref(q, k, v, cu_seqlens, causal=True, scale=None):
+    """fp32 reference. q ``[T, H, D]``, k/v ``[T, Hkv, D]``, ``cu_seqlens`` int32 ``[n+1]``."""
+    T, H, D = q.shape
+    Hkv = k.shape[1]
+    scale = scale or 1.0 / math.sqrt(D)
+    out = torch.empty(T, H, v.shape[-1], dtype=torch.float32, device=q.device)
+    cu = cu_seqlens.tolist()
+    rep = H // Hkv
+    outs = []
+    for a, b in zip(cu[:-1], cu[1:]):
+        qs = q[a:b].float().transpose(0, 1)  # [H, S, D]
+        ks = k[a:b].float().transpose(0, 1).repeat_interleave(rep, dim=0)
+        vs = v[a:b].float().transpose(0, 1).repeat_interleave(rep, dim=0)
+        s = qs @ ks.transpose(1, 2) * scale
+        if causal:
+            S = b - a
+            mask = torch.ones(S, S, dtype=torch.bool, device=q.device).tril()
+            s = s.masked_fill(~mask, float("-inf"))
+        p = torch.softmax(s, dim=-1)
+        outs.append((p @ vs).transpose(0, 1))
+    del out
+    return torch.cat(outs, 0) if outs else q.new_zeros(0, H, D, dtype=torch.float32)
+
+
+class _B200AttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, cu_seqlens, max_seqlen, scale, causal):
+        T, H, D = q.shape
+        out = torch.empty(T, H, D, device=q.device, dtype=q.dtype)
+        lse = torch.empty(H, T, device=q.device, dtype=torch.float32)
+        torch.ops.b200.attn_fwd(q, k, v, out, lse, cu_seqlens, max_seqlen, scale, causal)
+        _bump()
+        ctx.save_for_backward(q, k, v, out, lse, cu_seqlens)
+        ctx.cfg = (max_seqlen, scale, causal)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, out, lse, cu = ctx.saved_tensors
+        max_seqlen, scale, causal = ctx.cfg
+        T, H, D = q.shape
+        dout = dout.contiguous()
+        # gradients are written in the same (possibly packed/strided) layout as the inputs when those are views of one
+        # qkv tensor, so the RoPE backward and the wqkv wgrad consume them without a gather copy
+        dq = torch.empty_like(q) if q.is_contiguous() else torch.empty(q.shape, device=q.device, dtype=q.dtype)
+        dk = torch.empty(k.shape, device=k.device, dtype=k.dtype)
+        dv = torch.empty(v.shape, device=v.device, dtype=v.dtype)
+        delta = torch.empty(H, T, device=q.device, dtype=torch.float32)
+        dq_acc = torch.zeros(T, H, D, device=q.device, dtype=torch.float32)
+        torch.ops.b200.attn_bwd(dout, q, k, v, out, lse, dq, dk, dv, delta, dq_acc, cu, max_seqlen, scale, causal)
+        _bump(3)
+        return dq, dk, dv, None, None, None, None
+
+
+_b200_attn_ok: Optional[bool] = None
+
+
+def _b200_available() -> bool:
+    """The native attention kernel is mandatory on GPU unless explicitly overridden."""
+    return _lib.available()
+
+
+def flash_attention_varlen(q, k, v, cu_seqlens, max_seqlen: int, causal: bool = True, scale: Optional[float] = None,
+                           impl: Optional[str] = None) -> torch.Tensor:
+    """q ``[T, H, D]`` bf16, k/v ``[T, Hkv, D]``; returns ``[T, H, D]``."""
+    scale = scale or 1.0 / math.sqrt(q.shape[-1])
+    impl = impl or _IMPL
+    if not q.is_cuda:
+        return attention_ref(q, k, v, cu_seqlens, causal, scale).to(q.dtype)
+    if cu_seqlens.dtype != torch.int32:
+        cu_seqlens = cu_seqlens.int()
+    if impl == "b200" and q.dtype == torch.bfloat16 and q.shape[-1] == 128 and _b200_available():
+        return _B200AttnFn.apply(q, k, v, cu_seqlens.contiguous(), int(max_seqlen), float(scale), bool(causal))
+    if impl in ("b200", "flash_attn"):
+        try:
+            from flash_attn import flash_attn_varlen_func
+
+            return flash_attn_varlen_func(q, k, v, cu_seqlens, cu_seqlens, int(max_seqlen), int(max_seqlen),
+                                          softmax_scale=scale, causal=causal)
+        except ImportError:
+            pass
+    # torch SDPA per sequence (library fallback)
+    H, Hkv = q.shape[1], k.shape[1]
+    outs = []
+    cu = cu_seqlens.tolist()
+    for a, b in zip(cu[:-1], cu[1:]):
+        qs, ks, vs = (t[a:b].transpose(0, 1)[None] for t in (q, k, v))
+        o = torch.nn.functional.scaled_dot_product_attention(qs, ks, vs, is_causal=causal, scale=scale,
+                                                             enable_gqa=H != Hkv)
+        outs.append(o[0].transpose(0, 1))
+    return torch.cat(outs, 0)

@@ -46,10 +46,12 @@ class _CrossEntropyFn(torch.autograd.Function):
         loss = torch.where(valid, loss, torch.zeros_like(loss))
         ctx.save_for_backward(logits, labels, lse)
         ctx.cfg = (vocab_start, smoothing, total, ignore_index, inplace_backward)
-        return loss
+        correct = (tg >= mx) & valid  # the target holds the row maximum <=> greedy prediction is right
+        ctx.mark_non_differentiable(correct)
+        return loss, correct
 
     @staticmethod
-    def backward(ctx, dloss):
+    def backward(ctx, dloss, _dcorrect=None):
         logits, labels, lse = ctx.saved_tensors
         vocab_start, smoothing, total, ignore_index, inplace = ctx.cfg
         g = logits if inplace else logits.clone()
@@ -66,17 +68,25 @@ def _ce_ref(logits, labels, smoothing, ignore_index, group):
         from internevo_b200.parallel.functional import gather_forward_split_backward
 
         logits = gather_forward_split_backward(logits, group, dim=-1)
-    return torch.nn.functional.cross_entropy(
+    loss = torch.nn.functional.cross_entropy(
         logits.float(), labels, reduction="none", label_smoothing=smoothing, ignore_index=ignore_index
     )
+    with torch.no_grad():
+        correct = (logits.argmax(-1) == labels) & (labels != ignore_index)
+    return loss, correct
 
 
 def cross_entropy(logits: torch.Tensor, labels: torch.Tensor, label_smoothing: float = 0.0, ignore_index: int = -100,
-                  process_group: Optional[dist.ProcessGroup] = None, inplace_backward: bool = True) -> torch.Tensor:
-    """Per-token loss ``[rows]`` (fp32). ``logits`` may be a vocab shard when ``process_group`` is given."""
+                  process_group: Optional[dist.ProcessGroup] = None, inplace_backward: bool = True,
+                  return_correct: bool = False):
+    """Per-token loss ``[rows]`` (fp32). ``logits`` may be a vocab shard when ``process_group`` is given.
+    With ``return_correct`` also returns the boolean top-1 correctness per token (free: the kernel already has the row
+    maximum and the target logit), which replaces the reference's separate argmax pass in ``AccPerplex``."""
     logits2 = logits.reshape(-1, logits.shape[-1])
     labels1 = labels.reshape(-1)
     if _lib.use_native(logits2) and logits2.dtype == torch.bfloat16 and logits2.stride(-1) == 1 and logits2.stride(0) % 8 == 0:
-        return _CrossEntropyFn.apply(logits2, labels1.long().contiguous(), label_smoothing, ignore_index, process_group,
-                                     inplace_backward)
-    return _ce_ref(logits2, labels1.long(), label_smoothing, ignore_index, process_group)
+        loss, correct = _CrossEntropyFn.apply(logits2, labels1.long().contiguous(), label_smoothing, ignore_index,
+                                              process_group, inplace_backward)
+    else:
+        loss, correct = _ce_ref(logits2, labels1.long(), label_smoothing, ignore_index, process_group)
+    return (loss, correct) if return_correct else loss
