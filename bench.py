@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Headline benchmark: InternLM2-7B pre-training step throughput (tokens/s over the whole job; TGS and TFLOPS
+reported too) on synthetic packed tokens, bf16, seq 4096 — the metric/config named in BASELINE.json.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29500 \
+        bench.py --gpus 8 --steps 5 --warmup 3
+    python bench.py --impl reference ...      # the UNMODIFIED reference from baseline/_ref through its own public API
+
+Two timed regions per run, both through the public API (initialize_distributed_env → initialize_model →
+initialize_optimizer → initialize_trainer → trainer.execute_schedule / trainer.step):
+  * "value": K full optimizer steps (fwd + bwd over all micro-batches + grad sync + clip + AdamW + param sync), timed
+    with CUDA events between barrier+synchronize brackets, max over ranks;
+  * "e2e":   the same K steps with each step's batch copied from pinned host memory and the step loss read back to the host.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+BASELINE_TGS = 4078.0  # README headline, tokens/GPU/s (A100 x8, InternLM-7B)
+
+MODEL_7B = dict(hidden_size=4096, num_attention_heads=32, num_kv_attention_heads=8, mlp_ratio=3.5, vocab_size=92544,
+                num_layers=32)
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--tp", type=int, default=0, help="tensor parallel size (0 = BASELINE layout: 1 for N=1, else 2)")
+    p.add_argument("--tp-mode", default="mtp")
+    p.add_argument("--seq-len", type=int, default=4096)
+    p.add_argument("--micro-bsz", type=int, default=1)
+    p.add_argument("--micro-num", type=int, default=4)
+    p.add_argument("--layers", type=int, default=MODEL_7B["num_layers"], help="debug only: fewer layers is NOT the benchmark")
+    p.add_argument("--hidden", type=int, default=MODEL_7B["hidden_size"])
+    p.add_argument("--checkpoint", type=float, default=0.0)
+    p.add_argument("--attn", default=None, help="attention implementation override (b200|flash_attn|sdpa)")
+    p.add_argument("--fused-comm", type=int, default=-1, help="peer-memory fused collectives (default: on when N>1)")
+    return p.parse_args()
+
+
+def build_config(a, world):
+    tp = a.tp if a.tp > 0 else (1 if world == 1 else 2)
+    dp = world // tp
+    model = dict(
+        checkpoint=a.checkpoint, num_chunks=1, num_attention_heads=MODEL_7B["num_attention_heads"] * a.hidden // 4096,
+        embed_split_hidden=True, vocab_size=MODEL_7B["vocab_size"], embed_grad_scale=1, parallel_output=True,
+        hidden_size=a.hidden, num_layers=a.layers, no_bias=True, mlp_ratio=MODEL_7B["mlp_ratio"],
+        apply_post_layer_norm=False, dtype="torch.bfloat16", norm_type="rmsnorm", layer_norm_epsilon=1e-5,
+        num_kv_attention_heads=MODEL_7B["num_kv_attention_heads"], use_flash_attn=True,
+    )
+    cfg = dict(
+        JOB_NAME="bench_7b_internlm2", model_type="INTERNLM2_PUBLIC",
+        ckpt=dict(enable_save_ckpt=False, auto_resume=False),
+        data=dict(seq_len=a.seq_len, micro_num=a.micro_num, micro_bsz=a.micro_bsz, valid_micro_num=a.micro_num,
+                  valid_every=0, pack_sample_into_one=False, total_steps=a.steps + a.warmup + 8, skip_batches="",
+                  rampup_batch_size="", min_length=0, train_folder=None, valid_folder=None,
+                  empty_cache_and_diag_interval=10**9, diag_outlier_ratio=1.1),
+        grad_scaler=dict(fp16=dict(initial_scale=2**16, min_scale=1, growth_interval=1000), growth_factor=2,
+                         backoff_factor=0.5, max_scale=2**24, hysteresis=2),
+        hybrid_zero_optimizer=dict(overlap_sync_grad=True, overlap_sync_param=False,
+                                   reduce_bucket_size=512 * 1024 * 1024, clip_grad_norm=1.0),
+        loss=dict(label_smoothing=0),
+        adam=dict(lr=1e-4, adam_beta1=0.9, adam_beta2=0.95, adam_beta2_c=0, adam_eps=1e-8, weight_decay=0.01),
+        lr_scheduler=dict(total_steps=1000, init_steps=0, warmup_ratio=0.01, eta_min=1e-5, last_epoch=-1),
+        beta2_scheduler=dict(init_beta2=0.95, c=0, cur_iter=-1),
+        use_fp32_norm=False, model=model,
+        parallel=dict(zero1=dict(size=dp), tensor=dict(size=tp, mode=a.tp_mode),
+                      pipeline=dict(size=1, interleaved_overlap=True),
+                      weight=dict(size=1, overlap=True, memory_pool=True)),
+        cudnn_deterministic=False, cudnn_benchmark=False, enable_tb=False,
+        monitor=dict(alert=dict(enable_feishu_alert=False, feishu_alert_address=None, light_monitor_address=None,
+                                alert_file_path=None), tensorboard=dict(queue_max_length=10)),
+    )
+    return cfg, tp, dp
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (profiling recipe's clocks line)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.samples, self.proc, self.thread, self.idx = [], None, None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def rd():
+            for line in self.proc.stdout:
+                self.samples.append(line.strip())
+        self.thread = threading.Thread(target=rd, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_batches(n, micro_num, T, vocab, pin):
+    """Synthetic packed batches in (pinned) host memory: one 4096-token segment per micro-batch row."""
+    import torch
+
+    g = torch.Generator().manual_seed(1234)
+    out = []
+    for _ in range(n):
+        ids = torch.randint(1, vocab, (micro_num, T), generator=g, dtype=torch.long)
+        labels = torch.cat([ids[:, 1:], torch.full((micro_num, 1), -100, dtype=torch.long)], 1)
+        cu = torch.tensor([[0, T]] * micro_num, dtype=torch.int32)
+        idx = torch.arange(T, dtype=torch.long).repeat(micro_num, 1)
+        d = {"input_ids": ids, "cu_seqlens": cu, "indexes": idx}
+        if pin:
+            d = {k: v.pin_memory() for k, v in d.items()}
+            labels = labels.pin_memory()
+        out.append((d, labels))
+    return out
+
+
+def batch_bytes(b):
+    d, l = b
+    return sum(v.numel() * v.element_size() for v in d.values()) + l.numel() * l.element_size()
+
+
+def timed_loop(torch, dist, step_fn, batches, steps, world, sampler=None):
+    """K steps between barrier + synchronize brackets, CUDA events on the compute stream, max over ranks."""
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    s.record()
+    last = None
+    for i in range(steps):
+        last = step_fn(batches[i % len(batches)])
+    e.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    wall = time.time() - t0
+    clocks = sampler.stop() if sampler else None
+    ms = torch.tensor([s.elapsed_time(e), wall * 1e3], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms[0]), float(ms[1]), clocks, last
+
+
+def setup_env(a):
+    os.environ.setdefault("RANK", "0")
+    os.environ.setdefault("LOCAL_RANK", "0")
+    os.environ.setdefault("WORLD_SIZE", "1")
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", str(29400 + os.getpid() % 500))
+    world = int(os.environ["WORLD_SIZE"])
+    assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
+    return world, int(os.environ["RANK"])
+
+
+def run(a, ours: bool):
+    world, rank = setup_env(a)
+    cfg, tp, dp = build_config(a, world)
+    if ours:
+        sys.path.insert(0, ROOT)
+        if a.attn:
+            os.environ["INTERNEVO_ATTN_IMPL"] = a.attn
+        fused = a.fused_comm if a.fused_comm >= 0 else int(world > 1)
+        cfg["fused_comm"] = bool(fused)
+        import torch
+        import torch.distributed as dist
+        import internevo_b200 as fw
+        from internevo_b200 import ops
+        from internevo_b200.core.context import ParallelMode, global_context as gpc
+        from internevo_b200.initialize import initialize_distributed_env
+        from internevo_b200.models.losses import FlashGPTLMLoss
+        from internevo_b200.models.metrics import AccPerplex
+        from internevo_b200.train import get_scheduler_hooks, initialize_isp_communicator, initialize_model, initialize_optimizer
+        from internevo_b200.utils.common import get_megatron_flops
+        launches = ops.launch_count
+    else:
+        sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+        import torch
+        import torch.distributed as dist
+        import internlm as fw  # the unmodified reference package
+        from internlm.core.context import ParallelMode, global_context as gpc
+        from internlm.initialize import initialize_distributed_env
+        from internlm.model.losses import FlashGPTLMLoss
+        from internlm.model.metrics import AccPerplex
+        from internlm.train import get_scheduler_hooks, initialize_isp_communicator, initialize_model, initialize_optimizer
+        from internlm.utils.common import get_megatron_flops
+        launches = lambda: 0  # noqa: E731
+        assert "baseline/_ref" in fw.__file__.replace(os.sep, "/"), fw.__file__
+
+    initialize_distributed_env(config=cfg, launcher="torch", seed=1024)
+    model = initialize_model()
+    isp = initialize_isp_communicator(model)
+    criterion = FlashGPTLMLoss(parallel_output=True, label_smoothing=0)
+    optimizer, beta2_scheduler, lr_scheduler = initialize_optimizer(model, isp)
+    if ours:
+        metric = AccPerplex(dataset_types=None)
+        hooks = get_scheduler_hooks(metric, optimizer, isp)
+    else:
+        from internlm.model.metrics import SchedulerMetricHook
+
+        hooks = [SchedulerMetricHook(metric=None, skip=True)]  # no AccPerplex: torch_scatter is not in this image
+    trainer, _, _, _ = fw.initialize_trainer(model=model, optimizer=optimizer, criterion=criterion,
+                                             lr_scheduler=lr_scheduler, beta2_scheduler=beta2_scheduler,
+                                             scheduler_hooks=hooks)
+    trainer.train()
+    T = a.seq_len * a.micro_bsz
+    host_batches = make_batches(4, a.micro_num, T, MODEL_7B["vocab_size"], pin=True)
+    dev_batches = [({k: v.cuda() for k, v in d.items()}, l.cuda()) for d, l in host_batches]
+
+    def step_dev(batch):
+        d, l = batch
+        trainer.zero_grad()
+        out = trainer.execute_schedule(({k: v for k, v in d.items()}, l), forward_only=False, return_loss=True,
+                                       return_output_label=False)
+        ok, norms = trainer.step()
+        return out[2]
+
+    def step_e2e(batch):
+        loss = step_dev(batch)  # engine.load_batch copies the pinned host batch to the device (non_blocking)
+        return float(loss)  # device → host read of the step result
+
+    for i in range(a.warmup):
+        step_dev(dev_batches[i % len(dev_batches)])
+    l0 = launches()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) if rank == 0 else None
+    ms, wall_ms, clocks, last = timed_loop(torch, dist, step_dev, dev_batches, a.steps, world, sampler)
+    n_launch = launches() - l0
+    step_e2e(host_batches[0])
+    e2e_ms, e2e_wall, _, last_e2e = timed_loop(torch, dist, step_e2e, host_batches, a.steps, world, None)
+    e2e_ms = max(e2e_ms, e2e_wall)  # the host read-back is part of the region: take the host clock if it is longer
+
+    tokens_per_step = T * a.micro_num * dp
+    value = tokens_per_step * a.steps / (ms / 1e3)
+    e2e_value = tokens_per_step * a.steps / (e2e_ms / 1e3)
+    tflops = get_megatron_flops(ms / 1e3 / a.steps, checkpoint=bool(a.checkpoint), seq_len=a.seq_len,
+                                hidden_size=a.hidden, num_layers=a.layers, vocab_size=MODEL_7B["vocab_size"],
+                                global_batch_size=a.micro_bsz * a.micro_num * dp, global_world_size=world,
+                                mlp_ratio=MODEL_7B["mlp_ratio"])
+    mem = torch.cuda.max_memory_allocated() / 2**30
+    if rank == 0:
+        full = a.layers == MODEL_7B["num_layers"] and a.hidden == MODEL_7B["hidden_size"] and a.seq_len == 4096
+        res = {
+            "metric": "tokens_per_second (TGS x n_gpus), InternLM2-7B pre-training step", "value": round(value, 1),
+            "unit": "tokens/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": round(ms / a.steps, 2), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": round(value / (BASELINE_TGS * world), 3) if full else None, "dtype": "bf16",
+            "data": "synthetic packed tokens (random ids, one 4096-token segment per micro-batch), random-init weights",
+            "impl": "ours" if ours else "reference",
+            "tgs": round(value / world, 1), "tflops_per_gpu": round(tflops, 1),
+            "config": {"model": "InternLM2-7B (h4096 L32 H32/kv8 mlp3.5 V92544)" if full else
+                       f"DEBUG h{a.hidden} L{a.layers} (not the benchmark config)",
+                       "global_batch": a.micro_bsz * a.micro_num * dp, "seq_len": a.seq_len,
+                       "micro_bsz": a.micro_bsz, "micro_num": a.micro_num,
+                       "parallelism": f"tp{tp}({a.tp_mode})-dp{dp}-zero{dp}", "act_ckpt": a.checkpoint,
+                       "l2": "working set >> L2: 15.5 GB of bf16 weights + activations are streamed every step",
+                       "fused_comm": bool(cfg.get("fused_comm", False)) if ours else None},
+            "e2e": {"value": round(e2e_value, 1), "unit": "tokens/s", "h2d_bytes_per_step": batch_bytes(host_batches[0]),
+                    "d2h_bytes_per_step": 4 + 16 * (len(optimizer.groups) if ours else 1),
+                    "ms_per_step": round(e2e_ms / a.steps, 2)},
+            "gpu_launches": int(n_launch), "clocks": clocks, "last_loss": float(last) if last is not None else None,
+            "peak_mem_gib": round(mem, 1),
+        }
+        print(json.dumps(res), flush=True)
+    gpc.destroy()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        ref = os.path.join(ROOT, "baseline", "_ref", "internlm")
+        if not os.path.isdir(ref):
+            print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref is not installed "
+                              "(pip install --no-index --target baseline/_ref /root/reference)"}))
+            return 0
+        try:
+            run(a, ours=False)
+        except BaseException as e:  # the reference's stock path may not run on sm_100 in this image
+            if int(os.environ.get("RANK", "0")) == 0:
+                msg = f"{type(e).__name__}: {str(e).splitlines()[0] if str(e) else ''}"[:300]
+                print(json.dumps({"impl": "reference", "unavailable": msg}), flush=True)
+            if os.environ.get("BENCH_DEBUG"):
+                raise
+        return 0
+    run(a, ours=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

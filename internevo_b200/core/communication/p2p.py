@@ -64,10 +64,10 @@ def process_object_to_send(obj, scatter_gather_tensors):
     return [process_object_to_send(o, scatter_gather_tensors) for o in obj]
 
 
-def _ops_for(obj, peer, send: bool):
+def _ops_for(obj, peer, send: bool, group=None):
     fn = dist.isend if send else dist.irecv
     objs = obj if isinstance(obj, (list, tuple)) else [obj]
-    return [dist.P2POp(fn, o, peer) for o in objs]
+    return [dist.P2POp(fn, o, peer, group) for o in objs]
 
 
 def _communicate_async(object_send_next=None, object_send_prev=None, recv_prev=False, recv_next=False,
@@ -87,16 +87,19 @@ def _communicate_async(object_send_next=None, object_send_prev=None, recv_prev=F
         prev_rank = gpc.get_prev_global_rank(ParallelMode.PIPELINE) if prev_rank is None else prev_rank
     if object_send_next is not None or recv_next:
         next_rank = gpc.get_next_global_rank(ParallelMode.PIPELINE) if next_rank is None else next_rank
-    ops = []
-    if object_send_prev is not None:
-        ops += _ops_for(process_object_to_send(object_send_prev, scatter_gather_tensors), prev_rank, True)
-    if recv_prev_buf is not None:
-        ops += _ops_for(recv_prev_buf, prev_rank, False)
-    if recv_next_buf is not None:
-        ops += _ops_for(recv_next_buf, next_rank, False)
+    # activations travel on the PIPELINE communicator, gradients on its twin (see ParallelContext.pipeline_bwd_group)
+    fwd_group = gpc.get_group(ParallelMode.PIPELINE)
+    bwd_group = gpc.pipeline_bwd_group if gpc.pipeline_bwd_group is not None else fwd_group
+    fwd_ops, bwd_ops = [], []
     if object_send_next is not None:
-        ops += _ops_for(process_object_to_send(object_send_next, scatter_gather_tensors), next_rank, True)
-    reqs = dist.batch_isend_irecv(ops) if ops else []
+        fwd_ops += _ops_for(process_object_to_send(object_send_next, scatter_gather_tensors), next_rank, True, fwd_group)
+    if recv_prev_buf is not None:
+        fwd_ops += _ops_for(recv_prev_buf, prev_rank, False, fwd_group)
+    if object_send_prev is not None:
+        bwd_ops += _ops_for(process_object_to_send(object_send_prev, scatter_gather_tensors), prev_rank, True, bwd_group)
+    if recv_next_buf is not None:
+        bwd_ops += _ops_for(recv_next_buf, next_rank, False, bwd_group)
+    reqs = (dist.batch_isend_irecv(fwd_ops) if fwd_ops else []) + (dist.batch_isend_irecv(bwd_ops) if bwd_ops else [])
 
     def post(buf, split, shape):
         if buf is None:

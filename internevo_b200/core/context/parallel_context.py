@@ -77,6 +77,7 @@ class ParallelContext:
         self.virtual_pipeline_parallel_rank = None
         self._is_evaluating = False
         self.is_forward = True
+        self.pipeline_bwd_group = None
 
     # ------------------------------------------------------------------ config
     @property
@@ -274,6 +275,13 @@ class ParallelContext:
                         group = dist.new_group(ranks, timeout=LLM_NCCL_TIMEOUT)
                 if rank in ranks:
                     self._register(mode, ranks.index(rank), len(ranks), group, ranks)
+                if mode is ParallelMode.PIPELINE and len(ranks) > 1 and self.is_distributed:
+                    # second communicator for the backward (gradient) direction: with it, activations and gradients
+                    # exchanged between the same pair of stages can never be mis-matched (matters for pp == 2, where
+                    # the previous and the next stage are the same rank)
+                    bwd = dist.new_group(ranks, timeout=LLM_NCCL_TIMEOUT)
+                    if rank in ranks:
+                        self.pipeline_bwd_group = bwd
         if ParallelMode.PIPELINE not in self._world_sizes and s.pipeline == 1:
             pass  # queries fall back to size 1 / rank 0
 

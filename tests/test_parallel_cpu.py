@@ -1,0 +1,128 @@
+"""Hybrid-parallel equivalence on CPU/gloo: every layout (DP+ZeRO, TP in mtp/msp/fsp, 1F1B and interleaved pipeline)
+must reproduce the single-process loss trajectory from identical weights and data — the CPU analogue of the
+reference's ``tests/test_training/test_loss.py`` layout matrix and ``tests/test_core/test_pipeline.py``."""
+import pytest
+import torch
+
+from common import build_trainer, run_distributed, synthetic_batch, tiny_config
+
+STEPS = 3
+MICRO_TOTAL = 4
+
+
+def _golden_state(cfg, seed=7):
+    """Full (unsharded) InternLM2 weights generated from the config's shapes."""
+    m = cfg["model"]
+    h, H, Hkv, V, L = m["hidden_size"], m["num_attention_heads"], m["num_kv_attention_heads"], m["vocab_size"], m["num_layers"]
+    d = h // H
+    F = 256 * ((int(h * m["mlp_ratio"]) + 255) // 256)
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=g) * 0.05  # noqa: E731
+    sd = {"tok_embeddings.weight": r(V, h), "norm.weight": 1 + r(h), "output.weight": r(V, h)}
+    for i in range(L):
+        p = f"layers.{i}."
+        sd[p + "attention.wqkv.weight"] = r((H + 2 * Hkv) * d, h)
+        sd[p + "attention.wo.weight"] = r(h, h)
+        sd[p + "attention_norm.weight"] = 1 + r(h)
+        sd[p + "ffn_norm.weight"] = 1 + r(h)
+        sd[p + "feed_forward.w1.weight"] = r(F, h)
+        sd[p + "feed_forward.w3.weight"] = r(F, h)
+        sd[p + "feed_forward.w2.weight"] = r(h, F)
+    return sd
+
+
+def _load_golden(model, opt, cfg):
+    from internevo_b200.core.context import ParallelMode, global_context as gpc
+    from internevo_b200.models.sharding import pipeline_slice, shard_state_dict
+    from internevo_b200.solver.pipeline_utils import partition_uniform
+
+    full = _golden_state(cfg)
+    tp, tpr = gpc.get_world_size(ParallelMode.TENSOR), gpc.get_local_rank(ParallelMode.TENSOR)
+    pp, ppr = gpc.get_world_size(ParallelMode.PIPELINE), gpc.get_local_rank(ParallelMode.PIPELINE)
+    L, chunks = cfg["model"]["num_layers"], cfg["model"].get("num_chunks", 1)
+    parts = partition_uniform(L, pp, chunks)[ppr]
+    inner = model.model
+    mods = list(inner) if isinstance(inner, torch.nn.ModuleList) else [inner]
+    for mod, (s, e) in zip(mods, parts):
+        sd = pipeline_slice(full, s, e, first=s == 0, last=e == L)
+        sd = shard_state_dict(sd, tpr, tp)
+        missing, unexpected = mod.load_state_dict(sd, strict=True)
+        assert not missing and not unexpected
+    opt.reload_zero_fp32_buff()
+
+
+def _train(rank, world, kw):
+    from internevo_b200.core.context import ParallelMode, global_context as gpc
+
+    cfg = tiny_config(**kw)
+    trainer, opt, model, _ = build_trainer(cfg)
+    _load_golden(model, opt, cfg)
+    dp, dpr = gpc.get_world_size(ParallelMode.DATA), gpc.get_local_rank(ParallelMode.DATA)
+    per = MICRO_TOTAL // dp
+    T = cfg["data"]["seq_len"] * cfg["data"]["micro_bsz"]
+    losses = []
+    for step in range(STEPS):
+        data, labels = synthetic_batch(MICRO_TOTAL, T, cfg["model"]["vocab_size"], seed=0)
+        data = {k: v[dpr * per:(dpr + 1) * per] for k, v in data.items()}
+        labels = labels[dpr * per:(dpr + 1) * per]
+        trainer.zero_grad()
+        out = trainer.execute_schedule((data, labels), forward_only=False, return_loss=True, return_output_label=False)
+        ok, norms = trainer.step()
+        assert ok
+        loss = out[2]
+        if loss is not None:
+            loss = loss.detach().clone().reshape(1).float()
+            if dp > 1:
+                torch.distributed.all_reduce(loss, group=gpc.get_group(ParallelMode.DATA))
+                loss /= dp
+            losses.append(float(loss))
+        else:
+            losses.append(None)
+    return losses, norms
+
+
+@pytest.fixture(scope="module")
+def baseline():
+    return run_distributed(_train, 1, dict(micro_num=MICRO_TOTAL))[0]
+
+
+def _check(res, baseline, tol=2e-4):
+    ref_losses, ref_norms = baseline
+    got = [r for r in res if r[0][0] is not None]
+    assert got, "no rank reported a loss"
+    for losses, norms in got:
+        for a, b in zip(losses, ref_losses):
+            assert abs(a - b) < tol * max(1.0, abs(b)), (losses, ref_losses)
+        for k, v in norms.items():
+            assert abs(v - ref_norms[k]) < 1e-3 * max(1.0, ref_norms[k]), (norms, ref_norms)
+
+
+def test_single_process_trains(baseline):
+    losses, _ = baseline
+    assert losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("zero1", [-1, 1])
+def test_dp2_zero(baseline, zero1):
+    _check(run_distributed(_train, 2, dict(micro_num=MICRO_TOTAL // 2, zero1=zero1)), baseline)
+
+
+@pytest.mark.parametrize("mode", ["mtp", "msp", "fsp"])
+def test_tp2(baseline, mode):
+    _check(run_distributed(_train, 2, dict(tp=2, mode=mode, micro_num=MICRO_TOTAL)), baseline)
+
+
+def test_pp2_1f1b(baseline):
+    _check(run_distributed(_train, 2, dict(pp=2, micro_num=MICRO_TOTAL)), baseline)
+
+
+def test_pp2_interleaved(baseline):
+    _check(run_distributed(_train, 2, dict(pp=2, micro_num=MICRO_TOTAL, num_chunks=2)), baseline)
+
+
+def test_tp2_dp2_zero2(baseline):
+    _check(run_distributed(_train, 4, dict(tp=2, mode="fsp", micro_num=MICRO_TOTAL // 2, zero1=2)), baseline)
+
+
+def test_activation_checkpoint_matches(baseline):
+    _check(run_distributed(_train, 1, dict(micro_num=MICRO_TOTAL, checkpoint=True)), baseline, tol=1e-5)
