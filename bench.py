@@ -216,6 +216,16 @@ def run(a, ours: bool):
         launches = ops.launch_count
     else:
         sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+        # the reference builds its rendezvous URL as tcp://[{MASTER_ADDR}]:{port} (internlm/core/context/
+        # parallel_context.py:384); python >= 3.11 rejects a bracketed IPv4 literal, so hand it the IPv4-mapped IPv6 form
+        # of the same address (environment only; the reference code is untouched)
+        import ipaddress
+
+        try:
+            if isinstance(ipaddress.ip_address(os.environ["MASTER_ADDR"]), ipaddress.IPv4Address):
+                os.environ["MASTER_ADDR"] = "::ffff:" + os.environ["MASTER_ADDR"]
+        except ValueError:
+            pass
         import torch
         import torch.distributed as dist
         import internlm as fw  # the unmodified reference package

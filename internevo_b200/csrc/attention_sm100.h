@@ -13,6 +13,7 @@ struct AttnDesc {
     float* lse = nullptr;     // [H, T] natural-log LSE (scaled scores)
     int T = 0, H = 0, Hkv = 0, D = 0;
     int64_t q_stride_t = 0, q_stride_h = 0, k_stride_t = 0, k_stride_h = 0, v_stride_t = 0, v_stride_h = 0;
+    int64_t q_stride_g = 0;  // stride between kv groups of q heads (0: q_stride_h * H/Hkv); head (g,j) = g*q_stride_g + j*q_stride_h
     const int* cu_seqlens = nullptr;  // [num_seqs + 1]
     int num_seqs = 0, max_seqlen = 0;
     float scale = 1.f;

@@ -174,19 +174,35 @@ void clip_scalars(const Tensor& sumsq_in, Tensor& scalars, double loss_scale, do
 // ---------------------------------------------------------------------------------------------------------------
 // attention
 // ---------------------------------------------------------------------------------------------------------------
+static void fill_qkv(b200::AttnDesc& d, const Tensor& q, const Tensor& k, const Tensor& v) {
+    // q: [T, H, D] or the grouped view [T, Hkv, q_per_kv, D] of a packed qkv buffer; k, v: [T, Hkv, D]
+    TORCH_CHECK((q.dim() == 3 || q.dim() == 4) && k.dim() == 3 && v.dim() == 3, "attn: q [T,H,D] | [T,Hkv,qpk,D], k/v [T,Hkv,D]");
+    TORCH_CHECK(q.stride(-1) == 1 && k.stride(2) == 1 && v.stride(2) == 1, "attn: last dim must be contiguous");
+    d.q = q.data_ptr(); d.k = k.data_ptr(); d.v = v.data_ptr();
+    d.T = q.size(0); d.Hkv = k.size(1); d.D = q.size(-1);
+    d.q_stride_t = q.stride(0);
+    if (q.dim() == 4) {
+        d.H = q.size(1) * q.size(2); d.q_stride_g = q.stride(1); d.q_stride_h = q.stride(2);
+    } else {
+        d.H = q.size(1); d.q_stride_h = q.stride(1); d.q_stride_g = q.stride(1) * (d.H / d.Hkv);
+    }
+    d.k_stride_t = k.stride(0); d.k_stride_h = k.stride(1);
+    d.v_stride_t = v.stride(0); d.v_stride_h = v.stride(1);
+    TORCH_CHECK(d.q_stride_t % 8 == 0 && d.k_stride_t % 8 == 0 && d.v_stride_t % 8 == 0, "attn: token strides must be multiples of 8");
+    // TMA descriptors address whole token rows starting at the tensor's data pointer: that pointer must be 16B aligned
+    TORCH_CHECK((reinterpret_cast<uintptr_t>(d.q) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.k) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(d.v) & 15) == 0, "attn: q/k/v must be 16-byte aligned");
+}
+
 void attn_fwd(const Tensor& q, const Tensor& k, const Tensor& v, Tensor& out, Tensor& lse, const Tensor& cu_seqlens,
               int64_t max_seqlen, double scale, bool causal) {
     CHECK_BF16(q); CHECK_BF16(k); CHECK_BF16(v); CHECK_BF16(out);
-    TORCH_CHECK(q.dim() == 3 && k.dim() == 3 && v.dim() == 3, "attn: q [T,H,D], k/v [T,Hkv,D]");
-    TORCH_CHECK(q.stride(2) == 1 && k.stride(2) == 1 && v.stride(2) == 1 && out.is_contiguous(), "attn: strides");
+    TORCH_CHECK(out.is_contiguous(), "attn: out must be contiguous [T, H, D]");
     TORCH_CHECK(cu_seqlens.scalar_type() == at::kInt && cu_seqlens.is_contiguous(), "attn: cu_seqlens int32");
     c10::cuda::CUDAGuard guard(q.device());
     b200::AttnDesc d;
-    d.q = q.data_ptr(); d.k = k.data_ptr(); d.v = v.data_ptr(); d.o = out.data_ptr(); d.lse = lse.data_ptr<float>();
-    d.T = q.size(0); d.H = q.size(1); d.Hkv = k.size(1); d.D = q.size(2);
-    d.q_stride_t = q.stride(0); d.q_stride_h = q.stride(1);
-    d.k_stride_t = k.stride(0); d.k_stride_h = k.stride(1);
-    d.v_stride_t = v.stride(0); d.v_stride_h = v.stride(1);
+    fill_qkv(d, q, k, v);
+    d.o = out.data_ptr(); d.lse = lse.data_ptr<float>();
     d.cu_seqlens = cu_seqlens.data_ptr<int>(); d.num_seqs = cu_seqlens.numel() - 1; d.max_seqlen = max_seqlen;
     d.scale = (float)scale; d.causal = causal;
     CHECK_RC(b200::attn_fwd(d, cur_stream()), "b200::attn_fwd");
@@ -198,12 +214,9 @@ void attn_bwd(const Tensor& dout, const Tensor& q, const Tensor& k, const Tensor
     CHECK_BF16(q); CHECK_BF16(k); CHECK_BF16(v); CHECK_BF16(dout);
     c10::cuda::CUDAGuard guard(q.device());
     b200::AttnBwdDesc d;
-    d.f.q = q.data_ptr(); d.f.k = k.data_ptr(); d.f.v = v.data_ptr(); d.f.o = const_cast<void*>(out.data_ptr());
+    fill_qkv(d.f, q, k, v);
+    d.f.o = const_cast<void*>(out.data_ptr());
     d.f.lse = const_cast<float*>(lse.data_ptr<float>());
-    d.f.T = q.size(0); d.f.H = q.size(1); d.f.Hkv = k.size(1); d.f.D = q.size(2);
-    d.f.q_stride_t = q.stride(0); d.f.q_stride_h = q.stride(1);
-    d.f.k_stride_t = k.stride(0); d.f.k_stride_h = k.stride(1);
-    d.f.v_stride_t = v.stride(0); d.f.v_stride_h = v.stride(1);
     d.f.cu_seqlens = cu_seqlens.data_ptr<int>(); d.f.num_seqs = cu_seqlens.numel() - 1; d.f.max_seqlen = max_seqlen;
     d.f.scale = (float)scale; d.f.causal = causal;
     TORCH_CHECK(dout.is_contiguous() && out.is_contiguous(), "attn_bwd: dout/out contiguous");

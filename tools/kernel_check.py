@@ -307,13 +307,65 @@ def check_attn():
     return ok
 
 
+def check_attn_fwd():
+    """forward-only check of the native attention kernel (plain and packed-qkv grouped layouts) + speed."""
+    from internevo_b200.ops.attention import attention_ref
+
+    torch.manual_seed(0)
+    ok = True
+    for (seqs, H, Hkv) in [([128], 2, 2), ([256], 2, 1), ([384, 256], 4, 2), ([1000, 24, 513], 8, 2), ([4096], 8, 2)]:
+        D = 128
+        T = sum(seqs)
+        cu = torch.tensor([0] + torch.tensor(seqs).cumsum(0).tolist(), device=dev, dtype=torch.int32)
+        qpk = H // Hkv
+        qkv = torch.randn(T, Hkv, qpk + 2, D, device=dev, dtype=torch.bfloat16)
+        q4, k, v = qkv[:, :, :qpk], qkv[:, :, -2], qkv[:, :, -1]
+        out = torch.empty(T, H, D, device=dev, dtype=torch.bfloat16)
+        lse = torch.empty(H, T, device=dev, dtype=torch.float32)
+        scale = D ** -0.5
+        torch.ops.b200.attn_fwd(q4, k, v, out, lse, cu, max(seqs), scale, True)
+        torch.cuda.synchronize()
+        q3 = q4.reshape(T, H, D)
+        ref = attention_ref(q3, k, v, cu, True, scale)
+        ok &= err_report(f"attn fwd packed {seqs} H{H}/{Hkv}", out.flatten(1), ref.flatten(1), 2e-2)
+        out2 = torch.empty_like(out)
+        torch.ops.b200.attn_fwd(q3.contiguous(), k.contiguous(), v.contiguous(), out2, lse, cu, max(seqs), scale, True)
+        ok &= err_report("attn fwd contiguous", out2.flatten(1), ref.flatten(1), 2e-2)
+        # lse check
+        cul = cu.tolist()
+        a, b = cul[0], cul[1]
+        s = (q3[a:b].float().transpose(0, 1) @ k[a:b].float().transpose(0, 1).repeat_interleave(qpk, 0).transpose(1, 2)) * scale
+        s = s.masked_fill(~torch.ones(b - a, b - a, dtype=torch.bool, device=dev).tril(), float("-inf"))
+        ok &= err_report("attn lse", lse[:, a:b], torch.logsumexp(s, -1), 1e-2)
+    print("ATTN_FWD_ALL_OK" if ok else "ATTN_FWD_HAS_FAILURES", flush=True)
+    for S in (4096, 16384):
+        H, Hkv, D = 32, 8, 128
+        cu = torch.tensor([0, S], device=dev, dtype=torch.int32)
+        q = torch.randn(S, H, D, device=dev, dtype=torch.bfloat16)
+        k = torch.randn(S, Hkv, D, device=dev, dtype=torch.bfloat16)
+        v = torch.randn(S, Hkv, D, device=dev, dtype=torch.bfloat16)
+        out = torch.empty_like(q)
+        lse = torch.empty(H, S, device=dev, dtype=torch.float32)
+        ms = timeit(lambda: torch.ops.b200.attn_fwd(q, k, v, out, lse, cu, S, D ** -0.5, True))
+        fl = 4 * S * S * H * D / 2
+        print(f"  b200 attn fwd S={S}: {ms:.3f} ms {fl / ms / 1e9:.0f} TFLOP/s (causal flops)")
+        try:
+            from flash_attn import flash_attn_varlen_func
+            ms = timeit(lambda: flash_attn_varlen_func(q, k, v, cu, cu, S, S, causal=True))
+            print(f"  flash_attn lib fwd S={S}: {ms:.3f} ms {fl / ms / 1e9:.0f} TFLOP/s")
+        except Exception as e:  # noqa
+            print("  flash_attn lib unavailable:", repr(e)[:200])
+    return ok
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
     assert torch.cuda.is_available(), "needs a GPU"
     assert _lib.available()
     print("device", torch.cuda.get_device_name(0), "section", what, flush=True)
     t0 = time.time()
-    fn = {"gemm": check_gemm, "gemm_perf": gemm_perf, "elementwise": check_elementwise, "attn": check_attn}[what]
+    fn = {"gemm": check_gemm, "gemm_perf": gemm_perf, "elementwise": check_elementwise, "attn": check_attn,
+          "attn_fwd": check_attn_fwd}[what]
     r = fn()
     print(f"section {what} done in {time.time() - t0:.1f}s", flush=True)
     sys.exit(0 if r in (None, True) else 1)
