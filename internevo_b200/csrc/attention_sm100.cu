@@ -346,6 +346,410 @@ int attn_fwd(const AttnDesc& d, cudaStream_t stream) {
     return cudaGetLastError() == cudaSuccess ? 0 : -13;
 }
 
-int attn_bwd(const AttnBwdDesc&, cudaStream_t) { return -100; }
+
+// ================================================================================================================
+// backward
+// ================================================================================================================
+static constexpr int BQ = 64;                  // q rows per inner step
+static constexpr int BWD_THREADS = 384;
+static constexpr int QT_BYTES = BQ * D * 2;    // 16 KB
+
+struct BwdSmem {
+    static constexpr int K = 0;                          // 32 KB
+    static constexpr int V = K + TILE_BYTES;             // 32 KB
+    static constexpr int Q = V + TILE_BYTES;             // 2 x 16 KB
+    static constexpr int DO = Q + 2 * QT_BYTES;          // 2 x 16 KB
+    static constexpr int DS = DO + 2 * QT_BYTES;         // 2 x 16 KB  (dS^T, [128 kv rows x 64 q] bf16)
+    static constexpr int DQ = DS + 2 * QT_BYTES;         // 32 KB fp32 staging [64 q x 128 d] for the TMA reduce-add
+    static constexpr int BARS = DQ + BQ * D * 4;
+    static constexpr int TOTAL = BARS + 256 + 1024;
+};
+
+struct AttnBwdArgs {
+    AttnKernelArgs f;
+    const float* lse;
+    const float* delta;
+    float* dq_acc;            // [T, H, D] fp32
+    __nv_bfloat16 *dk, *dv;   // strided outputs
+    int64_t dk_stride_t, dk_stride_h, dv_stride_t, dv_stride_h;
+};
+
+// delta[h, t] = sum_d dO[t,h,d] * O[t,h,d]
+__global__ void attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+                                      float* __restrict__ delta, int T, int H) {
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per (t, h)
+    const int lane = threadIdx.x & 31;
+    if (gw >= (int64_t)T * H) return;
+    const int t = gw / H, h = gw % H;
+    const uint2 a = *reinterpret_cast<const uint2*>(dout + gw * D + lane * 4);
+    const uint2 b = *reinterpret_cast<const uint2*>(out + gw * D + lane * 4);
+    float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), b0 = unpack_bf16(b.x), b1 = unpack_bf16(b.y);
+    float s = a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) delta[(int64_t)h * T + t] = s;
+}
+
+// dq (bf16, strided [T, (g, j), D]) = dq_acc (fp32 [T, H, D])
+__global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int T, int H,
+                                           int qpk, int64_t st, int64_t sg, int64_t sh) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 8 elements
+    const int64_t n = (int64_t)T * H * (D / 8);
+    if (i >= n) return;
+    const int c = (i % (D / 8)) * 8;
+    const int64_t th = i / (D / 8);
+    const int h = th % H;
+    const int64_t t = th / H;
+    const float4 x = *reinterpret_cast<const float4*>(acc + th * D + c);
+    const float4 y = *reinterpret_cast<const float4*>(acc + th * D + c + 4);
+    uint4 o;
+    o.x = pack_bf16(x.x, x.y); o.y = pack_bf16(x.z, x.w); o.z = pack_bf16(y.x, y.y); o.w = pack_bf16(y.z, y.w);
+    *reinterpret_cast<uint4*>(dq + t * st + (int64_t)(h / qpk) * sg + (int64_t)(h % qpk) * sh + c) = o;
+}
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
+                const __grid_constant__ CUtensorMap tmap_dq, const AttnBwdArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BwdSmem::BARS);
+    uint64_t* kv_full = bars;            // 1
+    uint64_t* qdo_full = bars + 1;       // 2
+    uint64_t* qdo_empty = bars + 3;      // 2
+    uint64_t* s_full = bars + 5;         // 2
+    uint64_t* p_ready = bars + 7;        // 2 (count 4)
+    uint64_t* dp_full = bars + 9;        // 1
+    uint64_t* ds_ready = bars + 10;      // 1 (count 4)
+    uint64_t* ds_free = bars + 11;       // 2
+    uint64_t* dq_full = bars + 13;       // 1
+    uint64_t* dq_free = bars + 14;       // 1 (count 4)
+    uint64_t* dkv_done = bars + 15;      // 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+    const AttnKernelArgs& f = args.f;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int seq, blk, s0, len;
+    if (!find_qblock(f.cu_seqlens, f.num_seqs, blockIdx.x, TN, seq, blk, s0, len)) return;
+    const int nkv = (len + TN - 1) / TN;
+    blk = nkv - 1 - blk;                      // find_qblock reverses; bwd wants early (heavy) kv tiles first
+    const int hk = blockIdx.y;
+    const int qpk = f.H / f.Hkv;
+    const int kv0 = blk * TN;
+    const int mq0 = f.causal ? kv0 / BQ : 0;
+    const int nq = (len + BQ - 1) / BQ - mq0;   // q tiles per head
+    const int n_steps = nq * qpk;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
+        mbar_init(kv_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); mbar_init(&s_full[i], 1);
+            mbar_init(&p_ready[i], 4); mbar_init(&ds_free[i], 1);
+        }
+        mbar_init(dp_full, 1); mbar_init(ds_ready, 4); mbar_init(dq_full, 1); mbar_init(dq_free, 4);
+        mbar_init(dkv_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    // TMEM columns
+    const uint32_t T_S0 = 0, T_DP = 128, T_DQ = 192, T_DV = 256, T_DK = 384;  // S^T buffers at 0 and 64
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int kcol = (int)((int64_t)hk * f.k_stride_h), vcol = (int)((int64_t)hk * f.v_stride_h);
+            mbar_expect_tx(kv_full, 2 * TILE_BYTES);
+            for (int c = 0; c < 2; ++c) {
+                tma_load_2d(smem + BwdSmem::K + c * (TN * 128), &tmap_k, kv_full, kcol + c * 64, s0 + kv0);
+                tma_load_2d(smem + BwdSmem::V + c * (TN * 128), &tmap_v, kv_full, vcol + c * 64, s0 + kv0);
+            }
+            for (int i = 0; i < n_steps; ++i) {
+                const int st = i & 1;
+                const int j = i / nq, mq = mq0 + i % nq;
+                const int h = hk * qpk + j;
+                mbar_wait(&qdo_empty[st], ((i >> 1) & 1) ^ 1);
+                mbar_expect_tx(&qdo_full[st], 2 * QT_BYTES);
+                const int qcol = (int)((int64_t)hk * f.q_stride_g + (int64_t)j * f.q_stride_h);
+                for (int c = 0; c < 2; ++c) {
+                    tma_load_2d(smem + BwdSmem::Q + st * QT_BYTES + c * (BQ * 128), &tmap_q, &qdo_full[st], qcol + c * 64,
+                                s0 + mq * BQ);
+                    tma_load_2d(smem + BwdSmem::DO + st * QT_BYTES + c * (BQ * 128), &tmap_do, &qdo_full[st],
+                                h * D + c * 64, s0 + mq * BQ);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t id_s = make_idesc_f16(128, BQ, 0, 0);    // S^T / dP^T : A,B K-major
+            const uint32_t id_kv = make_idesc_f16(128, D, 0, 1);    // dV / dK    : A TMEM, B MN-major
+            const uint32_t id_dq = make_idesc_f16(128, BQ, 1, 1);   // dQ^T       : A,B MN-major
+            const uint32_t sK = smem_u32(smem + BwdSmem::K), sV = smem_u32(smem + BwdSmem::V);
+            auto issue_st = [&](uint32_t a_base, uint32_t b_base, uint32_t d_col) {
+#pragma unroll
+                for (int k = 0; k < D / 16; ++k) {
+                    const uint32_t ao = (k >> 2) * (TN * 128) + (k & 3) * 32;
+                    const uint32_t bo = (k >> 2) * (BQ * 128) + (k & 3) * 32;
+                    umma_f16_ss<1>(tmem + d_col, make_smem_desc_sw128(a_base + ao, 16, 1024),
+                                   make_smem_desc_sw128(b_base + bo, 16, 1024), id_s, k != 0);
+                }
+            };
+            auto issue_acc = [&](uint32_t a_col, uint32_t b_base, uint32_t d_col, bool acc) {
+#pragma unroll
+                for (int k = 0; k < BQ / 16; ++k)
+                    umma_f16_ts(tmem + d_col, tmem + a_col + k * 8,
+                                make_smem_desc_sw128(b_base + k * (16 * 128), BQ * 128, 1024), id_kv, acc || k != 0);
+            };
+            mbar_wait(kv_full, 0);
+            mbar_wait(&qdo_full[0], 0);
+            tc_fence_after();
+            issue_st(sK, smem_u32(smem + BwdSmem::Q), T_S0);
+            umma_commit<1>(&s_full[0]);
+            for (int i = 0; i < n_steps; ++i) {
+                const int st = i & 1;
+                const uint32_t ph2 = (i >> 1) & 1;
+                const uint32_t sQ = smem_u32(smem + BwdSmem::Q + st * QT_BYTES);
+                const uint32_t sDO = smem_u32(smem + BwdSmem::DO + st * QT_BYTES);
+                // dP^T(i) = V dO^T
+                issue_st(sV, sDO, T_DP);
+                umma_commit<1>(dp_full);
+                // dV += P^T dO
+                mbar_wait(&p_ready[st], ph2);
+                tc_fence_after();
+                issue_acc(T_S0 + st * 64, sDO, T_DV, i > 0);
+                // S^T(i+1)
+                if (i + 1 < n_steps) {
+                    const int ns = (i + 1) & 1;
+                    mbar_wait(&qdo_full[ns], ((i + 1) >> 1) & 1);
+                    tc_fence_after();
+                    issue_st(sK, smem_u32(smem + BwdSmem::Q + ns * QT_BYTES), T_S0 + ns * 64);
+                    umma_commit<1>(&s_full[ns]);
+                }
+                // dK += dS^T Q
+                mbar_wait(ds_ready, i & 1);
+                tc_fence_after();
+                issue_acc(T_DP, sQ, T_DK, i > 0);
+                umma_commit<1>(&qdo_empty[st]);
+                // dQ^T(i) = K^T dS^T
+                if (i > 0) { mbar_wait(dq_free, (i - 1) & 1); tc_fence_after(); }
+                {
+                    const uint32_t sDS = smem_u32(smem + BwdSmem::DS + st * QT_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TN / 16; ++k)
+                        umma_f16_ss<1>(tmem + T_DQ, make_smem_desc_sw128(sK + k * (16 * 128), TN * 128, 1024),
+                                       make_smem_desc_sw128(sDS + k * (16 * 128), TN * 128, 1024), id_dq, k != 0);
+                }
+                umma_commit<1>(dq_full);
+                umma_commit<1>(&ds_free[st]);
+            }
+            umma_commit<1>(dkv_done);
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===================== softmax / dS warpgroup: lane = kv row =====================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;          // kv row inside the tile
+        const int kv = kv0 + r;               // local kv index
+        const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+        const float sl2 = f.scale_log2;
+        const float LOG2E = 1.4426950408889634f;
+        for (int i = 0; i < n_steps; ++i) {
+            const int st = i & 1;
+            const int j = i / nq, mq = mq0 + i % nq;
+            const int h = hk * qpk + j;
+            const int q0 = mq * BQ;
+            const float* lse_p = args.lse + (int64_t)h * f.T + s0;
+            const float* del_p = args.delta + (int64_t)h * f.T + s0;
+            const bool edge = (q0 + BQ > len) || (kv0 + TN > len) || (f.causal && q0 < kv0 + TN);
+            uint32_t pk[32];  // P^T row, bf16 pairs
+            // ---- phase A: P^T = exp2(S^T * scale_log2 - lse * log2e)
+            mbar_wait(&s_full[st], (i >> 1) & 1);
+            tc_fence_after();
+            const uint32_t t_s = tmem + T_S0 + st * 64 + lane_off;
+#pragma unroll
+            for (int c = 0; c < BQ; c += 32) {
+                uint32_t x[32];
+                tmem_ld_32x32b_x32(t_s + c, x);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                    const int qa = q0 + c + e, qb = qa + 1;
+                    const float la = __ldg(lse_p + min(qa, len - 1)) * LOG2E, lb = __ldg(lse_p + min(qb, len - 1)) * LOG2E;
+                    float pa = fast_exp2(fmaf(__uint_as_float(x[e]), sl2, -la));
+                    float pb = fast_exp2(fmaf(__uint_as_float(x[e + 1]), sl2, -lb));
+                    if (edge) {
+                        if (qa >= len || kv >= len || (f.causal && kv > qa)) pa = 0.f;
+                        if (qb >= len || kv >= len || (f.causal && kv > qb)) pb = 0.f;
+                    }
+                    pk[(c + e) >> 1] = pack_bf16(pa, pb);
+                }
+            }
+            {
+                uint32_t lo[16], hi[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) { lo[e] = pk[e]; hi[e] = pk[16 + e]; }
+                tmem_st_32x32b_x16(t_s, lo);
+                tmem_st_32x32b_x16(t_s + 16, hi);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_ready[st]);
+            // ---- phase B: dS^T = scale * P^T * (dP^T - delta)
+            mbar_wait(dp_full, i & 1);
+            if (i >= 2) mbar_wait(&ds_free[st], ((i >> 1) - 1) & 1);
+            tc_fence_after();
+            const uint32_t t_dp = tmem + T_DP + lane_off;
+            uint8_t* ds_row = smem + BwdSmem::DS + st * QT_BYTES + r * 128;
+#pragma unroll
+            for (int c = 0; c < BQ; c += 32) {
+                uint32_t x[32];
+                tmem_ld_32x32b_x32(t_dp + c, x);
+                tmem_ld_wait();
+                uint32_t o[16];
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                    const int qa = q0 + c + e;
+                    const float da = __ldg(del_p + min(qa, len - 1)), db = __ldg(del_p + min(qa + 1, len - 1));
+                    const float2 p = unpack_bf16(pk[(c + e) >> 1]);
+                    o[e >> 1] = pack_bf16(f.scale * p.x * (__uint_as_float(x[e]) - da),
+                                          f.scale * p.y * (__uint_as_float(x[e + 1]) - db));
+                }
+                tmem_st_32x32b_x16(t_dp + (c >> 1), o);
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {  // 4 x 16-byte chunks = 32 q values
+                    const int chunk = (c >> 3) + ch;
+                    *reinterpret_cast<uint4*>(ds_row + ((chunk ^ (r & 7)) << 4)) =
+                        make_uint4(o[ch * 4], o[ch * 4 + 1], o[ch * 4 + 2], o[ch * 4 + 3]);
+                }
+            }
+            tmem_st_wait();
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ds_ready);
+        }
+        // ---- epilogue: dV, dK rows of this kv tile
+        mbar_wait(dkv_done, 0);
+        tc_fence_after();
+        const bool valid = kv < len;
+        const int64_t tok = (int64_t)s0 + kv;
+        for (int which = 0; which < 2; ++which) {
+            const uint32_t t_src = tmem + (which == 0 ? T_DV : T_DK) + lane_off;
+            __nv_bfloat16* dst = which == 0 ? args.dv + tok * args.dv_stride_t + (int64_t)hk * args.dv_stride_h
+                                            : args.dk + tok * args.dk_stride_t + (int64_t)hk * args.dk_stride_h;
+#pragma unroll 1
+            for (int c = 0; c < D; c += 32) {
+                uint32_t x[32];
+                tmem_ld_32x32b_x32(t_src + c, x);
+                tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 8) {
+                        uint4 o4;
+                        o4.x = pack_bf16(__uint_as_float(x[e]), __uint_as_float(x[e + 1]));
+                        o4.y = pack_bf16(__uint_as_float(x[e + 2]), __uint_as_float(x[e + 3]));
+                        o4.z = pack_bf16(__uint_as_float(x[e + 4]), __uint_as_float(x[e + 5]));
+                        o4.w = pack_bf16(__uint_as_float(x[e + 6]), __uint_as_float(x[e + 7]));
+                        *reinterpret_cast<uint4*>(dst + c + e) = o4;
+                    }
+                }
+            }
+        }
+    } else if (warp >= 8) {
+        // ===================== dQ reducer warpgroup: lane = head-dim index =====================
+        // dQ^T (d on lanes, q on columns) is transposed through a 32 KB fp32 staging tile and added to the global fp32
+        // accumulator with ONE TMA reduce-add per step (per-element red.global tops out at ~1.3 cycles/lane on the LSU,
+        // i.e. ~6 us per step; the bulk reduce rides the TMA/L2 path instead). Rows past the sequence end carry exact
+        // zeros (their P is masked), so adding them is harmless.
+        const int q = warp & 3;
+        const int d = q * 32 + lane;
+        const uint32_t t_dq = tmem + T_DQ + (static_cast<uint32_t>(q * 32) << 16);
+        float* stage = reinterpret_cast<float*>(smem + BwdSmem::DQ);
+        const bool issuer = (warp == 8 && lane == 0);
+        for (int i = 0; i < n_steps; ++i) {
+            const int j = i / nq, mq = mq0 + i % nq;
+            const int h = hk * qpk + j;
+            const int q0 = mq * BQ;
+            mbar_wait(dq_full, i & 1);
+            tc_fence_after();
+            uint32_t x0[32], x1[32];
+            tmem_ld_32x32b_x32(t_dq, x0);
+            tmem_ld_32x32b_x32(t_dq + 32, x1);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dq_free);  // values are in registers: the MMA may overwrite dQ^T now
+            if (issuer) tma_store_wait_read<0>();  // previous reduce has finished reading the staging tile
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < 32; ++c) stage[c * D + d] = __uint_as_float(x0[c]);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) stage[(c + 32) * D + d] = __uint_as_float(x1[c]);
+            fence_proxy_async();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (issuer) {
+                asm volatile(
+                    "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                    ::"l"(reinterpret_cast<uint64_t>(&tmap_dq)), "r"(smem_u32(stage)), "r"(h * D), "r"(s0 + q0)
+                    : "memory");
+                tma_store_commit();
+            }
+        }
+        if (issuer) tma_store_wait<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<1>(tmem, 512);
+    }
+}
+
+int attn_bwd(const AttnBwdDesc& b, cudaStream_t stream) {
+    const AttnDesc& d = b.f;
+    if (d.D != D) return -10;
+    if (d.T == 0) return 0;
+    CUtensorMap tq, tk, tv, tdo;
+    if (make_tmap_2d_bf16(&tq, d.q, (uint64_t)d.q_stride_t, d.T, (uint64_t)d.q_stride_t, 64, BQ)) return -11;
+    if (make_tmap_2d_bf16(&tk, d.k, (uint64_t)d.k_stride_t, d.T, (uint64_t)d.k_stride_t, 64, TN)) return -11;
+    if (make_tmap_2d_bf16(&tv, d.v, (uint64_t)d.v_stride_t, d.T, (uint64_t)d.v_stride_t, 64, TN)) return -11;
+    if (make_tmap_2d_bf16(&tdo, b.dout, (uint64_t)d.H * D, d.T, (uint64_t)d.H * D, 64, BQ)) return -11;
+    CUtensorMap tdq;
+    if (make_tmap_2d_f32_noswizzle(&tdq, b.dq_acc, (uint64_t)d.H * D, d.T, (uint64_t)d.H * D, D, BQ)) return -11;
+    {
+        const int64_t warps = (int64_t)d.T * d.H;
+        attn_bwd_delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(
+            (const __nv_bfloat16*)b.dout, (const __nv_bfloat16*)d.o, b.delta, d.T, d.H);
+    }
+    AttnBwdArgs a;
+    a.f.o = (__nv_bfloat16*)d.o; a.f.lse = d.lse; a.f.cu_seqlens = d.cu_seqlens; a.f.num_seqs = d.num_seqs;
+    a.f.T = d.T; a.f.H = d.H; a.f.Hkv = d.Hkv;
+    a.f.q_stride_g = d.q_stride_g ? d.q_stride_g : d.q_stride_h * (d.H / d.Hkv);
+    a.f.q_stride_h = d.q_stride_h; a.f.k_stride_h = d.k_stride_h; a.f.v_stride_h = d.v_stride_h;
+    a.f.scale = d.scale; a.f.scale_log2 = d.scale * 1.4426950408889634f; a.f.causal = d.causal;
+    a.lse = d.lse; a.delta = b.delta; a.dq_acc = b.dq_acc;
+    a.dk = (__nv_bfloat16*)b.dk; a.dv = (__nv_bfloat16*)b.dv;
+    a.dk_stride_t = b.dk_stride_t; a.dk_stride_h = b.dk_stride_h; a.dv_stride_t = b.dv_stride_t; a.dv_stride_h = b.dv_stride_h;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::TOTAL) != cudaSuccess)
+            return -12;
+        attr = true;
+    }
+    dim3 grid(upper_qblocks(d.T, d.num_seqs, TN), d.Hkv);
+    attn_bwd_kernel<<<grid, BWD_THREADS, BwdSmem::TOTAL, stream>>>(tq, tk, tv, tdo, tdq, a);
+    {
+        const int qpk = d.H / d.Hkv;
+        const int64_t n = (int64_t)d.T * d.H * (D / 8);
+        const int64_t sg = b.dq_stride_g ? b.dq_stride_g : b.dq_stride_h * qpk;
+        attn_bwd_dq_convert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+            b.dq_acc, (__nv_bfloat16*)b.dq, d.T, d.H, qpk, b.dq_stride_t, sg, b.dq_stride_h);
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : -13;
+}
 
 }  // namespace b200

@@ -26,6 +26,7 @@ struct AttnBwdDesc {
     void* dq = nullptr;          // [T, H, D]
     void* dk = nullptr;          // [T, Hkv, D]
     void* dv = nullptr;          // [T, Hkv, D]
+    int64_t dq_stride_g = 0;  // as q_stride_g
     int64_t dq_stride_t = 0, dq_stride_h = 0, dk_stride_t = 0, dk_stride_h = 0, dv_stride_t = 0, dv_stride_h = 0;
     float* delta = nullptr;   // [H, T] scratch: rowsum(dO * O)
     float* dq_acc = nullptr;  // [T, H, D] fp32 scratch (zero-initialised by the caller)

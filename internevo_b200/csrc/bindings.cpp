@@ -220,9 +220,11 @@ void attn_bwd(const Tensor& dout, const Tensor& q, const Tensor& k, const Tensor
     d.f.cu_seqlens = cu_seqlens.data_ptr<int>(); d.f.num_seqs = cu_seqlens.numel() - 1; d.f.max_seqlen = max_seqlen;
     d.f.scale = (float)scale; d.f.causal = causal;
     TORCH_CHECK(dout.is_contiguous() && out.is_contiguous(), "attn_bwd: dout/out contiguous");
-    TORCH_CHECK(dq.stride(2) == 1 && dk.stride(2) == 1 && dv.stride(2) == 1, "attn_bwd: grads last dim contiguous");
+    TORCH_CHECK(dq.stride(-1) == 1 && dk.stride(2) == 1 && dv.stride(2) == 1, "attn_bwd: grads last dim contiguous");
     d.dout = dout.data_ptr();
-    d.dq = dq.data_ptr(); d.dq_stride_t = dq.stride(0); d.dq_stride_h = dq.stride(1);
+    d.dq = dq.data_ptr(); d.dq_stride_t = dq.stride(0);
+    if (dq.dim() == 4) { d.dq_stride_g = dq.stride(1); d.dq_stride_h = dq.stride(2); }
+    else { d.dq_stride_h = dq.stride(1); d.dq_stride_g = dq.stride(1) * (d.f.H / d.f.Hkv); }
     d.dk = dk.data_ptr(); d.dk_stride_t = dk.stride(0); d.dk_stride_h = dk.stride(1);
     d.dv = dv.data_ptr(); d.dv_stride_t = dv.stride(0); d.dv_stride_h = dv.stride(1);
     d.delta = delta.data_ptr<float>();

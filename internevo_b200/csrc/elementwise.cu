@@ -63,10 +63,10 @@ B200_DEVICE uint4 pack8(const float (&f)[8]) {
 // RMSNorm: one CTA (256 threads) per row, row cached in registers (H <= 256*8*MAXV)
 // ----------------------------------------------------------------------------------------------------------------
 static constexpr int RN_THREADS = 256;
-static constexpr int RN_MAXV = 4;  // up to 8192 columns
 
-// res_out = x (+ res_in);  y = res_out * rstd * w
-__global__ void __launch_bounds__(RN_THREADS) rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+// res_out = x (+ res_in);  y = res_out * rstd * w        (RN_MAXV * 2048 >= H)
+template <int RN_MAXV>
+__global__ void __launch_bounds__(RN_THREADS, RN_MAXV <= 2 ? 3 : 2) rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
                                                                  const __nv_bfloat16* __restrict__ res_in,
                                                                  const __nv_bfloat16* __restrict__ w,
                                                                  __nv_bfloat16* __restrict__ y,
@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(RN_THREADS) rmsnorm_fwd_kernel(const __nv_bflo
 }
 
 // dx = rstd * (dy*w - xhat * mean(dy*w*xhat)) (+ dres);  dw_partial[block] += dy * xhat
-__global__ void __launch_bounds__(RN_THREADS) rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+template <int RN_MAXV>
+__global__ void __launch_bounds__(RN_THREADS, RN_MAXV == 1 ? 4 : (RN_MAXV == 2 ? 2 : 1)) rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
                                                                  const __nv_bfloat16* __restrict__ res,
                                                                  const __nv_bfloat16* __restrict__ w,
                                                                  const float* __restrict__ rstd_in,
@@ -139,13 +140,23 @@ __global__ void __launch_bounds__(RN_THREADS) rmsnorm_bwd_kernel(const __nv_bflo
     for (int row = blockIdx.x; row < rows; row += gridDim.x) {
         const float rstd = rstd_in[row];
         float g[RN_MAXV][8], xh[RN_MAXV][8];
+        uint4 ldy[RN_MAXV], lres[RN_MAXV], ldr[RN_MAXV];
+#pragma unroll
+        for (int i = 0; i < RN_MAXV; ++i) {  // all loads of this row in flight before any use
+            const int idx = threadIdx.x + i * RN_THREADS;
+            if (idx < nvec) {
+                ldy[i] = ld_nc_v4(reinterpret_cast<const uint4*>(dy + (int64_t)row * H) + idx);
+                lres[i] = ld_nc_v4(reinterpret_cast<const uint4*>(res + (int64_t)row * H) + idx);
+                if (dres) ldr[i] = ld_nc_v4(reinterpret_cast<const uint4*>(dres + (int64_t)row * H) + idx);
+            }
+        }
         float dot = 0.f;
 #pragma unroll
         for (int i = 0; i < RN_MAXV; ++i) {
             const int idx = threadIdx.x + i * RN_THREADS;
             if (idx < nvec) {
-                unpack8(reinterpret_cast<const uint4*>(dy + (int64_t)row * H)[idx], g[i]);
-                unpack8(reinterpret_cast<const uint4*>(res + (int64_t)row * H)[idx], xh[i]);
+                unpack8(ldy[i], g[i]);
+                unpack8(lres[i], xh[i]);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     xh[i][j] *= rstd;
@@ -165,7 +176,7 @@ __global__ void __launch_bounds__(RN_THREADS) rmsnorm_bwd_kernel(const __nv_bflo
                 for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - xh[i][j] * dot);
                 if (dres) {
                     float r[8];
-                    unpack8(reinterpret_cast<const uint4*>(dres + (int64_t)row * H)[idx], r);
+                    unpack8(ldr[i], r);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) o[j] += r[j];
                 }
@@ -184,37 +195,54 @@ __global__ void __launch_bounds__(RN_THREADS) rmsnorm_bwd_kernel(const __nv_bflo
     }
 }
 
-// dw[c] (+)= sum_b partial[b, c]
+// dw[c] (+)= sum_b partial[b, c]; block = 32 columns x 8 row-groups (coalesced 128-byte rows, H/32 blocks)
 __global__ void colsum_kernel(const float* __restrict__ partial, float* __restrict__ out_f32,
                               __nv_bfloat16* __restrict__ out_bf16, int nblocks, int H, int accumulate) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= H) return;
+    __shared__ float red[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
     float s = 0.f;
-    for (int b = 0; b < nblocks; ++b) s += partial[(int64_t)b * H + c];
-    if (out_f32) out_f32[c] = accumulate ? out_f32[c] + s : s;
-    if (out_bf16) out_bf16[c] = __float2bfloat16_rn(accumulate ? __bfloat162float(out_bf16[c]) + s : s);
+    if (c < H)
+        for (int b = threadIdx.y; b < nblocks; b += 8) s += partial[(int64_t)b * H + c];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < H) {
+#pragma unroll
+        for (int i = 1; i < 8; ++i) s += red[i][threadIdx.x];
+        if (out_f32) out_f32[c] = accumulate ? out_f32[c] + s : s;
+        if (out_bf16) out_bf16[c] = __float2bfloat16_rn(accumulate ? __bfloat162float(out_bf16[c]) + s : s);
+    }
 }
 
 int rmsnorm_fwd(const void* x, const void* res_in, const void* w, void* y, void* res_out, float* rstd, int rows, int H,
                 float eps, cudaStream_t s) {
-    if (H % 8 != 0 || H > RN_THREADS * 8 * RN_MAXV) return -1;
-    const int grid = rows < 148 * 8 ? rows : 148 * 8;
-    rmsnorm_fwd_kernel<<<grid, RN_THREADS, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res_in,
-                                                   (const __nv_bfloat16*)w, (__nv_bfloat16*)y, (__nv_bfloat16*)res_out,
-                                                   rstd, rows, H, eps);
+    if (H % 8 != 0 || H > RN_THREADS * 8 * 4) return -1;
+    const int grid = rows < 148 * 6 ? rows : 148 * 6;
+#define RN_FWD(MV)                                                                                                   \
+    rmsnorm_fwd_kernel<MV><<<grid, RN_THREADS, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res_in,        \
+                                                       (const __nv_bfloat16*)w, (__nv_bfloat16*)y,                   \
+                                                       (__nv_bfloat16*)res_out, rstd, rows, H, eps)
+    if (H <= 2048) RN_FWD(1);
+    else if (H <= 4096) RN_FWD(2);
+    else RN_FWD(4);
+#undef RN_FWD
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
-int rmsnorm_bwd_blocks(int rows) { return rows < 148 * 4 ? rows : 148 * 4; }
+int rmsnorm_bwd_blocks(int rows) { return rows < 148 * 2 ? rows : 148 * 2; }
 
 int rmsnorm_bwd(const void* dy, const void* res, const void* w, const float* rstd, const void* dres, void* dx,
                 float* dw_partial, float* dw_f32, void* dw_bf16, int accumulate, int rows, int H, cudaStream_t s) {
-    if (H % 8 != 0 || H > RN_THREADS * 8 * RN_MAXV) return -1;
+    if (H % 8 != 0 || H > RN_THREADS * 8 * 4) return -1;
     const int grid = rmsnorm_bwd_blocks(rows);
-    rmsnorm_bwd_kernel<<<grid, RN_THREADS, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)res,
-                                                   (const __nv_bfloat16*)w, rstd, (const __nv_bfloat16*)dres,
-                                                   (__nv_bfloat16*)dx, dw_partial, rows, H);
-    colsum_kernel<<<(H + 255) / 256, 256, 0, s>>>(dw_partial, dw_f32, (__nv_bfloat16*)dw_bf16, grid, H, accumulate);
+#define RN_BWD(MV)                                                                                                   \
+    rmsnorm_bwd_kernel<MV><<<grid, RN_THREADS, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)res,          \
+                                                       (const __nv_bfloat16*)w, rstd, (const __nv_bfloat16*)dres,    \
+                                                       (__nv_bfloat16*)dx, dw_partial, rows, H)
+    if (H <= 2048) RN_BWD(1);
+    else if (H <= 4096) RN_BWD(2);
+    else RN_BWD(4);
+#undef RN_BWD
+    colsum_kernel<<<(H + 31) / 32, dim3(32, 8), 0, s>>>(dw_partial, dw_f32, (__nv_bfloat16*)dw_bf16, grid, H, accumulate);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

@@ -349,6 +349,26 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_
     return 0;
 }
 
+// 2D fp32 tensor map without swizzle (TMA stores / reduce-adds of accumulator tiles)
+int make_tmap_2d_f32_noswizzle(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                               uint32_t box_inner, uint32_t box_outer) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return -1;
+    ensure_context();
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {ld_elems * 4};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "[b200] cuTensorMapEncodeTiled(f32) failed (%d)\n", (int)r);
+        return -2;
+    }
+    return 0;
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
     if (g_num_sms == 0) {

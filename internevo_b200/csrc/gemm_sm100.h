@@ -36,4 +36,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream);
 int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                       uint32_t box_inner, uint32_t box_outer);
 
+int make_tmap_2d_f32_noswizzle(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                               uint32_t box_inner, uint32_t box_outer);
+
 }  // namespace b200

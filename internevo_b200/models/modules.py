@@ -23,7 +23,7 @@ from torch import nn
 from internevo_b200 import ops
 from internevo_b200.core.context import ParallelMode
 from internevo_b200.core.context import global_context as gpc
-from internevo_b200.ops.attention import flash_attention_varlen
+from internevo_b200.ops.attention import flash_attention_packed, flash_attention_varlen
 from internevo_b200.ops.swiglu import swiglu_interleaved_bwd
 from internevo_b200.parallel.functional import (
     gather_forward_split_backward,
@@ -196,6 +196,7 @@ class MHA(nn.Module):
             qkv = qkv.view(T, -1, D)
             qkv = ops.apply_rotary_packed(qkv, indexes, cos, sin, gs, gs - 1, self.interleaved_rope)
             g = qkv.view(T, -1, gs, D)
+            self._packed = g  # consumed by forward(): the native attention kernel reads q/k/v out of this one buffer
             q = g[:, :, : self.q_per_kv]  # [T, Hkv, qpk, D]  (strided view)
             return q, g[:, :, -2], g[:, :, -1]
         if self.layout == "llama":
@@ -219,10 +220,18 @@ class MHA(nn.Module):
         if inference_params is not None:
             return self._forward_decode(x, inference_params, indexes)
         max_pos = int(kwargs.get("max_position", 0)) or (int(max_seqlen) if max_seqlen is not None else x.shape[0])
+        self._packed = None
         q, k, v = self._qkv(x, indexes, max_pos)
         T = q.shape[0]
         D = self.head_dim
         sp_group = self.sequence_process_group if self.tp_mode == "isp" else None
+        packed, self._packed = self._packed, None
+        if packed is not None and not (sp_group is not None and _ws(sp_group) > 1):
+            if cu_seqlens is None:
+                cu_seqlens = torch.tensor([0, T], device=x.device, dtype=torch.int32)
+                max_seqlen = T
+            ctx = flash_attention_packed(packed, cu_seqlens, max_seqlen, causal=self.causal, scale=self.softmax_scale)
+            return self.wo(ctx.reshape(T, -1))
         if q.dim() == 4:  # internlm2 grouped view → [T, H, D] (copy only when a library kernel needs it)
             q = q.reshape(T, -1, D)
         if sp_group is not None and _ws(sp_group) > 1:

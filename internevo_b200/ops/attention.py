@@ -16,7 +16,7 @@ import torch
 from . import _lib
 from .gemm import _bump
 
-_IMPL = os.environ.get("INTERNEVO_ATTN_IMPL", "flash_attn")  # b200 | flash_attn | sdpa
+_IMPL = os.environ.get("INTERNEVO_ATTN_IMPL", "b200")  # b200 | flash_attn | sdpa
 
 
 def set_attention_impl(name: str):
@@ -81,6 +81,56 @@ class _B200AttnFn(torch.autograd.Function):
         torch.ops.b200.attn_bwd(dout, q, k, v, out, lse, dq, dk, dv, delta, dq_acc, cu, max_seqlen, scale, causal)
         _bump(3)
         return dq, dk, dv, None, None, None, None
+
+
+class _B200AttnPackedFn(torch.autograd.Function):
+    """Attention straight on the packed InternLM2 ``wqkv`` output ``[T, kv_heads, q_per_kv + 2, D]`` (post-RoPE).
+
+    q / k / v are strided views of ONE buffer for the TMA descriptors, and the backward kernels write dq / dk / dv into
+    ONE ``dqkv`` buffer of the same layout — no split / concat / zero-fill + add chains in autograd (those cost ~36 ms
+    per 7B step with a q,k,v-separate op, see profiles/step_profile_r1_v1_7B_1gpu.txt)."""
+
+    @staticmethod
+    def forward(ctx, qkv, cu_seqlens, max_seqlen, scale, causal):
+        T, G, gs, D = qkv.shape
+        H = G * (gs - 2)
+        out = torch.empty(T, H, D, device=qkv.device, dtype=qkv.dtype)
+        lse = torch.empty(H, T, device=qkv.device, dtype=torch.float32)
+        torch.ops.b200.attn_fwd(qkv[:, :, : gs - 2], qkv[:, :, gs - 2], qkv[:, :, gs - 1], out, lse, cu_seqlens,
+                                max_seqlen, scale, causal)
+        _bump()
+        ctx.save_for_backward(qkv, out, lse, cu_seqlens)
+        ctx.cfg = (max_seqlen, scale, causal)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse, cu = ctx.saved_tensors
+        max_seqlen, scale, causal = ctx.cfg
+        T, G, gs, D = qkv.shape
+        H = G * (gs - 2)
+        dqkv = torch.empty_like(qkv)
+        delta = torch.empty(H, T, device=qkv.device, dtype=torch.float32)
+        dq_acc = torch.zeros(T, H, D, device=qkv.device, dtype=torch.float32)
+        torch.ops.b200.attn_bwd(dout.contiguous(), qkv[:, :, : gs - 2], qkv[:, :, gs - 2], qkv[:, :, gs - 1], out, lse,
+                                dqkv[:, :, : gs - 2], dqkv[:, :, gs - 2], dqkv[:, :, gs - 1], delta, dq_acc, cu,
+                                max_seqlen, scale, causal)
+        _bump(3)
+        return dqkv, None, None, None, None
+
+
+def flash_attention_packed(qkv: torch.Tensor, cu_seqlens, max_seqlen: int, causal: bool = True,
+                           scale: Optional[float] = None, impl: Optional[str] = None) -> torch.Tensor:
+    """``qkv`` ``[T, kv_heads, q_per_kv + 2, D]`` → ``[T, H, D]``; native kernel on the packed buffer when possible."""
+    T, G, gs, D = qkv.shape
+    scale = scale or 1.0 / math.sqrt(D)
+    impl = impl or _IMPL
+    if qkv.is_cuda and impl == "b200" and qkv.dtype == torch.bfloat16 and D == 128 and _b200_available():
+        if cu_seqlens.dtype != torch.int32:
+            cu_seqlens = cu_seqlens.int()
+        return _B200AttnPackedFn.apply(qkv, cu_seqlens.contiguous(), int(max_seqlen), float(scale), bool(causal))
+    q = qkv[:, :, : gs - 2].reshape(T, G * (gs - 2), D)
+    return flash_attention_varlen(q, qkv[:, :, gs - 2], qkv[:, :, gs - 1], cu_seqlens, max_seqlen, causal, scale, impl)
 
 
 _b200_attn_ok: Optional[bool] = None

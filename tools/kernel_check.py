@@ -273,7 +273,7 @@ def check_attn():
         q = torch.randn(T, H, D, device=dev, dtype=torch.bfloat16, requires_grad=True)
         k = torch.randn(T, Hkv, D, device=dev, dtype=torch.bfloat16, requires_grad=True)
         v = torch.randn(T, Hkv, D, device=dev, dtype=torch.bfloat16, requires_grad=True)
-        out = flash_attention_varlen(q, k, v, cu, max(seqs), causal=True)
+        out = flash_attention_varlen(q, k, v, cu, max(seqs), causal=True, impl="b200")
         dout = torch.randn_like(out)
         out.backward(dout)
         qf, kf, vf = [t.detach().float().requires_grad_(True) for t in (q, k, v)]
@@ -283,6 +283,16 @@ def check_attn():
         ok &= err_report("attn dq", q.grad.flatten(1), qf.grad.flatten(1), 3e-2)
         ok &= err_report("attn dk", k.grad.flatten(1), kf.grad.flatten(1), 3e-2)
         ok &= err_report("attn dv", v.grad.flatten(1), vf.grad.flatten(1), 3e-2)
+        # packed qkv path (one buffer in, one gradient buffer out)
+        from internevo_b200.ops.attention import flash_attention_packed
+        qpk = H // Hkv
+        qkv = torch.cat([q.detach().view(T, Hkv, qpk, D), k.detach()[:, :, None], v.detach()[:, :, None]], 2).contiguous().requires_grad_(True)
+        outp = flash_attention_packed(qkv, cu, max(seqs), causal=True, impl="b200")
+        outp.backward(dout)
+        ok &= err_report("attn packed fwd", outp.flatten(1), ref.flatten(1), 2e-2)
+        ok &= err_report("attn packed dq", qkv.grad[:, :, :qpk].reshape(T, -1), qf.grad.flatten(1), 3e-2)
+        ok &= err_report("attn packed dk", qkv.grad[:, :, qpk].reshape(T, -1), kf.grad.flatten(1), 3e-2)
+        ok &= err_report("attn packed dv", qkv.grad[:, :, qpk + 1].reshape(T, -1), vf.grad.flatten(1), 3e-2)
     print("ATTN_ALL_OK" if ok else "ATTN_HAS_FAILURES", flush=True)
     # speed: 7B shape, T=4096 one sequence and 16k
     for S in (4096, 16384):
@@ -291,10 +301,10 @@ def check_attn():
         q = torch.randn(S, H, D, device=dev, dtype=torch.bfloat16, requires_grad=True)
         k = torch.randn(S, Hkv, D, device=dev, dtype=torch.bfloat16, requires_grad=True)
         v = torch.randn(S, Hkv, D, device=dev, dtype=torch.bfloat16, requires_grad=True)
-        ms = timeit(lambda: flash_attention_varlen(q, k, v, cu, S, causal=True))
+        ms = timeit(lambda: flash_attention_varlen(q, k, v, cu, S, causal=True, impl="b200"))
         fl = 4 * S * S * H * D / 2
         print(f"  attn fwd S={S}: {ms:.3f} ms {fl / ms / 1e9:.0f} TFLOP/s (causal flops)")
-        out = flash_attention_varlen(q, k, v, cu, S, causal=True)
+        out = flash_attention_varlen(q, k, v, cu, S, causal=True, impl="b200")
         dout = torch.randn_like(out)
         ms = timeit(lambda: out.backward(dout, retain_graph=True))
         print(f"  attn bwd S={S}: {ms:.3f} ms {2.5 * fl / ms / 1e9:.0f} TFLOP/s")
@@ -302,6 +312,9 @@ def check_attn():
             from flash_attn import flash_attn_varlen_func
             ms = timeit(lambda: flash_attn_varlen_func(q, k, v, cu, cu, S, S, causal=True))
             print(f"  flash_attn lib fwd S={S}: {ms:.3f} ms {fl / ms / 1e9:.0f} TFLOP/s")
+            o2 = flash_attn_varlen_func(q, k, v, cu, cu, S, S, causal=True)
+            ms = timeit(lambda: o2.backward(dout, retain_graph=True))
+            print(f"  flash_attn lib bwd S={S}: {ms:.3f} ms {2.5 * fl / ms / 1e9:.0f} TFLOP/s")
         except Exception as e:  # noqa
             print("  flash_attn lib unavailable:", repr(e)[:200])
     return ok
