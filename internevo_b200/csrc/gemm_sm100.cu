@@ -58,12 +58,137 @@ B200_DEVICE void tile_coords(int tile, int tiles_m, int tiles_n, int& m, int& n)
     n = r / gsize;
 }
 
+struct CommKernelArgs {
+    int mode;
+    void* const* peer_ptrs;
+    uint32_t* const* flags_ptrs;
+    void* const* out_ptrs;
+    int rank, world;
+    uint32_t epoch;
+    int m_local;          // rows per rank
+    void* out_local;
+    int64_t ld_out;
+    int gemm_ctas;        // CTAs [0, gemm_ctas) run the GEMM, the rest run the communication role
+    int64_t ld_peer;      // row stride (elements) of the peer buffers
+};
+
+B200_DEVICE uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+B200_DEVICE void st_release_gpu(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+B200_DEVICE void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+B200_DEVICE uint4 ld_v4_volatile(const void* p) {
+    uint4 r;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// Rotation of the m-tile order: AG starts on the local shard, RS/AR finishes on it (peers get their rows first).
+B200_DEVICE int comm_remap_m(int m, int tiles_m, const CommKernelArgs& c) {
+    if (c.mode == GEMM_COMM_NONE) return m;
+    const int per = tiles_m / c.world;
+    const int shift = (c.mode == GEMM_COMM_ALL_GATHER ? c.rank : c.rank + 1) * per;
+    return (m + shift) % tiles_m;
+}
+
+// ---- communication role: runs in CTAs [gemm_ctas, gridDim.x) of the SAME kernel ------------------------------------
 template <int BN>
+B200_DEVICE void comm_role(const GemmKernelArgs& args, const CommKernelArgs& c) {
+    const int cta = blockIdx.x - c.gemm_ctas, ncta = gridDim.x - c.gemm_ctas;
+    uint32_t* my_flags = c.flags_ptrs[c.rank];
+    const int tiles_m = args.tiles_m, tiles_n = args.tiles_n;
+    const int per = tiles_m / c.world;  // m-tiles per rank
+    if (c.mode == GEMM_COMM_ALL_GATHER) {
+        // copy 128-row chunks of every rank's shard into the local gathered A (local shard first), flag each chunk
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(c.out_local);
+        const int K = args.K;
+        const int vec_per_row = K / 8;
+        for (int ch = cta; ch < tiles_m; ch += ncta) {
+            const int m = comm_remap_m(ch, tiles_m, c);  // same order in which the GEMM consumes
+            const int src_rank = m / per;
+            const int row0 = m * BM;
+            const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(c.peer_ptrs[src_rank]) +
+                                       (int64_t)(row0 - src_rank * c.m_local) * c.ld_peer;
+            const int rows = min(BM, args.M - row0);
+            for (int v = threadIdx.x; v < rows * vec_per_row; v += NUM_THREADS) {
+                const int r = v / vec_per_row, cc = (v - r * vec_per_row) * 8;
+                const uint4 x = ld_v4_volatile(src + (int64_t)r * c.ld_peer + cc);
+                *reinterpret_cast<uint4*>(dst + (int64_t)(row0 + r) * c.ld_out + cc) = x;
+            }
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                fence_proxy_async_global();  // generic-proxy stores above -> TMA (async proxy) reads in the GEMM CTAs
+                st_release_gpu(my_flags + m, c.epoch);
+            }
+        }
+        return;
+    }
+    // REDUCE_SCATTER / ALL_REDUCE: reduce the tiles of my row slice as soon as every rank has produced them
+    const int my_m0 = c.rank * per;
+    const int n_mine = per * tiles_n;
+    for (int t = cta; t < n_mine; t += ncta) {
+        // visit my tiles in the order the producers emit them (m rotates, n fastest inside the GROUP_M raster is
+        // irrelevant here: every producer finishes my slice early because of comm_remap_m)
+        const int tm = my_m0 + t / tiles_n, tn = t % tiles_n;
+        const int tile = tm * tiles_n + tn;
+        if (threadIdx.x < c.world) {
+            const uint32_t* f = my_flags + (int64_t)threadIdx.x * tiles_m * tiles_n + tile;
+            while (static_cast<int32_t>(ld_acquire_sys(f) - c.epoch) < 0) {
+            }
+        }
+        __syncthreads();
+        const int row0 = tm * BM, col0 = tn * BN;
+        const int rows = min(BM, args.M - row0), cols = min(BN, args.N - col0);
+        const int vec_per_row = cols / 8;
+        for (int v = threadIdx.x; v < rows * vec_per_row; v += NUM_THREADS) {
+            const int r = v / vec_per_row, cc = (v - r * vec_per_row) * 8;
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int p = 0; p < c.world; ++p) {
+                const int pr = (c.rank + p) % c.world;
+                const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(c.peer_ptrs[pr]) +
+                                           (int64_t)(row0 + r) * c.ld_peer + col0 + cc;
+                const uint4 x = ld_v4_volatile(src);
+                float2 a = unpack_bf16(x.x), b = unpack_bf16(x.y), cq = unpack_bf16(x.z), d = unpack_bf16(x.w);
+                acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+                acc[4] += cq.x; acc[5] += cq.y; acc[6] += d.x; acc[7] += d.y;
+            }
+            uint4 o;
+            o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
+            o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
+            if (c.mode == GEMM_COMM_REDUCE_SCATTER) {
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(c.out_local) +
+                                     (int64_t)(row0 - my_m0 * BM + r) * c.ld_out + col0 + cc;
+                *reinterpret_cast<uint4*>(dst) = o;
+            } else {
+                for (int p = 0; p < c.world; ++p) {
+                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(c.out_ptrs[(c.rank + p) % c.world]) +
+                                         (int64_t)(row0 + r) * c.ld_out + col0 + cc;
+                    *reinterpret_cast<uint4*>(dst) = o;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int BN, bool COMM>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const GemmKernelArgs args) {
+                 const GemmKernelArgs args, const CommKernelArgs comm) {
     using Cfg = GemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
+    if constexpr (COMM) {
+        if (static_cast<int>(blockIdx.x) >= comm.gemm_ctas) {
+            comm_role<BN>(args, comm);
+            return;
+        }
+    }
+    const int grid_ctas = COMM ? comm.gemm_ctas : static_cast<int>(gridDim.x);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -105,9 +230,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; tile < num_tiles; tile += grid_ctas) {
                 int tm, tn;
                 tile_coords(tile, args.tiles_m, args.tiles_n, tm, tn);
+                if constexpr (COMM) {
+                    tm = comm_remap_m(tm, args.tiles_m, comm);
+                    if (comm.mode == GEMM_COMM_ALL_GATHER) {
+                        // rows of this tile are being pulled from their owner by the communication CTAs
+                        const uint32_t* f = comm.flags_ptrs[comm.rank] + tm;
+                        while (static_cast<int32_t>(ld_acquire_gpu(f) - comm.epoch) < 0) {
+                        }
+                        fence_proxy_async_global();
+                    }
+                }
                 const int m0 = tm * BM, n0 = tn * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -146,7 +281,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; tile < num_tiles; tile += grid_ctas) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -177,9 +312,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const bool accumulate = args.flags & GEMM_ACCUMULATE;
         const bool swiglu = args.flags & GEMM_SWIGLU;
         const bool no_store_d = args.flags & GEMM_SKIP_D;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < num_tiles; tile += grid_ctas) {
             int tm, tn;
             tile_coords(tile, args.tiles_m, args.tiles_n, tm, tn);
+            if constexpr (COMM) tm = comm_remap_m(tm, args.tiles_m, comm);
             const int row = tm * BM + q * 32 + lane;
             const int n0 = tn * BN;
             mbar_wait(&tmem_full[acc], acc_phase);
@@ -275,6 +411,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if constexpr (COMM) {
+                if (comm.mode == GEMM_COMM_REDUCE_SCATTER || comm.mode == GEMM_COMM_ALL_REDUCE) {
+                    // the partial tile is in (symmetric) global memory: tell the owner of these rows
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (warp == 2 && lane == 0) {
+                        const int owner = tm / (args.tiles_m / comm.world);
+                        fence_acq_rel_sys();
+                        st_release_sys(comm.flags_ptrs[owner] + (int64_t)comm.rank * args.tiles_m * args.tiles_n +
+                                           tm * args.tiles_n + tn,
+                                       comm.epoch);
+                    }
+                }
+            }
         }
     }
 
@@ -408,7 +557,7 @@ static int launch(const GemmDesc& g, cudaStream_t stream) {
 
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::SMEM_BYTES);
         if (e != cudaSuccess) {
             fprintf(stderr, "[b200] cudaFuncSetAttribute(smem=%d) failed: %s\n", Cfg::SMEM_BYTES, cudaGetErrorString(e));
@@ -416,13 +565,57 @@ static int launch(const GemmDesc& g, cudaStream_t stream) {
         }
         attr_set = true;
     }
-    gemm_bf16_kernel<BN><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, a);
+    gemm_bf16_kernel<BN, false><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, a, CommKernelArgs{});
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         fprintf(stderr, "[b200] gemm launch failed: %s\n", cudaGetErrorString(e));
         return -4;
     }
     return 0;
+}
+
+// GEMM + communication CTAs in one launch. A (AG) / D (RS, AR) live in symmetric memory; see GemmCommArgs.
+int gemm_bf16_comm(const GemmDesc& g, const GemmCommArgs& c, cudaStream_t stream) {
+    constexpr int BN = 256;
+    using Cfg = GemmCfg<BN>;
+    if (c.world < 2 || g.a_mn_major) return -20;
+    const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
+    if (g.M % (BM * c.world) != 0) return -21;  // every rank owns whole 128-row tiles
+    if (g.N % 8 != 0 || g.K % 8 != 0) return -22;
+    CUtensorMap ta, tb;
+    int rc;
+    const void* a_ptr = c.mode == GEMM_COMM_ALL_GATHER ? c.out_local : g.A;
+    const int64_t a_ld = c.mode == GEMM_COMM_ALL_GATHER ? c.ld_out : g.lda;
+    rc = make_tmap_2d_bf16(&ta, a_ptr, g.K, g.M, a_ld, BK, BM);
+    if (rc) return rc;
+    if (!g.b_mn_major) rc = make_tmap_2d_bf16(&tb, g.B, g.K, g.N, g.ldb, BK, BN);
+    else               rc = make_tmap_2d_bf16(&tb, g.B, g.N, g.K, g.ldb, 64, BK);
+    if (rc) return rc;
+    GemmKernelArgs a;
+    a.M = g.M; a.N = g.N; a.K = g.K;
+    a.D = g.D; a.ldd = g.ldd;
+    a.bias = nullptr; a.H = g.H; a.ldh = g.ldh; a.flags = g.flags;
+    a.a_mn = 0; a.b_mn = g.b_mn_major;
+    a.tiles_m = tiles_m; a.tiles_n = tiles_n;
+    CommKernelArgs k;
+    k.mode = c.mode; k.peer_ptrs = c.peer_ptrs; k.flags_ptrs = c.flags_ptrs; k.out_ptrs = c.out_ptrs;
+    k.rank = c.rank; k.world = c.world; k.epoch = c.epoch; k.m_local = (int)c.m_local;
+    k.out_local = c.out_local; k.ld_out = c.ld_out;
+    k.ld_peer = c.mode == GEMM_COMM_ALL_GATHER ? g.lda : g.ldd;
+    const int sms = num_sms();
+    const int comm_ctas = c.comm_ctas > 0 ? c.comm_ctas : 16;
+    int gemm_ctas = sms - comm_ctas;
+    if (gemm_ctas > tiles_m * tiles_n) gemm_ctas = tiles_m * tiles_n;
+    k.gemm_ctas = gemm_ctas;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(gemm_bf16_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg::SMEM_BYTES) != cudaSuccess)
+            return -3;
+        attr_set = true;
+    }
+    gemm_bf16_kernel<BN, true><<<gemm_ctas + comm_ctas, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, a, k);
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
 int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {

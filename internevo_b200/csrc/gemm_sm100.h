@@ -33,6 +33,29 @@ struct GemmDesc {
 
 int gemm_bf16(const GemmDesc& g, cudaStream_t stream);
 
+// ---- GEMM with communication CTAs in the same launch (tensor parallel fused paths) ------------------------------
+enum GemmCommMode : int {
+    GEMM_COMM_NONE = 0,
+    GEMM_COMM_ALL_GATHER = 1,      // A = all-gather of per-rank row shards, pulled from peers while early tiles compute
+    GEMM_COMM_REDUCE_SCATTER = 2,  // D partial -> each rank reduces its row slice from all peers' partials
+    GEMM_COMM_ALL_REDUCE = 3,      // as above, reduced rows are pushed into every peer's output
+};
+
+struct GemmCommArgs {
+    int mode = GEMM_COMM_NONE;
+    void* const* peer_ptrs = nullptr;      // AG: per-rank x shard [m_local, K]; RS/AR: per-rank partial D [M, N]
+    uint32_t* const* flags_ptrs = nullptr; // per-rank flag arrays (uint32, >= 2 * tiles + 16 entries)
+    void* const* out_ptrs = nullptr;       // AR: per-rank final output [M, N]
+    int rank = 0, world = 1;
+    uint32_t epoch = 0;
+    int64_t m_local = 0;                   // rows per rank (AG: contributed, RS: owned)
+    void* out_local = nullptr;             // AG: gathered A [M, K]; RS: reduced rows [m_local, N]
+    int64_t ld_out = 0;
+    int comm_ctas = 16;
+};
+
+int gemm_bf16_comm(const GemmDesc& g, const GemmCommArgs& c, cudaStream_t stream);
+
 int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                       uint32_t box_inner, uint32_t box_outer);
 

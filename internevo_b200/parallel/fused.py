@@ -1,0 +1,224 @@
+"""Fused compute+collective back-ends over the symmetric peer-memory heap.
+
+* ``TPFusedBackend``  — tensor-parallel linears: ``ag_gemm`` (all-gather → GEMM, sequence-parallel column linear) and
+  ``gemm_rs`` (GEMM → reduce-scatter / all-reduce, row linear).  One kernel launch each: the tcgen05 GEMM runs on most
+  SMs while the remaining CTAs of the same grid pull / reduce tiles over NVLink with per-tile flags, so the transfer
+  overlaps the math tile by tile (reference sites N1/N3/N4, ``internlm/model/utils.py:25-217``).
+* ``ZeroFusedBackend`` — Hybrid-ZeRO step: reduce-scatter by peer loads fused with mean + bf16 cast + grad-norm partials,
+  then AdamW fused with the parameter all-gather (bf16 results are stored straight into every peer's arena)
+  (reference sites N11/N13, ``internlm/solver/optimizer/hybrid_zero_optim.py:455-523,809-837``).
+
+NCCL implementations of the same operations stay available as fall-back and numerical oracle
+(``parallel/linear.py``, ``HybridZeroOptimizer`` without ``fused_comm``).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from internevo_b200.ops.gemm import _bump
+from internevo_b200.utils.logger import get_logger
+
+from . import symm
+
+logger = get_logger(__file__)
+
+
+class TPFusedBackend:
+    """Symmetric scratch + launch logic for the fused TP linears of one process group."""
+
+    def __init__(self, group: dist.ProcessGroup, comm_ctas: int = 16):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.flags = symm.flags_for(group)
+        self.comm_ctas = comm_ctas
+        self._x: Dict[Tuple[int, int], list] = {}        # (m_local, K) -> [SymmBuffer, SymmBuffer] ping-pong
+        self._partial: Dict[Tuple[int, int], list] = {}  # (M, N) -> ping-pong partial-product buffers
+        self._out: Dict[Tuple[int, int], list] = {}      # (M, N) -> ping-pong all-reduce outputs
+        self._tick = 0
+
+    def supports(self, M: int, x: torch.Tensor, weight: torch.Tensor) -> bool:
+        """whole 128-row tiles per rank, bf16, 16-byte aligned rows"""
+        return (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and M % (128 * self.world) == 0
+                and x.shape[1] % 8 == 0 and weight.shape[0] % 8 == 0 and x.stride(1) == 1 and weight.stride(1) == 1)
+
+    def _pp(self, cache, key, numel):
+        if key not in cache:
+            cache[key] = [symm.SymmBuffer(numel, torch.bfloat16, self.group, zero=False) for _ in range(2)]
+        self._tick += 1
+        return cache[key][self._tick & 1]
+
+    # -- all-gather -> GEMM -----------------------------------------------------------------------------------------
+    def ag_gemm(self, x: torch.Tensor, weight: torch.Tensor, group=None, keep_gathered: bool = False):
+        """``all_gather(x, dim=0) @ weight^T``; returns ``(y, gathered_x)``."""
+        m_local, K = x.shape
+        N = weight.shape[0]
+        M = m_local * self.world
+        xs = self._pp(self._x, (m_local, K), m_local * K)
+        xs.tensor.view(m_local, K).copy_(x)  # publish this rank's shard in peer-visible memory
+        gathered = torch.empty(M, K, device=x.device, dtype=x.dtype)
+        out = torch.empty(M, N, device=x.device, dtype=x.dtype)
+        self.flags.barrier()  # every shard is published (and the previous user of this scratch slot is done)
+        torch.ops.b200.ag_gemm(xs.tensor.view(m_local, K), xs.table_ptr(0), symm.ag_flag_table(self.flags), self.rank,
+                               self.world, self.flags.next_epoch(), weight, False, gathered, out, 0, None,
+                               self.comm_ctas)
+        _bump(2)
+        return out, gathered
+
+    # -- GEMM -> reduce-scatter / all-reduce ------------------------------------------------------------------------------
+    def gemm_rs(self, x: torch.Tensor, weight: torch.Tensor, group=None, all_reduce: bool = False) -> torch.Tensor:
+        """``reduce_scatter(x @ weight^T, dim=0)`` (or all-reduce)."""
+        M, K = x.shape
+        N = weight.shape[0]
+        part = self._pp(self._partial, (M, N), M * N)
+        if all_reduce:
+            outb = self._pp(self._out, (M, N), M * N)
+            out = outb.tensor.view(M, N)
+            out_ptrs = outb.table_ptr(0)
+        else:
+            out = torch.empty(M // self.world, N, device=x.device, dtype=x.dtype)
+            out_ptrs = 0
+        self.flags.barrier()  # scratch slot is free on every rank
+        torch.ops.b200.gemm_rs(x, weight, part.tensor.view(M, N), out, part.table_ptr(0), out_ptrs,
+                               symm.rs_flag_table(self.flags), self.rank, self.world, self.flags.next_epoch(), False,
+                               1 if all_reduce else 0, self.comm_ctas)
+        _bump(2)
+        if all_reduce:
+            self.flags.barrier()  # every rank has pushed its slice into everybody's output
+            return out.clone()  # detach from the ping-pong slot (it is recycled two calls later)
+        return out
+
+
+_tp_backends: Dict[int, TPFusedBackend] = {}
+
+
+def enable_tp(group: Optional[dist.ProcessGroup]) -> Optional[TPFusedBackend]:
+    """Create (once) the fused backend for ``group`` and route the TP linears through it."""
+    if group is None or dist.get_world_size(group) <= 1 or not symm.symm_available():
+        return None
+    key = id(group)
+    if key not in _tp_backends:
+        _tp_backends[key] = TPFusedBackend(group)
+    from . import linear
+
+    linear.set_fused_backend(_tp_backends[key])
+    return _tp_backends[key]
+
+
+class ZeroFusedBackend:
+    """Fused reduce-scatter + AdamW + all-gather for ``HybridZeroOptimizer`` groups whose ZeRO group is the DP group."""
+
+    def __init__(self, opt):
+        from internevo_b200.core.context import global_context as gpc
+
+        self.gpc = gpc
+        self.groups = {}
+        for g in opt.groups:
+            if not g.params or g.zero_size <= 1 or g.dtype is not torch.bfloat16:
+                continue
+            same = g.zero_size == g.dp_size and gpc.get_ranks_in_group(g.dp_mode) == gpc.get_ranks_in_group(g.zero_mode)
+            if not same or g.zero_size not in (2, 4, 8):
+                continue
+            group = gpc.get_group(g.zero_mode)
+            # move both arenas into symmetric memory (parameters and grad_buf views are re-pointed)
+            pbuf = symm.SymmBuffer(g.total, torch.bfloat16, group, zero=False)
+            gbuf = symm.SymmBuffer(g.total, torch.bfloat16, group, zero=True)
+            pbuf.tensor.copy_(g.param_arena)
+            g.param_arena, g.grad_arena = pbuf.tensor, gbuf.tensor
+            for p in g.ordered:
+                o = g.offsets[id(p)]
+                p.data = g.param_arena[o: o + p.numel()].view(p.shape)
+                p.grad_buf = g.grad_arena[o: o + p.numel()].view(p.shape)
+            self.groups[g.gid] = (pbuf, gbuf, symm.flags_for(group))
+        if gpc.is_rank_for_log():
+            logger.info(f"fused Hybrid-ZeRO over peer memory enabled for groups {[opt.groups[i].name for i in self.groups]}")
+
+    @staticmethod
+    def try_create(opt):
+        if not symm.symm_available():
+            return None
+        try:
+            be = ZeroFusedBackend(opt)
+        except Exception as e:  # pragma: no cover - depends on driver / topology
+            logger.warning(f"fused ZeRO backend unavailable ({e}); using NCCL")
+            return None
+        return be if be.groups else None
+
+    def step(self, opt):
+        from internevo_b200 import ops
+
+        scale = opt.grad_scaler.scale
+        active = [g for g in opt.groups if g.params]
+        for g in active:
+            opt._collect_grads(g)
+            opt._reduce_replica_grads(g)
+        for g in active:
+            if g.gid in self.groups:
+                pbuf, gbuf, flags = self.groups[g.gid]
+                flags.barrier()  # every rank's backward has written its gradient arena
+                g.scalars.zero_()
+                torch.ops.b200.reduce_scatter_adam(gbuf.table_ptr(0), pbuf.table_ptr(0), flags.table_ptr(0), g.zero_rank,
+                                                   g.zero_size, 0, g.lo, g.shard, g.master, g.exp_avg, g.exp_avg_sq,
+                                                   g.scalars, 0.0, 0.9, 0.95, 1e-8, 0.0, 1.0, 1.0, float(g.zero_size), 0)
+                _bump()
+            else:
+                opt._sync_grads(g)
+        for g in active:
+            ops.clip_scalars_(self._sumsq(opt, g), g.scalars, scale, opt._clip_grad_norm)
+        if len(active) > 1:
+            flag = torch.stack([g.scalars[1] for g in active]).max()
+            for g in active:
+                g.scalars[1] = flag
+        for g in active:
+            cfg = g.cfg
+            if g.gid in self.groups:
+                pbuf, gbuf, flags = self.groups[g.gid]
+                beta1, beta2 = cfg.get("betas", (0.9, 0.95))
+                g.step += 1
+                torch.ops.b200.reduce_scatter_adam(gbuf.table_ptr(0), pbuf.table_ptr(0), flags.table_ptr(0), g.zero_rank,
+                                                   g.zero_size, 0, g.lo, g.shard, g.master, g.exp_avg, g.exp_avg_sq,
+                                                   g.scalars, cfg["lr"], beta1, beta2, cfg.get("eps", 1e-8),
+                                                   cfg.get("weight_decay", 0.0), 1.0 - beta1 ** g.step,
+                                                   1.0 - beta2 ** g.step, 1.0, 1)
+                _bump()
+                flags.barrier()  # all parameter pushes have landed before anyone starts the next forward
+            else:
+                opt._update(g)
+                opt._sync_params(g)
+        host = torch.stack([g.scalars for g in active]).cpu()
+        found_inf = bool((host[:, 1] != 0).any())
+        norms = {g.name: float(host[i, 2]) for i, g in enumerate(active)}
+        opt.grad_scaler.update(found_inf)
+        opt.zero_grad()
+        if found_inf:
+            for g in active:
+                g.step -= 1
+            return False, {k: -1.0 for k in norms}
+        return True, norms
+
+    def _sumsq(self, opt, g):
+        """Σ grad² for the clip: the fused reduce already left this rank's partial in ``scalars[3]``."""
+        if g.gid not in self.groups:
+            return opt._group_sumsq(g)
+        from internevo_b200.core.context import ParallelMode
+
+        gpc = self.gpc
+        g.sumsq.copy_(g.scalars[3:4])
+        # replica parameters are counted once per tensor-parallel group: subtract them on tp_rank != 0
+        model_mode = ParallelMode.WEIGHT if opt.use_isp else ParallelMode.TENSOR
+        rep_lo = max(g.replica_start, g.lo) - g.lo
+        if gpc.get_local_rank(model_mode) != 0 and rep_lo < g.shard:
+            from internevo_b200 import ops
+
+            rep = torch.zeros(1, device=g.sumsq.device)
+            ops.sumsq_(g.owned_grad()[rep_lo:], rep)
+            g.sumsq -= rep
+        dist.all_reduce(g.sumsq, group=gpc.get_group(g.zero_mode))
+        if gpc.get_world_size(model_mode) > 1:
+            dist.all_reduce(g.sumsq, group=gpc.get_group(model_mode))
+        if gpc.get_world_size(ParallelMode.PIPELINE) > 1:
+            dist.all_reduce(g.sumsq, group=gpc.get_group(ParallelMode.PIPELINE))
+        return g.sumsq

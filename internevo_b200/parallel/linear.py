@@ -72,7 +72,7 @@ class _ParallelLinearFn(torch.autograd.Function):
         fused = _fused_backend if (_fused_backend is not None and ws > 1 and x.is_cuda) else None
         if kind == "column":
             if sp:
-                if fused is not None and bias is None:
+                if fused is not None and bias is None and fused.supports(x.shape[0] * ws, x, weight):
                     y, x_full = fused.ag_gemm(x, weight, group, keep_gathered=(mode == "msp"))
                 else:
                     x_full, _ = all_gather_raw(x, group)
@@ -82,7 +82,7 @@ class _ParallelLinearFn(torch.autograd.Function):
                 y = _mm(x, weight, bias)
                 ctx.save_for_backward(x, weight)
         else:  # row
-            if fused is not None and bias is None and ws > 1:
+            if fused is not None and bias is None and ws > 1 and fused.supports(x.shape[0], x, weight):
                 y = fused.gemm_rs(x, weight, group, all_reduce=not sp)
             else:
                 y = _mm(x, weight, bias)

@@ -1,0 +1,110 @@
+"""Symmetric peer-memory heap over NVLink / NVSwitch.
+
+``torch.distributed._symmetric_memory`` is used ONLY for the plumbing (cuMem allocation, handle exchange over the
+process group's store, peer mapping); it hands back one base pointer per rank.  Everything that moves data through those
+pointers — barriers, reduce-scatter, all-gather, the GEMM-fused collectives — is our own kernel code
+(``csrc/comm_kernels.cu``, ``csrc/gemm_sm100.cu``).
+
+A ``SymmBuffer`` is one symmetric allocation (same size on every rank of the group) plus device-resident pointer tables;
+``SymmFlags`` is a symmetric ``uint32`` array with a monotonically increasing epoch: a flag is "set" when it holds a
+value ``>=`` the epoch of the operation, so flags never need to be cleared between operations.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+_BARRIER_SLOTS = 1024        # [0, 1024): barrier flags (one slot per peer)
+_AG_BASE = 1024              # [1024, 8192): all-gather chunk flags (local)
+_RS_BASE = 8192              # [8192, ...): reduce-scatter tile flags, `world` blocks of tiles each
+FLAG_WORDS = 8192 + 8 * 8192
+
+
+def symm_available() -> bool:
+    if not torch.cuda.is_available():
+        return False
+    try:
+        import torch.distributed._symmetric_memory  # noqa: F401
+
+        return True
+    except Exception:
+        return False
+
+
+class SymmBuffer:
+    """A symmetric allocation of ``numel`` elements of ``dtype`` on every rank of ``group``."""
+
+    def __init__(self, numel: int, dtype: torch.dtype, group: dist.ProcessGroup, zero: bool = True):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.tensor = symm_mem.empty(numel, dtype=dtype, device=torch.device("cuda", torch.cuda.current_device()))
+        if zero:
+            self.tensor.zero_()
+        self.handle = symm_mem.rendezvous(self.tensor, group)
+        self.base_ptrs: List[int] = [int(p) for p in self.handle.buffer_ptrs]
+        self.elem = self.tensor.element_size()
+        self._tables: Dict[int, torch.Tensor] = {}
+        dist.barrier(group)
+
+    def ptr_table(self, elem_offset: int = 0) -> torch.Tensor:
+        """Device ``int64[world]`` with every rank's pointer to element ``elem_offset`` of this buffer."""
+        t = self._tables.get(elem_offset)
+        if t is None:
+            t = torch.tensor([p + elem_offset * self.elem for p in self.base_ptrs], dtype=torch.int64,
+                             device=self.tensor.device)
+            self._tables[elem_offset] = t
+        return t
+
+    def table_ptr(self, elem_offset: int = 0) -> int:
+        return self.ptr_table(elem_offset).data_ptr()
+
+    def view(self, elem_offset: int, shape) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= s
+        return self.tensor[elem_offset: elem_offset + n].view(*shape)
+
+
+class SymmFlags(SymmBuffer):
+    """Symmetric flag words + the group's epoch counter and a stream-ordered device barrier."""
+
+    def __init__(self, group: dist.ProcessGroup, words: int = FLAG_WORDS):
+        super().__init__(words, torch.int32, group, zero=True)
+        self.epoch = 0
+        torch.cuda.synchronize()
+        dist.barrier(group)
+
+    def next_epoch(self) -> int:
+        self.epoch += 1
+        return self.epoch
+
+    def barrier(self):
+        """All ranks of the group rendezvous on the current stream (no host involvement)."""
+        torch.ops.b200.symm_barrier(self.table_ptr(0), self.rank, self.world, self.next_epoch())
+
+
+_flags_cache: Dict[int, SymmFlags] = {}
+
+
+def flags_for(group: dist.ProcessGroup) -> SymmFlags:
+    key = id(group)
+    if key not in _flags_cache:
+        _flags_cache[key] = SymmFlags(group)
+    return _flags_cache[key]
+
+
+def ag_flag_table(flags: SymmFlags) -> int:
+    return flags.table_ptr(_AG_BASE)
+
+
+def rs_flag_table(flags: SymmFlags) -> int:
+    return flags.table_ptr(_RS_BASE)
+
+
+def _unused() -> Tuple[Optional[int]]:
+    return (_BARRIER_SLOTS,)

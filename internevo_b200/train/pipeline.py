@@ -50,7 +50,13 @@ def initialize_model(pre_process_func: Optional[Callable] = None, post_process_f
         pre_output = pre_process_func()
     import internevo_b200.models  # noqa: F401  registers the builders
 
+    if gpc.config.get("fused_comm", False) and torch.cuda.is_available() and not is_using_isp():
+        # tensor-parallel linears run as fused GEMM+collective kernels over peer memory (parallel/fused.py)
+        from internevo_b200.parallel import fused
+
+        fused.enable_tp(gpc.get_group(ParallelMode.TENSOR))
     kwargs = dict(gpc.config.model)
+    kwargs.pop("output_to_fp32", None)
     for k in ("num_experts", "moe_use_residual", "moe_type"):
         if "MoE" not in gpc.config.model_type:
             kwargs.pop(k, None)

@@ -1,0 +1,167 @@
+"""Multi-GPU check of the peer-memory kernels (run with torchrun on N GPUs of one node):
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/fused_comm_check.py
+
+Validates against NCCL + our own GEMM: device barrier, GEMM→reduce-scatter, GEMM→all-reduce, all-gather→GEMM and the fused
+Hybrid-ZeRO step; prints device-timed (max over ranks) latencies and achieved fraction of the NVLink / GEMM roofline.
+"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+from internevo_b200 import ops
+from internevo_b200.parallel import fused, symm
+
+
+def timed(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    dist.barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([s.elapsed_time(e) / iters], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item()
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-6)).item()
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl")
+    group = dist.group.WORLD
+    ok = True
+    res = {"world": world}
+    flags = symm.flags_for(group)
+    for _ in range(3):
+        flags.barrier()
+    torch.cuda.synchronize()
+    res["barrier_us"] = round(timed(flags.barrier, iters=50) * 1e3, 1)
+
+    be = fused.TPFusedBackend(group)
+    torch.manual_seed(1234 + rank)
+    T, h, F = 4096, 4096, 14336
+    # ---- GEMM -> RS / AR (row-parallel: K sharded)
+    for name, (M, N, K) in {"wo": (T, h, h // world), "w2": (T, h, F // world)}.items():
+        x = torch.randn(M, K, device="cuda", dtype=torch.bfloat16) * 0.1
+        w = torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * 0.1
+        full = ops.matmul(x, w).float()
+        ref_rs = torch.empty(M // world, N, device="cuda")
+        dist.reduce_scatter_tensor(ref_rs, full)
+        out = be.gemm_rs(x, w, all_reduce=False)
+        r = rel(out, ref_rs)
+        ok &= r < 2e-2
+        ref_ar = full.clone()
+        dist.all_reduce(ref_ar)
+        out_ar = be.gemm_rs(x, w, all_reduce=True)
+        r2 = rel(out_ar, ref_ar)
+        ok &= r2 < 2e-2
+
+        def nccl_rs():
+            y = ops.matmul(x, w)
+            o = torch.empty(M // world, N, device="cuda", dtype=torch.bfloat16)
+            dist.reduce_scatter_tensor(o, y)
+
+        def nccl_ar():
+            y = ops.matmul(x, w)
+            dist.all_reduce(y)
+
+        t_f, t_n = timed(lambda: be.gemm_rs(x, w)), timed(nccl_rs)
+        t_fa, t_na = timed(lambda: be.gemm_rs(x, w, all_reduce=True)), timed(nccl_ar)
+        t_g = timed(lambda: ops.matmul(x, w))
+        res[f"gemm_rs_{name}"] = {"rel_err": r, "fused_ms": round(t_f, 4), "gemm+nccl_ms": round(t_n, 4),
+                                  "gemm_only_ms": round(t_g, 4),
+                                  "nvlink_floor_ms": round(M * N * 2 * (world - 1) / world / 770e9 * 1e3, 4)}
+        res[f"gemm_ar_{name}"] = {"rel_err": r2, "fused_ms": round(t_fa, 4), "gemm+nccl_ms": round(t_na, 4)}
+    # ---- AG -> GEMM (column-parallel with sequence parallel)
+    for name, (N, K) in {"wqkv": (6144 // world, h), "w13": (2 * F // world, h)}.items():
+        xs = torch.randn(T // world, K, device="cuda", dtype=torch.bfloat16) * 0.1
+        w = torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * 0.1
+        xg = torch.empty(T, K, device="cuda", dtype=torch.bfloat16)
+        dist.all_gather_into_tensor(xg, xs)
+        ref = ops.matmul(xg, w)
+        out, gathered = be.ag_gemm(xs, w)
+        r = rel(out, ref)
+        ok &= r < 2e-2 and torch.equal(gathered, xg)
+
+        def nccl_ag():
+            g = torch.empty(T, K, device="cuda", dtype=torch.bfloat16)
+            dist.all_gather_into_tensor(g, xs)
+            ops.matmul(g, w)
+
+        res[f"ag_gemm_{name}"] = {"rel_err": r, "fused_ms": round(timed(lambda: be.ag_gemm(xs, w)), 4),
+                                  "nccl+gemm_ms": round(timed(nccl_ag), 4),
+                                  "gemm_only_ms": round(timed(lambda: ops.matmul(xg, w)), 4)}
+    # ---- fused ZeRO kernels: reduce-scatter (mean) + sumsq, AdamW + parameter push
+    n = 64 * 1024 * 1024
+    gbuf = symm.SymmBuffer(n, torch.bfloat16, group)
+    pbuf = symm.SymmBuffer(n, torch.bfloat16, group)
+    gbuf.tensor.copy_(torch.randn(n, device="cuda") * 0.01)
+    ref = gbuf.tensor.float().clone()
+    dist.all_reduce(ref)
+    ref /= world
+    shard = n // world
+    lo = rank * shard
+    scal = torch.zeros(4, device="cuda")
+    p32 = torch.randn(shard, device="cuda")
+    m32, v32 = torch.zeros_like(p32), torch.zeros_like(p32)
+    flags.barrier()
+    torch.ops.b200.reduce_scatter_adam(gbuf.table_ptr(0), pbuf.table_ptr(0), flags.table_ptr(0), rank, world, 0, lo, shard,
+                                       p32, m32, v32, scal, 0.0, 0.9, 0.95, 1e-8, 0.0, 1.0, 1.0, float(world), 0)
+    torch.cuda.synchronize()
+    r = rel(gbuf.tensor[lo:lo + shard], ref[lo:lo + shard])
+    ss_ref = gbuf.tensor[lo:lo + shard].float().pow(2).sum()
+    ok &= r < 1e-2 and abs(scal[3].item() - ss_ref.item()) / ss_ref.item() < 1e-3
+    scal[0] = 1.0
+    pref = p32.clone()
+    ops.adamw_(pref, torch.zeros_like(pref), torch.zeros_like(pref), gbuf.tensor[lo:lo + shard], None, 1e-3, 0.9, 0.95,
+               1e-8, 0.1, 1, None)
+    torch.ops.b200.reduce_scatter_adam(gbuf.table_ptr(0), pbuf.table_ptr(0), flags.table_ptr(0), rank, world, 0, lo, shard,
+                                       p32, m32, v32, scal, 1e-3, 0.9, 0.95, 1e-8, 0.1, 1 - 0.9, 1 - 0.95, 1.0, 1)
+    flags.barrier()
+    torch.cuda.synchronize()
+    allp = [torch.empty(shard, device="cuda") for _ in range(world)]
+    dist.all_gather(allp, pref)
+    r_p = rel(pbuf.tensor, torch.cat(allp))
+    ok &= r_p < 1e-2 and rel(p32, pref) < 1e-5
+
+    def fused_rs():
+        torch.ops.b200.reduce_scatter_adam(gbuf.table_ptr(0), pbuf.table_ptr(0), flags.table_ptr(0), rank, world, 0, lo,
+                                           shard, p32, m32, v32, scal, 0.0, 0.9, 0.95, 1e-8, 0.0, 1.0, 1.0, float(world), 0)
+
+    def fused_adam():
+        torch.ops.b200.reduce_scatter_adam(gbuf.table_ptr(0), pbuf.table_ptr(0), flags.table_ptr(0), rank, world, 0, lo,
+                                           shard, p32, m32, v32, scal, 1e-3, 0.9, 0.95, 1e-8, 0.1, 0.1, 0.05, 1.0, 1)
+
+    tmp = torch.empty(shard, device="cuda", dtype=torch.bfloat16)
+    t_rs, t_ad = timed(fused_rs), timed(fused_adam)
+    t_nrs = timed(lambda: dist.reduce_scatter_tensor(tmp, gbuf.tensor, op=dist.ReduceOp.AVG))
+    t_nag = timed(lambda: dist.all_gather_into_tensor(pbuf.tensor, tmp))
+    res["zero"] = {"rs_rel_err": r, "param_rel_err": r_p, "fused_rs_ms": round(t_rs, 3), "nccl_rs_ms": round(t_nrs, 3),
+                   "fused_adam_allgather_ms": round(t_ad, 3), "nccl_allgather_only_ms": round(t_nag, 3),
+                   "rs_GBps_per_gpu": round(shard * 2 * (world - 1) / t_rs / 1e6, 1),
+                   "elements": n}
+    okt = torch.tensor([int(ok)], device="cuda")
+    dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        res["all_ok"] = bool(okt.item())
+        print(json.dumps(res, indent=1))
+        os.makedirs("gpurun_out", exist_ok=True)
+        json.dump(res, open(f"gpurun_out/fused_comm_check_n{world}.json", "w"), indent=1)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
