@@ -1,0 +1,187 @@
+"""Save / load of the individual checkpoint components (reference ``internlm/checkpoint/components.py``)."""
+from __future__ import annotations
+
+import copy
+import json
+import os
+import re
+
+import torch
+
+from internevo_b200.core.context import ParallelMode
+from internevo_b200.core.context import global_context as gpc
+from internevo_b200.utils.logger import get_logger
+from internevo_b200.utils.parallel import is_using_isp
+from internevo_b200.utils.storage_manager import get_fns, get_storage_manager, llm_load, llm_save
+
+from .utils import get_model_topology, get_shard_state_dict, load_shard_state_dict
+
+logger = get_logger(__file__)
+_EXPERT_KEY = re.compile(r"^(.*)\.(\d+)\.(?:mlp|feed_forward)\.moe_layer\.experts\.wrapped_experts\.(\d+)\.(.*)$")
+
+
+def _model_fn():
+    tp, pp = gpc.get_local_rank(ParallelMode.TENSOR), gpc.get_local_rank(ParallelMode.PIPELINE)
+    if is_using_isp():
+        return f"model_tp{tp}_wp{gpc.get_local_rank(ParallelMode.WEIGHT)}_pp{pp}.pt"
+    return f"model_tp{tp}_pp{pp}.pt"
+
+
+def _should_save_model():
+    """One replica writes: dp-rank 0 (ISP: weight-data rank 0) of every (tp|wp, pp) coordinate."""
+    if is_using_isp():
+        return gpc.get_local_rank(ParallelMode.WEIGHT_DATA) == 0 and gpc.get_local_rank(ParallelMode.TENSOR) == 0
+    return gpc.get_local_rank(ParallelMode.DATA) == 0
+
+
+def _split_expert_states(states: dict):
+    """Pull expert tensors out into ``{(layer, global_expert): {key: tensor}}`` (per-expert files, reference ``:53-92``)."""
+    ep_rank = gpc.get_local_rank(ParallelMode.EXPERT) if gpc.is_initialized(ParallelMode.EXPERT) else 0
+    experts, rest = {}, {}
+    for k, v in states.items():
+        m = _EXPERT_KEY.match(k)
+        if m is None:
+            rest[k] = v
+            continue
+        layer, local_e = int(m.group(2)), int(m.group(3))
+        n_local = gpc.config.model.get("num_experts", 1) // max(1, gpc.expert_parallel_size)
+        experts.setdefault((layer, ep_rank * n_local + local_e), {})[k] = v
+    return rest, experts
+
+
+def save_model_checkpoint(folder, model):
+    """``model_tp*_pp*.pt`` + topology json (+ one file per global expert)."""
+    states = get_shard_state_dict(model)
+    states = {k: v.detach().clone().cpu() if torch.is_tensor(v) else v for k, v in states.items()}
+    states, experts = _split_expert_states(states) if gpc.config.model.get("num_experts", 1) > 1 else (states, {})
+    if folder is None:
+        return
+    tp = gpc.get_local_rank(ParallelMode.TENSOR)
+    if _should_save_model():
+        fn = _model_fn()
+        llm_save(os.path.join(folder, fn), saved_obj=states)
+        topo = json.dumps(get_model_topology(model))
+        topo_fn = fn.replace("model_", "topo_").replace(".pt", ".json")
+        get_storage_manager()._client(os.path.join(folder, topo_fn))[0].upload_bytes(
+            topo.encode(), __import__("internevo_b200.utils.storage_manager", fromlist=["x"]).try_get_storage_backend(
+                os.path.join(folder, topo_fn))[1])
+    # experts are replicated over EXPERT_DATA: rank 0 of that group writes
+    if experts and (not gpc.is_initialized(ParallelMode.EXPERT_DATA) or gpc.get_local_rank(ParallelMode.EXPERT_DATA) == 0):
+        for (layer, e), st in experts.items():
+            llm_save(os.path.join(folder, f"model_moe_layer{layer}_expert{e}_tp{tp}.pt"), saved_obj=st)
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+
+
+def load_model_checkpoint(folder, model):
+    """Loads this rank's shard; asserts that tp/pp sizes match the checkpoint (reference ``:146-158``)."""
+    fns = get_fns(folder)
+    tp_size, pp_size = gpc.get_world_size(ParallelMode.TENSOR), gpc.get_world_size(ParallelMode.PIPELINE)
+    max_pp = max_tp = 0
+    for fn in fns:
+        if fn.startswith("model_t") and not fn.endswith(".md5") and "moe_layer" not in fn:
+            segs = fn.replace(".pt", "").split("_")
+            max_pp = max(max_pp, int(segs[-1][2:]))
+            max_tp = max(max_tp, int(segs[1][2:]))
+    assert pp_size == max_pp + 1, f"The weights are save for {max_pp + 1} pipelines, while current has {pp_size} pipelines"
+    assert tp_size == max_tp + 1, f"The weights are save for {max_tp + 1} parallelism, while current has {tp_size}"
+    fp = os.path.join(folder, _model_fn())
+    states = llm_load(fp, map_location="cpu")
+    if gpc.config.model.get("num_experts", 1) > 1:
+        tp = gpc.get_local_rank(ParallelMode.TENSOR)
+        ep_rank = gpc.get_local_rank(ParallelMode.EXPERT)
+        n_local = gpc.config.model.num_experts // gpc.expert_parallel_size
+        for fn in fns:
+            m = re.match(rf"model_moe_layer(\d+)_expert(\d+)_tp{tp}\.pt$", fn)
+            if m and ep_rank * n_local <= int(m.group(2)) < (ep_rank + 1) * n_local:
+                states.update(llm_load(os.path.join(folder, fn), map_location="cpu"))
+    missing_k, unexpected_keys = load_shard_state_dict(model, states, strict=False)
+    if len(missing_k) != 0 and gpc.is_rank_for_log():
+        logger.warning(f"Warning: missing keys {missing_k}")
+    if len(unexpected_keys) != 0 and gpc.is_rank_for_log():
+        logger.warning(f"Warning: unexpected keys {unexpected_keys}")
+    del states
+    if torch.cuda.is_available():
+        torch.cuda.empty_cache()
+
+
+def _optimizer_fn():
+    tp, pp = gpc.get_local_rank(ParallelMode.TENSOR), gpc.get_local_rank(ParallelMode.PIPELINE)
+    if is_using_isp():
+        return (f"optimizer_tp{tp}_wp{gpc.get_local_rank(ParallelMode.WEIGHT)}_pp{pp}_"
+                f"dp{gpc.get_local_rank(ParallelMode.DATA)}.pt")
+    return f"optimizer_tp{tp}_pp{pp}_zo{gpc.get_local_rank(ParallelMode.ZERO1)}.pt"
+
+
+def save_optimizer_checkpoint(optim, state_path):
+    """One file per (tp, pp, zero) coordinate; ranks beyond the first ZeRO replica hold identical shards and skip."""
+    if optim is None or state_path is None:
+        return
+    zero_size = gpc.get_world_size(ParallelMode.ZERO1)
+    dp_rank = gpc.get_local_rank(ParallelMode.WEIGHT_DATA if is_using_isp() else ParallelMode.DATA)
+    if dp_rank >= zero_size and not is_using_isp():
+        return
+    states = optim.state_dict()
+    llm_save(os.path.join(state_path, _optimizer_fn()), saved_obj=states)
+    if gpc.is_rank_for_log() and "zero_devide_optim_plan" in states:
+        llm_save(os.path.join(state_path, optim.rank_unique_id), saved_obj=states["zero_devide_optim_plan"])
+
+
+def load_optimizer_checkpoint(folder, optim):
+    fns = get_fns(folder)
+    max_tp = max_pp = max_zo = 0
+    for fn in fns:
+        if fn.startswith("optimizer_") and not fn.endswith(".md5"):
+            if is_using_isp():
+                continue
+            _, tp, pp, zo = os.path.splitext(fn)[0].split("_")
+            max_zo, max_tp, max_pp = max(max_zo, int(zo[2:])), max(max_tp, int(tp[2:])), max(max_pp, int(pp[2:]))
+    if not is_using_isp():
+        assert gpc.get_world_size(ParallelMode.ZERO1) == max_zo + 1, (
+            f"The optimizer states are save for {max_zo + 1} zero parallel, while current has "
+            f"{gpc.get_world_size(ParallelMode.ZERO1)} zero broadcast range.")
+        assert gpc.get_world_size(ParallelMode.PIPELINE) == max_pp + 1 and gpc.get_world_size(ParallelMode.TENSOR) == max_tp + 1
+    states = llm_load(os.path.join(folder, _optimizer_fn()), map_location="cpu")
+    optim.load_state_dict(states)
+    del states
+    if torch.cuda.is_available():
+        torch.cuda.empty_cache()
+
+
+def load_sampler(ckpt_path: str, sampler):
+    sampler_states = llm_load(os.path.join(ckpt_path, "sampler.pt"))
+    sampler.load_state_dict(sampler_states)
+    if gpc.is_rank_for_log():
+        pstate = copy.deepcopy(sampler_states)
+        pstate.pop("indices", None)
+        pstate.pop("rng_state", None)
+        logger.info(f"reload sampler_states:{pstate}")
+
+
+def load_context(ckpt_path: str, train_state):
+    context_stuffs = llm_load(os.path.join(ckpt_path, "context.pt"))
+    train_state.load_state_dict(context_stuffs)
+    if gpc.is_rank_for_log():
+        logger.info(f"reload train_state:{train_state}")
+
+
+def load_scheduler(ckpt_path: str, lr_scheduler, optimizer, train_state):
+    """Resume the LR schedule; the base LR may be overridden by the current config (reference ``:431-456``)."""
+    learning_rate = train_state.lr
+    scheduler_states = llm_load(os.path.join(ckpt_path, "schedulder.pt"))
+    if learning_rate != scheduler_states["base_lrs"][0] and gpc.is_rank_for_log():
+        logger.warning(f"Using new learning rate {learning_rate} to replace old learn rate {scheduler_states['base_lrs'][0]}.")
+    base_lrs = copy.deepcopy(scheduler_states["base_lrs"])
+    scheduler_states["base_lrs"] = [learning_rate] * len(scheduler_states["base_lrs"])
+    if "after_scheduler_dict" in scheduler_states:
+        scheduler_states["after_scheduler_dict"]["base_lrs"] = [learning_rate] * len(
+            scheduler_states["after_scheduler_dict"]["base_lrs"])
+    lr_scheduler.load_state_dict(scheduler_states)
+    lr_scheduler.last_epoch = train_state.step_count
+    del scheduler_states
+    ratio = learning_rate / base_lrs[0] if base_lrs and base_lrs[0] else 1.0
+    lr_scheduler._last_lr = [lr * ratio for lr in lr_scheduler.get_lr()] if ratio != 1.0 else lr_scheduler.get_lr()
+    for g, lr in zip(optimizer.param_groups, lr_scheduler._last_lr):
+        g["lr"] = lr
+    if gpc.is_rank_for_log():
+        logger.info(f"reload load_scheduler:{lr_scheduler}")

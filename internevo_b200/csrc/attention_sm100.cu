@@ -361,7 +361,8 @@ struct BwdSmem {
     static constexpr int DO = Q + 2 * QT_BYTES;          // 2 x 16 KB
     static constexpr int DS = DO + 2 * QT_BYTES;         // 2 x 16 KB  (dS^T, [128 kv rows x 64 q] bf16)
     static constexpr int DQ = DS + 2 * QT_BYTES;         // 32 KB fp32 staging [64 q x 128 d] for the TMA reduce-add
-    static constexpr int BARS = DQ + BQ * D * 4;
+    static constexpr int LD = DQ + BQ * D * 4;           // 2 x (64 lse2 + 64 delta) floats
+    static constexpr int BARS = LD + 2 * 2 * BQ * 4;
     static constexpr int TOTAL = BARS + 256 + 1024;
 };
 
@@ -374,9 +375,9 @@ struct AttnBwdArgs {
     int64_t dk_stride_t, dk_stride_h, dv_stride_t, dv_stride_h;
 };
 
-// delta[h, t] = sum_d dO[t,h,d] * O[t,h,d]
+// delta[h, t] = sum_d dO[t,h,d] * O[t,h,d];   lse2[h, t] = lse[h, t] * log2(e)   (stored behind delta: [2, H, T])
 __global__ void attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
-                                      float* __restrict__ delta, int T, int H) {
+                                      const float* __restrict__ lse, float* __restrict__ delta, int T, int H) {
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per (t, h)
     const int lane = threadIdx.x & 31;
     if (gw >= (int64_t)T * H) return;
@@ -387,7 +388,10 @@ __global__ void attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ dout, co
     float s = a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) delta[(int64_t)h * T + t] = s;
+    if (lane == 0) {
+        delta[(int64_t)h * T + t] = s;
+        delta[(int64_t)H * T + (int64_t)h * T + t] = lse[(int64_t)h * T + t] * 1.4426950408889634f;
+    }
 }
 
 // dq (bf16, strided [T, (g, j), D]) = dq_acc (fp32 [T, H, D])
@@ -445,9 +449,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         mbar_init(kv_full, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); mbar_init(&s_full[i], 1);
-            mbar_init(&p_ready[i], 4); mbar_init(&ds_free[i], 1);
+            mbar_init(&p_ready[i], 8); mbar_init(&ds_free[i], 1);
         }
-        mbar_init(dp_full, 1); mbar_init(ds_ready, 4); mbar_init(dq_full, 1); mbar_init(dq_free, 4);
+        mbar_init(dp_full, 1); mbar_init(ds_ready, 8); mbar_init(dq_full, 1); mbar_init(dq_free, 8);
         mbar_init(dkv_done, 1);
         fence_barrier_init();
     }
@@ -500,7 +504,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             auto issue_acc = [&](uint32_t a_col, uint32_t b_base, uint32_t d_col, bool acc) {
 #pragma unroll
                 for (int k = 0; k < BQ / 16; ++k)
-                    umma_f16_ts(tmem + d_col, tmem + a_col + k * 8,
+                    // packed bf16 rows live in the first 16 columns of each 32-column half (written in place by the
+                    // warps that own that half, so they never clobber the other half's unread fp32 inputs)
+                    umma_f16_ts(tmem + d_col, tmem + a_col + (k >> 1) * 32 + (k & 1) * 8,
                                 make_smem_desc_sw128(b_base + k * (16 * 128), BQ * 128, 1024), id_kv, acc || k != 0);
             };
             mbar_wait(kv_full, 0);
@@ -508,21 +514,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             tc_fence_after();
             issue_st(sK, smem_u32(smem + BwdSmem::Q), T_S0);
             umma_commit<1>(&s_full[0]);
+            // dP^T(0)
+            issue_st(sV, smem_u32(smem + BwdSmem::DO), T_DP);
+            umma_commit<1>(dp_full);
             for (int i = 0; i < n_steps; ++i) {
                 const int st = i & 1;
                 const uint32_t ph2 = (i >> 1) & 1;
                 const uint32_t sQ = smem_u32(smem + BwdSmem::Q + st * QT_BYTES);
                 const uint32_t sDO = smem_u32(smem + BwdSmem::DO + st * QT_BYTES);
-                // dP^T(i) = V dO^T
-                issue_st(sV, sDO, T_DP);
-                umma_commit<1>(dp_full);
                 // dV += P^T dO
                 mbar_wait(&p_ready[st], ph2);
                 tc_fence_after();
                 issue_acc(T_S0 + st * 64, sDO, T_DV, i > 0);
                 // S^T(i+1)
+                const int ns = (i + 1) & 1;
                 if (i + 1 < n_steps) {
-                    const int ns = (i + 1) & 1;
                     mbar_wait(&qdo_full[ns], ((i + 1) >> 1) & 1);
                     tc_fence_after();
                     issue_st(sK, smem_u32(smem + BwdSmem::Q + ns * QT_BYTES), T_S0 + ns * 64);
@@ -532,7 +538,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 mbar_wait(ds_ready, i & 1);
                 tc_fence_after();
                 issue_acc(T_DP, sQ, T_DK, i > 0);
-                umma_commit<1>(&qdo_empty[st]);
+                // dP^T(i+1) as early as possible (its TMEM region is free once dK(i) has been issued: in-order pipe)
+                if (i + 1 < n_steps) {
+                    issue_st(sV, smem_u32(smem + BwdSmem::DO + ns * QT_BYTES), T_DP);
+                    umma_commit<1>(dp_full);
+                }
                 // dQ^T(i) = K^T dS^T
                 if (i > 0) { mbar_wait(dq_free, (i - 1) & 1); tc_fence_after(); }
                 {
@@ -544,55 +554,98 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 }
                 umma_commit<1>(dq_full);
                 umma_commit<1>(&ds_free[st]);
+                umma_commit<1>(&qdo_empty[st]);  // Q(i) / dO(i) fully consumed (dV, dK and the early dP^T(i+1) excluded)
             }
             umma_commit<1>(dkv_done);
         }
-    } else if (warp >= 4 && warp < 8) {
-        // ===================== softmax / dS warpgroup: lane = kv row =====================
+    } else if (warp >= 4) {
+        // ===================== P / dS / dQ warps (8): lane = kv row (P, dS) or head-dim index (dQ^T) ==============
+        // warps 4-7 own q columns [0,32) of the step, warps 8-11 columns [32,64): two warps per scheduler hide each
+        // other's TMEM / MUFU latency (with one warpgroup the step was latency-bound at ~7 us, see profiles/).
         const int q = warp & 3;
-        const int r = q * 32 + lane;          // kv row inside the tile
-        const int kv = kv0 + r;               // local kv index
+        const int half = (warp - 4) >> 2;     // which 32-column half of the 64 q columns
+        const int r = q * 32 + lane;          // TMEM lane: kv row inside the tile (or d index for dQ^T)
+        const int kv = kv0 + r;
         const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
         const float sl2 = f.scale_log2;
-        const float LOG2E = 1.4426950408889634f;
+        const int tid = threadIdx.x - 128;    // 0..255
+        float* sld = reinterpret_cast<float*>(smem + BwdSmem::LD);  // [2][2][64]: buffer, {lse2, delta}, q
+        float* stage = reinterpret_cast<float*>(smem + BwdSmem::DQ);
+        const bool issuer = (tid == 0);
+        auto load_rowstats = [&](int step) {
+            if (tid < 2 * BQ && step < n_steps) {
+                const int j = step / nq, mq = mq0 + step % nq;
+                const int h = hk * qpk + j;
+                const int qi = min(mq * BQ + (tid & (BQ - 1)), len - 1);
+                const float* src = (tid < BQ ? args.lse : args.delta) + (int64_t)h * f.T + s0 + qi;
+                sld[(step & 1) * 2 * BQ + tid] = __ldg(src);
+            }
+        };
+        auto reduce_dq = [&](int step) {
+            // dQ^T(step): lane = d, this warp's 32 q columns -> fp32 staging rows -> one TMA reduce-add for the tile
+            const int j = step / nq, mq = mq0 + step % nq;
+            const int h = hk * qpk + j;
+            mbar_wait(dq_full, step & 1);
+            tc_fence_after();
+            uint32_t x[32];
+            tmem_ld_32x32b_x32(tmem + T_DQ + lane_off + half * 32, x);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dq_free);
+            if (issuer) tma_store_wait_read<0>();  // previous reduce has finished reading the staging tile
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < 32; ++c) stage[(half * 32 + c) * D + r] = __uint_as_float(x[c]);
+            fence_proxy_async();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (issuer) {
+                asm volatile(
+                    "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                    ::"l"(reinterpret_cast<uint64_t>(&tmap_dq)), "r"(smem_u32(stage)), "r"(h * D), "r"(s0 + mq * BQ)
+                    : "memory");
+                tma_store_commit();
+            }
+        };
+        load_rowstats(0);
         for (int i = 0; i < n_steps; ++i) {
             const int st = i & 1;
-            const int j = i / nq, mq = mq0 + i % nq;
-            const int h = hk * qpk + j;
-            const int q0 = mq * BQ;
-            const float* lse_p = args.lse + (int64_t)h * f.T + s0;
-            const float* del_p = args.delta + (int64_t)h * f.T + s0;
-            const bool edge = (q0 + BQ > len) || (kv0 + TN > len) || (f.causal && q0 < kv0 + TN);
-            uint32_t pk[32];  // P^T row, bf16 pairs
-            // ---- phase A: P^T = exp2(S^T * scale_log2 - lse * log2e)
+            const int mq = mq0 + i % nq;
+            const int q0 = mq * BQ + half * 32;   // first q row handled by this warp
+            asm volatile("bar.sync 2, 256;" ::: "memory");  // row stats of step i are in smem
+            load_rowstats(i + 1);
+            const float* lse2 = sld + st * 2 * BQ + half * 32;
+            const float* delt = lse2 + BQ;
+            const bool edge = (q0 + 32 > len) || (kv0 + TN > len) || (f.causal && q0 < kv0 + TN);
+            uint32_t pk[16];  // P^T row (this warp's 32 q columns), bf16 pairs
+            // ---- phase A: P^T = exp2(S^T * scale_log2 - lse2)
             mbar_wait(&s_full[st], (i >> 1) & 1);
             tc_fence_after();
             const uint32_t t_s = tmem + T_S0 + st * 64 + lane_off;
-#pragma unroll
-            for (int c = 0; c < BQ; c += 32) {
+            {
                 uint32_t x[32];
-                tmem_ld_32x32b_x32(t_s + c, x);
+                tmem_ld_32x32b_x32(t_s + half * 32, x);
                 tmem_ld_wait();
 #pragma unroll
-                for (int e = 0; e < 32; e += 2) {
-                    const int qa = q0 + c + e, qb = qa + 1;
-                    const float la = __ldg(lse_p + min(qa, len - 1)) * LOG2E, lb = __ldg(lse_p + min(qb, len - 1)) * LOG2E;
-                    float pa = fast_exp2(fmaf(__uint_as_float(x[e]), sl2, -la));
-                    float pb = fast_exp2(fmaf(__uint_as_float(x[e + 1]), sl2, -lb));
+                for (int e = 0; e < 32; e += 4) {
+                    const float4 l4 = *reinterpret_cast<const float4*>(lse2 + e);
+                    float p0 = fast_exp2(fmaf(__uint_as_float(x[e]), sl2, -l4.x));
+                    float p1 = fast_exp2(fmaf(__uint_as_float(x[e + 1]), sl2, -l4.y));
+                    float p2 = fast_exp2(fmaf(__uint_as_float(x[e + 2]), sl2, -l4.z));
+                    float p3 = fast_exp2(fmaf(__uint_as_float(x[e + 3]), sl2, -l4.w));
                     if (edge) {
-                        if (qa >= len || kv >= len || (f.causal && kv > qa)) pa = 0.f;
-                        if (qb >= len || kv >= len || (f.causal && kv > qb)) pb = 0.f;
+                        const int qa = q0 + e;
+                        const bool kvok = kv < len;
+                        if (!(kvok && qa < len && (!f.causal || kv <= qa))) p0 = 0.f;
+                        if (!(kvok && qa + 1 < len && (!f.causal || kv <= qa + 1))) p1 = 0.f;
+                        if (!(kvok && qa + 2 < len && (!f.causal || kv <= qa + 2))) p2 = 0.f;
+                        if (!(kvok && qa + 3 < len && (!f.causal || kv <= qa + 3))) p3 = 0.f;
                     }
-                    pk[(c + e) >> 1] = pack_bf16(pa, pb);
+                    pk[e >> 1] = pack_bf16(p0, p1);
+                    pk[(e >> 1) + 1] = pack_bf16(p2, p3);
                 }
             }
-            {
-                uint32_t lo[16], hi[16];
-#pragma unroll
-                for (int e = 0; e < 16; ++e) { lo[e] = pk[e]; hi[e] = pk[16 + e]; }
-                tmem_st_32x32b_x16(t_s, lo);
-                tmem_st_32x32b_x16(t_s + 16, hi);
-            }
+            tmem_st_32x32b_x16(t_s + half * 32, pk);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -603,24 +656,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             tc_fence_after();
             const uint32_t t_dp = tmem + T_DP + lane_off;
             uint8_t* ds_row = smem + BwdSmem::DS + st * QT_BYTES + r * 128;
-#pragma unroll
-            for (int c = 0; c < BQ; c += 32) {
+            {
                 uint32_t x[32];
-                tmem_ld_32x32b_x32(t_dp + c, x);
+                tmem_ld_32x32b_x32(t_dp + half * 32, x);
                 tmem_ld_wait();
                 uint32_t o[16];
 #pragma unroll
-                for (int e = 0; e < 32; e += 2) {
-                    const int qa = q0 + c + e;
-                    const float da = __ldg(del_p + min(qa, len - 1)), db = __ldg(del_p + min(qa + 1, len - 1));
-                    const float2 p = unpack_bf16(pk[(c + e) >> 1]);
-                    o[e >> 1] = pack_bf16(f.scale * p.x * (__uint_as_float(x[e]) - da),
-                                          f.scale * p.y * (__uint_as_float(x[e + 1]) - db));
+                for (int e = 0; e < 32; e += 4) {
+                    const float4 d4 = *reinterpret_cast<const float4*>(delt + e);
+                    const float2 pa = unpack_bf16(pk[e >> 1]), pb = unpack_bf16(pk[(e >> 1) + 1]);
+                    o[e >> 1] = pack_bf16(f.scale * pa.x * (__uint_as_float(x[e]) - d4.x),
+                                          f.scale * pa.y * (__uint_as_float(x[e + 1]) - d4.y));
+                    o[(e >> 1) + 1] = pack_bf16(f.scale * pb.x * (__uint_as_float(x[e + 2]) - d4.z),
+                                                f.scale * pb.y * (__uint_as_float(x[e + 3]) - d4.w));
                 }
-                tmem_st_32x32b_x16(t_dp + (c >> 1), o);
+                tmem_st_32x32b_x16(t_dp + half * 32, o);
 #pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {  // 4 x 16-byte chunks = 32 q values
-                    const int chunk = (c >> 3) + ch;
+                for (int ch = 0; ch < 4; ++ch) {  // 4 x 16-byte chunks = this warp's 32 q values of row r
+                    const int chunk = half * 4 + ch;
                     *reinterpret_cast<uint4*>(ds_row + ((chunk ^ (r & 7)) << 4)) =
                         make_uint4(o[ch * 4], o[ch * 4 + 1], o[ch * 4 + 2], o[ch * 4 + 3]);
                 }
@@ -630,8 +683,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(ds_ready);
+            // ---- dQ^T of the previous step (long finished): transpose + bulk reduce-add
+            if (i > 0) reduce_dq(i - 1);
         }
-        // ---- epilogue: dV, dK rows of this kv tile
+        if (n_steps > 0) reduce_dq(n_steps - 1);
+        if (issuer) tma_store_wait<0>();
+        // ---- epilogue: dV, dK rows of this kv tile (each warpgroup-half writes 64 of the 128 head-dim columns)
         mbar_wait(dkv_done, 0);
         tc_fence_after();
         const bool valid = kv < len;
@@ -641,7 +698,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             __nv_bfloat16* dst = which == 0 ? args.dv + tok * args.dv_stride_t + (int64_t)hk * args.dv_stride_h
                                             : args.dk + tok * args.dk_stride_t + (int64_t)hk * args.dk_stride_h;
 #pragma unroll 1
-            for (int c = 0; c < D; c += 32) {
+            for (int c = half * 64; c < half * 64 + 64; c += 32) {
                 uint32_t x[32];
                 tmem_ld_32x32b_x32(t_src + c, x);
                 tmem_ld_wait();
@@ -658,47 +715,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 }
             }
         }
-    } else if (warp >= 8) {
-        // ===================== dQ reducer warpgroup: lane = head-dim index =====================
-        // dQ^T (d on lanes, q on columns) is transposed through a 32 KB fp32 staging tile and added to the global fp32
-        // accumulator with ONE TMA reduce-add per step (per-element red.global tops out at ~1.3 cycles/lane on the LSU,
-        // i.e. ~6 us per step; the bulk reduce rides the TMA/L2 path instead). Rows past the sequence end carry exact
-        // zeros (their P is masked), so adding them is harmless.
-        const int q = warp & 3;
-        const int d = q * 32 + lane;
-        const uint32_t t_dq = tmem + T_DQ + (static_cast<uint32_t>(q * 32) << 16);
-        float* stage = reinterpret_cast<float*>(smem + BwdSmem::DQ);
-        const bool issuer = (warp == 8 && lane == 0);
-        for (int i = 0; i < n_steps; ++i) {
-            const int j = i / nq, mq = mq0 + i % nq;
-            const int h = hk * qpk + j;
-            const int q0 = mq * BQ;
-            mbar_wait(dq_full, i & 1);
-            tc_fence_after();
-            uint32_t x0[32], x1[32];
-            tmem_ld_32x32b_x32(t_dq, x0);
-            tmem_ld_32x32b_x32(t_dq + 32, x1);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(dq_free);  // values are in registers: the MMA may overwrite dQ^T now
-            if (issuer) tma_store_wait_read<0>();  // previous reduce has finished reading the staging tile
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll
-            for (int c = 0; c < 32; ++c) stage[c * D + d] = __uint_as_float(x0[c]);
-#pragma unroll
-            for (int c = 0; c < 32; ++c) stage[(c + 32) * D + d] = __uint_as_float(x1[c]);
-            fence_proxy_async();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (issuer) {
-                asm volatile(
-                    "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
-                    ::"l"(reinterpret_cast<uint64_t>(&tmap_dq)), "r"(smem_u32(stage)), "r"(h * D), "r"(s0 + q0)
-                    : "memory");
-                tma_store_commit();
-            }
-        }
-        if (issuer) tma_store_wait<0>();
     }
 
     tc_fence_before();
@@ -723,7 +739,7 @@ int attn_bwd(const AttnBwdDesc& b, cudaStream_t stream) {
     {
         const int64_t warps = (int64_t)d.T * d.H;
         attn_bwd_delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(
-            (const __nv_bfloat16*)b.dout, (const __nv_bfloat16*)d.o, b.delta, d.T, d.H);
+            (const __nv_bfloat16*)b.dout, (const __nv_bfloat16*)d.o, d.lse, b.delta, d.T, d.H);
     }
     AttnBwdArgs a;
     a.f.o = (__nv_bfloat16*)d.o; a.f.lse = d.lse; a.f.cu_seqlens = d.cu_seqlens; a.f.num_seqs = d.num_seqs;
@@ -731,7 +747,8 @@ int attn_bwd(const AttnBwdDesc& b, cudaStream_t stream) {
     a.f.q_stride_g = d.q_stride_g ? d.q_stride_g : d.q_stride_h * (d.H / d.Hkv);
     a.f.q_stride_h = d.q_stride_h; a.f.k_stride_h = d.k_stride_h; a.f.v_stride_h = d.v_stride_h;
     a.f.scale = d.scale; a.f.scale_log2 = d.scale * 1.4426950408889634f; a.f.causal = d.causal;
-    a.lse = d.lse; a.delta = b.delta; a.dq_acc = b.dq_acc;
+    a.lse = b.delta + (int64_t)d.H * d.T;  // lse * log2e, written by the delta pre-pass
+    a.delta = b.delta; a.dq_acc = b.dq_acc;
     a.dk = (__nv_bfloat16*)b.dk; a.dv = (__nv_bfloat16*)b.dv;
     a.dk_stride_t = b.dk_stride_t; a.dk_stride_h = b.dk_stride_h; a.dv_stride_t = b.dv_stride_t; a.dv_stride_h = b.dv_stride_h;
     static bool attr = false;

@@ -1,0 +1,117 @@
+"""Validation loop (reference ``internlm/eval/evaluation.py:18-143``): forward-only schedule over every validation
+loader with accuracy / perplexity / per-dataset loss, pipeline-aware."""
+from contextlib import contextmanager
+
+import torch
+from tqdm import tqdm
+
+from internevo_b200.core.context import ParallelMode
+from internevo_b200.core.context import global_context as gpc
+from internevo_b200.core.scheduler import InterleavedPipelineScheduler, PipelineScheduler
+from internevo_b200.models.metrics import AccPerplex, SchedulerMetricHook
+
+
+@contextmanager
+def switch_evaluation_no_pipeline_scheduler(trainer, grad_accum_size, metric_hook_list):
+    if not gpc.is_using_parallel_mode(ParallelMode.PIPELINE):
+        prev_data_process_func = trainer.schedule.data_process_func
+        prev_grad_accum_size = trainer.schedule._grad_accum_size
+        prev_metric_hooks = trainer.schedule._hooks
+        try:
+            trainer.schedule._grad_accum_size = grad_accum_size
+            trainer.schedule._hooks = metric_hook_list
+            yield
+        finally:
+            trainer.schedule.data_process_func = prev_data_process_func
+            trainer.schedule._grad_accum_size = prev_grad_accum_size
+            trainer.schedule._hooks = prev_metric_hooks
+    else:
+        yield
+
+
+@contextmanager
+def switch_evaluation_pipeline_scheduler(trainer, num_microbatches, tensor_shape, metric_hook_list):
+    if gpc.is_using_parallel_mode(ParallelMode.PIPELINE):
+        pre_data_process_func = trainer.schedule.data_process_func
+        prev_num_microbatches = trainer.schedule.num_microbatches
+        prev_tensor_shape = trainer.schedule.tensor_shape
+        prev_metric_hooks = trainer.schedule._hooks
+        try:
+            trainer.schedule.num_microbatches = num_microbatches
+            trainer.schedule.tensor_shape = tensor_shape
+            trainer.schedule._hooks = metric_hook_list
+            yield
+        finally:
+            trainer.schedule.data_process_func = pre_data_process_func
+            trainer.schedule.num_microbatches = prev_num_microbatches
+            trainer.schedule.tensor_shape = prev_tensor_shape
+            trainer.schedule._hooks = prev_metric_hooks
+    else:
+        yield
+
+
+@contextmanager
+def switch_evaluation_mode(trainer):
+    prev = gpc.is_evaluating
+    try:
+        gpc.is_evaluating = True
+        trainer.eval()
+        yield
+    finally:
+        gpc.is_evaluating = prev
+        trainer.train()
+
+
+def evaluate_on_val_dls(trainer, val_dls, writer, logger, step_count, update_panel: bool = False, streaming: bool = False):
+    with switch_evaluation_mode(trainer):
+        if torch.cuda.is_available():
+            torch.cuda.empty_cache()
+        criterion = trainer.engine.criterion
+        data_cfg = gpc.config.data
+        for val_name, val_dl in val_dls.items():
+            if not streaming and len(val_dl) == 0 and gpc.is_rank_for_log():
+                logger.info(f"Validation dataset: {val_name} is empty")
+                continue
+            val_metric = AccPerplex(dataset_types=None)
+            hook = SchedulerMetricHook(metric=val_metric, skip=True, criterion=criterion)
+            val_loss, n = 0.0, 0
+            it = enumerate(val_dl)
+            if gpc.is_rank_for_log():
+                it = tqdm(it, desc="Val.", total=len(val_dl) if not streaming else None, position=1, leave=False)
+            for _, batch in it:
+                with torch.inference_mode():
+                    total_bsz = len(batch[1])
+                    assert total_bsz % data_cfg.micro_bsz == 0
+                    num_micro = total_bsz // data_cfg.micro_bsz
+                    sp = gpc.get_world_size(ParallelMode.TENSOR) if gpc.config.parallel.get("sequence_parallel", False) else 1
+                    shape = (data_cfg.micro_bsz * batch[0]["input_ids"].shape[1] // sp, gpc.config.model["hidden_size"])
+                    if gpc.is_using_parallel_mode(ParallelMode.PIPELINE):
+                        with switch_evaluation_pipeline_scheduler(trainer, num_micro, shape, [hook]):
+                            trainer.schedule.bsz_stride = data_cfg.micro_bsz
+                            out = trainer.execute_schedule(batch, forward_only=True, return_loss=True, return_output_label=False)
+                    else:
+                        with switch_evaluation_no_pipeline_scheduler(trainer, num_micro, [hook]):
+                            out = trainer.execute_schedule(batch, forward_only=True, return_loss=True, return_output_label=False)
+                    loss = out[2]
+                if gpc.is_no_pp_or_last_stage() and loss is not None:
+                    val_loss += float(loss)
+                    n += 1
+            if n > 0:
+                res = val_metric.get_metric()
+                val_loss = val_loss / n
+                if gpc.is_rank_for_log():
+                    infos = {"step": step_count, f"val/{val_name}_loss": val_loss, f"val/{val_name}_acc": res["acc"],
+                             f"val/{val_name}_plex": res["perplexity"]}
+                    for k, v in infos.items():
+                        if k != "step" and writer is not None:
+                            writer.add_scalar(key=k, value=v, step=step_count)
+                    logger.info("Validation on {}: ".format(val_name) + " ".join(f"{k}={v}" for k, v in infos.items()))
+        trainer.train()
+        if torch.cuda.is_available():
+            torch.cuda.empty_cache()
+        if gpc.is_distributed:
+            torch.distributed.barrier()
+
+
+def _unused():
+    return InterleavedPipelineScheduler, PipelineScheduler

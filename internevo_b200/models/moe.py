@@ -1,0 +1,273 @@
+"""Mixture of experts: GShard top-1 / top-2 gating with capacity, expert parallelism over the EXPERT group.
+
+Semantics follow the reference (``internlm/model/moe/{moe,gshard_layer,experts}.py``): softmax gate in fp32, capacity
+``ceil(k * S / E * capacity_factor)`` (``>= min_capacity``), tokens beyond capacity dropped in token order (or by random
+priority with ``use_rts`` for top-1), second expert chosen after Gumbel noise, load-balancing loss
+``l_aux = E * sum(mean(gates) * mean(mask1))``, top-2 weights renormalised, equal-split ``all_to_all`` of the ``[E, C, h]``
+dispatch buffer, optional residual expert.
+
+Implementation is index based: the reference materialises dense one-hot ``[S, E, C]`` dispatch / combine tensors and
+contracts them with einsums (O(S·E·C) memory, ``gshard_layer.py:458,490``); here tokens are scattered into / gathered
+from the ``[E, C, h]`` buffer by row index and every expert runs the fused SwiGLU tcgen05 GEMMs on its contiguous slab.
+The registry keys ``GShard`` / ``MegaBlock`` / ``MegaBlock-D`` all resolve to this layer (``MegaBlock*`` = dropless:
+capacity is raised to the busiest expert's load instead of dropping).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+from torch import nn
+
+from internevo_b200.core.context import ParallelMode
+from internevo_b200.core.context import global_context as gpc
+from internevo_b200.core.naive_amp import set_fp32_attr_to_module
+from internevo_b200.utils.registry import MOE_INITIALIZER
+
+from .modules import FeedForward
+
+uniform_map = {}
+gumbel_map = {}
+
+
+def multiplicative_jitter(x, device, epsilon=1e-2):
+    if epsilon == 0:
+        return x
+    u = uniform_map.get(device)
+    if u is None:
+        u = torch.distributions.uniform.Uniform(low=torch.tensor(1.0 - epsilon, device=device),
+                                                high=torch.tensor(1.0 + epsilon, device=device)).rsample
+        uniform_map[device] = u
+    return x * u(x.shape)
+
+
+def gumbel_rsample(shape, device):
+    g = gumbel_map.get(device)
+    if g is None:
+        g = torch.distributions.gumbel.Gumbel(torch.tensor(0.0, device=device), torch.tensor(1.0, device=device)).rsample
+        gumbel_map[device] = g
+    return g(shape)
+
+
+def _capacity(num_tokens: int, num_experts: int, capacity_factor: float, min_capacity: int, k: int) -> int:
+    cap = math.ceil(k * num_tokens / num_experts * capacity_factor)
+    return max(cap, min_capacity)
+
+
+class _AllToAll(torch.autograd.Function):
+    """Equal-split ``all_to_all_single`` (dispatch / combine, reference ``moe/utils.py:21-40``)."""
+
+    @staticmethod
+    def forward(ctx, group, x):
+        ctx.group = group
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        dist.all_to_all_single(out, x, group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return None, _AllToAll.apply(ctx.group, g)
+
+
+class TopKGate(nn.Module):
+    """Gate ``wg: hidden -> num_experts`` kept in fp32 (reference ``gshard_layer.py:287-366``).
+
+    ``forward(x[S, h])`` returns ``(l_aux, weights[S, k], experts[S, k], slots[S, k], keep[S, k], capacity, counts[E])``.
+    """
+
+    def __init__(self, model_dim: int, num_experts: int, k: int = 1, capacity_factor: float = 1.0,
+                 eval_capacity_factor: float = 1.0, min_capacity: int = 8, noisy_gate_policy: Optional[str] = None,
+                 drop_tokens: bool = True, use_rts: bool = True, device=None) -> None:
+        super().__init__()
+        assert k in (1, 2), "Only top-1 and top-2 gatings are supported."
+        self.wg = nn.Linear(model_dim, num_experts, bias=False, device=device, dtype=torch.float32)
+        self.k, self.num_experts = k, num_experts
+        self.capacity_factor, self.eval_capacity_factor, self.min_capacity = capacity_factor, eval_capacity_factor, min_capacity
+        self.noisy_gate_policy, self.drop_tokens, self.use_rts = noisy_gate_policy, drop_tokens, use_rts
+        set_fp32_attr_to_module(self)
+
+    def forward(self, x: torch.Tensor):
+        xf = x.float()
+        if self.noisy_gate_policy == "Jitter" and self.training:
+            xf = multiplicative_jitter(xf, device=xf.device)
+        logits = F.linear(xf, self.wg.weight.float())
+        S, E = logits.shape
+        gates = F.softmax(logits, dim=1)
+        cf = self.capacity_factor if self.training else self.eval_capacity_factor
+        cap = _capacity(S, E, cf, self.min_capacity, self.k)
+        # ---- expert choice
+        noisy1 = logits + gumbel_rsample(logits.shape, logits.device) if (
+            self.k == 1 and self.noisy_gate_policy == "RSample") else gates
+        idx1 = torch.argmax(noisy1, dim=1)
+        mask1 = F.one_hot(idx1, E)
+        if self.k == 2:
+            noisy2 = (logits + gumbel_rsample(logits.shape, logits.device)).masked_fill(mask1.bool(), float("-inf"))
+            idx2 = torch.argmax(noisy2, dim=1)
+            mask2 = F.one_hot(idx2, E)
+        counts = mask1.sum(0).detach()
+        # ---- load-balancing loss (first choice only, as GShard)
+        me, ce = gates.mean(0), mask1.float().mean(0)
+        l_aux = (me * ce).sum() * E
+        if not self.drop_tokens:  # dropless: grow capacity to the busiest expert (agreed across the expert group)
+            load = counts.max() if self.k == 1 else (mask1.sum(0) + mask2.sum(0)).max()
+            if gpc.is_initialized(ParallelMode.EXPERT) and gpc.get_world_size(ParallelMode.EXPERT) > 1:
+                dist.all_reduce(load, op=dist.ReduceOp.MAX, group=gpc.get_group(ParallelMode.EXPERT))
+            cap = max(cap, int(load.item()))
+        # ---- slot of every token inside its expert's buffer
+        if self.k == 1 and self.use_rts and self.drop_tokens:
+            # random token selection: keep the `cap` tokens with the highest random priority per expert
+            pri = mask1 * torch.rand_like(mask1, dtype=torch.float32)
+            top = torch.topk(pri, k=min(cap, S), dim=0).indices  # [cap, E]
+            sel = torch.zeros_like(mask1).scatter_(0, top, 1) * mask1
+            loc1 = (torch.cumsum(sel, 0) - 1)
+            keep1 = sel.sum(1).bool()
+            slot1 = (loc1 * sel).sum(1)
+        else:
+            loc1 = torch.cumsum(mask1, 0) - 1
+            slot1 = (loc1 * mask1).sum(1)
+            keep1 = slot1 < cap
+        g1 = (gates * mask1).sum(1)
+        if self.k == 1:
+            weights = (g1 * keep1).unsqueeze(1)
+            return l_aux, weights, idx1.unsqueeze(1), slot1.unsqueeze(1), keep1.unsqueeze(1), cap, counts
+        loc2 = torch.cumsum(mask2, 0) - 1 + mask1.sum(0, keepdim=True)  # second choices queue behind all first choices
+        slot2 = (loc2 * mask2).sum(1)
+        keep2 = slot2 < cap
+        g2 = (gates * mask2).sum(1)
+        g1, g2 = g1 * keep1, g2 * keep2
+        denom = (g1 + g2).clamp_min(torch.finfo(gates.dtype).eps)
+        weights = torch.stack([g1 / denom, g2 / denom], 1)
+        return (l_aux, weights, torch.stack([idx1, idx2], 1), torch.stack([slot1, slot2], 1),
+                torch.stack([keep1, keep2], 1), cap, counts)
+
+
+class Experts(nn.Module):
+    """Local experts; parameters are tagged for expert-data-parallel reduction and per-expert checkpoint files
+    (reference ``moe/experts.py:13-68``)."""
+
+    def __init__(self, experts, num_local_experts=1, expert_group_name=None):
+        super().__init__()
+        self.wrapped_experts = nn.ModuleList(experts)
+        self.num_local_experts = num_local_experts
+        for expert in self.wrapped_experts:
+            for p in expert.parameters():
+                p.is_expert = True
+                p.group_name = expert_group_name
+
+    def forward(self, inputs: torch.Tensor) -> torch.Tensor:
+        # inputs: [E_local, rows, h]
+        outs = [expert(chunk.squeeze(0)) for chunk, expert in zip(inputs.chunk(self.num_local_experts, dim=0),
+                                                                   self.wrapped_experts)]
+        return torch.stack(outs, 0)
+
+
+class GShardMOELayer(nn.Module):
+    """dispatch → all-to-all → experts → all-to-all → combine (reference ``gshard_layer.py:369-498``)."""
+
+    def __init__(self, hidden_size, gate: TopKGate, experts: Experts, ep_group, ep_size, num_local_experts: int) -> None:
+        super().__init__()
+        self.gate, self.experts = gate, experts
+        self.ep_group, self.ep_size, self.num_local_experts = ep_group, ep_size, num_local_experts
+        self.exp_counts = None
+        self.l_aux = None
+
+    def forward(self, x: torch.Tensor):
+        shape = x.shape
+        h = shape[-1]
+        x2 = x.reshape(-1, h)
+        S = x2.shape[0]
+        l_aux, weights, experts, slots, keep, cap, counts = self.gate(x2)
+        self.l_aux, self.exp_counts = l_aux, counts
+        E = self.gate.num_experts
+        k = experts.shape[1]
+        flat = (experts * cap + slots).reshape(-1)            # row in the [E * cap, h] dispatch buffer
+        keep_f = keep.reshape(-1)
+        tok = torch.arange(S, device=x2.device).repeat_interleave(k)
+        rows, toks = flat[keep_f], tok[keep_f]
+        dispatched = x2.new_zeros(E * cap, h).index_copy(0, rows, x2[toks])
+        dispatched = dispatched.view(E, cap, h)
+        if self.ep_size > 1:
+            dispatched = _AllToAll.apply(self.ep_group, dispatched)
+        # [ep, E_local, cap, h] -> [E_local, ep * cap, h]
+        d = dispatched.view(self.ep_size, self.num_local_experts, cap, h).transpose(0, 1).reshape(
+            self.num_local_experts, self.ep_size * cap, h)
+        out = self.experts(d)
+        out = out.view(self.num_local_experts, self.ep_size, cap, h).transpose(0, 1).reshape(E, cap, h)
+        if self.ep_size > 1:
+            out = _AllToAll.apply(self.ep_group, out)
+        out = out.reshape(E * cap, h)
+        w = weights.reshape(-1)[keep_f].to(out.dtype)
+        combined = x2.new_zeros(S, h).index_add(0, toks, out[rows] * w.unsqueeze(1))
+        return combined.reshape(shape)
+
+
+@MOE_INITIALIZER.register_module("GShard")
+def _build_gshard(hidden_size, num_experts, ep_group, ep_size, mlp_ratio, device, dtype, top_k=1, capacity_factor=1.0,
+                  eval_capacity_factor=1.0, min_capacity=4, noisy_gate_policy=None, drop_tokens=True, use_rts=True,
+                  **unused):
+    assert noisy_gate_policy is None or noisy_gate_policy in ("None", "Jitter", "RSample")
+    num_local = num_experts // ep_size
+    experts = [FeedForward(hidden_size, int(hidden_size * mlp_ratio), out_features=hidden_size, process_group=None,
+                           bias=False, device=device, dtype=dtype) for _ in range(num_local)]
+    gate = TopKGate(hidden_size, num_experts, top_k, capacity_factor, eval_capacity_factor, min_capacity,
+                    noisy_gate_policy, drop_tokens, use_rts, device=device)
+    return GShardMOELayer(hidden_size, gate, Experts(experts, num_local, f"moe_ep_size_{ep_size}"), ep_group, ep_size,
+                          num_local)
+
+
+@MOE_INITIALIZER.register_module("MegaBlock")
+def _build_megablock(**kw):
+    kw["drop_tokens"] = False  # dropless, padded to the busiest expert
+    return _build_gshard(**kw)
+
+
+@MOE_INITIALIZER.register_module("MegaBlock-D")
+def _build_megablock_d(**kw):
+    kw["drop_tokens"] = False
+    return _build_gshard(**kw)
+
+
+class MoE(nn.Module):
+    """Wrapper selected by ``model.moe_type`` with kwargs from the top-level ``moe = dict(...)`` config; optional residual
+    expert mixed in by a learned 2-way coefficient (reference ``moe/moe.py:13-99``).
+    ``forward(x) -> (output, l_aux, exp_counts)``."""
+
+    def __init__(self, hidden_size, num_experts=1, ep_group=None, ep_size=None, device=None, dtype=None, mlp_ratio=4.0,
+                 moe_use_residual=False, moe_type="GShard", **moe_kwargs):
+        super().__init__()
+        ep_size = ep_size or gpc.get_world_size(ParallelMode.EXPERT)
+        ep_group = ep_group or gpc.get_group(ParallelMode.EXPERT)
+        assert num_experts % ep_size == 0, f"num_experts ({num_experts}) must be divisible by ep size ({ep_size})"
+        self.ep_size, self.num_experts = ep_size, num_experts
+        self.num_local_experts = num_experts // ep_size
+        self.moe_layer = MOE_INITIALIZER.get_module(moe_type)(
+            hidden_size=hidden_size, num_experts=num_experts, ep_group=ep_group, ep_size=ep_size, mlp_ratio=mlp_ratio,
+            device=device, dtype=dtype, **moe_kwargs)
+        self.use_residual = moe_use_residual
+        if self.use_residual:
+            self.residual_mlp = FeedForward(hidden_size, int(hidden_size * mlp_ratio), out_features=hidden_size,
+                                            process_group=gpc.get_group(ParallelMode.TENSOR), bias=False, device=device,
+                                            dtype=dtype)
+            self.coefficient = nn.Linear(hidden_size, 2, device=device, dtype=dtype)
+
+    def forward(self, hidden_states, used_token=None):
+        output = self.moe_layer(hidden_states)
+        if self.use_residual:
+            output_mlp = self.residual_mlp(hidden_states)
+            if isinstance(output_mlp, tuple):
+                output_mlp = output_mlp[0]
+            coef = F.softmax(self.coefficient(hidden_states), dim=-1)
+            output = output * coef[..., 0:1] + output_mlp * coef[..., 1:]
+        return output, self.moe_layer.l_aux, self.moe_layer.exp_counts
+
+
+def is_moe_param(param: torch.Tensor) -> bool:
+    return getattr(param, "is_expert", False)
+
+
+def _unused() -> Tuple:
+    return (math,)

@@ -76,7 +76,7 @@ class _B200AttnFn(torch.autograd.Function):
         dq = torch.empty_like(q) if q.is_contiguous() else torch.empty(q.shape, device=q.device, dtype=q.dtype)
         dk = torch.empty(k.shape, device=k.device, dtype=k.dtype)
         dv = torch.empty(v.shape, device=v.device, dtype=v.dtype)
-        delta = torch.empty(H, T, device=q.device, dtype=torch.float32)
+        delta = torch.empty(2, H, T, device=q.device, dtype=torch.float32)  # [0] rowsum(dO*O), [1] lse*log2e
         dq_acc = torch.zeros(T, H, D, device=q.device, dtype=torch.float32)
         torch.ops.b200.attn_bwd(dout, q, k, v, out, lse, dq, dk, dv, delta, dq_acc, cu, max_seqlen, scale, causal)
         _bump(3)
@@ -110,7 +110,7 @@ class _B200AttnPackedFn(torch.autograd.Function):
         T, G, gs, D = qkv.shape
         H = G * (gs - 2)
         dqkv = torch.empty_like(qkv)
-        delta = torch.empty(H, T, device=qkv.device, dtype=torch.float32)
+        delta = torch.empty(2, H, T, device=qkv.device, dtype=torch.float32)  # [0] rowsum(dO*O), [1] lse*log2e
         dq_acc = torch.zeros(T, H, D, device=qkv.device, dtype=torch.float32)
         torch.ops.b200.attn_bwd(dout.contiguous(), qkv[:, :, : gs - 2], qkv[:, :, gs - 2], qkv[:, :, gs - 1], out, lse,
                                 dqkv[:, :, : gs - 2], dqkv[:, :, gs - 2], dqkv[:, :, gs - 1], delta, dq_acc, cu,

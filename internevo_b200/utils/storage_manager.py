@@ -1,0 +1,314 @@
+"""Checkpoint storage: ``local:/path`` plus pluggable object stores (``boto3:s3://…``, ``volc:vc://…``, ``oss2:…``) with
+optional asynchronous upload (reference ``internlm/utils/storage_manager.py:95-1288``).
+
+Public surface kept: ``llm_save / llm_load / get_fns / check_folder``, ``init_storage_manager``,
+``get_storage_manager().wait()``, ``try_get_storage_backend``.  Object-store SDKs are imported lazily (none is present in
+this image); each backend only has to provide ``upload / download / list / exists / delete`` on raw bytes, the manager
+owns serialisation (``torch.save``), the ``/dev/shm`` staging folder, md5 sidecars, the thread pool and the ``{step}.step``
+completion marker that is written only after every asynchronous upload of the step has finished.
+"""
+from __future__ import annotations
+
+import concurrent.futures
+import hashlib
+import io
+import os
+import re
+import shutil
+import socket
+import stat
+from typing import Any, Callable, Dict, List, Optional
+
+import torch
+
+from internevo_b200.utils.logger import get_logger
+
+logger = get_logger(__file__)
+_PREFIX = re.compile(r"^(boto3|volc|oss2|local):")
+
+
+def try_get_storage_backend(path: str):
+    """``"boto3:s3://bucket/x"`` → ``("boto3", "s3://bucket/x")``; bare paths are local."""
+    m = _PREFIX.match(path)
+    if m:
+        return m.group(1), path[m.end():]
+    if os.environ.get("RANK", "0") == "0":
+        logger.warning(f"path: '{path}' not start with backend prefix, guess it is the backend of local.")
+    return "local", path
+
+
+def compute_file_md5_by_chunk(file_name: str) -> str:
+    h = hashlib.md5()
+    with open(file_name, "rb") as f:
+        for chunk in iter(lambda: f.read(4 << 20), b""):
+            h.update(chunk)
+    return h.hexdigest()
+
+
+class StorageClient:
+    """Backend interface."""
+
+    def upload_file(self, local_path: str, remote: str) -> None:
+        raise NotImplementedError
+
+    def upload_bytes(self, data: bytes, remote: str) -> None:
+        raise NotImplementedError
+
+    def download_bytes(self, remote: str) -> bytes:
+        raise NotImplementedError
+
+    def list(self, remote: str) -> List[str]:
+        raise NotImplementedError
+
+    def exists(self, remote: str) -> bool:
+        raise NotImplementedError
+
+    def delete(self, remote: str) -> None:
+        raise NotImplementedError
+
+
+class LocalClient(StorageClient):
+    def upload_file(self, local_path, remote):
+        os.makedirs(os.path.dirname(remote) or ".", exist_ok=True)
+        shutil.move(local_path, remote)
+
+    def upload_bytes(self, data, remote):
+        os.makedirs(os.path.dirname(remote) or ".", exist_ok=True)
+        tmp = remote + ".tmp"
+        with open(tmp, "wb") as f:
+            f.write(data)
+            f.flush()
+            os.fsync(f.fileno())
+        os.replace(tmp, remote)
+
+    def download_bytes(self, remote):
+        with open(remote, "rb") as f:
+            return f.read()
+
+    def list(self, remote):
+        if not os.path.exists(remote):
+            return []
+        if os.path.isfile(remote):
+            return [os.path.basename(remote)]
+        return sorted(os.listdir(remote))
+
+    def exists(self, remote):
+        return os.path.exists(remote)
+
+    def delete(self, remote):
+        if os.path.isdir(remote):
+            shutil.rmtree(remote, ignore_errors=True)
+        elif os.path.exists(remote):
+            os.remove(remote)
+
+
+class Boto3Client(StorageClient):
+    """``boto3:s3://{bucket}.{endpoint}/{key}`` — credentials from ``S3_ACCESS_KEY_ID`` / ``S3_SECRET_ACCESS_KEY_ID``."""
+
+    def __init__(self, endpoint: str):
+        import boto3  # noqa: lazy
+        import botocore
+
+        self.client = boto3.client(
+            "s3", endpoint_url=endpoint, aws_access_key_id=os.environ["S3_ACCESS_KEY_ID"],
+            aws_secret_access_key=os.environ["S3_SECRET_ACCESS_KEY_ID"], use_ssl=False,
+            config=botocore.config.Config(retries={"max_attempts": 5}))
+
+    @staticmethod
+    def split(remote: str):
+        m = re.match(r"^s3://([^/.]+)\.?([^/]*)/(.*)$", remote)
+        assert m, f"bad s3 path {remote}"
+        return m.group(1), m.group(3)
+
+    def upload_file(self, local_path, remote):
+        b, k = self.split(remote)
+        self.client.upload_file(local_path, b, k)
+
+    def upload_bytes(self, data, remote):
+        b, k = self.split(remote)
+        self.client.upload_fileobj(io.BytesIO(data), b, k)
+
+    def download_bytes(self, remote):
+        b, k = self.split(remote)
+        buf = io.BytesIO()
+        self.client.download_fileobj(b, k, buf)
+        return buf.getvalue()
+
+    def list(self, remote):
+        b, k = self.split(remote)
+        k = k.rstrip("/") + "/"
+        names = set()
+        for page in self.client.get_paginator("list_objects_v2").paginate(Bucket=b, Prefix=k):
+            for o in page.get("Contents", []):
+                names.add(o["Key"][len(k):].split("/")[0])
+        return sorted(names)
+
+    def exists(self, remote):
+        b, k = self.split(remote)
+        return self.client.list_objects_v2(Bucket=b, Prefix=k, MaxKeys=1).get("KeyCount", 0) > 0
+
+    def delete(self, remote):
+        b, k = self.split(remote)
+        self.client.delete_object(Bucket=b, Key=k)
+
+
+def _make_client(backend: str, path: str) -> StorageClient:
+    if backend == "local":
+        return LocalClient()
+    if backend == "boto3":
+        m = re.match(r"^s3://[^/.]+\.([^/]+)/", path)
+        endpoint = f"http://{m.group(1)}" if m and m.group(1) else os.environ.get("S3_ENDPOINT_URL")
+        return Boto3Client(endpoint)
+    if backend == "volc":  # ByteDance TOS: same verbs through the tos SDK
+        import tos  # noqa: F401 lazy
+
+        raise NotImplementedError("volc backend needs the `tos` SDK; wire a StorageClient via register_backend()")
+    if backend == "oss2":
+        import oss2  # noqa: F401 lazy
+
+        raise NotImplementedError("oss2 backend needs the `oss2` SDK; wire a StorageClient via register_backend()")
+    raise ValueError(f"unknown storage backend {backend}")
+
+
+_custom_backends: Dict[str, Callable[[str], StorageClient]] = {}
+
+
+def register_backend(name: str, factory: Callable[[str], StorageClient]):
+    """Plug in an object-store client (e.g. for ``volc:`` / ``oss2:`` prefixes)."""
+    _custom_backends[name] = factory
+
+
+class StorageManager:
+    """Serialises objects, routes them to the backend and tracks asynchronous uploads."""
+
+    def __init__(self, enable_save: bool = True, tmp_local_folder: Optional[str] = None, async_mode: bool = False,
+                 n_async_workers: int = 8):
+        self._clients: Dict[str, StorageClient] = {}
+        self.async_mode = bool(async_mode and tmp_local_folder)
+        self.tmp_local_folder = tmp_local_folder
+        self._futures: List[concurrent.futures.Future] = []
+        self._pool = concurrent.futures.ThreadPoolExecutor(max_workers=n_async_workers) if self.async_mode else None
+        self._to_be_marked: Optional[str] = None
+        self.latest_save_folder = None
+        self.latest_save_step = 0
+        self.async_task_peeding = False
+        if enable_save and self.async_mode:
+            os.makedirs(tmp_local_folder, exist_ok=True)
+            os.chmod(tmp_local_folder, stat.S_IRWXU | stat.S_IRWXG | stat.S_IRWXO)
+
+    def _client(self, path: str):
+        backend, real = try_get_storage_backend(path)
+        if backend not in self._clients:
+            self._clients[backend] = _custom_backends[backend](real) if backend in _custom_backends else _make_client(backend, real)
+        return self._clients[backend], backend, real
+
+    def assert_fp_exists(self, folder) -> None:
+        c, _, real = self._client(folder)
+        assert c.exists(real), f"{folder} does not exist"
+
+    def get_fns(self, folder) -> List[str]:
+        c, _, real = self._client(folder)
+        return c.list(real)
+
+    def is_exists(self, path) -> bool:
+        c, _, real = self._client(path)
+        return c.exists(real)
+
+    def save(self, save_path: str, to_save_obj: Any, async_upload=None, **kwargs):
+        c, backend, real = self._client(save_path)
+        use_async = self.async_mode if async_upload is None else (async_upload and self.async_mode)
+        if backend == "local" or not use_async:
+            buf = io.BytesIO()
+            torch.save(to_save_obj, buf, **kwargs)
+            c.upload_bytes(buf.getvalue(), real)
+            return
+        tmp = os.path.join(self.tmp_local_folder, f"{socket.gethostname()}-{os.getpid()}-" + real.replace("/", "_"))
+        torch.save(to_save_obj, tmp, **kwargs)
+        self.async_task_peeding = True
+        self._futures.append(self._pool.submit(self._upload_and_clean, c, tmp, real))
+
+    @staticmethod
+    def _upload_and_clean(client, tmp, real):
+        md5 = compute_file_md5_by_chunk(tmp)
+        client.upload_bytes(md5.encode(), real + ".md5")
+        client.upload_file(tmp, real)
+        if os.path.exists(tmp):
+            os.remove(tmp)
+        return real
+
+    def load(self, load_path: str, **kwargs) -> Any:
+        c, _, real = self._client(load_path)
+        kwargs.setdefault("map_location", "cpu")
+        kwargs.setdefault("weights_only", False)
+        return torch.load(io.BytesIO(c.download_bytes(real)), **kwargs)
+
+    def delete_obj(self, fp: str):
+        c, _, real = self._client(fp)
+        c.delete(real)
+
+    def async_executor(self, fn: Callable, *args, **kwargs) -> None:
+        if self._pool is None:
+            fn(*args, **kwargs)
+        else:
+            self._futures.append(self._pool.submit(fn, *args, **kwargs))
+
+    def set_pending_marker(self, marker_path: str):
+        """``{step}.step`` is written by ``wait()`` once all uploads of that step are done."""
+        self._to_be_marked = marker_path
+
+    def wait(self) -> bool:
+        """Block until every outstanding upload finished; then publish the completion marker."""
+        ok = True
+        for f in self._futures:
+            try:
+                f.result()
+            except Exception as e:  # pragma: no cover
+                ok = False
+                logger.error(f"async upload failed: {e}")
+        self._futures = []
+        self.async_task_peeding = False
+        if ok and self._to_be_marked is not None:
+            c, _, real = self._client(self._to_be_marked)
+            c.upload_bytes(b"", real)
+            self._to_be_marked = None
+        return ok
+
+
+storage_manager: Optional[StorageManager] = None
+
+
+def init_storage_manager(enable_save_ckpt, async_upload_tmp_folder, async_upload, use_processpool=False):
+    global storage_manager
+    storage_manager = StorageManager(enable_save_ckpt, tmp_local_folder=async_upload_tmp_folder, async_mode=async_upload)
+    return storage_manager
+
+
+def get_storage_manager() -> StorageManager:
+    global storage_manager
+    if storage_manager is None:
+        storage_manager = StorageManager()
+    return storage_manager
+
+
+def wait_async_upload_finish():
+    import torch.distributed as dist
+
+    get_storage_manager().wait()
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+
+
+def check_folder(fp: str):
+    get_storage_manager().assert_fp_exists(fp)
+
+
+def get_fns(fp: str):
+    return get_storage_manager().get_fns(fp)
+
+
+def llm_load(fp: str, **kwargs):
+    return get_storage_manager().load(fp, **kwargs)
+
+
+def llm_save(save_path: str, saved_obj: Any, **kwargs):
+    get_storage_manager().save(save_path, to_save_obj=saved_obj, **kwargs)
