@@ -45,7 +45,10 @@ struct GemmKernelArgs {
     int flags;
     int a_mn, b_mn;
     int tiles_m, tiles_n;
+    int tiles_full;   // work items [0, tiles_full) are whole BM x BN tiles
+    int tail_split;   // the remaining tiles are split into this many column slices (1, 2 or 4) to fill the last wave
 };
+
 
 B200_DEVICE void tile_coords(int tile, int tiles_m, int tiles_n, int& m, int& n) {
     constexpr int GROUP_M = 8;
@@ -56,6 +59,21 @@ B200_DEVICE void tile_coords(int tile, int tiles_m, int tiles_n, int& m, int& n)
     const int r = tile - g * per_group;
     m = first_m + r % gsize;
     n = r / gsize;
+}
+
+// work item -> (m tile, n tile, column offset inside the tile, slice width)
+template <int BN>
+B200_DEVICE void item_coords(int item, const GemmKernelArgs& a, int& tm, int& tn, int& n_off, int& width) {
+    int tile = item, slice = 0;
+    width = BN;
+    if (item >= a.tiles_full) {
+        const int w = item - a.tiles_full;
+        tile = a.tiles_full + w / a.tail_split;
+        slice = w % a.tail_split;
+        width = BN / a.tail_split;
+    }
+    tile_coords(tile, a.tiles_m, a.tiles_n, tm, tn);
+    n_off = slice * width;
 }
 
 struct CommKernelArgs {
@@ -179,7 +197,7 @@ B200_DEVICE void comm_role(const GemmKernelArgs& args, const CommKernelArgs& c) 
 template <int BN, bool COMM>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const GemmKernelArgs args, const CommKernelArgs comm) {
+                 const __grid_constant__ CUtensorMap tmap_bt, const GemmKernelArgs args, const CommKernelArgs comm) {
     using Cfg = GemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     if constexpr (COMM) {
@@ -204,6 +222,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_tiles = args.tiles_m * args.tiles_n;
+    const int num_items = args.tiles_full + (num_tiles - args.tiles_full) * args.tail_split;
     const int num_kb = (args.K + BK - 1) / BK;
 
     if (warp == 0 && lane == 0) {
@@ -230,9 +249,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += grid_ctas) {
-                int tm, tn;
-                tile_coords(tile, args.tiles_m, args.tiles_n, tm, tn);
+            for (int tile = blockIdx.x; tile < num_items; tile += grid_ctas) {
+                int tm, tn, n_off, width;
+                item_coords<BN>(tile, args, tm, tn, n_off, width);
                 if constexpr (COMM) {
                     tm = comm_remap_m(tm, args.tiles_m, comm);
                     if (comm.mode == GEMM_COMM_ALL_GATHER) {
@@ -243,10 +262,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         fence_proxy_async_global();
                     }
                 }
-                const int m0 = tm * BM, n0 = tn * BN;
+                const int m0 = tm * BM, n0 = tn * BN + n_off;
+                const int nb64 = width / 64;  // B arrives in 64-row (K-major) or 64-column (MN-major) boxes
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + width * (BK * 2));
                     uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
                     uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
                     const int k0 = kb * BK;
@@ -257,11 +277,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         for (int j = 0; j < BM / 64; ++j)
                             tma_load_2d(sa + j * (BK * 128), &tmap_a, &full_bar[stage], m0 + j * 64, k0);
                     }
-                    if (!args.b_mn) {
-                        tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
-                    } else {
+                    if (width == BN) {
+                        if (!args.b_mn) {
+                            tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < BN / 64; ++j)
+                            for (int j = 0; j < BN / 64; ++j)
+                                tma_load_2d(sb + j * (BK * 128), &tmap_b, &full_bar[stage], n0 + j * 64, k0);
+                        }
+                    } else if (!args.b_mn) {  // tail slice: 64-row boxes of the K-major operand
+                        for (int j = 0; j < nb64; ++j)
+                            tma_load_2d(sb + j * (64 * 128), &tmap_bt, &full_bar[stage], k0, n0 + j * 64);
+                    } else {
+                        for (int j = 0; j < nb64; ++j)
                             tma_load_2d(sb + j * (BK * 128), &tmap_b, &full_bar[stage], n0 + j * 64, k0);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -271,7 +299,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_f16(BM, BN, args.a_mn, args.b_mn);
+            const uint32_t idesc_full = make_idesc_f16(BM, BN, args.a_mn, args.b_mn);
             // K-major: 8-row groups are 1024 B apart, advance 32 B per UMMA_K.
             // MN-major: 64-element column blocks are BK*128 B apart (LBO), 8-k groups 1024 B apart, advance 2048 B.
             const uint32_t a_lbo = args.a_mn ? BK * 128 : 16, b_lbo = args.b_mn ? BK * 128 : 16;
@@ -281,7 +309,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += grid_ctas) {
+            for (int tile = blockIdx.x; tile < num_items; tile += grid_ctas) {
+                const uint32_t idesc = tile < args.tiles_full
+                                           ? idesc_full
+                                           : make_idesc_f16(BM, BN / args.tail_split, args.a_mn, args.b_mn);
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -312,17 +343,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const bool accumulate = args.flags & GEMM_ACCUMULATE;
         const bool swiglu = args.flags & GEMM_SWIGLU;
         const bool no_store_d = args.flags & GEMM_SKIP_D;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += grid_ctas) {
-            int tm, tn;
-            tile_coords(tile, args.tiles_m, args.tiles_n, tm, tn);
+        for (int tile = blockIdx.x; tile < num_items; tile += grid_ctas) {
+            int tm, tn, n_off, width;
+            item_coords<BN>(tile, args, tm, tn, n_off, width);
             if constexpr (COMM) tm = comm_remap_m(tm, args.tiles_m, comm);
             const int row = tm * BM + q * 32 + lane;
-            const int n0 = tn * BN;
+            const int n0 = tn * BN + n_off;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
+            for (int c = 0; c < width; c += 32) {
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(taddr + c, r);
                 tmem_ld_wait();
@@ -528,10 +559,13 @@ static int num_sms() {
     return g_num_sms;
 }
 
+static int g_tail_split = 1;
+void set_gemm_tail_split(int on) { g_tail_split = on; }
+
 template <int BN>
 static int launch(const GemmDesc& g, cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, tbt;
     int rc;
     // A: logical [M, K]
     if (!g.a_mn_major) rc = make_tmap_2d_bf16(&ta, g.A, g.K, g.M, g.lda, BK, BM);
@@ -541,6 +575,7 @@ static int launch(const GemmDesc& g, cudaStream_t stream) {
     if (!g.b_mn_major) rc = make_tmap_2d_bf16(&tb, g.B, g.K, g.N, g.ldb, BK, BN);
     else               rc = make_tmap_2d_bf16(&tb, g.B, g.N, g.K, g.ldb, 64, BK);
     if (rc) return rc;
+    tbt = tb;  // tail slices of a K-major B come in 64-row boxes
 
     GemmKernelArgs a;
     a.M = g.M; a.N = g.N; a.K = g.K;
@@ -554,6 +589,24 @@ static int launch(const GemmDesc& g, cudaStream_t stream) {
     const int tiles = a.tiles_m * a.tiles_n;
     int sms = g.max_ctas > 0 ? g.max_ctas : num_sms();
     const int grid = tiles < sms ? tiles : sms;
+    // Wave quantisation: split the tiles of the last (partial) wave into 2 or 4 column slices when that lets the
+    // whole tail run as ONE wave of narrower tiles (e.g. 512 tiles on 148 SMs: 3 full waves + 68 tiles -> 136 half
+    // tiles, 3.5 wave-times instead of 4).  The partial last n-tile (N % BN != 0) keeps the whole-tile path.
+    a.tiles_full = tiles;
+    a.tail_split = 1;
+    if (g_tail_split && tiles > grid && g.N % BN == 0) {
+        const int tail = tiles % grid;
+        if (tail > 0) {
+            int split = 1;
+            if (tail * 4 <= grid && BN / 4 >= 64) split = 4;
+            else if (tail * 2 <= grid && BN / 2 >= 64) split = 2;
+            if (split > 1) { a.tiles_full = tiles - tail; a.tail_split = split; }
+        }
+    }
+    if (a.tail_split > 1 && !g.b_mn_major) {
+        rc = make_tmap_2d_bf16(&tbt, g.B, g.K, g.N, g.ldb, BK, 64);
+        if (rc) return rc;
+    }
 
     static bool attr_set = false;
     if (!attr_set) {
@@ -565,7 +618,7 @@ static int launch(const GemmDesc& g, cudaStream_t stream) {
         }
         attr_set = true;
     }
-    gemm_bf16_kernel<BN, false><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, a, CommKernelArgs{});
+    gemm_bf16_kernel<BN, false><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tbt, a, CommKernelArgs{});
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         fprintf(stderr, "[b200] gemm launch failed: %s\n", cudaGetErrorString(e));
@@ -592,6 +645,7 @@ int gemm_bf16_comm(const GemmDesc& g, const GemmCommArgs& c, cudaStream_t stream
     else               rc = make_tmap_2d_bf16(&tb, g.B, g.N, g.K, g.ldb, 64, BK);
     if (rc) return rc;
     GemmKernelArgs a;
+    a.tiles_full = tiles_m * tiles_n; a.tail_split = 1;
     a.M = g.M; a.N = g.N; a.K = g.K;
     a.D = g.D; a.ldd = g.ldd;
     a.bias = nullptr; a.H = g.H; a.ldh = g.ldh; a.flags = g.flags;
@@ -614,7 +668,7 @@ int gemm_bf16_comm(const GemmDesc& g, const GemmCommArgs& c, cudaStream_t stream
             return -3;
         attr_set = true;
     }
-    gemm_bf16_kernel<BN, true><<<gemm_ctas + comm_ctas, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, a, k);
+    gemm_bf16_kernel<BN, true><<<gemm_ctas + comm_ctas, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tb, a, k);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 

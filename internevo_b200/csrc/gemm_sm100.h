@@ -32,6 +32,8 @@ struct GemmDesc {
 };
 
 int gemm_bf16(const GemmDesc& g, cudaStream_t stream);
+// Enable / disable splitting the tiles of the last partial wave into column slices (default on).
+void set_gemm_tail_split(int on);
 
 // ---- GEMM with communication CTAs in the same launch (tensor parallel fused paths) ------------------------------
 enum GemmCommMode : int {

@@ -39,6 +39,10 @@ class SymmBuffer:
     def __init__(self, numel: int, dtype: torch.dtype, group: dist.ProcessGroup, zero: bool = True):
         import torch.distributed._symmetric_memory as symm_mem
 
+        from internevo_b200.ops import _lib
+
+        assert _lib.available(), "peer-memory kernels need the native extension"
+
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)

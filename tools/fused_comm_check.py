@@ -50,6 +50,13 @@ def main():
     torch.cuda.synchronize()
     res["barrier_us"] = round(timed(flags.barrier, iters=50) * 1e3, 1)
 
+    def stage(msg):
+        torch.cuda.synchronize()
+        if rank == 0:
+            print(f"[stage] {msg} ok={ok}", file=sys.stderr, flush=True)
+
+    stage(f"barrier {res['barrier_us']} us")
+
     be = fused.TPFusedBackend(group)
     torch.manual_seed(1234 + rank)
     T, h, F = 4096, 4096, 14336
@@ -63,11 +70,13 @@ def main():
         out = be.gemm_rs(x, w, all_reduce=False)
         r = rel(out, ref_rs)
         ok &= r < 2e-2
+        stage(f"gemm_rs {name} rel={r}")
         ref_ar = full.clone()
         dist.all_reduce(ref_ar)
         out_ar = be.gemm_rs(x, w, all_reduce=True)
         r2 = rel(out_ar, ref_ar)
         ok &= r2 < 2e-2
+        stage(f"gemm_ar {name} rel={r2}")
 
         def nccl_rs():
             y = ops.matmul(x, w)
@@ -95,6 +104,7 @@ def main():
         out, gathered = be.ag_gemm(xs, w)
         r = rel(out, ref)
         ok &= r < 2e-2 and torch.equal(gathered, xg)
+        stage(f"ag_gemm {name} rel={r} gathered_equal={torch.equal(gathered, xg)}")
 
         def nccl_ag():
             g = torch.empty(T, K, device="cuda", dtype=torch.bfloat16)
@@ -124,6 +134,7 @@ def main():
     r = rel(gbuf.tensor[lo:lo + shard], ref[lo:lo + shard])
     ss_ref = gbuf.tensor[lo:lo + shard].float().pow(2).sum()
     ok &= r < 1e-2 and abs(scal[3].item() - ss_ref.item()) / ss_ref.item() < 1e-3
+    stage(f"zero rs rel={r} sumsq {scal[3].item()} vs {ss_ref.item()}")
     scal[0] = 1.0
     pref = p32.clone()
     ops.adamw_(pref, torch.zeros_like(pref), torch.zeros_like(pref), gbuf.tensor[lo:lo + shard], None, 1e-3, 0.9, 0.95,
@@ -136,6 +147,7 @@ def main():
     dist.all_gather(allp, pref)
     r_p = rel(pbuf.tensor, torch.cat(allp))
     ok &= r_p < 1e-2 and rel(p32, pref) < 1e-5
+    stage(f"zero adam+bcast rel={r_p} p32 rel={rel(p32, pref)}")
 
     def fused_rs():
         torch.ops.b200.reduce_scatter_adam(gbuf.table_ptr(0), pbuf.table_ptr(0), flags.table_ptr(0), rank, world, 0, lo,

@@ -137,12 +137,15 @@ def gemm_perf():
         A = a.t() if a_mn else a
         Bt = b if b_mn else b.t()
         row = {"case": name, "M": M, "N": N, "K": K}
-        for bn in (256, 128):
+        for bn, split in ((256, 1), (256, 0), (128, 1)):
+            key = f"ours_bn{bn}_tflops" if split else f"ours_bn{bn}_nosplit_tflops"
+            torch.ops.b200.set_gemm_tail_split(split)
             try:
                 ms = timeit(lambda: ops.matmul(a, b, a_mn=a_mn, b_mn=b_mn, out=out, force_bn=bn), flush=flush)
-                row[f"ours_bn{bn}_tflops"] = round(2 * M * N * K / ms / 1e9, 1)
+                row[key] = round(2 * M * N * K / ms / 1e9, 1)
             except Exception as e:  # noqa
-                row[f"ours_bn{bn}_tflops"] = f"ERR {e}"
+                row[key] = f"ERR {e}"
+        torch.ops.b200.set_gemm_tail_split(1)
         ms = timeit(lambda: torch.matmul(A, Bt, out=out), flush=flush)
         row["cublas_tflops"] = round(2 * M * N * K / ms / 1e9, 1)
         print(json.dumps(row), flush=True)
