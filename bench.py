@@ -36,7 +36,7 @@ def parse():
     p.add_argument("--steps", type=int, default=5)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--tp", type=int, default=0, help="tensor parallel size (0 = BASELINE layout: 1 for N=1, else 2)")
+    p.add_argument("--tp", type=int, default=0, help="tensor parallel size (0 = BASELINE layout: tp 1, ZeRO-1 over all N ranks, as configs/7B_internlm2.py)")
     p.add_argument("--tp-mode", default="mtp")
     p.add_argument("--seq-len", type=int, default=4096)
     p.add_argument("--micro-bsz", type=int, default=1)
@@ -50,7 +50,7 @@ def parse():
 
 
 def build_config(a, world):
-    tp = a.tp if a.tp > 0 else (1 if world == 1 else 2)
+    tp = a.tp if a.tp > 0 else 1
     dp = world // tp
     model = dict(
         checkpoint=a.checkpoint, num_chunks=1, num_attention_heads=MODEL_7B["num_attention_heads"] * a.hidden // 4096,

@@ -258,50 +258,53 @@ void reduce_scatter_adam(int64_t grad_ptrs, int64_t param_ptrs, int64_t flags_pt
     CHECK_RC(b200::reduce_scatter_adam(d, cur_stream()), "b200::reduce_scatter_adam");
 }
 
-// partial = a @ b^T written into this rank's symmetric scratch; communication CTAs of the same kernel reduce this
-// rank's row slice from all peers' scratch into `out` (mode 0: [M/world, N] local) or push it to every rank's `out`
-// (mode 1, all-reduce; out_ptrs = per-rank output pointer table).
-void gemm_rs(const Tensor& a, const Tensor& b, Tensor& partial, Tensor& out, int64_t partial_ptrs, int64_t out_ptrs,
-             int64_t flags_ptrs, int64_t rank, int64_t world, int64_t epoch, bool b_mn, int64_t mode, int64_t comm_ctas) {
-    CHECK_BF16(a); CHECK_BF16(b); CHECK_BF16(partial); CHECK_BF16(out);
+// reduce_scatter(a @ b^T) over rows (mode 0: `out` is this rank's [M/world, N]) or all-reduce (mode 1: `out` is the
+// [M, N] symmetric output, out_ptrs its per-rank pointer table).  stage_ptrs: per-rank symmetric staging
+// [world, M/world, N] that the peers' epilogues push their partial tiles into.
+void gemm_rs(const Tensor& a, const Tensor& b, Tensor& out, int64_t stage_ptrs, int64_t out_ptrs, int64_t flags_ptrs,
+             int64_t rank, int64_t world, int64_t epoch, bool b_mn, int64_t mode) {
+    CHECK_BF16(a); CHECK_BF16(b); CHECK_BF16(out);
     c10::cuda::CUDAGuard guard(a.device());
     b200::GemmCommDesc d;
     d.g.M = a.size(0); d.g.K = a.size(1); d.g.N = b_mn ? b.size(1) : b.size(0);
     TORCH_CHECK((b_mn ? b.size(0) : b.size(1)) == d.g.K, "gemm_rs: K mismatch");
-    TORCH_CHECK(partial.size(0) == d.g.M && partial.size(1) == d.g.N && partial.stride(1) == 1, "gemm_rs: partial shape");
+    TORCH_CHECK(a.stride(1) == 1 && b.stride(1) == 1 && out.stride(1) == 1, "gemm_rs: unit inner strides");
+    TORCH_CHECK(out.size(1) == d.g.N && out.size(0) == (mode == 1 ? d.g.M : d.g.M / world), "gemm_rs: out shape");
     d.g.A = a.data_ptr(); d.g.lda = a.stride(0); d.g.a_mn_major = 0;
     d.g.B = b.data_ptr(); d.g.ldb = b.stride(0); d.g.b_mn_major = b_mn;
-    d.g.D = partial.data_ptr(); d.g.ldd = partial.stride(0);
-    d.peer_ptrs = reinterpret_cast<void* const*>(partial_ptrs);
+    d.g.D = nullptr; d.g.ldd = d.g.N;
+    d.peer_ptrs = reinterpret_cast<void* const*>(stage_ptrs);
     d.out_ptrs = reinterpret_cast<void* const*>(out_ptrs);
     d.flags_ptrs = reinterpret_cast<uint32_t* const*>(flags_ptrs);
     d.rank = rank; d.world = world; d.epoch = (uint32_t)epoch; d.mode = mode;
     d.out_local = out.data_ptr(); d.ld_out = out.stride(0);
-    d.comm_ctas = comm_ctas;
     CHECK_RC(b200::gemm_reduce_scatter(d, cur_stream()), "b200::gemm_rs");
 }
 
-// out = all_gather(x shards) @ b^T: communication CTAs pull the peers' shards into `gathered` while the GEMM CTAs
-// start on the local rows.
-void ag_gemm(const Tensor& x_local, int64_t x_ptrs, int64_t flags_ptrs, int64_t rank, int64_t world, int64_t epoch,
-             const Tensor& b, bool b_mn, Tensor& gathered, Tensor& out, int64_t flags, const optional<Tensor>& h,
-             int64_t comm_ctas) {
+// out = all_gather(x shards) @ b^T.  `gathered` is this rank's symmetric [M, K] buffer (gathered_ptrs its per-rank
+// pointer table): copy CTAs of the same launch push x_local into every rank's buffer while the GEMM CTAs start on the
+// local rows (read in place from x_local).
+void ag_gemm(const Tensor& x_local, int64_t gathered_ptrs, int64_t flags_ptrs, int64_t rank, int64_t world,
+             int64_t epoch, const Tensor& b, bool b_mn, Tensor& gathered, Tensor& out, int64_t flags,
+             const optional<Tensor>& h, int64_t comm_ctas) {
     CHECK_BF16(b); CHECK_BF16(x_local); CHECK_BF16(gathered); CHECK_BF16(out);
     c10::cuda::CUDAGuard guard(b.device());
     b200::GemmCommDesc d;
     d.m_local = x_local.size(0);
     d.g.M = d.m_local * world; d.g.K = x_local.size(1); d.g.N = b_mn ? b.size(1) : b.size(0);
-    TORCH_CHECK(gathered.size(0) == d.g.M && gathered.size(1) == d.g.K && gathered.stride(1) == 1, "ag_gemm: gathered shape");
+    TORCH_CHECK(x_local.is_contiguous() && gathered.is_contiguous(), "ag_gemm: contiguous shard / gathered buffer");
+    TORCH_CHECK(gathered.size(0) == d.g.M && gathered.size(1) == d.g.K, "ag_gemm: gathered shape");
     TORCH_CHECK(out.size(0) == d.g.M && out.size(1) == d.g.N, "ag_gemm: out shape");
-    d.g.A = gathered.data_ptr(); d.g.lda = x_local.stride(0); d.g.a_mn_major = 0;
+    d.g.A = gathered.data_ptr(); d.g.lda = d.g.K; d.g.a_mn_major = 0;
     d.g.B = b.data_ptr(); d.g.ldb = b.stride(0); d.g.b_mn_major = b_mn;
     d.g.D = out.data_ptr(); d.g.ldd = out.stride(0);
     d.g.flags = flags;
     if (h.has_value()) { d.g.H = h->data_ptr(); d.g.ldh = h->stride(0); }
-    d.peer_ptrs = reinterpret_cast<void* const*>(x_ptrs);
+    d.peer_ptrs = reinterpret_cast<void* const*>(gathered_ptrs);
     d.flags_ptrs = reinterpret_cast<uint32_t* const*>(flags_ptrs);
     d.rank = rank; d.world = world; d.epoch = (uint32_t)epoch;
-    d.out_local = gathered.data_ptr(); d.ld_out = gathered.stride(0);
+    d.out_local = gathered.data_ptr(); d.ld_out = d.g.K;
+    d.x_local = x_local.data_ptr();
     d.comm_ctas = comm_ctas;
     CHECK_RC(b200::allgather_gemm(d, cur_stream()), "b200::ag_gemm");
 }
@@ -326,6 +329,6 @@ TORCH_LIBRARY(b200, m) {
     m.def("attn_bwd(Tensor dout, Tensor q, Tensor k, Tensor v, Tensor out, Tensor lse, Tensor(a!) dq, Tensor(b!) dk, Tensor(c!) dv, Tensor(d!) delta, Tensor(e!) dq_acc, Tensor cu_seqlens, int max_seqlen, float scale, bool causal) -> ()", &attn_bwd);
     m.def("symm_barrier(int flags_ptrs, int rank, int world, int epoch) -> ()", &symm_barrier);
     m.def("reduce_scatter_adam(int grad_ptrs, int param_ptrs, int flags_ptrs, int rank, int world, int epoch, int shard_off, int shard_n, Tensor(a!) p, Tensor(b!) m, Tensor(c!) v, Tensor scalars, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2, float grad_div, int phase) -> ()", &reduce_scatter_adam);
-    m.def("gemm_rs(Tensor a, Tensor b, Tensor(a!) partial, Tensor(b!) out, int partial_ptrs, int out_ptrs, int flags_ptrs, int rank, int world, int epoch, bool b_mn, int mode, int comm_ctas) -> ()", &gemm_rs);
-    m.def("ag_gemm(Tensor x_local, int x_ptrs, int flags_ptrs, int rank, int world, int epoch, Tensor b, bool b_mn, Tensor(a!) gathered, Tensor(b!) out, int flags, Tensor? h, int comm_ctas) -> ()", &ag_gemm);
+    m.def("gemm_rs(Tensor a, Tensor b, Tensor(a!) out, int stage_ptrs, int out_ptrs, int flags_ptrs, int rank, int world, int epoch, bool b_mn, int mode) -> ()", &gemm_rs);
+    m.def("ag_gemm(Tensor x_local, int gathered_ptrs, int flags_ptrs, int rank, int world, int epoch, Tensor b, bool b_mn, Tensor(a!) gathered, Tensor(b!) out, int flags, Tensor? h, int comm_ctas) -> ()", &ag_gemm);
 }

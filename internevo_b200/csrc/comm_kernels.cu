@@ -7,8 +7,8 @@
 //                          sum of squares of the reduced slice accumulated for the global grad norm
 //  * adamw_bcast           Hybrid-ZeRO phase 1: unscale+clip+AdamW on the fp32 master slice, bf16 parameters pushed
 //                          straight into EVERY peer's parameter arena (the all-gather is the store)
-//  * gemm_reduce_scatter / allgather_gemm: the tcgen05 GEMM with communication CTAs riding in the same launch
-//                          (see gemm_sm100.cu: GemmCommArgs)
+//  * gemm_reduce_scatter / allgather_gemm: the tcgen05 GEMM fused with its collective in the same launch
+//                          (epilogue pushes / TMA copy CTAs, see gemm_sm100.cu: GemmCommArgs)
 //
 // Replaces: bucketed all_reduce(AVG) + flatten/unflatten + per-owner broadcast of the reference
 // (internlm/solver/optimizer/hybrid_zero_optim.py:455-523,809-837) and the NCCL calls around the TP linears
@@ -185,6 +185,7 @@ int allgather_gemm(const GemmCommDesc& d, cudaStream_t s) {
     c.mode = GEMM_COMM_ALL_GATHER;
     c.peer_ptrs = d.peer_ptrs; c.flags_ptrs = d.flags_ptrs; c.rank = d.rank; c.world = d.world; c.epoch = d.epoch;
     c.out_local = d.out_local; c.ld_out = d.ld_out; c.m_local = d.m_local; c.comm_ctas = d.comm_ctas;
+    c.x_local = d.x_local;
     return gemm_bf16_comm(d.g, c, s);
 }
 

@@ -27,7 +27,7 @@ int reduce_scatter_adam(const RsAdamDesc& d, cudaStream_t s);
 
 struct GemmCommDesc {
     GemmDesc g;
-    void* const* peer_ptrs = nullptr;   // AG: per-rank x shards; RS/AR: per-rank partial-product buffers
+    void* const* peer_ptrs = nullptr;   // AG: per-rank gathered buffers; RS/AR: per-rank staging [world, M/world, N]
     void* const* out_ptrs = nullptr;    // AR: per-rank output buffers
     uint32_t* const* flags_ptrs = nullptr;
     int rank = 0, world = 1;
@@ -36,7 +36,8 @@ struct GemmCommDesc {
     int64_t m_local = 0;   // ag_gemm: rows contributed by each rank
     void* out_local = nullptr;
     int64_t ld_out = 0;
-    int comm_ctas = 16;
+    const void* x_local = nullptr;      // ag_gemm: this rank's shard
+    int comm_ctas = 8;
 };
 int gemm_reduce_scatter(const GemmCommDesc& d, cudaStream_t s);
 int allgather_gemm(const GemmCommDesc& d, cudaStream_t s);

@@ -33,6 +33,7 @@ struct GemmCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES_COMM = SMEM_BYTES + 4 * 8192;  // + per-warp transpose staging of the RS push
 };
 
 struct GemmKernelArgs {
@@ -78,34 +79,45 @@ B200_DEVICE void item_coords(int item, const GemmKernelArgs& a, int& tm, int& tn
 
 struct CommKernelArgs {
     int mode;
-    void* const* peer_ptrs;
-    uint32_t* const* flags_ptrs;
-    void* const* out_ptrs;
+    void* const* peer_ptrs;        // AG: every rank's gathered A [M, K]; RS/AR: every rank's staging [world, m_local, N]
+    uint32_t* const* flags_ptrs;   // every rank's flag words for this operation
+    void* const* out_ptrs;         // AR: every rank's output [M, N]
     int rank, world;
     uint32_t epoch;
     int m_local;          // rows per rank
-    void* out_local;
+    void* out_local;      // RS: reduced rows [m_local, N]
     int64_t ld_out;
-    int gemm_ctas;        // CTAs [0, gemm_ctas) run the GEMM, the rest run the communication role
-    int64_t ld_peer;      // row stride (elements) of the peer buffers
+    int gemm_ctas;        // CTAs [0, gemm_ctas) run the GEMM, the rest (AG only) run the copy-engine role
+    const void* x_local;  // AG: this rank's shard [m_local, K] (contiguous)
 };
 
-B200_DEVICE uint32_t ld_acquire_gpu(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-B200_DEVICE void st_release_gpu(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 B200_DEVICE void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
-B200_DEVICE uint4 ld_v4_volatile(const void* p) {
+B200_DEVICE void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+B200_DEVICE uint4 ld_cg_v4(const void* p) {
     uint4 r;
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
+// 1-D bulk copies through the TMA unit (no tensor map): global -> shared with mbarrier completion, shared -> global
+// (works on peer-mapped addresses: the destination may live in another GPU's HBM behind NVLink).
+B200_DEVICE void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+B200_DEVICE void bulk_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+template <int N>
+B200_DEVICE void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+B200_DEVICE void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Rotation of the m-tile order: AG starts on the local shard, RS/AR finishes on it (peers get their rows first).
+// Rotation of the m-tile order: AG starts on the local shard (no waiting), then the shards in the order the peers push
+// them; RS/AR starts with the rows of rank+1 (pushed to their owner first) and finishes on the rows this rank owns.
 B200_DEVICE int comm_remap_m(int m, int tiles_m, const CommKernelArgs& c) {
     if (c.mode == GEMM_COMM_NONE) return m;
     const int per = tiles_m / c.world;
@@ -113,84 +125,63 @@ B200_DEVICE int comm_remap_m(int m, int tiles_m, const CommKernelArgs& c) {
     return (m + shift) % tiles_m;
 }
 
-// ---- communication role: runs in CTAs [gemm_ctas, gridDim.x) of the SAME kernel ------------------------------------
+// ---- all-gather copy-engine role: CTAs [gemm_ctas, gridDim.x) of the SAME kernel ------------------------------------
+// One thread per CTA drives the TMA unit: 128-row chunks of the local shard stream HBM -> shared -> every peer's
+// gathered-A buffer (posted NVLink writes, so nothing here waits on a round trip), then the chunk's flag is released on
+// that peer.  The peer's GEMM producer acquires the flag right before the first TMA load of a tile that needs the rows.
 template <int BN>
-B200_DEVICE void comm_role(const GemmKernelArgs& args, const CommKernelArgs& c) {
+B200_DEVICE void ag_push_role(const GemmKernelArgs& args, const CommKernelArgs& c, uint8_t* smem) {
+    constexpr int PIECE = 32 * 1024, SLOTS = 7, AHEAD = 2, PENDING = SLOTS - AHEAD - 1;
+    __shared__ __align__(8) uint64_t ld_bar[SLOTS];
+    if (threadIdx.x != 0) return;
     const int cta = blockIdx.x - c.gemm_ctas, ncta = gridDim.x - c.gemm_ctas;
-    uint32_t* my_flags = c.flags_ptrs[c.rank];
-    const int tiles_m = args.tiles_m, tiles_n = args.tiles_n;
-    const int per = tiles_m / c.world;  // m-tiles per rank
-    if (c.mode == GEMM_COMM_ALL_GATHER) {
-        // copy 128-row chunks of every rank's shard into the local gathered A (local shard first), flag each chunk
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(c.out_local);
-        const int K = args.K;
-        const int vec_per_row = K / 8;
-        for (int ch = cta; ch < tiles_m; ch += ncta) {
-            const int m = comm_remap_m(ch, tiles_m, c);  // same order in which the GEMM consumes
-            const int src_rank = m / per;
-            const int row0 = m * BM;
-            const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(c.peer_ptrs[src_rank]) +
-                                       (int64_t)(row0 - src_rank * c.m_local) * c.ld_peer;
-            const int rows = min(BM, args.M - row0);
-            for (int v = threadIdx.x; v < rows * vec_per_row; v += NUM_THREADS) {
-                const int r = v / vec_per_row, cc = (v - r * vec_per_row) * 8;
-                const uint4 x = ld_v4_volatile(src + (int64_t)r * c.ld_peer + cc);
-                *reinterpret_cast<uint4*>(dst + (int64_t)(row0 + r) * c.ld_out + cc) = x;
-            }
-            __threadfence();
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                fence_proxy_async_global();  // generic-proxy stores above -> TMA (async proxy) reads in the GEMM CTAs
-                st_release_gpu(my_flags + m, c.epoch);
-            }
+    for (int i = 0; i < SLOTS; ++i) mbar_init(&ld_bar[i], 1);
+    fence_barrier_init();
+    const int per = args.tiles_m / c.world;
+    const int64_t row_bytes = (int64_t)args.K * 2;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(c.x_local);
+    const int64_t dst_base = (int64_t)c.rank * c.m_local * row_bytes;
+    auto chunk_bytes = [&](int ch) { return (int64_t)min(BM, c.m_local - ch * BM) * row_bytes; };
+
+    // two cursors over this CTA's piece sequence: loads run AHEAD pieces in front of the stores
+    int ld_ch = cta, st_ch = cta;
+    int64_t ld_o = 0, st_o = 0;
+    uint32_t n_ld = 0, n_st = 0;
+    auto issue_load = [&]() {
+        const int64_t cb = chunk_bytes(ld_ch);
+        const uint32_t n = static_cast<uint32_t>(min((int64_t)PIECE, cb - ld_o));
+        const int slot = n_ld % SLOTS;
+        bulk_wait_read<PENDING>();  // the stores that last read this slot (piece n_ld - SLOTS) have drained it
+        mbar_expect_tx(&ld_bar[slot], n);
+        bulk_load_1d(smem + slot * PIECE, src + (int64_t)ld_ch * BM * row_bytes + ld_o, n, &ld_bar[slot]);
+        ++n_ld;
+        ld_o += PIECE;
+        if (ld_o >= cb) { ld_o = 0; ld_ch += ncta; }
+    };
+    for (int i = 0; i < AHEAD && ld_ch < per; ++i) issue_load();
+    while (st_ch < per) {
+        if (ld_ch < per) issue_load();
+        const int64_t cb = chunk_bytes(st_ch);
+        const uint32_t n = static_cast<uint32_t>(min((int64_t)PIECE, cb - st_o));
+        const int slot = n_st % SLOTS;
+        mbar_wait(&ld_bar[slot], (n_st / SLOTS) & 1);
+        const int64_t off = dst_base + (int64_t)st_ch * BM * row_bytes + st_o;
+        for (int p = 0; p < c.world; ++p) {
+            const int pr = (c.rank + 1 + p) % c.world;  // peers first, the local copy (kept for wgrad) last
+            bulk_store_1d(reinterpret_cast<uint8_t*>(c.peer_ptrs[pr]) + off, smem + slot * PIECE, n);
         }
-        return;
-    }
-    // REDUCE_SCATTER / ALL_REDUCE: reduce the tiles of my row slice as soon as every rank has produced them
-    const int my_m0 = c.rank * per;
-    const int n_mine = per * tiles_n;
-    for (int t = cta; t < n_mine; t += ncta) {
-        // visit my tiles in the order the producers emit them (m rotates, n fastest inside the GROUP_M raster is
-        // irrelevant here: every producer finishes my slice early because of comm_remap_m)
-        const int tm = my_m0 + t / tiles_n, tn = t % tiles_n;
-        const int tile = tm * tiles_n + tn;
-        if (threadIdx.x < c.world) {
-            const uint32_t* f = my_flags + (int64_t)threadIdx.x * tiles_m * tiles_n + tile;
-            while (static_cast<int32_t>(ld_acquire_sys(f) - c.epoch) < 0) {
-            }
+        tma_store_commit();
+        ++n_st;
+        st_o += PIECE;
+        if (st_o >= cb) {
+            bulk_wait_all<0>();  // every write of this chunk has been performed
+            fence_proxy_async_all();
+            fence_acq_rel_sys();
+            const int m = c.rank * per + st_ch;
+            for (int p = 0; p < c.world; ++p) st_release_sys(c.flags_ptrs[(c.rank + 1 + p) % c.world] + m, c.epoch);
+            st_o = 0;
+            st_ch += ncta;
         }
-        __syncthreads();
-        const int row0 = tm * BM, col0 = tn * BN;
-        const int rows = min(BM, args.M - row0), cols = min(BN, args.N - col0);
-        const int vec_per_row = cols / 8;
-        for (int v = threadIdx.x; v < rows * vec_per_row; v += NUM_THREADS) {
-            const int r = v / vec_per_row, cc = (v - r * vec_per_row) * 8;
-            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            for (int p = 0; p < c.world; ++p) {
-                const int pr = (c.rank + p) % c.world;
-                const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(c.peer_ptrs[pr]) +
-                                           (int64_t)(row0 + r) * c.ld_peer + col0 + cc;
-                const uint4 x = ld_v4_volatile(src);
-                float2 a = unpack_bf16(x.x), b = unpack_bf16(x.y), cq = unpack_bf16(x.z), d = unpack_bf16(x.w);
-                acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
-                acc[4] += cq.x; acc[5] += cq.y; acc[6] += d.x; acc[7] += d.y;
-            }
-            uint4 o;
-            o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
-            o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
-            if (c.mode == GEMM_COMM_REDUCE_SCATTER) {
-                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(c.out_local) +
-                                     (int64_t)(row0 - my_m0 * BM + r) * c.ld_out + col0 + cc;
-                *reinterpret_cast<uint4*>(dst) = o;
-            } else {
-                for (int p = 0; p < c.world; ++p) {
-                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(c.out_ptrs[(c.rank + p) % c.world]) +
-                                         (int64_t)(row0 + r) * c.ld_out + col0 + cc;
-                    *reinterpret_cast<uint4*>(dst) = o;
-                }
-            }
-        }
-        __syncthreads();
     }
 }
 
@@ -200,16 +191,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                  const __grid_constant__ CUtensorMap tmap_bt, const GemmKernelArgs args, const CommKernelArgs comm) {
     using Cfg = GemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     if constexpr (COMM) {
         if (static_cast<int>(blockIdx.x) >= comm.gemm_ctas) {
-            comm_role<BN>(args, comm);
+            ag_push_role<BN>(args, comm, smem);
             return;
         }
     }
     const int grid_ctas = COMM ? comm.gemm_ctas : static_cast<int>(gridDim.x);
-
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
@@ -252,17 +242,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int tile = blockIdx.x; tile < num_items; tile += grid_ctas) {
                 int tm, tn, n_off, width;
                 item_coords<BN>(tile, args, tm, tn, n_off, width);
+                bool own_rows = false;
                 if constexpr (COMM) {
                     tm = comm_remap_m(tm, args.tiles_m, comm);
                     if (comm.mode == GEMM_COMM_ALL_GATHER) {
-                        // rows of this tile are being pulled from their owner by the communication CTAs
-                        const uint32_t* f = comm.flags_ptrs[comm.rank] + tm;
-                        while (static_cast<int32_t>(ld_acquire_gpu(f) - comm.epoch) < 0) {
+                        own_rows = tm / (args.tiles_m / comm.world) == comm.rank;
+                        if (!own_rows) {
+                            // these rows are pushed into the local gathered buffer by their owner's copy CTAs
+                            const uint32_t* f = comm.flags_ptrs[comm.rank] + tm;
+                            while (static_cast<int32_t>(ld_acquire_sys(f) - comm.epoch) < 0) {
+                            }
+                            fence_proxy_async_all();
                         }
-                        fence_proxy_async_global();
                     }
                 }
                 const int m0 = tm * BM, n0 = tn * BN + n_off;
+                const int m0_own = m0 - comm.rank * comm.m_local;
                 const int nb64 = width / 64;  // B arrives in 64-row (K-major) or 64-column (MN-major) boxes
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -270,7 +265,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
                     uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
                     const int k0 = kb * BK;
-                    if (!args.a_mn) {
+                    if (COMM && own_rows) {  // the local shard is read in place (tmap_bt doubles as its map)
+                        tma_load_2d(sa, &tmap_bt, &full_bar[stage], k0, m0_own);
+                    } else if (!args.a_mn) {
                         tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);
                     } else {
 #pragma unroll
@@ -349,11 +346,76 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if constexpr (COMM) tm = comm_remap_m(tm, args.tiles_m, comm);
             const int row = tm * BM + q * 32 + lane;
             const int n0 = tn * BN + n_off;
+            // reduce-scatter / all-reduce: rows owned by a peer are pushed straight into that peer's staging slot,
+            // rows owned by this rank are reduced with what the peers pushed and written as the final result
+            bool rs_mode = false, own = false;
+            int owner = 0, row_local = 0;
+            if constexpr (COMM) {
+                rs_mode = comm.mode == GEMM_COMM_REDUCE_SCATTER || comm.mode == GEMM_COMM_ALL_REDUCE;
+                if (rs_mode) {
+                    const int per = args.tiles_m / comm.world;
+                    owner = tm / per;
+                    own = owner == comm.rank;
+                    row_local = row - owner * comm.m_local;
+                    if (own) {
+                        if (warp == 2 && lane < comm.world && lane != comm.rank) {
+                            const uint32_t* f = comm.flags_ptrs[comm.rank] + (int64_t)lane * per * args.tiles_n +
+                                                (tm - owner * per) * args.tiles_n + tn;
+                            while (static_cast<int32_t>(ld_acquire_sys(f) - comm.epoch) < 0) {
+                            }
+                        }
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                    }
+                }
+            }
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+            bool pushed = false;
+            if constexpr (COMM) {
+                if (rs_mode && !own) {
+                    // Push the bf16 partial tile into its owner's staging slot.  NVLink wants whole 128-byte requests:
+                    // every warp transposes 32 rows x 128 columns through shared memory (16-byte units XOR-swizzled by
+                    // row) so that 16 lanes store one contiguous 256-byte row segment.
+                    uint8_t* wst = smem + STAGES * Cfg::STAGE_BYTES + 256 + q * 8192;
+                    __nv_bfloat16* dbase = reinterpret_cast<__nv_bfloat16*>(comm.peer_ptrs[owner]) +
+                                           ((int64_t)comm.rank * comm.m_local + (tm * BM + q * 32 - owner * comm.m_local)) *
+                                               args.N + n0;
 #pragma unroll 1
-            for (int c = 0; c < width; c += 32) {
+                    for (int half = 0; half < BN / 128; ++half) {
+#pragma unroll 1
+                        for (int c4 = 0; c4 < 4; ++c4) {
+                            uint32_t r[32];
+                            tmem_ld_32x32b_x32(taddr + half * 128 + c4 * 32, r);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                uint4 o;
+                                o.x = pack_bf16(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1]));
+                                o.y = pack_bf16(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+                                o.z = pack_bf16(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+                                o.w = pack_bf16(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+                                const int u = c4 * 4 + j;
+                                *reinterpret_cast<uint4*>(wst + lane * 256 + ((u ^ (lane & 7)) << 4)) = o;
+                            }
+                        }
+                        __syncwarp();
+                        const int u = lane & 15;
+                        const int col = n0 + half * 128 + u * 8;
+#pragma unroll 4
+                        for (int rr = 0; rr < 32; rr += 2) {
+                            const int rw = rr + (lane >> 4);
+                            const uint4 o = *reinterpret_cast<const uint4*>(wst + rw * 256 + ((u ^ (rw & 7)) << 4));
+                            if (col < args.N)
+                                *reinterpret_cast<uint4*>(dbase + (int64_t)rw * args.N + half * 128 + u * 8) = o;
+                        }
+                        __syncwarp();
+                    }
+                    pushed = true;
+                }
+            }
+#pragma unroll 1
+            for (int c = 0; c < width && !pushed; c += 32) {
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(taddr + c, r);
                 tmem_ld_wait();
@@ -363,6 +425,53 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
                     const int ncols = min(32, args.N - col);  // multiple of 8 (host asserts N % 8 == 0)
+                    if constexpr (COMM) {
+                        if (rs_mode) {
+                            {
+                                const __nv_bfloat16* mine = reinterpret_cast<const __nv_bfloat16*>(
+                                    comm.peer_ptrs[comm.rank]);
+                                for (int p = 1; p < comm.world; ++p) {
+                                    const int sl = (comm.rank + p) % comm.world;
+                                    const __nv_bfloat16* src = mine + ((int64_t)sl * comm.m_local + row_local) * args.N + col;
+#pragma unroll
+                                    for (int i = 0; i < 32; i += 8) {
+                                        if (i < ncols) {
+                                            const uint4 x = ld_cg_v4(src + i);
+                                            float2 a = unpack_bf16(x.x), b = unpack_bf16(x.y), cq = unpack_bf16(x.z),
+                                                   dd = unpack_bf16(x.w);
+                                            v[i] += a.x; v[i + 1] += a.y; v[i + 2] += b.x; v[i + 3] += b.y;
+                                            v[i + 4] += cq.x; v[i + 5] += cq.y; v[i + 6] += dd.x; v[i + 7] += dd.y;
+                                        }
+                                    }
+                                }
+                                uint4 o[4];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    o[i].x = pack_bf16(v[8 * i], v[8 * i + 1]);
+                                    o[i].y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+                                    o[i].z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+                                    o[i].w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+                                }
+                                if (comm.mode == GEMM_COMM_REDUCE_SCATTER) {
+                                    __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(comm.out_local) +
+                                                       (int64_t)row_local * comm.ld_out + col;
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i)
+                                        if (8 * i < ncols) *reinterpret_cast<uint4*>(d + 8 * i) = o[i];
+                                } else {
+                                    for (int p = 0; p < comm.world; ++p) {
+                                        __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(
+                                                               comm.out_ptrs[(comm.rank + p) % comm.world]) +
+                                                           (int64_t)row * comm.ld_out + col;
+#pragma unroll
+                                        for (int i = 0; i < 4; ++i)
+                                            if (8 * i < ncols) *reinterpret_cast<uint4*>(d + 8 * i) = o[i];
+                                    }
+                                }
+                            }
+                            continue;
+                        }
+                    }
                     if (args.bias != nullptr) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 8) {
@@ -443,14 +552,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             if constexpr (COMM) {
-                if (comm.mode == GEMM_COMM_REDUCE_SCATTER || comm.mode == GEMM_COMM_ALL_REDUCE) {
-                    // the partial tile is in (symmetric) global memory: tell the owner of these rows
+                if (rs_mode && !own) {
+                    // the partial tile has been stored into its owner's staging slot: publish it there
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                     if (warp == 2 && lane == 0) {
-                        const int owner = tm / (args.tiles_m / comm.world);
+                        const int per = args.tiles_m / comm.world;
                         fence_acq_rel_sys();
-                        st_release_sys(comm.flags_ptrs[owner] + (int64_t)comm.rank * args.tiles_m * args.tiles_n +
-                                           tm * args.tiles_n + tn,
+                        st_release_sys(comm.flags_ptrs[owner] + (int64_t)comm.rank * per * args.tiles_n +
+                                           (tm - owner * per) * args.tiles_n + tn,
                                        comm.epoch);
                     }
                 }
@@ -627,7 +736,13 @@ static int launch(const GemmDesc& g, cudaStream_t stream) {
     return 0;
 }
 
-// GEMM + communication CTAs in one launch. A (AG) / D (RS, AR) live in symmetric memory; see GemmCommArgs.
+// GEMM fused with its tensor-parallel collective in ONE launch (see GemmCommArgs).
+//   ALL_GATHER      A = all-gather of row shards: copy CTAs push the local shard into every peer's gathered buffer
+//                   through the TMA unit; the GEMM starts on the local shard (read in place) and acquires per-chunk
+//                   flags for the rest.
+//   REDUCE_SCATTER  the epilogue stores partial tiles owned by a peer directly into that peer's staging slot (posted
+//   / ALL_REDUCE    NVLink writes) and reduces the tiles this rank owns, which are scheduled last, with the slots the
+//                   peers filled.  No extra CTAs, no second pass over the output.
 int gemm_bf16_comm(const GemmDesc& g, const GemmCommArgs& c, cudaStream_t stream) {
     constexpr int BN = 256;
     using Cfg = GemmCfg<BN>;
@@ -635,15 +750,20 @@ int gemm_bf16_comm(const GemmDesc& g, const GemmCommArgs& c, cudaStream_t stream
     const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
     if (g.M % (BM * c.world) != 0) return -21;  // every rank owns whole 128-row tiles
     if (g.N % 8 != 0 || g.K % 8 != 0) return -22;
-    CUtensorMap ta, tb;
+    const bool ag = c.mode == GEMM_COMM_ALL_GATHER;
+    CUtensorMap ta, tb, tx;
     int rc;
-    const void* a_ptr = c.mode == GEMM_COMM_ALL_GATHER ? c.out_local : g.A;
-    const int64_t a_ld = c.mode == GEMM_COMM_ALL_GATHER ? c.ld_out : g.lda;
-    rc = make_tmap_2d_bf16(&ta, a_ptr, g.K, g.M, a_ld, BK, BM);
+    // A: the gathered buffer (AG) or the local activations (RS / AR)
+    rc = make_tmap_2d_bf16(&ta, ag ? c.out_local : g.A, g.K, g.M, ag ? (int64_t)g.K : g.lda, BK, BM);
     if (rc) return rc;
     if (!g.b_mn_major) rc = make_tmap_2d_bf16(&tb, g.B, g.K, g.N, g.ldb, BK, BN);
     else               rc = make_tmap_2d_bf16(&tb, g.B, g.N, g.K, g.ldb, 64, BK);
     if (rc) return rc;
+    tx = tb;
+    if (ag) {  // this rank's shard, read in place
+        rc = make_tmap_2d_bf16(&tx, c.x_local, g.K, c.m_local, g.K, BK, BM);
+        if (rc) return rc;
+    }
     GemmKernelArgs a;
     a.tiles_full = tiles_m * tiles_n; a.tail_split = 1;
     a.M = g.M; a.N = g.N; a.K = g.K;
@@ -654,21 +774,20 @@ int gemm_bf16_comm(const GemmDesc& g, const GemmCommArgs& c, cudaStream_t stream
     CommKernelArgs k;
     k.mode = c.mode; k.peer_ptrs = c.peer_ptrs; k.flags_ptrs = c.flags_ptrs; k.out_ptrs = c.out_ptrs;
     k.rank = c.rank; k.world = c.world; k.epoch = c.epoch; k.m_local = (int)c.m_local;
-    k.out_local = c.out_local; k.ld_out = c.ld_out;
-    k.ld_peer = c.mode == GEMM_COMM_ALL_GATHER ? g.lda : g.ldd;
+    k.out_local = c.out_local; k.ld_out = c.ld_out; k.x_local = c.x_local;
     const int sms = num_sms();
-    const int comm_ctas = c.comm_ctas > 0 ? c.comm_ctas : 16;
+    const int comm_ctas = ag ? (c.comm_ctas > 0 ? c.comm_ctas : 8) : 0;
     int gemm_ctas = sms - comm_ctas;
     if (gemm_ctas > tiles_m * tiles_n) gemm_ctas = tiles_m * tiles_n;
     k.gemm_ctas = gemm_ctas;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(gemm_bf16_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 Cfg::SMEM_BYTES) != cudaSuccess)
+                                 Cfg::SMEM_BYTES_COMM) != cudaSuccess)
             return -3;
         attr_set = true;
     }
-    gemm_bf16_kernel<BN, true><<<gemm_ctas + comm_ctas, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tb, a, k);
+    gemm_bf16_kernel<BN, true><<<gemm_ctas + comm_ctas, NUM_THREADS, Cfg::SMEM_BYTES_COMM, stream>>>(ta, tb, tx, a, k);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 

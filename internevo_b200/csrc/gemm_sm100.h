@@ -35,25 +35,26 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream);
 // Enable / disable splitting the tiles of the last partial wave into column slices (default on).
 void set_gemm_tail_split(int on);
 
-// ---- GEMM with communication CTAs in the same launch (tensor parallel fused paths) ------------------------------
+// ---- GEMM fused with its tensor-parallel collective (one launch, peer memory over NVLink) -------------------------
 enum GemmCommMode : int {
     GEMM_COMM_NONE = 0,
-    GEMM_COMM_ALL_GATHER = 1,      // A = all-gather of per-rank row shards, pulled from peers while early tiles compute
-    GEMM_COMM_REDUCE_SCATTER = 2,  // D partial -> each rank reduces its row slice from all peers' partials
+    GEMM_COMM_ALL_GATHER = 1,      // A = all-gather of per-rank row shards, pushed by copy CTAs while early tiles compute
+    GEMM_COMM_REDUCE_SCATTER = 2,  // epilogue pushes partial tiles to their owner; the owner's epilogue reduces
     GEMM_COMM_ALL_REDUCE = 3,      // as above, reduced rows are pushed into every peer's output
 };
 
 struct GemmCommArgs {
     int mode = GEMM_COMM_NONE;
-    void* const* peer_ptrs = nullptr;      // AG: per-rank x shard [m_local, K]; RS/AR: per-rank partial D [M, N]
-    uint32_t* const* flags_ptrs = nullptr; // per-rank flag arrays (uint32, >= 2 * tiles + 16 entries)
+    void* const* peer_ptrs = nullptr;      // AG: per-rank gathered A [M, K]; RS/AR: per-rank staging [world, m_local, N]
+    uint32_t* const* flags_ptrs = nullptr; // per-rank flag arrays (uint32): AG tiles_m words, RS/AR tiles_m * tiles_n
     void* const* out_ptrs = nullptr;       // AR: per-rank final output [M, N]
     int rank = 0, world = 1;
     uint32_t epoch = 0;
     int64_t m_local = 0;                   // rows per rank (AG: contributed, RS: owned)
-    void* out_local = nullptr;             // AG: gathered A [M, K]; RS: reduced rows [m_local, N]
-    int64_t ld_out = 0;
-    int comm_ctas = 16;
+    void* out_local = nullptr;             // AG: this rank's gathered A [M, K] (contiguous); RS: reduced rows [m_local, N]
+    int64_t ld_out = 0;                    // RS / AR: row stride of the output
+    const void* x_local = nullptr;         // AG: this rank's shard [m_local, K] (contiguous)
+    int comm_ctas = 8;                     // AG: number of copy CTAs
 };
 
 int gemm_bf16_comm(const GemmDesc& g, const GemmCommArgs& c, cudaStream_t stream);

@@ -27,53 +27,67 @@ logger = get_logger(__file__)
 
 
 class TPFusedBackend:
-    """Symmetric scratch + launch logic for the fused TP linears of one process group."""
+    """Symmetric scratch + launch logic for the fused TP linears of one process group.
 
-    def __init__(self, group: dist.ProcessGroup, comm_ctas: int = 16):
+    ``ag_gemm``  copy CTAs push this rank's activation shard into every peer's gathered buffer through the TMA unit
+                 while the GEMM CTAs of the same launch start on the local rows.
+    ``gemm_rs``  the GEMM epilogue stores partial tiles owned by a peer straight into that peer's staging slot over
+                 NVLink and reduces the tiles this rank owns (scheduled last) with what the peers pushed.
+    Scratch buffers are ping-pong pairs keyed by shape; a stream-ordered device barrier (6 us) in front of every launch
+    guarantees that the slot being overwritten on a peer is no longer in use there.
+    """
+
+    def __init__(self, group: dist.ProcessGroup, comm_ctas: int = 8):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.flags = symm.flags_for(group)
         self.comm_ctas = comm_ctas
-        self._x: Dict[Tuple[int, int], list] = {}        # (m_local, K) -> [SymmBuffer, SymmBuffer] ping-pong
-        self._partial: Dict[Tuple[int, int], list] = {}  # (M, N) -> ping-pong partial-product buffers
+        self._gath: Dict[Tuple[int, int], list] = {}     # (M, K) -> ping-pong gathered-activation buffers
+        self._stage: Dict[Tuple[int, int], list] = {}    # (M, N) -> ping-pong [world, M/world, N] staging
         self._out: Dict[Tuple[int, int], list] = {}      # (M, N) -> ping-pong all-reduce outputs
-        self._tick = 0
 
     def supports(self, M: int, x: torch.Tensor, weight: torch.Tensor) -> bool:
-        """whole 128-row tiles per rank, bf16, 16-byte aligned rows"""
+        """bf16, whole 128-row tiles per rank, 16-byte aligned rows, flag space for every tile."""
         return (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and M % (128 * self.world) == 0
-                and x.shape[1] % 8 == 0 and weight.shape[0] % 8 == 0 and x.stride(1) == 1 and weight.stride(1) == 1)
+                and x.shape[1] % 8 == 0 and weight.shape[0] % 8 == 0 and weight.shape[1] % 8 == 0
+                and x.stride(-1) == 1 and weight.stride(1) == 1
+                and (M // 128) * ((max(weight.shape) + 255) // 256) <= symm.RS_FLAG_WORDS)
 
     def _pp(self, cache, key, numel):
         if key not in cache:
-            cache[key] = [symm.SymmBuffer(numel, torch.bfloat16, self.group, zero=False) for _ in range(2)]
-        self._tick += 1
-        return cache[key][self._tick & 1]
+            cache[key] = [0] + [symm.SymmBuffer(numel, torch.bfloat16, self.group, zero=False) for _ in range(2)]
+        ent = cache[key]
+        ent[0] ^= 1
+        return ent[1 + ent[0]]
 
     # -- all-gather -> GEMM -----------------------------------------------------------------------------------------
-    def ag_gemm(self, x: torch.Tensor, weight: torch.Tensor, group=None, keep_gathered: bool = False):
-        """``all_gather(x, dim=0) @ weight^T``; returns ``(y, gathered_x)``."""
+    def ag_gemm(self, x: torch.Tensor, weight: torch.Tensor, group=None, keep_gathered: bool = False,
+                b_mn: bool = False):
+        """``all_gather(x, dim=0) @ weight^T`` (``b_mn``: ``@ weight``); returns ``(y, gathered_x)``.
+
+        ``gathered_x`` lives in a recycled symmetric slot: it is valid until the second next call with the same shape;
+        pass ``keep_gathered=True`` to get a private copy (e.g. to save it for backward)."""
+        x = x.contiguous()
         m_local, K = x.shape
-        N = weight.shape[0]
+        N = weight.shape[1] if b_mn else weight.shape[0]
         M = m_local * self.world
-        xs = self._pp(self._x, (m_local, K), m_local * K)
-        xs.tensor.view(m_local, K).copy_(x)  # publish this rank's shard in peer-visible memory
-        gathered = torch.empty(M, K, device=x.device, dtype=x.dtype)
+        gb = self._pp(self._gath, (M, K), M * K)
+        gathered = gb.tensor.view(M, K)
         out = torch.empty(M, N, device=x.device, dtype=x.dtype)
-        self.flags.barrier()  # every shard is published (and the previous user of this scratch slot is done)
-        torch.ops.b200.ag_gemm(xs.tensor.view(m_local, K), xs.table_ptr(0), symm.ag_flag_table(self.flags), self.rank,
-                               self.world, self.flags.next_epoch(), weight, False, gathered, out, 0, None,
-                               self.comm_ctas)
+        self.flags.barrier()  # the slot is free on every rank (its previous reader is stream-ordered before this)
+        torch.ops.b200.ag_gemm(x, gb.table_ptr(0), symm.ag_flag_table(self.flags), self.rank, self.world,
+                               self.flags.next_epoch(), weight, b_mn, gathered, out, 0, None, self.comm_ctas)
         _bump(2)
-        return out, gathered
+        return out, (gathered.clone() if keep_gathered else gathered)
 
     # -- GEMM -> reduce-scatter / all-reduce ------------------------------------------------------------------------------
-    def gemm_rs(self, x: torch.Tensor, weight: torch.Tensor, group=None, all_reduce: bool = False) -> torch.Tensor:
-        """``reduce_scatter(x @ weight^T, dim=0)`` (or all-reduce)."""
+    def gemm_rs(self, x: torch.Tensor, weight: torch.Tensor, group=None, all_reduce: bool = False,
+                b_mn: bool = False) -> torch.Tensor:
+        """``reduce_scatter(x @ weight^T, dim=0)`` (or all-reduce; ``b_mn``: ``x @ weight``)."""
         M, K = x.shape
-        N = weight.shape[0]
-        part = self._pp(self._partial, (M, N), M * N)
+        N = weight.shape[1] if b_mn else weight.shape[0]
+        stage = self._pp(self._stage, (M, N), M * N)
         if all_reduce:
             outb = self._pp(self._out, (M, N), M * N)
             out = outb.tensor.view(M, N)
@@ -81,13 +95,12 @@ class TPFusedBackend:
         else:
             out = torch.empty(M // self.world, N, device=x.device, dtype=x.dtype)
             out_ptrs = 0
-        self.flags.barrier()  # scratch slot is free on every rank
-        torch.ops.b200.gemm_rs(x, weight, part.tensor.view(M, N), out, part.table_ptr(0), out_ptrs,
-                               symm.rs_flag_table(self.flags), self.rank, self.world, self.flags.next_epoch(), False,
-                               1 if all_reduce else 0, self.comm_ctas)
+        self.flags.barrier()  # staging / output slots are free on every rank
+        torch.ops.b200.gemm_rs(x, weight, out, stage.table_ptr(0), out_ptrs, symm.rs_flag_table(self.flags), self.rank,
+                               self.world, self.flags.next_epoch(), b_mn, 1 if all_reduce else 0)
         _bump(2)
         if all_reduce:
-            self.flags.barrier()  # every rank has pushed its slice into everybody's output
+            self.flags.barrier()  # every rank has pushed its rows into everybody's output
             return out.clone()  # detach from the ping-pong slot (it is recycled two calls later)
         return out
 

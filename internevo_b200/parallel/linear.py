@@ -102,6 +102,7 @@ class _ParallelLinearFn(torch.autograd.Function):
         sp = mode in ("msp", "fsp") and ws > 1
         dy = dy.contiguous()
         dx = dw = db = None
+        fused = _fused_backend if (_fused_backend is not None and ws > 1 and dy.is_cuda) else None
         if kind == "column":
             handle_x = None
             if sp and mode == "fsp":
@@ -110,12 +111,16 @@ class _ParallelLinearFn(torch.autograd.Function):
                 x_full = x
             handle = None
             if ctx.needs_input_grad[0]:
-                dx = _mm_dgrad(dy, weight)
-                if ws > 1:
-                    if sp:
-                        dx, handle = reduce_scatter_raw(dx, group, async_op=True)
-                    else:
-                        dx, handle = all_reduce_raw(dx, group, async_op=True)
+                if fused is not None and fused.supports(dy.shape[0], dy, weight):
+                    # dgrad with the reduce-scatter / all-reduce done by the GEMM epilogue over NVLink
+                    dx = fused.gemm_rs(dy, weight, group, all_reduce=not sp, b_mn=True)
+                else:
+                    dx = _mm_dgrad(dy, weight)
+                    if ws > 1:
+                        if sp:
+                            dx, handle = reduce_scatter_raw(dx, group, async_op=True)
+                        else:
+                            dx, handle = all_reduce_raw(dx, group, async_op=True)
             if handle_x is not None:
                 handle_x.wait()
             if ctx.needs_input_grad[1]:
@@ -125,10 +130,14 @@ class _ParallelLinearFn(torch.autograd.Function):
             if handle is not None:
                 handle.wait()
         else:  # row
-            if sp:
-                dy, _ = all_gather_raw(dy, group)
-            if ctx.needs_input_grad[0]:
-                dx = _mm_dgrad(dy, weight)
+            if sp and fused is not None and ctx.needs_input_grad[0] and fused.supports(dy.shape[0] * ws, dy, weight):
+                # all-gather(dy) pushed by copy CTAs while the dgrad GEMM runs; the gathered dy feeds wgrad right away
+                dx, dy = fused.ag_gemm(dy, weight, group, b_mn=True)
+            else:
+                if sp:
+                    dy, _ = all_gather_raw(dy, group)
+                if ctx.needs_input_grad[0]:
+                    dx = _mm_dgrad(dy, weight)
             if ctx.needs_input_grad[1]:
                 dw = _mm_wgrad(dy, x, weight)
             if ctx.has_bias:

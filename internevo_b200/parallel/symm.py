@@ -19,15 +19,17 @@ import torch.distributed as dist
 _BARRIER_SLOTS = 1024        # [0, 1024): barrier flags (one slot per peer)
 _AG_BASE = 1024              # [1024, 8192): all-gather chunk flags (local)
 _RS_BASE = 8192              # [8192, ...): reduce-scatter tile flags, `world` blocks of tiles each
-FLAG_WORDS = 8192 + 8 * 8192
+RS_FLAG_WORDS = 8 * 8192
+FLAG_WORDS = 8192 + RS_FLAG_WORDS
 
 
 def symm_available() -> bool:
     if not torch.cuda.is_available():
         return False
     try:
-        import torch.distributed._symmetric_memory  # noqa: F401
+        import importlib
 
+        importlib.import_module("torch.distributed._symmetric_memory")
         return True
     except Exception:
         return False

@@ -69,6 +69,8 @@ def main():
         dist.reduce_scatter_tensor(ref_rs, full)
         out = be.gemm_rs(x, w, all_reduce=False)
         r = rel(out, ref_rs)
+        out_b = be.gemm_rs(x, w.t().contiguous(), all_reduce=False, b_mn=True)
+        ok &= rel(out_b, ref_rs) < 2e-2
         ok &= r < 2e-2
         stage(f"gemm_rs {name} rel={r}")
         ref_ar = full.clone()
@@ -103,6 +105,10 @@ def main():
         ref = ops.matmul(xg, w)
         out, gathered = be.ag_gemm(xs, w)
         r = rel(out, ref)
+        # dgrad form: all_gather(x) @ w_t with w_t given [K, N] (MN-major B)
+        wt = w.t().contiguous()
+        out2, _ = be.ag_gemm(xs, wt, b_mn=True)
+        ok &= rel(out2, ref) < 2e-2
         ok &= r < 2e-2 and torch.equal(gathered, xg)
         stage(f"ag_gemm {name} rel={r} gathered_equal={torch.equal(gathered, xg)}")
 
@@ -111,7 +117,13 @@ def main():
             dist.all_gather_into_tensor(g, xs)
             ops.matmul(g, w)
 
+        sweep = {}
+        for cc in (2, 4, 8, 16):
+            be.comm_ctas = cc
+            sweep[cc] = round(timed(lambda: be.ag_gemm(xs, w)), 4)
+        be.comm_ctas = 8
         res[f"ag_gemm_{name}"] = {"rel_err": r, "fused_ms": round(timed(lambda: be.ag_gemm(xs, w)), 4),
+                                  "fused_ms_by_copy_ctas": sweep,
                                   "nccl+gemm_ms": round(timed(nccl_ag), 4),
                                   "gemm_only_ms": round(timed(lambda: ops.matmul(xg, w)), 4)}
     # ---- fused ZeRO kernels: reduce-scatter (mean) + sumsq, AdamW + parameter push
