@@ -25,11 +25,14 @@ static constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B atom row
 static constexpr int UMMA_K = 16;
 static constexpr int NUM_THREADS = 192;
 
-template <int BN>
+// CG = CTAs cooperating on one tile (tcgen05 cta_group): with CG == 2 a cluster of two CTAs computes a 256 x BN tile,
+// every CTA stages its own 128 rows of A and HALF of B, and the pair's tensor cores read both halves -> one third less
+// shared-memory traffic per SM and room for a deeper ring.
+template <int BN, int CG = 1>
 struct GemmCfg {
-    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int STAGES = (BN == 256 && CG == 1) ? 4 : 6;
     static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int B_BYTES = (BN / CG) * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -185,11 +188,13 @@ B200_DEVICE void ag_push_role(const GemmKernelArgs& args, const CommKernelArgs& 
     }
 }
 
-template <int BN, bool COMM>
+template <int BN, bool COMM, int CG = 1>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_bt, const GemmKernelArgs args, const CommKernelArgs comm) {
-    using Cfg = GemmCfg<BN>;
+    static_assert(CG == 1 || (!COMM && BN == 256), "2-CTA tiles: plain GEMM, BN = 256");
+    using Cfg = GemmCfg<BN, CG>;
+    const int cta_rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -199,7 +204,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             return;
         }
     }
-    const int grid_ctas = COMM ? comm.gemm_ctas : static_cast<int>(gridDim.x);
+    // persistent schedule over work units (a unit = one CTA, or one CTA pair)
+    const int grid_ctas = (COMM ? comm.gemm_ctas : static_cast<int>(gridDim.x)) / CG;
+    const int unit = static_cast<int>(blockIdx.x) / CG;
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
@@ -224,13 +231,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 4);
+            mbar_init(&tmem_empty[i], 4 * CG);  // the leader collects the epilogue warps of the whole pair
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<1>(tmem_base_smem, Cfg::TMEM_COLS);
+    if (warp == 1) tmem_alloc<CG>(tmem_base_smem, Cfg::TMEM_COLS);
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync();  // the peer's barriers are initialised before anything signals them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
 
@@ -239,7 +247,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_items; tile += grid_ctas) {
+            for (int tile = unit; tile < num_items; tile += grid_ctas) {
                 int tm, tn, n_off, width;
                 item_coords<BN>(tile, args, tm, tn, n_off, width);
                 bool own_rows = false;
@@ -256,31 +264,36 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         }
                     }
                 }
-                const int m0 = tm * BM, n0 = tn * BN + n_off;
+                const int m0 = (tm * CG + cta_rank) * BM, n0 = tn * BN + n_off + cta_rank * (BN / CG);
                 const int m0_own = m0 - comm.rank * comm.m_local;
+                // 2-CTA: every CTA loads its rows of A and its half of B, all bytes are counted on the leader's barrier
+                auto ld = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+                    if constexpr (CG == 2) tma_load_2d_2sm(dst, map, bar, c0, c1);
+                    else tma_load_2d(dst, map, bar, c0, c1);
+                };
                 const int nb64 = width / 64;  // B arrives in 64-row (K-major) or 64-column (MN-major) boxes
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + width * (BK * 2));
+                    if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES * CG + width * (BK * 2));
                     uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
                     uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
                     const int k0 = kb * BK;
                     if (COMM && own_rows) {  // the local shard is read in place (tmap_bt doubles as its map)
                         tma_load_2d(sa, &tmap_bt, &full_bar[stage], k0, m0_own);
                     } else if (!args.a_mn) {
-                        tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);
+                        ld(sa, &tmap_a, &full_bar[stage], k0, m0);
                     } else {
 #pragma unroll
                         for (int j = 0; j < BM / 64; ++j)
-                            tma_load_2d(sa + j * (BK * 128), &tmap_a, &full_bar[stage], m0 + j * 64, k0);
+                            ld(sa + j * (BK * 128), &tmap_a, &full_bar[stage], m0 + j * 64, k0);
                     }
                     if (width == BN) {
                         if (!args.b_mn) {
-                            tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
+                            ld(sb, &tmap_b, &full_bar[stage], k0, n0);
                         } else {
 #pragma unroll
-                            for (int j = 0; j < BN / 64; ++j)
-                                tma_load_2d(sb + j * (BK * 128), &tmap_b, &full_bar[stage], n0 + j * 64, k0);
+                            for (int j = 0; j < BN / CG / 64; ++j)
+                                ld(sb + j * (BK * 128), &tmap_b, &full_bar[stage], n0 + j * 64, k0);
                         }
                     } else if (!args.b_mn) {  // tail slice: 64-row boxes of the K-major operand
                         for (int j = 0; j < nb64; ++j)
@@ -295,8 +308,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc_full = make_idesc_f16(BM, BN, args.a_mn, args.b_mn);
+        if (lane == 0 && cta_rank == 0) {  // the leader CTA issues the MMAs of the pair
+            const uint32_t idesc_full = make_idesc_f16(BM * CG, BN, args.a_mn, args.b_mn);
             // K-major: 8-row groups are 1024 B apart, advance 32 B per UMMA_K.
             // MN-major: 64-element column blocks are BK*128 B apart (LBO), 8-k groups 1024 B apart, advance 2048 B.
             const uint32_t a_lbo = args.a_mn ? BK * 128 : 16, b_lbo = args.b_mn ? BK * 128 : 16;
@@ -306,7 +319,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_items; tile += grid_ctas) {
+            for (int tile = unit; tile < num_items; tile += grid_ctas) {
                 const uint32_t idesc = tile < args.tiles_full
                                            ? idesc_full
                                            : make_idesc_f16(BM, BN / args.tail_split, args.a_mn, args.b_mn);
@@ -322,12 +335,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t da = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
                         const uint64_t db = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
-                        umma_f16_ss<1>(d_tmem, da, db, idesc, (kb | k) != 0);
+                        umma_f16_ss<CG>(d_tmem, da, db, idesc, (kb | k) != 0);
                     }
-                    umma_commit<1>(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    umma_commit<CG>(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit<1>(&tmem_full[acc]);  // accumulator complete -> epilogue
+                umma_commit<CG>(&tmem_full[acc]);  // accumulator complete -> epilogue
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -340,11 +353,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const bool accumulate = args.flags & GEMM_ACCUMULATE;
         const bool swiglu = args.flags & GEMM_SWIGLU;
         const bool no_store_d = args.flags & GEMM_SKIP_D;
-        for (int tile = blockIdx.x; tile < num_items; tile += grid_ctas) {
+        for (int tile = unit; tile < num_items; tile += grid_ctas) {
             int tm, tn, n_off, width;
             item_coords<BN>(tile, args, tm, tn, n_off, width);
             if constexpr (COMM) tm = comm_remap_m(tm, args.tiles_m, comm);
-            const int row = tm * BM + q * 32 + lane;
+            const int row = (tm * CG + cta_rank) * BM + q * 32 + lane;
             const int n0 = tn * BN + n_off;
             // reduce-scatter / all-reduce: rows owned by a peer are pushed straight into that peer's staging slot,
             // rows owned by this rank are reduced with what the peers pushed and written as the final result
@@ -549,7 +562,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+                if constexpr (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0);
+                else mbar_arrive(&tmem_empty[acc]);
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             if constexpr (COMM) {
                 if (rs_mode && !own) {
@@ -568,10 +584,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync();  // no CTA of the pair may exit while the other still uses its smem / TMEM
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<1>(tmem_base, Cfg::TMEM_COLS);
+        tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
@@ -671,9 +688,9 @@ static int num_sms() {
 static int g_tail_split = 1;
 void set_gemm_tail_split(int on) { g_tail_split = on; }
 
-template <int BN>
+template <int BN, int CG = 1>
 static int launch(const GemmDesc& g, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, CG>;
     CUtensorMap ta, tb, tbt;
     int rc;
     // A: logical [M, K]
@@ -681,7 +698,7 @@ static int launch(const GemmDesc& g, cudaStream_t stream) {
     else               rc = make_tmap_2d_bf16(&ta, g.A, g.M, g.K, g.lda, 64, BK);
     if (rc) return rc;
     // B: logical [N, K]
-    if (!g.b_mn_major) rc = make_tmap_2d_bf16(&tb, g.B, g.K, g.N, g.ldb, BK, BN);
+    if (!g.b_mn_major) rc = make_tmap_2d_bf16(&tb, g.B, g.K, g.N, g.ldb, BK, BN / CG);
     else               rc = make_tmap_2d_bf16(&tb, g.B, g.N, g.K, g.ldb, 64, BK);
     if (rc) return rc;
     tbt = tb;  // tail slices of a K-major B come in 64-row boxes
@@ -693,17 +710,17 @@ static int launch(const GemmDesc& g, cudaStream_t stream) {
     a.H = g.H; a.ldh = g.ldh;
     a.flags = g.flags;
     a.a_mn = g.a_mn_major; a.b_mn = g.b_mn_major;
-    a.tiles_m = (g.M + BM - 1) / BM;
+    a.tiles_m = (g.M + BM * CG - 1) / (BM * CG);
     a.tiles_n = (g.N + BN - 1) / BN;
     const int tiles = a.tiles_m * a.tiles_n;
-    int sms = g.max_ctas > 0 ? g.max_ctas : num_sms();
+    int sms = (g.max_ctas > 0 ? g.max_ctas : num_sms()) / CG;  // work units: CTAs or CTA pairs
     const int grid = tiles < sms ? tiles : sms;
     // Wave quantisation: split the tiles of the last (partial) wave into 2 or 4 column slices when that lets the
     // whole tail run as ONE wave of narrower tiles (e.g. 512 tiles on 148 SMs: 3 full waves + 68 tiles -> 136 half
     // tiles, 3.5 wave-times instead of 4).  The partial last n-tile (N % BN != 0) keeps the whole-tile path.
     a.tiles_full = tiles;
     a.tail_split = 1;
-    if (g_tail_split && tiles > grid && g.N % BN == 0) {
+    if (CG == 1 && g_tail_split && tiles > grid && g.N % BN == 0) {
         const int tail = tiles % grid;
         if (tail > 0) {
             int split = 1;
@@ -719,7 +736,7 @@ static int launch(const GemmDesc& g, cudaStream_t stream) {
 
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, false, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::SMEM_BYTES);
         if (e != cudaSuccess) {
             fprintf(stderr, "[b200] cudaFuncSetAttribute(smem=%d) failed: %s\n", Cfg::SMEM_BYTES, cudaGetErrorString(e));
@@ -727,8 +744,25 @@ static int launch(const GemmDesc& g, cudaStream_t stream) {
         }
         attr_set = true;
     }
-    gemm_bf16_kernel<BN, false><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tbt, a, CommKernelArgs{});
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e;
+    if constexpr (CG == 1) {
+        gemm_bf16_kernel<BN, false, 1><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tbt, a, CommKernelArgs{});
+        e = cudaGetLastError();
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid * CG);
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CG;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, false, CG>, ta, tb, tbt, a, CommKernelArgs{});
+    }
     if (e != cudaSuccess) {
         fprintf(stderr, "[b200] gemm launch failed: %s\n", cudaGetErrorString(e));
         return -4;
@@ -796,6 +830,8 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     // pick the narrower tile when the 256-wide grid would leave SMs idle
     const int tiles256 = ((g.M + BM - 1) / BM) * ((g.N + 255) / 256);
     const bool use128 = g.force_bn == 128 || (g.force_bn == 0 && tiles256 < num_sms());
+    // default for large problems: 256 x 256 tile on a CTA pair (cta_group::2); force_bn 512 / 256 / 128 pin a variant
+    if (g.force_bn == 512 || (g.force_bn == 0 && !use128 && g.max_ctas == 0)) return launch<256, 2>(g, stream);
     return use128 ? launch<128>(g, stream) : launch<256>(g, stream);
 }
 

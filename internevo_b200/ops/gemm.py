@@ -75,7 +75,7 @@ def matmul(
     return out
 
 
-def matmul_swiglu(x: torch.Tensor, w_gu: torch.Tensor, store_gu: bool = True):
+def matmul_swiglu(x: torch.Tensor, w_gu: torch.Tensor, store_gu: bool = True, force_bn: int = 0):
     """``gu = x @ w_gu^T`` with interleaved (gate, up) rows in ``w_gu``; returns ``(gu, silu(gate) * up)``.
 
     The activation is applied in the GEMM epilogue straight out of TMEM, so the separate SwiGLU pass over ``[T, 2F]``
@@ -90,7 +90,7 @@ def matmul_swiglu(x: torch.Tensor, w_gu: torch.Tensor, store_gu: bool = True):
     d = torch.empty(M, N, device=x.device, dtype=torch.bfloat16)
     h = torch.empty(M, N // 2, device=x.device, dtype=torch.bfloat16)
     flags = GEMM_SWIGLU | (0 if store_gu else GEMM_SKIP_D)
-    torch.ops.b200.gemm(x, w_gu, d, False, False, None, flags, h, 0, 0)
+    torch.ops.b200.gemm(x, w_gu, d, False, False, None, flags, h, force_bn, 0)
     _bump()
     return (d if store_gu else None), h
 

@@ -50,38 +50,45 @@ def check_gemm():
         a = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
         b = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
         ref = a.float() @ b.float().t()
-        for bn in (256, 128):
+        for bn in (256, 128, 512):  # 512 = 256x256 tile on a CTA pair (cta_group::2)
             out = ops.matmul(a, b, force_bn=bn)
             allok &= err_report(f"NT  {M}x{N}x{K} bn{bn}", out, ref, 1e-2)
         if M % 8 == 0:
             bt = b.t().contiguous()  # [K, N]
-            out = ops.matmul(a, bt, b_mn=True)
-            allok &= err_report(f"NN  {M}x{N}x{K} (B MN-major)", out, ref, 1e-2)
             at = a.t().contiguous()  # [K, M]
-            out = ops.matmul(at, bt, a_mn=True, b_mn=True)
-            allok &= err_report(f"TN  {M}x{N}x{K} (A,B MN-major)", out, ref, 1e-2)
-            out = ops.matmul(at, b, a_mn=True)
-            allok &= err_report(f"TT  {M}x{N}x{K} (A MN-major)", out, ref, 1e-2)
+            for bn in (0, 512):
+                out = ops.matmul(a, bt, b_mn=True, force_bn=bn)
+                allok &= err_report(f"NN  {M}x{N}x{K} (B MN-major) bn{bn}", out, ref, 1e-2)
+                out = ops.matmul(at, bt, a_mn=True, b_mn=True, force_bn=bn)
+                allok &= err_report(f"TN  {M}x{N}x{K} (A,B MN-major) bn{bn}", out, ref, 1e-2)
+                out = ops.matmul(at, b, a_mn=True, force_bn=bn)
+                allok &= err_report(f"TT  {M}x{N}x{K} (A MN-major) bn{bn}", out, ref, 1e-2)
     # epilogues
     M, N, K = 512, 1024, 512
     a = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
     b = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
     bias = torch.randn(N, device=dev, dtype=torch.bfloat16)
     ref = a.float() @ b.float().t()
-    allok &= err_report("bias", ops.matmul(a, b, bias=bias), ref + bias.float(), 1e-2)
-    allok &= err_report("fp32 out", ops.matmul(a, b, out_dtype=torch.float32), ref, 1e-3)
-    acc = torch.randn(M, N, device=dev, dtype=torch.float32)
-    acc0 = acc.clone()
-    ops.matmul(a, b, out=acc, accumulate=True)
-    allok &= err_report("fp32 accumulate", acc, ref + acc0, 1e-3)
-    accb = torch.randn(M, N, device=dev, dtype=torch.bfloat16)
-    accb0 = accb.clone()
-    ops.matmul(a, b, out=accb, accumulate=True)
-    allok &= err_report("bf16 accumulate", accb, ref + accb0.float(), 1e-2)
-    gu, h = ops.matmul_swiglu(a, b)
-    allok &= err_report("swiglu gu", gu, ref, 1e-2)
-    g, u = gu[:, 0::2].float(), gu[:, 1::2].float()
-    allok &= err_report("swiglu h", h, torch.nn.functional.silu(g) * u, 1e-2)
+    for bn in (128, 256, 512):
+        allok &= err_report(f"bias bn{bn}", ops.matmul(a, b, bias=bias, force_bn=bn), ref + bias.float(), 1e-2)
+        allok &= err_report(f"fp32 out bn{bn}", ops.matmul(a, b, out_dtype=torch.float32, force_bn=bn), ref, 1e-3)
+        acc = torch.randn(M, N, device=dev, dtype=torch.float32)
+        acc0 = acc.clone()
+        ops.matmul(a, b, out=acc, accumulate=True, force_bn=bn)
+        allok &= err_report(f"fp32 accumulate bn{bn}", acc, ref + acc0, 1e-3)
+        accb = torch.randn(M, N, device=dev, dtype=torch.bfloat16)
+        accb0 = accb.clone()
+        ops.matmul(a, b, out=accb, accumulate=True, force_bn=bn)
+        allok &= err_report(f"bf16 accumulate bn{bn}", accb, ref + accb0.float(), 1e-2)
+        gu, h = ops.matmul_swiglu(a, b, force_bn=bn)
+        allok &= err_report(f"swiglu gu bn{bn}", gu, ref, 1e-2)
+        g, u = gu[:, 0::2].float(), gu[:, 1::2].float()
+        allok &= err_report(f"swiglu h bn{bn}", h, torch.nn.functional.silu(g) * u, 1e-2)
+    # ragged M for the pair tile (M % 256 == 128) and wgrad-style accumulate into a strided view
+    a3 = torch.randn(384 + 128, 320, device=dev, dtype=torch.bfloat16)[:384 + 128 - 0]
+    a3 = torch.randn(640, 320, device=dev, dtype=torch.bfloat16)
+    b3 = torch.randn(768, 320, device=dev, dtype=torch.bfloat16)
+    allok &= err_report("2cta M=640", ops.matmul(a3, b3, force_bn=512), a3.float() @ b3.float().t(), 1e-2)
     # autograd linear
     x = torch.randn(256, 512, device=dev, dtype=torch.bfloat16, requires_grad=True)
     w = torch.randn(384, 512, device=dev, dtype=torch.bfloat16, requires_grad=True)
@@ -137,8 +144,8 @@ def gemm_perf():
         A = a.t() if a_mn else a
         Bt = b if b_mn else b.t()
         row = {"case": name, "M": M, "N": N, "K": K}
-        for bn, split in ((256, 1), (256, 0), (128, 1)):
-            key = f"ours_bn{bn}_tflops" if split else f"ours_bn{bn}_nosplit_tflops"
+        for bn, split in ((256, 1), (256, 0), (128, 1), (512, 1)):
+            key = {256: "ours_bn256", 128: "ours_bn128", 512: "ours_2cta"}[bn] + ("_tflops" if split else "_nosplit_tflops")
             torch.ops.b200.set_gemm_tail_split(split)
             try:
                 ms = timeit(lambda: ops.matmul(a, b, a_mn=a_mn, b_mn=b_mn, out=out, force_bn=bn), flush=flush)
