@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnKernelArgs args) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::BARS);
     uint64_t* q_full = bars;                 // 1
     uint64_t* k_full = bars + 1;             // KV_STAGES
@@ -353,13 +353,15 @@ int attn_fwd(const AttnDesc& d, cudaStream_t stream) {
 static constexpr int BQ = 64;                  // q rows per inner step
 static constexpr int BWD_THREADS = 384;
 static constexpr int QT_BYTES = BQ * D * 2;    // 16 KB
+static constexpr int QSTAGES = 3;              // Q / dO ring depth: the slot of step i is released when dQ(i) retires,
+                                               // so two stages left the TMA one MMA batch of lead -> S^T(i+1) issued late
 
 struct BwdSmem {
     static constexpr int K = 0;                          // 32 KB
     static constexpr int V = K + TILE_BYTES;             // 32 KB
     static constexpr int Q = V + TILE_BYTES;             // 2 x 16 KB
-    static constexpr int DO = Q + 2 * QT_BYTES;          // 2 x 16 KB
-    static constexpr int DS = DO + 2 * QT_BYTES;         // 2 x 16 KB  (dS^T, [128 kv rows x 64 q] bf16)
+    static constexpr int DO = Q + QSTAGES * QT_BYTES;    // QSTAGES x 16 KB
+    static constexpr int DS = DO + QSTAGES * QT_BYTES;   // 2 x 16 KB  (dS^T, [128 kv rows x 64 q] bf16)
     static constexpr int DQ = DS + 2 * QT_BYTES;         // 32 KB fp32 staging [64 q x 128 d] for the TMA reduce-add
     static constexpr int LD = DQ + BQ * D * 4;           // 2 x (64 lse2 + 64 delta) floats
     static constexpr int BARS = LD + 2 * 2 * BQ * 4;
@@ -396,7 +398,7 @@ __global__ void attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ dout, co
 
 // dq (bf16, strided [T, (g, j), D]) = dq_acc (fp32 [T, H, D])
 __global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int T, int H,
-                                           int qpk, int64_t st, int64_t sg, int64_t sh) {
+                                           int qpk, int64_t st, int64_t sg, int64_t sh, float scale) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 8 elements
     const int64_t n = (int64_t)T * H * (D / 8);
     if (i >= n) return;
@@ -407,7 +409,8 @@ __global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_b
     const float4 x = *reinterpret_cast<const float4*>(acc + th * D + c);
     const float4 y = *reinterpret_cast<const float4*>(acc + th * D + c + 4);
     uint4 o;
-    o.x = pack_bf16(x.x, x.y); o.y = pack_bf16(x.z, x.w); o.z = pack_bf16(y.x, y.y); o.w = pack_bf16(y.z, y.w);
+    o.x = pack_bf16(x.x * scale, x.y * scale); o.y = pack_bf16(x.z * scale, x.w * scale);
+    o.z = pack_bf16(y.x * scale, y.y * scale); o.w = pack_bf16(y.z * scale, y.w * scale);
     *reinterpret_cast<uint4*>(dq + t * st + (int64_t)(h / qpk) * sg + (int64_t)(h % qpk) * sh + c) = o;
 }
 
@@ -416,11 +419,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
                 const __grid_constant__ CUtensorMap tmap_dq, const AttnBwdArgs args) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BwdSmem::BARS);
     uint64_t* kv_full = bars;            // 1
-    uint64_t* qdo_full = bars + 1;       // 2
-    uint64_t* qdo_empty = bars + 3;      // 2
+    uint64_t* qdo_full = bars + 17;      // QSTAGES
+    uint64_t* qdo_empty = bars + 17 + QSTAGES;  // QSTAGES
     uint64_t* s_full = bars + 5;         // 2
     uint64_t* p_ready = bars + 7;        // 2 (count 4)
     uint64_t* dp_full = bars + 9;        // 1
@@ -448,9 +451,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
         mbar_init(kv_full, 1);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); mbar_init(&s_full[i], 1);
+            mbar_init(&s_full[i], 1);
             mbar_init(&p_ready[i], 8); mbar_init(&ds_free[i], 1);
         }
+        for (int i = 0; i < QSTAGES; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
         mbar_init(dp_full, 1); mbar_init(ds_ready, 8); mbar_init(dq_full, 1); mbar_init(dq_free, 8);
         mbar_init(dkv_done, 1);
         fence_barrier_init();
@@ -472,10 +476,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 tma_load_2d(smem + BwdSmem::V + c * (TN * 128), &tmap_v, kv_full, vcol + c * 64, s0 + kv0);
             }
             for (int i = 0; i < n_steps; ++i) {
-                const int st = i & 1;
+                const int st = i % QSTAGES;
                 const int j = i / nq, mq = mq0 + i % nq;
                 const int h = hk * qpk + j;
-                mbar_wait(&qdo_empty[st], ((i >> 1) & 1) ^ 1);
+                mbar_wait(&qdo_empty[st], ((i / QSTAGES) & 1) ^ 1);
                 mbar_expect_tx(&qdo_full[st], 2 * QT_BYTES);
                 const int qcol = (int)((int64_t)hk * f.q_stride_g + (int64_t)j * f.q_stride_h);
                 for (int c = 0; c < 2; ++c) {
@@ -520,8 +524,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             for (int i = 0; i < n_steps; ++i) {
                 const int st = i & 1;
                 const uint32_t ph2 = (i >> 1) & 1;
-                const uint32_t sQ = smem_u32(smem + BwdSmem::Q + st * QT_BYTES);
-                const uint32_t sDO = smem_u32(smem + BwdSmem::DO + st * QT_BYTES);
+                const int qs = i % QSTAGES, nqs = (i + 1) % QSTAGES;
+                const uint32_t sQ = smem_u32(smem + BwdSmem::Q + qs * QT_BYTES);
+                const uint32_t sDO = smem_u32(smem + BwdSmem::DO + qs * QT_BYTES);
                 // dV += P^T dO
                 mbar_wait(&p_ready[st], ph2);
                 tc_fence_after();
@@ -529,9 +534,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 // S^T(i+1)
                 const int ns = (i + 1) & 1;
                 if (i + 1 < n_steps) {
-                    mbar_wait(&qdo_full[ns], ((i + 1) >> 1) & 1);
+                    mbar_wait(&qdo_full[nqs], ((i + 1) / QSTAGES) & 1);
                     tc_fence_after();
-                    issue_st(sK, smem_u32(smem + BwdSmem::Q + ns * QT_BYTES), T_S0 + ns * 64);
+                    issue_st(sK, smem_u32(smem + BwdSmem::Q + nqs * QT_BYTES), T_S0 + ns * 64);
                     umma_commit<1>(&s_full[ns]);
                 }
                 // dK += dS^T Q
@@ -540,7 +545,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 issue_acc(T_DP, sQ, T_DK, i > 0);
                 // dP^T(i+1) as early as possible (its TMEM region is free once dK(i) has been issued: in-order pipe)
                 if (i + 1 < n_steps) {
-                    issue_st(sV, smem_u32(smem + BwdSmem::DO + ns * QT_BYTES), T_DP);
+                    issue_st(sV, smem_u32(smem + BwdSmem::DO + nqs * QT_BYTES), T_DP);
                     umma_commit<1>(dp_full);
                 }
                 // dQ^T(i) = K^T dS^T
@@ -554,7 +559,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 }
                 umma_commit<1>(dq_full);
                 umma_commit<1>(&ds_free[st]);
-                umma_commit<1>(&qdo_empty[st]);  // Q(i) / dO(i) fully consumed (dV, dK and the early dP^T(i+1) excluded)
+                umma_commit<1>(&qdo_empty[qs]);  // Q(i) / dO(i) fully consumed (dV, dK and the early dP^T(i+1) excluded)
             }
             umma_commit<1>(dkv_done);
         }
@@ -572,18 +577,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         float* sld = reinterpret_cast<float*>(smem + BwdSmem::LD);  // [2][2][64]: buffer, {lse2, delta}, q
         float* stage = reinterpret_cast<float*>(smem + BwdSmem::DQ);
         const bool issuer = (tid == 0);
-        auto load_rowstats = [&](int step) {
+        // (head j, q tile mq) of a step are tracked incrementally: no integer division in the loop
+        auto load_rowstats = [&](int step, int j, int mq) {
             if (tid < 2 * BQ && step < n_steps) {
-                const int j = step / nq, mq = mq0 + step % nq;
                 const int h = hk * qpk + j;
                 const int qi = min(mq * BQ + (tid & (BQ - 1)), len - 1);
                 const float* src = (tid < BQ ? args.lse : args.delta) + (int64_t)h * f.T + s0 + qi;
                 sld[(step & 1) * 2 * BQ + tid] = __ldg(src);
             }
         };
-        auto reduce_dq = [&](int step) {
+        auto reduce_dq = [&](int step, int j, int mq) {
             // dQ^T(step): lane = d, this warp's 32 q columns -> fp32 staging rows -> one TMA reduce-add for the tile
-            const int j = step / nq, mq = mq0 + step % nq;
             const int h = hk * qpk + j;
             mbar_wait(dq_full, step & 1);
             tc_fence_after();
@@ -607,17 +611,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 tma_store_commit();
             }
         };
-        load_rowstats(0);
+        load_rowstats(0, 0, mq0);
+        int cj = 0, cm = mq0;          // step i
+        int pj = 0, pm = mq0;          // step i - 1
         for (int i = 0; i < n_steps; ++i) {
             const int st = i & 1;
-            const int mq = mq0 + i % nq;
+            const int mq = cm;
             const int q0 = mq * BQ + half * 32;   // first q row handled by this warp
+            int nj = cj, nm = cm + 1;  // step i + 1
+            if (nm == mq0 + nq) { nm = mq0; ++nj; }
             asm volatile("bar.sync 2, 256;" ::: "memory");  // row stats of step i are in smem
-            load_rowstats(i + 1);
+            load_rowstats(i + 1, nj, nm);
             const float* lse2 = sld + st * 2 * BQ + half * 32;
             const float* delt = lse2 + BQ;
             const bool edge = (q0 + 32 > len) || (kv0 + TN > len) || (f.causal && q0 < kv0 + TN);
             uint32_t pk[16];  // P^T row (this warp's 32 q columns), bf16 pairs
+            float pf[32];     // the same values in fp32, reused by phase B (no unpack)
             // ---- phase A: P^T = exp2(S^T * scale_log2 - lse2)
             mbar_wait(&s_full[st], (i >> 1) & 1);
             tc_fence_after();
@@ -643,6 +652,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                     }
                     pk[e >> 1] = pack_bf16(p0, p1);
                     pk[(e >> 1) + 1] = pack_bf16(p2, p3);
+                    pf[e] = p0; pf[e + 1] = p1; pf[e + 2] = p2; pf[e + 3] = p3;
                 }
             }
             tmem_st_32x32b_x16(t_s + half * 32, pk);
@@ -650,7 +660,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_ready[st]);
-            // ---- phase B: dS^T = scale * P^T * (dP^T - delta)
+            // ---- phase B: dS^T = P^T * (dP^T - delta); the softmax scale is applied once to dK (epilogue) and dQ (convert)
             mbar_wait(dp_full, i & 1);
             if (i >= 2) mbar_wait(&ds_free[st], ((i >> 1) - 1) & 1);
             tc_fence_after();
@@ -664,11 +674,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
                 for (int e = 0; e < 32; e += 4) {
                     const float4 d4 = *reinterpret_cast<const float4*>(delt + e);
-                    const float2 pa = unpack_bf16(pk[e >> 1]), pb = unpack_bf16(pk[(e >> 1) + 1]);
-                    o[e >> 1] = pack_bf16(f.scale * pa.x * (__uint_as_float(x[e]) - d4.x),
-                                          f.scale * pa.y * (__uint_as_float(x[e + 1]) - d4.y));
-                    o[(e >> 1) + 1] = pack_bf16(f.scale * pb.x * (__uint_as_float(x[e + 2]) - d4.z),
-                                                f.scale * pb.y * (__uint_as_float(x[e + 3]) - d4.w));
+                    o[e >> 1] = pack_bf16(pf[e] * (__uint_as_float(x[e]) - d4.x),
+                                          pf[e + 1] * (__uint_as_float(x[e + 1]) - d4.y));
+                    o[(e >> 1) + 1] = pack_bf16(pf[e + 2] * (__uint_as_float(x[e + 2]) - d4.z),
+                                                pf[e + 3] * (__uint_as_float(x[e + 3]) - d4.w));
                 }
                 tmem_st_32x32b_x16(t_dp + half * 32, o);
 #pragma unroll
@@ -684,9 +693,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(ds_ready);
             // ---- dQ^T of the previous step (long finished): transpose + bulk reduce-add
-            if (i > 0) reduce_dq(i - 1);
+            if (i > 0) reduce_dq(i - 1, pj, pm);
+            pj = cj; pm = cm; cj = nj; cm = nm;
         }
-        if (n_steps > 0) reduce_dq(n_steps - 1);
+        if (n_steps > 0) reduce_dq(n_steps - 1, pj, pm);
         if (issuer) tma_store_wait<0>();
         // ---- epilogue: dV, dK rows of this kv tile (each warpgroup-half writes 64 of the 128 head-dim columns)
         mbar_wait(dkv_done, 0);
@@ -695,6 +705,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const int64_t tok = (int64_t)s0 + kv;
         for (int which = 0; which < 2; ++which) {
             const uint32_t t_src = tmem + (which == 0 ? T_DV : T_DK) + lane_off;
+            const float mul = which == 0 ? 1.f : f.scale;
             __nv_bfloat16* dst = which == 0 ? args.dv + tok * args.dv_stride_t + (int64_t)hk * args.dv_stride_h
                                             : args.dk + tok * args.dk_stride_t + (int64_t)hk * args.dk_stride_h;
 #pragma unroll 1
@@ -706,10 +717,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
                     for (int e = 0; e < 32; e += 8) {
                         uint4 o4;
-                        o4.x = pack_bf16(__uint_as_float(x[e]), __uint_as_float(x[e + 1]));
-                        o4.y = pack_bf16(__uint_as_float(x[e + 2]), __uint_as_float(x[e + 3]));
-                        o4.z = pack_bf16(__uint_as_float(x[e + 4]), __uint_as_float(x[e + 5]));
-                        o4.w = pack_bf16(__uint_as_float(x[e + 6]), __uint_as_float(x[e + 7]));
+                        o4.x = pack_bf16(mul * __uint_as_float(x[e]), mul * __uint_as_float(x[e + 1]));
+                        o4.y = pack_bf16(mul * __uint_as_float(x[e + 2]), mul * __uint_as_float(x[e + 3]));
+                        o4.z = pack_bf16(mul * __uint_as_float(x[e + 4]), mul * __uint_as_float(x[e + 5]));
+                        o4.w = pack_bf16(mul * __uint_as_float(x[e + 6]), mul * __uint_as_float(x[e + 7]));
                         *reinterpret_cast<uint4*>(dst + c + e) = o4;
                     }
                 }
@@ -764,7 +775,7 @@ int attn_bwd(const AttnBwdDesc& b, cudaStream_t stream) {
         const int64_t n = (int64_t)d.T * d.H * (D / 8);
         const int64_t sg = b.dq_stride_g ? b.dq_stride_g : b.dq_stride_h * qpk;
         attn_bwd_dq_convert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
-            b.dq_acc, (__nv_bfloat16*)b.dq, d.T, d.H, qpk, b.dq_stride_t, sg, b.dq_stride_h);
+            b.dq_acc, (__nv_bfloat16*)b.dq, d.T, d.H, qpk, b.dq_stride_t, sg, b.dq_stride_h, d.scale);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -13;
 }

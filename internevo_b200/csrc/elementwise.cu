@@ -251,61 +251,72 @@ int rmsnorm_bwd(const void* dy, const void* res, const void* w, const float* rst
 // (InternLM2 packed wqkv "(h gs d)": group = q_per_kv + 2, rot_per_group = q_per_kv + 1 -> q and k rotate, v not).
 // Non-interleaved (GPT-NeoX halves) or interleaved pairs.  cos/sin tables are [max_pos, D/2] fp32.
 // ----------------------------------------------------------------------------------------------------------------
-__global__ void rope_kernel(__nv_bfloat16* __restrict__ x, const int* __restrict__ pos, const float* __restrict__ cos_t,
-                            const float* __restrict__ sin_t, int T, int heads, int D, int64_t stride_t, int group,
-                            int rot_per_group, float sign, int interleaved) {
-    // one warp per (token, head); each lane handles D/64 chunks of (4 + 4) elements
-    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (gw >= (int64_t)T * heads) return;
-    const int t = gw / heads, h = gw % heads;
-    if ((h % group) >= rot_per_group) return;
-    const int p = pos ? pos[t] : t;
-    __nv_bfloat16* xp = x + (int64_t)t * stride_t + (int64_t)h * D;
-    const float* c = cos_t + (int64_t)p * (D / 2);
-    const float* s = sin_t + (int64_t)p * (D / 2);
-    const int half = D / 2;
-    if (!interleaved) {
-        for (int i = lane * 4; i < half; i += 128) {
-            uint2 a = *reinterpret_cast<uint2*>(xp + i);
-            uint2 b = *reinterpret_cast<uint2*>(xp + half + i);
-            float4 cc = *reinterpret_cast<const float4*>(c + i);
-            float4 ss = *reinterpret_cast<const float4*>(s + i);
-            float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), b0 = unpack_bf16(b.x), b1 = unpack_bf16(b.y);
-            ss.x *= sign; ss.y *= sign; ss.z *= sign; ss.w *= sign;
-            uint2 oa, ob;
-            oa.x = pack_bf16(a0.x * cc.x - b0.x * ss.x, a0.y * cc.y - b0.y * ss.y);
-            oa.y = pack_bf16(a1.x * cc.z - b1.x * ss.z, a1.y * cc.w - b1.y * ss.w);
-            ob.x = pack_bf16(a0.x * ss.x + b0.x * cc.x, a0.y * ss.y + b0.y * cc.y);
-            ob.y = pack_bf16(a1.x * ss.z + b1.x * cc.z, a1.y * ss.w + b1.y * cc.w);
-            *reinterpret_cast<uint2*>(xp + i) = oa;
-            *reinterpret_cast<uint2*>(xp + half + i) = ob;
-        }
-    } else {
-        for (int i = lane * 4; i < half; i += 128) {  // 4 pairs = 8 elements
-            uint4 a = *reinterpret_cast<uint4*>(xp + 2 * i);
-            float4 cc = *reinterpret_cast<const float4*>(c + i);
-            float4 ss = *reinterpret_cast<const float4*>(s + i);
-            ss.x *= sign; ss.y *= sign; ss.z *= sign; ss.w *= sign;
-            float2 p0 = unpack_bf16(a.x), p1 = unpack_bf16(a.y), p2 = unpack_bf16(a.z), p3 = unpack_bf16(a.w);
-            uint4 o;
-            o.x = pack_bf16(p0.x * cc.x - p0.y * ss.x, p0.x * ss.x + p0.y * cc.x);
-            o.y = pack_bf16(p1.x * cc.y - p1.y * ss.y, p1.x * ss.y + p1.y * cc.y);
-            o.z = pack_bf16(p2.x * cc.z - p2.y * ss.z, p2.x * ss.z + p2.y * cc.z);
-            o.w = pack_bf16(p3.x * cc.w - p3.y * ss.w, p3.x * ss.w + p3.y * cc.w);
-            *reinterpret_cast<uint4*>(xp + 2 * i) = o;
+__global__ void __launch_bounds__(256) rope_kernel(__nv_bfloat16* __restrict__ x, const int* __restrict__ pos,
+                                                   const float* __restrict__ cos_t, const float* __restrict__ sin_t,
+                                                   int T, int heads, int D, int64_t stride_t, int group,
+                                                   int rot_per_group, int rot_heads, float sign, int interleaved) {
+    // one thread per 8 rotation pairs (16 elements: 2 x 16 B of x, 2 x 32 B of the tables); only rotating heads are
+    // enumerated, so v never costs an instruction: item -> (token, rotating head index, chunk)
+    const int chunks = D / 16;
+    const int64_t items = (int64_t)T * rot_heads * chunks;
+    for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
+        const int ch = it % chunks;
+        const int64_t th = it / chunks;
+        const int rh = th % rot_heads;
+        const int t = th / rot_heads;
+        const int h = (rh / rot_per_group) * group + rh % rot_per_group;
+        const int p = pos ? pos[t] : t;
+        __nv_bfloat16* xp = x + (int64_t)t * stride_t + (int64_t)h * D;
+        const float* c = cos_t + (int64_t)p * (D / 2) + ch * 8;
+        const float* s = sin_t + (int64_t)p * (D / 2) + ch * 8;
+        const float4 c0 = *reinterpret_cast<const float4*>(c), c1 = *reinterpret_cast<const float4*>(c + 4);
+        float4 s0 = *reinterpret_cast<const float4*>(s), s1 = *reinterpret_cast<const float4*>(s + 4);
+        const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        const float ss[8] = {s0.x * sign, s0.y * sign, s0.z * sign, s0.w * sign,
+                             s1.x * sign, s1.y * sign, s1.z * sign, s1.w * sign};
+        float a[8], b[8];
+        if (!interleaved) {
+            __nv_bfloat16* pa = xp + ch * 8;
+            __nv_bfloat16* pb = xp + D / 2 + ch * 8;
+            unpack8(*reinterpret_cast<const uint4*>(pa), a);
+            unpack8(*reinterpret_cast<const uint4*>(pb), b);
+            float oa[8], ob[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                oa[j] = a[j] * cc[j] - b[j] * ss[j];
+                ob[j] = a[j] * ss[j] + b[j] * cc[j];
+            }
+            *reinterpret_cast<uint4*>(pa) = pack8(oa);
+            *reinterpret_cast<uint4*>(pb) = pack8(ob);
+        } else {
+            __nv_bfloat16* pa = xp + ch * 16;
+            unpack8(*reinterpret_cast<const uint4*>(pa), a);       // pairs 0..3
+            unpack8(*reinterpret_cast<const uint4*>(pa + 8), b);   // pairs 4..7
+            float oa[8], ob[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                oa[2 * j] = a[2 * j] * cc[j] - a[2 * j + 1] * ss[j];
+                oa[2 * j + 1] = a[2 * j] * ss[j] + a[2 * j + 1] * cc[j];
+                ob[2 * j] = b[2 * j] * cc[4 + j] - b[2 * j + 1] * ss[4 + j];
+                ob[2 * j + 1] = b[2 * j] * ss[4 + j] + b[2 * j + 1] * cc[4 + j];
+            }
+            *reinterpret_cast<uint4*>(pa) = pack8(oa);
+            *reinterpret_cast<uint4*>(pa + 8) = pack8(ob);
         }
     }
 }
 
 int rope_inplace(void* x, const int* pos, const float* cos_t, const float* sin_t, int T, int heads, int D,
                  int64_t stride_t, int group, int rot_per_group, int conj, int interleaved, cudaStream_t s) {
-    if (D % 8 != 0) return -1;
-    const int64_t warps = (int64_t)T * heads;
+    if (D % 16 != 0 || heads % group != 0) return -1;
+    const int rot_heads = heads / group * rot_per_group;
+    const int64_t items = (int64_t)T * rot_heads * (D / 16);
     const int threads = 256;
-    const int64_t blocks = (warps * 32 + threads - 1) / threads;
+    int64_t blocks = (items + threads - 1) / threads;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (blocks == 0) return 0;
     rope_kernel<<<(unsigned)blocks, threads, 0, s>>>((__nv_bfloat16*)x, pos, cos_t, sin_t, T, heads, D, stride_t, group,
-                                                     rot_per_group, conj ? -1.f : 1.f, interleaved);
+                                                     rot_per_group, rot_heads, conj ? -1.f : 1.f, interleaved);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

@@ -197,7 +197,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int cta_rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
     if constexpr (COMM) {
         if (static_cast<int>(blockIdx.x) >= comm.gemm_ctas) {
             ag_push_role<BN>(args, comm, smem);

@@ -193,8 +193,7 @@ class MHA(nn.Module):
             qkv = self.wqkv(x)  # [T, Hkv_l * (qpk + 2) * D]
             T = qkv.shape[0]
             gs = self.q_per_kv + 2
-            qkv = qkv.view(T, -1, D)
-            qkv = ops.apply_rotary_packed(qkv, indexes, cos, sin, gs, gs - 1, self.interleaved_rope)
+            qkv = ops.apply_rotary_packed(qkv, indexes, cos, sin, gs, gs - 1, self.interleaved_rope, head_dim=D)
             g = qkv.view(T, -1, gs, D)
             self._packed = g  # consumed by forward(): the native attention kernel reads q/k/v out of this one buffer
             q = g[:, :, : self.q_per_kv]  # [T, Hkv, qpk, D]  (strided view)
@@ -202,17 +201,15 @@ class MHA(nn.Module):
         if self.layout == "llama":
             q, k, v = self.wq(x), self.wk(x), self.wv(x)
             T = q.shape[0]
-            q = ops.apply_rotary_packed(q.view(T, -1, D), indexes, cos, sin, 1, 1, self.interleaved_rope)
-            k = ops.apply_rotary_packed(k.view(T, -1, D), indexes, cos, sin, 1, 1, self.interleaved_rope)
+            q = ops.apply_rotary_packed(q, indexes, cos, sin, 1, 1, self.interleaved_rope, head_dim=D).view(T, -1, D)
+            k = ops.apply_rotary_packed(k, indexes, cos, sin, 1, 1, self.interleaved_rope, head_dim=D).view(T, -1, D)
             return q, k, v.view(T, -1, D)
         qkv = self.Wqkv(x)  # [T, 3 * H_l * D] ordered (three, head, dim)
         T = qkv.shape[0]
-        qkv = qkv.view(T, 3, -1, D)
-        H = qkv.shape[2]
-        flat = qkv.view(T, 3 * H, D)
+        H = qkv.shape[1] // (3 * D)
         # rotate q and k heads only: group = 3H heads, first 2H rotate
-        flat = ops.apply_rotary_packed(flat, indexes, cos, sin, 3 * H, 2 * H, self.interleaved_rope)
-        qkv = flat.view(T, 3, H, D)
+        qkv = ops.apply_rotary_packed(qkv, indexes, cos, sin, 3 * H, 2 * H, self.interleaved_rope, head_dim=D)
+        qkv = qkv.view(T, 3, H, D)
         return qkv[:, 0], qkv[:, 1], qkv[:, 2]
 
     def forward(self, x, cu_seqlens=None, indexes=None, max_seqlen=None, inference_params=None, **kwargs):

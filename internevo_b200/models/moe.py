@@ -9,8 +9,8 @@ dispatch buffer, optional residual expert.
 Implementation is index based: the reference materialises dense one-hot ``[S, E, C]`` dispatch / combine tensors and
 contracts them with einsums (O(S·E·C) memory, ``gshard_layer.py:458,490``); here tokens are scattered into / gathered
 from the ``[E, C, h]`` buffer by row index and every expert runs the fused SwiGLU tcgen05 GEMMs on its contiguous slab.
-The registry keys ``GShard`` / ``MegaBlock`` / ``MegaBlock-D`` all resolve to this layer (``MegaBlock*`` = dropless:
-capacity is raised to the busiest expert's load instead of dropping).
+``MegaBlock`` is the same layer with the capacity raised to the busiest expert's load instead of dropping;
+``MegaBlock-D`` is ``DroplessMOELayer``: sorted tokens, variable-split all-to-all, grouped GEMM, no padding at all.
 """
 from __future__ import annotations
 
@@ -219,16 +219,106 @@ def _build_gshard(hidden_size, num_experts, ep_group, ep_size, mlp_ratio, device
                           num_local)
 
 
+class _AllToAllV(torch.autograd.Function):
+    """Variable-split ``all_to_all_single`` over rows (reference ``moe/megablock/megablock_moe.py:155-247``)."""
+
+    @staticmethod
+    def forward(ctx, group, x, send_splits, recv_splits):
+        ctx.group, ctx.send, ctx.recv = group, send_splits, recv_splits
+        out = x.new_empty(sum(recv_splits), *x.shape[1:])
+        dist.all_to_all_single(out, x.contiguous(), output_split_sizes=recv_splits, input_split_sizes=send_splits,
+                               group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return None, _AllToAllV.apply(ctx.group, g, ctx.recv, ctx.send), None, None
+
+
+class DroplessMOELayer(nn.Module):
+    """Dropless top-k MoE (the ``MegaBlock-D`` registry entry): no capacity, no padding.
+
+    Tokens are sorted by destination expert, exchanged with ONE variable-split all-to-all (row counts first, then the
+    rows), every local expert runs its fused SwiGLU GEMMs on its contiguous, exactly-sized slab (a grouped GEMM: the
+    tcgen05 kernel takes any M, ragged tiles are zero-filled by TMA), and results travel back through the inverse
+    permutation.  Replaces the block-sparse SDD/DSD kernels of MegaBlocks (reference ``moe/megablock/*``): on Blackwell
+    the dense grouped form keeps the 128 x 256 tensor-core tile busy without a block topology."""
+
+    def __init__(self, hidden_size, num_experts, ep_group, ep_size, experts: Experts, top_k: int = 1,
+                 noisy_gate_policy=None, device=None):
+        super().__init__()
+        self.wg = nn.Linear(hidden_size, num_experts, bias=False, device=device, dtype=torch.float32)
+        set_fp32_attr_to_module(self.wg)
+        self.experts = experts
+        self.num_experts, self.top_k = num_experts, top_k
+        self.ep_group, self.ep_size = ep_group, ep_size
+        self.num_local_experts = num_experts // ep_size
+        self.noisy_gate_policy = noisy_gate_policy
+        self.l_aux, self.exp_counts = None, None
+
+    def forward(self, x: torch.Tensor):
+        shape = x.shape
+        h = shape[-1]
+        x2 = x.reshape(-1, h)
+        S, E, k = x2.shape[0], self.num_experts, self.top_k
+        xf = x2.float()
+        if self.noisy_gate_policy == "Jitter" and self.training:
+            xf = multiplicative_jitter(xf, device=xf.device)
+        gates = F.softmax(F.linear(xf, self.wg.weight.float()), dim=1)
+        w, idx = torch.topk(gates, k, dim=1)                      # [S, k]
+        if k > 1:
+            w = w / w.sum(1, keepdim=True).clamp_min(torch.finfo(w.dtype).eps)
+        mask1 = F.one_hot(idx[:, 0], E)
+        self.exp_counts = mask1.sum(0).detach()
+        self.l_aux = (gates.mean(0) * mask1.float().mean(0)).sum() * E
+        # ---- sort assignments by expert: rows of expert e are contiguous, experts of one ep rank are adjacent
+        flat_e = idx.reshape(-1)
+        order = torch.argsort(flat_e, stable=True)
+        tok = torch.arange(S, device=x2.device).repeat_interleave(k)[order]
+        counts = torch.bincount(flat_e, minlength=E)
+        send = x2[tok]
+        if self.ep_size > 1:
+            recv_counts = torch.empty_like(counts)
+            dist.all_to_all_single(recv_counts, counts, group=self.ep_group)   # [ep, E_local] rows coming from each rank
+            send_splits = counts.view(self.ep_size, -1).sum(1).tolist()
+            rc = recv_counts.view(self.ep_size, self.num_local_experts)
+            recv_splits = rc.sum(1).tolist()
+            recv = _AllToAllV.apply(self.ep_group, send, send_splits, recv_splits)
+            # received rows are grouped (source rank, local expert): regroup by local expert
+            src_expert = torch.repeat_interleave(
+                torch.arange(self.num_local_experts, device=x2.device).repeat(self.ep_size), rc.reshape(-1))
+            regroup = torch.argsort(src_expert, stable=True)
+            rows = recv[regroup]
+            per_expert = rc.sum(0).tolist()
+        else:
+            rows, per_expert, regroup = send, counts.tolist(), None
+        outs, start = [], 0
+        for e, n in enumerate(per_expert):  # grouped GEMM over exactly-sized slabs
+            outs.append(self.experts.wrapped_experts[e](rows[start:start + n]) if n > 0 else rows[start:start])
+            start += n
+        out = torch.cat(outs, 0) if outs else rows
+        if self.ep_size > 1:
+            back = torch.empty_like(out).index_copy(0, regroup, out)
+            out = _AllToAllV.apply(self.ep_group, back, recv_splits, send_splits)
+        wsel = w.reshape(-1)[order].to(out.dtype)
+        combined = x2.new_zeros(S, h).index_add(0, tok, out * wsel.unsqueeze(1))
+        return combined.reshape(shape)
+
+
 @MOE_INITIALIZER.register_module("MegaBlock")
 def _build_megablock(**kw):
-    kw["drop_tokens"] = False  # dropless, padded to the busiest expert
+    kw["drop_tokens"] = False  # capacity-padded variant: padded to the busiest expert instead of dropping
     return _build_gshard(**kw)
 
 
 @MOE_INITIALIZER.register_module("MegaBlock-D")
-def _build_megablock_d(**kw):
-    kw["drop_tokens"] = False
-    return _build_gshard(**kw)
+def _build_megablock_d(hidden_size, num_experts, ep_group, ep_size, mlp_ratio, device, dtype, top_k=1,
+                       noisy_gate_policy=None, **unused):
+    num_local = num_experts // ep_size
+    experts = [FeedForward(hidden_size, int(hidden_size * mlp_ratio), out_features=hidden_size, process_group=None,
+                           bias=False, device=device, dtype=dtype) for _ in range(num_local)]
+    return DroplessMOELayer(hidden_size, num_experts, ep_group, ep_size, Experts(experts, num_local, f"moe_ep_size_{ep_size}"),
+                            top_k=top_k, noisy_gate_policy=noisy_gate_policy, device=device)
 
 
 class MoE(nn.Module):

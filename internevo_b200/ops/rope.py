@@ -79,24 +79,30 @@ def rope_(x: torch.Tensor, pos: Optional[torch.Tensor], cos: torch.Tensor, sin: 
 
 
 class _RopeFn(torch.autograd.Function):
+    """In place on ``x`` (``[T, heads * D]`` or ``[T, heads, D]``).  Call it on the tensor the projection GEMM returned,
+    not on a view of it: an in-place autograd op on a view makes autograd insert CopySlices (two full copies of the
+    gradient per call in backward)."""
+
     @staticmethod
-    def forward(ctx, x, pos, cos, sin, group, rot, interleaved):
+    def forward(ctx, x, pos, cos, sin, group, rot, interleaved, head_dim):
         ctx.save_for_backward(pos, cos, sin)
-        ctx.cfg = (group, rot, interleaved)
+        ctx.cfg = (group, rot, interleaved, head_dim)
         ctx.mark_dirty(x)
-        rope_(x, pos, cos, sin, group, rot, False, interleaved)
+        rope_(x.view(x.shape[0], -1, head_dim), pos, cos, sin, group, rot, False, interleaved)
         return x
 
     @staticmethod
     def backward(ctx, dx):
         pos, cos, sin = ctx.saved_tensors
-        group, rot, interleaved = ctx.cfg
+        group, rot, interleaved, head_dim = ctx.cfg
         dx = dx.contiguous()  # the incoming gradient is produced by our attention backward: safe to rotate in place
-        rope_(dx, pos, cos, sin, group, rot, True, interleaved)
-        return dx, None, None, None, None, None, None
+        rope_(dx.view(dx.shape[0], -1, head_dim), pos, cos, sin, group, rot, True, interleaved)
+        return dx, None, None, None, None, None, None, None
 
 
 def apply_rotary_packed(x: torch.Tensor, pos: Optional[torch.Tensor], cos: torch.Tensor, sin: torch.Tensor,
-                        group: int = 1, rot_per_group: int = 1, interleaved: bool = False) -> torch.Tensor:
-    """Autograd-aware in-place RoPE on ``[T, heads, D]`` (the InternLM2 packed wqkv output viewed as heads)."""
-    return _RopeFn.apply(x, pos, cos, sin, group, rot_per_group, interleaved)
+                        group: int = 1, rot_per_group: int = 1, interleaved: bool = False,
+                        head_dim: Optional[int] = None) -> torch.Tensor:
+    """Autograd-aware in-place RoPE on ``[T, heads, D]`` or, with ``head_dim``, on the flat ``[T, heads * D]`` projection
+    output (the InternLM2 packed wqkv viewed as heads)."""
+    return _RopeFn.apply(x, pos, cos, sin, group, rot_per_group, interleaved, head_dim or x.shape[-1])

@@ -79,11 +79,22 @@ def initialize_model(pre_process_func: Optional[Callable] = None, post_process_f
 
 def wrap_FSDP_model(model: Union[nn.Module, nn.ModuleList]):
     """Optional torch-FSDP (ZeRO-3) wrapping over the ZERO1 group (reference ``:217-250``)."""
+    import functools
+
+    from torch.distributed.fsdp import BackwardPrefetch
     from torch.distributed.fsdp import FullyShardedDataParallel as FSDP
     from torch.distributed.fsdp.fully_sharded_data_parallel import ShardingStrategy
+    from torch.distributed.fsdp.wrap import transformer_auto_wrap_policy
 
+    from internevo_b200.models.decoder import DecoderLayer
+
+    policy = functools.partial(transformer_auto_wrap_policy, transformer_layer_cls={DecoderLayer})
+    kw = {}
+    if torch.cuda.is_available():
+        kw["device_id"] = torch.cuda.current_device()
     return FSDP(module=model, process_group=gpc.get_group(ParallelMode.ZERO1), sharding_strategy=ShardingStrategy.FULL_SHARD,
-                forward_prefetch=True, use_orig_params=True)
+                auto_wrap_policy=policy, forward_prefetch=True, backward_prefetch=BackwardPrefetch.BACKWARD_PRE,
+                limit_all_gathers=True, use_orig_params=True, **kw)
 
 
 def initialize_isp_communicator(model: Union[nn.Module, nn.ModuleList]):
@@ -120,8 +131,13 @@ def initialize_optimizer(model: Union[nn.Module, nn.ModuleList], isp_communicato
     zero_cfg = gpc.config.hybrid_zero_optimizer
     if gpc.is_using_parallel_mode(ParallelMode.PIPELINE) and not gpc.is_pipeline_first_stage(ignore_virtual=True):
         zero_cfg.overlap_sync_grad = False
-    optimizer = HybridZeroOptimizer(naive, grad_scal_cfg=gpc.config.grad_scaler, zero_cfg=zero_cfg,
-                                    isp_communicator=isp_communicator)
+    if gpc.config.parallel.zero1.get("fsdp", False):
+        from internevo_b200.solver.optimizer import FSDPadaptOptimizer
+
+        optimizer = FSDPadaptOptimizer(naive, grad_scal_cfg=gpc.config.grad_scaler, zero_cfg=zero_cfg)
+    else:
+        optimizer = HybridZeroOptimizer(naive, grad_scal_cfg=gpc.config.grad_scaler, zero_cfg=zero_cfg,
+                                        isp_communicator=isp_communicator)
     beta2_scheduler = Beta2Scheduler(optimizer=naive, **gpc.config.beta2_scheduler)
     lr_scheduler = FineTuneCosineAnnealingWarmupLR(optimizer, **gpc.config.lr_scheduler)
     return optimizer, beta2_scheduler, lr_scheduler

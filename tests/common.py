@@ -59,7 +59,7 @@ def run_distributed(fn, world, *args, timeout=300):
 
 def tiny_config(tp=1, pp=1, zero1=-1, mode="mtp", dtype="torch.float32", num_layers=4, micro_num=2, num_chunks=1,
                 model_type="INTERNLM2_PUBLIC", wp=1, hidden=64, heads=4, kv_heads=2, seq_len=32, micro_bsz=2,
-                vocab=128, checkpoint=False, **model_extra):
+                vocab=128, checkpoint=False, fsdp=False, **model_extra):
     model = dict(checkpoint=checkpoint, num_chunks=num_chunks, num_attention_heads=heads, embed_split_hidden=True,
                  vocab_size=vocab, embed_grad_scale=1, parallel_output=True, hidden_size=hidden, num_layers=num_layers,
                  mlp_ratio=2, apply_post_layer_norm=False, dtype=dtype, norm_type="rmsnorm",
@@ -80,7 +80,7 @@ def tiny_config(tp=1, pp=1, zero1=-1, mode="mtp", dtype="torch.float32", num_lay
         lr_scheduler=dict(total_steps=10, init_steps=0, warmup_ratio=0.1, eta_min=1e-4, last_epoch=-1),
         beta2_scheduler=dict(init_beta2=0.95, c=0, cur_iter=-1),
         model=model, enable_tb=False,
-        parallel=dict(zero1=dict(size=zero1), tensor=dict(size=tp, mode=mode),
+        parallel=dict(zero1=dict(size=zero1, fsdp=fsdp), tensor=dict(size=tp, mode=mode),
                       pipeline=dict(size=pp, interleaved_overlap=True), weight=dict(size=wp, overlap=True, memory_pool=True)),
     )
 
