@@ -314,6 +314,7 @@ void ag_gemm(const Tensor& x_local, int64_t gathered_ptrs, int64_t flags_ptrs, i
 TORCH_LIBRARY(b200, m) {
     m.def("gemm(Tensor a, Tensor b, Tensor(a!) out, bool a_mn, bool b_mn, Tensor? bias, int flags, Tensor? h, int force_bn, int max_ctas) -> ()", &gemm);
     m.def("set_gemm_tail_split(int on) -> ()", [](int64_t on) { b200::set_gemm_tail_split(static_cast<int>(on)); });
+    m.def("set_gemm_group_m(int g) -> ()", [](int64_t g) { b200::set_gemm_group_m(static_cast<int>(g)); });
     m.def("rmsnorm_fwd(Tensor x, Tensor? res_in, Tensor w, Tensor(a!) y, Tensor? res_out, Tensor? rstd, float eps) -> ()", &rmsnorm_fwd);
     m.def("rmsnorm_bwd_blocks(int rows) -> int", &rmsnorm_bwd_blocks);
     m.def("rmsnorm_bwd(Tensor dy, Tensor res, Tensor w, Tensor rstd, Tensor? dres, Tensor(a!) dx, Tensor(b!) dw_partial, Tensor(c!) dw, bool accumulate) -> ()", &rmsnorm_bwd);

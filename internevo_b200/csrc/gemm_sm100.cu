@@ -49,13 +49,15 @@ struct GemmKernelArgs {
     int flags;
     int a_mn, b_mn;
     int tiles_m, tiles_n;
+    int group_m;      // raster group height in tile rows
     int tiles_full;   // work items [0, tiles_full) are whole BM x BN tiles
     int tail_split;   // the remaining tiles are split into this many column slices (1, 2 or 4) to fill the last wave
 };
 
 
-B200_DEVICE void tile_coords(int tile, int tiles_m, int tiles_n, int& m, int& n) {
-    constexpr int GROUP_M = 8;
+// Raster: groups of `GROUP_M` tile rows are swept column by column (8 rows: square-ish footprint of one wave of tiles;
+// taller groups were not measurably better on the 7B shapes, see profiles/gemm_perf_r1_v4_group_ab.json).
+B200_DEVICE void tile_coords(int tile, int tiles_m, int tiles_n, int& m, int& n, int GROUP_M) {
     const int per_group = GROUP_M * tiles_n;
     const int g = tile / per_group;
     const int first_m = g * GROUP_M;
@@ -76,7 +78,7 @@ B200_DEVICE void item_coords(int item, const GemmKernelArgs& a, int& tm, int& tn
         slice = w % a.tail_split;
         width = BN / a.tail_split;
     }
-    tile_coords(tile, a.tiles_m, a.tiles_n, tm, tn);
+    tile_coords(tile, a.tiles_m, a.tiles_n, tm, tn, a.group_m);
     n_off = slice * width;
 }
 
@@ -686,7 +688,9 @@ static int num_sms() {
 }
 
 static int g_tail_split = 1;
+static int g_group_m = 0;  // 0 = default (8)
 void set_gemm_tail_split(int on) { g_tail_split = on; }
+void set_gemm_group_m(int g) { g_group_m = g; }
 
 template <int BN, int CG = 1>
 static int launch(const GemmDesc& g, cudaStream_t stream) {
@@ -712,6 +716,7 @@ static int launch(const GemmDesc& g, cudaStream_t stream) {
     a.a_mn = g.a_mn_major; a.b_mn = g.b_mn_major;
     a.tiles_m = (g.M + BM * CG - 1) / (BM * CG);
     a.tiles_n = (g.N + BN - 1) / BN;
+    a.group_m = g_group_m > 0 ? g_group_m : 8;
     const int tiles = a.tiles_m * a.tiles_n;
     int sms = (g.max_ctas > 0 ? g.max_ctas : num_sms()) / CG;  // work units: CTAs or CTA pairs
     const int grid = tiles < sms ? tiles : sms;
@@ -799,7 +804,7 @@ int gemm_bf16_comm(const GemmDesc& g, const GemmCommArgs& c, cudaStream_t stream
         if (rc) return rc;
     }
     GemmKernelArgs a;
-    a.tiles_full = tiles_m * tiles_n; a.tail_split = 1;
+    a.tiles_full = tiles_m * tiles_n; a.tail_split = 1; a.group_m = 8;
     a.M = g.M; a.N = g.N; a.K = g.K;
     a.D = g.D; a.ldd = g.ldd;
     a.bias = nullptr; a.H = g.H; a.ldh = g.ldh; a.flags = g.flags;

@@ -34,6 +34,8 @@ struct GemmDesc {
 int gemm_bf16(const GemmDesc& g, cudaStream_t stream);
 // Enable / disable splitting the tiles of the last partial wave into column slices (default on).
 void set_gemm_tail_split(int on);
+// Raster group height in tile rows (0 = automatic: whole M when it fits 32 tile rows, else 8).
+void set_gemm_group_m(int g);
 
 // ---- GEMM fused with its tensor-parallel collective (one launch, peer memory over NVLink) -------------------------
 enum GemmCommMode : int {

@@ -144,15 +144,17 @@ def gemm_perf():
         A = a.t() if a_mn else a
         Bt = b if b_mn else b.t()
         row = {"case": name, "M": M, "N": N, "K": K}
-        for bn, split in ((256, 1), (256, 0), (128, 1), (512, 1)):
-            key = {256: "ours_bn256", 128: "ours_bn128", 512: "ours_2cta"}[bn] + ("_tflops" if split else "_nosplit_tflops")
+        for bn, split, grp in ((256, 1, 0), (128, 1, 0), (512, 1, 8), (512, 1, 0)):
+            key = {256: "ours_bn256", 128: "ours_bn128", 512: "ours_2cta"}[bn] + ("_group8" if grp else "") + "_tflops"
             torch.ops.b200.set_gemm_tail_split(split)
+            torch.ops.b200.set_gemm_group_m(grp)
             try:
                 ms = timeit(lambda: ops.matmul(a, b, a_mn=a_mn, b_mn=b_mn, out=out, force_bn=bn), flush=flush)
                 row[key] = round(2 * M * N * K / ms / 1e9, 1)
             except Exception as e:  # noqa
                 row[key] = f"ERR {e}"
         torch.ops.b200.set_gemm_tail_split(1)
+        torch.ops.b200.set_gemm_group_m(0)
         ms = timeit(lambda: torch.matmul(A, Bt, out=out), flush=flush)
         row["cublas_tflops"] = round(2 * M * N * K / ms / 1e9, 1)
         print(json.dumps(row), flush=True)
