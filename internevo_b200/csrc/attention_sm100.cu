@@ -92,8 +92,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int seq, blk, s0, len;
-    if (!find_qblock(args.cu_seqlens, args.num_seqs, blockIdx.x, 2 * TM, seq, blk, s0, len)) return;
-    const int h = blockIdx.y;
+    // grid = (heads, q blocks): CTAs are dispatched x-fastest, so the heaviest (latest) q blocks of ALL heads start first
+    if (!find_qblock(args.cu_seqlens, args.num_seqs, blockIdx.y, 2 * TM, seq, blk, s0, len)) return;
+    const int h = blockIdx.x;
     const int qpk = args.H / args.Hkv;
     const int hk = h / qpk;
     const int q_row0 = blk * 2 * TM;  // local row of the block inside the sequence
@@ -341,7 +342,7 @@ int attn_fwd(const AttnDesc& d, cudaStream_t stream) {
             return -12;
         attr = true;
     }
-    dim3 grid(upper_qblocks(d.T, d.num_seqs, 2 * TM), d.H);
+    dim3 grid(d.H, upper_qblocks(d.T, d.num_seqs, 2 * TM));
     attn_fwd_kernel<<<grid, FWD_THREADS, FwdSmem::TOTAL, stream>>>(tq, tk, tv, a);
     return cudaGetLastError() == cudaSuccess ? 0 : -13;
 }
@@ -437,10 +438,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const AttnKernelArgs& f = args.f;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int seq, blk, s0, len;
-    if (!find_qblock(f.cu_seqlens, f.num_seqs, blockIdx.x, TN, seq, blk, s0, len)) return;
+    // grid = (kv heads, kv tiles): x-fastest dispatch starts the heaviest kv tiles of all heads first (LPT order)
+    if (!find_qblock(f.cu_seqlens, f.num_seqs, blockIdx.y, TN, seq, blk, s0, len)) return;
     const int nkv = (len + TN - 1) / TN;
     blk = nkv - 1 - blk;                      // find_qblock reverses; bwd wants early (heavy) kv tiles first
-    const int hk = blockIdx.y;
+    const int hk = blockIdx.x;
     const int qpk = f.H / f.Hkv;
     const int kv0 = blk * TN;
     const int mq0 = f.causal ? kv0 / BQ : 0;
@@ -768,7 +770,7 @@ int attn_bwd(const AttnBwdDesc& b, cudaStream_t stream) {
             return -12;
         attr = true;
     }
-    dim3 grid(upper_qblocks(d.T, d.num_seqs, TN), d.Hkv);
+    dim3 grid(d.Hkv, upper_qblocks(d.T, d.num_seqs, TN));
     attn_bwd_kernel<<<grid, BWD_THREADS, BwdSmem::TOTAL, stream>>>(tq, tk, tv, tdo, tdq, a);
     {
         const int qpk = d.H / d.Hkv;
