@@ -176,8 +176,7 @@ def load_scheduler(ckpt_path: str, lr_scheduler, optimizer, train_state):
     if "after_scheduler_dict" in scheduler_states:
         scheduler_states["after_scheduler_dict"]["base_lrs"] = [learning_rate] * len(
             scheduler_states["after_scheduler_dict"]["base_lrs"])
-    lr_scheduler.load_state_dict(scheduler_states)
-    lr_scheduler.last_epoch = train_state.step_count
+    lr_scheduler.load_state_dict(scheduler_states)  # last_epoch == number of completed steps (closed-form schedule)
     del scheduler_states
     ratio = learning_rate / base_lrs[0] if base_lrs and base_lrs[0] else 1.0
     lr_scheduler._last_lr = [lr * ratio for lr in lr_scheduler.get_lr()] if ratio != 1.0 else lr_scheduler.get_lr()

@@ -45,7 +45,9 @@ class TrainState:
         self.num_consumed_tokens = other_stuffs["num_consumed_tokens"]
         self.inf_nan_skip_batches = other_stuffs["inf_nan_skip_batches"]
         self.batch_count = other_stuffs["batch_count"] + 1  # resume from the next batch
-        self.step_count = other_stuffs.get("step_count", other_stuffs["batch_count"]) + 1
+        # step_count counts COMPLETED optimizer steps and the checkpoint is written after it was incremented
+        # (reference trainer.py:114-118): restore it as saved
+        self.step_count = other_stuffs.get("step_count", other_stuffs["batch_count"] + 1)
         if self.resume_tb_folder is None:
             self.resume_tb_folder = other_stuffs.get("tensorboard_folder", None)
 

@@ -230,3 +230,6 @@ class SchedulerHook(ABC):
     @abstractmethod
     def post_helper_func(self, scheduler, outputs, label) -> None:
         """metrics etc."""
+
+
+from internevo_b200.core.context.config import read_base  # noqa: E402,F401  (config files import it from here too)

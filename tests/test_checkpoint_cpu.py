@@ -1,0 +1,76 @@
+"""Checkpoint manager: file layout, completion marker, snapshot alternation, stop-file protocol and bit-exact auto-resume
+(reference strategy: tests/test_utils/test_model_checkpoint.py — save, 'crash', resume, compare)."""
+import os
+
+import torch
+
+from common import build_trainer, run_distributed, synthetic_batch, tiny_config
+
+
+def _step(trainer, cfg, dpr, seed):
+    T = cfg["data"]["seq_len"] * cfg["data"]["micro_bsz"]
+    data, labels = synthetic_batch(2, T, cfg["model"]["vocab_size"], seed=seed * 10 + dpr)
+    trainer.zero_grad()
+    out = trainer.execute_schedule((data, labels), forward_only=False, return_loss=True, return_output_label=False)
+    ok, norms = trainer.step()
+    assert ok
+    return float(out[2])
+
+
+def _run(rank, world, folder, phase):
+    from internevo_b200.checkpoint import CheckpointManager
+    from internevo_b200.core.context import ParallelMode, global_context as gpc
+    from internevo_b200.core.trainer import TrainState
+
+    cfg = tiny_config(zero1=world, num_layers=2, micro_num=2)
+    cfg["ckpt"] = dict(enable_save_ckpt=True, save_ckpt_folder=f"local:{folder}", checkpoint_every=2, oss_snapshot_freq=3,
+                       auto_resume=(phase == "resume"), async_upload=False, stop_file_path=os.path.join(folder, "stop"))
+    trainer, opt, model, _ = build_trainer(cfg)
+    dpr = gpc.get_local_rank(ParallelMode.DATA)
+    ts = TrainState(gpc.config, None)
+    mm = CheckpointManager(ckpt_config=gpc.config.ckpt, model=model, optimizer=opt, lr_scheduler=trainer.engine._lr_scheduler,
+                           model_config=gpc.config.model)
+    mm.try_resume_training(ts)
+    losses = {}
+    if phase == "first":
+        assert ts.step_count == 0
+        for step in range(1, 5):  # same bookkeeping as train.py: 0-based batch_count, step_count = completed steps
+            ts.batch_count = step - 1
+            losses[step] = _step(trainer, cfg, dpr, step)
+            ts.step_count += 1
+            stop = mm.try_save_checkpoint(ts)
+            assert not stop
+        mm.wait_async_upload_finish()
+        if rank == 0:
+            for s in (2, 4):
+                names = set(os.listdir(os.path.join(folder, str(s))))
+                assert {"model_tp0_pp0.pt", "context.pt", "schedulder.pt", "model_config.pt", f"{s}.step"} <= names, names
+                assert {f"optimizer_tp0_pp0_zo{z}.pt" for z in range(world)} <= names, names
+            assert "3.step" in os.listdir(os.path.join(folder, "snapshot", "0"))   # step 3 snapshot
+        # continue two more steps without saving: the reference trajectory for the resumed run
+        for step in (5, 6):
+            losses[step] = _step(trainer, cfg, dpr, step)
+    else:
+        assert ts.step_count == 4 and ts.batch_count == 4, (ts.step_count, ts.batch_count)  # newest complete ckpt: step 4
+        for step in (5, 6):
+            losses[step] = _step(trainer, cfg, dpr, step)
+        # stop file: "save at step 6 and quit"
+        if rank == 0:
+            open(os.path.join(folder, "stop"), "w").write("6")
+        torch.distributed.barrier()
+        ts.step_count, ts.batch_count = 6, 5
+        mm.checkpoint_every = 1000
+        mm.oss_snapshot_freq = 1000
+        assert mm.try_save_checkpoint(ts) is True
+        if rank == 0:
+            assert os.path.exists(os.path.join(folder, "6", "6.step"))
+            assert open(os.path.join(folder, "stop")).read().strip() == "0"
+    return losses
+
+
+def test_save_resume_is_exact(tmp_path):
+    first = run_distributed(_run, 2, str(tmp_path), "first")
+    resumed = run_distributed(_run, 2, str(tmp_path), "resume")
+    for r in range(2):
+        for step in (5, 6):
+            assert abs(first[r][step] - resumed[r][step]) < 1e-6, (first[r], resumed[r])
