@@ -42,6 +42,21 @@ def _ws(group):
 # ----------------------------------------------------------------------------------------------------------------
 # embeddings
 # ----------------------------------------------------------------------------------------------------------------
+class _ScaleGrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, s):
+        ctx.s = s
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * ctx.s, None
+
+
+def _scale_grad(x, s):
+    return _ScaleGrad.apply(x, s)
+
+
 class Embedding1D(nn.Module):
     """Token embedding split along the *hidden* dimension; forward gathers the hidden shards and (under sequence
     parallel) keeps only the local sequence slice (reference ``modules/embedding.py:17-60``)."""
@@ -59,8 +74,12 @@ class Embedding1D(nn.Module):
         out = F.embedding(input_, self.weight, self.padding_idx)
         group = gpc.get_group(ParallelMode.TENSOR)
         if _is_isp():
-            # ISP: weights are replicated over the sequence group, activations sequence-sharded
-            return split_forward_gather_backward(out, group, dim=0) if _ws(group) > 1 else out
+            # ISP: weights are replicated over the sequence group, activations sequence-sharded.  Every rank's loss is the
+            # mean over ITS shard and the objective is the mean of those, so the gathered gradient (one block per shard)
+            # carries a factor 1 / tp: without it the embedding would be updated with tp x the true gradient.
+            if _ws(group) <= 1:
+                return out
+            return _scale_grad(split_forward_gather_backward(out, group, dim=0), 1.0 / _ws(group))
         out = gather_forward_split_backward(out, group, dim=-1)
         if gpc.config.parallel.get("sequence_parallel", False) and _ws(group) > 1:
             out = split_forward_gather_backward(out, group, dim=0)

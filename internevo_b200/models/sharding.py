@@ -63,6 +63,17 @@ def unshard_tensors(name: str, parts, embed_split_hidden: bool = True) -> torch.
     return parts[0]
 
 
+_LINEAR_W = _COL + _ROW + ("wqkv.weight", "Wqkv.weight", "wqkv.bias", "Wqkv.bias")
+
+
+def shard_state_dict_isp(full: Dict[str, torch.Tensor], rank: int, size: int):
+    """ISP / weight parallel: EVERY linear weight (column- and row-parallel alike) is split along the output dimension
+    over the WEIGHT group (``ISPLinear`` all-gathers it right before use); embeddings and norms are replicated."""
+    if size == 1:
+        return dict(full)
+    return {k: (_chunk(v, size, rank, 0) if any(k.endswith(e) for e in _LINEAR_W) else v) for k, v in full.items()}
+
+
 def pipeline_slice(full: Dict[str, torch.Tensor], start: int, end: int, first: bool, last: bool,
                    layers_name: str = "layers", embed_name: str = "tok_embeddings", final_norm: str = "norm",
                    head: str = "output"):

@@ -326,8 +326,29 @@ class BaseScaleColumnParallelLinear(nn.Module):
         return self.tmp_weight
 
 
+class _GatherWeightFn(torch.autograd.Function):
+    """Weight-parallel parameter → full weight: all-gather forward, reduce-scatter (AVG) of the gradient backward
+    (every rank of the WEIGHT group saw different tokens, like data parallel ranks)."""
+
+    @staticmethod
+    def forward(ctx, w, group):
+        ctx.group = group
+        ws = _ws(group)
+        out = torch.empty(ws * w.shape[0], *w.shape[1:], dtype=w.dtype, device=w.device)
+        dist.all_gather_into_tensor(out, w.contiguous(), group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        ws = _ws(ctx.group)
+        out = torch.empty(g.shape[0] // ws, *g.shape[1:], dtype=g.dtype, device=g.device)
+        dist.reduce_scatter_tensor(out, g.contiguous(), group=ctx.group)
+        return out.div_(ws), None
+
+
 class ScaleColumnParallelLinear(BaseScaleColumnParallelLinear):
-    """LM head. ``forward(x, gather_dim, tp_mode)`` accepts sequence-sharded ``x`` under msp/fsp."""
+    """LM head. ``forward(x, gather_dim, tp_mode)`` accepts sequence-sharded ``x`` under msp/fsp; under ``isp`` the
+    vocabulary shards (WEIGHT group) are gathered and the logits are full-vocabulary for the local sequence shard."""
 
     def forward(self, x, gather_dim=0, tp_mode: str = "mtp"):
         weight = self._scaled_weight()
@@ -335,6 +356,11 @@ class ScaleColumnParallelLinear(BaseScaleColumnParallelLinear):
             weight = self._norm_weight(weight)
         shape = x.shape
         x2 = x.reshape(-1, shape[-1])
+        if tp_mode == "isp":
+            if _ws(self.process_group) > 1:
+                weight = _GatherWeightFn.apply(weight, self.process_group)
+            y = ops.linear(x2, weight, self.bias) if x2.is_cuda else F.linear(x2, weight, self.bias)
+            return y if len(shape) == 2 else y.reshape(*shape[:-2], -1, y.shape[-1])
         mode = tp_mode if tp_mode in ("msp", "fsp") else "mtp"
         y = _ParallelLinearFn.apply(x2, weight, self.bias, self.process_group, "column", mode)
         return y if len(shape) == 2 else y.reshape(*shape[:-2], -1, y.shape[-1])
