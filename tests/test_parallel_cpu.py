@@ -7,7 +7,7 @@ import torch
 from common import build_trainer, run_distributed, synthetic_batch, tiny_config
 
 STEPS = 3
-MICRO_TOTAL = 4
+MICRO_TOTAL = 4  # micro-batches per step (split over dp ranks)
 
 
 def _golden_state(cfg, seed=7):
@@ -144,3 +144,24 @@ def test_isp_tp2_wp2(baseline):
 
 def test_pp4_1f1b(baseline):
     _check(run_distributed(_train, 4, dict(pp=4, micro_num=MICRO_TOTAL)), baseline)
+
+
+def test_pp4_interleaved_8layers():
+    """4 stages x 2 virtual chunks, 8 micro-batches: the steady-state 1F1B phase crosses chunk boundaries."""
+    import test_parallel_cpu as me
+
+    old = me.MICRO_TOTAL
+    me.MICRO_TOTAL = 8
+    try:
+        kw = dict(micro_num=8, num_layers=8)
+        base = run_distributed(_train8, 1, kw)[0]
+        _check(run_distributed(_train8, 4, dict(pp=4, num_chunks=2, **kw)), base)
+    finally:
+        me.MICRO_TOTAL = old
+
+
+def _train8(rank, world, kw):
+    import test_parallel_cpu as me
+
+    me.MICRO_TOTAL = 8
+    return _train(rank, world, kw)
