@@ -54,6 +54,12 @@ void gemm(const Tensor& a, const Tensor& b, Tensor& out, bool a_mn, bool b_mn, c
                     "gemm: bad swiglu output");
         g.H = h->data_ptr(); g.ldh = h->stride(0);
     }
+    if (flags & b200::GEMM_GELU) {
+        TORCH_CHECK(h.has_value() && h->scalar_type() == at::kBFloat16 && h->size(0) == g.M && h->size(1) == g.N &&
+                        h->stride(1) == 1 && h->stride(0) % 8 == 0 && !(flags & b200::GEMM_OUT_F32),
+                    "gemm: bad gelu output");
+        g.H = h->data_ptr(); g.ldh = h->stride(0);
+    }
     g.flags = static_cast<int>(flags);
     g.force_bn = static_cast<int>(force_bn);
     g.max_ctas = static_cast<int>(max_ctas);
@@ -110,6 +116,28 @@ void swiglu_fwd(const Tensor& gu, Tensor& h) {
     c10::cuda::CUDAGuard guard(gu.device());
     const int64_t F = h.size(-1);
     CHECK_RC(b200::swiglu_fwd(gu.data_ptr(), h.data_ptr(), h.numel() / F, F, cur_stream()), "b200::swiglu_fwd");
+}
+// one decode step: q [B, H, D] against the first `seqlen` positions of the caches [B, Smax, Hkv, D]
+void attn_decode(const Tensor& q, const Tensor& kcache, const Tensor& vcache, Tensor& out, Tensor& work, Tensor& tickets,
+                 int64_t seqlen, int64_t nsplit, double scale) {
+    CHECK_BF16(q); CHECK_BF16(kcache); CHECK_BF16(vcache); CHECK_BF16(out);
+    TORCH_CHECK(q.dim() == 3 && q.is_contiguous() && out.is_contiguous() && kcache.dim() == 4, "attn_decode: shapes");
+    const int64_t B = q.size(0), H = q.size(1), D = q.size(2), Hkv = kcache.size(2);
+    TORCH_CHECK(kcache.stride(3) == 1 && kcache.stride(2) == D && vcache.strides() == kcache.strides(), "attn_decode: cache layout");
+    TORCH_CHECK(work.scalar_type() == at::kFloat && work.numel() >= B * H * nsplit * (D + 4), "attn_decode: work size");
+    TORCH_CHECK(tickets.scalar_type() == at::kInt && tickets.numel() >= B * Hkv, "attn_decode: tickets");
+    c10::cuda::CUDAGuard guard(q.device());
+    CHECK_RC(b200::attn_decode(q.data_ptr(), kcache.data_ptr(), vcache.data_ptr(), out.data_ptr(), work.data_ptr<float>(),
+                               reinterpret_cast<unsigned int*>(tickets.data_ptr<int>()), B, H, Hkv, D, seqlen, nsplit,
+                               kcache.stride(0), kcache.stride(1), static_cast<float>(scale), cur_stream()),
+             "b200::attn_decode");
+}
+void gelu_bwd(const Tensor& dh, const Tensor& pre, Tensor& dpre) {
+    CHECK_BF16(dh); CHECK_BF16(pre); CHECK_BF16(dpre);
+    TORCH_CHECK(dh.is_contiguous() && pre.is_contiguous() && dpre.is_contiguous() && dh.numel() == pre.numel(),
+                "gelu_bwd: contiguous tensors of equal size");
+    c10::cuda::CUDAGuard guard(dh.device());
+    CHECK_RC(b200::gelu_bwd(dh.data_ptr(), pre.data_ptr(), dpre.data_ptr(), dh.numel(), cur_stream()), "b200::gelu_bwd");
 }
 void swiglu_bwd(const Tensor& dh, const Tensor& gu, Tensor& dgu) {
     CHECK_BF16(dh); CHECK_BF16(gu); CHECK_BF16(dgu);
@@ -321,6 +349,8 @@ TORCH_LIBRARY(b200, m) {
     m.def("rope(Tensor(a!) x, Tensor? pos, Tensor cos_t, Tensor sin_t, int group, int rot_per_group, bool conj, bool interleaved) -> ()", &rope);
     m.def("swiglu_fwd(Tensor gu, Tensor(a!) h) -> ()", &swiglu_fwd);
     m.def("swiglu_bwd(Tensor dh, Tensor gu, Tensor(a!) dgu) -> ()", &swiglu_bwd);
+    m.def("gelu_bwd(Tensor dh, Tensor pre, Tensor(a!) dpre) -> ()", &gelu_bwd);
+    m.def("attn_decode(Tensor q, Tensor kcache, Tensor vcache, Tensor(a!) out, Tensor(b!) work, Tensor(c!) tickets, int seqlen, int nsplit, float scale) -> ()", &attn_decode);
     m.def("ce_fwd(Tensor logits, Tensor labels, int vocab_start, Tensor(a!) out_max, Tensor(b!) out_sum, Tensor(c!) out_sumx, Tensor(d!) out_tgt) -> ()", &ce_fwd);
     m.def("ce_bwd(Tensor(a!) logits, Tensor labels, Tensor lse, Tensor gscale, int vocab_start, float smoothing, int total_classes, int ignore_index) -> ()", &ce_bwd);
     m.def("adamw(Tensor(a!) p, Tensor(b!) m, Tensor(c!) v, Tensor g, Tensor? p_lp, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2, Tensor? scalars) -> ()", &adamw);

@@ -353,6 +353,32 @@ __global__ void swiglu_bwd_kernel(const uint2* __restrict__ dh, const uint4* __r
         dgu[i] = pack8(o);
     }
 }
+// dpre = dh * d/dx gelu_tanh(pre)
+__global__ void gelu_bwd_kernel(const uint4* __restrict__ dh, const uint4* __restrict__ pre, uint4* __restrict__ dpre,
+                                int64_t nvec) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        float x[8], d[8], o[8];
+        unpack8(pre[i], x);
+        unpack8(dh[i], d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float u = 0.7978845608028654f * (x[j] + 0.044715f * x[j] * x[j] * x[j]);
+            const float t = tanhf(u);
+            const float du = 0.7978845608028654f * (1.f + 3.f * 0.044715f * x[j] * x[j]);
+            o[j] = d[j] * (0.5f * (1.f + t) + 0.5f * x[j] * (1.f - t * t) * du);
+        }
+        dpre[i] = pack8(o);
+    }
+}
+int gelu_bwd(const void* dh, const void* pre, void* dpre, int64_t n, cudaStream_t s) {
+    if (n % 8 != 0) return -1;
+    const int64_t nvec = n / 8;
+    const int blocks = (int)((nvec + 255) / 256 < 148 * 16 ? (nvec + 255) / 256 : 148 * 16);
+    if (blocks == 0) return 0;
+    gelu_bwd_kernel<<<blocks, 256, 0, s>>>((const uint4*)dh, (const uint4*)pre, (uint4*)dpre, nvec);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
 int swiglu_fwd(const void* gu, void* h, int64_t rows, int64_t F, cudaStream_t s) {
     if (F % 4 != 0) return -1;
     const int64_t nvec = rows * F / 4;
@@ -597,6 +623,137 @@ __global__ void clip_scalars_kernel(const float* __restrict__ sumsq_in, float* _
 }
 int clip_scalars(const float* sumsq_in, float* scalars, float loss_scale, float clip, cudaStream_t s) {
     clip_scalars_kernel<<<1, 1, 0, s>>>(sumsq_in, scalars, loss_scale, clip);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Decode attention (one new token per sequence against the KV cache), split over the keys: bandwidth bound, CUDA cores.
+//   q [B, H, D] bf16, kcache / vcache [B, Smax, Hkv, D] bf16 (first `seqlen` positions valid), out [B, H, D] bf16.
+//   grid (nsplit, Hkv, B); one warp per q head of the kv group; 8 keys in flight per warp (4 lanes x 32 dims per key).
+//   Partials (fp32 acc, m, l) go to `work`; the last-arriving split of each (b, head group) merges them (ticket counter).
+// Replaces the split-KV flash-decoding kernel / FasterTransformer decode MHA the reference links (flash_fwd_splitkv,
+// ft_attention).
+// ----------------------------------------------------------------------------------------------------------------
+static constexpr int DEC_D = 128;
+
+__global__ void __launch_bounds__(256) attn_decode_kernel(const __nv_bfloat16* __restrict__ q,
+                                                          const __nv_bfloat16* __restrict__ kc,
+                                                          const __nv_bfloat16* __restrict__ vc,
+                                                          __nv_bfloat16* __restrict__ out, float* __restrict__ work,
+                                                          unsigned int* __restrict__ tickets, int H, int Hkv, int seqlen,
+                                                          int64_t stride_b, int64_t stride_s, float scale_log2) {
+    const int split = blockIdx.x, nsplit = gridDim.x, hk = blockIdx.y, b = blockIdx.z;
+    const int qpk = H / Hkv;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int per = (seqlen + nsplit - 1) / nsplit;
+    const int k0 = split * per, k1 = min(seqlen, k0 + per);
+    __shared__ int s_last;
+    for (int j = warp; j < qpk; j += blockDim.x >> 5) {
+        const int h = hk * qpk + j;
+        float qf[32];
+        {
+            const uint4* qp = reinterpret_cast<const uint4*>(q + ((int64_t)b * H + h) * DEC_D + t * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float f[8];
+                unpack8(qp[i], f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) qf[i * 8 + e] = f[e] * scale_log2;
+            }
+        }
+        float m = -INFINITY, l = 0.f, acc[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+        for (int base = k0; base < k1; base += 8) {  // uniform trip count: the shuffles below need the whole warp
+            const int key = base + g;
+            const bool valid = key < k1;
+            const int64_t off = (int64_t)b * stride_b + (int64_t)(valid ? key : k0) * stride_s + (int64_t)hk * DEC_D + t * 32;
+            const uint4* kp = reinterpret_cast<const uint4*>(kc + off);
+            const uint4* vp = reinterpret_cast<const uint4*>(vc + off);
+            uint4 kr[4], vr[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { kr[i] = kp[i]; vr[i] = vp[i]; }
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float f[8];
+                unpack8(kr[i], f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) s = fmaf(qf[i * 8 + e], f[e], s);
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (valid) {
+                const float mn = fmaxf(m, s);
+                const float corr = exp2f(m - mn), p = exp2f(s - mn);
+                l = l * corr + p;
+                m = mn;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float f[8];
+                    unpack8(vr[i], f);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[i * 8 + e] = fmaf(acc[i * 8 + e], corr, p * f[e]);
+                }
+            }
+        }
+        // merge the 8 key groups of the warp (lanes with equal t hold the same 32 dims)
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            const float m2 = __shfl_xor_sync(0xffffffffu, m, o), l2 = __shfl_xor_sync(0xffffffffu, l, o);
+            const float mn = fmaxf(m, m2);
+            const float c1 = (m == -INFINITY) ? 0.f : exp2f(m - mn), c2 = (m2 == -INFINITY) ? 0.f : exp2f(m2 - mn);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = acc[i] * c1 + __shfl_xor_sync(0xffffffffu, acc[i], o) * c2;
+            l = l * c1 + l2 * c2;
+            m = mn;
+        }
+        if (g == 0) {
+            float* w = work + (((int64_t)b * H + h) * nsplit + split) * (DEC_D + 4);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<float4*>(w + t * 32 + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+            if (t == 0) { w[DEC_D] = m; w[DEC_D + 1] = l; }
+        }
+    }
+    // the last split to finish for this (b, kv group) combines all partials
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(&tickets[b * Hkv + hk], 1u);
+        s_last = (prev == (unsigned)nsplit - 1);
+        if (s_last) tickets[b * Hkv + hk] = 0;  // ready for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int idx = threadIdx.x; idx < qpk * DEC_D; idx += blockDim.x) {
+        const int j = idx / DEC_D, d = idx % DEC_D;
+        const int h = hk * qpk + j;
+        const float* w = work + ((int64_t)b * H + h) * nsplit * (DEC_D + 4);
+        float M = -INFINITY;
+        for (int s = 0; s < nsplit; ++s) M = fmaxf(M, __ldcg(w + s * (DEC_D + 4) + DEC_D));
+        float num = 0.f, den = 0.f;
+        for (int s = 0; s < nsplit; ++s) {
+            const float ms = __ldcg(w + s * (DEC_D + 4) + DEC_D);
+            const float c = (ms == -INFINITY) ? 0.f : exp2f(ms - M);
+            num += c * __ldcg(w + s * (DEC_D + 4) + d);
+            den += c * __ldcg(w + s * (DEC_D + 4) + DEC_D + 1);
+        }
+        out[((int64_t)b * H + h) * DEC_D + d] = __float2bfloat16_rn(den > 0.f ? num / den : 0.f);
+    }
+}
+
+int attn_decode(const void* q, const void* kc, const void* vc, void* out, float* work, unsigned int* tickets, int B, int H,
+                int Hkv, int D, int seqlen, int nsplit, int64_t stride_b, int64_t stride_s, float scale, cudaStream_t s) {
+    if (D != DEC_D || H % Hkv != 0 || seqlen <= 0) return -1;
+    const int qpk = H / Hkv;
+    const int warps = qpk < 8 ? qpk : 8;
+    dim3 grid(nsplit, Hkv, B);
+    attn_decode_kernel<<<grid, warps * 32, 0, s>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)kc,
+                                                  (const __nv_bfloat16*)vc, (__nv_bfloat16*)out, work, tickets, H, Hkv,
+                                                  seqlen, stride_b, stride_s, scale * 1.4426950408889634f);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

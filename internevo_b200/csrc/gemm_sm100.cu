@@ -535,6 +535,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                 }
                             }
                         }
+                        if (args.flags & GEMM_GELU) {
+                            // H = gelu_tanh(D) on the bf16-rounded pre-activation (backward reads the stored D)
+                            __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(args.H) +
+                                               static_cast<int64_t>(row) * args.ldh + col;
+#pragma unroll
+                            for (int i = 0; i < 32; i += 8) {
+                                if (i < ncols) {
+                                    float hv[8];
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        const float x = __bfloat162float(__float2bfloat16_rn(v[i + j]));
+                                        const float t = tanhf(0.7978845608028654f * (x + 0.044715f * x * x * x));
+                                        hv[j] = 0.5f * x * (1.f + t);
+                                    }
+                                    uint4 o;
+                                    o.x = pack_bf16(hv[0], hv[1]);
+                                    o.y = pack_bf16(hv[2], hv[3]);
+                                    o.z = pack_bf16(hv[4], hv[5]);
+                                    o.w = pack_bf16(hv[6], hv[7]);
+                                    *reinterpret_cast<uint4*>(h + i) = o;
+                                }
+                            }
+                        }
                         if (swiglu) {
                             // columns are interleaved (gate, up) pairs; h = silu(gate) * up, computed on the
                             // bf16-rounded values so that backward (which reads the stored gate/up) matches

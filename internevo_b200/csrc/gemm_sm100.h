@@ -11,6 +11,7 @@ enum GemmFlags : int {
     GEMM_ACCUMULATE = 2,   // D += A*B^T (reads the previous D)
     GEMM_SWIGLU = 4,       // columns of D are interleaved (gate, up); also write H[:, j] = silu(gate_j) * up_j
     GEMM_SKIP_D = 8,       // with GEMM_SWIGLU: do not materialise D
+    GEMM_GELU = 16,        // also write H[:, j] = gelu_tanh(D[:, j]) (bias included), H is bf16 [M, N]
 };
 
 struct GemmDesc {
@@ -24,7 +25,7 @@ struct GemmDesc {
     void* D = nullptr;  // [M, N] row stride ldd, bf16 or fp32
     int64_t ldd = 0;
     const void* bias = nullptr;  // bf16 [N] or null
-    void* H = nullptr;           // bf16 [M, N/2] (GEMM_SWIGLU)
+    void* H = nullptr;           // bf16 [M, N/2] (GEMM_SWIGLU) or [M, N] (GEMM_GELU)
     int64_t ldh = 0;
     int flags = 0;
     int force_bn = 0;   // 0 = auto, 128 or 256

@@ -268,7 +268,8 @@ class MHA(nn.Module):
     # -- generation path: KV cache, one sequence per row -------------------------------------------------------------
     def _forward_decode(self, x, inference_params, indexes=None):
         """x ``[B, S, hidden]`` with a per-layer KV cache in ``inference_params`` (reference ``MHA._forward``
-        inference branch, ``modeling_internlm2.py:245-402``).  Library SDPA: generation is not a training hot path."""
+        inference branch, ``modeling_internlm2.py:245-402``).  Prefill runs the training attention kernel, decode steps the
+        split-KV kernel; masked (left-padded) batches and CPU use library SDPA."""
         B, S, _ = x.shape
         D = self.head_dim
         off = inference_params.sequence_len_offset
@@ -289,6 +290,18 @@ class MHA(nn.Module):
         b0 = inference_params.batch_size_offset
         kc[b0:b0 + B, off:off + S] = k
         vc[b0:b0 + B, off:off + S] = v
+        proj = self.out_proj if self.layout == "internlm" else self.wo
+        if getattr(inference_params, "attention_mask", None) is None and x.is_cuda:
+            if S == 1:      # decode step: split-KV kernel over the cache
+                from internevo_b200.ops.attention import decode_attention
+
+                o = decode_attention(q[:, 0], kc[b0:b0 + B], vc[b0:b0 + B], off + 1, self.softmax_scale)
+                return proj(o.reshape(B, 1, -1))
+            if off == 0:    # prefill: the training attention kernel on B packed sequences of length S
+                cu = torch.arange(0, (B + 1) * S, S, device=x.device, dtype=torch.int32)
+                o = flash_attention_varlen(q.reshape(B * S, -1, D), k.reshape(B * S, -1, D), v.reshape(B * S, -1, D), cu, S,
+                                           causal=True, scale=self.softmax_scale)
+                return proj(o.reshape(B, S, -1))
         kk, vv = kc[b0:b0 + B, : off + S], vc[b0:b0 + B, : off + S]
         mask = None
         if S > 1:
@@ -300,7 +313,6 @@ class MHA(nn.Module):
         o = F.scaled_dot_product_attention(q.transpose(1, 2), kk.transpose(1, 2), vv.transpose(1, 2), attn_mask=mask,
                                            scale=self.softmax_scale, enable_gqa=q.shape[2] != kk.shape[2])
         o = o.transpose(1, 2).reshape(B, S, -1)
-        proj = self.out_proj if self.layout == "internlm" else self.wo
         return proj(o)
 
 
@@ -406,7 +418,11 @@ class GeluMLP(nn.Module):
                        sequence_parallel=sp, device=device, dtype=dtype)
 
     def forward(self, x):
-        return self.fc2(F.gelu(self.fc1(x), approximate="tanh"))
+        fc1 = self.fc1
+        if _ws(getattr(fc1, "process_group", None)) <= 1 and x.is_cuda and x.dtype == torch.bfloat16 and \
+                type(fc1).__name__.startswith("ColumnParallelLinear"):
+            return self.fc2(ops.linear_gelu(x, fc1.weight, fc1.bias))  # GELU in the GEMM epilogue
+        return self.fc2(F.gelu(fc1(x), approximate="tanh"))
 
 
 def _unused():  # keep linters quiet about optional imports used by subclasses

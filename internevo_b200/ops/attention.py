@@ -170,3 +170,31 @@ def flash_attention_varlen(q, k, v, cu_seqlens, max_seqlen: int, causal: bool = 
                                                              enable_gqa=H != Hkv)
         outs.append(o[0].transpose(0, 1))
     return torch.cat(outs, 0)
+
+
+_decode_ws = {}
+
+
+def decode_attention(q: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, seqlen: int,
+                     scale: Optional[float] = None) -> torch.Tensor:
+    """One generation step: ``q [B, H, D]`` attends to the first ``seqlen`` cache positions (``[B, Smax, Hkv, D]``).
+    Native split-KV kernel for bf16 / D = 128, library SDPA otherwise."""
+    B, H, D = q.shape
+    Hkv = kcache.shape[2]
+    scale = scale or 1.0 / math.sqrt(D)
+    if q.is_cuda and q.dtype == torch.bfloat16 and D == 128 and _b200_available():
+        ctas = B * Hkv
+        nsplit = max(1, min(32, (2 * 148 + ctas - 1) // ctas, (seqlen + 63) // 64))
+        key = (q.device, B, H, nsplit)
+        ws = _decode_ws.get(key)
+        if ws is None:
+            ws = (torch.empty(B * H * nsplit * (D + 4), device=q.device, dtype=torch.float32),
+                  torch.zeros(B * Hkv, device=q.device, dtype=torch.int32))
+            _decode_ws[key] = ws
+        out = torch.empty_like(q)
+        torch.ops.b200.attn_decode(q.contiguous(), kcache, vcache, out, ws[0], ws[1], int(seqlen), nsplit, float(scale))
+        _bump()
+        return out
+    kk, vv = kcache[:, :seqlen].transpose(1, 2), vcache[:, :seqlen].transpose(1, 2)
+    o = torch.nn.functional.scaled_dot_product_attention(q[:, :, None], kk, vv, scale=scale, enable_gqa=H != Hkv)
+    return o[:, :, 0]

@@ -17,6 +17,7 @@ GEMM_OUT_F32 = 1
 GEMM_ACCUMULATE = 2
 GEMM_SWIGLU = 4
 GEMM_SKIP_D = 8
+GEMM_GELU = 16
 
 _launches = 0  # counted for bench.py's "gpu_launches"
 
@@ -93,6 +94,55 @@ def matmul_swiglu(x: torch.Tensor, w_gu: torch.Tensor, store_gu: bool = True, fo
     torch.ops.b200.gemm(x, w_gu, d, False, False, None, flags, h, force_bn, 0)
     _bump()
     return (d if store_gu else None), h
+
+
+def matmul_gelu(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None):
+    """``pre = x @ w^T + bias`` and ``gelu_tanh(pre)`` from ONE GEMM (activation applied in the epilogue out of TMEM);
+    returns ``(pre, act)`` — replaces the cuBLASLt GELU epilogue of the reference's fused-dense extension
+    (``csrc/fused_dense_lib`` ``linear_act_forward``)."""
+    if not (_lib.use_native(x, w) and x.dtype == torch.bfloat16):
+        pre = torch.nn.functional.linear(x.float(), w.float(), None if bias is None else bias.float()).to(x.dtype)
+        return pre, torch.nn.functional.gelu(pre.float(), approximate="tanh").to(x.dtype)
+    M, N = x.shape[0], w.shape[0]
+    pre = torch.empty(M, N, device=x.device, dtype=torch.bfloat16)
+    act = torch.empty(M, N, device=x.device, dtype=torch.bfloat16)
+    torch.ops.b200.gemm(x, w, pre, False, False, bias, GEMM_GELU, act, 0, 0)
+    _bump()
+    return pre, act
+
+
+class _LinearGeluFn(torch.autograd.Function):
+    """``gelu(x W^T + b)`` with the pre-activation kept for backward (``bias_act_linear_dgrad_bgrad`` of the reference)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x2 = x.reshape(-1, x.shape[-1])
+        pre, act = matmul_gelu(x2, weight, bias)
+        ctx.save_for_backward(x2, weight, pre)
+        ctx.has_bias, ctx.x_shape = bias is not None, x.shape
+        return act.reshape(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dact):
+        x2, weight, pre = ctx.saved_tensors
+        d2 = dact.reshape(-1, dact.shape[-1]).contiguous()
+        if _lib.use_native(d2, pre):
+            dpre = torch.empty_like(pre)
+            torch.ops.b200.gelu_bwd(d2, pre, dpre)
+            _bump()
+        else:
+            p = pre.float().requires_grad_(True)
+            with torch.enable_grad():
+                a = torch.nn.functional.gelu(p, approximate="tanh")
+            dpre = torch.autograd.grad(a, p, d2.float())[0].to(pre.dtype)
+        dx = matmul(dpre, weight, b_mn=True).reshape(ctx.x_shape) if ctx.needs_input_grad[0] else None
+        dw = wgrad(dpre, x2, weight) if ctx.needs_input_grad[1] else None
+        db = dpre.float().sum(0).to(dpre.dtype) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return dx, dw, db
+
+
+def linear_gelu(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    return _LinearGeluFn.apply(x, weight, bias)
 
 
 class _LinearFn(torch.autograd.Function):

@@ -84,6 +84,25 @@ def check_gemm():
         allok &= err_report(f"swiglu gu bn{bn}", gu, ref, 1e-2)
         g, u = gu[:, 0::2].float(), gu[:, 1::2].float()
         allok &= err_report(f"swiglu h bn{bn}", h, torch.nn.functional.silu(g) * u, 1e-2)
+    # GELU epilogue (+ bias) and its backward kernel
+    pre, act = ops.matmul_gelu(a, b, bias)
+    pre_ref = ref + bias.float()
+    allok &= err_report("gelu pre", pre, pre_ref, 1e-2)
+    allok &= err_report("gelu act", act, torch.nn.functional.gelu(pre.float(), approximate="tanh"), 1e-2)
+    xg = torch.randn(256, 512, device=dev, dtype=torch.bfloat16, requires_grad=True)
+    wg = torch.randn(384, 512, device=dev, dtype=torch.bfloat16, requires_grad=True) * 0.05
+    wg = wg.detach().requires_grad_(True)
+    bg = torch.randn(384, device=dev, dtype=torch.bfloat16, requires_grad=True)
+    yg = ops.linear_gelu(xg, wg, bg)
+    dyg = torch.randn_like(yg)
+    yg.backward(dyg)
+    xf, wf, bf = (t.detach().float().requires_grad_(True) for t in (xg, wg, bg))
+    yf = torch.nn.functional.gelu(xf @ wf.t() + bf, approximate="tanh")
+    yf.backward(dyg.float())
+    allok &= err_report("linear_gelu fwd", yg, yf, 1e-2)
+    allok &= err_report("linear_gelu dx", xg.grad, xf.grad, 2e-2)
+    allok &= err_report("linear_gelu dw", wg.grad, wf.grad, 2e-2)
+    allok &= err_report("linear_gelu db", bg.grad, bf.grad, 2e-2)
     # ragged M for the pair tile (M % 256 == 128) and wgrad-style accumulate into a strided view
     a3 = torch.randn(384 + 128, 320, device=dev, dtype=torch.bfloat16)[:384 + 128 - 0]
     a3 = torch.randn(640, 320, device=dev, dtype=torch.bfloat16)
