@@ -5,7 +5,7 @@ The decode path runs through ``MHA._forward_decode`` (KV cache + library SDPA): 
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple, Union
+from typing import List, Tuple
 
 import torch
 import torch.nn.functional as F
@@ -280,7 +280,3 @@ def _beam_search(gen: SequenceGenerator, tokens, max_length, num_beams, num_retu
         for j, h in enumerate(hs):
             res[b, j, : len(h)] = h
     return res
-
-
-def _unused() -> Optional[Union[int, None]]:
-    return None

@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import os
 from enum import Enum
-from typing import Callable, Dict, Union
+from typing import Dict
 
 import torch
 import torch.distributed as dist
@@ -372,7 +372,3 @@ class CheckpointManager:
             llm_save(p, saved_obj={"ping": 1})
             assert llm_load(p)["ping"] == 1
             get_storage_manager().delete_obj(p)
-
-
-def _unused() -> Union[Callable, None]:
-    return None

@@ -1,11 +1,8 @@
 """Checkpoint helpers (reference ``internlm/checkpoint/utils.py``)."""
 from __future__ import annotations
 
-import itertools
 
-import torch
 
-from internevo_b200.core.context import ParallelMode
 from internevo_b200.core.context import global_context as gpc
 from internevo_b200.utils.logger import get_logger
 
@@ -48,7 +45,3 @@ def try_get_tp_pp_from_fns(fns):
             max_tp = max(max_tp, int(segs[1][2:]))
             max_pp = max(max_pp, int(segs[-1][2:]))
     return max_tp + 1, max_pp + 1
-
-
-def _unused():
-    return itertools, torch, ParallelMode

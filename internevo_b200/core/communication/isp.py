@@ -18,7 +18,6 @@ import torch
 import torch.distributed as dist
 from torch import nn
 
-from internevo_b200.core.context import ParallelMode
 from internevo_b200.core.context import global_context as gpc
 from internevo_b200.utils.common import SchedulerHook
 
@@ -187,7 +186,3 @@ class ISPCommunicatorSchedulerHook(SchedulerHook):
 
     def post_helper_func(self, scheduler, outputs, label) -> None:
         pass
-
-
-def _unused():
-    return ParallelMode

@@ -18,7 +18,6 @@ from internevo_b200.core.context import ParallelMode
 from internevo_b200.core.context import global_context as gpc
 from internevo_b200.core.naive_amp import NaiveAMPModel
 from internevo_b200.utils.common import SchedulerHook, get_current_device, move_to_device
-from internevo_b200.utils.parallel import is_using_isp
 from internevo_b200.utils.timeout import llm_timeout
 
 from .base_scheduler import BaseScheduler
@@ -571,7 +570,3 @@ class InterleavedPipelineScheduler(PipelineScheduler):
         if is_moe:
             return output, label, accum_loss, accum_moe
         return output, label, accum_loss
-
-
-def _unused():
-    return is_using_isp

@@ -266,14 +266,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         }
                     }
                 }
-                const int m0 = (tm * CG + cta_rank) * BM, n0 = tn * BN + n_off + cta_rank * (BN / CG);
+                const int m0 = (tm * CG + cta_rank) * BM, n0 = tn * BN + n_off + cta_rank * (width / CG);
                 const int m0_own = m0 - comm.rank * comm.m_local;
                 // 2-CTA: every CTA loads its rows of A and its half of B, all bytes are counted on the leader's barrier
                 auto ld = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
                     if constexpr (CG == 2) tma_load_2d_2sm(dst, map, bar, c0, c1);
                     else tma_load_2d(dst, map, bar, c0, c1);
                 };
-                const int nb64 = width / 64;  // B arrives in 64-row (K-major) or 64-column (MN-major) boxes
+                const int nb64 = width / CG / 64;  // B arrives in 64-row (K-major) or 64-column (MN-major) boxes
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES * CG + width * (BK * 2));
@@ -299,10 +299,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         }
                     } else if (!args.b_mn) {  // tail slice: 64-row boxes of the K-major operand
                         for (int j = 0; j < nb64; ++j)
-                            tma_load_2d(sb + j * (64 * 128), &tmap_bt, &full_bar[stage], k0, n0 + j * 64);
+                            ld(sb + j * (64 * 128), &tmap_bt, &full_bar[stage], k0, n0 + j * 64);
                     } else {
                         for (int j = 0; j < nb64; ++j)
-                            tma_load_2d(sb + j * (BK * 128), &tmap_b, &full_bar[stage], n0 + j * 64, k0);
+                            ld(sb + j * (BK * 128), &tmap_b, &full_bar[stage], n0 + j * 64, k0);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -324,7 +324,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int tile = unit; tile < num_items; tile += grid_ctas) {
                 const uint32_t idesc = tile < args.tiles_full
                                            ? idesc_full
-                                           : make_idesc_f16(BM, BN / args.tail_split, args.a_mn, args.b_mn);
+                                           : make_idesc_f16(BM * CG, BN / args.tail_split, args.a_mn, args.b_mn);
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -748,12 +748,12 @@ static int launch(const GemmDesc& g, cudaStream_t stream) {
     // tiles, 3.5 wave-times instead of 4).  The partial last n-tile (N % BN != 0) keeps the whole-tile path.
     a.tiles_full = tiles;
     a.tail_split = 1;
-    if (CG == 1 && g_tail_split && tiles > grid && g.N % BN == 0) {
+    if (g_tail_split && tiles > grid && g.N % BN == 0) {
         const int tail = tiles % grid;
         if (tail > 0) {
-            int split = 1;
-            if (tail * 4 <= grid && BN / 4 >= 64) split = 4;
-            else if (tail * 2 <= grid && BN / 2 >= 64) split = 2;
+            int split = 1;  // every CTA of a pair must still stage whole 64-row boxes of B
+            if (tail * 4 <= grid && BN / 4 / CG >= 64) split = 4;
+            else if (tail * 2 <= grid && BN / 2 / CG >= 64) split = 2;
             if (split > 1) { a.tiles_full = tiles - tail; a.tail_split = split; }
         }
     }

@@ -7,7 +7,6 @@ from tqdm import tqdm
 
 from internevo_b200.core.context import ParallelMode
 from internevo_b200.core.context import global_context as gpc
-from internevo_b200.core.scheduler import InterleavedPipelineScheduler, PipelineScheduler
 from internevo_b200.models.metrics import AccPerplex, SchedulerMetricHook
 
 
@@ -111,7 +110,3 @@ def evaluate_on_val_dls(trainer, val_dls, writer, logger, step_count, update_pan
             torch.cuda.empty_cache()
         if gpc.is_distributed:
             torch.distributed.barrier()
-
-
-def _unused():
-    return InterleavedPipelineScheduler, PipelineScheduler

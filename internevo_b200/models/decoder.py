@@ -11,7 +11,6 @@ one GEMM with SwiGLU epilogue + one GEMM; activations are ``[tokens, hidden]``.
 """
 from __future__ import annotations
 
-import math
 from dataclasses import dataclass
 from typing import Optional
 
@@ -424,7 +423,3 @@ def build_generic_model_1d(spec: FamilySpec, num_layers, num_chunks, device=None
     setattr(model, "first_layer", 0)
     setattr(model, "last_layer", num_layers)
     return model
-
-
-def _unused():
-    return math

@@ -3,7 +3,6 @@ pipeline; with ``parallel_output`` the logits are a vocabulary shard and the los
 (max, sum-exp, target) statistics over the tensor group."""
 from __future__ import annotations
 
-import torch
 from torch import nn
 
 from internevo_b200 import ops
@@ -48,7 +47,3 @@ class FlashGPTLMLoss(nn.Module):
             # each sequence shard normalises by its own token count; gradients are averaged over all ranks later
             pass
         return loss
-
-
-def _unused():
-    return torch

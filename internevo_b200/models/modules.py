@@ -12,7 +12,6 @@ Parity targets: ``internlm/model/modules/{embedding,mlp,multi_head_attention}.py
 """
 from __future__ import annotations
 
-import math
 from typing import Optional
 
 import torch
@@ -32,7 +31,7 @@ from internevo_b200.parallel.functional import (
     seq_all_to_all,
     split_forward_gather_backward,
 )
-from internevo_b200.parallel.linear import _ParallelLinearFn, get_linear_cls
+from internevo_b200.parallel.linear import get_linear_cls
 
 
 def _ws(group):
@@ -423,7 +422,3 @@ class GeluMLP(nn.Module):
                 type(fc1).__name__.startswith("ColumnParallelLinear"):
             return self.fc2(ops.linear_gelu(x, fc1.weight, fc1.bias))  # GELU in the GEMM epilogue
         return self.fc2(F.gelu(fc1(x), approximate="tanh"))
-
-
-def _unused():  # keep linters quiet about optional imports used by subclasses
-    return math, _ParallelLinearFn

@@ -15,7 +15,7 @@ from the ``[E, C, h]`` buffer by row index and every expert runs the fused SwiGL
 from __future__ import annotations
 
 import math
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 import torch.distributed as dist
@@ -357,7 +357,3 @@ class MoE(nn.Module):
 
 def is_moe_param(param: torch.Tensor) -> bool:
     return getattr(param, "is_expert", False)
-
-
-def _unused() -> Tuple:
-    return (math,)

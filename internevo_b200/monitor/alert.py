@@ -5,7 +5,6 @@ from __future__ import annotations
 import json
 import math
 import os
-import re
 import time
 from typing import Dict
 
@@ -52,7 +51,3 @@ def send_feishu_msg_with_webhook(webhook: str, title: str, message: str):
         logger.info(f"alert sent, response: {res}")
     except Exception as err:  # pragma: no cover
         logger.error(f"alert send failed: {err}")
-
-
-def _unused():
-    return re

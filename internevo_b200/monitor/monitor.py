@@ -7,7 +7,6 @@ import os
 import signal
 import socket
 import time
-import traceback
 from contextlib import contextmanager
 from threading import Thread
 
@@ -176,7 +175,3 @@ def initialize_monitor_manager(job_name: str = None, alert_address: str = None):
             monitor_manager.stop_monitor()
     else:
         yield
-
-
-def _unused():
-    return traceback

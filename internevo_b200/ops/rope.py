@@ -5,7 +5,6 @@ cos/sin come from fp32 tables indexed by the packed-sequence position ids (``ind
 """
 from __future__ import annotations
 
-import math
 from typing import Optional
 
 import torch

@@ -6,7 +6,6 @@ are validated against these.
 """
 from __future__ import annotations
 
-from typing import Optional
 
 import torch
 import torch.distributed as dist

@@ -16,7 +16,6 @@ with the neighbouring GEMM exactly where the reference overlaps it.
 from __future__ import annotations
 
 import math
-from typing import Optional
 
 import torch
 import torch.distributed as dist
@@ -24,8 +23,6 @@ import torch.nn.functional as F
 from torch import nn
 
 from internevo_b200 import ops
-from internevo_b200.core.context import ParallelMode
-from internevo_b200.core.context import global_context as gpc
 from internevo_b200.ops.gemm import wgrad as _wgrad
 
 from .functional import all_gather_raw, all_reduce_raw, reduce_scatter_raw

@@ -11,7 +11,7 @@ value ``>=`` the epoch of the operation, so flags never need to be cleared betwe
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List
 
 import torch
 import torch.distributed as dist
@@ -110,7 +110,3 @@ def ag_flag_table(flags: SymmFlags) -> int:
 
 def rs_flag_table(flags: SymmFlags) -> int:
     return flags.table_ptr(_RS_BASE)
-
-
-def _unused() -> Tuple[Optional[int]]:
-    return (_BARRIER_SLOTS,)

@@ -2,7 +2,6 @@
 ``internlm/solver/activation_checkpoint.py:40-152``), with optional CPU offload of the saved inputs."""
 from __future__ import annotations
 
-import weakref
 
 import torch
 from torch.utils.checkpoint import check_backward_validity, detach_variable
@@ -112,7 +111,3 @@ def activation_checkpoint(function, activation_offload, *args, use_reentrant: bo
     if use_reentrant:
         return CheckpointFunction.apply(function, activation_offload, *args)
     return torch.utils.checkpoint.checkpoint(function, *args, use_reentrant=False)
-
-
-def _unused():
-    return weakref

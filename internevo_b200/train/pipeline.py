@@ -2,7 +2,6 @@
 profiler (reference ``internlm/train/pipeline.py:157-633``)."""
 from __future__ import annotations
 
-import math
 import time
 from typing import Callable, Iterable, List, Optional, Union
 
@@ -278,7 +277,3 @@ def record_current_batch_training_metrics(get_tflops_func, logger, writer, succe
     mm.monitor_loss_spike(alert_address=alert.get("feishu_alert_address", None), step_count=batch_count,
                           cur_step_loss=loss_v)
     return infos
-
-
-def _unused():
-    return math

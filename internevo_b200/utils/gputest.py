@@ -3,7 +3,6 @@ GEMM/attention micro-benchmark, NVLink all-reduce bench, allocator analysis."""
 from __future__ import annotations
 
 import gc
-import math
 import socket
 
 import torch

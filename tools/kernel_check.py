@@ -163,19 +163,20 @@ def gemm_perf():
         A = a.t() if a_mn else a
         Bt = b if b_mn else b.t()
         row = {"case": name, "M": M, "N": N, "K": K}
-        for bn, split, grp in ((256, 1, 0), (128, 1, 0), (512, 1, 8), (512, 1, 0)):
-            key = {256: "ours_bn256", 128: "ours_bn128", 512: "ours_2cta"}[bn] + ("_group8" if grp else "") + "_tflops"
-            torch.ops.b200.set_gemm_tail_split(split)
-            torch.ops.b200.set_gemm_group_m(grp)
-            try:
-                ms = timeit(lambda: ops.matmul(a, b, a_mn=a_mn, b_mn=b_mn, out=out, force_bn=bn), flush=flush)
-                row[key] = round(2 * M * N * K / ms / 1e9, 1)
-            except Exception as e:  # noqa
-                row[key] = f"ERR {e}"
+        # variants are measured round-robin (3 rounds) so that clock / power drift hits all of them alike
+        variants = {"ours_2cta": (512, 1), "ours_2cta_nosplit": (512, 0), "ours_bn256": (256, 1), "ours_bn128": (128, 1)}
+        acc = {k: [] for k in list(variants) + ["cublas"]}
+        for _ in range(3):
+            for key, (bn, split) in variants.items():
+                torch.ops.b200.set_gemm_tail_split(split)
+                try:
+                    acc[key].append(timeit(lambda: ops.matmul(a, b, a_mn=a_mn, b_mn=b_mn, out=out, force_bn=bn), flush=flush))
+                except Exception as e:  # noqa
+                    acc[key].append(float("nan"))
+            acc["cublas"].append(timeit(lambda: torch.matmul(A, Bt, out=out), flush=flush))
         torch.ops.b200.set_gemm_tail_split(1)
-        torch.ops.b200.set_gemm_group_m(0)
-        ms = timeit(lambda: torch.matmul(A, Bt, out=out), flush=flush)
-        row["cublas_tflops"] = round(2 * M * N * K / ms / 1e9, 1)
+        for key, ms in acc.items():
+            row[f"{key}_tflops"] = round(2 * M * N * K / (sum(ms) / len(ms)) / 1e9, 1)
         print(json.dumps(row), flush=True)
         res.append(row)
     os.makedirs("gpurun_out", exist_ok=True)
