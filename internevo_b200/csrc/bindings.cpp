@@ -35,7 +35,9 @@ void gemm(const Tensor& a, const Tensor& b, Tensor& out, bool a_mn, bool b_mn, c
     const int64_t kb = b_mn ? b.size(0) : b.size(1);
     TORCH_CHECK(kb == g.K, "gemm: K mismatch ", kb, " vs ", g.K);
     TORCH_CHECK(out.size(0) == g.M && out.size(1) == g.N, "gemm: bad output shape");
-    TORCH_CHECK(g.N % 8 == 0 && g.K % 8 == 0, "gemm: N and K must be multiples of 8");
+    // K is the contiguous dimension of a K-major operand (16-byte rows for TMA); with both operands MN-major (wgrad:
+    // dy^T @ x over a ragged token count) K is the outer TMA dimension and the last k-block is zero-filled by TMA.
+    TORCH_CHECK(g.N % 8 == 0 && (g.K % 8 == 0 || (a_mn && b_mn)), "gemm: N (and K for K-major operands) must be multiples of 8");
     TORCH_CHECK(a.stride(0) % 8 == 0 && b.stride(0) % 8 == 0, "gemm: row strides must be multiples of 8 elements");
     TORCH_CHECK((reinterpret_cast<uintptr_t>(a.data_ptr()) & 15) == 0 && (reinterpret_cast<uintptr_t>(b.data_ptr()) & 15) == 0,
                 "gemm: operands must be 16-byte aligned");
@@ -94,6 +96,42 @@ void rmsnorm_bwd(const Tensor& dy, const Tensor& res, const Tensor& w, const Ten
                                dx.data_ptr(), dw_partial.data_ptr<float>(), f32 ? dw.data_ptr<float>() : nullptr,
                                f32 ? nullptr : dw.data_ptr(), accumulate, rows, H, cur_stream()),
              "b200::rmsnorm_bwd");
+}
+
+void layernorm_fwd(const Tensor& x, const optional<Tensor>& res_in, const optional<Tensor>& keep, double drop_scale,
+                   const Tensor& w, const optional<Tensor>& b, Tensor& y, const optional<Tensor>& res_out, Tensor& mean,
+                   Tensor& rstd, double eps) {
+    CHECK_BF16(x); CHECK_BF16(w); CHECK_BF16(y);
+    TORCH_CHECK(x.is_contiguous() && y.is_contiguous() && w.is_contiguous(), "layernorm: contiguous tensors required");
+    if (keep.has_value())
+        TORCH_CHECK(keep->scalar_type() == at::kByte && keep->is_contiguous() && keep->numel() == x.numel(),
+                    "layernorm: keep mask must be uint8 of x's shape");
+    c10::cuda::CUDAGuard guard(x.device());
+    const int H = x.size(-1);
+    const int rows = x.numel() / H;
+    CHECK_RC(b200::layernorm_fwd(x.data_ptr(), optptr(res_in), keep.has_value() ? keep->data_ptr<uint8_t>() : nullptr,
+                                 (float)drop_scale, w.data_ptr(), optptr(b), y.data_ptr(),
+                                 res_out.has_value() ? res_out->data_ptr() : nullptr, mean.data_ptr<float>(),
+                                 rstd.data_ptr<float>(), rows, H, (float)eps, cur_stream()),
+             "b200::layernorm_fwd");
+}
+
+int64_t layernorm_bwd_blocks(int64_t rows) { return b200::layernorm_bwd_blocks((int)rows); }
+
+void layernorm_bwd(const Tensor& dy, const Tensor& res, const Tensor& w, const Tensor& mean, const Tensor& rstd,
+                   const optional<Tensor>& dres, Tensor& dx, Tensor& partial, Tensor& dwdb) {
+    CHECK_BF16(dy); CHECK_BF16(res); CHECK_BF16(w); CHECK_BF16(dx);
+    TORCH_CHECK(dy.is_contiguous() && res.is_contiguous() && dx.is_contiguous(), "layernorm_bwd: contiguous required");
+    c10::cuda::CUDAGuard guard(dy.device());
+    const int H = dy.size(-1);
+    const int rows = dy.numel() / H;
+    TORCH_CHECK(partial.numel() >= (int64_t)b200::layernorm_bwd_blocks(rows) * 2 * H && dwdb.numel() == 2 * H &&
+                    partial.scalar_type() == at::kFloat && dwdb.scalar_type() == at::kFloat,
+                "layernorm_bwd: bad partial / dwdb buffers");
+    CHECK_RC(b200::layernorm_bwd(dy.data_ptr(), res.data_ptr(), w.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(),
+                                 optptr(dres), dx.data_ptr(), partial.data_ptr<float>(), dwdb.data_ptr<float>(), rows, H,
+                                 cur_stream()),
+             "b200::layernorm_bwd");
 }
 
 // x: [T, heads, D] view with contiguous (heads, D) and token stride x.stride(0)
@@ -286,6 +324,26 @@ void reduce_scatter_adam(int64_t grad_ptrs, int64_t param_ptrs, int64_t flags_pt
     CHECK_RC(b200::reduce_scatter_adam(d, cur_stream()), "b200::reduce_scatter_adam");
 }
 
+// NVLS form of the two ZeRO phases: `grad_mc` / `param_mc` are the NVSwitch multicast addresses of the gradient / parameter
+// arenas, `grad_local` this rank's own mapping of the gradient arena.
+void reduce_scatter_adam_mc(int64_t grad_mc, int64_t param_mc, int64_t grad_local, int64_t world, int64_t shard_off,
+                            int64_t shard_n, Tensor& p, Tensor& m, Tensor& v, const Tensor& scalars, double lr, double beta1,
+                            double beta2, double eps, double wd, double bc1, double bc2, double grad_div, int64_t phase) {
+    c10::cuda::CUDAGuard guard(p.device());
+    TORCH_CHECK(grad_mc != 0 && param_mc != 0 && grad_local != 0, "reduce_scatter_adam_mc: null multicast mapping");
+    b200::RsAdamDesc d;
+    d.grad_mc = reinterpret_cast<const void*>(grad_mc);
+    d.param_mc = reinterpret_cast<void*>(param_mc);
+    d.grad_local = reinterpret_cast<void*>(grad_local);
+    d.world = world;
+    d.shard_off = shard_off; d.shard_n = shard_n;
+    d.p = p.data_ptr<float>(); d.m = m.data_ptr<float>(); d.v = v.data_ptr<float>();
+    d.scalars = scalars.data_ptr<float>();
+    d.lr = lr; d.beta1 = beta1; d.beta2 = beta2; d.eps = eps; d.wd = wd; d.bc1 = bc1; d.bc2 = bc2; d.grad_div = grad_div;
+    d.phase = phase;
+    CHECK_RC(b200::reduce_scatter_adam(d, cur_stream()), "b200::reduce_scatter_adam_mc");
+}
+
 // reduce_scatter(a @ b^T) over rows (mode 0: `out` is this rank's [M/world, N]) or all-reduce (mode 1: `out` is the
 // [M, N] symmetric output, out_ptrs its per-rank pointer table).  stage_ptrs: per-rank symmetric staging
 // [world, M/world, N] that the peers' epilogues push their partial tiles into.
@@ -339,12 +397,73 @@ void ag_gemm(const Tensor& x_local, int64_t gathered_ptrs, int64_t flags_ptrs, i
 
 }  // namespace
 
+// ---- MoE dispatch / combine over peer memory
+void symm_allgather_small(int64_t buf_ptrs, const Tensor& src, int64_t flags_ptrs, int64_t rank, int64_t world, int64_t epoch) {
+    c10::cuda::CUDAGuard guard(src.device());
+    TORCH_CHECK(src.is_cuda() && src.is_contiguous() && src.element_size() == 4, "symm_allgather_small: 32-bit contiguous src");
+    CHECK_RC(b200::symm_allgather_small(reinterpret_cast<uint32_t* const*>(buf_ptrs),
+                                        reinterpret_cast<const uint32_t*>(src.data_ptr()), (int)src.numel(),
+                                        reinterpret_cast<uint32_t* const*>(flags_ptrs), rank, world, (uint32_t)epoch,
+                                        cur_stream()),
+             "b200::symm_allgather_small");
+}
+
+static void check_slots(const Tensor& slot_rank, const Tensor& slot_row, const c10::optional<Tensor>& scale, const char* who) {
+    TORCH_CHECK(slot_rank.scalar_type() == at::kInt && slot_row.scalar_type() == at::kInt && slot_rank.is_contiguous() &&
+                    slot_row.is_contiguous() && slot_rank.numel() == slot_row.numel(),
+                who, ": slot_rank / slot_row must be contiguous int32 of equal length");
+    if (scale.has_value())
+        TORCH_CHECK(scale->scalar_type() == at::kFloat && scale->is_contiguous() && scale->numel() == slot_row.numel(), who,
+                    ": scale must be contiguous fp32 [n_slots]");
+}
+
+void moe_scatter_rows(const Tensor& x, const Tensor& slot_rank, const Tensor& slot_row, const c10::optional<Tensor>& scale,
+                      int64_t x_ptrs, int64_t y_ptrs, c10::optional<Tensor> dw, int64_t k) {
+    c10::cuda::CUDAGuard guard(x.device());
+    TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && x.dim() == 2 && x.stride(1) == 1, "moe_scatter_rows: x bf16 [T, H]");
+    check_slots(slot_rank, slot_row, scale, "moe_scatter_rows");
+    TORCH_CHECK(slot_row.numel() == x.size(0) * k, "moe_scatter_rows: n_slots != T * k");
+    TORCH_CHECK(x_ptrs != 0, "moe_scatter_rows: null destination table");
+    b200::MoeCommDesc d;
+    d.x = x.data_ptr(); d.ldx = x.stride(0);
+    d.slot_rank = slot_rank.data_ptr<int>(); d.slot_row = slot_row.data_ptr<int>();
+    d.scale = scale.has_value() ? scale->data_ptr<float>() : nullptr;
+    d.x_ptrs = reinterpret_cast<void* const*>(x_ptrs);
+    d.y_ptrs = reinterpret_cast<void* const*>(y_ptrs);
+    if (dw.has_value()) {
+        TORCH_CHECK(dw->scalar_type() == at::kFloat && dw->is_contiguous() && dw->numel() == slot_row.numel() && y_ptrs != 0,
+                    "moe_scatter_rows: dw fp32 [n_slots] needs y_ptrs");
+        d.dw = dw->data_ptr<float>();
+    }
+    d.n_slots = (int)slot_row.numel(); d.k = (int)k; d.H = (int)x.size(1);
+    CHECK_RC(b200::moe_scatter_rows(d, cur_stream()), "b200::moe_scatter_rows");
+}
+
+void moe_gather_combine(Tensor& out, const c10::optional<Tensor>& w, const Tensor& slot_rank, const Tensor& slot_row,
+                        int64_t y_ptrs, int64_t k) {
+    c10::cuda::CUDAGuard guard(out.device());
+    TORCH_CHECK(out.is_cuda() && out.scalar_type() == at::kBFloat16 && out.dim() == 2 && out.stride(1) == 1,
+                "moe_gather_combine: out bf16 [T, H]");
+    check_slots(slot_rank, slot_row, w, "moe_gather_combine");
+    TORCH_CHECK(slot_row.numel() == out.size(0) * k && y_ptrs != 0, "moe_gather_combine: n_slots != T * k or null table");
+    b200::MoeCommDesc d;
+    d.out = out.data_ptr(); d.ldo = out.stride(0);
+    d.slot_rank = slot_rank.data_ptr<int>(); d.slot_row = slot_row.data_ptr<int>();
+    d.scale = w.has_value() ? w->data_ptr<float>() : nullptr;
+    d.y_ptrs = reinterpret_cast<void* const*>(y_ptrs);
+    d.n_slots = (int)slot_row.numel(); d.k = (int)k; d.H = (int)out.size(1);
+    CHECK_RC(b200::moe_gather_combine(d, cur_stream()), "b200::moe_gather_combine");
+}
+
 TORCH_LIBRARY(b200, m) {
     m.def("gemm(Tensor a, Tensor b, Tensor(a!) out, bool a_mn, bool b_mn, Tensor? bias, int flags, Tensor? h, int force_bn, int max_ctas) -> ()", &gemm);
     m.def("set_gemm_tail_split(int on) -> ()", [](int64_t on) { b200::set_gemm_tail_split(static_cast<int>(on)); });
     m.def("set_gemm_group_m(int g) -> ()", [](int64_t g) { b200::set_gemm_group_m(static_cast<int>(g)); });
     m.def("rmsnorm_fwd(Tensor x, Tensor? res_in, Tensor w, Tensor(a!) y, Tensor? res_out, Tensor? rstd, float eps) -> ()", &rmsnorm_fwd);
     m.def("rmsnorm_bwd_blocks(int rows) -> int", &rmsnorm_bwd_blocks);
+    m.def("layernorm_fwd(Tensor x, Tensor? res_in, Tensor? keep, float drop_scale, Tensor w, Tensor? b, Tensor(a!) y, Tensor? res_out, Tensor(b!) mean, Tensor(c!) rstd, float eps) -> ()", &layernorm_fwd);
+    m.def("layernorm_bwd_blocks(int rows) -> int", &layernorm_bwd_blocks);
+    m.def("layernorm_bwd(Tensor dy, Tensor res, Tensor w, Tensor mean, Tensor rstd, Tensor? dres, Tensor(a!) dx, Tensor(b!) partial, Tensor(c!) dwdb) -> ()", &layernorm_bwd);
     m.def("rmsnorm_bwd(Tensor dy, Tensor res, Tensor w, Tensor rstd, Tensor? dres, Tensor(a!) dx, Tensor(b!) dw_partial, Tensor(c!) dw, bool accumulate) -> ()", &rmsnorm_bwd);
     m.def("rope(Tensor(a!) x, Tensor? pos, Tensor cos_t, Tensor sin_t, int group, int rot_per_group, bool conj, bool interleaved) -> ()", &rope);
     m.def("swiglu_fwd(Tensor gu, Tensor(a!) h) -> ()", &swiglu_fwd);
@@ -360,6 +479,10 @@ TORCH_LIBRARY(b200, m) {
     m.def("attn_bwd(Tensor dout, Tensor q, Tensor k, Tensor v, Tensor out, Tensor lse, Tensor(a!) dq, Tensor(b!) dk, Tensor(c!) dv, Tensor(d!) delta, Tensor(e!) dq_acc, Tensor cu_seqlens, int max_seqlen, float scale, bool causal) -> ()", &attn_bwd);
     m.def("symm_barrier(int flags_ptrs, int rank, int world, int epoch) -> ()", &symm_barrier);
     m.def("reduce_scatter_adam(int grad_ptrs, int param_ptrs, int flags_ptrs, int rank, int world, int epoch, int shard_off, int shard_n, Tensor(a!) p, Tensor(b!) m, Tensor(c!) v, Tensor scalars, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2, float grad_div, int phase) -> ()", &reduce_scatter_adam);
+    m.def("reduce_scatter_adam_mc(int grad_mc, int param_mc, int grad_local, int world, int shard_off, int shard_n, Tensor(a!) p, Tensor(b!) m, Tensor(c!) v, Tensor scalars, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2, float grad_div, int phase) -> ()", &reduce_scatter_adam_mc);
+    m.def("symm_allgather_small(int buf_ptrs, Tensor src, int flags_ptrs, int rank, int world, int epoch) -> ()", &symm_allgather_small);
+    m.def("moe_scatter_rows(Tensor x, Tensor slot_rank, Tensor slot_row, Tensor? scale, int x_ptrs, int y_ptrs, Tensor(a!)? dw, int k) -> ()", &moe_scatter_rows);
+    m.def("moe_gather_combine(Tensor(a!) out, Tensor? w, Tensor slot_rank, Tensor slot_row, int y_ptrs, int k) -> ()", &moe_gather_combine);
     m.def("gemm_rs(Tensor a, Tensor b, Tensor(a!) out, int stage_ptrs, int out_ptrs, int flags_ptrs, int rank, int world, int epoch, bool b_mn, int mode) -> ()", &gemm_rs);
     m.def("ag_gemm(Tensor x_local, int gathered_ptrs, int flags_ptrs, int rank, int world, int epoch, Tensor b, bool b_mn, Tensor(a!) gathered, Tensor(b!) out, int flags, Tensor? h, int comm_ctas) -> ()", &ag_gemm);
 }

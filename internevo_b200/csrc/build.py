@@ -19,7 +19,7 @@ PKG = os.path.dirname(HERE)
 BUILD_DIR = os.path.join(HERE, "build")
 SO_PATH = os.path.join(PKG, "_C.so")
 
-CU_SOURCES = ["gemm_sm100.cu", "elementwise.cu", "attention_sm100.cu", "comm_kernels.cu"]
+CU_SOURCES = ["gemm_sm100.cu", "elementwise.cu", "attention_sm100.cu", "comm_kernels.cu", "moe_comm.cu", "layernorm.cu"]
 CPP_SOURCES = ["bindings.cpp"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

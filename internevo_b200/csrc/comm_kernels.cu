@@ -142,11 +142,111 @@ __global__ void __launch_bounds__(256) adamw_bcast_kernel(float* __restrict__ p,
     }
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// NVLS variants: the arenas are also mapped through an NVSwitch MULTICAST address.  `multimem.ld_reduce` makes the
+// switch fetch the same 16 bytes from every GPU and add them (fp32 accumulation) on the way back: the owner reads its
+// slice ONCE instead of once per peer.  `multimem.st` makes the switch replicate one store into every GPU's arena: the
+// owner writes its updated parameters ONCE instead of once per peer.  Link traffic per GPU drops from (W-1)/W * arena to
+// 1/W * arena in both phases.
+// ----------------------------------------------------------------------------------------------------------------
+B200_DEVICE uint4 multimem_ld_reduce_bf16x8(const void* mc) {
+    uint4 r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(mc)
+                 : "memory");
+    return r;
+}
+B200_DEVICE void multimem_st_v4(void* mc, uint4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(__uint_as_float(v.x)),
+                 "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(256) rs_reduce_mc_kernel(const void* grad_mc, void* grad_local, int64_t shard_off,
+                                                           int64_t shard_n, float inv_div, float* scalars) {
+    __shared__ float red[32];
+    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(grad_mc) + shard_off;
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(grad_local) + shard_off;
+    const int64_t nvec = shard_n / 8;
+    float ss = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 v = multimem_ld_reduce_bf16x8(src + i * 8);
+        float2 a = unpack_bf16(v.x), b = unpack_bf16(v.y), c = unpack_bf16(v.z), d = unpack_bf16(v.w);
+        uint4 o;
+        o.x = pack_bf16(a.x * inv_div, a.y * inv_div);
+        o.y = pack_bf16(b.x * inv_div, b.y * inv_div);
+        o.z = pack_bf16(c.x * inv_div, c.y * inv_div);
+        o.w = pack_bf16(d.x * inv_div, d.y * inv_div);
+        *reinterpret_cast<uint4*>(dst + i * 8) = o;
+        a = unpack_bf16(o.x); b = unpack_bf16(o.y); c = unpack_bf16(o.z); d = unpack_bf16(o.w);
+        ss += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) atomicAdd(scalars + 3, t);
+    }
+}
+
+__global__ void __launch_bounds__(256) adamw_bcast_mc_kernel(float* __restrict__ p, float* __restrict__ m,
+                                                             float* __restrict__ v, const void* grad_local,
+                                                             void* param_mc, int64_t shard_off, int64_t n, float lr,
+                                                             float beta1, float beta2, float eps, float wd, float bc1,
+                                                             float bc2, const float* scalars) {
+    const float mult = scalars[0];
+    if (scalars[1] != 0.f) return;
+    const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(grad_local) + shard_off;
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(param_mc) + shard_off;
+    const int64_t n8 = n / 8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        float pv[8], mv[8], vv[8], gv[8];
+        *reinterpret_cast<float4*>(pv) = reinterpret_cast<float4*>(p)[2 * i];
+        *reinterpret_cast<float4*>(pv + 4) = reinterpret_cast<float4*>(p)[2 * i + 1];
+        *reinterpret_cast<float4*>(mv) = reinterpret_cast<float4*>(m)[2 * i];
+        *reinterpret_cast<float4*>(mv + 4) = reinterpret_cast<float4*>(m)[2 * i + 1];
+        *reinterpret_cast<float4*>(vv) = reinterpret_cast<float4*>(v)[2 * i];
+        *reinterpret_cast<float4*>(vv + 4) = reinterpret_cast<float4*>(v)[2 * i + 1];
+        const uint4 gu = reinterpret_cast<const uint4*>(g)[i];
+        float2 g0 = unpack_bf16(gu.x), g1 = unpack_bf16(gu.y), g2 = unpack_bf16(gu.z), g3 = unpack_bf16(gu.w);
+        gv[0] = g0.x; gv[1] = g0.y; gv[2] = g1.x; gv[3] = g1.y; gv[4] = g2.x; gv[5] = g2.y; gv[6] = g3.x; gv[7] = g3.y;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float gg = gv[j] * mult;
+            mv[j] = beta1 * mv[j] + (1.f - beta1) * gg;
+            vv[j] = beta2 * vv[j] + (1.f - beta2) * gg * gg;
+            pv[j] = pv[j] * (1.f - lr * wd) - lr * (mv[j] / bc1) / (sqrtf(vv[j] / bc2) + eps);
+        }
+        reinterpret_cast<float4*>(p)[2 * i] = *reinterpret_cast<float4*>(pv);
+        reinterpret_cast<float4*>(p)[2 * i + 1] = *reinterpret_cast<float4*>(pv + 4);
+        reinterpret_cast<float4*>(m)[2 * i] = *reinterpret_cast<float4*>(mv);
+        reinterpret_cast<float4*>(m)[2 * i + 1] = *reinterpret_cast<float4*>(mv + 4);
+        reinterpret_cast<float4*>(v)[2 * i] = *reinterpret_cast<float4*>(vv);
+        reinterpret_cast<float4*>(v)[2 * i + 1] = *reinterpret_cast<float4*>(vv + 4);
+        uint4 o;
+        o.x = pack_bf16(pv[0], pv[1]); o.y = pack_bf16(pv[2], pv[3]);
+        o.z = pack_bf16(pv[4], pv[5]); o.w = pack_bf16(pv[6], pv[7]);
+        multimem_st_v4(dst + i * 8, o);
+    }
+}
+
 template <int W>
 static int launch_zero(const RsAdamDesc& d, cudaStream_t s) {
     const int64_t want = (d.shard_n / 8 + 255) / 256;
     const int blocks = (int)(want < 148 * 4 ? (want > 0 ? want : 1) : 148 * 4);
-    if (d.phase == 0) {
+    if (d.phase == 0 && d.grad_mc != nullptr) {
+        rs_reduce_mc_kernel<<<blocks, 256, 0, s>>>(d.grad_mc, d.grad_local, d.shard_off, d.shard_n, (float)(1.0 / d.grad_div),
+                                                   d.scalars);
+    } else if (d.phase == 1 && d.param_mc != nullptr) {
+        adamw_bcast_mc_kernel<<<blocks, 256, 0, s>>>(d.p, d.m, d.v, d.grad_local, d.param_mc, d.shard_off, d.shard_n,
+                                                     (float)d.lr, (float)d.beta1, (float)d.beta2, (float)d.eps, (float)d.wd,
+                                                     (float)d.bc1, (float)d.bc2, d.scalars);
+    } else if (d.phase == 0) {
         rs_reduce_kernel<W><<<blocks, 256, 0, s>>>(d.grad_ptrs, d.rank, d.shard_off, d.shard_n, (float)(1.0 / d.grad_div),
                                                    d.scalars);
     } else {

@@ -15,6 +15,10 @@ struct RsAdamDesc {
     void* const* grad_ptrs = nullptr;    // per-rank bf16 gradient arena (same layout on every rank)
     void* const* param_ptrs = nullptr;   // per-rank bf16 parameter arena
     uint32_t* const* flags_ptrs = nullptr;
+    // optional NVSwitch multicast mappings of the same arenas (nullptr -> unicast peer loads / stores) + local pointers
+    const void* grad_mc = nullptr;
+    void* param_mc = nullptr;
+    void* grad_local = nullptr;
     int rank = 0, world = 1;
     uint32_t epoch = 0;
     int64_t shard_off = 0, shard_n = 0;  // this rank's owned slice [shard_off, shard_off + shard_n) of the arena
@@ -41,5 +45,26 @@ struct GemmCommDesc {
 };
 int gemm_reduce_scatter(const GemmCommDesc& d, cudaStream_t s);
 int allgather_gemm(const GemmCommDesc& d, cudaStream_t s);
+
+// ---- MoE expert-parallel dispatch / combine over peer memory (moe_comm.cu)
+// all ranks push `nwords` words into slot `rank` of every peer's table and rendezvous (one launch)
+int symm_allgather_small(uint32_t* const* buf_ptrs, const uint32_t* src, int nwords, uint32_t* const* flags_ptrs, int rank,
+                         int world, uint32_t epoch, cudaStream_t s);
+
+struct MoeCommDesc {
+    const void* x = nullptr;     // scatter: local bf16 rows [n_slots / k, H] (row of slot s is s / k)
+    int64_t ldx = 0;
+    void* out = nullptr;         // combine: local bf16 output [n_slots / k, H]
+    int64_t ldo = 0;
+    const int* slot_rank = nullptr;  // [n_slots] owner GPU of the slot's expert row
+    const int* slot_row = nullptr;   // [n_slots] row inside the owner's slab (< 0: dropped slot)
+    const float* scale = nullptr;    // [n_slots] optional per-slot weight
+    void* const* x_ptrs = nullptr;   // scatter destination: per-rank bf16 [rows, H] symmetric slabs
+    void* const* y_ptrs = nullptr;   // combine source (and, for scatter, rows to dot with for d(gate weight))
+    float* dw = nullptr;             // scatter: optional [n_slots] <x[t], y_row>
+    int n_slots = 0, k = 1, H = 0;
+};
+int moe_scatter_rows(const MoeCommDesc& d, cudaStream_t s);
+int moe_gather_combine(const MoeCommDesc& d, cudaStream_t s);
 
 }  // namespace b200

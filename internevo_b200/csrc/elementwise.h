@@ -11,6 +11,13 @@ int rmsnorm_bwd_blocks(int rows);
 int rmsnorm_bwd(const void* dy, const void* res, const void* w, const float* rstd, const void* dres, void* dx,
                 float* dw_partial, float* dw_f32, void* dw_bf16, int accumulate, int rows, int H, cudaStream_t s);
 
+// fused dropout + residual-add + LayerNorm (layernorm.cu); partial: [layernorm_bwd_blocks(rows), 2H] fp32, dwdb: [2H] fp32
+int layernorm_bwd_blocks(int rows);
+int layernorm_fwd(const void* x, const void* res_in, const uint8_t* keep, float drop_scale, const void* w, const void* b,
+                  void* y, void* res_out, float* mean, float* rstd, int rows, int H, float eps, cudaStream_t s);
+int layernorm_bwd(const void* dy, const void* res, const void* w, const float* mean, const float* rstd, const void* dres,
+                  void* dx, float* partial, float* dwdb, int rows, int H, cudaStream_t s);
+
 int rope_inplace(void* x, const int* pos, const float* cos_t, const float* sin_t, int T, int heads, int D,
                  int64_t stride_t, int group, int rot_per_group, int conj, int interleaved, cudaStream_t s);
 

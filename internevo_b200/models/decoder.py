@@ -74,18 +74,11 @@ def _linear_group():
     return gpc.get_group(ParallelMode.WEIGHT if _is_isp() else ParallelMode.TENSOR)
 
 
-class _LayerNormCompat(nn.LayerNorm):
-    def forward(self, x, residual=None):
-        if residual is None:
-            return super().forward(x)
-        new_res = x + residual
-        return super().forward(new_res), new_res
-
-
 def _make_norm(norm_type, hidden_size, eps, device, dtype):
     if norm_type == "rmsnorm":
         return ops.RMSNorm(hidden_size, eps=eps, device=device, dtype=dtype)
-    return _LayerNormCompat(hidden_size, eps=eps, device=device, dtype=dtype)
+    # fused (dropout +) residual-add + LayerNorm kernel (csrc/layernorm.cu); plain PyTorch on CPU / fp32
+    return ops.LayerNorm(hidden_size, eps=eps, device=device, dtype=dtype)
 
 
 class DecoderLayer(nn.Module):

@@ -15,6 +15,7 @@ from the ``[E, C, h]`` buffer by row index and every expert runs the fused SwiGL
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -256,6 +257,19 @@ class DroplessMOELayer(nn.Module):
         self.noisy_gate_policy = noisy_gate_policy
         self.l_aux, self.exp_counts = None, None
 
+    def _fused_backend(self, x2: torch.Tensor, n_slots: int):
+        """Peer-memory dispatch / combine when the expert group spans 2 / 4 / 8 NVLink-connected GPUs (``B200_MOE_FUSED=0``
+        forces the NCCL all-to-all path, which stays as fall-back and numerical oracle)."""
+        if self.ep_size <= 1 or not x2.is_cuda or x2.dtype is not torch.bfloat16 or x2.shape[1] % 8 != 0:
+            return None
+        if os.environ.get("B200_MOE_FUSED", "1") == "0":
+            return None
+        from internevo_b200.parallel.moe_fused import backend_for
+
+        # worst case: every slot of every rank lands on one GPU; B200_MOE_CAPACITY < 1 trades memory for an overflow check
+        max_rows = max(1, int(n_slots * self.ep_size * float(os.environ.get("B200_MOE_CAPACITY", "1.0"))))
+        return backend_for(self.ep_group, x2.shape[1], max_rows, self.num_experts)
+
     def forward(self, x: torch.Tensor):
         shape = x.shape
         h = shape[-1]
@@ -276,6 +290,18 @@ class DroplessMOELayer(nn.Module):
         order = torch.argsort(flat_e, stable=True)
         tok = torch.arange(S, device=x2.device).repeat_interleave(k)[order]
         counts = torch.bincount(flat_e, minlength=E)
+        be = self._fused_backend(x2, S * k)
+        if be is not None:
+            # dispatch / combine as ONE kernel each over NVLink peer memory (parallel/moe_fused.py, csrc/moe_comm.cu)
+            from internevo_b200.parallel.moe_fused import fused_combine, fused_dispatch
+
+            rows, per_expert, plan = fused_dispatch(x2, flat_e, counts, be, k)
+            outs, start = [], 0
+            for e, n in enumerate(per_expert):
+                outs.append(self.experts.wrapped_experts[e](rows[start:start + n]) if n > 0 else rows[start:start])
+                start += n
+            out = torch.cat(outs, 0) if outs else rows
+            return fused_combine(out, w.reshape(-1), be, plan).reshape(shape)
         send = x2[tok]
         if self.ep_size > 1:
             recv_counts = torch.empty_like(counts)

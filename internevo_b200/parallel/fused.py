@@ -13,6 +13,7 @@ NCCL implementations of the same operations stay available as fall-back and nume
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -146,8 +147,15 @@ class ZeroFusedBackend:
                 p.data = g.param_arena[o: o + p.numel()].view(p.shape)
                 p.grad_buf = g.grad_arena[o: o + p.numel()].view(p.shape)
             self.groups[g.gid] = (pbuf, gbuf, symm.flags_for(group))
+        # NVLS variant: reduce in the switch (multimem.ld_reduce) and broadcast by one multicast store (multimem.st).  Opt-in:
+        # a reduce-SCATTER / all-GATHER moves (W-1)/W of the arena over every GPU's links either way (only an all-reduce
+        # halves its traffic in the switch), and measured at 2 GPUs it is slower than the unicast kernels (0.212 vs 0.114 ms
+        # per 64 Mi elements, profiles/fused_comm_check_n2_r1_v3.json), so peer loads / stores stay the default.
+        self.use_mc = os.environ.get("B200_ZERO_NVLS", "0") == "1" and bool(self.groups) and all(
+            pb.mc_ptr and gb.mc_ptr for pb, gb, _ in self.groups.values())
         if gpc.is_rank_for_log():
-            logger.info(f"fused Hybrid-ZeRO over peer memory enabled for groups {[opt.groups[i].name for i in self.groups]}")
+            logger.info(f"fused Hybrid-ZeRO over peer memory enabled for groups {[opt.groups[i].name for i in self.groups]}"
+                        f" (NVLS multicast: {self.use_mc})")
 
     @staticmethod
     def try_create(opt):
@@ -173,9 +181,15 @@ class ZeroFusedBackend:
                 pbuf, gbuf, flags = self.groups[g.gid]
                 flags.barrier()  # every rank's backward has written its gradient arena
                 g.scalars.zero_()
-                torch.ops.b200.reduce_scatter_adam(gbuf.table_ptr(0), pbuf.table_ptr(0), flags.table_ptr(0), g.zero_rank,
-                                                   g.zero_size, 0, g.lo, g.shard, g.master, g.exp_avg, g.exp_avg_sq,
-                                                   g.scalars, 0.0, 0.9, 0.95, 1e-8, 0.0, 1.0, 1.0, float(g.zero_size), 0)
+                if self.use_mc:
+                    torch.ops.b200.reduce_scatter_adam_mc(gbuf.mc_ptr, pbuf.mc_ptr, gbuf.tensor.data_ptr(), g.zero_size,
+                                                          g.lo, g.shard, g.master, g.exp_avg, g.exp_avg_sq, g.scalars,
+                                                          0.0, 0.9, 0.95, 1e-8, 0.0, 1.0, 1.0, float(g.zero_size), 0)
+                else:
+                    torch.ops.b200.reduce_scatter_adam(gbuf.table_ptr(0), pbuf.table_ptr(0), flags.table_ptr(0),
+                                                       g.zero_rank, g.zero_size, 0, g.lo, g.shard, g.master, g.exp_avg,
+                                                       g.exp_avg_sq, g.scalars, 0.0, 0.9, 0.95, 1e-8, 0.0, 1.0, 1.0,
+                                                       float(g.zero_size), 0)
                 _bump()
             else:
                 opt._sync_grads(g)
@@ -191,11 +205,16 @@ class ZeroFusedBackend:
                 pbuf, gbuf, flags = self.groups[g.gid]
                 beta1, beta2 = cfg.get("betas", (0.9, 0.95))
                 g.step += 1
-                torch.ops.b200.reduce_scatter_adam(gbuf.table_ptr(0), pbuf.table_ptr(0), flags.table_ptr(0), g.zero_rank,
-                                                   g.zero_size, 0, g.lo, g.shard, g.master, g.exp_avg, g.exp_avg_sq,
-                                                   g.scalars, cfg["lr"], beta1, beta2, cfg.get("eps", 1e-8),
-                                                   cfg.get("weight_decay", 0.0), 1.0 - beta1 ** g.step,
-                                                   1.0 - beta2 ** g.step, 1.0, 1)
+                hyper = (cfg["lr"], beta1, beta2, cfg.get("eps", 1e-8), cfg.get("weight_decay", 0.0),
+                         1.0 - beta1 ** g.step, 1.0 - beta2 ** g.step, 1.0, 1)
+                if self.use_mc:
+                    torch.ops.b200.reduce_scatter_adam_mc(gbuf.mc_ptr, pbuf.mc_ptr, gbuf.tensor.data_ptr(), g.zero_size,
+                                                          g.lo, g.shard, g.master, g.exp_avg, g.exp_avg_sq, g.scalars,
+                                                          *hyper)
+                else:
+                    torch.ops.b200.reduce_scatter_adam(gbuf.table_ptr(0), pbuf.table_ptr(0), flags.table_ptr(0),
+                                                       g.zero_rank, g.zero_size, 0, g.lo, g.shard, g.master, g.exp_avg,
+                                                       g.exp_avg_sq, g.scalars, *hyper)
                 _bump()
                 flags.barrier()  # all parameter pushes have landed before anyone starts the next forward
             else:

@@ -1,0 +1,192 @@
+"""Expert-parallel dispatch / combine fused over NVLink peer memory (``csrc/moe_comm.cu``).
+
+The NCCL formulation of an MoE layer (reference ``internlm/moe/sharded_moe.py:369-498`` and
+``internlm/moe/megablock/megablock_moe.py:155-247``) is  sort/permute → ``all_to_all`` → regroup → experts → regroup →
+``all_to_all`` → un-permute → weighted sum.  Here every routed (token, j) *slot* gets its final address ``(rank, row)`` in
+the owner GPU's expert slab from the ``[world, E]`` matrix of per-expert counts, and two kernels do the rest:
+
+* dispatch  = ``moe_scatter_rows``: token rows are stored straight into the owner's slab over NVLink,
+* combine   = ``moe_gather_combine``: the k expert outputs of a token are pulled from their owners, weighted in fp32 and
+  summed.
+
+The backward passes are the same two kernels with the roles swapped (``d dispatch`` is a gather with unit weights,
+``d combine`` is a scatter of ``w · dOut`` that also produces ``d w`` from the pulled expert outputs).
+
+``slot_plan`` is pure tensor arithmetic (no communication, any device) so the addressing is unit-tested on CPU against
+the all-to-all ordering (``tests/test_moe_cpu.py``).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from internevo_b200.ops.gemm import _bump
+from internevo_b200.utils.logger import get_logger
+
+from . import symm
+
+logger = get_logger(__file__)
+
+
+def slot_plan(expert_of_slot: torch.Tensor, count_matrix: torch.Tensor, rank: int, num_local_experts: int):
+    """Addresses of this rank's routed slots inside the owners' expert slabs.
+
+    ``expert_of_slot``  int64 ``[n_slots]`` global expert of every (token, j) slot of THIS rank (slot = token * k + j)
+    ``count_matrix``    int64 ``[world, E]``: rows routed by rank ``s`` to expert ``e``
+
+    The slab of a GPU is ordered (local expert, source rank, arrival order) — exactly the order produced by a
+    variable-split all-to-all followed by the regroup-by-expert permutation, so a local expert's rows are contiguous.
+
+    Returns ``(slot_rank int32[n_slots], slot_row int32[n_slots], rows_per_local_expert int64[El], rows_per_rank
+    int64[world])``.
+    """
+    world, E = count_matrix.shape
+    El = num_local_experts
+    assert E == world * El
+    cd = count_matrix.view(world, world, El)                      # [src, dst, el]
+    lay = cd.permute(1, 2, 0).reshape(world, El * world)          # per dst: (el, src) order
+    off = (lay.cumsum(1) - lay).view(world, El, world)            # exclusive prefix: slab offset of (dst, el, src)
+    my_base = off[:, :, rank].reshape(E)                          # [E]: where MY rows for expert e start on its owner
+    # arrival order inside (me -> expert e): stable order of the slots routed to e
+    order = torch.argsort(expert_of_slot, stable=True)
+    e_sorted = expert_of_slot[order]
+    my_counts = count_matrix[rank]
+    start = my_counts.cumsum(0) - my_counts
+    pos_sorted = torch.arange(e_sorted.numel(), device=e_sorted.device) - start[e_sorted]
+    row_sorted = my_base[e_sorted] + pos_sorted
+    slot_row = torch.empty_like(row_sorted)
+    slot_row[order] = row_sorted
+    slot_rank = torch.div(expert_of_slot, El, rounding_mode="floor")
+    return slot_rank.to(torch.int32), slot_row.to(torch.int32), cd[:, rank, :].sum(0), lay.sum(1)
+
+
+class MoEFusedBackend:
+    """Symmetric slabs + flags of one expert-parallel group.  ``max_rows`` bounds the rows a GPU can receive."""
+
+    def __init__(self, group: dist.ProcessGroup, hidden: int, max_rows: int, num_experts: int):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.hidden, self.max_rows, self.num_experts = hidden, max_rows, num_experts
+        self.xbuf = symm.SymmBuffer(max_rows * hidden, torch.bfloat16, group, zero=False)   # rows pushed to the owner
+        self.ybuf = symm.SymmBuffer(max_rows * hidden, torch.bfloat16, group, zero=False)   # rows pulled by the source
+        self.cnt = symm.SymmBuffer(self.world * num_experts, torch.int32, group, zero=True)
+        self.flags = symm.flags_for(group)
+
+    # ---- counts: [world, E] on every rank after ONE launch (push + rendezvous)
+    def exchange_counts(self, counts: torch.Tensor) -> torch.Tensor:
+        torch.ops.b200.symm_allgather_small(self.cnt.table_ptr(0), counts.to(torch.int32).contiguous(),
+                                            self.flags.table_ptr(0), self.rank, self.world, self.flags.next_epoch())
+        _bump()
+        return self.cnt.tensor.view(self.world, self.num_experts).to(torch.int64)
+
+    def x_rows(self, n: int) -> torch.Tensor:
+        return self.xbuf.view(0, (n, self.hidden))
+
+    def y_rows(self, n: int) -> torch.Tensor:
+        return self.ybuf.view(0, (n, self.hidden))
+
+
+_backends: Dict[Tuple[int, int, int, int], MoEFusedBackend] = {}
+
+
+def backend_for(group, hidden: int, max_rows: int, num_experts: int) -> Optional[MoEFusedBackend]:
+    """One backend per (group, hidden): the slabs are shared by all MoE layers of the model (they are used strictly one
+    layer at a time, every use bracketed by device barriers)."""
+    if not symm.symm_available() or dist.get_world_size(group) not in (2, 4, 8):
+        return None
+    key = (id(group), hidden, num_experts, 0)
+    be = _backends.get(key)
+    if be is None or be.max_rows < max_rows:
+        try:
+            be = MoEFusedBackend(group, hidden, max_rows, num_experts)
+        except Exception as e:  # pragma: no cover - depends on driver / topology
+            logger.warning(f"fused MoE dispatch unavailable ({e}); using NCCL all-to-all")
+            return None
+        _backends[key] = be
+    return be
+
+
+class _Plan:
+    __slots__ = ("slot_rank", "slot_row", "n_recv", "k", "n_tokens")
+
+    def __init__(self, slot_rank, slot_row, n_recv, k, n_tokens):
+        self.slot_rank, self.slot_row, self.n_recv, self.k, self.n_tokens = slot_rank, slot_row, n_recv, k, n_tokens
+
+
+class _FusedDispatch(torch.autograd.Function):
+    """x [T, H] → rows received by this GPU's experts [n_recv, H] (a private copy: the slab is reused by the next layer)."""
+
+    @staticmethod
+    def forward(ctx, x, be: MoEFusedBackend, plan: _Plan):
+        ctx.be, ctx.plan = be, plan
+        torch.ops.b200.moe_scatter_rows(x, plan.slot_rank, plan.slot_row, None, be.xbuf.table_ptr(0), 0, None, plan.k)
+        _bump()
+        be.flags.barrier()                      # every peer's rows have landed in my slab
+        rows = be.x_rows(plan.n_recv).clone()
+        be.flags.barrier()                      # nobody overwrites a slab that is still being read
+        return rows
+
+    @staticmethod
+    def backward(ctx, g_rows):
+        be, plan = ctx.be, ctx.plan
+        be.y_rows(plan.n_recv).copy_(g_rows)
+        be.flags.barrier()
+        gx = torch.empty(plan.n_tokens, be.hidden, dtype=torch.bfloat16, device=g_rows.device)
+        torch.ops.b200.moe_gather_combine(gx, None, plan.slot_rank, plan.slot_row, be.ybuf.table_ptr(0), plan.k)
+        _bump()
+        be.flags.barrier()
+        return gx, None, None
+
+
+class _FusedCombine(torch.autograd.Function):
+    """expert outputs [n_recv, H] (on their owner) + gate weights [T * k] → combined [T, H] on the token's GPU."""
+
+    @staticmethod
+    def forward(ctx, out_rows, w, be: MoEFusedBackend, plan: _Plan):
+        ctx.be, ctx.plan = be, plan
+        ctx.save_for_backward(out_rows, w)
+        be.y_rows(plan.n_recv).copy_(out_rows)
+        be.flags.barrier()
+        out = torch.empty(plan.n_tokens, be.hidden, dtype=torch.bfloat16, device=out_rows.device)
+        torch.ops.b200.moe_gather_combine(out, w, plan.slot_rank, plan.slot_row, be.ybuf.table_ptr(0), plan.k)
+        _bump()
+        be.flags.barrier()
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        be, plan = ctx.be, ctx.plan
+        out_rows, w = ctx.saved_tensors
+        g_out = g_out.contiguous()
+        be.y_rows(plan.n_recv).copy_(out_rows)   # the owners publish their outputs again for d(gate weight)
+        be.flags.barrier()
+        dw = torch.empty_like(w)
+        torch.ops.b200.moe_scatter_rows(g_out, plan.slot_rank, plan.slot_row, w, be.xbuf.table_ptr(0),
+                                        be.ybuf.table_ptr(0), dw, plan.k)
+        _bump()
+        be.flags.barrier()
+        g_rows = be.x_rows(plan.n_recv).clone()
+        be.flags.barrier()
+        return g_rows, dw, None, None
+
+
+def fused_dispatch(x2: torch.Tensor, expert_of_slot: torch.Tensor, counts: torch.Tensor, be: MoEFusedBackend, k: int):
+    """Returns ``(rows [n_recv, H], rows_per_local_expert list, plan)``; one host sync (the slab sizes)."""
+    cm = be.exchange_counts(counts)
+    El = be.num_experts // be.world
+    slot_rank, slot_row, per_expert, per_rank = slot_plan(expert_of_slot, cm, be.rank, El)
+    host = torch.cat([per_expert, per_rank.max().view(1)]).tolist()
+    per_expert_l, worst = host[:-1], host[-1]
+    if worst > be.max_rows:
+        raise RuntimeError(f"fused MoE dispatch: a GPU would receive {worst} rows but the slab holds {be.max_rows}; "
+                           f"raise moe fused_capacity_factor")
+    plan = _Plan(slot_rank, slot_row, int(sum(per_expert_l)), k, x2.shape[0])
+    rows = _FusedDispatch.apply(x2.contiguous(), be, plan)
+    return rows, [int(v) for v in per_expert_l], plan
+
+
+def fused_combine(out_rows: torch.Tensor, w_slots: torch.Tensor, be: MoEFusedBackend, plan: _Plan) -> torch.Tensor:
+    return _FusedCombine.apply(out_rows.contiguous(), w_slots.float().contiguous(), be, plan)

@@ -53,6 +53,11 @@ class SymmBuffer:
             self.tensor.zero_()
         self.handle = symm_mem.rendezvous(self.tensor, group)
         self.base_ptrs: List[int] = [int(p) for p in self.handle.buffer_ptrs]
+        # NVSwitch multicast (NVLS) mapping of the same allocation: 0 when the fabric / driver has no multicast support
+        try:
+            self.mc_ptr: int = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        except Exception:  # pragma: no cover - older torch builds raise instead of returning 0
+            self.mc_ptr = 0
         self.elem = self.tensor.element_size()
         self._tables: Dict[int, torch.Tensor] = {}
         dist.barrier(group)

@@ -33,12 +33,12 @@ logger = get_logger(__file__)
 
 def set_fp32_attr_for_model(model: Union[nn.Module, nn.ModuleList]):
     """``use_fp32_norm``: tag every norm module so ``NaiveAMPModel`` keeps it in fp32 (reference ``:88-95``)."""
-    from internevo_b200.ops.norm import RMSNorm
+    from internevo_b200.ops.norm import LayerNorm, RMSNorm
 
     models = model if isinstance(model, nn.ModuleList) else [model]
     for m in models:
         for sub in m.modules():
-            if isinstance(sub, (RMSNorm, nn.LayerNorm)):
+            if isinstance(sub, (RMSNorm, LayerNorm, nn.LayerNorm)):
                 set_fp32_attr_to_module(sub)
 
 

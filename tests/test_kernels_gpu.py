@@ -60,3 +60,60 @@ def test_linear_autograd_accumulates_into_grad_buf():
     ref = 2 * (torch.ones(256, 384, device="cuda").t() @ x.detach().float())
     assert w.grad is None and w.grad_ready
     assert (w.grad_buf.float() - ref).abs().max() / ref.abs().max() < 2e-2
+
+
+@pytest.mark.parametrize("H", [1024, 4096, 5120])
+@pytest.mark.parametrize("with_res,p", [(True, 0.0), (False, 0.0), (True, 0.1)])
+def test_dropout_add_layernorm_matches_fp32_reference(H, with_res, p):
+    """csrc/layernorm.cu vs plain fp32 PyTorch: outputs, new residual, dx, dres, dweight, dbias."""
+    _native_loaded()
+    from internevo_b200 import ops
+    from internevo_b200.ops.norm import _DropAddLayerNormFn
+
+    torch.manual_seed(0)
+    rows = 777
+    x = (torch.randn(rows, H, device="cuda") * 2 + 0.5).to(torch.bfloat16).requires_grad_(True)
+    res = torch.randn(rows, H, device="cuda").to(torch.bfloat16).requires_grad_(True) if with_res else None
+    w = torch.nn.Parameter((torch.rand(H, device="cuda") + 0.5).to(torch.bfloat16))
+    b = torch.nn.Parameter((torch.randn(H, device="cuda") * 0.1).to(torch.bfloat16))
+    keep = (torch.rand(rows, H, device="cuda") >= p).to(torch.uint8) if p > 0 else None
+    scale = 1.0 / (1.0 - p) if p > 0 else 1.0
+    n0 = ops.launch_count()
+    y, new_res = _DropAddLayerNormFn.apply(x, res, w, b, 1e-5, keep, scale)
+    gy, gr = torch.randn_like(y), torch.randn_like(y)
+    ((y.float() * gy.float()).sum() + (new_res.float() * gr.float()).sum()).backward()
+    assert ops.launch_count() - n0 == 3
+    got = [y, new_res, x.grad, res.grad if with_res else None, w.grad, b.grad]
+    # fp32 oracle
+    xf = x.detach().float().requires_grad_(True)
+    rf = res.detach().float().requires_grad_(True) if with_res else None
+    wf, bf = w.detach().float().requires_grad_(True), b.detach().float().requires_grad_(True)
+    d = xf * keep.float() * scale if keep is not None else xf
+    nr = d + rf if with_res else d
+    nr_b = nr.to(torch.bfloat16).float() + (nr - nr.detach())  # the kernel normalises the bf16-rounded residual
+    yr = torch.nn.functional.layer_norm(nr_b, (H,), wf, bf, 1e-5)
+    ((yr * gy.float()).sum() + (nr * gr.float()).sum()).backward()
+    want = [yr, nr, xf.grad, rf.grad if with_res else None, wf.grad, bf.grad]
+    tol = [2e-2, 1e-2, 2e-2, 2e-2, 2e-2, 2e-2]
+    for g, r, t in zip(got, want, tol):
+        if r is None:
+            continue
+        err = float((g.float() - r).norm() / (r.norm() + 1e-9))
+        assert err < t, (H, with_res, p, err)
+
+
+def test_layernorm_module_in_decoder_block():
+    """norm_type='layernorm' models run the native kernel (module API: forward(x) and forward(x, residual))."""
+    _native_loaded()
+    from internevo_b200 import ops
+
+    ln = ops.LayerNorm(512, eps=1e-5, device="cuda", dtype=torch.bfloat16)
+    x = torch.randn(64, 512, device="cuda", dtype=torch.bfloat16)
+    r = torch.randn(64, 512, device="cuda", dtype=torch.bfloat16)
+    n0 = ops.launch_count()
+    y1 = ln(x)
+    y2, nr = ln(x, r)
+    assert ops.launch_count() - n0 == 2
+    assert torch.allclose(y1.float(), torch.nn.functional.layer_norm(x.float(), (512,)), atol=3e-2)
+    assert torch.allclose(nr.float(), (x + r).float(), atol=1e-6)
+    assert torch.allclose(y2.float(), torch.nn.functional.layer_norm((x + r).float(), (512,)), atol=3e-2)

@@ -116,3 +116,57 @@ def _train_dropless(rank, world, kw):
 def test_dropless_expert_parallel_dp2():
     for losses in run_distributed(_train_dropless, 2, {}):
         assert losses[-1] < losses[0]
+
+
+def test_fused_dispatch_slot_plan_matches_all_to_all_order():
+    """The peer-memory dispatch addresses every routed slot by (owner rank, slab row).  Simulate `world` ranks in one
+    process: pushing rows by `slot_plan` must build, on every owner, exactly the slab that the variable-split all-to-all +
+    regroup-by-expert path builds (rows of a local expert contiguous, ordered by source rank then arrival), and pulling them
+    back by the same addresses with the gate weights must reproduce the combine."""
+    from internevo_b200.parallel.moe_fused import slot_plan
+
+    torch.manual_seed(0)
+    world, El, k, S, H = 4, 2, 2, 37, 8
+    E = world * El
+    xs = [torch.randn(S, H) for _ in range(world)]
+    experts = [torch.stack([torch.randperm(E)[:k] for _ in range(S)]).reshape(-1) for _ in range(world)]  # [S * k]
+    weights = [torch.rand(S * k) for _ in range(world)]
+    counts = torch.stack([torch.bincount(e, minlength=E) for e in experts])          # [world, E]
+    plans = [slot_plan(experts[r], counts, r, El) for r in range(world)]
+    # ---- push
+    slabs = [torch.full((int(plans[0][3][d]), H), float("nan")) for d in range(world)]
+    for r in range(world):
+        slot_rank, slot_row, per_expert, per_rank = plans[r]
+        assert per_rank.tolist() == [int(counts[:, d * El:(d + 1) * El].sum()) for d in range(world)]
+        for s in range(S * k):
+            slabs[int(slot_rank[s])][int(slot_row[s])] = xs[r][s // k]
+    # ---- oracle: what all_to_all_v + regroup gives on owner d
+    for d in range(world):
+        assert not torch.isnan(slabs[d]).any()                      # every row written exactly where expected
+        recv = []
+        for el in range(El):
+            for src in range(world):
+                e = d * El + el
+                sel = (experts[src] == e).nonzero().flatten()       # arrival order = slot order (stable sort)
+                recv.append(xs[src][sel // k])
+        oracle = torch.cat(recv, 0)
+        assert torch.equal(slabs[d], oracle)
+        assert plans[d][2].tolist() == [int(counts[:, d * El + el].sum()) for el in range(El)]
+    # ---- pull back with weights ("expert" = multiply by (global expert id + 1))
+    outs = []
+    for d in range(world):
+        per_expert = plans[d][2].tolist()
+        chunks, start = [], 0
+        for el, n in enumerate(per_expert):
+            chunks.append(slabs[d][start:start + n] * (d * El + el + 1))
+            start += n
+        outs.append(torch.cat(chunks, 0))
+    for r in range(world):
+        slot_rank, slot_row = plans[r][0], plans[r][1]
+        got = torch.zeros(S, H)
+        for s in range(S * k):
+            got[s // k] += weights[r][s] * outs[int(slot_rank[s])][int(slot_row[s])]
+        want = torch.zeros(S, H)
+        for s in range(S * k):
+            want[s // k] += weights[r][s] * xs[r][s // k] * (int(experts[r][s]) + 1)
+        assert torch.allclose(got, want, atol=1e-5)

@@ -192,3 +192,25 @@ def test_monitor_loss_spike_and_exception_filter(tmp_path):
         assert len(hooks) == 2 and "boom" in hooks[0] and "other" in hooks[1]
     finally:
         mon.send_alert_message = orig
+
+
+def test_layernorm_module_cpu_matches_torch():
+    """ops.LayerNorm (CPU / fp32 path): same numbers as nn.LayerNorm, block-prologue calling convention."""
+    import torch
+
+    from internevo_b200 import ops
+
+    torch.manual_seed(0)
+    ln, ref = ops.LayerNorm(32, eps=1e-5), torch.nn.LayerNorm(32, eps=1e-5)
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.normal_()
+        ref.weight.copy_(ln.weight)
+        ref.bias.copy_(ln.bias)
+    x, r = torch.randn(5, 32, requires_grad=True), torch.randn(5, 32)
+    y, nr = ln(x, r)
+    assert torch.allclose(y, ref(x + r), atol=1e-5) and torch.allclose(nr, x + r)
+    y.sum().backward()
+    assert x.grad is not None and ln.weight.grad is not None and ln.bias.grad is not None
+    assert torch.allclose(ln(x), ref(x), atol=1e-5)
+    assert set(ln.state_dict()) == {"weight", "bias"}

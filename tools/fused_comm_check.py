@@ -177,6 +177,110 @@ def main():
                    "fused_adam_allgather_ms": round(t_ad, 3), "nccl_allgather_only_ms": round(t_nag, 3),
                    "rs_GBps_per_gpu": round(shard * 2 * (world - 1) / t_rs / 1e6, 1),
                    "elements": n}
+    # ---- the same two phases through the NVSwitch multicast mapping (multimem.ld_reduce / multimem.st)
+    if gbuf.mc_ptr and pbuf.mc_ptr:
+        gbuf.tensor.copy_(torch.randn(n, device="cuda") * 0.01)
+        ref = gbuf.tensor.float().clone()
+        dist.all_reduce(ref)
+        ref /= world
+        scal.zero_()
+        p32 = torch.randn(shard, device="cuda")
+        m32.zero_(); v32.zero_()
+        flags.barrier()
+
+        def mc(phase, *hyper):
+            torch.ops.b200.reduce_scatter_adam_mc(gbuf.mc_ptr, pbuf.mc_ptr, gbuf.tensor.data_ptr(), world, lo, shard, p32,
+                                                  m32, v32, scal, *hyper, phase)
+
+        mc(0, 0.0, 0.9, 0.95, 1e-8, 0.0, 1.0, 1.0, float(world))
+        torch.cuda.synchronize()
+        r = rel(gbuf.tensor[lo:lo + shard], ref[lo:lo + shard])
+        ss_ref = gbuf.tensor[lo:lo + shard].float().pow(2).sum()
+        ok &= r < 1e-2 and abs(scal[3].item() - ss_ref.item()) / ss_ref.item() < 1e-3
+        stage(f"zero NVLS rs rel={r}")
+        scal[0] = 1.0
+        pref = p32.clone()
+        ops.adamw_(pref, torch.zeros_like(pref), torch.zeros_like(pref), gbuf.tensor[lo:lo + shard], None, 1e-3, 0.9,
+                   0.95, 1e-8, 0.1, 1, None)
+        mc(1, 1e-3, 0.9, 0.95, 1e-8, 0.1, 1 - 0.9, 1 - 0.95, 1.0)
+        flags.barrier()
+        torch.cuda.synchronize()
+        allp = [torch.empty(shard, device="cuda") for _ in range(world)]
+        dist.all_gather(allp, pref)
+        r_p = rel(pbuf.tensor, torch.cat(allp))
+        ok &= r_p < 1e-2 and rel(p32, pref) < 1e-5
+        stage(f"zero NVLS adam+bcast rel={r_p}")
+        t_rs = timed(lambda: mc(0, 0.0, 0.9, 0.95, 1e-8, 0.0, 1.0, 1.0, float(world)))
+        t_ad = timed(lambda: mc(1, 1e-3, 0.9, 0.95, 1e-8, 0.1, 0.1, 0.05, 1.0))
+        res["zero_nvls"] = {"rs_rel_err": r, "param_rel_err": r_p, "fused_rs_ms": round(t_rs, 3),
+                            "fused_adam_allgather_ms": round(t_ad, 3)}
+    else:
+        res["zero_nvls"] = {"unavailable": "no multicast mapping (handle.multicast_ptr == 0)"}
+    # ---- MoE dispatch / combine over peer memory vs permute + NCCL all-to-all(v) + un-permute
+    from internevo_b200.parallel.moe_fused import MoEFusedBackend, slot_plan
+
+    S, H, k, El = 4096, 4096, 2, 1
+    E = world * El
+    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    xt = (torch.randn(S, H, device="cuda", generator=gen) * 0.5).to(torch.bfloat16)
+    eos = torch.stack([torch.randperm(E, device="cuda", generator=gen)[:k] for _ in range(S)]).reshape(-1) if E >= k else \
+        torch.zeros(S * k, dtype=torch.int64, device="cuda")
+    wts = torch.rand(S * k, device="cuda", generator=gen)
+    counts = torch.bincount(eos, minlength=E)
+    mbe = MoEFusedBackend(group, H, S * k * world, E)
+    cm = mbe.exchange_counts(counts)
+    slot_rank, slot_row, per_expert, per_rank = slot_plan(eos, cm, rank, El)
+    n_recv = int(per_expert.sum())
+    order = torch.argsort(eos, stable=True)
+    tok = (torch.arange(S * k, device="cuda") // k)[order]
+    send_splits = counts.view(world, El).sum(1).tolist()
+    recv_splits = cm.view(world, world, El)[:, rank, :].sum(1).tolist()
+    src_expert = torch.repeat_interleave(torch.arange(El, device="cuda").repeat(world), cm.view(world, world, El)[:, rank, :].reshape(-1))
+    regroup = torch.argsort(src_expert, stable=True)
+
+    def nccl_dispatch():
+        send = xt[tok]
+        recv = send.new_empty(n_recv, H)
+        dist.all_to_all_single(recv, send, output_split_sizes=recv_splits, input_split_sizes=send_splits)
+        return recv[regroup]
+
+    def fused_dispatch_k():
+        torch.ops.b200.moe_scatter_rows(xt, slot_rank, slot_row, None, mbe.xbuf.table_ptr(0), 0, None, k)
+        mbe.flags.barrier()
+
+    fused_dispatch_k()
+    torch.cuda.synchronize()
+    r_d = rel(mbe.x_rows(n_recv), nccl_dispatch())
+    ok &= r_d == 0.0
+    stage(f"moe dispatch rel={r_d} rows={n_recv}")
+    yrows = (mbe.x_rows(n_recv).float() * 1.5).to(torch.bfloat16)
+
+    def nccl_combine():
+        back = torch.empty_like(yrows).index_copy(0, regroup, yrows)
+        outb = back.new_empty(S * k, H)
+        dist.all_to_all_single(outb, back, output_split_sizes=send_splits, input_split_sizes=recv_splits)
+        return torch.zeros(S, H, device="cuda", dtype=torch.bfloat16).index_add(0, tok, outb * wts[order].to(outb.dtype).unsqueeze(1))
+
+    comb = torch.empty(S, H, device="cuda", dtype=torch.bfloat16)
+
+    def fused_combine_k():
+        mbe.y_rows(n_recv).copy_(yrows)
+        mbe.flags.barrier()
+        torch.ops.b200.moe_gather_combine(comb, wts, slot_rank, slot_row, mbe.ybuf.table_ptr(0), k)
+        mbe.flags.barrier()
+
+    fused_combine_k()
+    torch.cuda.synchronize()
+    r_c = rel(comb, nccl_combine())
+    ok &= r_c < 1e-2
+    stage(f"moe combine rel={r_c}")
+    t_fd, t_nd = timed(fused_dispatch_k), timed(nccl_dispatch)
+    t_fc, t_nc = timed(fused_combine_k), timed(nccl_combine)
+    remote = S * k * H * 2 * (world - 1) / world
+    res["moe"] = {"tokens": S, "k": k, "hidden": H, "dispatch_rel_err": r_d, "combine_rel_err": r_c,
+                  "fused_dispatch_ms": round(t_fd, 4), "nccl_permute_a2a_ms": round(t_nd, 4),
+                  "fused_combine_ms": round(t_fc, 4), "nccl_a2a_unpermute_ms": round(t_nc, 4),
+                  "dispatch_remote_GBps": round(remote / t_fd / 1e6, 1), "combine_remote_GBps": round(remote / t_fc / 1e6, 1)}
     okt = torch.tensor([int(ok)], device="cuda")
     dist.all_reduce(okt, op=dist.ReduceOp.MIN)
     if rank == 0:

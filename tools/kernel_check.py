@@ -63,6 +63,14 @@ def check_gemm():
                 allok &= err_report(f"TN  {M}x{N}x{K} (A,B MN-major) bn{bn}", out, ref, 1e-2)
                 out = ops.matmul(at, b, a_mn=True, force_bn=bn)
                 allok &= err_report(f"TT  {M}x{N}x{K} (A MN-major) bn{bn}", out, ref, 1e-2)
+    # ragged K with both operands MN-major (wgrad over an MoE expert's exactly-sized token slab): TMA zero-fills the tail
+    for (M, N, K) in [(512, 1024, 1003), (1024, 512, 37), (256, 256, 1)]:
+        at = torch.randn(K, M, device=dev, dtype=torch.bfloat16)
+        bt = torch.randn(K, N, device=dev, dtype=torch.bfloat16)
+        ref = at.float().t() @ bt.float()
+        for bn in (0, 128, 256, 512):
+            out = ops.matmul(at, bt, a_mn=True, b_mn=True, force_bn=bn)
+            allok &= err_report(f"TN  {M}x{N}x{K} ragged K bn{bn}", out, ref, 1e-2)
     # epilogues
     M, N, K = 512, 1024, 512
     a = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
