@@ -10,6 +10,7 @@ from torch.nn.modules.loss import _Loss
 
 from internevo_b200.core.gradient_handler import BaseGradientHandler
 from internevo_b200.utils.common import get_batch_size, move_to_device
+from internevo_b200.utils.nvtx import nvtx_range
 
 
 class Engine:
@@ -45,9 +46,10 @@ class Engine:
 
     def step(self):
         """gradient handlers → optimizer.step → (on success) lr / beta2 schedulers. Returns ``(success, grad_norms)``."""
-        self._all_reduce_gradients()
-        self.optimizer.clip_grad_norm(self.model, self._clip_grad_norm)
-        success, group_norms = self.optimizer.step()
+        with nvtx_range("engine.step"):
+            self._all_reduce_gradients()
+            self.optimizer.clip_grad_norm(self.model, self._clip_grad_norm)
+            success, group_norms = self.optimizer.step()
         if success and self._lr_scheduler is not None:
             self._lr_scheduler.step()
         if success and self._beta2_scheduler is not None:
@@ -63,13 +65,16 @@ class Engine:
         self._model.eval()
 
     def backward(self, loss: torch.Tensor):
-        return self.optimizer.backward(loss)
+        with nvtx_range("backward"):
+            return self.optimizer.backward(loss)
 
     def backward_by_grad(self, tensor, grad):
-        return self.optimizer.backward_by_grad(tensor, grad)
+        with nvtx_range("backward"):
+            return self.optimizer.backward_by_grad(tensor, grad)
 
     def __call__(self, *args, **kwargs):
-        return self.model(*args, **kwargs)
+        with nvtx_range("forward"):
+            return self.model(*args, **kwargs)
 
     def load_batch(self, data_iter, to_gpu=True):
         """→ ``(batch_data, batch_size)`` moved to the device (pinned → async H2D)."""

@@ -33,6 +33,7 @@ from internevo_b200.parallel.linear import RewardModelLinear, ScaleColumnParalle
 from internevo_b200.solver.activation_checkpoint import activation_checkpoint
 from internevo_b200.solver.pipeline_utils import partition_uniform
 from internevo_b200.utils.logger import get_logger
+from internevo_b200.utils.nvtx import nvtx_range
 
 from .modules import Embedding1D, FeedForward, GeluMLP, MHA, VocabParallelEmbedding, _is_isp
 
@@ -93,6 +94,7 @@ class DecoderLayer(nn.Module):
                  tp_mode="mtp", moe_cfg: Optional[dict] = None, adapt_hf=False, dropout_selective_checkpoint=True):
         super().__init__()
         self.spec, self.checkpoint, self.layer_idx = spec, checkpoint, layer_idx
+        self._nvtx_name = f"layer{layer_idx}"
         self.prenorm = not apply_post_layer_norm
         self.drop_rate = drop_rate
         self.residual_in_fp32 = residual_in_fp32
@@ -159,10 +161,11 @@ class DecoderLayer(nn.Module):
 
     def forward(self, hidden_states, residual=None, cu_seqlens=None, indexes=None, inference_params=None,
                 max_seqlen=None):
-        if self.checkpoint and self.training:
-            return activation_checkpoint(self._forward, False, hidden_states, residual, cu_seqlens, indexes,
-                                         inference_params, max_seqlen)
-        return self._forward(hidden_states, residual, cu_seqlens, indexes, inference_params, max_seqlen)
+        with nvtx_range(self._nvtx_name):
+            if self.checkpoint and self.training:
+                return activation_checkpoint(self._forward, False, hidden_states, residual, cu_seqlens, indexes,
+                                             inference_params, max_seqlen)
+            return self._forward(hidden_states, residual, cu_seqlens, indexes, inference_params, max_seqlen)
 
     def _drop(self, x):
         return F.dropout(x, self.drop_rate, self.training) if self.drop_rate > 0 else x

@@ -21,6 +21,7 @@ import torch.distributed as dist
 
 from internevo_b200.ops.gemm import _bump
 from internevo_b200.utils.logger import get_logger
+from internevo_b200.utils.nvtx import nvtx_range
 
 from . import symm
 
@@ -169,6 +170,10 @@ class ZeroFusedBackend:
         return be if be.groups else None
 
     def step(self, opt):
+        with nvtx_range("zero.fused_step(rs+adamw+ag)"):
+            return self._step(opt)
+
+    def _step(self, opt):
         from internevo_b200 import ops
 
         scale = opt.grad_scaler.scale

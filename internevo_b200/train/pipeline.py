@@ -180,6 +180,10 @@ def load_new_batch(train_dl: DataLoader, train_iter: Iterable, train_state: Trai
 
 def initialize_llm_profile(profiling: bool = False, start_time: str = None):
     """``torch.profiler`` on dp0 ∧ tp0 ranks when ``--profiling`` (reference ``:417-459``), else a dummy."""
+    if profiling:
+        from internevo_b200.utils import nvtx
+
+        nvtx.enable(True)  # layer / fwd / bwd / optimizer / fused-collective ranges show up in the trace
     if profiling and gpc.get_local_rank(ParallelMode.DATA) == 0 and gpc.get_local_rank(ParallelMode.TENSOR) == 0:
         acts = [torch.profiler.ProfilerActivity.CPU]
         if torch.cuda.is_available():

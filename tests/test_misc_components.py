@@ -1,0 +1,157 @@
+"""Components that had no dedicated test: shared-module gradient handler (C12), logger (F2), gputest helpers (F5),
+SimpleMemoryProfiler (F6), init functions (G3), web demo page (T3)."""
+import logging
+import math
+import os
+import sys
+
+import torch
+
+from common import run_distributed
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---------------------------------------------------------------------------------------------------------------- C12
+def _shared_module_grads(rank, world):
+    import torch.distributed as dist
+
+    from internevo_b200.core.gradient_handler import PipelineSharedModuleGradientHandler
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    model = torch.nn.Linear(4, 3)
+    model.weight.pipeline_shared_module_pg = dist.group.WORLD      # tied across "stages"
+    model.weight.grad = torch.full_like(model.weight, float(rank + 1))
+    model.bias.grad = torch.full_like(model.bias, float(rank + 1))  # not tagged: untouched
+    PipelineSharedModuleGradientHandler(model, None).handle_gradient()
+    out = (model.weight.grad.clone(), model.bias.grad.clone())
+    dist.destroy_process_group()
+    return out
+
+
+def test_pipeline_shared_module_gradient_handler_sums_tagged_grads():
+    for rank, (gw, gb) in enumerate(run_distributed(_shared_module_grads, 2)):
+        assert torch.all(gw == 3.0)              # 1 + 2 summed over the shared group
+        assert torch.all(gb == float(rank + 1))
+
+
+# ----------------------------------------------------------------------------------------------------------------- F2
+def test_logger_singleton_file_sink_and_extra_handler(tmp_path):
+    from internevo_b200.utils import logger as L
+
+    lg = L.get_logger("whatever")
+    assert lg is L.get_logger() and lg.name == L.LOGGER_NAME and not lg.propagate
+    n_stream = sum(isinstance(h, logging.StreamHandler) and not isinstance(h, logging.FileHandler) for h in lg.handlers)
+    assert n_stream == 1                          # repeated get_logger calls never stack stream handlers
+
+    seen = []
+
+    class Sink(logging.Handler):
+        def emit(self, record):
+            seen.append(record.getMessage())
+
+    sink = Sink()
+    L.add_handler(sink)
+    lg2 = L.initialize_uniscale_logger(job_name="job", launch_time="t0", file_name="rank0", file_path=str(tmp_path))
+    lg2.info("hello sinks")
+    for h in lg2.handlers:
+        h.flush()
+    assert "hello sinks" in seen
+    assert "hello sinks" in open(tmp_path / "rank0.log").read()
+    lg.removeHandler(sink)
+    for h in list(lg.handlers):
+        if isinstance(h, logging.FileHandler):
+            lg.removeHandler(h)
+            h.close()
+
+
+# ----------------------------------------------------------------------------------------------------------------- F5
+def test_gputest_helpers_cpu():
+    from internevo_b200.utils import gputest
+
+    # attention TFLOPS formula used by the micro-benchmark: 4 * b * s^2 * h * d / time / 1e12
+    assert math.isclose(gputest.flops(2, 128, 64, 8, 1.0), 4 * 2 * 128 ** 2 * 8 * 64 / 1e12, rel_tol=1e-9)
+    assert isinstance(gputest.get_cpu_temperature(), (int, float))
+    assert isinstance(gputest.get_gpu_temperature(), (int, float))   # -1 when no NVML device is present
+
+
+# ----------------------------------------------------------------------------------------------------------------- F6
+def test_simple_memory_profiler_accounts_params_grads_optimizer_and_activations(tmp_path):
+    from internevo_b200.utils.simple_memory_profiler import SimpleMemoryProfiler, SimpleMemState
+
+    st = SimpleMemState("root")
+    st.add("a.b", 10)
+    st.add("a.c", 6)
+    st.add("d", 4)
+    assert st.total_mem == 20 and "a" in st.dump() and st.to_json()["name"] == "root"
+
+    model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+
+    class G:
+        name = "default"
+        master = torch.zeros(10)
+        exp_avg = torch.zeros(10)
+        exp_avg_sq = torch.zeros(10)
+
+    class Opt:
+        groups = [G()]
+
+    prof = SimpleMemoryProfiler(model, Opt(), str(tmp_path), total_steps=2)
+    n_param_bytes = sum(p.numel() * p.element_size() for p in model.parameters())
+    assert prof._param.total_mem == n_param_bytes == prof._grad.total_mem
+    assert prof._os.total_mem == 3 * 10 * 4
+    for _ in range(2):
+        model(torch.randn(5, 8)).sum().backward()
+        prof.step()
+    text = open(tmp_path / "memory_2.log").read()
+    assert "parameters" in text and "activations" in text and "optimizer_states" in text
+    assert prof._stoped and prof._activation.total_mem == (5 * 16 + 5 * 16 + 5 * 4) * 4
+    model(torch.randn(5, 8))                      # hooks are removed after the last profiled step
+    assert prof._activation.total_mem == (5 * 16 + 5 * 16 + 5 * 4) * 4
+
+
+# ----------------------------------------------------------------------------------------------------------------- G3
+def test_init_functions_statistics():
+    from internevo_b200.initialize.initialize_tensor import (normal_, scaled_init_method_normal,
+                                                              scaled_init_method_uniform, uniform_)
+
+    torch.manual_seed(0)
+    t = torch.empty(400, 400)
+    normal_(std=0.02)(t)
+    assert abs(float(t.std()) - 0.02) < 1e-3 and abs(float(t.mean())) < 1e-3
+    scaled_init_method_normal(sigma=0.02, num_layers=8)(t)
+    assert abs(float(t.std()) - 0.02 / 4.0) < 5e-4           # sigma / sqrt(2 * num_layers)
+    uniform_(std=0.03)(t)
+    a = math.sqrt(3 * 0.03)
+    assert float(t.max()) <= a and float(t.min()) >= -a and float(t.max()) > 0.95 * a
+    scaled_init_method_uniform(sigma=0.02, num_layers=2)(t)
+    a = math.sqrt(3 * 0.02 / 2.0)
+    assert float(t.abs().max()) <= a and float(t.abs().max()) > 0.95 * a
+
+
+# ----------------------------------------------------------------------------------------------------------------- T3
+def test_web_demo_serves_chat_page():
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        import web_demo
+        from fastapi.testclient import TestClient
+    except Exception as e:  # httpx (TestClient) may be missing in the image: check the route table instead
+        import web_demo
+
+        paths = {r.path for r in web_demo.app.routes}
+        assert "/" in paths and "/v1/chat/completions" in paths, (paths, e)
+        assert "/v1/chat/completions" in web_demo.PAGE
+        return
+    r = TestClient(web_demo.app).get("/")
+    assert r.status_code == 200 and "internevo_b200 chat" in r.text
+
+
+def test_nvtx_ranges_are_noops_without_cuda_and_toggle():
+    from internevo_b200.utils import nvtx
+
+    nvtx.enable(True)
+    with nvtx.nvtx_range("cpu-safe"):       # no CUDA here: must not raise
+        pass
+    assert nvtx.enabled() == torch.cuda.is_available()
+    nvtx.enable(False)
+    assert not nvtx.enabled()
