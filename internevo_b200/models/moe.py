@@ -187,6 +187,9 @@ class GShardMOELayer(nn.Module):
         k = experts.shape[1]
         flat = (experts * cap + slots).reshape(-1)            # row in the [E * cap, h] dispatch buffer
         keep_f = keep.reshape(-1)
+        be = self._fused_backend(x2, E * cap)
+        if be is not None:
+            return self._forward_fused(x2, be, weights, experts, slots, keep_f, cap).reshape(shape)
         tok = torch.arange(S, device=x2.device).repeat_interleave(k)
         rows, toks = flat[keep_f], tok[keep_f]
         dispatched = x2.new_zeros(E * cap, h).index_copy(0, rows, x2[toks])
@@ -204,6 +207,34 @@ class GShardMOELayer(nn.Module):
         w = weights.reshape(-1)[keep_f].to(out.dtype)
         combined = x2.new_zeros(S, h).index_add(0, toks, out[rows] * w.unsqueeze(1))
         return combined.reshape(shape)
+
+
+    # ---- peer-memory path: dispatch / combine are ONE kernel each over NVLink (parallel/moe_fused.py, csrc/moe_comm.cu)
+    def _fused_backend(self, x2: torch.Tensor, rows_per_rank: int):
+        if self.ep_size <= 1 or not x2.is_cuda or x2.dtype is not torch.bfloat16 or x2.shape[1] % 8 != 0:
+            return None
+        if os.environ.get("B200_MOE_FUSED", "1") == "0":
+            return None
+        from internevo_b200.parallel.moe_fused import backend_for
+
+        return backend_for(self.ep_group, x2.shape[1], rows_per_rank, self.gate.num_experts)
+
+    def _forward_fused(self, x2, be, weights, experts, slots, keep_f, cap):
+        """The owner's slab is the ``[E_local, ep * cap, h]`` expert input itself: slot (token, j) routed to expert ``e`` with
+        capacity slot ``c`` lands at row ``(e % E_local) * ep * cap + my_rank * cap + c`` of GPU ``e // E_local``; dropped
+        slots carry row -1 (nothing sent, zero contribution).  Unused capacity rows are zero, as in the dense buffer."""
+        from internevo_b200.parallel.moe_fused import fused_capacity_combine, fused_capacity_dispatch
+
+        El, ep = self.num_local_experts, self.ep_size
+        e_flat, c_flat = experts.reshape(-1), slots.reshape(-1)
+        row = (e_flat % El) * (ep * cap) + be.rank * cap + c_flat
+        slot_row = torch.where(keep_f, row, torch.full_like(row, -1)).to(torch.int32)
+        slot_rank = torch.div(e_flat, El, rounding_mode="floor").to(torch.int32)
+        k = experts.shape[1]
+        d, plan = fused_capacity_dispatch(x2, slot_rank, slot_row, be, k, El * ep * cap)
+        out = self.experts(d.view(El, ep * cap, -1)).reshape(El * ep * cap, -1)
+        w = (weights.reshape(-1) * keep_f.to(weights.dtype))
+        return fused_capacity_combine(out, w, be, plan)
 
 
 @MOE_INITIALIZER.register_module("GShard")

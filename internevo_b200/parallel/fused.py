@@ -78,9 +78,15 @@ class TPFusedBackend:
         gathered = gb.tensor.view(M, K)
         out = torch.empty(M, N, device=x.device, dtype=x.dtype)
         self.flags.barrier()  # the slot is free on every rank (its previous reader is stream-ordered before this)
+        if symm.DEBUG:
+            symm.poison(gathered)
+            self.flags.barrier()
         torch.ops.b200.ag_gemm(x, gb.table_ptr(0), symm.ag_flag_table(self.flags), self.rank, self.world,
                                self.flags.next_epoch(), weight, b_mn, gathered, out, 0, None, self.comm_ctas)
         _bump(2)
+        if symm.DEBUG:
+            symm.assert_clean(gathered, "ag_gemm gathered activations")
+            symm.assert_clean(out, "ag_gemm output")
         return out, (gathered.clone() if keep_gathered else gathered)
 
     # -- GEMM -> reduce-scatter / all-reduce ------------------------------------------------------------------------------
@@ -98,12 +104,21 @@ class TPFusedBackend:
             out = torch.empty(M // self.world, N, device=x.device, dtype=x.dtype)
             out_ptrs = 0
         self.flags.barrier()  # staging / output slots are free on every rank
+        if symm.DEBUG:
+            symm.poison(stage.tensor)
+            if all_reduce:
+                symm.poison(out)
+            self.flags.barrier()
         torch.ops.b200.gemm_rs(x, weight, out, stage.table_ptr(0), out_ptrs, symm.rs_flag_table(self.flags), self.rank,
                                self.world, self.flags.next_epoch(), b_mn, 1 if all_reduce else 0)
         _bump(2)
         if all_reduce:
             self.flags.barrier()  # every rank has pushed its rows into everybody's output
+            if symm.DEBUG:
+                symm.assert_clean(out, "gemm_rs all-reduce output")
             return out.clone()  # detach from the ping-pong slot (it is recycled two calls later)
+        if symm.DEBUG:
+            symm.assert_clean(out, "gemm_rs reduce-scatter output")
         return out
 
 

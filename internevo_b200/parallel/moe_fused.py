@@ -110,10 +110,11 @@ def backend_for(group, hidden: int, max_rows: int, num_experts: int) -> Optional
 
 
 class _Plan:
-    __slots__ = ("slot_rank", "slot_row", "n_recv", "k", "n_tokens")
+    __slots__ = ("slot_rank", "slot_row", "n_recv", "k", "n_tokens", "zero_fill")
 
-    def __init__(self, slot_rank, slot_row, n_recv, k, n_tokens):
+    def __init__(self, slot_rank, slot_row, n_recv, k, n_tokens, zero_fill=False):
         self.slot_rank, self.slot_row, self.n_recv, self.k, self.n_tokens = slot_rank, slot_row, n_recv, k, n_tokens
+        self.zero_fill = zero_fill   # capacity layout: rows nobody writes must read as zero
 
 
 class _FusedDispatch(torch.autograd.Function):
@@ -122,10 +123,18 @@ class _FusedDispatch(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, be: MoEFusedBackend, plan: _Plan):
         ctx.be, ctx.plan = be, plan
+        if plan.zero_fill:
+            be.x_rows(plan.n_recv).zero_()
+            be.flags.barrier()                  # every slab is cleared before the first row arrives
+        elif symm.DEBUG:
+            symm.poison(be.x_rows(plan.n_recv))
+            be.flags.barrier()
         torch.ops.b200.moe_scatter_rows(x, plan.slot_rank, plan.slot_row, None, be.xbuf.table_ptr(0), 0, None, plan.k)
         _bump()
         be.flags.barrier()                      # every peer's rows have landed in my slab
         rows = be.x_rows(plan.n_recv).clone()
+        if symm.DEBUG:
+            symm.assert_clean(rows, "moe dispatch slab")
         be.flags.barrier()                      # nobody overwrites a slab that is still being read
         return rows
 
@@ -151,9 +160,13 @@ class _FusedCombine(torch.autograd.Function):
         be.y_rows(plan.n_recv).copy_(out_rows)
         be.flags.barrier()
         out = torch.empty(plan.n_tokens, be.hidden, dtype=torch.bfloat16, device=out_rows.device)
+        if symm.DEBUG:
+            symm.poison(out)
         torch.ops.b200.moe_gather_combine(out, w, plan.slot_rank, plan.slot_row, be.ybuf.table_ptr(0), plan.k)
         _bump()
         be.flags.barrier()
+        if symm.DEBUG:
+            symm.assert_clean(out, "moe combine output")
         return out
 
     @staticmethod
@@ -162,6 +175,8 @@ class _FusedCombine(torch.autograd.Function):
         out_rows, w = ctx.saved_tensors
         g_out = g_out.contiguous()
         be.y_rows(plan.n_recv).copy_(out_rows)   # the owners publish their outputs again for d(gate weight)
+        if plan.zero_fill:
+            be.x_rows(plan.n_recv).zero_()       # capacity rows nobody routed to receive a zero gradient
         be.flags.barrier()
         dw = torch.empty_like(w)
         torch.ops.b200.moe_scatter_rows(g_out, plan.slot_rank, plan.slot_row, w, be.xbuf.table_ptr(0),
@@ -189,4 +204,18 @@ def fused_dispatch(x2: torch.Tensor, expert_of_slot: torch.Tensor, counts: torch
 
 
 def fused_combine(out_rows: torch.Tensor, w_slots: torch.Tensor, be: MoEFusedBackend, plan: _Plan) -> torch.Tensor:
+    return _FusedCombine.apply(out_rows.contiguous(), w_slots.float().contiguous(), be, plan)
+
+
+def fused_capacity_dispatch(x2: torch.Tensor, slot_rank: torch.Tensor, slot_row: torch.Tensor, be: MoEFusedBackend, k: int,
+                            rows_per_rank: int):
+    """Capacity (GShard) layout: the slab addresses are a pure function of (expert, capacity slot, source rank), so there is
+    no count exchange and no host sync; ``slot_row < 0`` marks a dropped slot."""
+    if rows_per_rank > be.max_rows:
+        raise RuntimeError(f"fused MoE dispatch: slab of {be.max_rows} rows, {rows_per_rank} needed")
+    plan = _Plan(slot_rank.contiguous(), slot_row.contiguous(), rows_per_rank, k, x2.shape[0], zero_fill=True)
+    return _FusedDispatch.apply(x2.contiguous(), be, plan), plan
+
+
+def fused_capacity_combine(out_rows: torch.Tensor, w_slots: torch.Tensor, be: MoEFusedBackend, plan: _Plan) -> torch.Tensor:
     return _FusedCombine.apply(out_rows.contiguous(), w_slots.float().contiguous(), be, plan)

@@ -11,6 +11,7 @@ value ``>=`` the epoch of the operation, so flags never need to be cleared betwe
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List
 
 import torch
@@ -21,6 +22,23 @@ _AG_BASE = 1024              # [1024, 8192): all-gather chunk flags (local)
 _RS_BASE = 8192              # [8192, ...): reduce-scatter tile flags, `world` blocks of tiles each
 RS_FLAG_WORDS = 8 * 8192
 FLAG_WORDS = 8192 + RS_FLAG_WORDS
+
+
+# B200_SYMM_DEBUG=1: race / protocol debugging of the in-kernel peer-memory signalling.  Every back-end
+# poisons the slab it is about to receive into with NaN (after a barrier, so no in-flight reader is disturbed), and
+# asserts after the exchange that nothing it consumes is still poison: a missing flag wait, a wrong slab address or a
+# too-early read shows up as a hard error instead of a silently wrong gradient.  Costs a host sync per exchange.
+DEBUG = os.environ.get("B200_SYMM_DEBUG", "0") == "1"
+
+
+def poison(t: torch.Tensor) -> None:
+    t.fill_(float("nan"))
+
+
+def assert_clean(t: torch.Tensor, what: str) -> None:
+    bad = int(torch.isnan(t.float()).sum())
+    if bad:
+        raise RuntimeError(f"[B200_SYMM_DEBUG] {what}: {bad} of {t.numel()} consumed elements were never written by a peer")
 
 
 def symm_available() -> bool:

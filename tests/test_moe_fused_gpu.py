@@ -10,12 +10,12 @@ from common import run_distributed
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs with NVLink")]
 
 
-def _layer_run(rank, world, fused):
+def _layer_run(rank, world, fused, kind="dropless"):
     import torch.distributed as dist
 
     from internevo_b200 import ops
     from internevo_b200.models.modules import FeedForward
-    from internevo_b200.models.moe import DroplessMOELayer, Experts
+    from internevo_b200.models.moe import DroplessMOELayer, Experts, GShardMOELayer, TopKGate
 
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -26,7 +26,12 @@ def _layer_run(rank, world, fused):
     all_experts = [FeedForward(h, 1024, out_features=h, process_group=None, bias=False, device="cuda", dtype=torch.bfloat16)
                    for _ in range(E)]
     mine = all_experts[rank * El:(rank + 1) * El]
-    layer = DroplessMOELayer(h, E, dist.group.WORLD, world, Experts(mine, El, f"moe_ep_size_{world}"), top_k=k, device="cuda")
+    if kind == "dropless":
+        layer = DroplessMOELayer(h, E, dist.group.WORLD, world, Experts(mine, El, f"moe_ep_size_{world}"), top_k=k,
+                                 device="cuda")
+    else:  # GShard top-2 with capacity 1.0: tokens beyond capacity are dropped (slot row -1 in the fused path)
+        gate = TopKGate(h, E, k, 1.0, 1.0, 4, None, True, True, device="cuda")
+        layer = GShardMOELayer(h, gate, Experts(mine, El, f"moe_ep_size_{world}"), dist.group.WORLD, world, El)
     torch.manual_seed(100 + rank)
     x = (torch.randn(S, h, device="cuda") * 0.5).to(torch.bfloat16).requires_grad_(True)
     n0 = ops.launch_count()
@@ -35,7 +40,8 @@ def _layer_run(rank, world, fused):
     (y.float() * gy.float()).sum().backward()
     torch.cuda.synchronize()
     launches = ops.launch_count() - n0
-    res = dict(y=y.detach().float().cpu(), gx=x.grad.float().cpu(), gwg=layer.wg.weight.grad.float().cpu(),
+    wg = layer.wg if kind == "dropless" else layer.gate.wg
+    res = dict(y=y.detach().float().cpu(), gx=x.grad.float().cpu(), gwg=wg.weight.grad.float().cpu(),
                gexp=[p.grad.float().cpu() if p.grad is not None else getattr(p, "grad_buf", torch.zeros(1)).float().cpu()
                      for e in mine for p in e.parameters()],
                launches=launches)
@@ -48,9 +54,10 @@ def _rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-12))
 
 
-def test_fused_moe_dispatch_combine_matches_nccl():
-    ref = run_distributed(_layer_run, 2, False)
-    got = run_distributed(_layer_run, 2, True)
+@pytest.mark.parametrize("kind", ["dropless", "gshard"])
+def test_fused_moe_dispatch_combine_matches_nccl(kind):
+    ref = run_distributed(_layer_run, 2, False, kind)
+    got = run_distributed(_layer_run, 2, True, kind)
     for r, g in zip(ref, got):
         assert _rel(g["y"], r["y"]) < 2e-2, _rel(g["y"], r["y"])
         assert _rel(g["gx"], r["gx"]) < 2e-2, _rel(g["gx"], r["gx"])

@@ -411,6 +411,74 @@ def check_attn_fwd():
     return ok
 
 
+def check_small():
+    """Every hand-written kernel once on a tiny problem: the workload of ``ci_scripts/sanitize_kernels.sh``
+    (``compute-sanitizer --tool memcheck | racecheck | synccheck | initcheck`` slows kernels 10-100x)."""
+    from internevo_b200.ops.attention import attention_ref, flash_attention_varlen
+
+    torch.manual_seed(0)
+    ok = True
+    # GEMM: all layouts, ragged M / K, every tile variant, epilogues
+    for (M, N, K) in [(200, 264, 136), (256, 512, 64)]:
+        a = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
+        b = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
+        ref = a.float() @ b.float().t()
+        for bn in (128, 256, 512):
+            ok &= err_report(f"NT {M}x{N}x{K} bn{bn}", ops.matmul(a, b, force_bn=bn), ref, 1e-2)
+            if M % 8 == 0:
+                ok &= err_report(f"TN bn{bn}", ops.matmul(a.t().contiguous(), b.t().contiguous(), a_mn=True, b_mn=True,
+                                                         force_bn=bn), ref, 1e-2)
+    a = torch.randn(256, 128, device=dev, dtype=torch.bfloat16)
+    b = torch.randn(512, 128, device=dev, dtype=torch.bfloat16)
+    gu, h = ops.matmul_swiglu(a, b)
+    g, u = gu[:, 0::2].float(), gu[:, 1::2].float()
+    ok &= err_report("swiglu epilogue", h, torch.nn.functional.silu(g) * u, 2e-2)
+    # norms
+    x = torch.randn(67, 1024, device=dev, dtype=torch.bfloat16, requires_grad=True)
+    r = torch.randn(67, 1024, device=dev, dtype=torch.bfloat16)
+    w = torch.ones(1024, device=dev, dtype=torch.bfloat16, requires_grad=True)
+    y, nr = ops.add_rmsnorm(x, r, w, 1e-5)
+    (y.float().sum() + nr.float().sum()).backward()
+    ln = ops.LayerNorm(1024, device=dev, dtype=torch.bfloat16)
+    y2, _ = ln(x, r)
+    y2.float().sum().backward()
+    ok &= err_report("layernorm", y2, torch.nn.functional.layer_norm((x + r).float(), (1024,)), 2e-2)
+    # rope, swiglu, CE, adam, sumsq
+    qkv = torch.randn(67, 6, 128, device=dev, dtype=torch.bfloat16)
+    pos = torch.randint(0, 512, (67,), device=dev, dtype=torch.int32)
+    cos, sin = ops.RotaryTables(128, 1e6).get(512, dev)
+    ops.rope_(qkv, pos, cos, sin, 3, 2, False, False)
+    gu = torch.randn(67, 512, device=dev, dtype=torch.bfloat16, requires_grad=True)
+    ops.swiglu_interleaved(gu).float().sum().backward()
+    lg = torch.randn(67, 1000, device=dev, dtype=torch.bfloat16, requires_grad=True)
+    lb = torch.randint(0, 1000, (67,), device=dev)
+    loss = ops.cross_entropy(lg, lb, inplace_backward=False)
+    loss.sum().backward()
+    ok &= err_report("ce", loss[None], torch.nn.functional.cross_entropy(lg.detach().float(), lb, reduction="none")[None], 1e-3)
+    n = 10_007
+    p, m, v = torch.randn(n, device=dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    gr = torch.randn(n, device=dev).to(torch.bfloat16)
+    ss = torch.zeros(1, device=dev)
+    ops.sumsq_(gr, ss)
+    scal = torch.zeros(4, device=dev)
+    ops.clip_scalars_(ss, scal, 1.0, 1.0)
+    ops.adamw_(p, m, v, gr, torch.empty(n, device=dev, dtype=torch.bfloat16), 1e-3, 0.9, 0.95, 1e-8, 0.1, 1, scal)
+    # attention fwd + bwd, two packed sequences, GQA
+    seqs, H, Hkv, D = [200, 312], 4, 2, 128
+    T = sum(seqs)
+    cu = torch.tensor([0, 200, 512], device=dev, dtype=torch.int32)
+    q = torch.randn(T, H, D, device=dev, dtype=torch.bfloat16, requires_grad=True)
+    k = torch.randn(T, Hkv, D, device=dev, dtype=torch.bfloat16, requires_grad=True)
+    vv = torch.randn(T, Hkv, D, device=dev, dtype=torch.bfloat16, requires_grad=True)
+    out = flash_attention_varlen(q, k, vv, cu, max(seqs), causal=True, impl="b200")
+    out.backward(torch.randn_like(out))
+    ok &= err_report("attn", out.flatten(1), attention_ref(q.detach().float(), k.detach().float(), vv.detach().float(), cu,
+                                                          causal=True).flatten(1), 2e-2)
+    torch.cuda.synchronize()
+    print("SMALL_ALL_OK" if ok else "SMALL_HAS_FAILURES", flush=True)
+    return ok
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
     assert torch.cuda.is_available(), "needs a GPU"
@@ -418,7 +486,7 @@ if __name__ == "__main__":
     print("device", torch.cuda.get_device_name(0), "section", what, flush=True)
     t0 = time.time()
     fn = {"gemm": check_gemm, "gemm_perf": gemm_perf, "elementwise": check_elementwise, "attn": check_attn,
-          "attn_fwd": check_attn_fwd}[what]
+          "attn_fwd": check_attn_fwd, "small": check_small}[what]
     r = fn()
     print(f"section {what} done in {time.time() - t0:.1f}s", flush=True)
     sys.exit(0 if r in (None, True) else 1)
