@@ -129,6 +129,13 @@ def enable_tp(group: Optional[dist.ProcessGroup]) -> Optional[TPFusedBackend]:
     """Create (once) the fused backend for ``group`` and route the TP linears through it."""
     if group is None or dist.get_world_size(group) <= 1 or not symm.symm_available():
         return None
+    # measured (profiles/fused_comm_check_n{2,8}_*.json): ahead of GEMM + NCCL at tp = 2, behind it at tp = 8 where a rank's
+    # slice of a 4096-token micro-batch is only 512 rows and the chunk-granular copy CTAs idle; tp = 4 is untested.
+    # B200_TP_FUSED=1 forces the fused linears for any tp size, =0 disables them.
+    force = os.environ.get("B200_TP_FUSED", "")
+    if force == "0" or (force != "1" and dist.get_world_size(group) > 2):
+        logger.info(f"fused TP linears not enabled for tp={dist.get_world_size(group)} (NCCL + tcgen05 GEMM is faster there)")
+        return None
     key = id(group)
     if key not in _tp_backends:
         _tp_backends[key] = TPFusedBackend(group)

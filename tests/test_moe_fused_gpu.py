@@ -65,3 +65,40 @@ def test_fused_moe_dispatch_combine_matches_nccl(kind):
         for a, b in zip(g["gexp"], r["gexp"]):
             assert _rel(a, b) < 3e-2, _rel(a, b)
         assert g["launches"] > r["launches"]       # the peer-memory kernels really ran
+
+
+def _train_moe(rank, world, fused, moe_type):
+    """A tiny InternLM-MoE model trained through the public API (expert parallel over all ranks, bf16, native kernels)."""
+    from common import build_trainer, synthetic_batch, tiny_config
+
+    os.environ["B200_MOE_FUSED"] = "1" if fused else "0"
+    cfg = tiny_config(model_type="INTERNLM_MoE", num_layers=2, micro_num=2, num_experts=2 * world, moe_type=moe_type,
+                      dtype="torch.bfloat16", hidden=512, heads=4, seq_len=512, micro_bsz=1, vocab=1024)
+    cfg["model"].pop("no_bias", None)
+    cfg["model"].pop("num_kv_attention_heads", None)
+    cfg["moe"] = dict(top_k=2)
+    cfg["loss"]["moe_loss_coeff"] = 0.1
+    trainer, opt, model, _ = build_trainer(cfg)
+    losses = []
+    for step in range(5):
+        data, labels = synthetic_batch(2, 512, 1024, seed=rank)
+        trainer.zero_grad()
+        out = trainer.execute_schedule((data, labels), forward_only=False, return_loss=True, return_output_label=False)
+        ok, norms = trainer.step()
+        assert ok
+        losses.append((float(out[2]), float(list(norms.values())[0])))
+    return losses
+
+
+@pytest.mark.parametrize("moe_type", ["MegaBlock-D", "GShard"])
+def test_moe_training_with_fused_dispatch_tracks_nccl(moe_type):
+    world = int(os.environ.get("B200_TEST_WORLD", "2"))
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    ref = run_distributed(_train_moe, world, False, moe_type)
+    got = run_distributed(_train_moe, world, True, moe_type)
+    for r, g in zip(ref, got):
+        assert g[-1][0] < g[0][0], g                                   # it learns
+        for (l0, n0), (l1, n1) in zip(r, g):
+            assert abs(l0 - l1) < 0.03 * abs(l0) + 0.02, (r, g)        # and follows the NCCL all-to-all run
+            assert abs(n0 - n1) < 0.15 * n0 + 0.05, (r, g)
