@@ -42,6 +42,51 @@ def set_fp32_attr_for_model(model: Union[nn.Module, nn.ModuleList]):
                 set_fp32_attr_to_module(sub)
 
 
+def set_parallel_attr_for_param_groups(model: Union[nn.Module, nn.ModuleList]):
+    """(Re-)tag every parameter with its reduction class: replica (norms, MoE gates), tensor / weight ZeRO-parallel
+    (linears), tensor-data parallel (ISP embedding / head), expert-data parallel (MoE experts) — reference
+    ``internlm/train/pipeline.py:98-154``.  The decoders tag their own parameters at construction
+    (``PackedDecoder._set_param_attrs``); this entry point serves user models assembled from the public modules."""
+    from internevo_b200.core.context import (IS_REPLICA_ZERO_PARALLEL, IS_TENSOR_DATA_PARALLEL,
+                                             IS_TENSOR_EXPERT_DATA_PARALLEL, IS_TENSOR_ZERO_PARALLEL,
+                                             IS_WEIGHT_ZERO_PARALLEL)
+    from internevo_b200.models.modules import Embedding1D, VocabParallelEmbedding
+    from internevo_b200.models.moe import MoE, is_moe_param
+    from internevo_b200.ops.norm import LayerNorm, RMSNorm
+    from internevo_b200.parallel.linear import BaseScaleColumnParallelLinear
+    from internevo_b200.utils.parallel import is_using_isp
+
+    isp = gpc.config is not None and is_using_isp()
+    all_tags = (IS_REPLICA_ZERO_PARALLEL, IS_TENSOR_DATA_PARALLEL, IS_TENSOR_EXPERT_DATA_PARALLEL, IS_TENSOR_ZERO_PARALLEL,
+                IS_WEIGHT_ZERO_PARALLEL)
+
+    def tag(p, name):
+        for t in all_tags:
+            if hasattr(p, t):
+                delattr(p, t)
+        setattr(p, name, True)
+
+    models = model if isinstance(model, nn.ModuleList) else [model]
+    for m in models:
+        m = m.model if hasattr(m, "model") and isinstance(getattr(m, "model"), nn.Module) else m
+        for p in m.parameters():                                   # default class: every linear
+            if is_moe_param(p):
+                tag(p, IS_TENSOR_EXPERT_DATA_PARALLEL)
+            else:
+                tag(p, IS_WEIGHT_ZERO_PARALLEL if isp else IS_TENSOR_ZERO_PARALLEL)
+        for sub in m.modules():
+            if isinstance(sub, (RMSNorm, LayerNorm, nn.LayerNorm)):
+                for p in sub.parameters():
+                    tag(p, IS_REPLICA_ZERO_PARALLEL)
+            elif isinstance(sub, MoE):
+                gate = getattr(sub.moe_layer, "gate", None) or getattr(sub.moe_layer, "wg", None)
+                for p in (gate.parameters() if gate is not None else []):
+                    tag(p, IS_REPLICA_ZERO_PARALLEL)
+            elif isinstance(sub, (Embedding1D, VocabParallelEmbedding, BaseScaleColumnParallelLinear)):
+                for p in sub.parameters():
+                    tag(p, IS_TENSOR_DATA_PARALLEL if isp else IS_TENSOR_ZERO_PARALLEL)
+
+
 @llm_timeout(func_name="initialize_model")
 def initialize_model(pre_process_func: Optional[Callable] = None, post_process_func: Optional[Callable] = None):
     """Build this rank's model chunk(s) from the registry, wrap in ``NaiveAMPModel``, synchronise replicas."""

@@ -155,3 +155,92 @@ def test_nvtx_ranges_are_noops_without_cuda_and_toggle():
     assert nvtx.enabled() == torch.cuda.is_available()
     nvtx.enable(False)
     assert not nvtx.enabled()
+
+
+def test_accelerator_facade_cpu_answers_and_alias():
+    """`internlm.accelerator.get_accelerator()` call surface (reference internlm/accelerator): one implementation, CPU-safe."""
+    import internlm  # noqa: F401  (alias package)
+    from internlm.accelerator import AcceleratorType, get_accelerator
+
+    acc = get_accelerator()
+    assert acc is get_accelerator()
+    if not torch.cuda.is_available():
+        assert acc.get_accelerator_backend() == AcceleratorType.CPU and acc.get_backend_name() == "cpu"
+        assert acc.device_name() == "cpu" and acc.device_count() == 0 and acc.memory_allocated() == 0
+        assert acc.communication_backend_name() == "gloo"
+    else:
+        assert acc.get_accelerator_backend() == AcceleratorType.GPU and acc.communication_backend_name() == "nccl"
+    acc.synchronize()
+    acc.empty_cache()
+    acc.manual_seed(3)
+    st = acc.get_rng_state()
+    acc.set_rng_state(st)
+    assert acc.is_bf16_supported() and acc.FloatTensor([1.0, 2.0]).dtype == torch.float32
+
+
+def test_public_api_surface_importable_through_internlm_alias():
+    """the names user scripts import from `internlm.*` resolve to this framework."""
+    import importlib
+
+    surface = {
+        "internlm": ["initialize_trainer", "launch_from_torch", "launch_from_slurm", "get_default_parser"],
+        "internlm.initialize": ["initialize_distributed_env", "try_bind_numa"],
+        "internlm.core.context": ["global_context", "ParallelMode", "Config", "IS_TENSOR_ZERO_PARALLEL",
+                                  "IS_REPLICA_ZERO_PARALLEL", "IS_WEIGHT_ZERO_PARALLEL", "IS_TENSOR_DATA_PARALLEL",
+                                  "IS_TENSOR_EXPERT_DATA_PARALLEL", "set_mode", "get_seeds", "get_states", "seed",
+                                  "sync_states", "add_seed", "get_current_mode"],
+        "internlm.core.communication": ["recv_forward", "recv_backward", "send_forward", "send_backward",
+                                        "send_forward_recv_backward", "send_backward_recv_forward", "send_obj_meta",
+                                        "recv_obj_meta"],
+        "internlm.core.scheduler": ["BaseScheduler", "NonPipelineScheduler", "PipelineScheduler",
+                                    "InterleavedPipelineScheduler"],
+        "internlm.train": ["initialize_model", "initialize_optimizer", "initialize_isp_communicator", "get_scheduler_hooks",
+                           "load_new_batch", "record_current_batch_training_metrics", "initialize_llm_profile",
+                           "set_fp32_attr_for_model", "set_parallel_attr_for_param_groups", "wrap_FSDP_model"],
+        "internlm.model": ["MHA", "FeedForward", "Embedding1D", "RotaryEmbedding", "MoE", "ScaleColumnParallelLinear",
+                           "BaseScaleColumnParallelLinear", "RewardModelLinear", "AccPerplex", "build_model_with_cfg",
+                           "build_model_with_moe_cfg", "gather_forward_split_backward"],
+        "internlm.solver": ["HybridZeroOptimizer", "Beta2Scheduler", "FineTuneCosineAnnealingWarmupLR"],
+        "internlm.checkpoint": ["CheckpointManager"],
+        "internlm.data": ["build_train_loader_with_data_type", "build_valid_loader_with_data_type"],
+        "internlm.monitor": ["initialize_monitor_manager", "send_alert_message", "send_heartbeat", "set_env_var",
+                             "initialize_light_monitor"],
+        "internlm.utils.registry": ["MODEL_INITIALIZER"],
+        "internlm.utils.common": ["SchedulerHook", "BatchSkipper", "get_megatron_flops", "parse_args", "launch_time",
+                                  "get_current_device", "DummyProfile"],
+        "internlm.accelerator": ["get_accelerator", "AcceleratorType"],
+        "internlm.apis.inference": ["SequenceGenerator"],
+        "internlm.utils.storage_manager": ["get_fns", "llm_load", "llm_save", "init_storage_manager", "get_storage_manager",
+                                           "wait_async_upload_finish"],
+        "internlm.utils.timeout": ["llm_timeout"],
+        "internlm.utils.megatron_timers": ["megatron_timer"],
+        "internlm.model.metrics": ["AccPerplex", "SchedulerMetricHook"],
+        "internlm.model.losses": ["FlashGPTLMLoss"],
+        "internlm.eval.evaluation": ["evaluate_on_val_dls"],
+    }
+    missing = {}
+    for mod, names in surface.items():
+        m = importlib.import_module(mod)
+        miss = [n for n in names if not hasattr(m, n)]
+        if miss:
+            missing[mod] = miss
+    assert not missing, missing
+
+
+def test_set_parallel_attr_for_param_groups_tags_user_model():
+    from internevo_b200 import ops
+    from internevo_b200.core.context import IS_REPLICA_ZERO_PARALLEL, IS_TENSOR_ZERO_PARALLEL
+    from internevo_b200.train import set_parallel_attr_for_param_groups
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.norm = ops.RMSNorm(8)
+            self.ln = ops.LayerNorm(8)
+            self.fc = torch.nn.Linear(8, 8)
+
+    m = Tiny()
+    set_parallel_attr_for_param_groups(m)
+    assert getattr(m.norm.weight, IS_REPLICA_ZERO_PARALLEL) and getattr(m.ln.bias, IS_REPLICA_ZERO_PARALLEL)
+    assert getattr(m.fc.weight, IS_TENSOR_ZERO_PARALLEL) and not hasattr(m.fc.weight, IS_REPLICA_ZERO_PARALLEL)
+    assert not hasattr(m.norm.weight, IS_TENSOR_ZERO_PARALLEL)
