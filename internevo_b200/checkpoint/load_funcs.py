@@ -61,7 +61,7 @@ def load_llama_pretrained_weights(ckpt_mm, load_info, train_state=None):
 
 
 def load_hf_llama_pretrained_weights(ckpt_mm, load_info, train_state=None):
-    """HF format: ``model.layers.{i}.self_attn.{q,k,v,o}_proj``, ``mlp.{gate,up,down}_proj`` (q/k permuted for HF rope)."""
+    """HF format: ``model.layers.{i}.self_attn.{q,k,v,o}_proj``, ``mlp.{gate,up,down}_proj`` (q/k row order depends on ``model.adapt_hf``)."""
     folder = load_info["path"]
     fns = sorted(f for f in get_fns(folder) if f.endswith(".bin") and f.startswith("pytorch_model"))
     hf = {}
@@ -72,7 +72,14 @@ def load_hf_llama_pretrained_weights(ckpt_mm, load_info, train_state=None):
     h = gpc.config.model.hidden_size
     d = h // H
 
-    def unpermute(w, nh):  # HF stores q/k rows as [head, 2, d/2]; ours (non-interleaved rope) wants [head, d/2, 2]→ same as Meta
+    hf_rope = bool(gpc.config.model.get("adapt_hf", False))
+
+    def unpermute(w, nh):
+        """HF stores q/k rows of a head as [2, d/2] (rotate-half RoPE).  With ``adapt_hf=True`` the model rotates the same
+        way and the rows are taken as they are (the reference requires this setting, ``load_funcs.py:74``); with
+        interleaved RoPE (``adapt_hf=False``) they go back to Meta's [d/2, 2] order."""
+        if hf_rope:
+            return w
         return w.view(nh, 2, d // 2, w.shape[-1]).transpose(1, 2).reshape(nh * d, w.shape[-1])
 
     full = {"tok_embeddings.weight": hf["model.embed_tokens.weight"], "norm.weight": hf["model.norm.weight"],

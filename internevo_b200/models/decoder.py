@@ -91,7 +91,7 @@ class DecoderLayer(nn.Module):
                  residual_in_fp32=False, device=None, apply_post_layer_norm=False, no_bias=True, norm_type="rmsnorm",
                  use_scaled_init=True, use_swiglu=True, attn_wqkv_init_std=0.02, attn_other_init_std=0.02,
                  ffn_uplayer_init_std=0.02, ffn_other_init_std=0.02, init_type="normal", rope_base=10000,
-                 tp_mode="mtp", moe_cfg: Optional[dict] = None, adapt_hf=False, dropout_selective_checkpoint=True):
+                 tp_mode="mtp", moe_cfg: Optional[dict] = None, adapt_hf=True, dropout_selective_checkpoint=True):
         super().__init__()
         self.spec, self.checkpoint, self.layer_idx = spec, checkpoint, layer_idx
         self._nvtx_name = f"layer{layer_idx}"
@@ -106,7 +106,7 @@ class DecoderLayer(nn.Module):
         attn = MHA(hidden_size, num_attention_heads, num_kv_attention_heads, process_group=_linear_group(),
                    sequence_process_group=gpc.get_group(ParallelMode.TENSOR), bias=bias, rope_base=rope_base,
                    max_position_embeddings=max_position_embeddings, use_dynamic_ntk_rope=use_dynamic_ntk_rope,
-                   layout=spec.attn_layout, tp_mode=tp_mode, interleaved_rope=adapt_hf, layer_idx=layer_idx,
+                   layout=spec.attn_layout, tp_mode=tp_mode, interleaved_rope=not adapt_hf, layer_idx=layer_idx,
                    device=device, dtype=dtype, dropout=attn_drop_rate)
         setattr(self, spec.attn_name, attn)
         setattr(self, spec.norm1_name, _make_norm(norm_type, hidden_size, layer_norm_epsilon, device, dtype))
@@ -217,7 +217,7 @@ class PackedDecoder(nn.Module):
                  dropout_selective_checkpoint=True, use_scaled_init=True, use_swiglu=True, use_flash_attn=True,
                  apply_post_layer_norm=False, no_bias=True, embedding_init_std=0.02, attn_wqkv_init_std=0.02,
                  attn_other_init_std=0.02, ffn_uplayer_init_std=0.02, ffn_other_init_std=0.02, out_head_init_std=0.02,
-                 init_type="normal", rope_base=10000, norm_head=False, adapt_hf=False, moe_cfg=None, **unused):
+                 init_type="normal", rope_base=10000, norm_head=False, adapt_hf=True, moe_cfg=None, **unused):
         super().__init__()
         self.spec = spec
         self.first, self.last = first, last

@@ -20,7 +20,10 @@ _COMMON = dict(
 _V2_EXTRA = dict(
     num_kv_attention_heads=None, no_bias=True, embedding_init_std=0.02, attn_wqkv_init_std=0.02,
     attn_other_init_std=0.02, ffn_uplayer_init_std=0.02, ffn_other_init_std=0.02, out_head_init_std=0.02,
-    init_type="normal", norm_head=False, adapt_hf=False,
+    init_type="normal", norm_head=False,
+    # adapt_hf=True: rotate-half RoPE (the HF convention, no row permutation on conversion); False: interleaved pairs.
+    # Defaults are the reference's: InternLM2 True (modeling_internlm2.py:1071), LLaMA-2 False (modeling_llama.py:1039).
+    adapt_hf=True,
 )
 
 
@@ -55,7 +58,7 @@ def build_model_with_cfg_internlm2(num_chunks=1, num_layers=48, **kwargs):
 @MODEL_INITIALIZER.register_module("LLAMA2")
 def build_model_with_cfg_llama(num_chunks=1, num_layers=48, **kwargs):
     """LLaMA-2: separate ``wq / wk / wv``."""
-    cfg = _cfg({**_COMMON, **_V2_EXTRA}, kwargs)
+    cfg = _cfg({**_COMMON, **_V2_EXTRA, "adapt_hf": False}, kwargs)
     cfg["num_kv_attention_heads"] = cfg["num_kv_attention_heads"] or cfg["num_attention_heads"]
     return build_generic_model_1d(LLAMA_SPEC, num_layers=num_layers, num_chunks=num_chunks, **cfg)
 

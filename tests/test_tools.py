@@ -117,3 +117,77 @@ def test_hf_roundtrip_llama_names():
     assert "model.layers.1.self_attn.q_proj.weight" in hf and "lm_head.weight" in hf
     back = revert_hf.from_hf(hf, hf_cfg, True)
     assert set(back) == set(ll) and all(torch.equal(back[k], ll[k]) for k in ll)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# generation interface, PAL runtime, MOSS SFT data
+# ---------------------------------------------------------------------------------------------------------------------
+class _CharTok:
+    """Minimal tokenizer double: one id per character (ids 3..), bos 1, eos 2."""
+    eos_token_id, bos_token_id = 2, 1
+
+    def __call__(self, texts, return_tensors=None, **kw):
+        return {"input_ids": torch.tensor([[1] + [3 + (ord(c) % 40) for c in texts[0]]])}
+
+    def encode(self, text, add_special_tokens=True):
+        return ([1] if add_special_tokens else []) + [3 + (ord(c) % 40) for c in text]
+
+    def decode(self, ids, skip_special_tokens=True):
+        return "".join(chr(97 + (i - 3) % 26) for i in ids if i > 2)
+
+
+def test_generate_interactive_streams_greedy_tokens():
+    sys.path.insert(0, ROOT)
+    import interface
+    from huggingface.internlm2_model import InternLM2Config, InternLM2ForCausalLM
+
+    torch.manual_seed(0)
+    m = InternLM2ForCausalLM(InternLM2Config(vocab_size=50, hidden_size=32, intermediate_size=64, num_hidden_layers=2,
+                                             num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=64)).eval()
+    tok = _CharTok()
+    cfg = interface.GenerationConfig(max_new_tokens=6, do_sample=False)
+    chunks = list(interface.generate_interactive(m, tok, "hello", cfg))
+    assert 1 <= len(chunks) <= 6 and all(chunks[i + 1].startswith(chunks[i]) for i in range(len(chunks) - 1))
+    ids = tok(["hello"])["input_ids"]
+    with torch.no_grad():
+        ref = m.generate(ids, max_new_tokens=6, do_sample=False, eos_token_id=2)
+    assert chunks[-1] == tok.decode(ref[0, ids.shape[1]:].tolist())
+    # sampling utilities: top-k = 1 is greedy, repetition penalty demotes seen tokens
+    lg = torch.tensor([1.0, 3.0, 2.0])
+    assert interface.sample_next(lg, [], interface.GenerationConfig(top_k=1, top_p=1.0)) == 1
+    assert interface.sample_next(lg, [1], interface.GenerationConfig(do_sample=False, repetition_penalty=4.0)) == 2
+    kept = interface._filter_logits(torch.tensor([0.0, 5.0, 4.9, -3.0]), 0, 0.6)
+    assert torch.isinf(kept[0]) and torch.isinf(kept[3]) and not torch.isinf(kept[1])
+
+
+def test_pal_runtime_extracts_runs_and_times_out():
+    import pal_inference as pal
+
+    gen = "Sure.\n```python\ndef solution():\n    a = 23 - 5 * 3\n    return a\n```\nDone"
+    code = pal.extract_code(gen)
+    assert code[0].startswith("def solution")
+    assert pal.run_with_timeout(code, time_out=20) == ("ok", 8)
+    assert pal.run_with_timeout(["def solution():", "    while True:", "        pass"], time_out=1.0)[0] == "timeout"
+    assert pal.run_with_timeout(["def solution():", "    return 1 / 0"], time_out=20)[0] == "err"
+    assert pal.gold_answer("blah blah #### 1,234") == 1234.0 and pal.is_correct(8.0004, 8.0) and not pal.is_correct("x", 8.0)
+    iface = pal.PALInterface(lambda prompt: gen, time_out=20)
+    value, g, status = iface.run("Olivia has $23 ...")
+    assert value == 8 and status == "ok" and "How about this question" in pal.PROMPT_HEAD
+
+
+def test_moss_sft_processing_masks_instruction_and_cuts_on_turn_boundary():
+    import moss_002_sft as ms
+
+    tok = _CharTok()
+    sample = {"prefix": "sys:", "num_turns": 3, "plain_text": "<|Human|>: hi<eoh> <|MOSS|>: yo<eoa><|Human|>: a<eoh> <|MOSS|>: b<eoa>"
+              "<|Human|>: c<eoh> <|MOSS|>: dddddddddddddddddddddddddddddddddddddddddddddddd<eoa>"}
+    full = ms.process(sample, tok, 10_000)
+    cut = ms.process(sample, tok, len(full["input_ids"]) - 5)
+    assert full["no_loss_spans"] == [(0, 5)] and len(cut["input_ids"]) < len(full["input_ids"])
+    assert ms.process(sample, tok, 8) == {"input_ids": [], "no_loss_spans": []}
+    ds = ms.SFTDataset([full, cut])
+    data, label = ds[0]
+    assert torch.all(label[:5] == -100) and torch.equal(label[5:], data[5:])
+    batch = ms.collate_fn([ds[0], ds[1]], tok)
+    assert batch["input_ids"].shape == batch["labels"].shape == batch["attention_mask"].shape
+    assert int(batch["attention_mask"][1].sum()) == len(cut["input_ids"]) and batch["labels"][1, -1] == -100

@@ -117,6 +117,35 @@ def save_hf(tensors, hf_cfg, tgt, dtype, max_shard_bytes):
     json.dump(hf_cfg, open(os.path.join(tgt, "config.json"), "w"), indent=1)
 
 
+def install_remote_code(tgt: str, family: str):
+    """Make the folder self-contained for ``from_pretrained(tgt, trust_remote_code=True)``: copy the HF model / tokenizer
+    code of ``huggingface/{family}_model`` next to the weights (flattened: the v1 files import the shared helpers from the
+    InternLM2 files) and register it in ``config.json`` / ``tokenizer_config.json`` (reference
+    ``transformers/convert2hf_internlm2.py:246-262``)."""
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "huggingface")
+    files = ["internlm2_model/configuration_internlm2.py", "internlm2_model/modeling_internlm2.py",
+             "internlm2_model/tokenization_internlm2.py"]
+    if family == "internlm":
+        files += ["internlm_model/configuration_internlm.py", "internlm_model/modeling_internlm.py",
+                  "internlm_model/tokenization_internlm.py"]
+    for f in files:
+        src = open(os.path.join(root, f)).read()
+        src = src.replace("from ..internlm2_model.", "from .")     # one flat folder
+        with open(os.path.join(tgt, os.path.basename(f)), "w") as out:
+            out.write(src)
+    tag = "internlm2" if family == "internlm2" else "internlm"
+    cls = "InternLM2" if family == "internlm2" else "InternLM"
+    cfg_path = os.path.join(tgt, "config.json")
+    cfg = json.load(open(cfg_path))
+    cfg["auto_map"] = {"AutoConfig": f"configuration_{tag}.{cls}Config", "AutoModel": f"modeling_{tag}.{cls}ForCausalLM",
+                       "AutoModelForCausalLM": f"modeling_{tag}.{cls}ForCausalLM"}
+    json.dump(cfg, open(cfg_path, "w"), indent=1)
+    json.dump({"auto_map": {"AutoTokenizer": [f"tokenization_{tag}.{cls}Tokenizer", None]}, "tokenizer_class": f"{cls}Tokenizer",
+               "bos_token": "<s>", "eos_token": "</s>", "unk_token": "<unk>", "pad_token": "</s>", "add_bos_token": True,
+               "add_eos_token": False, "clean_up_tokenization_spaces": False},
+              open(os.path.join(tgt, "tokenizer_config.json"), "w"), indent=1)
+
+
 def main():
     p = argparse.ArgumentParser()
     p.add_argument("--src", required=True)
@@ -137,6 +166,8 @@ def main():
     save_hf(tensors, hf_cfg, a.tgt, getattr(torch, a.dtype), max_bytes)
     if a.tokenizer:
         shutil.copy(a.tokenizer, os.path.join(a.tgt, "tokenizer.model"))
+    if a.family in ("internlm2", "internlm"):
+        install_remote_code(a.tgt, a.family)
     print(f"wrote {len(tensors)} tensors to {a.tgt}")
 
 
