@@ -129,12 +129,14 @@ def enable_tp(group: Optional[dist.ProcessGroup]) -> Optional[TPFusedBackend]:
     """Create (once) the fused backend for ``group`` and route the TP linears through it."""
     if group is None or dist.get_world_size(group) <= 1 or not symm.symm_available():
         return None
-    # measured (profiles/fused_comm_check_n{2,8}_*.json): ahead of GEMM + NCCL at tp = 2, behind it at tp = 8 where a rank's
-    # slice of a 4096-token micro-batch is only 512 rows and the chunk-granular copy CTAs idle; tp = 4 is untested.
-    # B200_TP_FUSED=1 forces the fused linears for any tp size, =0 disables them.
-    force = os.environ.get("B200_TP_FUSED", "")
-    if force == "0" or (force != "1" and dist.get_world_size(group) > 2):
-        logger.info(f"fused TP linears not enabled for tp={dist.get_world_size(group)} (NCCL + tcgen05 GEMM is faster there)")
+    # Opt-in (B200_TP_FUSED=1).  Measured after the 2-CTA (cta_group::2) GEMM became the default for plain GEMMs
+    # (profiles/fused_comm_check_n2_r1_v3.json, profiles/bench_ours_n2_tp2_*): the fused kernels still run the 1-CTA tile, so
+    # only GEMM -> reduce-scatter of wo stays ahead of "2-CTA GEMM + NCCL" (0.095 vs 0.109 ms); all-gather -> GEMM and the
+    # all-reduce forms are behind, and a tp = 2 training step is 3 % slower with them (477.6 vs 463.2 ms).  They remain the
+    # numerically verified basis for a 2-CTA fused variant; Hybrid-ZeRO and MoE dispatch / combine (which do win) are
+    # unaffected by this switch.
+    if os.environ.get("B200_TP_FUSED", "0") != "1":
+        logger.info("fused TP linears are opt-in (B200_TP_FUSED=1); using the 2-CTA tcgen05 GEMM + NCCL")
         return None
     key = id(group)
     if key not in _tp_backends:
