@@ -16,6 +16,7 @@ Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -264,6 +265,8 @@ def run(a, ours: bool):
         out = trainer.execute_schedule(({k: v for k, v in d.items()}, l), forward_only=False, return_loss=True,
                                        return_output_label=False)
         ok, norms = trainer.step()
+        if not ok:  # overflow / non-finite gradients: the optimizer skipped its update -> not the benchmark's work
+            raise RuntimeError(f"bench: optimizer step skipped (non-finite gradients, norms {norms}); measurement invalid")
         return out[2]
 
     def step_e2e(batch):
@@ -288,6 +291,10 @@ def run(a, ours: bool):
                                 global_batch_size=a.micro_bsz * a.micro_num * dp, global_world_size=world,
                                 mlp_ratio=MODEL_7B["mlp_ratio"])
     mem = torch.cuda.max_memory_allocated() / 2**30
+    # a step that produced a non-finite loss did not do the benchmark's work (the optimizer skips it): never report it
+    for name, val in (("device-timed", last), ("e2e", last_e2e)):
+        if val is not None and not math.isfinite(float(val)):
+            raise RuntimeError(f"bench: non-finite loss in the {name} loop ({float(val)}); the measurement is invalid")
     if rank == 0:
         full = a.layers == MODEL_7B["num_layers"] and a.hidden == MODEL_7B["hidden_size"] and a.seq_len == 4096
         res = {

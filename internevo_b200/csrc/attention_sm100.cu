@@ -20,6 +20,7 @@
 #include <math.h>
 
 #include "gemm_sm100.h"
+#include "launch.h"
 #include "sm100_ptx.cuh"
 
 namespace b200 {
@@ -77,6 +78,8 @@ B200_DEVICE float fast_exp2(float x) {
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnKernelArgs args) {
+    griddep_launch_dependents();  // PDL (launch.h)
+    griddep_wait();               // cu_seqlens is read right away: no prologue to overlap here
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::BARS);
@@ -343,7 +346,7 @@ int attn_fwd(const AttnDesc& d, cudaStream_t stream) {
         attr = true;
     }
     dim3 grid(d.H, upper_qblocks(d.T, d.num_seqs, 2 * TM));
-    attn_fwd_kernel<<<grid, FWD_THREADS, FwdSmem::TOTAL, stream>>>(tq, tk, tv, a);
+    launch_pdl(attn_fwd_kernel, dim3(grid), dim3(FWD_THREADS), FwdSmem::TOTAL, stream, 1, tq, tk, tv, a);
     return cudaGetLastError() == cudaSuccess ? 0 : -13;
 }
 
@@ -381,6 +384,8 @@ struct AttnBwdArgs {
 // delta[h, t] = sum_d dO[t,h,d] * O[t,h,d];   lse2[h, t] = lse[h, t] * log2(e)   (stored behind delta: [2, H, T])
 __global__ void attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
                                       const float* __restrict__ lse, float* __restrict__ delta, int T, int H) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per (t, h)
     const int lane = threadIdx.x & 31;
     if (gw >= (int64_t)T * H) return;
@@ -400,6 +405,8 @@ __global__ void attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ dout, co
 // dq (bf16, strided [T, (g, j), D]) = dq_acc (fp32 [T, H, D])
 __global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int T, int H,
                                            int qpk, int64_t st, int64_t sg, int64_t sh, float scale) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 8 elements
     const int64_t n = (int64_t)T * H * (D / 8);
     if (i >= n) return;
@@ -419,6 +426,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
                 const __grid_constant__ CUtensorMap tmap_dq, const AttnBwdArgs args) {
+    griddep_launch_dependents();  // PDL (launch.h)
+    griddep_wait();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BwdSmem::BARS);
@@ -751,7 +760,7 @@ int attn_bwd(const AttnBwdDesc& b, cudaStream_t stream) {
     if (make_tmap_2d_f32_noswizzle(&tdq, b.dq_acc, (uint64_t)d.H * D, d.T, (uint64_t)d.H * D, D, BQ)) return -11;
     {
         const int64_t warps = (int64_t)d.T * d.H;
-        attn_bwd_delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(
+        launch_pdl(attn_bwd_delta_kernel, dim3((unsigned)((warps * 32 + 255) / 256)), dim3(256), 0, stream, 1, 
             (const __nv_bfloat16*)b.dout, (const __nv_bfloat16*)d.o, d.lse, b.delta, d.T, d.H);
     }
     AttnBwdArgs a;
@@ -771,12 +780,12 @@ int attn_bwd(const AttnBwdDesc& b, cudaStream_t stream) {
         attr = true;
     }
     dim3 grid(d.Hkv, upper_qblocks(d.T, d.num_seqs, TN));
-    attn_bwd_kernel<<<grid, BWD_THREADS, BwdSmem::TOTAL, stream>>>(tq, tk, tv, tdo, tdq, a);
+    launch_pdl(attn_bwd_kernel, dim3(grid), dim3(BWD_THREADS), BwdSmem::TOTAL, stream, 1, tq, tk, tv, tdo, tdq, a);
     {
         const int qpk = d.H / d.Hkv;
         const int64_t n = (int64_t)d.T * d.H * (D / 8);
         const int64_t sg = b.dq_stride_g ? b.dq_stride_g : b.dq_stride_h * qpk;
-        attn_bwd_dq_convert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+        launch_pdl(attn_bwd_dq_convert_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, 1, 
             b.dq_acc, (__nv_bfloat16*)b.dq, d.T, d.H, qpk, b.dq_stride_t, sg, b.dq_stride_h, d.scale);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -13;

@@ -12,6 +12,7 @@
 #include <cuda_bf16.h>
 #include <math.h>
 
+#include "launch.h"
 #include "sm100_ptx.cuh"
 
 namespace b200 {
@@ -73,6 +74,8 @@ __global__ void __launch_bounds__(RN_THREADS, RN_MAXV <= 2 ? 3 : 2) rmsnorm_fwd_
                                                                  __nv_bfloat16* __restrict__ res_out,
                                                                  float* __restrict__ rstd_out, int rows, int H,
                                                                  float eps) {
+    griddep_launch_dependents();
+    griddep_wait();
     __shared__ float red[32];
     const int nvec = H / 8;
     for (int row = blockIdx.x; row < rows; row += gridDim.x) {
@@ -126,6 +129,8 @@ __global__ void __launch_bounds__(RN_THREADS, RN_MAXV == 1 ? 4 : (RN_MAXV == 2 ?
                                                                  const __nv_bfloat16* __restrict__ dres,
                                                                  __nv_bfloat16* __restrict__ dx,
                                                                  float* __restrict__ dw_partial, int rows, int H) {
+    griddep_launch_dependents();
+    griddep_wait();
     __shared__ float red[32];
     const int nvec = H / 8;
     float dwacc[RN_MAXV][8];
@@ -198,6 +203,8 @@ __global__ void __launch_bounds__(RN_THREADS, RN_MAXV == 1 ? 4 : (RN_MAXV == 2 ?
 // dw[c] (+)= sum_b partial[b, c]; block = 32 columns x 8 row-groups (coalesced 128-byte rows, H/32 blocks)
 __global__ void colsum_kernel(const float* __restrict__ partial, float* __restrict__ out_f32,
                               __nv_bfloat16* __restrict__ out_bf16, int nblocks, int H, int accumulate) {
+    griddep_launch_dependents();
+    griddep_wait();
     __shared__ float red[8][33];
     const int c = blockIdx.x * 32 + threadIdx.x;
     float s = 0.f;
@@ -218,7 +225,7 @@ int rmsnorm_fwd(const void* x, const void* res_in, const void* w, void* y, void*
     if (H % 8 != 0 || H > RN_THREADS * 8 * 4) return -1;
     const int grid = rows < 148 * 6 ? rows : 148 * 6;
 #define RN_FWD(MV)                                                                                                   \
-    rmsnorm_fwd_kernel<MV><<<grid, RN_THREADS, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res_in,        \
+    launch_pdl(rmsnorm_fwd_kernel<MV>, dim3(grid), dim3(RN_THREADS), 0, s, 1, (const __nv_bfloat16*)x, (const __nv_bfloat16*)res_in,        \
                                                        (const __nv_bfloat16*)w, (__nv_bfloat16*)y,                   \
                                                        (__nv_bfloat16*)res_out, rstd, rows, H, eps)
     if (H <= 2048) RN_FWD(1);
@@ -235,14 +242,14 @@ int rmsnorm_bwd(const void* dy, const void* res, const void* w, const float* rst
     if (H % 8 != 0 || H > RN_THREADS * 8 * 4) return -1;
     const int grid = rmsnorm_bwd_blocks(rows);
 #define RN_BWD(MV)                                                                                                   \
-    rmsnorm_bwd_kernel<MV><<<grid, RN_THREADS, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)res,          \
+    launch_pdl(rmsnorm_bwd_kernel<MV>, dim3(grid), dim3(RN_THREADS), 0, s, 1, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)res,          \
                                                        (const __nv_bfloat16*)w, rstd, (const __nv_bfloat16*)dres,    \
                                                        (__nv_bfloat16*)dx, dw_partial, rows, H)
     if (H <= 2048) RN_BWD(1);
     else if (H <= 4096) RN_BWD(2);
     else RN_BWD(4);
 #undef RN_BWD
-    colsum_kernel<<<(H + 31) / 32, dim3(32, 8), 0, s>>>(dw_partial, dw_f32, (__nv_bfloat16*)dw_bf16, grid, H, accumulate);
+    launch_pdl(colsum_kernel, dim3((H + 31) / 32), dim3(dim3(32, 8)), 0, s, 1, dw_partial, dw_f32, (__nv_bfloat16*)dw_bf16, grid, H, accumulate);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -255,6 +262,8 @@ __global__ void __launch_bounds__(256) rope_kernel(__nv_bfloat16* __restrict__ x
                                                    const float* __restrict__ cos_t, const float* __restrict__ sin_t,
                                                    int T, int heads, int D, int64_t stride_t, int group,
                                                    int rot_per_group, int rot_heads, float sign, int interleaved) {
+    griddep_launch_dependents();
+    griddep_wait();
     // one thread per 8 rotation pairs (16 elements: 2 x 16 B of x, 2 x 32 B of the tables); only rotating heads are
     // enumerated, so v never costs an instruction: item -> (token, rotating head index, chunk)
     const int chunks = D / 16;
@@ -315,7 +324,7 @@ int rope_inplace(void* x, const int* pos, const float* cos_t, const float* sin_t
     int64_t blocks = (items + threads - 1) / threads;
     if (blocks > 148 * 32) blocks = 148 * 32;
     if (blocks == 0) return 0;
-    rope_kernel<<<(unsigned)blocks, threads, 0, s>>>((__nv_bfloat16*)x, pos, cos_t, sin_t, T, heads, D, stride_t, group,
+    launch_pdl(rope_kernel, dim3((unsigned)blocks), dim3(threads), 0, s, 1, (__nv_bfloat16*)x, pos, cos_t, sin_t, T, heads, D, stride_t, group,
                                                      rot_per_group, rot_heads, conj ? -1.f : 1.f, interleaved);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
@@ -324,6 +333,8 @@ int rope_inplace(void* x, const int* pos, const float* cos_t, const float* sin_t
 // SwiGLU on interleaved (gate, up) columns: gu [rows, 2F] -> h [rows, F];  bwd: dgu from dh, gu
 // ----------------------------------------------------------------------------------------------------------------
 __global__ void swiglu_fwd_kernel(const uint4* __restrict__ gu, uint2* __restrict__ h, int64_t nvec) {
+    griddep_launch_dependents();
+    griddep_wait();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
         float f[8];
         unpack8(gu[i], f);
@@ -337,6 +348,8 @@ __global__ void swiglu_fwd_kernel(const uint4* __restrict__ gu, uint2* __restric
 }
 __global__ void swiglu_bwd_kernel(const uint2* __restrict__ dh, const uint4* __restrict__ gu, uint4* __restrict__ dgu,
                                   int64_t nvec) {
+    griddep_launch_dependents();
+    griddep_wait();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
         float f[8], o[8];
         unpack8(gu[i], f);
@@ -356,6 +369,8 @@ __global__ void swiglu_bwd_kernel(const uint2* __restrict__ dh, const uint4* __r
 // dpre = dh * d/dx gelu_tanh(pre)
 __global__ void gelu_bwd_kernel(const uint4* __restrict__ dh, const uint4* __restrict__ pre, uint4* __restrict__ dpre,
                                 int64_t nvec) {
+    griddep_launch_dependents();
+    griddep_wait();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
         float x[8], d[8], o[8];
         unpack8(pre[i], x);
@@ -375,7 +390,7 @@ int gelu_bwd(const void* dh, const void* pre, void* dpre, int64_t n, cudaStream_
     const int64_t nvec = n / 8;
     const int blocks = (int)((nvec + 255) / 256 < 148 * 16 ? (nvec + 255) / 256 : 148 * 16);
     if (blocks == 0) return 0;
-    gelu_bwd_kernel<<<blocks, 256, 0, s>>>((const uint4*)dh, (const uint4*)pre, (uint4*)dpre, nvec);
+    launch_pdl(gelu_bwd_kernel, dim3(blocks), dim3(256), 0, s, 1, (const uint4*)dh, (const uint4*)pre, (uint4*)dpre, nvec);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -383,14 +398,14 @@ int swiglu_fwd(const void* gu, void* h, int64_t rows, int64_t F, cudaStream_t s)
     if (F % 4 != 0) return -1;
     const int64_t nvec = rows * F / 4;
     const int blocks = (int)((nvec + 255) / 256 < 148 * 16 ? (nvec + 255) / 256 : 148 * 16);
-    swiglu_fwd_kernel<<<blocks, 256, 0, s>>>((const uint4*)gu, (uint2*)h, nvec);
+    launch_pdl(swiglu_fwd_kernel, dim3(blocks), dim3(256), 0, s, 1, (const uint4*)gu, (uint2*)h, nvec);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 int swiglu_bwd(const void* dh, const void* gu, void* dgu, int64_t rows, int64_t F, cudaStream_t s) {
     if (F % 4 != 0) return -1;
     const int64_t nvec = rows * F / 4;
     const int blocks = (int)((nvec + 255) / 256 < 148 * 16 ? (nvec + 255) / 256 : 148 * 16);
-    swiglu_bwd_kernel<<<blocks, 256, 0, s>>>((const uint2*)dh, (const uint4*)gu, (uint4*)dgu, nvec);
+    launch_pdl(swiglu_bwd_kernel, dim3(blocks), dim3(256), 0, s, 1, (const uint2*)dh, (const uint4*)gu, (uint4*)dgu, nvec);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -405,6 +420,8 @@ __global__ void __launch_bounds__(CE_THREADS) ce_fwd_kernel(const __nv_bfloat16*
                                                             const int64_t* __restrict__ labels, int V, int vocab_start,
                                                             float* __restrict__ out_max, float* __restrict__ out_sum,
                                                             float* __restrict__ out_sumx, float* __restrict__ out_tgt) {
+    griddep_launch_dependents();
+    griddep_wait();
     __shared__ float red[32];
     const int row = blockIdx.x;
     const __nv_bfloat16* x = logits + (int64_t)row * ld;
@@ -448,6 +465,8 @@ __global__ void __launch_bounds__(CE_THREADS) ce_bwd_kernel(__nv_bfloat16* __res
                                                             const float* __restrict__ lse,
                                                             const float* __restrict__ gscale, int V, int vocab_start,
                                                             float smoothing, int total_classes, int ignore_index) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int row = blockIdx.x;
     __nv_bfloat16* x = logits + (int64_t)row * ld;
     const int64_t label = labels[row];
@@ -477,14 +496,14 @@ __global__ void __launch_bounds__(CE_THREADS) ce_bwd_kernel(__nv_bfloat16* __res
 int ce_fwd(const void* logits, int64_t ld, const int64_t* labels, int rows, int V, int vocab_start, float* out_max,
            float* out_sum, float* out_sumx, float* out_tgt, cudaStream_t s) {
     if (ld % 8 != 0) return -1;
-    ce_fwd_kernel<<<rows, CE_THREADS, 0, s>>>((const __nv_bfloat16*)logits, ld, labels, V, vocab_start, out_max, out_sum,
+    launch_pdl(ce_fwd_kernel, dim3(rows), dim3(CE_THREADS), 0, s, 1, (const __nv_bfloat16*)logits, ld, labels, V, vocab_start, out_max, out_sum,
                                               out_sumx, out_tgt);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 int ce_bwd(void* logits, int64_t ld, const int64_t* labels, const float* lse, const float* gscale, int rows, int V,
            int vocab_start, float smoothing, int total_classes, int ignore_index, cudaStream_t s) {
     if (ld % 8 != 0) return -1;
-    ce_bwd_kernel<<<rows, CE_THREADS, 0, s>>>((__nv_bfloat16*)logits, ld, labels, lse, gscale, V, vocab_start, smoothing,
+    launch_pdl(ce_bwd_kernel, dim3(rows), dim3(CE_THREADS), 0, s, 1, (__nv_bfloat16*)logits, ld, labels, lse, gscale, V, vocab_start, smoothing,
                                               total_classes, ignore_index);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
@@ -498,6 +517,8 @@ template <typename G>
 __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
                              const G* __restrict__ g, __nv_bfloat16* __restrict__ p_lp, int64_t n, float lr, float beta1,
                              float beta2, float eps, float wd, float bc1, float bc2, const float* __restrict__ scalars) {
+    griddep_launch_dependents();
+    griddep_wait();
     const float mult = scalars ? scalars[0] : 1.f;
     if (scalars && scalars[1] != 0.f) return;
     const int64_t n4 = n / 4;
@@ -556,10 +577,10 @@ int adamw_step(float* p, float* m, float* v, const void* g, int g_is_bf16, void*
     const int64_t want = (n / 4 + 255) / 256;
     const int blocks = (int)(want < 148 * 8 ? (want > 0 ? want : 1) : 148 * 8);
     if (g_is_bf16)
-        adamw_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(p, m, v, (const __nv_bfloat16*)g, (__nv_bfloat16*)p_lp, n, lr,
+        launch_pdl(adamw_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, s, 1, p, m, v, (const __nv_bfloat16*)g, (__nv_bfloat16*)p_lp, n, lr,
                                                            beta1, beta2, eps, wd, bc1, bc2, scalars);
     else
-        adamw_kernel<float><<<blocks, 256, 0, s>>>(p, m, v, (const float*)g, (__nv_bfloat16*)p_lp, n, lr, beta1, beta2,
+        launch_pdl(adamw_kernel<float>, dim3(blocks), dim3(256), 0, s, 1, p, m, v, (const float*)g, (__nv_bfloat16*)p_lp, n, lr, beta1, beta2,
                                                    eps, wd, bc1, bc2, scalars);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
@@ -569,6 +590,8 @@ int adamw_step(float* p, float* m, float* v, const void* g, int g_is_bf16, void*
 // ----------------------------------------------------------------------------------------------------------------
 template <typename G>
 __global__ void sumsq_kernel(const G* __restrict__ g, int64_t n, float* __restrict__ out) {
+    griddep_launch_dependents();
+    griddep_wait();
     __shared__ float red[32];
     float acc = 0.f;
     constexpr int VEC = 16 / sizeof(G);
@@ -601,14 +624,16 @@ int sumsq(const void* g, int is_bf16, int64_t n, float* out, cudaStream_t s) {
     if (n == 0) return 0;
     const int64_t want = (n / 8 + 255) / 256;
     const int blocks = (int)(want < 148 * 4 ? (want > 0 ? want : 1) : 148 * 4);
-    if (is_bf16) sumsq_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)g, n, out);
-    else sumsq_kernel<float><<<blocks, 256, 0, s>>>((const float*)g, n, out);
+    if (is_bf16) launch_pdl(sumsq_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, s, 1, (const __nv_bfloat16*)g, n, out);
+    else launch_pdl(sumsq_kernel<float>, dim3(blocks), dim3(256), 0, s, 1, (const float*)g, n, out);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 // scalars[0] = 1 / (loss_scale * max(1, norm/clip)) ; scalars[1] = overflow flag; scalars[2] = norm (unscaled)
 __global__ void clip_scalars_kernel(const float* __restrict__ sumsq_in, float* __restrict__ scalars, float loss_scale,
                                     float clip) {
+    griddep_launch_dependents();
+    griddep_wait();
     const float ss = *sumsq_in;
     const bool bad = !(ss == ss) || isinf(ss);
     const float norm = sqrtf(ss) / loss_scale;
@@ -622,7 +647,7 @@ __global__ void clip_scalars_kernel(const float* __restrict__ sumsq_in, float* _
     scalars[2] = bad ? -1.f : norm;
 }
 int clip_scalars(const float* sumsq_in, float* scalars, float loss_scale, float clip, cudaStream_t s) {
-    clip_scalars_kernel<<<1, 1, 0, s>>>(sumsq_in, scalars, loss_scale, clip);
+    launch_pdl(clip_scalars_kernel, dim3(1), dim3(1), 0, s, 1, sumsq_in, scalars, loss_scale, clip);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -642,6 +667,8 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const __nv_bfloat16* _
                                                           __nv_bfloat16* __restrict__ out, float* __restrict__ work,
                                                           unsigned int* __restrict__ tickets, int H, int Hkv, int seqlen,
                                                           int64_t stride_b, int64_t stride_s, float scale_log2) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int split = blockIdx.x, nsplit = gridDim.x, hk = blockIdx.y, b = blockIdx.z;
     const int qpk = H / Hkv;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -751,7 +778,7 @@ int attn_decode(const void* q, const void* kc, const void* vc, void* out, float*
     const int qpk = H / Hkv;
     const int warps = qpk < 8 ? qpk : 8;
     dim3 grid(nsplit, Hkv, B);
-    attn_decode_kernel<<<grid, warps * 32, 0, s>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)kc,
+    launch_pdl(attn_decode_kernel, dim3(grid), dim3(warps * 32), 0, s, 1, (const __nv_bfloat16*)q, (const __nv_bfloat16*)kc,
                                                   (const __nv_bfloat16*)vc, (__nv_bfloat16*)out, work, tickets, H, Hkv,
                                                   seqlen, stride_b, stride_s, scale * 1.4426950408889634f);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;

@@ -16,6 +16,7 @@
 #include <mutex>
 #include <unordered_map>
 
+#include "launch.h"
 #include "sm100_ptx.cuh"
 
 namespace b200 {
@@ -196,6 +197,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                  const __grid_constant__ CUtensorMap tmap_bt, const GemmKernelArgs args, const CommKernelArgs comm) {
     static_assert(CG == 1 || (!COMM && BN == 256), "2-CTA tiles: plain GEMM, BN = 256");
     using Cfg = GemmCfg<BN, CG>;
+    griddep_launch_dependents();  // PDL (launch.h): the next kernel's CTAs may take over SMs this grid's tail has left
     const int cta_rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -238,6 +240,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<CG>(tmem_base_smem, Cfg::TMEM_COLS);
+    griddep_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
     tc_fence_before();
     if constexpr (CG == 2) cluster_sync();  // the peer's barriers are initialised before anything signals them
     else __syncthreads();
@@ -772,25 +775,9 @@ static int launch(const GemmDesc& g, cudaStream_t stream) {
         }
         attr_set = true;
     }
-    cudaError_t e;
-    if constexpr (CG == 1) {
-        gemm_bf16_kernel<BN, false, 1><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tbt, a, CommKernelArgs{});
-        e = cudaGetLastError();
-    } else {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid * CG);
-        cfg.blockDim = dim3(NUM_THREADS);
-        cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = CG;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, false, CG>, ta, tb, tbt, a, CommKernelArgs{});
-    }
+    // PDL launch (launch.h); CG = 2 adds the cluster dimension of the CTA pair
+    cudaError_t e = launch_pdl(gemm_bf16_kernel<BN, false, CG>, dim3(grid * CG), dim3(NUM_THREADS), Cfg::SMEM_BYTES, stream, CG,
+                               ta, tb, tbt, a, CommKernelArgs{});
     if (e != cudaSuccess) {
         fprintf(stderr, "[b200] gemm launch failed: %s\n", cudaGetErrorString(e));
         return -4;

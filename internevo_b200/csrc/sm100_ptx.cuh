@@ -283,6 +283,10 @@ B200_DEVICE uint4 ld_nc_v4(const void* p) {
     return r;
 }
 
+// programmatic dependent launch (see launch.h): no-ops for grids launched without the attribute
+B200_DEVICE void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+B200_DEVICE void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 B200_DEVICE uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
