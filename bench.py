@@ -230,7 +230,7 @@ def run(a, ours: bool):
         import torch
         import torch.distributed as dist
         import internlm as fw  # the unmodified reference package
-        from internlm.core.context import ParallelMode, global_context as gpc
+        from internlm.core.context import global_context as gpc
         from internlm.initialize import initialize_distributed_env
         from internlm.model.losses import FlashGPTLMLoss
         from internlm.model.metrics import AccPerplex

@@ -7,8 +7,7 @@ plain-PyTorch inference / fine-tuning model (SDPA attention, HF ``DynamicCache``
 ``internevo_b200.models`` with the sm_100a kernels.  ``tests/test_hf_models.py`` checks that both produce the same logits
 from the same weights.
 """
-import math
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 import torch.nn.functional as F

@@ -1,7 +1,6 @@
 """Packed dataset / sampler behaviour (reference semantics: ``tests/test_data/test_batch_sampler.py`` and the
 ``PackedDatasetWithCut`` docstring example)."""
 import numpy as np
-import torch
 
 from internevo_b200.core.context import Config
 from internevo_b200.core.context import global_context as gpc

@@ -2,7 +2,6 @@
 `test_timeout`, on CPU / gloo with 2 ranks: hidden-split embedding, gather / split autograd pairs, reward head,
 fp32-tagged modules under NaiveAMPModel + fp32 optimizer group, replica (norm) weights staying identical across the tensor
 group after training, and a hung collective being turned into an error by the process-group timeout."""
-import os
 import time
 
 import pytest
