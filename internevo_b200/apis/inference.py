@@ -1,7 +1,9 @@
 """Text generation on top of a trained model: greedy / sampling (top-k, top-p, temperature, repetition penalty), beam
 search and token streaming with a per-layer KV cache (reference ``internlm/apis/inference.py:13-966``).
 
-The decode path runs through ``MHA._forward_decode`` (KV cache + library SDPA): generation is not a training hot path.
+The decode path runs through ``MHA._forward_decode``: prefill uses the training flash-attention kernel, decode steps the
+split-KV kernel over the KV cache; greedy / sampling generation replays ONE captured CUDA graph per token (``DecodeGraph``:
+the position lives on the device, so nothing in a step depends on the host).  Masked batches and CPU use library SDPA.
 """
 from __future__ import annotations
 
@@ -12,6 +14,10 @@ import torch.nn.functional as F
 from torch import nn
 
 __all__ = ["SequenceGenerator", "InferenceParams", "top_k_top_p_filtering", "BeamHypotheses"]
+
+from internevo_b200.utils.logger import get_logger
+
+logger = get_logger(__file__)
 
 
 class InferenceParams:
@@ -27,6 +33,7 @@ class InferenceParams:
         self.fused_ft_kernel: bool = False
         self.lengths_per_sample = lengths_per_sample
         self.attention_mask = attention_mask
+        self.graph_pos = None   # cuda int32 [1]: current position on the device while a CUDA-graph decode is active
 
     def reorder_state(self, indices):
         """Beam search: permute the batch dimension of every cached tensor."""
@@ -93,6 +100,53 @@ class BeamHypotheses:
         if self.early_stopping:
             return True
         return self.worst_score >= best_sum_logprobs / self.max_length**self.length_penalty
+
+
+class DecodeGraph:
+    """One decode step of the whole model (embedding → L layers → head) captured in a CUDA graph.
+
+    A decode step is ~10 launches per layer of kernels that run for a few microseconds each: launch-bound.  The step is
+    made capture-safe by keeping the position on the device (``InferenceParams.graph_pos``: RoPE positions, the KV-cache
+    row and the split-KV attention length all read it, see ``MHA._forward_decode_graph``); the graph ends by incrementing
+    it, so a replay needs one tiny copy (the new token ids) and nothing else from the host.
+    Used by greedy / sampling generation on one tensor-parallel rank without an attention mask; anything else (and any
+    capture failure) keeps the eager path."""
+
+    def __init__(self, decoder, params: "InferenceParams", batch: int, device):
+        self.params = params
+        self.tok = torch.zeros(batch, 1, dtype=torch.long, device=device)
+        params.graph_pos = torch.full((1,), params.sequence_len_offset, dtype=torch.int32, device=device)
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):          # warm-up outside capture: lazy allocations, RoPE tables, workspaces
+            for _ in range(2):
+                decoder(input_ids=self.tok, inference_params=params)
+        torch.cuda.current_stream(device).wait_stream(side)
+        params.graph_pos.fill_(params.sequence_len_offset)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.logits = _logits_of(decoder(input_ids=self.tok, inference_params=params))[:, -1]
+            params.graph_pos += 1
+
+    @staticmethod
+    def usable(decoder, params: "InferenceParams", device) -> bool:
+        import os
+
+        from internevo_b200.core.context import ParallelMode
+        from internevo_b200.core.context import global_context as gpc
+
+        if os.environ.get("B200_DECODE_GRAPH", "1") == "0" or device.type != "cuda" or params.attention_mask is not None:
+            return False
+        if gpc.is_initialized(ParallelMode.TENSOR) and gpc.get_world_size(ParallelMode.TENSOR) > 1:
+            return False
+        p = next(decoder.parameters())
+        return p.dtype == torch.bfloat16
+
+    def step(self, tokens: torch.Tensor) -> torch.Tensor:
+        self.tok.copy_(tokens)
+        self.graph.replay()
+        self.params.sequence_len_offset += 1
+        return self.logits
 
 
 def _logits_of(out):
@@ -176,9 +230,19 @@ def _no_beam_search(gen: SequenceGenerator, tokens, max_length, temperature, top
     done = torch.zeros(B, dtype=torch.bool, device=device)
     seq = tokens
     cur = tokens
-    for _ in range(L0, max_length):
-        scores = gen._step_logits(cur, params)
-        params.sequence_len_offset += cur.shape[1]
+    graph = None
+    for step in range(L0, max_length):
+        if graph is not None:
+            scores = graph.step(cur)
+        else:
+            scores = gen._step_logits(cur, params)
+            params.sequence_len_offset += cur.shape[1]
+            if step == L0 and max_length - L0 > 2 and DecodeGraph.usable(gen.decoder, params, device):
+                try:                           # prefill done (eager); the remaining steps replay one captured graph
+                    graph = DecodeGraph(gen.decoder, params, B, device)
+                except Exception as e:         # noqa: BLE001 - capture is an optimisation, never a requirement
+                    params.graph_pos = None
+                    logger.warning(f"CUDA-graph decode unavailable ({type(e).__name__}: {e}); using eager steps")
         scores = gen._apply_penalty(scores, seq, repetition_penalty)
         if do_sample:
             if temperature > 0 and temperature != 1:

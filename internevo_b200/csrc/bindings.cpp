@@ -157,16 +157,20 @@ void swiglu_fwd(const Tensor& gu, Tensor& h) {
 }
 // one decode step: q [B, H, D] against the first `seqlen` positions of the caches [B, Smax, Hkv, D]
 void attn_decode(const Tensor& q, const Tensor& kcache, const Tensor& vcache, Tensor& out, Tensor& work, Tensor& tickets,
-                 int64_t seqlen, int64_t nsplit, double scale) {
+                 int64_t seqlen, int64_t nsplit, double scale, const optional<Tensor>& seqlen_dev) {
     CHECK_BF16(q); CHECK_BF16(kcache); CHECK_BF16(vcache); CHECK_BF16(out);
     TORCH_CHECK(q.dim() == 3 && q.is_contiguous() && out.is_contiguous() && kcache.dim() == 4, "attn_decode: shapes");
     const int64_t B = q.size(0), H = q.size(1), D = q.size(2), Hkv = kcache.size(2);
     TORCH_CHECK(kcache.stride(3) == 1 && kcache.stride(2) == D && vcache.strides() == kcache.strides(), "attn_decode: cache layout");
     TORCH_CHECK(work.scalar_type() == at::kFloat && work.numel() >= B * H * nsplit * (D + 4), "attn_decode: work size");
     TORCH_CHECK(tickets.scalar_type() == at::kInt && tickets.numel() >= B * Hkv, "attn_decode: tickets");
+    if (seqlen_dev.has_value())
+        TORCH_CHECK(seqlen_dev->is_cuda() && seqlen_dev->scalar_type() == at::kInt && seqlen_dev->numel() >= 1,
+                    "attn_decode: seqlen_dev must be a cuda int32 tensor");
     c10::cuda::CUDAGuard guard(q.device());
     CHECK_RC(b200::attn_decode(q.data_ptr(), kcache.data_ptr(), vcache.data_ptr(), out.data_ptr(), work.data_ptr<float>(),
-                               reinterpret_cast<unsigned int*>(tickets.data_ptr<int>()), B, H, Hkv, D, seqlen, nsplit,
+                               reinterpret_cast<unsigned int*>(tickets.data_ptr<int>()), B, H, Hkv, D, seqlen,
+                               seqlen_dev.has_value() ? seqlen_dev->data_ptr<int>() : nullptr, nsplit,
                                kcache.stride(0), kcache.stride(1), static_cast<float>(scale), cur_stream()),
              "b200::attn_decode");
 }
@@ -469,7 +473,7 @@ TORCH_LIBRARY(b200, m) {
     m.def("swiglu_fwd(Tensor gu, Tensor(a!) h) -> ()", &swiglu_fwd);
     m.def("swiglu_bwd(Tensor dh, Tensor gu, Tensor(a!) dgu) -> ()", &swiglu_bwd);
     m.def("gelu_bwd(Tensor dh, Tensor pre, Tensor(a!) dpre) -> ()", &gelu_bwd);
-    m.def("attn_decode(Tensor q, Tensor kcache, Tensor vcache, Tensor(a!) out, Tensor(b!) work, Tensor(c!) tickets, int seqlen, int nsplit, float scale) -> ()", &attn_decode);
+    m.def("attn_decode(Tensor q, Tensor kcache, Tensor vcache, Tensor(a!) out, Tensor(b!) work, Tensor(c!) tickets, int seqlen, int nsplit, float scale, Tensor? seqlen_dev=None) -> ()", &attn_decode);
     m.def("ce_fwd(Tensor logits, Tensor labels, int vocab_start, Tensor(a!) out_max, Tensor(b!) out_sum, Tensor(c!) out_sumx, Tensor(d!) out_tgt) -> ()", &ce_fwd);
     m.def("ce_bwd(Tensor(a!) logits, Tensor labels, Tensor lse, Tensor gscale, int vocab_start, float smoothing, int total_classes, int ignore_index) -> ()", &ce_bwd);
     m.def("adamw(Tensor(a!) p, Tensor(b!) m, Tensor(c!) v, Tensor g, Tensor? p_lp, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2, Tensor? scalars) -> ()", &adamw);

@@ -665,10 +665,14 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const __nv_bfloat16* _
                                                           const __nv_bfloat16* __restrict__ kc,
                                                           const __nv_bfloat16* __restrict__ vc,
                                                           __nv_bfloat16* __restrict__ out, float* __restrict__ work,
-                                                          unsigned int* __restrict__ tickets, int H, int Hkv, int seqlen,
-                                                          int64_t stride_b, int64_t stride_s, float scale_log2) {
+                                                          unsigned int* __restrict__ tickets, int H, int Hkv, int seqlen_host,
+                                                          const int* __restrict__ seqlen_dev, int64_t stride_b,
+                                                          int64_t stride_s, float scale_log2) {
     griddep_launch_dependents();
     griddep_wait();
+    // CUDA-graph decode: the number of valid cache positions lives on the device (`*seqlen_dev + seqlen_host`), so one
+    // captured launch serves every step; splits beyond the current length simply contribute empty partials
+    const int seqlen = seqlen_dev != nullptr ? *seqlen_dev + seqlen_host : seqlen_host;
     const int split = blockIdx.x, nsplit = gridDim.x, hk = blockIdx.y, b = blockIdx.z;
     const int qpk = H / Hkv;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -773,14 +777,15 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const __nv_bfloat16* _
 }
 
 int attn_decode(const void* q, const void* kc, const void* vc, void* out, float* work, unsigned int* tickets, int B, int H,
-                int Hkv, int D, int seqlen, int nsplit, int64_t stride_b, int64_t stride_s, float scale, cudaStream_t s) {
-    if (D != DEC_D || H % Hkv != 0 || seqlen <= 0) return -1;
+                int Hkv, int D, int seqlen, const int* seqlen_dev, int nsplit, int64_t stride_b, int64_t stride_s, float scale,
+                cudaStream_t s) {
+    if (D != DEC_D || H % Hkv != 0 || (seqlen_dev == nullptr && seqlen <= 0)) return -1;
     const int qpk = H / Hkv;
     const int warps = qpk < 8 ? qpk : 8;
     dim3 grid(nsplit, Hkv, B);
     launch_pdl(attn_decode_kernel, dim3(grid), dim3(warps * 32), 0, s, 1, (const __nv_bfloat16*)q, (const __nv_bfloat16*)kc,
                                                   (const __nv_bfloat16*)vc, (__nv_bfloat16*)out, work, tickets, H, Hkv,
-                                                  seqlen, stride_b, stride_s, scale * 1.4426950408889634f);
+                                                  seqlen, seqlen_dev, stride_b, stride_s, scale * 1.4426950408889634f);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

@@ -23,7 +23,8 @@ int rope_inplace(void* x, const int* pos, const float* cos_t, const float* sin_t
 
 int swiglu_fwd(const void* gu, void* h, int64_t rows, int64_t F, cudaStream_t s);
 int attn_decode(const void* q, const void* kc, const void* vc, void* out, float* work, unsigned int* tickets, int B, int H,
-                int Hkv, int D, int seqlen, int nsplit, int64_t stride_b, int64_t stride_s, float scale, cudaStream_t s);
+                int Hkv, int D, int seqlen, const int* seqlen_dev, int nsplit, int64_t stride_b, int64_t stride_s, float scale,
+                cudaStream_t s);
 int gelu_bwd(const void* dh, const void* pre, void* dpre, int64_t n, cudaStream_t s);
 int swiglu_bwd(const void* dh, const void* gu, void* dgu, int64_t rows, int64_t F, cudaStream_t s);
 

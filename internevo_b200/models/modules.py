@@ -271,6 +271,9 @@ class MHA(nn.Module):
         split-KV kernel; masked (left-padded) batches and CPU use library SDPA."""
         B, S, _ = x.shape
         D = self.head_dim
+        gpos = getattr(inference_params, "graph_pos", None)
+        if gpos is not None and S == 1:
+            return self._forward_decode_graph(x, inference_params, gpos)
         off = inference_params.sequence_len_offset
         pos = torch.arange(off, off + S, device=x.device, dtype=torch.int32).repeat(B)
         q, k, v = self._qkv(x.reshape(B * S, -1), pos, off + S)
@@ -313,6 +316,25 @@ class MHA(nn.Module):
                                            scale=self.softmax_scale, enable_gqa=q.shape[2] != kk.shape[2])
         o = o.transpose(1, 2).reshape(B, S, -1)
         return proj(o)
+
+
+    def _forward_decode_graph(self, x, inference_params, gpos):
+        """Decode step whose position lives on the device (``gpos``: cuda int32 ``[1]``): nothing in it depends on a host
+        value that changes from step to step, so the whole model step can be captured once in a CUDA graph and replayed
+        (``apis/inference.py::DecodeGraph``).  RoPE positions, the KV-cache row and the attention length all read ``gpos``."""
+        from internevo_b200.ops.attention import decode_attention
+
+        B = x.shape[0]
+        D = self.head_dim
+        q, k, v = self._qkv(x.reshape(B, -1), gpos.expand(B).contiguous(), inference_params.max_sequence_len)
+        kc, vc = inference_params.key_value_memory_dict[self.layer_idx]
+        b0 = inference_params.batch_size_offset
+        row = gpos.to(torch.int64)
+        kc[b0:b0 + B].index_copy_(1, row, k.reshape(B, 1, -1, D))
+        vc[b0:b0 + B].index_copy_(1, row, v.reshape(B, 1, -1, D))
+        o = decode_attention(q.reshape(B, -1, D), kc[b0:b0 + B], vc[b0:b0 + B], 1, self.softmax_scale, seqlen_dev=gpos)
+        proj = self.out_proj if self.layout == "internlm" else self.wo
+        return proj(o.reshape(B, 1, -1))
 
 
 # ----------------------------------------------------------------------------------------------------------------

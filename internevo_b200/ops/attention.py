@@ -176,15 +176,20 @@ _decode_ws = {}
 
 
 def decode_attention(q: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, seqlen: int,
-                     scale: Optional[float] = None) -> torch.Tensor:
+                     scale: Optional[float] = None, seqlen_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     """One generation step: ``q [B, H, D]`` attends to the first ``seqlen`` cache positions (``[B, Smax, Hkv, D]``).
-    Native split-KV kernel for bf16 / D = 128, library SDPA otherwise."""
+    Native split-KV kernel for bf16 / D = 128, library SDPA otherwise.
+
+    ``seqlen_dev`` (cuda int32 ``[1]``): the valid length is ``seqlen_dev[0] + seqlen`` read ON THE DEVICE — the form used
+    inside a captured CUDA graph, where one launch must serve every decode step (the split count is then sized for the
+    whole cache; splits beyond the current length produce empty partials)."""
     B, H, D = q.shape
     Hkv = kcache.shape[2]
     scale = scale or 1.0 / math.sqrt(D)
     if q.is_cuda and q.dtype == torch.bfloat16 and D == 128 and _b200_available():
         ctas = B * Hkv
-        nsplit = max(1, min(32, (2 * 148 + ctas - 1) // ctas, (seqlen + 63) // 64))
+        span = kcache.shape[1] if seqlen_dev is not None else seqlen
+        nsplit = max(1, min(32, (2 * 148 + ctas - 1) // ctas, (span + 63) // 64))
         key = (q.device, B, H, nsplit)
         ws = _decode_ws.get(key)
         if ws is None:
@@ -192,9 +197,11 @@ def decode_attention(q: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor
                   torch.zeros(B * Hkv, device=q.device, dtype=torch.int32))
             _decode_ws[key] = ws
         out = torch.empty_like(q)
-        torch.ops.b200.attn_decode(q.contiguous(), kcache, vcache, out, ws[0], ws[1], int(seqlen), nsplit, float(scale))
+        torch.ops.b200.attn_decode(q.contiguous(), kcache, vcache, out, ws[0], ws[1], int(seqlen), nsplit, float(scale),
+                                   seqlen_dev)
         _bump()
         return out
+    assert seqlen_dev is None, "device-side sequence length needs the native decode kernel"
     kk, vv = kcache[:, :seqlen].transpose(1, 2), vcache[:, :seqlen].transpose(1, 2)
     o = torch.nn.functional.scaled_dot_product_attention(q[:, :, None], kk, vv, scale=scale, enable_gqa=H != Hkv)
     return o[:, :, 0]
