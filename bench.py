@@ -39,6 +39,7 @@ def parse():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--tp", type=int, default=0, help="tensor parallel size (0 = BASELINE layout: tp 1, ZeRO-1 over all N ranks, as configs/7B_internlm2.py)")
     p.add_argument("--tp-mode", default="mtp")
+    p.add_argument("--wp", type=int, default=1, help="weight parallel size (tp-mode isp)")
     p.add_argument("--seq-len", type=int, default=4096)
     p.add_argument("--micro-bsz", type=int, default=1)
     p.add_argument("--micro-num", type=int, default=4)
@@ -78,7 +79,7 @@ def build_config(a, world):
         use_fp32_norm=False, model=model,
         parallel=dict(zero1=dict(size=dp), tensor=dict(size=tp, mode=a.tp_mode),
                       pipeline=dict(size=1, interleaved_overlap=True),
-                      weight=dict(size=1, overlap=True, memory_pool=True)),
+                      weight=dict(size=a.wp, overlap=True, memory_pool=True)),
         cudnn_deterministic=False, cudnn_benchmark=False, enable_tb=False,
         monitor=dict(alert=dict(enable_feishu_alert=False, feishu_alert_address=None, light_monitor_address=None,
                                 alert_file_path=None), tensorboard=dict(queue_max_length=10)),
