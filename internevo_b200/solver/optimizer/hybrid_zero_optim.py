@@ -22,7 +22,6 @@ Redesign (what changes on a B200 node):
 """
 from __future__ import annotations
 
-import math
 import os
 from typing import Dict, List, Optional
 
@@ -34,7 +33,6 @@ from internevo_b200.core.context import (
     IS_REPLICA_ZERO_PARALLEL,
     IS_TENSOR_DATA_PARALLEL,
     IS_TENSOR_EXPERT_DATA_PARALLEL,
-    IS_WEIGHT_ZERO_PARALLEL,
     ParallelMode,
 )
 from internevo_b200.core.context import global_context as gpc
@@ -511,6 +509,3 @@ class HybridZeroOptimizer:
         self.flush_param_update()
         for g in self.groups:
             g.master.copy_(g.param_arena[g.lo: g.hi])
-
-    def _unused(self):
-        return math, IS_WEIGHT_ZERO_PARALLEL
