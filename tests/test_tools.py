@@ -191,3 +191,38 @@ def test_moss_sft_processing_masks_instruction_and_cuts_on_turn_boundary():
     batch = ms.collate_fn([ds[0], ds[1]], tok)
     assert batch["input_ids"].shape == batch["labels"].shape == batch["attention_mask"].shape
     assert int(batch["attention_mask"][1].sum()) == len(cut["input_ids"]) and batch["labels"][1, -1] == -100
+
+
+def test_openai_api_chat_completions_and_streaming(sp_model):
+    """`/v1/models`, `/v1/chat/completions` (plain and SSE streaming) over a tiny random model: OpenAI response schema,
+    `max_tokens` counts generated tokens, streamed deltas concatenate to a complete message."""
+    import sentencepiece as spm
+    from fastapi.testclient import TestClient
+
+    import openai_api
+    from load_internlm_model import initialize_internlm_model
+
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29661")
+    cfg = dict(num_layers=2, hidden_size=64, num_attention_heads=4, num_kv_attention_heads=2, vocab_size=64, mlp_ratio=2.0,
+               embed_split_hidden=False, no_bias=True, norm_type="rmsnorm", layer_norm_epsilon=1e-5, use_flash_attn=True,
+               max_position_embeddings=256)
+    torch.manual_seed(0)
+    sp = spm.SentencePieceProcessor()
+    sp.Load(sp_model[0])
+    openai_api.STATE.update(model=initialize_internlm_model("INTERNLM2_PUBLIC", None, cfg, param_dtype=torch.float32),
+                            tokenizer=sp, name="tiny")
+    client = TestClient(openai_api.app)
+    assert client.get("/v1/models").json()["data"][0]["id"] == "tiny"
+    body = {"model": "tiny", "messages": [{"role": "system", "content": "be brief"}, {"role": "user", "content": "alpha beta"}],
+            "max_tokens": 6, "temperature": 0.0}
+    r = client.post("/v1/chat/completions", json=body).json()
+    assert r["object"] == "chat.completion" and r["choices"][0]["message"]["role"] == "assistant"
+    assert r["choices"][0]["finish_reason"] == "stop" and isinstance(r["choices"][0]["message"]["content"], str)
+    prompt = openai_api.build_prompt([openai_api.Message(**m) for m in body["messages"]])
+    assert prompt.startswith("<|System|>:be brief\n<|User|>:alpha beta<eoh>\n") and prompt.endswith("<|Bot|>:")
+    with client.stream("POST", "/v1/chat/completions", json=dict(body, stream=True)) as resp:
+        lines = [ln for ln in resp.iter_lines() if ln.startswith("data: ")]
+    assert lines[-1] == "data: [DONE]" and 1 <= len(lines) - 1 <= 6          # at most max_tokens chunks
+    deltas = [json.loads(ln[6:])["choices"][0]["delta"]["content"] for ln in lines[:-1]]
+    assert "".join(deltas) == r["choices"][0]["message"]["content"]           # greedy: streaming == non-streaming

@@ -88,14 +88,18 @@ def get_model_device(model):
 @torch.inference_mode()
 def internlm_interactive_generation(model, tokenizer, prompt: str, additional_eos_token_list=None, max_length: int = 512,
                                     do_sample: bool = True, temperature: float = 1.0, top_k: int = 50, top_p: float = 1.0,
-                                    repetition_penalty: float = 1.0, length_penalty: float = 1.0):
-    """Yields the decoded text after every generated token (streaming)."""
+                                    repetition_penalty: float = 1.0, length_penalty: float = 1.0,
+                                    max_new_tokens: int = None):
+    """Yields the decoded text after every generated token (streaming).  ``max_length`` counts prompt + generated tokens
+    (the reference's convention); ``max_new_tokens`` (OpenAI's ``max_tokens``) counts generated tokens only."""
     ids = tokenizer.encode(prompt)
     bos, eos = tokenizer.bos_id(), tokenizer.eos_id()
     tokens = torch.tensor([[bos] + list(ids)], device=get_model_device(model))
     gen = SequenceGenerator(decoder=model, eos_token_id=eos, pad_token_id=bos, bos_token_id=bos,
                             additional_eos_token_list=additional_eos_token_list)
     n_prompt = tokens.shape[1]
+    if max_new_tokens is not None:
+        max_length = n_prompt + max(1, int(max_new_tokens))
     for out in gen.streaming_generate(tokens=tokens, max_length=max_length, do_sample=do_sample, temperature=temperature,
                                       top_k=top_k, top_p=top_p, repetition_penalty=repetition_penalty,
                                       length_penalty=length_penalty):

@@ -48,7 +48,7 @@ def build_prompt(messages: List[Message]) -> str:
 def _stream(prompt, req):
     from load_internlm_model import internlm_interactive_generation
 
-    return internlm_interactive_generation(STATE["model"], STATE["tokenizer"], prompt, max_length=req.max_tokens or 512,
+    return internlm_interactive_generation(STATE["model"], STATE["tokenizer"], prompt, max_new_tokens=req.max_tokens or 512,
                                            temperature=max(req.temperature, 1e-3), top_p=req.top_p,
                                            do_sample=req.temperature > 0,
                                            additional_eos_token_list=STATE.get("extra_eos"))
