@@ -84,7 +84,9 @@ def run_flow(tmp_path, gpu: bool):
                      "--master-port", str(port), "train.py", "--config", str(cfg), "--launcher", "torch", "--backend",
                      "nccl" if gpu else "gloo"], ROOT, timeout=900, env=env)
 
-    launch(8, 29651)
+    from common import find_free_port
+
+    launch(8, find_free_port())
     saved = sorted(int(d) for d in os.listdir(ckpt) if d.isdigit())
     assert saved == [4, 8], os.listdir(ckpt)
     files = set(os.listdir(ckpt / "8"))
@@ -92,7 +94,7 @@ def run_flow(tmp_path, gpu: bool):
             "schedulder.pt", "model_config.pt"} <= files, files
 
     # ---- 3. second launch: auto-resume from step 8, run to 12
-    log = launch(12, 29652)
+    log = launch(12, find_free_port())
     assert "12" in [d for d in os.listdir(ckpt)], os.listdir(ckpt)
     assert "resum" in log.lower() or "load" in log.lower()
 
