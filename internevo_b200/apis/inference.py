@@ -139,6 +139,8 @@ class DecodeGraph:
             return False
         if gpc.is_initialized(ParallelMode.TENSOR) and gpc.get_world_size(ParallelMode.TENSOR) > 1:
             return False
+        if any(type(m).__name__ == "MoE" for m in decoder.modules()):
+            return False   # MoE routing reads slab sizes on the host: not capturable
         p = next(decoder.parameters())
         return p.dtype == torch.bfloat16
 
