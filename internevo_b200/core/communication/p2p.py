@@ -53,7 +53,8 @@ def _split_1d(t: torch.Tensor) -> torch.Tensor:
 def _gather_1d(t: torch.Tensor, shape) -> torch.Tensor:
     tp = gpc.get_world_size(ParallelMode.TENSOR)
     out = torch.empty(t.numel() * tp, dtype=t.dtype, device=t.device)
-    dist.all_gather_into_tensor(out, t.contiguous(), group=gpc.get_group(ParallelMode.TENSOR))
+    with torch.no_grad():  # the receive buffer is a leaf that requires grad; the collective itself is not differentiated
+        dist.all_gather_into_tensor(out, t.detach().contiguous(), group=gpc.get_group(ParallelMode.TENSOR))
     return out.view(shape).requires_grad_()
 
 

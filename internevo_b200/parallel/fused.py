@@ -223,7 +223,10 @@ class ZeroFusedBackend:
             else:
                 opt._sync_grads(g)
         for g in active:
-            ops.clip_scalars_(self._sumsq(opt, g), g.scalars, scale, opt._clip_grad_norm)
+            self._sumsq(opt, g)
+        opt._reduce_sumsq_over_pipeline(active)   # one vector all-reduce over the union of group names (no-op without PP)
+        for g in active:
+            ops.clip_scalars_(g.sumsq, g.scalars, scale, opt._clip_grad_norm)
         if len(active) > 1:
             flag = torch.stack([g.scalars[1] for g in active]).max()
             for g in active:
@@ -280,6 +283,4 @@ class ZeroFusedBackend:
         dist.all_reduce(g.sumsq, group=gpc.get_group(g.zero_mode))
         if gpc.get_world_size(model_mode) > 1:
             dist.all_reduce(g.sumsq, group=gpc.get_group(model_mode))
-        if gpc.get_world_size(ParallelMode.PIPELINE) > 1:
-            dist.all_reduce(g.sumsq, group=gpc.get_group(ParallelMode.PIPELINE))
         return g.sumsq

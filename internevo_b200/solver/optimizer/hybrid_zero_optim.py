@@ -170,6 +170,7 @@ class HybridZeroOptimizer:
         self._owner_seen: Dict[int, int] = {}        # id(module) -> update generation it has already waited for
         self._update_gen = 0
         self._model_attached = False
+        self._pp_group_names = None   # union of parameter-group names over the pipeline group (agreed at the first step)
 
     # ------------------------------------------------------------------------------------------------------------
     def _modes_for_group(self, pg, params):
@@ -257,8 +258,9 @@ class HybridZeroOptimizer:
         del zero_group
 
     def _group_sumsq(self, g: _GroupState) -> torch.Tensor:
-        """Σ grad² of the owned slice with replica parameters counted only on tp/wp rank 0, reduced over the ZeRO,
-        tensor(weight) and pipeline groups (reference ``compute_norm``, ``optimizer/utils.py:265-378``)."""
+        """Σ grad² of the owned slice with replica parameters counted only on tp/wp rank 0, reduced over the ZeRO and
+        tensor (weight) groups (reference ``compute_norm``, ``optimizer/utils.py:265-378``).  The sum over pipeline stages
+        is done for all groups at once by ``_reduce_sumsq_over_pipeline``."""
         g.sumsq.zero_()
         owned = g.owned_grad()
         rep_lo = max(g.replica_start, g.lo) - g.lo
@@ -278,9 +280,30 @@ class HybridZeroOptimizer:
                 dist.all_reduce(g.sumsq, group=gpc.get_group(ParallelMode.EXPERT))
         if _group_size(model_mode) > 1 and not (self.use_isp and g.dp_mode is ParallelMode.DATA):
             dist.all_reduce(g.sumsq, group=gpc.get_group(model_mode))
-        if _group_size(ParallelMode.PIPELINE) > 1:
-            dist.all_reduce(g.sumsq, group=gpc.get_group(ParallelMode.PIPELINE))
         return g.sumsq
+
+    def _reduce_sumsq_over_pipeline(self, active) -> None:
+        """Add the per-group Σ grad² of all pipeline stages.  Stages own different parameter groups (under ISP the embedding
+        group exists on the first stage only, MoE / fp32 groups only where such layers live), so the reduction runs over the
+        UNION of group names - agreed once over the pipeline group - as ONE vector all-reduce: every stage issues the same
+        collective whatever it owns (a per-group all-reduce would dead-lock as soon as two stages disagree)."""
+        if _group_size(ParallelMode.PIPELINE) <= 1:
+            return
+        group = gpc.get_group(ParallelMode.PIPELINE)
+        if self._pp_group_names is None:
+            gathered = [None] * _group_size(ParallelMode.PIPELINE)
+            dist.all_gather_object(gathered, [g.name for g in self.groups if g.params], group=group)
+            self._pp_group_names = sorted({n for names in gathered for n in names})
+        by_name = {g.name: g for g in active}
+        dev = active[0].sumsq.device if active else self.device
+        vec = torch.zeros(len(self._pp_group_names), dtype=torch.float32, device=dev)
+        for i, n in enumerate(self._pp_group_names):
+            if n in by_name:
+                vec[i:i + 1] = by_name[n].sumsq
+        dist.all_reduce(vec, group=group)
+        for i, n in enumerate(self._pp_group_names):
+            if n in by_name:
+                by_name[n].sumsq.copy_(vec[i:i + 1])
 
     def _update(self, g: _GroupState):
         cfg = g.cfg
@@ -422,10 +445,12 @@ class HybridZeroOptimizer:
         timer("sync_grad").stop()
         timer("step").start()
         scale = self.grad_scaler.scale
-        for g in self.groups:
-            if not g.params:
-                continue
-            ops.clip_scalars_(self._group_sumsq(g), g.scalars, scale, self._clip_grad_norm)
+        active = [g for g in self.groups if g.params]
+        for g in active:
+            self._group_sumsq(g)
+        self._reduce_sumsq_over_pipeline(active)
+        for g in active:
+            ops.clip_scalars_(g.sumsq, g.scalars, scale, self._clip_grad_norm)
         # overflow anywhere must skip every group: fold the flags (tiny device op), still no host sync
         if len(self.groups) > 1:
             flag = torch.stack([g.scalars[1] for g in self.groups if g.params]).max()

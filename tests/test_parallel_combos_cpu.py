@@ -1,0 +1,49 @@
+"""Combined layouts on CPU / gloo (4 ranks): every combination must reproduce the single-process trajectory of
+``tests/test_parallel_cpu.py`` — TP x PP (1F1B and interleaved), ISP x PP, DP x PP with ZeRO, activation checkpointing under
+PP, sequence-parallel TP with ZeRO off, ISP with weight parallel + data parallel."""
+import pytest
+
+import test_parallel_cpu as T
+from common import run_distributed
+
+
+@pytest.fixture(scope="module")
+def baseline():
+    return run_distributed(T._train, 1, dict(micro_num=T.MICRO_TOTAL))[0]
+
+
+COMBOS = {
+    "tp2_pp2_mtp": (4, dict(tp=2, pp=2, micro_num=4)),
+    "tp2_pp2_msp_interleaved": (4, dict(tp=2, pp=2, mode="msp", micro_num=4, num_chunks=2)),
+    "isp_sp2_wp2_pp2": (4, dict(tp=2, wp=2, pp=2, mode="isp", micro_num=4)),
+    "dp2_pp2_zero": (4, dict(pp=2, micro_num=2)),
+    "ckpt_pp2": (2, dict(pp=2, micro_num=4, checkpoint=True)),
+    "fsp_tp2_dp2_zero_off": (4, dict(tp=2, mode="fsp", micro_num=2, zero1=1)),
+}
+
+
+def _check_union(res, baseline, tol=2e-4):
+    """Like ``test_parallel_cpu._check`` but with the gradient norms merged over the ranks: under pipeline parallelism a
+    parameter group may live on one stage only (ISP keeps the embedding in its own group on the first stage)."""
+    ref_losses, ref_norms = baseline
+    got = [r for r in res if r[0][0] is not None]
+    assert got, "no rank reported a loss"
+    for losses, _ in got:
+        for a, b in zip(losses, ref_losses):
+            assert abs(a - b) < tol * max(1.0, abs(b)), (losses, ref_losses)
+    merged = {}
+    for _, norms in res:
+        for k, v in norms.items():
+            merged[k] = max(merged.get(k, 0.0), v)
+    total = sum(v * v for v in merged.values()) ** 0.5
+    ref_total = sum(v * v for v in ref_norms.values()) ** 0.5
+    assert abs(total - ref_total) < 1e-3 * max(1.0, ref_total), (merged, ref_norms)
+
+
+@pytest.mark.parametrize("name", list(COMBOS))
+def test_combined_layout_matches_single_process(baseline, name):
+    world, kw = COMBOS[name]
+    # ISP clips the embedding in its own parameter group (as the reference does); with Adam the trajectory then differs from
+    # the single-group baseline by a few 1e-4 after some steps (step 1 is exact: Adam is invariant to the gradient scale)
+    tol = 6e-4 if kw.get("mode") == "isp" else 2e-4
+    _check_union(run_distributed(T._train, world, kw, timeout=600), baseline, tol)
