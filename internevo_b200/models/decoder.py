@@ -272,7 +272,8 @@ class PackedDecoder(nn.Module):
         for name, p in self.named_parameters():
             if getattr(p, "is_expert", False):
                 setattr(p, IS_TENSOR_EXPERT_DATA_PARALLEL, True)
-            elif "norm" in name.split(".")[-2] or ".gate." in name or name.endswith("gate.weight"):
+            elif ("norm" in name.split(".")[-2] or ".gate." in name or name.endswith("gate.weight")
+                  or name.endswith(".wg.weight") or name.endswith("coefficient.weight") or name.endswith("coefficient.bias")):
                 setattr(p, IS_REPLICA_ZERO_PARALLEL, True)
             elif isp and (self.spec.embed_name in name):
                 setattr(p, IS_TENSOR_DATA_PARALLEL, True)

@@ -87,6 +87,7 @@ class _GroupState:
         for p in rep:
             self.offsets[id(p)] = off
             off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.replica_end = off     # [replica_start, replica_end): same SIZE on every tensor rank (offsets may differ)
         quantum = self.zero_size * 1024
         self.total = max(quantum, (off + quantum - 1) // quantum * quantum)
         self.shard = self.total // self.zero_size
@@ -237,9 +238,18 @@ class HybridZeroOptimizer:
         if not is_using_sequence_parallel() and not self.use_isp:
             return
         mode = ParallelMode.WEIGHT if self.use_isp else ParallelMode.TENSOR
-        if _group_size(mode) <= 1 or g.replica_start >= g.total:
+        if _group_size(mode) <= 1:
             return
-        rep = g.grad_arena[g.replica_start:]
+        if g.dp_mode is ParallelMode.EXPERT_DATA and not self.use_isp:
+            # experts are replicated over the tensor group (they are not tensor-sharded here); under sequence parallelism each
+            # tensor rank routed a different sequence shard through them, so their gradients are partial sums as well
+            dist.all_reduce(g.grad_arena, group=gpc.get_group(mode))
+            return
+        if g.replica_start >= g.replica_end:
+            return
+        # the slice ends at the last replica parameter: the tail padding and the START offset may differ between tensor ranks
+        # (a row-parallel bias lives on tensor rank 0 only), the replica region itself has the same size everywhere
+        rep = g.grad_arena[g.replica_start: g.replica_end]
         if self.use_isp:
             _all_reduce_avg(rep, mode)
         else:
@@ -278,7 +288,8 @@ class HybridZeroOptimizer:
         if g.dp_mode is ParallelMode.EXPERT_DATA:
             if _group_size(ParallelMode.EXPERT) > 1:
                 dist.all_reduce(g.sumsq, group=gpc.get_group(ParallelMode.EXPERT))
-        if _group_size(model_mode) > 1 and not (self.use_isp and g.dp_mode is ParallelMode.DATA):
+        replicated_experts = g.dp_mode is ParallelMode.EXPERT_DATA and not self.use_isp   # same gradient on every tensor rank
+        if _group_size(model_mode) > 1 and not (self.use_isp and g.dp_mode is ParallelMode.DATA) and not replicated_experts:
             dist.all_reduce(g.sumsq, group=gpc.get_group(model_mode))
         return g.sumsq
 

@@ -1,4 +1,5 @@
 """MoE: gating semantics (capacity, renormalised top-2 weights, l_aux) and expert-parallel training on CPU/gloo."""
+import pytest
 import torch
 
 from common import build_trainer, run_distributed, synthetic_batch, tiny_config
@@ -170,3 +171,92 @@ def test_fused_dispatch_slot_plan_matches_all_to_all_order():
         for s in range(S * k):
             want[s // k] += weights[r][s] * xs[r][s // k] * (int(experts[r][s]) + 1)
         assert torch.allclose(got, want, atol=1e-5)
+
+
+def _train_moe_tp(rank, world, kw):
+    """MoE under tensor parallelism (experts and gates are replicated over the tensor group, not sharded): returns the loss
+    trajectory and whether every replicated parameter is still bit-identical on all tensor ranks after training."""
+    import torch.distributed as dist
+
+    from internevo_b200.core.context import ParallelMode
+    from internevo_b200.core.context import global_context as gpc
+
+    kw = dict(kw)
+    moe_type = kw.pop("moe_type", "MegaBlock-D")
+    cfg = tiny_config(model_type="INTERNLM_MoE", num_layers=2, micro_num=2, num_experts=4, moe_type=moe_type, **kw)
+    cfg["model"].pop("no_bias", None)
+    cfg["model"].pop("num_kv_attention_heads", None)
+    cfg["moe"] = dict(top_k=2)
+    cfg["loss"]["moe_loss_coeff"] = 0.1
+    trainer, opt, model, _ = build_trainer(cfg)
+    T = cfg["data"]["seq_len"] * cfg["data"]["micro_bsz"]
+    losses = []
+    for step in range(4):
+        data, labels = synthetic_batch(2, T, cfg["model"]["vocab_size"], seed=0)
+        trainer.zero_grad()
+        out = trainer.execute_schedule((data, labels), forward_only=False, return_loss=True, return_output_label=False)
+        ok, _ = trainer.step()
+        assert ok
+        losses.append(float(out[2]) if out[2] is not None else None)
+    same = True
+    group = gpc.get_group(ParallelMode.TENSOR)
+    for name, p in model.named_parameters():
+        if getattr(p, "is_expert", False) or name.endswith("wg.weight") or "norm" in name:
+            both = [torch.empty_like(p.data) for _ in range(gpc.get_world_size(ParallelMode.TENSOR))]
+            dist.all_gather(both, p.data.contiguous(), group=group)
+            same &= all(torch.equal(both[0], b) for b in both[1:])
+    return losses, same
+
+
+@pytest.mark.parametrize("kw", [dict(tp=2), dict(tp=2, mode="msp"), dict(tp=2, mode="fsp", moe_type="GShard"),
+                                dict(tp=2, pp=2)], ids=["mtp", "msp_dropless", "fsp_gshard", "mtp_pp2"])
+def test_moe_under_tensor_parallel_keeps_replicas_identical(kw):
+    """Regressions: (1) the replica gradient all-reduce used a slice whose size differed between tensor ranks when a
+    row-parallel bias lives on rank 0 only (v1 blocks); (2) the dropless gate was not tagged as a replica; (3) replicated
+    experts were initialised from the per-rank tensor RNG stream and never reduced under sequence parallelism."""
+    world = 4 if kw.get("pp", 1) > 1 else 2
+    res = run_distributed(_train_moe_tp, world, kw, timeout=600)
+    reported = [r for r in res if r[0][0] is not None]
+    assert reported and all(r[1] for r in res), [r[1] for r in res]
+    for losses, _ in reported:
+        assert losses == reported[0][0]                 # tensor ranks see the same loss
+        assert losses[-1] < losses[0]
+
+
+def _train_v1_tp(rank, world, mode):
+    import torch.distributed as dist
+
+    from internevo_b200.core.context import ParallelMode
+    from internevo_b200.core.context import global_context as gpc
+
+    cfg = tiny_config(model_type="INTERNLM", num_layers=2, micro_num=2, tp=2, mode=mode)
+    cfg["model"].pop("no_bias", None)
+    cfg["model"].pop("num_kv_attention_heads", None)
+    trainer, opt, model, _ = build_trainer(cfg)
+    T = cfg["data"]["seq_len"] * cfg["data"]["micro_bsz"]
+    losses = []
+    for step in range(4):
+        data, labels = synthetic_batch(2, T, cfg["model"]["vocab_size"], seed=0)
+        trainer.zero_grad()
+        out = trainer.execute_schedule((data, labels), forward_only=False, return_loss=True, return_output_label=False)
+        ok, _ = trainer.step()
+        assert ok
+        losses.append(float(out[2]))
+    same = True
+    for name, p in model.named_parameters():
+        if "norm" in name:
+            both = [torch.empty_like(p.data) for _ in range(2)]
+            dist.all_gather(both, p.data.contiguous(), group=gpc.get_group(ParallelMode.TENSOR))
+            same &= torch.equal(both[0], both[1])
+    n_params = sum(1 for _ in model.parameters())
+    return losses, same, n_params
+
+
+@pytest.mark.parametrize("mode", ["msp", "fsp"])
+def test_internlm_v1_bias_blocks_under_sequence_parallel(mode):
+    """InternLM v1 blocks carry biases; the row-parallel bias exists on tensor rank 0 only, so the ranks' gradient arenas
+    have different layouts - the replica (norm) gradient all-reduce must still line up."""
+    res = run_distributed(_train_v1_tp, 2, mode, timeout=600)
+    assert res[0][2] != res[1][2]                       # the premise: different parameter counts per tensor rank
+    assert res[0][0] == res[1][0] and res[0][0][-1] < res[0][0][0]
+    assert res[0][1] and res[1][1]
