@@ -238,12 +238,18 @@ class HybridZeroOptimizer:
         if not is_using_sequence_parallel() and not self.use_isp:
             return
         mode = ParallelMode.WEIGHT if self.use_isp else ParallelMode.TENSOR
-        if _group_size(mode) <= 1:
+        if g.dp_mode is ParallelMode.EXPERT_DATA:
+            # experts are replicated over the tensor (sequence) group - they are neither tensor- nor weight-sharded here; under
+            # sequence parallelism each of those ranks routed a different sequence shard through them, so their gradients are
+            # partial: summed for msp / fsp (the loss is normalised over the full sequence), averaged for isp (every rank
+            # normalises over its own shard)
+            if _group_size(ParallelMode.TENSOR) > 1:
+                if self.use_isp:
+                    _all_reduce_avg(g.grad_arena, ParallelMode.TENSOR)
+                else:
+                    dist.all_reduce(g.grad_arena, group=gpc.get_group(ParallelMode.TENSOR))
             return
-        if g.dp_mode is ParallelMode.EXPERT_DATA and not self.use_isp:
-            # experts are replicated over the tensor group (they are not tensor-sharded here); under sequence parallelism each
-            # tensor rank routed a different sequence shard through them, so their gradients are partial sums as well
-            dist.all_reduce(g.grad_arena, group=gpc.get_group(mode))
+        if _group_size(mode) <= 1:
             return
         if g.replica_start >= g.replica_end:
             return
@@ -288,7 +294,7 @@ class HybridZeroOptimizer:
         if g.dp_mode is ParallelMode.EXPERT_DATA:
             if _group_size(ParallelMode.EXPERT) > 1:
                 dist.all_reduce(g.sumsq, group=gpc.get_group(ParallelMode.EXPERT))
-        replicated_experts = g.dp_mode is ParallelMode.EXPERT_DATA and not self.use_isp   # same gradient on every tensor rank
+        replicated_experts = g.dp_mode is ParallelMode.EXPERT_DATA   # same gradient on every tensor / weight rank
         if _group_size(model_mode) > 1 and not (self.use_isp and g.dp_mode is ParallelMode.DATA) and not replicated_experts:
             dist.all_reduce(g.sumsq, group=gpc.get_group(model_mode))
         return g.sumsq

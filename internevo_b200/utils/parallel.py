@@ -76,9 +76,10 @@ def sync_model_replica_param_group(model):
     for param in model.parameters():
         if is_replica_zero_parallel_parameter(param):
             _bcast(param.data, mode)
-        elif is_expert_param(param) and not is_using_isp():
-            # MoE experts are not tensor-sharded in this framework: every tensor rank holds the same copy, which must start
-            # identical (the tensor-parallel RNG stream differs per rank) and stays identical (see _reduce_replica_grads)
+        elif is_expert_param(param):
+            # MoE experts are not tensor- / weight-sharded in this framework: every tensor (sequence) rank holds the same
+            # copy, which must start identical (the tensor-parallel RNG stream differs per rank) and stays identical
+            # (HybridZeroOptimizer._reduce_replica_grads)
             _bcast(param.data, ParallelMode.TENSOR)
 
 
