@@ -281,6 +281,9 @@ class ZeroFusedBackend:
             ops.sumsq_(g.owned_grad()[rep_lo:], rep)
             g.sumsq -= rep
         dist.all_reduce(g.sumsq, group=gpc.get_group(g.zero_mode))
-        if gpc.get_world_size(model_mode) > 1:
+        # tensor- / weight-SHARDED parameters: add the other shards' squares; replicated MoE experts (and, under isp, the
+        # embedding group that reduces over DATA) hold the same gradient on every model-parallel rank: nothing to add
+        replicated = g.dp_mode is ParallelMode.EXPERT_DATA or (opt.use_isp and g.dp_mode is ParallelMode.DATA)
+        if gpc.get_world_size(model_mode) > 1 and not replicated:
             dist.all_reduce(g.sumsq, group=gpc.get_group(model_mode))
         return g.sumsq
