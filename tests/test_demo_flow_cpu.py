@@ -36,7 +36,7 @@ model = dict(checkpoint=False, num_chunks=1, num_attention_heads=4, embed_split_
              embed_grad_scale=1, parallel_output=True, hidden_size={hidden}, num_layers=2, no_bias=True, mlp_ratio=2,
              apply_post_layer_norm=False, dtype="{dtype}", norm_type="rmsnorm", layer_norm_epsilon=1e-5,
              num_kv_attention_heads=2, use_flash_attn=True)
-parallel = dict(zero1=dict(size=-1), tensor=dict(size=1, mode="mtp"), pipeline=dict(size=1, interleaved_overlap=True),
+parallel = dict(zero1=dict(size=-1), tensor=dict(size={tp}, mode="mtp"), pipeline=dict(size={pp}, interleaved_overlap=True),
                 weight=dict(size=1, overlap=True, memory_pool=True))
 cudnn_deterministic = False
 cudnn_benchmark = False
@@ -52,7 +52,7 @@ def _run(cmd, cwd, timeout=600, env=None):
     return r.stdout + r.stderr
 
 
-def run_flow(tmp_path, gpu: bool):
+def run_flow(tmp_path, gpu: bool, tp: int = 1, pp: int = 1):
     """``gpu=False``: 2 gloo ranks, fp32, plain-PyTorch ops.  ``gpu=True``: 2 GPUs, bf16, the sm_100a kernels and the fused
     Hybrid-ZeRO step over peer memory (``tests/test_demo_flow_gpu.py``)."""
     import sentencepiece as spm
@@ -73,14 +73,15 @@ def run_flow(tmp_path, gpu: bool):
 
     # ---- 2. train 8 steps on 2 ranks (gloo), checkpoints at 4 and 8
     ckpt = tmp_path / "ckpts"
+    world = 2 * tp * pp          # data parallel 2 on top of the model-parallel layout
 
     def launch(steps, port):
         cfg = tmp_path / f"cfg_{steps}.py"
         text = CONFIG.format(ckpt=ckpt, steps=steps, train=tmp_path / "data" / "train", valid=tmp_path / "data" / "valid",
-                             hidden=512 if gpu else 64, dtype="torch.bfloat16" if gpu else "torch.float32")
+                             hidden=512 if gpu else 64, dtype="torch.bfloat16" if gpu else "torch.float32", tp=tp, pp=pp)
         cfg.write_text(text + ("fused_comm = True\n" if gpu else ""))
         env = dict(os.environ) if gpu else dict(os.environ, CUDA_VISIBLE_DEVICES="")
-        return _run([PY, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+        return _run([PY, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                      "--master-port", str(port), "train.py", "--config", str(cfg), "--launcher", "torch", "--backend",
                      "nccl" if gpu else "gloo"], ROOT, timeout=900, env=env)
 
@@ -90,8 +91,11 @@ def run_flow(tmp_path, gpu: bool):
     saved = sorted(int(d) for d in os.listdir(ckpt) if d.isdigit())
     assert saved == [4, 8], os.listdir(ckpt)
     files = set(os.listdir(ckpt / "8"))
-    assert {"model_tp0_pp0.pt", "optimizer_tp0_pp0_zo0.pt", "optimizer_tp0_pp0_zo1.pt", "context.pt", "sampler.pt",
-            "schedulder.pt", "model_config.pt"} <= files, files
+    want = {"context.pt", "sampler.pt", "schedulder.pt", "model_config.pt"}
+    for t in range(tp):
+        for q in range(pp):
+            want |= {f"model_tp{t}_pp{q}.pt", f"optimizer_tp{t}_pp{q}_zo0.pt", f"optimizer_tp{t}_pp{q}_zo1.pt"}
+    assert want <= files, (sorted(want - files), sorted(files))
 
     # ---- 3. second launch: auto-resume from step 8, run to 12
     log = launch(12, find_free_port())
@@ -120,3 +124,9 @@ def run_flow(tmp_path, gpu: bool):
 
 def test_tokenize_train_resume_convert_load(tmp_path):
     run_flow(tmp_path, gpu=False)
+
+
+def test_flow_with_tensor_and_pipeline_parallel_checkpoints(tmp_path):
+    """Same journey on 8 gloo ranks (dp2 x tp2 x pp2): sharded checkpoint files per (tp, pp, zero) rank, auto-resume with the
+    same layout, and `convert2hf` merging the tp / pp shards back into one HF model."""
+    run_flow(tmp_path, gpu=False, tp=2, pp=2)
