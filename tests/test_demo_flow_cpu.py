@@ -17,7 +17,7 @@ PY = sys.executable
 
 CONFIG = '''
 JOB_NAME = "demo_flow"
-model_type = "INTERNLM2_PUBLIC"
+model_type = "{model_type}"
 ckpt = dict(enable_save_ckpt=True, save_ckpt_folder="local:{ckpt}", checkpoint_every=4, auto_resume=True,
             async_upload=False, oss_snapshot_freq=0)
 data = dict(seq_len=64, micro_num=2, micro_bsz=2, valid_micro_num=1, valid_every=4, pack_sample_into_one=False,
@@ -35,7 +35,8 @@ use_fp32_norm = False
 model = dict(checkpoint=False, num_chunks=1, num_attention_heads=4, embed_split_hidden=True, vocab_size=64,
              embed_grad_scale=1, parallel_output=True, hidden_size={hidden}, num_layers=2, no_bias=True, mlp_ratio=2,
              apply_post_layer_norm=False, dtype="{dtype}", norm_type="rmsnorm", layer_norm_epsilon=1e-5,
-             num_kv_attention_heads=2, use_flash_attn=True)
+             num_kv_attention_heads=2, use_flash_attn=True{model_extra})
+{moe_section}
 parallel = dict(zero1=dict(size=-1), tensor=dict(size={tp}, mode="mtp"), pipeline=dict(size={pp}, interleaved_overlap=True),
                 weight=dict(size=1, overlap=True, memory_pool=True))
 cudnn_deterministic = False
@@ -52,7 +53,7 @@ def _run(cmd, cwd, timeout=600, env=None):
     return r.stdout + r.stderr
 
 
-def run_flow(tmp_path, gpu: bool, tp: int = 1, pp: int = 1):
+def run_flow(tmp_path, gpu: bool, tp: int = 1, pp: int = 1, moe: bool = False):
     """``gpu=False``: 2 gloo ranks, fp32, plain-PyTorch ops.  ``gpu=True``: 2 GPUs, bf16, the sm_100a kernels and the fused
     Hybrid-ZeRO step over peer memory (``tests/test_demo_flow_gpu.py``)."""
     import sentencepiece as spm
@@ -78,7 +79,13 @@ def run_flow(tmp_path, gpu: bool, tp: int = 1, pp: int = 1):
     def launch(steps, port):
         cfg = tmp_path / f"cfg_{steps}.py"
         text = CONFIG.format(ckpt=ckpt, steps=steps, train=tmp_path / "data" / "train", valid=tmp_path / "data" / "valid",
-                             hidden=512 if gpu else 64, dtype="torch.bfloat16" if gpu else "torch.float32", tp=tp, pp=pp)
+                             hidden=512 if gpu else 64, dtype="torch.bfloat16" if gpu else "torch.float32", tp=tp, pp=pp,
+                             model_type="INTERNLM_MoE" if moe else "INTERNLM2_PUBLIC",
+                             model_extra=", num_experts=4, moe_type='GShard'" if moe else "",
+                             moe_section="moe = dict(top_k=2)" if moe else "")
+        if moe:   # v1 block: multi-head attention with biases
+            text = text.replace("num_kv_attention_heads=2, ", "").replace("no_bias=True, ", "")
+            text = text.replace("loss = dict(label_smoothing=0)", "loss = dict(label_smoothing=0, moe_loss_coeff=0.1)")
         cfg.write_text(text + ("fused_comm = True\n" if gpu else ""))
         env = dict(os.environ) if gpu else dict(os.environ, CUDA_VISIBLE_DEVICES="")
         return _run([PY, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
@@ -102,6 +109,10 @@ def run_flow(tmp_path, gpu: bool, tp: int = 1, pp: int = 1):
     assert "12" in [d for d in os.listdir(ckpt)], os.listdir(ckpt)
     assert "resum" in log.lower() or "load" in log.lower()
 
+    if moe:   # expert parallel (ep = dp = 2): every expert-parallel rank wrote its own experts' file next to the dense part
+        files = set(os.listdir(ckpt / "12"))
+        assert any("expert" in f or "moe" in f for f in files), sorted(files)
+        return
     # ---- 4. convert the last checkpoint to HF and load it with the Auto classes
     hf = tmp_path / "hf"
     _run([PY, "tools/convert2hf.py", "--src", str(ckpt / "12"), "--tgt", str(hf), "--dtype", "float32", "--tokenizer", tok_model,
@@ -130,3 +141,8 @@ def test_flow_with_tensor_and_pipeline_parallel_checkpoints(tmp_path):
     """Same journey on 8 gloo ranks (dp2 x tp2 x pp2): sharded checkpoint files per (tp, pp, zero) rank, auto-resume with the
     same layout, and `convert2hf` merging the tp / pp shards back into one HF model."""
     run_flow(tmp_path, gpu=False, tp=2, pp=2)
+
+
+def test_flow_with_moe_expert_parallel_checkpoints(tmp_path):
+    """MoE (4 experts, expert parallel over 2 ranks): train, checkpoint (dense part + per-expert files), auto-resume."""
+    run_flow(tmp_path, gpu=False, moe=True)
