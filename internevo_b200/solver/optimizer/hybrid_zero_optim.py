@@ -318,6 +318,9 @@ class HybridZeroOptimizer:
             if n in by_name:
                 vec[i:i + 1] = by_name[n].sumsq
         dist.all_reduce(vec, group=group)
+        # an overflow in ANY group of ANY stage must skip the step on every stage (a group may exist on one stage only):
+        # poison all entries when one is not finite - a device-side select, no host sync
+        vec = torch.where(torch.isfinite(vec).all(), vec, torch.full_like(vec, float("inf")))
         for i, n in enumerate(self._pp_group_names):
             if n in by_name:
                 by_name[n].sumsq.copy_(vec[i:i + 1])
