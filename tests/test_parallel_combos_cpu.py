@@ -47,3 +47,33 @@ def test_combined_layout_matches_single_process(baseline, name):
     # the single-group baseline by a few 1e-4 after some steps (step 1 is exact: Adam is invariant to the gradient scale)
     tol = 6e-4 if kw.get("mode") == "isp" else 2e-4
     _check_union(run_distributed(T._train, world, kw, timeout=600), baseline, tol)
+
+
+def _overflow_on_one_stage(rank, world):
+    """Pipeline of 2 stages; the gradients of stage 0 are poisoned with inf before the optimizer step."""
+    import torch
+
+    from common import build_trainer, synthetic_batch, tiny_config
+
+    cfg = tiny_config(pp=2, micro_num=4)
+    trainer, opt, model, _ = build_trainer(cfg)
+    before = [p.detach().clone() for p in model.parameters()]
+    data, labels = synthetic_batch(4, cfg["data"]["seq_len"] * cfg["data"]["micro_bsz"], cfg["model"]["vocab_size"], seed=0)
+    trainer.zero_grad()
+    trainer.execute_schedule((data, labels), forward_only=False, return_loss=True, return_output_label=False)
+    if rank == 0:
+        victim = next(model.parameters())
+        (victim.grad if victim.grad is not None else victim.grad_buf).fill_(float("inf"))
+    ok, norms = trainer.step()
+    unchanged = all(torch.equal(a, b.detach()) for a, b in zip(before, model.parameters()))
+    # the next, healthy step must go through on both stages
+    trainer.zero_grad()
+    trainer.execute_schedule((data, labels), forward_only=False, return_loss=True, return_output_label=False)
+    ok2, _ = trainer.step()
+    return ok, unchanged, ok2
+
+
+def test_overflow_on_one_pipeline_stage_skips_the_step_everywhere():
+    for ok, unchanged, ok2 in run_distributed(_overflow_on_one_stage, 2):
+        assert ok is False and unchanged        # no stage applied the poisoned step
+        assert ok2 is True
