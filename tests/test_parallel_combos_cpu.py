@@ -19,6 +19,9 @@ COMBOS = {
     "dp2_pp2_zero": (4, dict(pp=2, micro_num=2)),
     "ckpt_pp2": (2, dict(pp=2, micro_num=4, checkpoint=True)),
     "fsp_tp2_dp2_zero_off": (4, dict(tp=2, mode="fsp", micro_num=2, zero1=1)),
+    "dp4_hybrid_zero2": (4, dict(micro_num=1, zero1=2)),
+    "isp_sp2_wp4": (4, dict(tp=2, wp=4, mode="isp", micro_num=2)),
+    "isp_sp1_wp2": (2, dict(tp=1, wp=2, mode="isp", micro_num=2)),
 }
 
 
