@@ -28,9 +28,12 @@ def _model_fn():
 
 
 def _should_save_model():
-    """One replica writes: dp-rank 0 (ISP: weight-data rank 0) of every (tp|wp, pp) coordinate."""
+    """One replica of every shard writes.  mtp / msp / fsp: data-parallel rank 0 of each (tp, pp) coordinate.  isp: files are
+    named by (tp, wp, pp); the first data-parallel replica covers every tensor (sequence) rank and the first weight-data
+    replica every weight shard, so ``wdp_rank == 0 or dp_rank == 0`` writes each (tp, wp) combination that exists
+    (reference ``components.py:245-252``)."""
     if is_using_isp():
-        return gpc.get_local_rank(ParallelMode.WEIGHT_DATA) == 0 and gpc.get_local_rank(ParallelMode.TENSOR) == 0
+        return gpc.get_local_rank(ParallelMode.WEIGHT_DATA) == 0 or gpc.get_local_rank(ParallelMode.DATA) == 0
     return gpc.get_local_rank(ParallelMode.DATA) == 0
 
 

@@ -74,3 +74,69 @@ def test_save_resume_is_exact(tmp_path):
     for r in range(2):
         for step in (5, 6):
             assert abs(first[r][step] - resumed[r][step]) < 1e-6, (first[r], resumed[r])
+
+
+def _run_layout(rank, world, folder, phase, kw, moe):
+    """Train 2 steps, save, train 2 more (reference trajectory) / resume from the checkpoint and train the same 2 steps."""
+    from internevo_b200.checkpoint import CheckpointManager
+    from internevo_b200.core.context import ParallelMode, global_context as gpc
+    from internevo_b200.core.trainer import TrainState
+
+    cfg = tiny_config(num_layers=2, micro_num=2, **kw)
+    if moe:
+        cfg["model"].pop("no_bias", None)
+        cfg["model"].pop("num_kv_attention_heads", None)
+        cfg["moe"] = dict(top_k=2)
+        cfg["loss"]["moe_loss_coeff"] = 0.1
+    cfg["ckpt"] = dict(enable_save_ckpt=True, save_ckpt_folder=f"local:{folder}", checkpoint_every=2, oss_snapshot_freq=0,
+                       auto_resume=(phase == "resume"), async_upload=False)
+    trainer, opt, model, _ = build_trainer(cfg)
+    dpr = gpc.get_local_rank(ParallelMode.DATA)
+    ts = TrainState(gpc.config, None)
+    mm = CheckpointManager(ckpt_config=gpc.config.ckpt, model=model, optimizer=opt, lr_scheduler=trainer.engine._lr_scheduler,
+                           model_config=gpc.config.model)
+    mm.try_resume_training(ts)
+    T = cfg["data"]["seq_len"] * cfg["data"]["micro_bsz"]
+
+    def step(seed):
+        data, labels = synthetic_batch(2, T, cfg["model"]["vocab_size"], seed=seed * 10 + dpr)
+        trainer.zero_grad()
+        out = trainer.execute_schedule((data, labels), forward_only=False, return_loss=True, return_output_label=False)
+        ok, norms = trainer.step()
+        assert ok
+        return (float(out[2]) if out[2] is not None else None, sorted(norms.items()))
+
+    res = {}
+    if phase == "first":
+        for s in (1, 2):
+            ts.batch_count = s - 1
+            step(s)
+            ts.step_count += 1
+            mm.try_save_checkpoint(ts)
+        mm.wait_async_upload_finish()
+    else:
+        assert ts.step_count == 2
+    for s in (3, 4):
+        res[s] = step(s)
+    return res
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("name,world,kw,moe", [
+    ("tp2_pp2", 4, dict(tp=2, pp=2), False),
+    ("isp_sp2_wp2", 2, dict(tp=2, wp=2, mode="isp"), False),
+    ("moe_ep2", 2, dict(model_type="INTERNLM_MoE", num_experts=4, moe_type="MegaBlock-D"), True),  # dropless: no gate noise
+])
+def test_resume_is_exact_for_model_parallel_and_moe_layouts(tmp_path, name, world, kw, moe):
+    first = run_distributed(_run_layout, world, str(tmp_path), "first", kw, moe)
+    resumed = run_distributed(_run_layout, world, str(tmp_path), "resume", kw, moe)
+    for r in range(world):
+        for s in (3, 4):
+            (l0, n0), (l1, n1) = first[r][s], resumed[r][s]
+            assert (l0 is None) == (l1 is None)
+            if l0 is not None:
+                assert abs(l0 - l1) < 1e-6, (name, first[r], resumed[r])
+            for (k0, v0), (k1, v1) in zip(n0, n1):
+                assert k0 == k1 and abs(v0 - v1) < 1e-5 * max(1.0, abs(v0)), (name, n0, n1)
