@@ -132,6 +132,30 @@ def run_flow(tmp_path, gpu: bool, tp: int = 1, pp: int = 1, moe: bool = False):
         loss = float(model(input_ids=line, labels=line).loss)
     assert loss < 3.9, loss
 
+    if gpu or tp * pp > 1:
+        return
+    # ---- 5. the way back (SFT workflow): HF folder -> tools/revert_hf.py -> tp = 2 training shards -> `load_ckpt_info`
+    #         (model only) in a tensor-parallel run: the very first step already sees a trained model
+    back = tmp_path / "from_hf"
+    _run([PY, "tools/revert_hf.py", "--src", str(hf), "--tgt", str(back), "--tp_size", "2", "--embed_split"], ROOT)
+    assert {"model_tp0_pp0.pt", "model_tp1_pp0.pt", "model_config.pt"} <= set(os.listdir(back))
+    text = CONFIG.format(ckpt=tmp_path / "ckpts_sft", steps=2, train=tmp_path / "data" / "train",
+                         valid=tmp_path / "data" / "valid", hidden=64, dtype="torch.float32", tp=2, pp=1,
+                         model_type="INTERNLM2_PUBLIC", model_extra="", moe_section="")
+    text = text.replace("auto_resume=True", f"auto_resume=False, load_ckpt_info=dict(path='local:{back}', content=('model',), "
+                                            "ckpt_type='internevo')")
+    text = text.replace("lr=3e-3", "lr=1e-5")
+    cfg = tmp_path / "cfg_sft.py"
+    cfg.write_text(text)
+    log = _run([PY, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                "--master-port", str(find_free_port()), "train.py", "--config", str(cfg), "--launcher", "torch", "--backend",
+                "gloo"], ROOT, timeout=900, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    import re
+
+    first = re.search(r"step=0 loss=([0-9.]+)", log)
+    assert first is not None, log[-2000:]
+    assert float(first.group(1)) < 3.9, first.group(0)       # ln(64) = 4.16 for an untrained model
+
 
 def test_tokenize_train_resume_convert_load(tmp_path):
     run_flow(tmp_path, gpu=False)
