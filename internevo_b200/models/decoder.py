@@ -361,6 +361,12 @@ class PackedDecoder(nn.Module):
     @torch.no_grad()
     def _forward_generate(self, hidden_states, input_ids, inference_params):
         s = self.spec
+        if gpc.get_world_size(ParallelMode.TENSOR) > 1 and gpc.config.parallel.get("sequence_parallel", False):
+            # a decode step is ONE token per sequence: there is nothing to shard along the sequence, and the msp / fsp / isp
+            # linears expect sequence-sharded activations.  Generation runs with tensor mode "mtp" (or tp = 1), as in the
+            # reference, whose inference path has no sequence-parallel branch either.
+            raise NotImplementedError("generation with a KV cache needs parallel.tensor.mode='mtp' (or tensor size 1); "
+                                      "load the checkpoint with an mtp layout for inference")
         if self.first and input_ids is not None:
             B, S = input_ids.shape
             hidden_states = getattr(self, s.embed_name)(input_ids.reshape(-1)).reshape(B, S, -1)
