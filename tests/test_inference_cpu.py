@@ -48,3 +48,35 @@ def test_generate_matches_full_forward_and_beam():
 
     stream = list(gen.streaming_generate(prompt[:1], max_length=8, do_sample=False))
     assert len(stream) == 4 and torch.equal(stream[-1][0, 0], out[0, 0, :8])
+
+
+def _generate_with_layout(rank, world, kw):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_parallel_cpu as T
+    from common import build_trainer, tiny_config
+
+    from internevo_b200.apis.inference import SequenceGenerator
+
+    cfg = tiny_config(**kw)
+    trainer, opt, model, _ = build_trainer(cfg)
+    T._load_golden(model, opt, cfg)            # identical full weights in every layout
+    model.eval()
+    gen = SequenceGenerator(model, eos_token_id=None, pad_token_id=0, bos_token_id=1)
+    prompt = torch.tensor([[1, 5, 9, 13], [1, 7, 11, 15]])
+    greedy = gen.generate(prompt, max_length=12, do_sample=False)[:, 0].tolist()
+    beams = gen.generate(prompt[:1], max_length=10, num_beams=3, num_return_sequences=2, do_sample=False)[0].tolist()
+    return greedy, beams
+
+
+def test_generation_under_tensor_parallel_matches_single_rank():
+    """tp = 2 (mtp): vocabulary-parallel logits are gathered, KV caches hold the local heads - same tokens as tp = 1, for
+    greedy and beam search; sequence-parallel tensor modes refuse generation with a clear error."""
+    import pytest
+
+    from common import run_distributed
+
+    single = run_distributed(_generate_with_layout, 1, dict())[0]
+    for res in run_distributed(_generate_with_layout, 2, dict(tp=2)):
+        assert res == single
+    with pytest.raises(AssertionError, match="needs parallel.tensor.mode='mtp'"):
+        run_distributed(_generate_with_layout, 2, dict(tp=2, mode="msp"))
