@@ -67,9 +67,10 @@ def run_flow(tmp_path, gpu: bool, tp: int = 1, pp: int = 1, moe: bool = False):
                                    unk_id=0, pad_id=-1, model_type="bpe", minloglevel=2)
     tok_model = str(tmp_path / "tok.model")
     for split in ("train", "valid"):
-        os.makedirs(tmp_path / "data" / split / "en")
-        _run([PY, "tools/tokenizer.py", "--text_input_path", str(corpus), "--bin_output_path",
-              str(tmp_path / "data" / split / "en" / "part0.bin"), "--tokenizer_model", tok_model], ROOT)
+        for lang in ("en", "cn"):          # two dataset types: exercises the per-type loss / accuracy bookkeeping
+            os.makedirs(tmp_path / "data" / split / lang)
+            _run([PY, "tools/tokenizer.py", "--text_input_path", str(corpus), "--bin_output_path",
+                  str(tmp_path / "data" / split / lang / "part0.bin"), "--tokenizer_model", tok_model], ROOT)
     assert os.path.exists(tmp_path / "data" / "train" / "en" / "part0.bin.meta")
 
     # ---- 2. train 8 steps on 2 ranks (gloo), checkpoints at 4 and 8
