@@ -171,3 +171,36 @@ def test_flow_with_tensor_and_pipeline_parallel_checkpoints(tmp_path):
 def test_flow_with_moe_expert_parallel_checkpoints(tmp_path):
     """MoE (4 experts, expert parallel over 2 ranks): train, checkpoint (dense part + per-expert files), auto-resume."""
     run_flow(tmp_path, gpu=False, moe=True)
+
+
+def test_alpaca_sft_shards_train(tmp_path):
+    """SFT journey: Alpaca-format JSON -> `tools/alpaca_tokenizer.py` (prompt tokens negated = no loss) -> `train.py` on the
+    resulting train / valid folders: the loss falls."""
+    import json
+    import re
+
+    import sentencepiece as spm
+    from common import find_free_port
+
+    words = ["alpha", "beta", "gamma", "delta", "epsilon", "zeta", "eta", "theta", "iota", "kappa"]
+    rng = np.random.RandomState(0)
+    corpus = tmp_path / "corpus.txt"
+    corpus.write_text("\n".join(" ".join(rng.choice(words, 12)) for _ in range(300)))
+    spm.SentencePieceTrainer.Train(input=str(corpus), model_prefix=str(tmp_path / "tok"), vocab_size=64, bos_id=1, eos_id=2,
+                                   unk_id=0, pad_id=-1, model_type="bpe", minloglevel=2)
+    samples = [{"instruction": " ".join(rng.choice(words, 5)), "input": "", "output": " ".join(rng.choice(words, 8))}
+               for _ in range(300)]
+    (tmp_path / "alpaca.json").write_text(json.dumps(samples))
+    _run([PY, "tools/alpaca_tokenizer.py", str(tmp_path / "alpaca.json"), str(tmp_path / "data"), str(tmp_path / "tok.model"),
+          "--split_ratio", "0.1", "--eoh_id", "3", "--eoa_id", "4", "--nl_id", "5"], ROOT)
+    assert os.path.exists(tmp_path / "data" / "train" / "en" / "dataset.bin.meta")
+    text = CONFIG.format(ckpt=tmp_path / "ckpts", steps=6, train=tmp_path / "data" / "train", valid=tmp_path / "data" / "valid",
+                         hidden=64, dtype="torch.float32", tp=1, pp=1, model_type="INTERNLM2_PUBLIC", model_extra="",
+                         moe_section="").replace("enable_save_ckpt=True", "enable_save_ckpt=False")
+    cfg = tmp_path / "cfg.py"
+    cfg.write_text(text)
+    log = _run([PY, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                "--master-port", str(find_free_port()), "train.py", "--config", str(cfg), "--launcher", "torch", "--backend",
+                "gloo"], ROOT, timeout=900, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    losses = [float(x) for x in re.findall(r"step=\d+ loss=([0-9.]+)", log)]
+    assert len(losses) >= 6 and losses[-1] < losses[0] - 0.5, losses
