@@ -12,7 +12,7 @@ from internevo_b200.core.context import ParallelMode
 from internevo_b200.core.context import global_context as gpc
 from internevo_b200.utils.logger import get_logger
 from internevo_b200.utils.parallel import is_using_isp
-from internevo_b200.utils.storage_manager import get_fns, get_storage_manager, llm_load, llm_save
+from internevo_b200.utils.storage_manager import get_fns, get_storage_manager, llm_load, llm_save, try_get_storage_backend
 
 from .utils import get_model_topology, get_shard_state_dict, load_shard_state_dict
 
@@ -65,9 +65,8 @@ def save_model_checkpoint(folder, model):
         llm_save(os.path.join(folder, fn), saved_obj=states)
         topo = json.dumps(get_model_topology(model))
         topo_fn = fn.replace("model_", "topo_").replace(".pt", ".json")
-        get_storage_manager()._client(os.path.join(folder, topo_fn))[0].upload_bytes(
-            topo.encode(), __import__("internevo_b200.utils.storage_manager", fromlist=["x"]).try_get_storage_backend(
-                os.path.join(folder, topo_fn))[1])
+        topo_path = os.path.join(folder, topo_fn)
+        get_storage_manager()._client(topo_path)[0].upload_bytes(topo.encode(), try_get_storage_backend(topo_path)[1])
     # experts are replicated over EXPERT_DATA: rank 0 of that group writes
     if experts and (not gpc.is_initialized(ParallelMode.EXPERT_DATA) or gpc.get_local_rank(ParallelMode.EXPERT_DATA) == 0):
         for (layer, e), st in experts.items():
