@@ -22,6 +22,8 @@ _MAP = {  # longest prefix wins
     "internlm.model.utils": "internevo_b200.parallel.functional",
     "internlm.model": "internevo_b200.models",
     "internlm.solver.optimizer.hybrid_zero_optim": "internevo_b200.solver.optimizer.hybrid_zero_optim",
+    "internlm.solver.beta2_scheduler": "internevo_b200.solver.schedulers.beta2_scheduler",
+    "internlm.solver.lr_scheduler": "internevo_b200.solver.schedulers.lr_scheduler",
     "internlm.data.tokenized.dummy_dataset": "internevo_b200.data.datasets",
     "internlm.data.tokenized.packed_dataset": "internevo_b200.data.datasets",
     "internlm.data.tokenized.single_dataset": "internevo_b200.data.datasets",
@@ -61,18 +63,31 @@ class _AliasLoader(importlib.abc.Loader):
         pass
 
 
+class _NamespaceLoader(importlib.abc.Loader):
+    """Empty package for a reference path that has no counterpart of its own but contains aliased modules
+    (``internlm.model.ops`` -> only ``internlm.model.ops.linear`` / ``.norm`` map to something)."""
+
+    def create_module(self, spec):
+        return None
+
+    def exec_module(self, module):
+        module.__path__ = []
+
+
 class _AliasFinder(importlib.abc.MetaPathFinder):
     def find_spec(self, fullname, path, target=None):
         if not fullname.startswith(_PREFIX):
             return None
         tgt = _target(fullname)
-        if tgt is None:
-            return None
-        try:
-            importlib.import_module(tgt)
-        except ImportError:
-            return None
-        return importlib.util.spec_from_loader(fullname, _AliasLoader(tgt), is_package=True)
+        if tgt is not None:
+            try:
+                importlib.import_module(tgt)
+                return importlib.util.spec_from_loader(fullname, _AliasLoader(tgt), is_package=True)
+            except ImportError:
+                pass
+        if any(k.startswith(fullname + ".") for k in _MAP):      # a parent of an aliased module
+            return importlib.util.spec_from_loader(fullname, _NamespaceLoader(), is_package=True)
+        return None
 
 
 if not any(isinstance(f, _AliasFinder) for f in sys.meta_path):

@@ -219,7 +219,30 @@ def test_public_api_surface_importable_through_internlm_alias():
         "internlm.utils.megatron_timers": ["megatron_timer"],
         "internlm.model.metrics": ["AccPerplex", "SchedulerMetricHook"],
         "internlm.model.losses": ["FlashGPTLMLoss"],
-        "internlm.eval.evaluation": ["evaluate_on_val_dls"],
+        "internlm.eval.evaluation": ["evaluate_on_val_dls", "switch_evaluation_mode"],
+        # deep module paths that scripts written against the reference import directly
+        "internlm.core.context.parallel_context": ["Config"],
+        "internlm.core.trainer": ["TrainState", "Trainer"],
+        "internlm.data.train_state": ["get_train_state"],
+        "internlm.initialize.launch": ["args_sanity_check", "launch_from_torch"],
+        "internlm.monitor.monitor": ["monitor_manager"],
+        "internlm.solver.optimizer.hybrid_zero_optim": ["HybridZeroOptimizer"],
+        "internlm.solver.beta2_scheduler": ["Beta2Scheduler"],
+        "internlm.solver.lr_scheduler": ["FineTuneCosineAnnealingWarmupLR"],
+        "internlm.data.tokenized.dummy_dataset": ["RandomDataset"],
+        "internlm.data.tokenized.packed_dataset": ["PackedDatasetWithCut", "PackedDatasetWithoutCuSeqlen"],
+        "internlm.data.tokenized.batch_sampler": ["StaticBatchSampler"],
+        "internlm.data.tokenized.collaters": ["packed_collate_fn"],
+        "internlm.model.ops.linear": ["ScaleColumnParallelLinear", "RewardModelLinear"],
+        "internlm.model.ops.norm": ["RMSNorm"],
+        "internlm.model.modules.embedding": ["Embedding1D", "RotaryEmbedding"],
+        "internlm.model.modules.mlp": ["FeedForward"],
+        "internlm.model.modules.multi_head_attention": ["MHA"],
+        "internlm.model.utils": ["gather_forward_split_backward", "split_forward_gather_backward"],
+        "internlm.utils.gputest": ["empty_cache_and_diag"],
+        "internlm.utils.parallel": ["get_parallel_log_file_name"],
+        "internlm.core.scheduler.pipeline_scheduler": ["PipelineScheduler", "InterleavedPipelineScheduler"],
+        "internlm.core.gradient_handler": ["PipelineSharedModuleGradientHandler"],
     }
     missing = {}
     for mod, names in surface.items():
