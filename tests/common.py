@@ -23,6 +23,9 @@ def _worker(rank, world, port, fn, args, ret):
     os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
                       MASTER_PORT=str(port), INTERNEVO_FORCE_DIST="1")
     try:
+        import torch
+
+        torch.set_num_threads(1)   # several ranks share the cores of one box: intra-op threading only adds contention
         out = fn(rank, world, *args)
         ret[rank] = ("ok", out)
     except Exception:
