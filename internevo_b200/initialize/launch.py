@@ -52,6 +52,14 @@ def _d(cfg: Config, key: str, value):
         cfg._add_item(key, value)
 
 
+def get_config_value(config, key, defalut):
+    """``config[key]`` or the default (reference ``launch.py:637-642``; the misspelt keyword is part of its signature)."""
+    try:
+        return config[key]
+    except KeyError:
+        return defalut
+
+
 def args_sanity_check():
     """Fill config defaults and validate combinations (reference ``launch.py:71-445``)."""
     assert gpc.config is not None, "config is not loaded!"

@@ -192,3 +192,11 @@ class _SeqAllToAll(torch.autograd.Function):
 
 def seq_all_to_all(x, group, scatter_dim: int, gather_dim: int):
     return _SeqAllToAll.apply(x, group, scatter_dim, gather_dim) if _ws(group) > 1 else x
+
+
+def try_import_RMSNorm():
+    """The RMSNorm class to use (reference ``model/utils.py:662-675`` picks apex or a torch fall-back; here it is always the
+    fused residual-add + RMSNorm kernel wrapper, which degrades to plain PyTorch on CPU)."""
+    from internevo_b200.ops.norm import RMSNorm
+
+    return RMSNorm

@@ -32,6 +32,9 @@ def try_get_storage_backend(path: str):
     m = _PREFIX.match(path)
     if m:
         return m.group(1), path[m.end():]
+    for scheme, backend in (("s3://", "boto3"), ("vc://", "volc"), ("ali://", "oss2")):   # URL scheme names the backend
+        if path.startswith(scheme):
+            return backend, path
     if os.environ.get("RANK", "0") == "0":
         logger.warning(f"path: '{path}' not start with backend prefix, guess it is the backend of local.")
     return "local", path
@@ -176,6 +179,19 @@ _custom_backends: Dict[str, Callable[[str], StorageClient]] = {}
 def register_backend(name: str, factory: Callable[[str], StorageClient]):
     """Plug in an object-store client (e.g. for ``volc:`` / ``oss2:`` prefixes)."""
     _custom_backends[name] = factory
+
+
+class SingletonMeta(type):
+    """One instance per class; a second construction with arguments is an error (reference ``storage_manager.py:967-981``)."""
+
+    _instances = {}
+
+    def __call__(cls, *args, **kwargs):
+        if cls not in cls._instances:
+            cls._instances[cls] = super().__call__(*args, **kwargs)
+        else:
+            assert len(args) == 0 and len(kwargs) == 0, f"{cls.__name__} is a singleton class and a instance has been created."
+        return cls._instances[cls]
 
 
 class StorageManager:
