@@ -1,10 +1,36 @@
 """Scheduler base class (reference ``internlm/core/scheduler/base_scheduler.py``)."""
 from __future__ import annotations
 
+import inspect
 from abc import ABC, abstractmethod
 from typing import Any, Callable, Dict, Iterable
 
 import torch
+
+_ACCEPTS_HINT: Dict[type, bool] = {}
+
+
+def model_kwargs(target, data: Dict) -> Dict:
+    """``data`` as keyword arguments for ``target`` (an Engine, a NaiveAMPModel or a bare module).  ``max_seqlen`` is a
+    host-side hint this framework adds to packed batches (it saves the decoders a device sync); a user model whose
+    ``forward`` neither names it nor takes ``**kwargs`` (e.g. the toy models of the reference's tests) does not get it."""
+    if "max_seqlen" not in data:
+        return data
+    m = target
+    while isinstance(getattr(m, "model", None), (torch.nn.Module, torch.nn.ModuleList)):
+        m = m.model
+    if isinstance(m, torch.nn.ModuleList) and len(m):
+        m = m[0]
+    fwd = getattr(m, "forward", None)
+    ok = _ACCEPTS_HINT.get(type(m))
+    if ok is None:
+        try:
+            params = inspect.signature(fwd).parameters.values()
+            ok = any(p.kind is inspect.Parameter.VAR_KEYWORD or p.name == "max_seqlen" for p in params)
+        except (TypeError, ValueError):
+            ok = True
+        _ACCEPTS_HINT[type(m)] = ok
+    return data if ok else {k: v for k, v in data.items() if k != "max_seqlen"}
 
 
 class BaseScheduler(ABC):
@@ -33,7 +59,7 @@ class BaseScheduler(ABC):
         if isinstance(inputs, (list, tuple)):
             return engine(*inputs)
         if isinstance(inputs, dict):
-            return engine(**inputs)
+            return engine(**model_kwargs(engine, inputs))
         raise TypeError(f"Expected engine inputs to be tensor, list, tuple or dict, got {type(inputs)}")
 
     @staticmethod

@@ -20,7 +20,7 @@ from internevo_b200.core.naive_amp import NaiveAMPModel
 from internevo_b200.utils.common import SchedulerHook, get_current_device, move_to_device
 from internevo_b200.utils.timeout import llm_timeout
 
-from .base_scheduler import BaseScheduler
+from .base_scheduler import BaseScheduler, model_kwargs
 
 
 def get_tensor_shape():
@@ -137,7 +137,7 @@ class PipelineScheduler(BaseScheduler):
     def _call_engine(self, engine, data):  # pylint: disable=W0237
         if data is None:
             return None
-        return engine(**data) if isinstance(data, dict) else engine(data)
+        return engine(**model_kwargs(engine, data)) if isinstance(data, dict) else engine(data)
 
     def _forward_step(self, engine, input_obj, return_tensors, return_output_label=True, accum_loss=None,
                       accum_moe_loss=None, model=None):
@@ -147,7 +147,7 @@ class PipelineScheduler(BaseScheduler):
         is_moe = hasattr(gpc.config.model, "num_experts")
         self._call_hooks("before_forward", data)
         run = engine if model is None else model
-        out = run(**data)
+        out = run(**model_kwargs(run, data))
         if is_moe:
             output_obj, moe_losses = out
         else:

@@ -50,15 +50,30 @@ def switch_evaluation_pipeline_scheduler(trainer, num_microbatches, tensor_shape
 
 
 @contextmanager
-def switch_evaluation_mode(trainer):
+def switch_evaluation_mode(trainer, metric_hook_list=None):
+    """``gpc.is_evaluating`` for the duration of the block.  Without ``metric_hook_list`` (this framework's own validation
+    loop) the trainer is also put into eval mode and back; with it the call has the reference's semantics
+    (``eval/evaluation.py:28-42``): the schedule's hooks are replaced by the list and its data_process_func is disabled."""
     prev = gpc.is_evaluating
+    if metric_hook_list is None:
+        try:
+            gpc.is_evaluating = True
+            trainer.eval()
+            yield
+        finally:
+            gpc.is_evaluating = prev
+            trainer.train()
+        return
+    prev_func, prev_hooks = trainer.schedule.data_process_func, trainer.schedule._hooks
     try:
         gpc.is_evaluating = True
-        trainer.eval()
+        trainer.schedule.data_process_func = None
+        trainer.schedule._hooks = metric_hook_list
         yield
     finally:
         gpc.is_evaluating = prev
-        trainer.train()
+        trainer.schedule.data_process_func = prev_func
+        trainer.schedule._hooks = prev_hooks
 
 
 def evaluate_on_val_dls(trainer, val_dls, writer, logger, step_count, update_panel: bool = False, streaming: bool = False):

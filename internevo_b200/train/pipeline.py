@@ -204,7 +204,10 @@ def get_scheduler_hooks(metric, zero_optim=None, isp_communicator=None, criterio
 
 @llm_timeout(func_name="load_new_batch")
 def load_new_batch(train_dl: DataLoader, train_iter: Iterable, train_state: TrainState):
-    """Next batch (restarting the iterator at epoch end); pops ``type_ids``; advances the resume anchor."""
+    """Next batch (restarting the iterator at epoch end) with the resume anchor advanced.  ``type_ids`` (dataset type of every
+    token, for the per-dataset loss / accuracy metrics) stay in ``batch[0]`` - un-packed to ``[micro, micro_bsz, seq]`` for
+    un-packed datasets - and are consumed by the caller with ``metric.set_current_type_ids(batch[0].pop("type_ids"))`` before
+    the batch goes to the scheduler (reference ``train/pipeline.py:381-414``, ``train.py:217-218``)."""
     timer("batch-gen").start()
     try:
         batch = next(train_iter)
@@ -217,10 +220,12 @@ def load_new_batch(train_dl: DataLoader, train_iter: Iterable, train_state: Trai
         next(train_state.batch_sampler_iter)
         train_state.num_consumed_samples_in_epoch = 0
     timer("batch-gen").stop()
-    if batch[0].get("type_ids", None) is not None:
-        if not gpc.config.data.get("use_packed_dataset", True):
-            pass
-        batch[0].pop("type_ids", None)
+    if batch[0].get("type_ids", None) is not None and not gpc.config.data.get("use_packed_dataset", True):
+        from internevo_b200.data.datasets import unpack_data
+
+        t = batch[0]["type_ids"]
+        batch[0]["type_ids"] = torch.stack([unpack_data(t[i:i + 1], batch[0]["cu_seqlens"][i:i + 1], is_type_ids=True)
+                                            for i in range(t.shape[0])])
     attach_host_max_seqlen(batch[0])
     return batch, train_iter
 

@@ -16,15 +16,17 @@ from internevo_b200.core.context import global_context as gpc
 
 
 def is_using_sequence_parallel():
-    return (
-        isinstance(gpc.config.parallel["tensor"], dict)
-        and gpc.config.parallel["tensor"].get("mode", "mtp") != "mtp"
-        and gpc.config.parallel["tensor"]["size"] > 1
-    )
+    par = gpc.config.get("parallel", None) if gpc.config is not None else None
+    if not par or "tensor" not in par:
+        return False
+    return isinstance(par["tensor"], dict) and par["tensor"].get("mode", "mtp") != "mtp" and par["tensor"]["size"] > 1
 
 
 def is_using_isp():
-    return isinstance(gpc.config.parallel["tensor"], dict) and gpc.config.parallel["tensor"].get("mode", "mtp") == "isp"
+    par = gpc.config.get("parallel", None) if gpc.config is not None else None   # partial configs (data-only tests, tools)
+    if not par or "tensor" not in par:
+        return False
+    return isinstance(par["tensor"], dict) and par["tensor"].get("mode", "mtp") == "isp"
 
 
 def is_replica_zero_parallel_parameter(p):

@@ -140,6 +140,11 @@ def main(args):
                 timer("one-batch").stop()
                 continue
 
+            # dataset type of every token: feeds the per-dataset loss / accuracy metrics, not the model
+            type_ids = batch[0].pop("type_ids", None)
+            if type_ids is not None and metric is not None:
+                metric.set_current_type_ids(type_ids=type_ids)
+
             trainer.zero_grad()
             timer("fwd-bwd").start()
             moe_loss = None
