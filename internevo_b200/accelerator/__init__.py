@@ -234,4 +234,8 @@ def get_accelerator() -> B200Accelerator:
 
 get_accelerator()
 
-__all__ = ["AcceleratorType", "get_accelerator", "internlm_accelerator", "B200Accelerator"]
+# reference class names (``accelerator/abstract_accelerator.py`` / ``cuda_accelerator.py``); there is one backend
+Accelerator = B200Accelerator
+CUDA_Accelerator = B200Accelerator
+
+__all__ = ["AcceleratorType", "get_accelerator", "internlm_accelerator", "B200Accelerator", "Accelerator", "CUDA_Accelerator"]

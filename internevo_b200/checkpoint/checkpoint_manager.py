@@ -17,6 +17,7 @@ import torch.distributed as dist
 from internevo_b200.core.context import ParallelMode
 from internevo_b200.core.context import global_context as gpc
 from internevo_b200.core.trainer import TrainState
+from internevo_b200.initialize.legacy.launch import auto_resume_sanity_check, ckpt_info_sanity_check
 from internevo_b200.monitor import send_alert_message
 from internevo_b200.utils.common import get_current_device
 from internevo_b200.utils.logger import get_logger
@@ -153,6 +154,8 @@ class CheckpointManager:
         # strip the AMP wrapper so keys match the reference's state dict
         self.model = model.model if hasattr(model, "model") and not isinstance(model, torch.nn.ModuleList) else model
         self.load_ckpt_info = ckpt_config.get("load_ckpt_info", None)
+        if self.load_ckpt_info is None:      # old-style keys: load_ckpt_folder / load_model_only_folder / load_optimizer
+            self.load_ckpt_info = ckpt_info_sanity_check(ckpt_config)
         self.defalut_load_type_func = {CheckpointLoadType.INTERNLM: try_load_internevo_ckpt,
                                        CheckpointLoadType.INTERNEVO: try_load_internevo_ckpt}
         for ckpt_load_type in LOAD_FUNC_DICT:
@@ -164,7 +167,10 @@ class CheckpointManager:
             open(self.stop_file_path, "a").close()
         self.ckpt_quit_signal_handled = False
         # auto-resume takes precedence over load_ckpt_info
-        if ckpt_config.get("auto_resume", False) and self.save_ckpt_folder:
+        auto_resume = ckpt_config.get("auto_resume", None)
+        if auto_resume is None:                  # old-style: load_given_ckpt=True pins the named folder
+            auto_resume = auto_resume_sanity_check(ckpt_config)
+        if auto_resume and self.save_ckpt_folder:
             latest = self.query_lastest_ckpt()
             if latest is not None:
                 self.load_ckpt_info = dict(path=latest, content=("all",), ckpt_type="internevo")

@@ -76,3 +76,23 @@ class ParamAsyncBcastHandler:
 
     def bind(self, optimizer):
         self._optimizer = optimizer
+
+
+def split_tensor_into_1d_equal_chunks(tensor: torch.Tensor, new_buffer: bool = False) -> torch.Tensor:
+    """This tensor-parallel rank's 1/tp slice of the flattened tensor — the "scatter" half of scatter-gather pipeline
+    p2p (reference ``core/communication/utils.py:96-114``); a view unless ``new_buffer``."""
+    tp, r = gpc.get_world_size(ParallelMode.TENSOR), gpc.get_local_rank(ParallelMode.TENSOR)
+    n = tensor.numel() // tp
+    part = tensor.reshape(-1)[r * n: (r + 1) * n]
+    return part.clone() if new_buffer else part
+
+
+def gather_split_1d_tensor(tensor: torch.Tensor) -> torch.Tensor:
+    """Inverse of :func:`split_tensor_into_1d_equal_chunks`: all-gather the slices over the TENSOR group (flat result)."""
+    tp = gpc.get_world_size(ParallelMode.TENSOR)
+    if tp <= 1:
+        return tensor.reshape(-1)
+    out = torch.empty(tensor.numel() * tp, dtype=tensor.dtype, device=tensor.device)
+    with torch.no_grad():
+        dist.all_gather_into_tensor(out, tensor.detach().contiguous().view(-1), group=gpc.get_group(ParallelMode.TENSOR))
+    return out

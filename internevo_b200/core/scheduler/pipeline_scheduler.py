@@ -8,6 +8,7 @@ host-synchronises, and the interleaved overlap starts the exchange *before* the 
 """
 from __future__ import annotations
 
+from contextlib import contextmanager
 from typing import Callable, List, Optional, Tuple, Union
 
 import torch
@@ -21,6 +22,28 @@ from internevo_b200.utils.common import SchedulerHook, get_current_device, move_
 from internevo_b200.utils.timeout import llm_timeout
 
 from .base_scheduler import BaseScheduler, model_kwargs
+
+
+@contextmanager
+def switch_virtual_pipeline_parallel_rank(rank):
+    """Temporarily make ``rank`` the current model chunk (reference ``pipeline_scheduler.py:91-98``)."""
+    prev = gpc.virtual_pipeline_parallel_rank
+    try:
+        gpc.set_virtual_pipeline_parallel_rank(rank)
+        yield
+    finally:
+        gpc.set_virtual_pipeline_parallel_rank(prev)
+
+
+@contextmanager
+def switch_optimizer_grad_sync_skip_mode(optimizer, skip: bool = True):
+    """Temporarily (un)set the optimizer's "do not reduce gradients yet" flag (reference ``:101-108``)."""
+    prev = optimizer.skip_grad_reduce
+    try:
+        optimizer.skip_grad_reduce = skip
+        yield
+    finally:
+        optimizer.skip_grad_reduce = prev
 
 
 def get_tensor_shape():

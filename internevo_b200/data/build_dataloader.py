@@ -18,6 +18,7 @@ from .datasets import (
     PackedDatasetWithCut,
     PackedDatasetWithoutCuSeqlen,
     RandomDataset,
+    get_dataset_dict,
     get_packed_dataset_without_short_length,
 )
 
@@ -59,16 +60,14 @@ def get_tokenized_train_loader_items(data_cfg):
 
 
 def get_tokenized_valid_loader_items(data_cfg):
+    """→ ``({name: dataset}, collate_fn)``: one entry per sub-folder of ``valid_folder`` (reference ``:69-85``)."""
     if not data_cfg.get("valid_folder", None):
-        valid_ds = RandomDataset(num_samples=gpc.get_world_size(ParallelMode.DATA) * 500, max_len=data_cfg.seq_len)
+        valid_ds = RandomDataset(num_samples=gpc.get_world_size(ParallelMode.DATA) * 500, max_len=data_cfg.seq_len,
+                                 fixed_seqlen=data_cfg.get("fixed_random_dataset_seqlen", False))
     else:
-        valid_ds = JsonlDataset(data_cfg.valid_folder, min_length=0) if data_cfg.valid_folder.endswith(".bin") else None
-        if valid_ds is None:
-            import os
-
-            files = sorted(os.path.join(r, f) for r, _, fs in os.walk(data_cfg.valid_folder) for f in fs
-                           if f.endswith(".bin"))
-            valid_ds = ConcatDataset([JsonlDataset(f, min_length=0) for f in files])
+        valid_ds = get_dataset_dict(folder=data_cfg.valid_folder, split="")
+    if not isinstance(valid_ds, dict):
+        valid_ds = {"val": valid_ds}
     return valid_ds, partial(jsonl_ds_collate_fn, max_length_per_sample=data_cfg.seq_len)
 
 
@@ -87,15 +86,23 @@ def build_train_loader_with_data_type():
 
 
 def build_valid_loader_with_data_type():
+    """``{name: DataLoader}``; the batch is clamped to what every data-parallel rank can fill, sets too small for a single
+    micro-batch per rank are skipped (reference ``:116-157``)."""
     data_cfg = gpc.config.data
-    assert data_cfg.type == "tokenized"
+    assert data_cfg.type == "tokenized", f"unsupported data type {data_cfg.type}"
     valid_ds, valid_collate_fn = get_tokenized_valid_loader_items(data_cfg)
     if valid_ds is None:
         return None
-    bsz = data_cfg.valid_micro_num * data_cfg.micro_bsz
-    n = min(len(valid_ds), bsz)
-    if n < bsz and gpc.is_rank_for_log():
-        logger.info(f"validation set smaller than one batch: using {n}")
-    dl = get_dpsampler_dataloader(valid_ds, shuffle=False, num_workers=0, batch_size=bsz, collate_fn=valid_collate_fn,
-                                  drop_last=True)
-    return {"val": dl} if not isinstance(dl, dict) else dl
+    val_dls = {}
+    for name, ds in valid_ds.items():
+        bsz = min(data_cfg.valid_micro_num * data_cfg.micro_bsz, len(ds) // gpc.get_world_size(ParallelMode.DATA))
+        bsz = bsz // data_cfg.micro_bsz * data_cfg.micro_bsz
+        if bsz == 0:
+            if gpc.is_rank_for_log():
+                logger.info(f"skip validate {name}.")
+            continue
+        val_dls[name] = get_dpsampler_dataloader(ds, shuffle=False, num_workers=data_cfg.get("num_worker", 0),
+                                                 batch_size=bsz, collate_fn=valid_collate_fn, drop_last=True)
+        if gpc.is_rank_for_log():
+            logger.info(f"load validation dataset {name} with valid batch size {bsz} and samples {len(val_dls[name])}.")
+    return val_dls

@@ -278,6 +278,26 @@ class PackedDatasetWithoutCuSeqlen(PackedDataset):
 DATASET_TYPE_IDS_MAP = {"en": 0, "cn": 1, "code": 2}
 
 
+def get_dataset_dict(folder, split="valid") -> Dict[str, Dataset]:
+    """``{sub-folder name: ConcatDataset of its *.bin files whose name contains `split`}`` — one validation set per data
+    source, walked in sorted order so every rank builds the same dict (reference ``data/tokenized/dataset.py:9-56``)."""
+    assert os.path.exists(folder), f"folder `{folder}` not exists"
+    if os.path.isfile(folder):
+        return {os.path.basename(os.path.dirname(os.path.abspath(folder))) or "val": JsonlDataset(folder, min_length=0)}
+    out: Dict[str, Dataset] = {}
+    for root, dirs, files in os.walk(folder, followlinks=True):
+        dirs.sort()
+        bins = [os.path.join(root, f) for f in sorted(files) if f.endswith(".bin") and split in f]
+        if bins:
+            out[os.path.basename(os.path.normpath(root))] = ConcatDataset([JsonlDataset(b, min_length=0) for b in bins])
+    return out
+
+
+def get_dataset_type_ids_map(path):
+    """``{sub-folder name: type id}`` in sorted order (reference ``data/utils.py:11-14``)."""
+    return {name: i for i, name in enumerate(sorted(os.listdir(path)))}
+
+
 def get_dataset_type_id(dataset_type_ids_map, path):
     matches = [v for k, v in dataset_type_ids_map.items() if f"/{k}/" in path or path.startswith(f"{k}/")]
     assert len(matches) == 1, f"{path} should match exactly one of {list(dataset_type_ids_map)}"

@@ -16,6 +16,7 @@ import torch
 
 from internevo_b200.core.context import Config, ParallelMode
 from internevo_b200.core.context import global_context as gpc
+from internevo_b200.initialize.legacy.launch import auto_resume_sanity_check
 from internevo_b200.utils.logger import get_logger
 from internevo_b200.utils.timeout import llm_timeout
 
@@ -128,7 +129,7 @@ def args_sanity_check():
             ckpt._add_item(k, v)
     _d(ckpt, "load_ckpt_folder", None)
     _d(ckpt, "stop_file_path", None)
-    _d(ckpt, "auto_resume", True)
+    _d(ckpt, "auto_resume", auto_resume_sanity_check(ckpt))      # True unless an old-style config says load_given_ckpt
 
     # ---- tensorboard / misc
     _d(cfg, "enable_tb", True)

@@ -190,3 +190,25 @@ class SchedulerMetricHook(SchedulerHook):
     def post_helper_func(self, scheduler, outputs, label) -> None:
         # metric update is driven from the criterion's by-products (see train.pipeline.get_scheduler_hooks)
         pass
+
+
+def broadcast(src: torch.Tensor, other: torch.Tensor, dim: int) -> torch.Tensor:
+    """Expand an index vector so it can address ``other`` along ``dim`` (reference ``metrics.py:17-29``)."""
+    if dim < 0:
+        dim += other.dim()
+    if src.dim() == 1:
+        src = src.view([-1 if i == dim else 1 for i in range(other.dim())])
+    while src.dim() < other.dim():
+        src = src.unsqueeze(-1)
+    return src.expand(other.size())
+
+
+def vanilla_scatter(src: torch.Tensor, index: torch.Tensor, dim: int = -1, out=None, dim_size=None, reduce=None):
+    """``scatter(..., reduce="sum")`` of torch_scatter in plain torch: per-dataset-type sums of the metric code
+    (reference ``metrics.py:32-52``)."""
+    index = broadcast(index, src, dim)
+    if out is None:
+        size = list(src.size())
+        size[dim] = dim_size if dim_size is not None else (int(index.max()) + 1 if index.numel() else 0)
+        out = torch.zeros(size, dtype=src.dtype, device=src.device)
+    return out.scatter_add_(dim, index, src)

@@ -444,3 +444,88 @@ class GeluMLP(nn.Module):
                 type(fc1).__name__.startswith("ColumnParallelLinear"):
             return self.fc2(ops.linear_gelu(x, fc1.weight, fc1.bias))  # GELU in the GEMM epilogue
         return self.fc2(F.gelu(fc1(x), approximate="tanh"))
+
+
+# ---- reference module names that are one class here ----------------------------------------------------------------
+# The reference keeps a FeedForward per tensor-parallel mode (``modules/mlp.py``: FeedForward / MegatronFeedForward /
+# ISPFeedForward); here the linear classes returned by ``get_linear_cls(tp_mode)`` carry the mode and the block is shared.
+BaseFeedForward = FeedForward
+MegatronFeedForward = FeedForward
+ISPFeedForward = FeedForward
+
+
+def get_mlp_cls(tp_mode: str):
+    assert tp_mode in ("mtp", "msp", "fsp", "isp"), tp_mode
+    return FeedForward
+
+
+class SelfAttention(nn.Module):
+    """Unfused softmax attention on packed-projection input ``qkv [B, S, 3, H, D]`` (reference
+    ``multi_head_attention.py`` / flash-attn's module of the same name): fp32 softmax, optional causal mask and
+    ``key_padding_mask [B, S]`` (True = keep).  CPU path and numerical oracle for the tcgen05 flash kernel."""
+
+    def __init__(self, causal: bool = False, softmax_scale=None, attention_dropout: float = 0.0):
+        super().__init__()
+        self.causal, self.softmax_scale = causal, softmax_scale
+        self.dropout = nn.Dropout(attention_dropout)
+
+    def forward(self, qkv, causal=None, key_padding_mask=None):
+        q, k, v = qkv.unbind(dim=2)
+        return _reference_attention(q, k, v, self.causal if causal is None else causal, self.softmax_scale,
+                                    key_padding_mask, self.dropout)
+
+
+class CrossAttention(nn.Module):
+    """Unfused attention with separate ``q [B, Sq, H, D]`` and ``kv [B, Sk, 2, Hkv, D]`` (grouped-query when
+    ``Hkv < H``); causal masking is aligned to the END of the key sequence, which is what a KV cache needs."""
+
+    def __init__(self, causal: bool = False, softmax_scale=None, attention_dropout: float = 0.0):
+        super().__init__()
+        self.causal, self.softmax_scale = causal, softmax_scale
+        self.dropout = nn.Dropout(attention_dropout)
+
+    def forward(self, q, kv, causal=None, key_padding_mask=None):
+        k, v = kv.unbind(dim=2)
+        if k.shape[2] != q.shape[2]:
+            rep = q.shape[2] // k.shape[2]
+            k, v = k.repeat_interleave(rep, dim=2), v.repeat_interleave(rep, dim=2)
+        return _reference_attention(q, k, v, self.causal if causal is None else causal, self.softmax_scale,
+                                    key_padding_mask, self.dropout)
+
+
+def _reference_attention(q, k, v, causal, scale, key_padding_mask, dropout):
+    Sq, Sk, D = q.shape[1], k.shape[1], q.shape[-1]
+    scale = scale if scale is not None else D ** -0.5
+    scores = torch.einsum("bqhd,bkhd->bhqk", q.float(), k.float()) * scale
+    if key_padding_mask is not None:
+        scores = scores.masked_fill(~key_padding_mask[:, None, None, :].bool(), float("-inf"))
+    if causal:
+        row = torch.arange(Sq, device=q.device)[:, None] + (Sk - Sq)
+        scores = scores.masked_fill(torch.arange(Sk, device=q.device)[None, :] > row, float("-inf"))
+    probs = dropout(torch.softmax(scores, dim=-1).to(v.dtype))
+    return torch.einsum("bhqk,bkhd->bqhd", probs, v)
+
+
+class DistributedAttention(nn.Module):
+    """Ulysses wrapper: scatter heads / gather sequence over ``sequence_process_group`` before ``local_attention``,
+    inverse afterwards (reference ``multi_head_attention.py:56-135``).  ``MHA`` inlines the same exchange around the
+    varlen flash kernel; this module exists for custom attention cores.  Tensors are ``[B, S_local, ..., H, D]``."""
+
+    def __init__(self, local_attention: nn.Module, sequence_process_group, scatter_idx: int = 2, gather_idx: int = 1):
+        super().__init__()
+        self.local_attn, self.spg = local_attention, sequence_process_group
+        self.scatter_idx, self.gather_idx = scatter_idx, gather_idx
+
+    def _a2a(self, x, head_dim, seq_dim, inverse=False):
+        if self.spg is None or _ws(self.spg) <= 1:
+            return x
+        sd, gd = (seq_dim, head_dim) if inverse else (head_dim, seq_dim)
+        return seq_all_to_all(x.contiguous(), self.spg, scatter_dim=sd, gather_dim=gd)
+
+    def forward(self, qkv=None, kv=None, q=None, **kwargs):
+        if qkv is not None:                                        # [B, S, 3, H, D]
+            out = self.local_attn(self._a2a(qkv, 3, 1), **kwargs)
+        else:                                                      # q [B, S, H, D], kv [B, S, 2, Hkv, D]
+            out = self.local_attn(self._a2a(q, 2, 1), self._a2a(kv, 3, 1), **kwargs)
+        return self._a2a(out, 2, 1, inverse=True)                  # [B, S_full, H/sp, D] -> [B, S_local, H, D]
+

@@ -58,6 +58,12 @@ def _capacity(num_tokens: int, num_experts: int, capacity_factor: float, min_cap
     return max(cap, min_capacity)
 
 
+class BaseMoELayer(nn.Module):
+    """Attribute contract of an MoE layer — ``gate`` (or ``wg``), ``experts`` (:class:`Experts`), ``ep_group``, ``ep_size``,
+    ``num_local_experts``, and after each forward ``l_aux`` / ``exp_counts`` (reference ``moe/base_layer.py:17-41``);
+    ``MoE`` and the loss / metric code only rely on these."""
+
+
 class _AllToAll(torch.autograd.Function):
     """Equal-split ``all_to_all_single`` (dispatch / combine, reference ``moe/utils.py:21-40``)."""
 
@@ -166,7 +172,7 @@ class Experts(nn.Module):
         return torch.stack(outs, 0)
 
 
-class GShardMOELayer(nn.Module):
+class GShardMOELayer(BaseMoELayer):
     """dispatch → all-to-all → experts → all-to-all → combine (reference ``gshard_layer.py:369-498``)."""
 
     def __init__(self, hidden_size, gate: TopKGate, experts: Experts, ep_group, ep_size, num_local_experts: int) -> None:
@@ -267,7 +273,7 @@ class _AllToAllV(torch.autograd.Function):
         return None, _AllToAllV.apply(ctx.group, g, ctx.recv, ctx.send), None, None
 
 
-class DroplessMOELayer(nn.Module):
+class DroplessMOELayer(BaseMoELayer):
     """Dropless top-k MoE (the ``MegaBlock-D`` registry entry): no capacity, no padding.
 
     Tokens are sorted by destination expert, exchanged with ONE variable-split all-to-all (row counts first, then the
@@ -414,3 +420,17 @@ class MoE(nn.Module):
 
 def is_moe_param(param: torch.Tensor) -> bool:
     return getattr(param, "is_expert", False)
+
+
+def all_to_all(x, output_split_sizes=None, input_split_sizes=None, group=None, async_op=False):
+    """Differentiable ``all_to_all_single`` with optional row splits (reference ``moe/utils.py:62-63``)."""
+    assert not async_op, "the autograd all_to_all is synchronous; overlap comes from the fused peer-memory dispatch"
+    if output_split_sizes is None and input_split_sizes is None:
+        return _AllToAll.apply(group, x)
+    return _AllToAllV.apply(group, x, list(input_split_sizes), list(output_split_sizes))
+
+
+# reference class names (``moe/utils.py``, ``moe/megablock/megablock_{moe,dmoe}.py``)
+AllToAll = _AllToAll
+MegaBlockMoE = GShardMOELayer           # capacity raised to the busiest expert's load: see _build_megablock
+MegaBlockdMoE = DroplessMOELayer

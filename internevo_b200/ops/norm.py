@@ -195,3 +195,36 @@ class LayerNorm(nn.Module):
 
     def extra_repr(self):
         return f"{tuple(self.weight.shape)}, eps={self.eps}"
+
+
+def manual_rms_norm(my_input, normalized_shape, weight, eps):
+    """Unfused RMSNorm over the trailing ``normalized_shape`` dims with fp32 statistics (reference ``ops/norm.py``)."""
+    dims = tuple(range(-len(normalized_shape), 0))
+    var = my_input.float().pow(2).mean(dims, keepdim=True)
+    y = my_input * torch.rsqrt(var + eps)
+    if weight is None:
+        return y
+    if weight.dtype in (torch.float16, torch.bfloat16):
+        y = y.to(weight.dtype)
+    return weight * y
+
+
+class RMSNormTorch(nn.Module):
+    """Pure-PyTorch RMSNorm: CPU runs and numerical oracle for :class:`RMSNorm`."""
+
+    def __init__(self, normalized_shape, eps: float = 1e-5, device=None, dtype=None):
+        super().__init__()
+        if isinstance(normalized_shape, int):
+            normalized_shape = (normalized_shape,)
+        self.normalized_shape = torch.Size(normalized_shape)
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(*normalized_shape, device=device, dtype=dtype))
+
+    def reset_parameters(self):
+        nn.init.ones_(self.weight)
+
+    def forward(self, x):
+        return manual_rms_norm(x, self.normalized_shape, self.weight, self.eps)
+
+    def extra_repr(self):
+        return f"{tuple(self.normalized_shape)}, eps={self.eps}"

@@ -200,3 +200,14 @@ def try_import_RMSNorm():
     from internevo_b200.ops.norm import RMSNorm
 
     return RMSNorm
+
+
+def Silu(w1_o, w2_o):
+    """``silu(w1_o) * w2_o`` — one fused kernel on the GPU (reference ``model/utils.py:684-688`` jit-scripts it)."""
+    from internevo_b200.ops import silu_mul
+
+    return silu_mul(w1_o, w2_o)
+
+
+def is_moe_param(param) -> bool:
+    return getattr(param, "is_expert", False)

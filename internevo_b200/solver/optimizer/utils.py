@@ -62,3 +62,122 @@ class DynamicGradScaler:
         self._scale = float(state_dict["_scale"])
         self._growth_step = state_dict["_growth_step"]
         self._hysteresis_step = state_dict["_hysteresis_step"]
+
+
+# ---- tensor-list helpers of the reference's optimizer utilities (``solver/optimizer/utils.py:42-330``).  The arena
+# optimizer does not need them (its gradients are one flat buffer and the norm is one fused kernel); they are kept for
+# user code and for optimizers plugged in through ``BaseOptimizer``.
+import math as _math  # noqa: E402
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+from torch._utils import _flatten_dense_tensors, _unflatten_dense_tensors  # noqa: E402
+
+
+def flatten(tensors):
+    return _flatten_dense_tensors(tensors)
+
+
+def unflatten(flat, tensors):
+    return _unflatten_dense_tensors(flat, tensors)
+
+
+def split_half_float_double(tensor_list):
+    """Bucket tensors by type string, preserving first-seen order."""
+    buckets = {}
+    for t in tensor_list:
+        buckets.setdefault(t.type(), []).append(t)
+    return list(buckets.values())
+
+
+def reduce_tensor(tensor, dtype=None, dst_rank=None, parallel_mode=None):
+    """Asynchronous averaging all-reduce (or reduce to ``dst_rank`` of the group) in the tensor's own dtype → handle."""
+    from internevo_b200.core.context import ParallelMode
+
+    assert dtype is None or dtype == tensor.dtype, "communication happens in the tensor's dtype"
+    mode = ParallelMode.DATA if parallel_mode is None else parallel_mode
+    group, n = gpc.get_group(mode), gpc.get_world_size(mode)
+    if group is None or n <= 1:
+        return None
+    avg = dist.ReduceOp.AVG if tensor.is_cuda else dist.ReduceOp.SUM          # gloo has no AVG
+    if not tensor.is_cuda:
+        tensor.div_(n)
+    if dst_rank is None:
+        return dist.all_reduce(tensor, op=avg, group=group, async_op=True)
+    return dist.reduce(tensor, dst=gpc.get_ranks_in_group(mode)[dst_rank], op=avg, group=group, async_op=True)
+
+
+def has_inf_or_nan(tensor) -> bool:
+    s = float(tensor.float().sum())
+    return _math.isinf(s) or _math.isnan(s)
+
+
+def release_param_grad(tensor_list):
+    for t in tensor_list:
+        t.grad = None
+
+
+def sync_param(flat_tensor, tensor_list):
+    """Re-point every tensor of ``tensor_list`` at its slice of ``flat_tensor``."""
+    for p, view in zip(tensor_list, _unflatten_dense_tensors(flat_tensor, tensor_list)):
+        p.data = view
+
+
+def multi_tensor_l2norm_torch(tensor_list, per_tensor: bool):
+    norms = torch.stack([t.float().norm(2) for t in tensor_list])
+    return norms.norm(2).unsqueeze(0), (norms if per_tensor else norms.new_empty(0))
+
+
+def calc_l2_norm(grads):
+    """L2 norm of a tensor list; contiguous bf16 / fp32 CUDA tensors go through the fused sum-of-squares kernel."""
+    if len(grads) == 0:
+        return 0.0
+    if all(g.is_cuda and g.is_contiguous() for g in grads):
+        from internevo_b200.ops import sumsq_
+
+        acc = torch.zeros(1, dtype=torch.float32, device=grads[0].device)
+        for g in grads:
+            sumsq_(g, acc)
+        return acc.sqrt()
+    return multi_tensor_l2norm_torch(grads, False)[0]
+
+
+def calc_lp(grads, norm_type):
+    total = 0.0
+    for g in grads:
+        total = total + g.float().norm(norm_type) ** norm_type
+    return total
+
+
+def get_norm(grads, norm_type, enable_cuda_kernels: bool = True):
+    """``max|g|`` for the inf-norm, else ``sum ||g||_p ** p`` (the caller reduces over ranks and takes the root)."""
+    if norm_type == _math.inf:
+        return max(g.detach().abs().max() for g in grads)
+    if norm_type == 2.0 and enable_cuda_kernels:
+        return calc_l2_norm(grads) ** norm_type
+    return calc_lp(grads, norm_type)
+
+
+class BaseGradScaler:
+    """Constant loss scale; ``DynamicGradScaler`` adds the growth / back-off policy."""
+
+    def __init__(self, initial_scale: float):
+        assert initial_scale > 0
+        self._scale = float(initial_scale)
+
+    @property
+    def scale(self) -> float:
+        return self._scale
+
+    @property
+    def inv_scale(self) -> float:
+        return 1.0 / self._scale
+
+    def state_dict(self):
+        return {"scale": self._scale}
+
+    def load_state_dict(self, state_dict) -> None:
+        self._scale = float(state_dict["scale"])
+
+    def update(self, overflow: bool) -> None:
+        pass

@@ -11,7 +11,22 @@ import sys
 
 _PREFIX = __name__ + "."
 _MAP = {  # longest prefix wins
+    "internlm.model.losses.ce_loss": "internevo_b200.models.losses",
     "internlm.model.losses": "internevo_b200.models.losses",
+    "internlm.model.moe.base_layer": "internevo_b200.models.moe",
+    "internlm.model.moe.experts": "internevo_b200.models.moe",
+    "internlm.model.moe.gshard_layer": "internevo_b200.models.moe",
+    "internlm.model.moe.megablock.megablock_moe": "internevo_b200.models.moe",
+    "internlm.model.moe.megablock.megablock_dmoe": "internevo_b200.models.moe",
+    "internlm.model.moe.megablock.mlp": "internevo_b200.models.moe",
+    "internlm.model.moe.megablock.utils": "internevo_b200.models.moe",
+    "internlm.model.moe.megablock": "internevo_b200.models.moe",
+    "internlm.model.moe.moe": "internevo_b200.models.moe",
+    "internlm.model.moe.utils": "internevo_b200.models.moe",
+    "internlm.accelerator.abstract_accelerator": "internevo_b200.accelerator",
+    "internlm.accelerator.cuda_accelerator": "internevo_b200.accelerator",
+    "internlm.data.tokenized.dataset": "internevo_b200.data.datasets",
+    "internlm.solver.optimizer.base_optimizer": "internevo_b200.solver.optimizer.base_optimizer",
     "internlm.model.metrics": "internevo_b200.models.metrics",
     "internlm.model.moe": "internevo_b200.models.moe",
     "internlm.model.ops.linear": "internevo_b200.parallel.linear",

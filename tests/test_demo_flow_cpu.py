@@ -109,6 +109,7 @@ def run_flow(tmp_path, gpu: bool, tp: int = 1, pp: int = 1, moe: bool = False):
     log = launch(12, find_free_port())
     assert "12" in [d for d in os.listdir(ckpt)], os.listdir(ckpt)
     assert "resum" in log.lower() or "load" in log.lower()
+    assert "Validation on en" in log and "Validation on cn" in log, "one validation set per sub-folder of valid_folder"
 
     if moe:   # expert parallel (ep = dp = 2): every expert-parallel rank wrote its own experts' file next to the dense part
         files = set(os.listdir(ckpt / "12"))
