@@ -128,6 +128,36 @@ def try_load_internevo_ckpt(ckpt_mm, load_info, train_state: TrainState = None):
     return load_content_str
 
 
+class CheckpointLoadMethod:
+    """Registry of ``ckpt_type`` → loader, so user code can add its own checkpoint format
+    (reference ``checkpoint_manager.py:145-163``).  A loader is called as ``fn(ckpt_manager, load_info, train_state)`` and
+    returns a string naming what it loaded."""
+
+    LOAD_TYPE_FUNC = {"internevo": try_load_internevo_ckpt, "internlm": try_load_internevo_ckpt, **LOAD_FUNC_DICT}
+
+    @staticmethod
+    def register_ckpt_load_type(load_type, load_func):
+        if load_type in CheckpointLoadMethod.LOAD_TYPE_FUNC:
+            if gpc.is_rank_for_log():
+                logger.warning(f"{load_type} has already been registered!")
+            return
+        CheckpointLoadMethod.LOAD_TYPE_FUNC[load_type] = load_func
+
+    @staticmethod
+    def get_ckpt_load_type_func(load_type):
+        return CheckpointLoadMethod.LOAD_TYPE_FUNC[getattr(load_type, "value", load_type)]
+
+
+def try_load_internlm_ckpt_func(ckpt_mm, load_info, *args, func=None, **kwargs):
+    """Model-only load through ``func(folder=, model=)`` followed by the master-weight refresh
+    (reference ``checkpoint_manager.py:201-219``)."""
+    assert func is not None, "pass the loader as func="
+    func(folder=load_info["path"], model=ckpt_mm.model)
+    if ckpt_mm.optimizer is not None and hasattr(ckpt_mm.optimizer, "reload_zero_fp32_buff"):
+        ckpt_mm.optimizer.reload_zero_fp32_buff()
+    return f"{CheckpointLoadContent.MODEL}, "
+
+
 class CheckpointManager:
     """StorageManager is a singleton; the checkpoint manager is created once by ``train.py``."""
 
@@ -158,8 +188,8 @@ class CheckpointManager:
             self.load_ckpt_info = ckpt_info_sanity_check(ckpt_config)
         self.defalut_load_type_func = {CheckpointLoadType.INTERNLM: try_load_internevo_ckpt,
                                        CheckpointLoadType.INTERNEVO: try_load_internevo_ckpt}
-        for ckpt_load_type in LOAD_FUNC_DICT:
-            self.defalut_load_type_func[ckpt_load_type] = LOAD_FUNC_DICT[ckpt_load_type]
+        for ckpt_load_type, fn in CheckpointLoadMethod.LOAD_TYPE_FUNC.items():       # built-ins + user-registered types
+            self.defalut_load_type_func.setdefault(ckpt_load_type, fn)
         if self.stop_file_path and gpc.get_global_rank() == 0:
             dir_path = os.path.dirname(self.stop_file_path)
             if dir_path not in ("", ".") and not os.path.exists(dir_path):

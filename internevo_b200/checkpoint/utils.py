@@ -45,3 +45,11 @@ def try_get_tp_pp_from_fns(fns):
             max_tp = max(max_tp, int(segs[1][2:]))
             max_pp = max(max_pp, int(segs[-1][2:]))
     return max_tp + 1, max_pp + 1
+
+
+def get_non_moe_state_dict(full_state_dict):
+    """Drop expert tensors (they go to per-expert files), keep the gates (reference ``checkpoint/utils.py:29-37``)."""
+    for key in list(full_state_dict.keys()):
+        if "expert" in key and "moe_layer.gate" not in key and ".wg." not in key:
+            full_state_dict.pop(key)
+    return full_state_dict

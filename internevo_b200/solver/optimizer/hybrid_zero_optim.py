@@ -554,3 +554,10 @@ class HybridZeroOptimizer:
         self.flush_param_update()
         for g in self.groups:
             g.master.copy_(g.param_arena[g.lo: g.hi])
+
+
+def reload_zero_fp32_buff(optimizer):
+    """Module-level form of :meth:`HybridZeroOptimizer.reload_zero_fp32_buff` (reference ``hybrid_zero_optim.py:939-950``):
+    refresh the fp32 master shards after weights were loaded into the model; a no-op for other optimizers."""
+    if isinstance(optimizer, HybridZeroOptimizer):
+        optimizer.reload_zero_fp32_buff()

@@ -253,3 +253,37 @@ def _ulysses_worker(rank, world):
 
 def test_distributed_attention_and_1d_split_two_ranks():
     assert all(run_distributed(_ulysses_worker, 2))
+
+
+def _custom_ckpt_type_worker(rank, world, folder):
+    from common import build_trainer, tiny_config
+
+    from internevo_b200.checkpoint import CheckpointManager
+    from internevo_b200.checkpoint.checkpoint_manager import CheckpointLoadMethod
+    from internevo_b200.core.context import global_context as gpc
+    from internevo_b200.core.trainer import TrainState
+
+    seen = []
+
+    def load_mine(ckpt_mm, load_info, train_state):
+        seen.append((load_info["path"], sorted(c for c in ("model", "optimizer") if load_info["content"].need_load(c))))
+        return "model, "
+
+    CheckpointLoadMethod.register_ckpt_load_type("mine", load_mine)
+    cfg = tiny_config(num_layers=2)
+    # old-style keys are translated; an explicit load_ckpt_info wins over them
+    cfg["ckpt"] = dict(enable_save_ckpt=False, auto_resume=False, load_ckpt_folder=folder, load_optimizer=False)
+    trainer, opt, model, _ = build_trainer(cfg)
+    mm = CheckpointManager(ckpt_config=gpc.config.ckpt, model=model, optimizer=opt, lr_scheduler=None, model_config=gpc.config.model)
+    legacy = dict(mm.load_ckpt_info)
+    assert legacy["path"] == folder and legacy["content"].need_load("model") and legacy["content"].need_load("sampler")
+    assert not legacy["content"].need_load("optimizer")
+    gpc.config.ckpt["load_ckpt_info"] = dict(path=folder, content=("model",), ckpt_type="mine")
+    mm = CheckpointManager(ckpt_config=gpc.config.ckpt, model=model, optimizer=opt, lr_scheduler=None, model_config=gpc.config.model)
+    mm.try_resume_training(TrainState(gpc.config, None))
+    return seen
+
+
+def test_custom_checkpoint_type_and_legacy_keys(tmp_path):
+    (seen,) = run_distributed(_custom_ckpt_type_worker, 1, str(tmp_path))
+    assert seen == [(str(tmp_path), ["model"])]
