@@ -210,3 +210,21 @@ class AsynCommunicator:
     def wait_and_receive(self):
         prev, nxt = self._finish()
         return prev if self.forward else nxt
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# two-phase coroutines of the reference's interleaved scheduler (``p2p.py:429-546``): ``next(co)`` starts the exchange,
+# the second ``next(co)`` waits for it and returns the received tensor.  ``AsynCommunicator`` is the object form.
+# --------------------------------------------------------------------------------------------------------------------
+def send_forward_and_recv_next_forward_async(output_tensor, recv_prev_shape=None, dtype=None, scatter_gather_tensors=False):
+    finish = _communicate_async(object_send_next=output_tensor, recv_prev=recv_prev_shape is not None,
+                                recv_prev_shape=recv_prev_shape, dtype=dtype, scatter_gather_tensors=scatter_gather_tensors)
+    yield
+    yield finish()[0]
+
+
+def send_backward_and_recv_next_backward_async(input_tensor, recv_next_shape=None, dtype=None, scatter_gather_tensors=False):
+    finish = _communicate_async(object_send_prev=input_tensor, recv_next=recv_next_shape is not None,
+                                recv_next_shape=recv_next_shape, dtype=dtype, scatter_gather_tensors=scatter_gather_tensors)
+    yield
+    yield finish()[1]

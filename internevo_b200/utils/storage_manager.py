@@ -3,7 +3,7 @@ optional asynchronous upload (reference ``internlm/utils/storage_manager.py:95-1
 
 Public surface kept: ``llm_save / llm_load / get_fns / check_folder``, ``init_storage_manager``,
 ``get_storage_manager().wait()``, ``try_get_storage_backend``.  Object-store SDKs are imported lazily (none is present in
-this image); each backend only has to provide ``upload / download / list / exists / delete`` on raw bytes, the manager
+this image); each backend (``LocalClient``, ``Boto3Client``, ``VolcClient``, ``AliClient``) only has to provide ``upload / download / list / exists / delete`` on raw bytes, the manager
 owns serialisation (``torch.save``), the ``/dev/shm`` staging folder, md5 sidecars, the thread pool and the ``{step}.step``
 completion marker that is written only after every asynchronous upload of the step has finished.
 """
@@ -155,6 +155,168 @@ class Boto3Client(StorageClient):
         self.client.delete_object(Bucket=b, Key=k)
 
 
+def _credentials(prefix: str):
+    """``ACCESS_KEY`` / ``SECRET_ACCESS_KEY`` win over ``{prefix}_ACCESS_KEY_ID`` / ``{prefix}_SECRET_ACCESS_KEY_ID``."""
+    ak = os.environ.get("ACCESS_KEY") or os.environ.get(f"{prefix}_ACCESS_KEY_ID")
+    sk = os.environ.get("SECRET_ACCESS_KEY") or os.environ.get(f"{prefix}_SECRET_ACCESS_KEY_ID")
+    assert ak and sk, f"set {prefix}_ACCESS_KEY_ID / {prefix}_SECRET_ACCESS_KEY_ID (or ACCESS_KEY / SECRET_ACCESS_KEY)"
+    return ak, sk
+
+
+def _split_bucket_url(remote: str, scheme: str):
+    """``{scheme}{bucket}.{endpoint}/{key}`` → ``(bucket, endpoint, key)``."""
+    m = re.match(rf"^{re.escape(scheme)}([^/.]+)\.([^/]+)/?(.*)$", remote)
+    assert m, f"url '{remote}' is not a valid {scheme} url: expected {scheme}<bucket>.<endpoint>/<key>"
+    return m.group(1), m.group(2), m.group(3)
+
+
+def _under(key: str, prefix: str) -> bool:
+    """Object stores match raw string prefixes (``run/7`` also matches ``run/7.step``): keep the object itself and what
+    lies below it as a folder."""
+    prefix = prefix.rstrip("/")
+    return prefix == "" or key == prefix or key.startswith(prefix + "/")
+
+
+def _first_segments(keys, prefix: str) -> List[str]:
+    """Names directly under ``prefix`` (files or "folders"), the listing the checkpoint code expects."""
+    prefix, names = prefix.rstrip("/"), set()
+    for k in keys:
+        if not _under(k, prefix):
+            continue
+        rest = k[len(prefix):].strip("/")
+        names.add(rest.split("/", 1)[0] if rest else os.path.basename(k))
+    return sorted(names)
+
+
+class VolcClient(StorageClient):
+    """``volc:vc://{bucket}.{endpoint}/{key}`` through the ``tos`` SDK (ByteDance TOS; reference
+    ``storage_manager.py:485-672``).  The region is derived from the endpoint (``tos-cn-beijing.volces.com`` →
+    ``cn-beijing``)."""
+
+    PART = 64 << 20
+
+    def __init__(self, endpoint: str, region: Optional[str] = None):
+        import tos  # noqa: lazy — not part of the image
+
+        ak, sk = _credentials("VOLC")
+        region = region or "-".join(endpoint.split(".")[0].split("-")[1:])
+        self.client = tos.TosClientV2(ak, sk, endpoint, region, enable_crc=False)
+
+    @staticmethod
+    def split(remote: str):
+        b, _, k = _split_bucket_url(remote, "vc://")
+        return b, k
+
+    def _keys(self, bucket: str, prefix: str):
+        token = None
+        while True:
+            kw = dict(prefix=prefix) if token is None else dict(prefix=prefix, continuation_token=token)
+            res = self.client.list_objects_type2(bucket, **kw)
+            for item in getattr(res, "contents", None) or []:
+                yield item.key
+            if not getattr(res, "is_truncated", False):
+                return
+            token = res.next_continuation_token
+
+    def upload_bytes(self, data, remote):
+        b, k = self.split(remote)
+        self.client.put_object(b, k, content=io.BytesIO(data))
+
+    def upload_file(self, local_path, remote):
+        b, k = self.split(remote)
+        if os.path.getsize(local_path) <= self.PART:
+            with open(local_path, "rb") as f:
+                self.client.put_object(b, k, content=f)
+            return
+        upload_id, parts, n = self.client.create_multipart_upload(b, k).upload_id, [], 1
+        with open(local_path, "rb") as f:
+            for chunk in iter(lambda: f.read(self.PART), b""):
+                parts.append(self.client.upload_part(b, k, upload_id, n, content=io.BytesIO(chunk)))
+                n += 1
+        self.client.complete_multipart_upload(b, k, upload_id, parts)
+
+    def download_bytes(self, remote):
+        b, k = self.split(remote)
+        return self.client.get_object(b, k).read()
+
+    def list(self, remote):
+        b, k = self.split(remote)
+        return _first_segments(self._keys(b, k), k)
+
+    def exists(self, remote):
+        b, k = self.split(remote)
+        return any(_under(key, k) for key in self._keys(b, k))
+
+    def delete(self, remote):
+        b, k = self.split(remote)
+        self.client.delete_object(b, k)
+
+
+class AliClient(StorageClient):
+    """``oss2:ali://{bucket}.{endpoint}/{key}`` through the ``oss2`` SDK (Aliyun OSS; reference
+    ``storage_manager.py:675-816``); one ``Bucket`` handle per bucket name."""
+
+    def __init__(self, endpoint: str):
+        import oss2  # noqa: lazy — not part of the image
+
+        self._sdk, self.endpoint = oss2, endpoint
+        self.auth = oss2.Auth(*_credentials("ALI"))
+        self._buckets: Dict[str, Any] = {}
+
+    def _bucket(self, remote: str):
+        b, _, k = _split_bucket_url(remote, "ali://")
+        if b not in self._buckets:
+            self._buckets[b] = self._sdk.Bucket(self.auth, self.endpoint, b, enable_crc=False)
+        return self._buckets[b], k
+
+    def upload_bytes(self, data, remote):
+        bucket, k = self._bucket(remote)
+        bucket.put_object(k, data)
+
+    def upload_file(self, local_path, remote):
+        bucket, k = self._bucket(remote)
+        self._sdk.resumable_upload(bucket, k, local_path) if hasattr(self._sdk, "resumable_upload") else \
+            bucket.put_object_from_file(k, local_path)
+
+    def download_bytes(self, remote):
+        bucket, k = self._bucket(remote)
+        return bucket.get_object(k).read()
+
+    def list(self, remote):
+        bucket, k = self._bucket(remote)
+        return _first_segments((o.key for o in self._sdk.ObjectIteratorV2(bucket, prefix=k)), k)
+
+    def exists(self, remote):
+        bucket, k = self._bucket(remote)
+        return any(_under(o.key, k) for o in self._sdk.ObjectIteratorV2(bucket, prefix=k))
+
+    def delete(self, remote):
+        bucket, k = self._bucket(remote)
+        bucket.delete_object(k)
+
+
+def get_tmp_file_name(tmp_local_folder: str, fp: str) -> str:
+    """Staging file of an asynchronous upload: unique per host, process and remote path (reference ``:840-856``)."""
+    base = re.sub(r"^[a-z0-9]+://", "", fp).replace(os.path.sep, "_")
+    return os.path.join(tmp_local_folder, f"{socket.gethostname()}-{os.getpid()}-{base}")
+
+
+def get_mount_point_free_size(path: str) -> float:
+    """Free space of the file system holding ``path`` in GB."""
+    st = os.statvfs(path)
+    return st.f_bavail * st.f_frsize / (1 << 30)
+
+
+def check_tmp_folder_accessibility(tmp_local_folder: str, min_free_gb: float = 0.1):
+    """The staging folder must be readable, writable, listable and not (nearly) full (reference ``:1217-1245``)."""
+    os.makedirs(tmp_local_folder, exist_ok=True)
+    ok = os.access(tmp_local_folder, os.R_OK | os.W_OK | os.X_OK)
+    free = get_mount_point_free_size(tmp_local_folder)
+    if not ok or free < min_free_gb:
+        raise RuntimeError(f"async upload staging folder {tmp_local_folder}: accessible={ok}, free={free:.2f} GB "
+                           f"(need >= {min_free_gb} GB)")
+
+
 def _make_client(backend: str, path: str) -> StorageClient:
     if backend == "local":
         return LocalClient()
@@ -162,14 +324,10 @@ def _make_client(backend: str, path: str) -> StorageClient:
         m = re.match(r"^s3://[^/.]+\.([^/]+)/", path)
         endpoint = f"http://{m.group(1)}" if m and m.group(1) else os.environ.get("S3_ENDPOINT_URL")
         return Boto3Client(endpoint)
-    if backend == "volc":  # ByteDance TOS: same verbs through the tos SDK
-        import tos  # noqa: F401 lazy
-
-        raise NotImplementedError("volc backend needs the `tos` SDK; wire a StorageClient via register_backend()")
+    if backend == "volc":
+        return VolcClient(_split_bucket_url(path, "vc://")[1])
     if backend == "oss2":
-        import oss2  # noqa: F401 lazy
-
-        raise NotImplementedError("oss2 backend needs the `oss2` SDK; wire a StorageClient via register_backend()")
+        return AliClient(_split_bucket_url(path, "ali://")[1])
     raise ValueError(f"unknown storage backend {backend}")
 
 
@@ -238,7 +396,7 @@ class StorageManager:
             torch.save(to_save_obj, buf, **kwargs)
             c.upload_bytes(buf.getvalue(), real)
             return
-        tmp = os.path.join(self.tmp_local_folder, f"{socket.gethostname()}-{os.getpid()}-" + real.replace("/", "_"))
+        tmp = get_tmp_file_name(self.tmp_local_folder, real)
         torch.save(to_save_obj, tmp, **kwargs)
         self.async_task_peeding = True
         self._futures.append(self._pool.submit(self._upload_and_clean, c, tmp, real))

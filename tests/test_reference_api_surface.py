@@ -287,3 +287,144 @@ def _custom_ckpt_type_worker(rank, world, folder):
 def test_custom_checkpoint_type_and_legacy_keys(tmp_path):
     (seen,) = run_distributed(_custom_ckpt_type_worker, 1, str(tmp_path))
     assert seen == [(str(tmp_path), ["model"])]
+
+
+def _async_p2p_worker(rank, world):
+    from common import tiny_config
+
+    from internevo_b200.core.communication.p2p import (
+        send_backward_and_recv_next_backward_async,
+        send_forward_and_recv_next_forward_async,
+    )
+    from internevo_b200.initialize import initialize_distributed_env
+
+    initialize_distributed_env(config=tiny_config(pp=2, num_layers=4, micro_num=2), launcher="torch", seed=5)
+    shape = torch.Size([3, 4])
+    # forward direction: stage 0 sends, stage 1 receives; the work between the two next() calls overlaps the transfer
+    co = send_forward_and_recv_next_forward_async(torch.full(shape, 7.0) if rank == 0 else None,
+                                                  recv_prev_shape=shape if rank == 1 else None, dtype=torch.float32)
+    next(co)
+    busy = torch.ones(8).sum()
+    got = next(co)
+    assert (got is None) if rank == 0 else (torch.equal(got, torch.full(shape, 7.0)) and got.requires_grad)
+    # backward direction: stage 1 sends the input gradient, stage 0 receives it
+    co = send_backward_and_recv_next_backward_async(torch.full(shape, -2.0) if rank == 1 else None,
+                                                    recv_next_shape=shape if rank == 0 else None, dtype=torch.float32)
+    next(co)
+    got = next(co)
+    assert (got is None) if rank == 1 else torch.equal(got, torch.full(shape, -2.0))
+    return float(busy)
+
+
+def test_two_phase_async_p2p_coroutines():
+    assert run_distributed(_async_p2p_worker, 2) == [8.0, 8.0]
+
+
+class _FakeObjectStore:
+    """In-memory stand-ins for the ``tos`` and ``oss2`` SDK surfaces the storage clients use."""
+
+    def __init__(self):
+        self.blobs = {}                                             # (bucket, key) -> bytes
+        store = self
+
+        class _Obj:
+            def __init__(self, key):
+                self.key = key
+
+        class _Stream:
+            def __init__(self, data):
+                self._d = data
+
+            def read(self):
+                return self._d
+
+        class TosClientV2:
+            def __init__(self, ak, sk, endpoint, region, enable_crc=False):
+                store.tos_args = (ak, sk, endpoint, region)
+                self._mp = {}
+
+            def put_object(self, bucket, key, content=None):
+                store.blobs[(bucket, key)] = content.read()
+
+            def get_object(self, bucket, key):
+                return _Stream(store.blobs[(bucket, key)])
+
+            def delete_object(self, bucket, key):
+                store.blobs.pop((bucket, key), None)
+
+            def list_objects_type2(self, bucket, prefix="", continuation_token=None):
+                keys = sorted(k for b, k in store.blobs if b == bucket and k.startswith(prefix))
+                start = int(continuation_token or 0)                # two keys per page: exercises the continuation loop
+                page = type("R", (), {})()
+                page.contents = [_Obj(k) for k in keys[start:start + 2]]
+                page.is_truncated = start + 2 < len(keys)
+                page.next_continuation_token = str(start + 2)
+                return page
+
+            def create_multipart_upload(self, bucket, key):
+                self._mp[(bucket, key)] = {}
+                return type("R", (), {"upload_id": "u1"})()
+
+            def upload_part(self, bucket, key, upload_id, n, content=None):
+                self._mp[(bucket, key)][n] = content.read()
+                return n
+
+            def complete_multipart_upload(self, bucket, key, upload_id, parts):
+                store.blobs[(bucket, key)] = b"".join(self._mp[(bucket, key)][n] for n in parts)
+
+        class Bucket:
+            def __init__(self, auth, endpoint, name, enable_crc=False):
+                self.name = name
+
+            def put_object(self, key, data):
+                store.blobs[(self.name, key)] = data if isinstance(data, bytes) else data.read()
+
+            def put_object_from_file(self, key, path):
+                store.blobs[(self.name, key)] = open(path, "rb").read()
+
+            def get_object(self, key):
+                return _Stream(store.blobs[(self.name, key)])
+
+            def delete_object(self, key):
+                store.blobs.pop((self.name, key), None)
+
+        def iterator(bucket, prefix=""):
+            return iter([_Obj(k) for b, k in sorted(store.blobs) if b == bucket.name and k.startswith(prefix)])
+
+        import types
+
+        self.tos = types.SimpleNamespace(TosClientV2=TosClientV2)
+        self.oss2 = types.SimpleNamespace(Auth=lambda ak, sk: (ak, sk), Bucket=Bucket, ObjectIteratorV2=iterator)
+
+
+@pytest.mark.parametrize("url", ["volc:vc://ckpts.tos-cn-beijing.volces.com/run1", "oss2:ali://ckpts.oss-cn-hangzhou.aliyuncs.com/run1"])
+def test_volc_and_ali_object_stores(monkeypatch, tmp_path, url):
+    import internevo_b200.utils.storage_manager as sm
+
+    fake = _FakeObjectStore()
+    monkeypatch.setitem(sys.modules, "tos", fake.tos)
+    monkeypatch.setitem(sys.modules, "oss2", fake.oss2)
+    for k in ("VOLC_ACCESS_KEY_ID", "ALI_ACCESS_KEY_ID"):
+        monkeypatch.setenv(k, "ak")
+    for k in ("VOLC_SECRET_ACCESS_KEY_ID", "ALI_SECRET_ACCESS_KEY_ID"):
+        monkeypatch.setenv(k, "sk")
+    monkeypatch.setattr(sm.VolcClient, "PART", 1 << 10)             # force the multipart path for the async upload
+    sm.check_tmp_folder_accessibility(str(tmp_path / "stage"))
+    mgr = sm.StorageManager(True, tmp_local_folder=str(tmp_path / "stage"), async_mode=True)
+    state = {"w": torch.arange(2000.0), "step": 7}
+    mgr.save(f"{url}/7/model_tp0_pp0.pt", state)                    # asynchronous: staged file + md5 sidecar
+    mgr.save(f"{url}/7/context.pt", {"step": 7}, async_upload=False)
+    mgr.save(f"{url}/8/context.pt", {"step": 8}, async_upload=False)
+    mgr.set_pending_marker(f"{url}/7.step")
+    assert not mgr.is_exists(f"{url}/7.step")                       # the marker appears only after the uploads finished
+    assert mgr.wait() and mgr.is_exists(f"{url}/7.step")
+    assert os.listdir(tmp_path / "stage") == []
+    assert mgr.get_fns(url) == ["7", "7.step", "8"]
+    assert mgr.get_fns(f"{url}/7") == ["context.pt", "model_tp0_pp0.pt", "model_tp0_pp0.pt.md5"]
+    back = mgr.load(f"{url}/7/model_tp0_pp0.pt")
+    assert torch.equal(back["w"], state["w"]) and back["step"] == 7
+    mgr.delete_obj(f"{url}/8/context.pt")
+    assert not mgr.is_exists(f"{url}/8") and mgr.is_exists(f"{url}/7")
+    if url.startswith("volc"):
+        assert fake.tos_args == ("ak", "sk", "tos-cn-beijing.volces.com", "cn-beijing")
+    assert sm.get_mount_point_free_size(str(tmp_path)) > 0
