@@ -80,6 +80,58 @@ class _AllToAll(torch.autograd.Function):
         return None, _AllToAll.apply(ctx.group, g)
 
 
+def _route(logits, k, cf, min_capacity, noisy_gate_policy, drop_tokens, use_rts):
+    """Routing decision from fp32 gate logits ``[S, E]`` in index form →
+    ``(l_aux, weights[S, k], experts[S, k], slots[S, k], keep[S, k], capacity, counts[E])``."""
+    S, E = logits.shape
+    gates = F.softmax(logits, dim=1)
+    cap = _capacity(S, E, cf, min_capacity, k)
+    # ---- expert choice
+    noisy1 = logits + gumbel_rsample(logits.shape, logits.device) if (
+        k == 1 and noisy_gate_policy == "RSample") else gates
+    idx1 = torch.argmax(noisy1, dim=1)
+    mask1 = F.one_hot(idx1, E)
+    if k == 2:
+        noisy2 = (logits + gumbel_rsample(logits.shape, logits.device)).masked_fill(mask1.bool(), float("-inf"))
+        idx2 = torch.argmax(noisy2, dim=1)
+        mask2 = F.one_hot(idx2, E)
+    counts = mask1.sum(0).detach()
+    # ---- load-balancing loss (first choice only, as GShard)
+    me, ce = gates.mean(0), mask1.float().mean(0)
+    l_aux = (me * ce).sum() * E
+    if not drop_tokens:  # dropless: grow capacity to the busiest expert (agreed across the expert group)
+        load = counts.max() if k == 1 else (mask1.sum(0) + mask2.sum(0)).max()
+        if gpc.is_initialized(ParallelMode.EXPERT) and gpc.get_world_size(ParallelMode.EXPERT) > 1:
+            dist.all_reduce(load, op=dist.ReduceOp.MAX, group=gpc.get_group(ParallelMode.EXPERT))
+        cap = max(cap, int(load.item()))
+    # ---- slot of every token inside its expert's buffer
+    if k == 1 and use_rts and drop_tokens:
+        # random token selection: keep the `cap` tokens with the highest random priority per expert
+        pri = mask1 * torch.rand_like(mask1, dtype=torch.float32)
+        top = torch.topk(pri, k=min(cap, S), dim=0).indices  # [cap, E]
+        sel = torch.zeros_like(mask1).scatter_(0, top, 1) * mask1
+        loc1 = (torch.cumsum(sel, 0) - 1)
+        keep1 = sel.sum(1).bool()
+        slot1 = (loc1 * sel).sum(1)
+    else:
+        loc1 = torch.cumsum(mask1, 0) - 1
+        slot1 = (loc1 * mask1).sum(1)
+        keep1 = slot1 < cap
+    g1 = (gates * mask1).sum(1)
+    if k == 1:
+        weights = (g1 * keep1).unsqueeze(1)
+        return l_aux, weights, idx1.unsqueeze(1), slot1.unsqueeze(1), keep1.unsqueeze(1), cap, counts
+    loc2 = torch.cumsum(mask2, 0) - 1 + mask1.sum(0, keepdim=True)  # second choices queue behind all first choices
+    slot2 = (loc2 * mask2).sum(1)
+    keep2 = slot2 < cap
+    g2 = (gates * mask2).sum(1)
+    g1, g2 = g1 * keep1, g2 * keep2
+    denom = (g1 + g2).clamp_min(torch.finfo(gates.dtype).eps)
+    weights = torch.stack([g1 / denom, g2 / denom], 1)
+    return (l_aux, weights, torch.stack([idx1, idx2], 1), torch.stack([slot1, slot2], 1),
+            torch.stack([keep1, keep2], 1), cap, counts)
+
+
 class TopKGate(nn.Module):
     """Gate ``wg: hidden -> num_experts`` kept in fp32 (reference ``gshard_layer.py:287-366``).
 
@@ -102,54 +154,8 @@ class TopKGate(nn.Module):
         if self.noisy_gate_policy == "Jitter" and self.training:
             xf = multiplicative_jitter(xf, device=xf.device)
         logits = F.linear(xf, self.wg.weight.float())
-        S, E = logits.shape
-        gates = F.softmax(logits, dim=1)
         cf = self.capacity_factor if self.training else self.eval_capacity_factor
-        cap = _capacity(S, E, cf, self.min_capacity, self.k)
-        # ---- expert choice
-        noisy1 = logits + gumbel_rsample(logits.shape, logits.device) if (
-            self.k == 1 and self.noisy_gate_policy == "RSample") else gates
-        idx1 = torch.argmax(noisy1, dim=1)
-        mask1 = F.one_hot(idx1, E)
-        if self.k == 2:
-            noisy2 = (logits + gumbel_rsample(logits.shape, logits.device)).masked_fill(mask1.bool(), float("-inf"))
-            idx2 = torch.argmax(noisy2, dim=1)
-            mask2 = F.one_hot(idx2, E)
-        counts = mask1.sum(0).detach()
-        # ---- load-balancing loss (first choice only, as GShard)
-        me, ce = gates.mean(0), mask1.float().mean(0)
-        l_aux = (me * ce).sum() * E
-        if not self.drop_tokens:  # dropless: grow capacity to the busiest expert (agreed across the expert group)
-            load = counts.max() if self.k == 1 else (mask1.sum(0) + mask2.sum(0)).max()
-            if gpc.is_initialized(ParallelMode.EXPERT) and gpc.get_world_size(ParallelMode.EXPERT) > 1:
-                dist.all_reduce(load, op=dist.ReduceOp.MAX, group=gpc.get_group(ParallelMode.EXPERT))
-            cap = max(cap, int(load.item()))
-        # ---- slot of every token inside its expert's buffer
-        if self.k == 1 and self.use_rts and self.drop_tokens:
-            # random token selection: keep the `cap` tokens with the highest random priority per expert
-            pri = mask1 * torch.rand_like(mask1, dtype=torch.float32)
-            top = torch.topk(pri, k=min(cap, S), dim=0).indices  # [cap, E]
-            sel = torch.zeros_like(mask1).scatter_(0, top, 1) * mask1
-            loc1 = (torch.cumsum(sel, 0) - 1)
-            keep1 = sel.sum(1).bool()
-            slot1 = (loc1 * sel).sum(1)
-        else:
-            loc1 = torch.cumsum(mask1, 0) - 1
-            slot1 = (loc1 * mask1).sum(1)
-            keep1 = slot1 < cap
-        g1 = (gates * mask1).sum(1)
-        if self.k == 1:
-            weights = (g1 * keep1).unsqueeze(1)
-            return l_aux, weights, idx1.unsqueeze(1), slot1.unsqueeze(1), keep1.unsqueeze(1), cap, counts
-        loc2 = torch.cumsum(mask2, 0) - 1 + mask1.sum(0, keepdim=True)  # second choices queue behind all first choices
-        slot2 = (loc2 * mask2).sum(1)
-        keep2 = slot2 < cap
-        g2 = (gates * mask2).sum(1)
-        g1, g2 = g1 * keep1, g2 * keep2
-        denom = (g1 + g2).clamp_min(torch.finfo(gates.dtype).eps)
-        weights = torch.stack([g1 / denom, g2 / denom], 1)
-        return (l_aux, weights, torch.stack([idx1, idx2], 1), torch.stack([slot1, slot2], 1),
-                torch.stack([keep1, keep2], 1), cap, counts)
+        return _route(logits, self.k, cf, self.min_capacity, self.noisy_gate_policy, self.drop_tokens, self.use_rts)
 
 
 class Experts(nn.Module):
@@ -428,6 +434,31 @@ def all_to_all(x, output_split_sizes=None, input_split_sizes=None, group=None, a
     if output_split_sizes is None and input_split_sizes is None:
         return _AllToAll.apply(group, x)
     return _AllToAllV.apply(group, x, list(input_split_sizes), list(output_split_sizes))
+
+
+def _dense_routing(l_aux, weights, experts, slots, keep, cap, counts, num_experts):
+    """Index form → the dense GShard tensors ``combine_weights [S, E, C]`` / ``dispatch_mask [S, E, C]``."""
+    S, k = experts.shape
+    combine = weights.new_zeros(S, num_experts, cap)
+    tok = torch.arange(S, device=experts.device).unsqueeze(1).expand(S, k)
+    combine.index_put_((tok[keep], experts[keep], slots[keep]), weights[keep], accumulate=True)
+    return l_aux, combine, combine.bool(), counts
+
+
+def top1gating(logits, capacity_factor, min_capacity, used_token=None, noisy_gate_policy=None, drop_tokens=True,
+               use_rts=True):
+    """Top-1 gating on logits in the dense form of the reference (``gshard_layer.py:138-218``) →
+    ``(l_aux, combine_weights[S, E, C], dispatch_mask[S, E, C], exp_counts[E])``.  The layers use the index form
+    (:func:`_route`); this is the O(S·E·C) view of the same decision for inspection and tests."""
+    assert used_token is None, "token masks are applied by the caller in this framework"
+    E = logits.shape[1]
+    return _dense_routing(*_route(logits.float(), 1, capacity_factor, min_capacity, noisy_gate_policy, drop_tokens, use_rts), E)
+
+
+def top2gating(logits, capacity_factor, min_capacity):
+    """Top-2 gating (second expert after Gumbel noise, weights renormalised; reference ``:221-284``), dense form."""
+    E = logits.shape[1]
+    return _dense_routing(*_route(logits.float(), 2, capacity_factor, min_capacity, None, True, False), E)
 
 
 # reference class names (``moe/utils.py``, ``moe/megablock/megablock_{moe,dmoe}.py``)

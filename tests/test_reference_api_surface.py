@@ -428,3 +428,35 @@ def test_volc_and_ali_object_stores(monkeypatch, tmp_path, url):
     if url.startswith("volc"):
         assert fake.tos_args == ("ak", "sk", "tos-cn-beijing.volces.com", "cn-beijing")
     assert sm.get_mount_point_free_size(str(tmp_path)) > 0
+
+
+def test_dense_gating_functions_agree_with_the_layer_and_the_einsum_form():
+    from internlm.model.moe.gshard_layer import TopKGate, top1gating, top2gating
+
+    torch.manual_seed(0)
+    S, h, E = 48, 16, 4
+    x = torch.randn(S, h)
+    for k in (1, 2):
+        gate = TopKGate(h, E, k=k, capacity_factor=1.0, min_capacity=4, use_rts=False)
+        logits = torch.nn.functional.linear(x, gate.wg.weight)
+        torch.manual_seed(7)
+        l_aux, w, ex, sl, keep, cap, counts = gate(x)
+        torch.manual_seed(7)                                         # same Gumbel draw for the second expert
+        l2, combine, mask, c2 = (top1gating(logits, 1.0, 4, use_rts=False) if k == 1 else top2gating(logits, 1.0, 4))
+        assert combine.shape == (S, E, cap) and torch.equal(c2, counts) and torch.allclose(l2, l_aux)
+        assert mask.sum(0).max() <= 1, "one token per (expert, slot)"
+        assert mask.sum((1, 2)).max() <= k and int(mask.sum()) == int(keep.sum())
+        assert mask.sum((0, 2)).max() <= cap
+        # dense dispatch / combine einsums (GShard) == index scatter / gather used by the layer
+        dispatched = torch.einsum("sec,sm->ecm", mask.float(), x)
+        rows = (ex * cap + sl)[keep]
+        tok = torch.arange(S).unsqueeze(1).expand(S, k)[keep]
+        want = torch.zeros(E * cap, h).index_copy(0, rows, x[tok]).view(E, cap, h)
+        assert torch.allclose(dispatched, want)
+        y = torch.randn(E, cap, h)
+        combined = torch.einsum("sec,ecm->sm", combine, y)
+        want = torch.zeros(S, h).index_add_(0, tok, y.view(E * cap, h)[rows] * w[keep].unsqueeze(1))
+        assert torch.allclose(combined, want, atol=1e-6)
+        if k == 2:
+            kept_both = keep.all(1)
+            assert torch.allclose(combine.sum((1, 2))[kept_both], torch.ones(int(kept_both.sum())), atol=1e-6)
