@@ -95,7 +95,7 @@ def test_optimizer_tensor_list_helpers():
     params = [torch.nn.Parameter(t.clone()) for t in g[:2]]
     sync_param(flat, params)
     flat.zero_()
-    assert all(float(p.abs().sum()) == 0 for p in params)            # they alias the flat buffer now
+    assert all(float(p.detach().abs().sum()) == 0 for p in params)            # they alias the flat buffer now
     for p in params:
         p.grad = torch.ones_like(p)
     release_param_grad(params)
