@@ -241,17 +241,21 @@ class CheckpointManager:
             t = torch.tensor([signal], device=get_current_device(), dtype=torch.int64)
             dist.broadcast(t, src=0)
             signal = int(t.item())
-        if signal != 0 and train_state.step_count >= abs(signal) - 0 and not self.ckpt_quit_signal_handled:
-            if train_state.step_count == abs(signal) or train_state.step_count > abs(signal):
-                now_save_ckpt = True
-                now_break = signal > 0
-                self.ckpt_quit_signal_handled = True
-                if gpc.get_global_rank() == 0:
-                    with open(self.stop_file_path, "w", encoding="utf-8") as f:
-                        f.write("0")
-                    msg = "Stop file: saving a checkpoint" + (" and quitting" if now_break else "")
-                    logger.warning(msg + f" at step {train_state.step_count}")
-                    send_alert_message(address=self.feishu_address, message=msg)
+        # The request fires at exactly step |N| (reference ``:355-371``); rank 0 then rewrites the file to 0, which also
+        # re-arms the protocol: a later request in the same run (e.g. "-100" then "200") is honoured again.
+        if signal != 0 and train_state.step_count == abs(signal):
+            now_save_ckpt = True
+            now_break = signal > 0
+            if gpc.get_global_rank() == 0:
+                with open(self.stop_file_path, "w", encoding="utf-8") as f:
+                    f.write("0")
+                msg = "Stop file: saving a checkpoint" + (" and quitting" if now_break else "")
+                logger.warning(msg + f" at step {train_state.step_count}")
+                send_alert_message(address=self.feishu_address, message=msg)
+        elif signal != 0 and train_state.step_count > abs(signal) and gpc.get_global_rank() == 0 \
+                and not self.ckpt_quit_signal_handled:
+            self.ckpt_quit_signal_handled = True   # warn once: the requested step has already passed
+            logger.warning(f"Stop file asks for step {abs(signal)} but training is at step {train_state.step_count}; ignored")
         return now_break, now_save_ckpt, save_type
 
     def is_now_to_save_ckpt(self, train_state, force=False) -> (bool, CheckpointSaveType, bool):

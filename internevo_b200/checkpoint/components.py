@@ -37,26 +37,67 @@ def _should_save_model():
     return gpc.get_local_rank(ParallelMode.DATA) == 0
 
 
-def _split_expert_states(states: dict):
-    """Pull expert tensors out into ``{(layer, global_expert): {key: tensor}}`` (per-expert files, reference ``:53-92``)."""
+def _chunk_layer_offsets(model) -> dict:
+    """``{state-dict prefix of a pipeline chunk: global index of its first block}``.  Every stage numbers its blocks from 0,
+    so per-expert file names take the chunk's ``start_layer_idx`` (reference ``components.py:53-92`` uses
+    ``pp_rank * layers_per_stage + i``; interleaved chunks are covered too)."""
+    offs = {}
+    for name, mod in model.named_modules():
+        if hasattr(mod, "start_layer_idx") and hasattr(mod, "spec"):
+            offs[name] = int(mod.start_layer_idx)
+    return offs or {"": 0}
+
+
+def _layer_offset(prefix: str, offsets: dict) -> int:
+    """``prefix`` is everything before ``.<local layer>.`` (e.g. ``model.layers`` or ``1.layers``): longest chunk name wins."""
+    best, off = -1, 0
+    for name, o in offsets.items():
+        if (name == "" or prefix == name or prefix.startswith(name + ".")) and len(name) > best:
+            best, off = len(name), o
+    return off
+
+
+def _expert_geometry():
     ep_rank = gpc.get_local_rank(ParallelMode.EXPERT) if gpc.is_initialized(ParallelMode.EXPERT) else 0
+    n_local = gpc.config.model.get("num_experts", 1) // max(1, gpc.expert_parallel_size)
+    return ep_rank, n_local
+
+
+def _split_expert_states(states: dict, offsets: dict):
+    """Pull expert tensors out into ``{(global layer, global expert): {key: tensor}}``.  Inside a file the key carries the
+    GLOBAL expert id (``wrapped_experts.<global>``), so a checkpoint can be re-read under another expert-parallel size and
+    exchanged with the reference (``try_save_moe_checkpoint``, reference ``components.py:53-92``)."""
+    ep_rank, n_local = _expert_geometry()
     experts, rest = {}, {}
     for k, v in states.items():
         m = _EXPERT_KEY.match(k)
         if m is None:
             rest[k] = v
             continue
-        layer, local_e = int(m.group(2)), int(m.group(3))
-        n_local = gpc.config.model.get("num_experts", 1) // max(1, gpc.expert_parallel_size)
-        experts.setdefault((layer, ep_rank * n_local + local_e), {})[k] = v
+        prefix, layer, local_e, tail = m.group(1), int(m.group(2)), int(m.group(3)), m.group(4)
+        glob_e = ep_rank * n_local + local_e
+        gkey = k[: m.start(3)] + str(glob_e) + k[m.end(3):]
+        assert gkey.endswith(tail)
+        experts.setdefault((layer + _layer_offset(prefix, offsets), glob_e), {})[gkey] = v
     return rest, experts
+
+
+def _expert_keys_to_local(st: dict, glob_e: int, local_e: int) -> dict:
+    out = {}
+    for k, v in st.items():
+        m = _EXPERT_KEY.match(k)
+        if m is None or int(m.group(3)) not in (glob_e, local_e):
+            raise KeyError(f"unexpected key {k!r} in the file of expert {glob_e}")
+        out[k[: m.start(3)] + str(local_e) + k[m.end(3):]] = v
+    return out
 
 
 def save_model_checkpoint(folder, model):
     """``model_tp*_pp*.pt`` + topology json (+ one file per global expert)."""
     states = get_shard_state_dict(model)
     states = {k: v.detach().clone().cpu() if torch.is_tensor(v) else v for k, v in states.items()}
-    states, experts = _split_expert_states(states) if gpc.config.model.get("num_experts", 1) > 1 else (states, {})
+    states, experts = (_split_expert_states(states, _chunk_layer_offsets(model))
+                       if gpc.config.model.get("num_experts", 1) > 1 else (states, {}))
     if folder is None:
         return
     tp = gpc.get_local_rank(ParallelMode.TENSOR)
@@ -75,6 +116,33 @@ def save_model_checkpoint(folder, model):
         torch.cuda.synchronize()
 
 
+def _load_expert_files(folder, fns, model) -> dict:
+    """This stage's layers x this rank's experts, keys mapped back to the local numbering of both."""
+    tp = gpc.get_local_rank(ParallelMode.TENSOR)
+    ep_rank, n_local = _expert_geometry()
+    offsets = _chunk_layer_offsets(model)
+    # (global layer) -> state-dict prefix + local layer, for every MoE block this rank holds
+    where = {}
+    for k in model.state_dict().keys():
+        m = _EXPERT_KEY.match(k)
+        if m is not None:
+            where[int(m.group(2)) + _layer_offset(m.group(1), offsets)] = (m.group(1), int(m.group(2)))
+    out = {}
+    for fn in fns:
+        m = re.match(rf"model_moe_layer(\d+)_expert(\d+)_tp{tp}\.pt$", fn)
+        if m is None:
+            continue
+        layer, e = int(m.group(1)), int(m.group(2))
+        if layer not in where or not ep_rank * n_local <= e < (ep_rank + 1) * n_local:
+            continue
+        prefix, local_layer = where[layer]
+        st = _expert_keys_to_local(llm_load(os.path.join(folder, fn), map_location="cpu"), e, e - ep_rank * n_local)
+        for k, v in st.items():   # the file was written under the saver's chunk prefix / local layer: re-home it
+            km = _EXPERT_KEY.match(k)
+            out[f"{prefix}.{local_layer}." + k[km.end(2) + 1:]] = v
+    return out
+
+
 def load_model_checkpoint(folder, model):
     """Loads this rank's shard; asserts that tp/pp sizes match the checkpoint (reference ``:146-158``)."""
     fns = get_fns(folder)
@@ -90,14 +158,10 @@ def load_model_checkpoint(folder, model):
     fp = os.path.join(folder, _model_fn())
     states = llm_load(fp, map_location="cpu")
     if gpc.config.model.get("num_experts", 1) > 1:
-        tp = gpc.get_local_rank(ParallelMode.TENSOR)
-        ep_rank = gpc.get_local_rank(ParallelMode.EXPERT)
-        n_local = gpc.config.model.num_experts // gpc.expert_parallel_size
-        for fn in fns:
-            m = re.match(rf"model_moe_layer(\d+)_expert(\d+)_tp{tp}\.pt$", fn)
-            if m and ep_rank * n_local <= int(m.group(2)) < (ep_rank + 1) * n_local:
-                states.update(llm_load(os.path.join(folder, fn), map_location="cpu"))
+        states.update(_load_expert_files(folder, fns, model))
     missing_k, unexpected_keys = load_shard_state_dict(model, states, strict=False)
+    lost = [k for k in missing_k if _EXPERT_KEY.match(k)]
+    assert not lost, f"expert weights missing from the checkpoint (they would keep their random init): {lost[:4]}..."
     if len(missing_k) != 0 and gpc.is_rank_for_log():
         logger.warning(f"Warning: missing keys {missing_k}")
     if len(unexpected_keys) != 0 and gpc.is_rank_for_log():

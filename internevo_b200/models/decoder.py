@@ -179,7 +179,10 @@ class DecoderLayer(nn.Module):
             # residual_{l} = dropout(hidden) + residual ; hidden = norm1(residual)   -- one fused kernel
             if residual is None:
                 residual = self._drop(hidden_states)
-                hidden_states = norm1(residual)
+                if self.residual_in_fp32 and residual.dtype != torch.float32:
+                    hidden_states, residual = norm1(torch.zeros_like(residual), residual.float())
+                else:
+                    hidden_states = norm1(residual)
             else:
                 hidden_states, residual = norm1(self._drop(hidden_states), residual)
             hidden_states = attn(hidden_states, cu_seqlens=cu_seqlens, indexes=indexes, max_seqlen=max_seqlen,
@@ -221,6 +224,7 @@ class PackedDecoder(nn.Module):
         super().__init__()
         self.spec = spec
         self.first, self.last = first, last
+        self.start_layer_idx = start_layer_idx   # global index of this chunk's first block (per-expert checkpoint names)
         self.embed_grad_scale = embed_grad_scale
         self.parallel_output = parallel_output
         self.tp_mode = _tp_mode()
@@ -353,7 +357,7 @@ class PackedDecoder(nn.Module):
                 hidden_states = gather_forward_split_backward(hidden_states, gpc.get_group(ParallelMode.TENSOR), dim=-1)
         elif residual is not None:
             # pipeline boundary: ship one tensor (hidden + residual folded), the next stage restarts the pair
-            hidden_states = hidden_states + residual
+            hidden_states = (hidden_states + residual).to(hidden_states.dtype)   # residual may be fp32 (residual_in_fp32)
         if self.is_moe:
             return hidden_states, moe_losses
         return hidden_states

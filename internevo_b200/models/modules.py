@@ -241,7 +241,8 @@ class MHA(nn.Module):
         D = self.head_dim
         sp_group = self.sequence_process_group if self.tp_mode == "isp" else None
         packed, self._packed = self._packed, None
-        if packed is not None and not (sp_group is not None and _ws(sp_group) > 1):
+        drop_p = float(self.dropout) if self.training else 0.0
+        if packed is not None and drop_p == 0.0 and not (sp_group is not None and _ws(sp_group) > 1):
             if cu_seqlens is None:
                 cu_seqlens = torch.tensor([0, T], device=x.device, dtype=torch.int32)
                 max_seqlen = T
@@ -257,7 +258,8 @@ class MHA(nn.Module):
         if cu_seqlens is None:
             cu_seqlens = torch.tensor([0, q.shape[0]], device=q.device, dtype=torch.int32)
             max_seqlen = q.shape[0]
-        ctx = flash_attention_varlen(q, k, v, cu_seqlens, max_seqlen, causal=self.causal, scale=self.softmax_scale)
+        ctx = flash_attention_varlen(q, k, v, cu_seqlens, max_seqlen, causal=self.causal, scale=self.softmax_scale,
+                                     dropout_p=drop_p)
         if sp_group is not None and _ws(sp_group) > 1:
             ctx = seq_all_to_all(ctx, sp_group, scatter_dim=0, gather_dim=1)
         ctx = ctx.reshape(ctx.shape[0], -1)

@@ -14,11 +14,16 @@ from . import _lib
 from .gemm import _bump
 
 
+# The kernels read bf16 or fp32 gradients; fp16 models (``model.dtype`` defaults to ``torch.float16`` as in the reference,
+# ``initialize/launch.py``) take the plain PyTorch arithmetic below instead of tripping the kernel's dtype check.
+_NATIVE_GRAD = (torch.bfloat16, torch.float32)
+
+
 def sumsq_(g: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     """``out[0] += sum(g^2)`` (fp32)."""
     if g.numel() == 0:
         return out
-    if _lib.use_native(g, out):
+    if _lib.use_native(g, out) and g.dtype in _NATIVE_GRAD:
         torch.ops.b200.sumsq(g.contiguous().view(-1), out)
         _bump()
     else:
@@ -52,7 +57,7 @@ def adamw_(p: torch.Tensor, m: torch.Tensor, v: torch.Tensor, g: torch.Tensor, p
     bc2 = 1.0 - beta2 ** step
     if p.numel() == 0:
         return
-    if _lib.use_native(p, g):
+    if _lib.use_native(p, g) and g.dtype in _NATIVE_GRAD and (p_lp is None or p_lp.dtype in _NATIVE_GRAD):
         torch.ops.b200.adamw(p, m, v, g, p_lp, lr, beta1, beta2, eps, weight_decay, bc1, bc2, scalars)
         _bump()
         return

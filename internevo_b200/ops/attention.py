@@ -141,11 +141,53 @@ def _b200_available() -> bool:
     return _lib.available()
 
 
+_warned_dropout = False
+
+
+def _attention_with_dropout(q, k, v, cu_seqlens, max_seqlen, causal, scale, dropout_p):
+    """Attention-probability dropout (``model.attn_drop_rate`` > 0 while training; reference
+    ``multi_head_attention.py:27-53`` passes it to flash-attn).  The tcgen05 kernel has no in-kernel Philox dropout, so this
+    knob runs the flash-attn library kernel - said once in the log - or, without it / on CPU, an explicit softmax → dropout
+    path per sequence.  It is never silently ignored."""
+    global _warned_dropout
+    if q.is_cuda:
+        try:
+            from flash_attn import flash_attn_varlen_func
+
+            if not _warned_dropout:
+                _warned_dropout = True
+                import logging
+
+                logging.getLogger(__name__).warning(
+                    "attn_drop_rate=%.3f: attention dropout runs on the flash-attn library kernel, not the tcgen05 kernel",
+                    dropout_p)
+            return flash_attn_varlen_func(q, k, v, cu_seqlens.int(), cu_seqlens.int(), int(max_seqlen), int(max_seqlen),
+                                          dropout_p=dropout_p, softmax_scale=scale, causal=causal)
+        except ImportError:
+            pass
+    H, Hkv = q.shape[1], k.shape[1]
+    outs = []
+    cu = cu_seqlens.tolist()
+    for a, b in zip(cu[:-1], cu[1:]):
+        qs = q[a:b].transpose(0, 1).float()
+        ks = k[a:b].transpose(0, 1).float().repeat_interleave(H // Hkv, 0)
+        vs = v[a:b].transpose(0, 1).float().repeat_interleave(H // Hkv, 0)
+        s_ = torch.einsum("hqd,hkd->hqk", qs, ks) * scale
+        if causal:
+            n = b - a
+            s_ = s_.masked_fill(torch.ones(n, n, dtype=torch.bool, device=q.device).triu(1), float("-inf"))
+        p = torch.nn.functional.dropout(torch.softmax(s_, -1), dropout_p, True)
+        outs.append(torch.einsum("hqk,hkd->hqd", p, vs).transpose(0, 1).to(q.dtype))
+    return torch.cat(outs, 0)
+
+
 def flash_attention_varlen(q, k, v, cu_seqlens, max_seqlen: int, causal: bool = True, scale: Optional[float] = None,
-                           impl: Optional[str] = None) -> torch.Tensor:
+                           impl: Optional[str] = None, dropout_p: float = 0.0) -> torch.Tensor:
     """q ``[T, H, D]`` bf16, k/v ``[T, Hkv, D]``; returns ``[T, H, D]``."""
     scale = scale or 1.0 / math.sqrt(q.shape[-1])
     impl = impl or _IMPL
+    if dropout_p > 0.0:
+        return _attention_with_dropout(q, k, v, cu_seqlens, max_seqlen, causal, scale, dropout_p)
     if not q.is_cuda:
         return attention_ref(q, k, v, cu_seqlens, causal, scale).to(q.dtype)
     if cu_seqlens.dtype != torch.int32:

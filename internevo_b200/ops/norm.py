@@ -75,6 +75,11 @@ def add_rmsnorm(
 ) -> Tuple[torch.Tensor, torch.Tensor]:
     """``new_res = x + residual``; ``y = RMSNorm(new_res) * weight``.  Returns ``(y, new_res)``."""
     H = x.shape[-1]
+    if residual is not None and residual.dtype != x.dtype:
+        # ``model.residual_in_fp32``: the residual stream stays fp32 across blocks (reference ``modeling_internlm2.py:697-707``);
+        # the normalised activations go back to the compute dtype
+        new_res = x.to(residual.dtype) + residual
+        return rmsnorm_ref(new_res, weight, eps).to(x.dtype), new_res
     if (
         _lib.use_native(x, weight)
         and x.dtype == torch.bfloat16

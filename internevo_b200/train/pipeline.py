@@ -216,6 +216,12 @@ def load_new_batch(train_dl: DataLoader, train_iter: Iterable, train_state: Trai
     except StopIteration:
         train_iter = iter(train_dl)
         batch = next(train_iter)
+        # The anchor sampler trails the loader's own copy by exactly one `next`: drive its suspended generator over the end
+        # so it reshuffles (``get_indices``) once, like the copy did, before a fresh generator is started on the new epoch.
+        old_anchor = getattr(train_state, "batch_sampler_iter", None)
+        if old_anchor is not None:
+            for _ in old_anchor:
+                pass
         train_state.batch_sampler_iter = iter(train_state.batch_sampler)
         next(train_state.batch_sampler_iter)
         train_state.num_consumed_samples_in_epoch = 0

@@ -65,6 +65,21 @@ def _run(rank, world, folder, phase):
         if rank == 0:
             assert os.path.exists(os.path.join(folder, "6", "6.step"))
             assert open(os.path.join(folder, "stop")).read().strip() == "0"
+        # a second request in the same run is honoured too: "-8" = save at step 8 and continue; nothing happens at step 7
+        torch.distributed.barrier()
+        if rank == 0:
+            open(os.path.join(folder, "stop"), "w").write("-8")
+        torch.distributed.barrier()
+        ts.step_count, ts.batch_count = 7, 6
+        assert mm.try_save_checkpoint(ts) is False
+        torch.distributed.barrier()
+        assert not os.path.exists(os.path.join(folder, "7"))
+        ts.step_count, ts.batch_count = 8, 7
+        assert mm.try_save_checkpoint(ts) is False
+        mm.wait_async_upload_finish()
+        if rank == 0:
+            assert os.path.exists(os.path.join(folder, "8", "8.step"))
+            assert open(os.path.join(folder, "stop")).read().strip() == "0"
     return losses
 
 
@@ -128,6 +143,8 @@ import pytest  # noqa: E402
     ("tp2_pp2", 4, dict(tp=2, pp=2), False),
     ("isp_sp2_wp2", 2, dict(tp=2, wp=2, mode="isp"), False),
     ("moe_ep2", 2, dict(model_type="INTERNLM_MoE", num_experts=4, moe_type="MegaBlock-D"), True),  # dropless: no gate noise
+    # MoE x pipeline: every stage numbers its blocks from 0 - the per-expert files must carry GLOBAL layer ids
+    ("moe_pp2", 2, dict(pp=2, model_type="INTERNLM_MoE", num_experts=4, moe_type="MegaBlock-D"), True),
 ])
 def test_resume_is_exact_for_model_parallel_and_moe_layouts(tmp_path, name, world, kw, moe):
     first = run_distributed(_run_layout, world, str(tmp_path), "first", kw, moe)
@@ -140,3 +157,12 @@ def test_resume_is_exact_for_model_parallel_and_moe_layouts(tmp_path, name, worl
                 assert abs(l0 - l1) < 1e-6, (name, first[r], resumed[r])
             for (k0, v0), (k1, v1) in zip(n0, n1):
                 assert k0 == k1 and abs(v0 - v1) < 1e-5 * max(1.0, abs(v0)), (name, n0, n1)
+    if moe:
+        import glob
+        import re as _re
+
+        files = sorted(os.path.basename(f) for f in glob.glob(os.path.join(str(tmp_path), "2", "model_moe_layer*")))
+        layers = {int(_re.match(r"model_moe_layer(\d+)_", f).group(1)) for f in files}
+        assert layers == {0, 1} and len(files) == 2 * 4, files    # 2 global layers x 4 global experts, no collisions
+        st = torch.load(os.path.join(str(tmp_path), "2", "model_moe_layer1_expert3_tp0.pt"), weights_only=False)
+        assert st and all(".wrapped_experts.3." in k for k in st), list(st)[:3]   # keys carry the global expert id

@@ -93,3 +93,43 @@ def test_ranks_get_disjoint_samples():
     xa, xb = next(iter(a)), next(iter(b))
     assert not set(xa.tolist()) & set(xb.tolist())
 
+
+
+def test_load_new_batch_crosses_epoch_boundary():
+    """Three epochs through ``load_new_batch``: the loader restarts, the resume anchor reshuffles in lock step with the
+    loader's own sampler copy (same batches, same order) and its counters restart (reference ``train/pipeline.py:381-414``)."""
+    import torch
+    from torch.utils.data import DataLoader
+
+    from internevo_b200.core.trainer import TrainState
+    from internevo_b200.train.pipeline import load_new_batch
+
+    gpc.set_config(Config(dict(data=dict(micro_bsz=1, total_steps=100, use_packed_dataset=True), adam=dict(lr=1e-4),
+                               model=dict(use_flash_attn=True))))
+
+    class _DS(torch.utils.data.Dataset):
+        def __len__(self):
+            return 12
+
+        def __getitem__(self, i):
+            return i
+
+    def collate(items):
+        return ({"input_ids": torch.tensor(items)[None], "cu_seqlens": torch.tensor([[0, len(items)]])}, torch.tensor(items))
+
+    ds = _DS()
+    sampler = StaticBatchSampler([ds], batch_size=4, rampup_batch_size="", micro_bsz=1, seed=3, data_rank=0, data_world_size=1)
+    state = TrainState(gpc.config, sampler)
+    dl = DataLoader(ds, batch_sampler=sampler, collate_fn=collate, num_workers=0)
+    it = iter(dl)
+    seen = []
+    for step in range(9):   # 3 batches per epoch
+        expect = state.batch_sampler.indices[(step % 3) * 4:(step % 3) * 4 + 4] if step % 3 else None
+        (data, labels), it = load_new_batch(dl, it, state)
+        if expect is not None:   # the anchor walks the very permutation the loader is serving
+            assert labels.tolist() == list(expect)
+        seen.append(labels.tolist())
+    for e in range(3):
+        assert sorted(sum(seen[3 * e:3 * e + 3], [])) == list(range(12))
+    assert seen[0:3] != seen[3:6]   # reshuffled between epochs
+    assert state.batch_sampler.num_consumed_samples_in_epoch == 12

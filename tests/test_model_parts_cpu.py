@@ -149,3 +149,40 @@ def test_hung_collective_raises_within_the_group_timeout():
     res = run_distributed(_hang, 2, timeout=60)
     status, elapsed, _ = res[0]
     assert status == "raised" and elapsed < 11, res
+
+
+def _knobs(rank, world, extra):
+    """One training step with a model-config knob switched on; returns the loss and what the knob must have changed."""
+    cfg = tiny_config(num_layers=2, dtype="torch.bfloat16", **extra)
+    trainer, opt, model, _ = build_trainer(cfg)
+    seen = {}
+
+    def grab(mod, args, kwargs=None):
+        if len(args) > 1 and torch.is_tensor(args[1]):
+            seen["residual_dtype"] = str(args[1].dtype)
+
+    layers = [m for m in model.modules() if type(m).__name__ == "DecoderLayer"]
+    layers[1].register_forward_pre_hook(grab)
+    data, labels = synthetic_batch(2, 64, cfg["model"]["vocab_size"], seed=3)
+    losses = []
+    for _ in range(2):
+        trainer.zero_grad()
+        out = trainer.execute_schedule((data, labels), forward_only=False, return_loss=True, return_output_label=False)
+        ok, _ = trainer.step()
+        assert ok
+        losses.append(float(out[2]))
+    return losses, seen
+
+
+def test_residual_in_fp32_keeps_an_fp32_residual_stream():
+    (base, seen0), = run_distributed(_knobs, 1, dict())
+    (fp32, seen1), = run_distributed(_knobs, 1, dict(residual_in_fp32=True))
+    assert seen0["residual_dtype"] == "torch.bfloat16" and seen1["residual_dtype"] == "torch.float32"
+    assert all(l == l for l in fp32) and abs(fp32[0] - base[0]) < 0.05
+
+
+def test_attention_dropout_is_applied_in_training():
+    (base, _), = run_distributed(_knobs, 1, dict())
+    (drop, _), = run_distributed(_knobs, 1, dict(attn_drop_rate=0.5))
+    assert all(l == l for l in drop)
+    assert abs(drop[0] - base[0]) > 1e-4, "attn_drop_rate had no effect on the training loss"
