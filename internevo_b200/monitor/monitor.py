@@ -28,52 +28,63 @@ def send_alert_message(address: str = None, title: str = None, message: str = No
         logger.warning(f"[alert] {title or get_job_key()}: {message}")
 
 
+def _env_number(key: str):
+    """Numeric value another part of the process published through the environment, or ``None``."""
+    raw = os.getenv(key)
+    if raw is None:
+        return None
+    try:
+        return float(raw)
+    except ValueError:
+        return None
+
+
 class MonitorTracker(Thread):
-    """Polls ``LAST_ACTIVE_TIMESTAMP`` (refreshed every step) and alerts when training looks stuck."""
+    """Watchdog thread.  The training loop publishes a heartbeat (``LAST_ACTIVE_TIMESTAMP``) and, on the log rank, the
+    latest ``LOSS`` / ``STEP_ID`` through the process environment (``train/pipeline.py``); every ``check_interval`` seconds
+    this thread compares them with what it saw last time: a heartbeat that did not advance means a hang, a loss that grew by
+    more than ``loss_spike_limit`` x means a spike (reference behaviour: ``internlm/monitor/monitor.py:35-118``)."""
+
+    daemon = True
 
     def __init__(self, alert_address: str, check_interval: float = 300, loss_spike_limit: float = 1.5):
         super().__init__()
         self.alert_address = alert_address
         self.check_interval = check_interval
         self.loss_spike_limit = loss_spike_limit
-        self.last_active_time = -1
-        self.last_loss_value = -1
+        self._seen_heartbeat = None
+        self._seen_loss = None
         self.stopped = False
         self.start()
 
     def run(self):
         while not self.stopped:
-            try:
-                self._check_stuck()
-                self._check_loss_spike()
-            except Exception:  # pragma: no cover
-                continue
-            slept = 0.0
-            while slept < self.check_interval and not self.stopped:
-                time.sleep(min(1.0, self.check_interval - slept))
-                slept += 1.0
+            for probe in (self._check_stuck, self._check_loss_spike):
+                try:
+                    probe()
+                except Exception as e:  # pragma: no cover - a monitoring failure must never take the job down
+                    logger.debug(f"monitor probe failed: {e}")
+            deadline = time.monotonic() + self.check_interval
+            while not self.stopped and time.monotonic() < deadline:
+                time.sleep(min(1.0, max(0.0, deadline - time.monotonic())))
 
     def _check_stuck(self):
-        new_active_time = -1
-        if os.getenv("LAST_ACTIVE_TIMESTAMP") is not None:
-            new_active_time = os.getenv("LAST_ACTIVE_TIMESTAMP")
-        if int(new_active_time) <= int(self.last_active_time) and new_active_time != -1:
-            self._send_alert("Training may be in stuck status, please check it.")
-        self.last_active_time = new_active_time
+        beat = _env_number("LAST_ACTIVE_TIMESTAMP")
+        if beat is not None and self._seen_heartbeat is not None and beat <= self._seen_heartbeat:
+            self._send_alert(f"No training step finished during the last {self.check_interval:.0f} s: the job may be stuck.")
+        if beat is not None:
+            self._seen_heartbeat = beat
 
     def _check_loss_spike(self):
-        if gpc.is_rank_for_log():
-            new_loss_value = -1
-            new_step_id = -1
-            if os.getenv("LOSS") is not None:
-                new_loss_value = os.getenv("LOSS")
-            if os.getenv("STEP_ID") is not None:
-                new_step_id = os.getenv("STEP_ID")
-            if (float(new_loss_value) / float(self.last_loss_value)) > self.loss_spike_limit and new_loss_value != -1:
-                assert int(new_step_id) >= 0
-                self._send_alert(f"Checking periodically: Loss spike may be happened in step {new_step_id}, "
-                                 f"loss value from {self.last_loss_value} to {new_loss_value}, please check it.")
-            self.last_loss_value = new_loss_value
+        if not gpc.is_rank_for_log():
+            return
+        loss, step = _env_number("LOSS"), _env_number("STEP_ID")
+        if loss is None:
+            return
+        prev, self._seen_loss = self._seen_loss, loss
+        if prev is not None and prev > 0 and loss / prev > self.loss_spike_limit:
+            self._send_alert(f"Periodic check: possible loss spike around step {int(step) if step is not None else '?'} "
+                             f"({prev:.4f} -> {loss:.4f}).")
 
     def _send_alert(self, message):
         send_alert_message(address=self.alert_address, message=message)
@@ -83,6 +94,8 @@ class MonitorTracker(Thread):
 
 
 class MonitorManager(metaclass=SingletonMeta):
+    """Process-wide switchboard: owns the watchdog thread, per-step spike check, exception and SIGTERM alerts."""
+
     def __init__(self, loss_spike_limit: float = 1.5) -> None:
         self.monitor_thread = None
         self.loss_spike_limit = loss_spike_limit
@@ -92,19 +105,21 @@ class MonitorManager(metaclass=SingletonMeta):
         self.light_monitor_address = None
 
     def monitor_loss_spike(self, alert_address: str = None, step_count: int = 0, cur_step_loss: float = 0.0):
-        """Alert when the loss jumps by more than ``loss_spike_limit`` between consecutive steps."""
-        if self.enable_alert:
-            set_env_var(key="LOSS", value=cur_step_loss)
-            set_env_var(key="STEP_ID", value=step_count)
-            if self.last_step_loss != -1 and cur_step_loss > self.loss_spike_limit * self.last_step_loss:
-                send_alert_message(address=alert_address, message=(
-                    f"Checking step by step: Loss spike may be happened in step {step_count}, "
-                    f"loss value from {self.last_step_loss} to {cur_step_loss}, please check it."))
-            self.last_step_loss = cur_step_loss
+        """Per-step check (the watchdog repeats it at its own period); also publishes loss / step for the watchdog."""
+        if not self.enable_alert:
+            return
+        set_env_var(key="LOSS", value=cur_step_loss)
+        set_env_var(key="STEP_ID", value=step_count)
+        prev, self.last_step_loss = self.last_step_loss, cur_step_loss
+        if prev != -1 and cur_step_loss > self.loss_spike_limit * prev:
+            send_alert_message(address=alert_address,
+                               message=f"Step {step_count}: loss went from {prev} to {cur_step_loss} "
+                                       f"(> {self.loss_spike_limit}x), possible loss spike.")
 
     def exception_should_be_alert(self, msg: str, alert_address: str = None):
-        """Only the first rank to write the (flock'd) alert file sends; the rest stay quiet (reference ``:158-176``)."""
-        if self.enable_alert is False:
+        """De-duplication across ranks: the alert file is an flock'd set of already reported messages; only the rank that
+        adds a message reports it (reference ``:158-176``)."""
+        if not self.enable_alert:
             return False
         if self.alert_file_path is None:
             return True
@@ -112,35 +127,38 @@ class MonitorManager(metaclass=SingletonMeta):
             os.makedirs(os.path.dirname(self.alert_file_path) or ".", exist_ok=True)
             with open(self.alert_file_path, "a+") as f:
                 fcntl.flock(f, fcntl.LOCK_EX)
-                f.seek(0)
-                if msg in f.read():
+                try:
+                    f.seek(0)
+                    known = set(f.read().splitlines())
+                    if msg in known:
+                        return False
+                    f.write(msg + "\n")
+                    return True
+                finally:
                     fcntl.flock(f, fcntl.LOCK_UN)
-                    return False
-                f.write(msg + "\n")
-                fcntl.flock(f, fcntl.LOCK_UN)
-            return True
-        except Exception:  # pragma: no cover
+        except OSError:  # pragma: no cover - an unwritable alert file must not hide the exception
             return True
 
     def monitor_exception(self, alert_address: str = None, excp_info: str = None):
-        if self.enable_alert:
-            filtered = excp_info.split("\n")[-10:]
-            msg = "\n".join(filtered)
-            if self.exception_should_be_alert(filtered[-1] if filtered else "", alert_address):
-                message = f"Catch Exception from {socket.gethostname()} with rank id {gpc.get_global_rank()}:{msg}"
-                # exceptions are reported by whichever rank hits them, not only the log rank
-                if alert_address:
-                    send_feishu_msg_with_webhook(alert_address, get_job_key(), message)
-                else:
-                    logger.error(message)
+        if not self.enable_alert:
+            return
+        tail = (excp_info or "").strip().split("\n")[-10:]
+        if not self.exception_should_be_alert(tail[-1] if tail else "", alert_address):
+            return
+        message = (f"Exception on {socket.gethostname()} (global rank {gpc.get_global_rank()}):\n" + "\n".join(tail))
+        # exceptions are reported by whichever rank hits them, not only the log rank
+        if alert_address:
+            send_feishu_msg_with_webhook(alert_address, get_job_key(), message)
+        else:
+            logger.error(message)
 
     def handle_sigterm(self, alert_address: str = None):
-        def sigterm_handler(sys_signal, frame):
-            message = f"Process received signal {signal} and exited."
-            send_alert_message(address=alert_address, message=message)
-            raise SystemExit(128 + sys_signal)
+        def on_sigterm(signum, frame):
+            send_alert_message(address=alert_address,
+                               message=f"Process on {socket.gethostname()} received signal {signum} and is exiting.")
+            raise SystemExit(128 + signum)
 
-        signal.signal(signal.SIGTERM, sigterm_handler)
+        signal.signal(signal.SIGTERM, on_sigterm)
 
     def start_monitor(self, job_name: str, alert_address: str, monitor_interval_seconds: int = 300,
                       loss_spike_limit: float = 1.5):

@@ -1,44 +1,31 @@
-"""Thin wrapper exposing a ``torch.optim.Optimizer`` behind the engine's optimizer protocol — ``backward`` /
-``backward_by_grad`` / ``clip_grad_norm`` next to the usual ``step`` / ``zero_grad`` / ``state_dict``
-(reference ``internlm/solver/optimizer/base_optimizer.py:8-46``).  ``HybridZeroOptimizer`` and ``FSDPadaptOptimizer``
-implement the same protocol on their own storage; this class is for plugging a plain optimizer into ``Engine``."""
+"""Adapter that lets a plain ``torch.optim.Optimizer`` sit where ``Engine`` expects the framework's optimizer protocol
+(``backward`` / ``backward_by_grad`` / ``clip_grad_norm`` next to ``step`` / ``zero_grad`` / ``state_dict``; reference
+``internlm/solver/optimizer/base_optimizer.py:8-46``).  ``HybridZeroOptimizer`` and ``FSDPadaptOptimizer`` implement the
+protocol on their own storage; everything a wrapped optimizer already provides is forwarded by ``__getattr__`` instead of
+being re-declared method by method."""
 from __future__ import annotations
 
 import torch
+
+_FORWARDED = ("param_groups", "defaults", "state", "add_param_group", "step", "zero_grad", "load_state_dict", "state_dict")
 
 
 class BaseOptimizer:
     def __init__(self, optim: torch.optim.Optimizer):
         self.optim = optim
 
-    @property
-    def param_groups(self):
-        return self.optim.param_groups
+    def __getattr__(self, name):
+        # only reached for attributes this adapter does not define itself
+        if name in _FORWARDED:
+            return getattr(self.__dict__["optim"], name)
+        raise AttributeError(f"{type(self).__name__} has no attribute {name!r}")
 
-    @property
-    def defaults(self):
-        return self.optim.defaults
-
-    def add_param_group(self, *args, **kwargs):
-        return self.optim.add_param_group(*args, **kwargs)
-
-    def step(self, *args, **kwargs):
-        return self.optim.step(*args, **kwargs)
-
-    def zero_grad(self, *args, **kwargs):
-        self.optim.zero_grad(*args, **kwargs)
-
-    def load_state_dict(self, *args, **kwargs):
-        self.optim.load_state_dict(*args, **kwargs)
-
-    def state_dict(self):
-        return self.optim.state_dict()
-
+    # -- the part of the protocol a torch optimizer lacks ----------------------------------------------------------------
     def backward(self, loss, retain_graph: bool = False):
         loss.backward(retain_graph=retain_graph)
 
     def backward_by_grad(self, tensor, grad):
         torch.autograd.backward(tensors=tensor, grad_tensors=grad)
 
-    def clip_grad_norm(self):
-        pass
+    def clip_grad_norm(self, *_, **__):
+        """Clipping belongs to the concrete optimizer (``HybridZeroOptimizer.step``); nothing to do for a plain one."""

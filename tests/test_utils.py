@@ -214,3 +214,34 @@ def test_layernorm_module_cpu_matches_torch():
     assert x.grad is not None and ln.weight.grad is not None and ln.bias.grad is not None
     assert torch.allclose(ln(x), ref(x), atol=1e-5)
     assert set(ln.state_dict()) == {"weight", "bias"}
+
+
+def test_monitor_watchdog_detects_a_stalled_heartbeat_and_periodic_loss_spike(monkeypatch):
+    """The tracker thread's two probes, driven by hand: a heartbeat that does not advance between two checks raises the
+    "stuck" alert, a loss that grows past the limit between two checks raises the spike alert."""
+    from internevo_b200.monitor import monitor as mon
+
+    sent = []
+    monkeypatch.setattr(mon, "send_alert_message", lambda address=None, title=None, message=None: sent.append(message))
+    monkeypatch.setattr(mon.MonitorTracker, "start", lambda self: None)   # no thread: call the probes directly
+    t = mon.MonitorTracker(alert_address="x", check_interval=5, loss_spike_limit=1.5)
+    monkeypatch.delenv("LAST_ACTIVE_TIMESTAMP", raising=False)
+    t._check_stuck()
+    assert not sent                      # no heartbeat published yet: nothing to compare
+    monkeypatch.setenv("LAST_ACTIVE_TIMESTAMP", "100")
+    t._check_stuck()
+    monkeypatch.setenv("LAST_ACTIVE_TIMESTAMP", "130")
+    t._check_stuck()
+    assert not sent                      # heartbeat advanced
+    t._check_stuck()
+    assert len(sent) == 1 and "stuck" in sent[0]
+    monkeypatch.setenv("LOSS", "2.0")
+    monkeypatch.setenv("STEP_ID", "7")
+    t._check_loss_spike()
+    monkeypatch.setenv("LOSS", "2.5")
+    t._check_loss_spike()
+    assert len(sent) == 1
+    monkeypatch.setenv("LOSS", "5.0")
+    monkeypatch.setenv("STEP_ID", "9")
+    t._check_loss_spike()
+    assert len(sent) == 2 and "step 9" in sent[1]
