@@ -148,7 +148,16 @@ def enable_tp(group: Optional[dist.ProcessGroup]) -> Optional[TPFusedBackend]:
 
 
 class ZeroFusedBackend:
-    """Fused reduce-scatter + AdamW + all-gather for ``HybridZeroOptimizer`` groups whose ZeRO group is the DP group."""
+    """Peer-memory primitives of ``HybridZeroOptimizer`` for groups whose ZeRO group is the DP group: the optimizer decides
+    WHEN a range is reduced / updated (during backward / ahead of the next forward), this class does it over NVLink.
+
+    ``reduce_range``  side stream: device barrier (every rank's backward has written the range), then ``rs_reduce``: this rank's
+                      sub-slice = mean over the peers' arenas (P2P loads), cast to bf16 in place, Σ g² accumulated on the way.
+    ``update_range``  unscale + clip + AdamW on the fp32 master sub-slice; the bf16 result is stored straight into EVERY
+                      peer's parameter arena (the all-gather is the store), then a device barrier so that the event the next
+                      forward waits on covers all peers' stores.
+    The flag words and the epoch counter are private to this backend: its barriers run on the optimizer's side stream and
+    must never share a counter with the main-stream barriers of the TP / MoE back-ends."""
 
     def __init__(self, opt):
         from internevo_b200.core.context import global_context as gpc
@@ -171,7 +180,7 @@ class ZeroFusedBackend:
                 o = g.offsets[id(p)]
                 p.data = g.param_arena[o: o + p.numel()].view(p.shape)
                 p.grad_buf = g.grad_arena[o: o + p.numel()].view(p.shape)
-            self.groups[g.gid] = (pbuf, gbuf, symm.flags_for(group))
+            self.groups[g.gid] = (pbuf, gbuf, symm.SymmFlags(group, words=1024))
         # NVLS variant: reduce in the switch (multimem.ld_reduce) and broadcast by one multicast store (multimem.st).  Opt-in:
         # a reduce-SCATTER / all-GATHER moves (W-1)/W of the arena over every GPU's links either way (only an all-reduce
         # halves its traffic in the switch), and measured at 2 GPUs it is slower than the unicast kernels (0.212 vs 0.114 ms
@@ -193,97 +202,58 @@ class ZeroFusedBackend:
             return None
         return be if be.groups else None
 
-    def step(self, opt):
-        with nvtx_range("zero.fused_step(rs+adamw+ag)"):
-            return self._step(opt)
+    # ---- phase 0 -------------------------------------------------------------------------------------------------------
+    def _launch(self, g, i, hyper, phase):
+        pbuf, gbuf, flags = self.groups[g.gid]
+        a, m, n = g.sub(i)
+        if n == 0:
+            return
+        mst, ea, es = g.master[m: m + n], g.exp_avg[m: m + n], g.exp_avg_sq[m: m + n]
+        if self.use_mc:
+            torch.ops.b200.reduce_scatter_adam_mc(gbuf.mc_ptr, pbuf.mc_ptr, gbuf.tensor.data_ptr(), g.zero_size, a, n, mst, ea,
+                                                  es, g.scalars, *hyper, phase)
+        else:
+            torch.ops.b200.reduce_scatter_adam(gbuf.table_ptr(0), pbuf.table_ptr(0), flags.table_ptr(0), g.zero_rank,
+                                               g.zero_size, 0, a, n, mst, ea, es, g.scalars, *hyper, phase)
+        _bump()
 
-    def _step(self, opt):
-        from internevo_b200 import ops
-
-        scale = opt.grad_scaler.scale
-        active = [g for g in opt.groups if g.params]
-        for g in active:
-            opt._collect_grads(g)
-            opt._reduce_replica_grads(g)
-        for g in active:
-            if g.gid in self.groups:
-                pbuf, gbuf, flags = self.groups[g.gid]
-                flags.barrier()  # every rank's backward has written its gradient arena
+    def reduce_range(self, opt, g, i):
+        _, _, flags = self.groups[g.gid]
+        side, main = opt._side(), torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)                      # the kernels that wrote this range's gradients are ahead of this point
+        side.wait_event(ev)
+        with torch.cuda.stream(side), nvtx_range("zero.rs_reduce"):
+            if not g.scalars_fresh:
                 g.scalars.zero_()
-                if self.use_mc:
-                    torch.ops.b200.reduce_scatter_adam_mc(gbuf.mc_ptr, pbuf.mc_ptr, gbuf.tensor.data_ptr(), g.zero_size,
-                                                          g.lo, g.shard, g.master, g.exp_avg, g.exp_avg_sq, g.scalars,
-                                                          0.0, 0.9, 0.95, 1e-8, 0.0, 1.0, 1.0, float(g.zero_size), 0)
-                else:
-                    torch.ops.b200.reduce_scatter_adam(gbuf.table_ptr(0), pbuf.table_ptr(0), flags.table_ptr(0),
-                                                       g.zero_rank, g.zero_size, 0, g.lo, g.shard, g.master, g.exp_avg,
-                                                       g.exp_avg_sq, g.scalars, 0.0, 0.9, 0.95, 1e-8, 0.0, 1.0, 1.0,
-                                                       float(g.zero_size), 0)
-                _bump()
-            else:
-                opt._sync_grads(g)
-        for g in active:
-            self._sumsq(opt, g)
-        opt._reduce_sumsq_over_pipeline(active)   # one vector all-reduce over the union of group names (no-op without PP)
-        for g in active:
-            ops.clip_scalars_(g.sumsq, g.scalars, scale, opt._clip_grad_norm)
-        if len(active) > 1:
-            flag = torch.stack([g.scalars[1] for g in active]).max()
-            for g in active:
-                g.scalars[1] = flag
-        for g in active:
-            cfg = g.cfg
-            if g.gid in self.groups:
-                pbuf, gbuf, flags = self.groups[g.gid]
-                beta1, beta2 = cfg.get("betas", (0.9, 0.95))
-                g.step += 1
-                hyper = (cfg["lr"], beta1, beta2, cfg.get("eps", 1e-8), cfg.get("weight_decay", 0.0),
-                         1.0 - beta1 ** g.step, 1.0 - beta2 ** g.step, 1.0, 1)
-                if self.use_mc:
-                    torch.ops.b200.reduce_scatter_adam_mc(gbuf.mc_ptr, pbuf.mc_ptr, gbuf.tensor.data_ptr(), g.zero_size,
-                                                          g.lo, g.shard, g.master, g.exp_avg, g.exp_avg_sq, g.scalars,
-                                                          *hyper)
-                else:
-                    torch.ops.b200.reduce_scatter_adam(gbuf.table_ptr(0), pbuf.table_ptr(0), flags.table_ptr(0),
-                                                       g.zero_rank, g.zero_size, 0, g.lo, g.shard, g.master, g.exp_avg,
-                                                       g.exp_avg_sq, g.scalars, *hyper)
-                _bump()
-                flags.barrier()  # all parameter pushes have landed before anyone starts the next forward
-            else:
-                opt._update(g)
-                opt._sync_params(g)
-        host = torch.stack([g.scalars for g in active]).cpu()
-        found_inf = bool((host[:, 1] != 0).any())
-        norms = {g.name: float(host[i, 2]) for i, g in enumerate(active)}
-        opt.grad_scaler.update(found_inf)
-        opt.zero_grad()
-        if found_inf:
-            for g in active:
-                g.step -= 1
-            return False, {k: -1.0 for k in norms}
-        return True, norms
+                g.scalars_fresh = True
+            flags.barrier()                  # ... on every rank
+            self._launch(g, i, (0.0, 0.9, 0.95, 1e-8, 0.0, 1.0, 1.0, float(g.zero_size)), 0)
 
-    def _sumsq(self, opt, g):
-        """Σ grad² for the clip: the fused reduce already left this rank's partial in ``scalars[3]``."""
-        if g.gid not in self.groups:
-            return opt._group_sumsq(g)
-        from internevo_b200.core.context import ParallelMode
+    def join(self, opt):
+        torch.cuda.current_stream().wait_stream(opt._side())
 
-        gpc = self.gpc
+    def local_sumsq(self, opt, g, count_replica: bool):
+        """Σ grad² of the owned sub-slices: the reduce kernels left it in ``scalars[3]``; replica parameters are counted on one
+        tensor rank only, so the others subtract their (tiny) replica sub-slices again."""
         g.sumsq.copy_(g.scalars[3:4])
-        # replica parameters are counted once per tensor-parallel group: subtract them on tp_rank != 0
-        model_mode = ParallelMode.WEIGHT if opt.use_isp else ParallelMode.TENSOR
-        rep_lo = max(g.replica_start, g.lo) - g.lo
-        if gpc.get_local_rank(model_mode) != 0 and rep_lo < g.shard:
+        if not count_replica:
             from internevo_b200 import ops
 
             rep = torch.zeros(1, device=g.sumsq.device)
-            ops.sumsq_(g.owned_grad()[rep_lo:], rep)
+            for i in range(g.n_sharded_ranges, len(g.ranges)):
+                a, m, n = g.sub(i)
+                if n:
+                    ops.sumsq_(g.grad_arena[a: a + n], rep)
             g.sumsq -= rep
-        dist.all_reduce(g.sumsq, group=gpc.get_group(g.zero_mode))
-        # tensor- / weight-SHARDED parameters: add the other shards' squares; replicated MoE experts (and, under isp, the
-        # embedding group that reduces over DATA) hold the same gradient on every model-parallel rank: nothing to add
-        replicated = g.dp_mode is ParallelMode.EXPERT_DATA or (opt.use_isp and g.dp_mode is ParallelMode.DATA)
-        if gpc.get_world_size(model_mode) > 1 and not replicated:
-            dist.all_reduce(g.sumsq, group=gpc.get_group(model_mode))
-        return g.sumsq
+
+    # ---- phase 1 -------------------------------------------------------------------------------------------------------
+    def update_range(self, opt, g, i, hyper):
+        lr, beta1, beta2, eps, wd = hyper
+        _, _, flags = self.groups[g.gid]
+        with nvtx_range("zero.adamw_bcast"):
+            self._launch(g, i, (lr, beta1, beta2, eps, wd, 1.0 - beta1 ** g.step, 1.0 - beta2 ** g.step, 1.0), 1)
+            flags.barrier()   # every peer's stores of this range have landed before anyone's forward reads it
+
+    def after_update(self, opt, g):
+        """Serial path: nothing left to do (every range ended with its own barrier)."""

@@ -1,10 +1,12 @@
-"""Hybrid-ZeRO (ZeRO-1.5) optimizer on persistent arenas.
+"""Hybrid-ZeRO (ZeRO-1.5) optimizer on persistent arenas, overlapped with backward and with the next forward.
 
 Semantics preserved from the reference (``internlm/solver/optimizer/hybrid_zero_optim.py:55-950``): parameter groups with
 their own reduction group (DATA / WEIGHT_DATA / EXPERT_DATA), optimizer state + fp32 master sharded over the ZeRO
 sub-group while gradients are averaged over the whole data-parallel group, dynamic loss scale with skip-on-overflow,
 per-group grad-norm + clipping with replica parameters counted once, updated parameters redistributed inside the ZeRO
-group, resumable ``state_dict``.
+group, gradient reduction overlapped with backward (``overlap_sync_grad``, reference ``:290-365,427-523``), parameter
+redistribution overlapped with the next forward (``overlap_sync_param``, reference ``core/communication/utils.py:134-235``),
+resumable ``state_dict``.
 
 Redesign (what changes on a B200 node):
 
@@ -12,18 +14,28 @@ Redesign (what changes on a B200 node):
   parameters are views into the first and the wgrad GEMM epilogues / norm-backward kernels accumulate straight into
   the second (``param.grad_buf``).  The reference's per-step flatten → all-reduce → unflatten → copy chain
   (``store.py:315-322``, ``hybrid_zero_optim.py:455-523,740-797``) disappears;
-* the arena is sharded by *element* (not by whole parameter), so gradient sync is a reduce-scatter and parameter sync an
-  all-gather when the ZeRO group is the DP group; with a smaller ZeRO group the gradient is all-reduced over DP (as the
-  reference does) and only the owned slice is consumed;
-* unscale + clip + AdamW + bf16 cast-back are ONE kernel over the owned shard whose multiplier / skip flag live on the
-  device, so the step issues no host sync until the norm is read back for logging;
-* with a peer-memory heap (``parallel/symm.py``) the reduce-scatter, the update and the parameter all-gather are fused in
-  one NVLink kernel (``reduce_scatter_adam``) — NCCL is the fallback and the oracle.
+* the arena is cut into RANGES (whole parameters, about one transformer block each, ``reduce_bucket_size`` caps them) and
+  every range is sharded by element over the ZeRO group: rank ``r`` owns sub-slice ``r`` of EVERY range
+  (range-interleaved ownership).  The fp32 master and the moments are the concatenation of the owned sub-slices.  Every
+  rank therefore has work as soon as ANY range has its final gradient, which is what makes the overlap below possible;
+* gradient sync: the kernels that write a parameter's final gradient of the step (last micro-batch) call
+  ``param.grad_hook``; when all parameters of the next range in the fixed launch order (arena order reversed = backward
+  order) have reported, its reduce-scatter is issued on a side stream while the backward of the earlier blocks continues.
+  The order is the same on every rank whatever the timing, so the collectives / device barriers always match up;
+  ranges whose hooks never fire are launched from ``step``;
+* unscale + clip + AdamW + bf16 cast-back are ONE kernel per range whose multiplier / skip flag live on the device; the
+  update and the parameter all-gather of range ``c`` run on the side stream and the forward of the NEXT step waits, block
+  by block, only for the ranges that hold that block's parameters;
+* with a peer-memory heap (``parallel/symm.py``) the reduce-scatter is a peer-load kernel fused with mean + cast +
+  grad-norm partials and the all-gather is the store of the AdamW kernel into every peer's arena
+  (``parallel/fused.py::ZeroFusedBackend``) — NCCL is the fallback and the oracle.
 """
 from __future__ import annotations
 
+import bisect
+import math
 import os
-from typing import Dict, List, Optional
+from typing import Dict, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -63,10 +75,10 @@ def _all_reduce_avg(t: torch.Tensor, mode: ParallelMode):
 
 
 class _GroupState:
-    """Arena bookkeeping of one parameter group."""
+    """Arena bookkeeping of one parameter group (see the module docstring for the range-interleaved layout)."""
 
     def __init__(self, gid: int, cfg: dict, params: List[torch.nn.Parameter], dp_mode: ParallelMode,
-                 zero_mode: ParallelMode, device):
+                 zero_mode: ParallelMode, device, bucket_elems: int):
         self.gid, self.cfg, self.params = gid, cfg, params
         self.name = cfg.get("name", f"group{gid}")
         self.dp_mode, self.zero_mode = dp_mode, zero_mode
@@ -74,6 +86,8 @@ class _GroupState:
         self.zero_rank = gpc.get_local_rank(zero_mode) if gpc.is_initialized(zero_mode) else 0
         self.dp_size = _group_size(dp_mode)
         self.dtype = params[0].dtype if params else torch.float32
+        W = self.zero_size
+        align = math.lcm(_ALIGN, 8 * W)   # every range (whole parameters) splits into W sub-slices of a multiple of 8 elements
         # sharded params first, replica params (norm weights / gates: identical on every TP rank) last
         rep = [p for p in params if getattr(p, IS_REPLICA_ZERO_PARALLEL, False)]
         shd = [p for p in params if not getattr(p, IS_REPLICA_ZERO_PARALLEL, False)]
@@ -82,16 +96,46 @@ class _GroupState:
         self.offsets: Dict[int, int] = {}
         for p in shd:
             self.offsets[id(p)] = off
-            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+            off += (p.numel() + align - 1) // align * align
         self.replica_start = off
         for p in rep:
             self.offsets[id(p)] = off
-            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+            off += (p.numel() + align - 1) // align * align
         self.replica_end = off     # [replica_start, replica_end): same SIZE on every tensor rank (offsets may differ)
-        quantum = self.zero_size * 1024
+        quantum = math.lcm(W * 1024, align)
         self.total = max(quantum, (off + quantum - 1) // quantum * quantum)
-        self.shard = self.total // self.zero_size
-        self.lo, self.hi = self.zero_rank * self.shard, (self.zero_rank + 1) * self.shard
+        self.shard = self.total // W                      # elements of master / moments on this rank
+        # ---- ranges: cut at parameter starts once `target` elements have accumulated; never across replica_start
+        target = max(align, min(int(bucket_elems), max(1 << 22, self.replica_start // 48)))
+        cuts = [0]
+        for p in shd[1:]:
+            s = self.offsets[id(p)]
+            if s - cuts[-1] >= target:
+                cuts.append(s)
+        if self.replica_start > cuts[-1] and self.replica_start < self.total:
+            cuts.append(self.replica_start)
+        cuts.append(self.total)
+        self.ranges: List[Tuple[int, int]] = [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+        self.n_sharded_ranges = sum(1 for lo, _ in self.ranges if lo < self.replica_start)
+        self.replica_moff = self.replica_start // W if self.replica_start < self.total else self.shard
+        # launch order of the gradient reduction = expected completion order of the backward: sharded ranges from the end
+        # of the arena (head, last block) to its start (first block, embedding), the replica tail (norm weights of ALL blocks)
+        # last
+        self.order = list(range(self.n_sharded_ranges - 1, -1, -1)) + list(range(self.n_sharded_ranges, len(self.ranges)))
+        self.range_of: Dict[int, int] = {}
+        counts = [0] * len(self.ranges)
+        starts = [lo for lo, _ in self.ranges]
+        for p in self.ordered:
+            i = bisect.bisect_right(starts, self.offsets[id(p)]) - 1
+            self.range_of[id(p)] = i
+            counts[i] += 1
+        self.range_params = counts
+        self.pending = list(counts)      # parameters of each range still waiting for their final gradient this step
+        self.next = 0                    # position in `order` of the next range to launch
+        self.launched = [False] * len(self.ranges)
+        self.handles: list = []          # in-flight NCCL work of this step's gradient reduction
+        self.copy_back: List[int] = []   # ranges reduced by all-reduce whose owned sub-slice still goes to `gshard`
+        self.scalars_fresh = False       # fused path: scalars zeroed on the side stream for this step
         self.param_arena = torch.zeros(self.total, dtype=self.dtype, device=device)
         self.grad_arena = torch.zeros(self.total, dtype=self.dtype, device=device)
         for p in self.ordered:
@@ -101,18 +145,56 @@ class _GroupState:
             p.data = view
             p.grad_buf = self.grad_arena[o: o + p.numel()].view(p.shape)
             p.grad_ready = False
-        # fp32 master + moments of the owned slice
-        self.master = self.param_arena[self.lo: self.hi].float()
+        # fp32 master + moments of the owned sub-slices (compact: range i lives at [lo_i / W, hi_i / W))
+        self.master = torch.empty(self.shard, dtype=torch.float32, device=device)
+        self.pull_master()
         self.exp_avg = torch.zeros_like(self.master)
         self.exp_avg_sq = torch.zeros_like(self.master)
+        self.gshard: Optional[torch.Tensor] = None   # compact reduced gradient of the owned sub-slices (NCCL / gloo path)
         self.step = 0
         self.scalars = torch.zeros(4, dtype=torch.float32, device=device)
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=device)
-        self.param_sync_handle = None
-        self.plan = None      # chunk plan of the overlapped update (HybridZeroOptimizer._chunk_plan)
+        self.events = None      # per-range CUDA events of the overlapped update (HybridZeroOptimizer._ensure_events)
+        self.ready_ev = None
 
-    def owned_grad(self) -> torch.Tensor:
-        return self.grad_arena[self.lo: self.hi]
+    # -- geometry ---------------------------------------------------------------------------------------------------
+    def sub(self, i: int) -> Tuple[int, int, int]:
+        """``(arena offset, compact offset, length)`` of this rank's sub-slice of range ``i``."""
+        lo, hi = self.ranges[i]
+        n = (hi - lo) // self.zero_size
+        return lo + self.zero_rank * n, lo // self.zero_size, n
+
+    def is_replica_range(self, i: int) -> bool:
+        return i >= self.n_sharded_ranges
+
+    def owned_views(self, arena: torch.Tensor):
+        for i in range(len(self.ranges)):
+            a, m, n = self.sub(i)
+            yield arena[a: a + n], m, n
+
+    def pull_master(self):
+        """fp32 master ← the owned sub-slices of the low-precision arena."""
+        for v, m, n in self.owned_views(self.param_arena):
+            self.master[m: m + n].copy_(v)
+
+    def push_master(self):
+        """Owned sub-slices of the low-precision arena ← fp32 master."""
+        for v, m, n in self.owned_views(self.param_arena):
+            v.copy_(self.master[m: m + n])
+
+    def grad_shard(self) -> torch.Tensor:
+        """Compact reduced gradient of the owned sub-slices; with a ZeRO group of one the arena itself (same offsets)."""
+        if self.zero_size == 1:
+            return self.grad_arena
+        if self.gshard is None:
+            self.gshard = torch.zeros(self.shard, dtype=self.dtype, device=self.grad_arena.device)
+        return self.gshard
+
+    def reset_step_state(self):
+        self.pending = list(self.range_params)
+        self.next = 0
+        self.launched = [False] * len(self.ranges)
+        self.scalars_fresh = False
 
 
 class HybridZeroOptimizer:
@@ -131,9 +213,13 @@ class HybridZeroOptimizer:
         self.use_isp = is_using_isp()
         self._isp_communicator = isp_communicator
         self._clip_grad_norm = zero_cfg.get("clip_grad_norm", 0.0)
-        self._overlap_sync_grad = zero_cfg.get("overlap_sync_grad", False)
-        self._overlap_sync_param = zero_cfg.get("overlap_sync_param", False)
-        self._reduce_bucket_size = zero_cfg.get("reduce_bucket_size", 512 * 1024 * 1024)
+        # overlap_sync_grad: reduce a range as soon as its gradients are final (during backward) instead of inside step();
+        # overlap_sync_param: keep the parameter all-gather of the NCCL path asynchronous until the owning block runs;
+        # reduce_bucket_size: upper bound (elements) of one range.  B200_ZERO_OVERLAP=0 forces the serial path.
+        self._overlap_sync_grad = bool(zero_cfg.get("overlap_sync_grad", False)) and \
+            os.environ.get("B200_ZERO_OVERLAP", "1") != "0"
+        self._overlap_sync_param = bool(zero_cfg.get("overlap_sync_param", False))
+        self._reduce_bucket_size = int(zero_cfg.get("reduce_bucket_size", 512 * 1024 * 1024))
         self.skip_grad_reduce = False
         self.device = get_current_device()
         if self._dtype is torch.float32:
@@ -149,7 +235,7 @@ class HybridZeroOptimizer:
         for gid, pg in enumerate(self.param_groups):
             params = [p for p in pg["params"] if p.requires_grad]
             dp_mode, zero_mode = self._modes_for_group(pg, params)
-            self.groups.append(_GroupState(gid, pg, params, dp_mode, zero_mode, self.device))
+            self.groups.append(_GroupState(gid, pg, params, dp_mode, zero_mode, self.device, self._reduce_bucket_size))
         self.rank_unique_id = (
             f"gpus-{gpc.get_world_size(ParallelMode.GLOBAL)}_wp-{gpc.get_local_rank(ParallelMode.WEIGHT)}_"
             f"tp-{gpc.get_local_rank(ParallelMode.TENSOR)}_dp-{gpc.get_local_rank(ParallelMode.DATA)}_"
@@ -163,15 +249,18 @@ class HybridZeroOptimizer:
 
             self._fused = fused.ZeroFusedBackend.try_create(self)
         self.has_params = sum(len(g.params) for g in self.groups) > 0
-        # AdamW of step s overlapped with the forward of step s + 1 (unsharded groups, see _update_overlapped)
+        # parameter update of step s overlapped with the forward of step s + 1 (CUDA; see _update_overlapped)
         self._adam_overlap = os.environ.get("B200_ADAM_OVERLAP", "1") != "0" and torch.cuda.is_available() \
             and not self.use_isp
-        self._opt_stream = None
-        self._owner_events: Dict[int, list] = {}     # id(module) -> events of the chunks holding its parameters
+        self._side_stream = None
+        self._owner_events: Dict[int, list] = {}     # id(module) -> events of the ranges holding its parameters
         self._owner_seen: Dict[int, int] = {}        # id(module) -> update generation it has already waited for
         self._update_gen = 0
         self._model_attached = False
         self._pp_group_names = None   # union of parameter-group names over the pipeline group (agreed at the first step)
+        self._group_of: Dict[int, _GroupState] = {}
+        self.overlap_stats = {"hook_launches": 0, "step_launches": 0}   # ranges reduced during backward / inside step()
+        self._install_grad_hooks()
 
     # ------------------------------------------------------------------------------------------------------------
     def _modes_for_group(self, pg, params):
@@ -206,6 +295,7 @@ class HybridZeroOptimizer:
             for p in g.params:
                 p.grad = None
                 p.grad_ready = False
+            g.reset_step_state()
 
     def backward(self, loss, retain_graph=False):
         (loss * self.grad_scaler.scale).backward(retain_graph=retain_graph)
@@ -214,22 +304,127 @@ class HybridZeroOptimizer:
         torch.autograd.backward(tensors=tensor, grad_tensors=grad)
 
     def wait_param_sync(self):
+        """Kept for the scheduler protocol: parameter redistribution is tracked per range by CUDA events consumed in the
+        blocks' pre-forward hooks (or completed inside ``step`` when the overlap is off), so there is nothing to wait for."""
+
+    # ---- gradient readiness ------------------------------------------------------------------------------------------------
+    def _install_grad_hooks(self):
+        """``param.grad_hook(param)`` is called by the kernels that accumulate straight into ``grad_buf`` (wgrad GEMM
+        epilogue, norm backward); parameters whose gradient arrives through autograd (``.grad``: embedding, biases, MoE gates)
+        get a post-accumulate hook that folds it into the arena right away and then reports the same way."""
         for g in self.groups:
-            if g.param_sync_handle is not None:
-                g.param_sync_handle.wait()
-                g.param_sync_handle = None
+            for p in g.params:
+                self._group_of[id(p)] = g
+                p.grad_hook = self._on_grad_ready
+                if hasattr(p, "register_post_accumulate_grad_hook"):
+                    p.register_post_accumulate_grad_hook(self._on_autograd_grad)
+
+    @staticmethod
+    def _fold_autograd_grad(p):
+        if p.grad is None:
+            return
+        if p.grad_ready:
+            p.grad_buf.add_(p.grad)
+        else:
+            p.grad_buf.copy_(p.grad)
+        p.grad = None
+        p.grad_ready = True
+
+    def _on_autograd_grad(self, p):
+        if p.grad is None:
+            return
+        self._fold_autograd_grad(p)
+        self._on_grad_ready(p)
+
+    def _on_grad_ready(self, p):
+        """A parameter's gradient of the current micro-batch is in the arena.  On the LAST micro-batch of the step (the
+        schedulers clear ``skip_grad_reduce`` for it, as in the reference) this is the final value: count it and launch every
+        range of the fixed order that is now complete."""
+        if self.skip_grad_reduce or not self._overlap_sync_grad:
+            return
+        g = self._group_of.get(id(p))
+        if g is None or not self._can_overlap_reduce(g):
+            return
+        g.pending[g.range_of[id(p)]] -= 1
+        self._advance(g, final=False)
+
+    def _can_overlap_reduce(self, g: _GroupState) -> bool:
+        # expert gradients are pre-reduced over the tensor group inside step(); a group without data parallelism has
+        # nothing to reduce
+        return g.dp_size > 1 and g.dp_mode is not ParallelMode.EXPERT_DATA and not self.use_isp
+
+    def _range_is_late(self, g: _GroupState, i: int) -> bool:
+        """Replica ranges under sequence parallelism need their tensor-group reduction first (done in step())."""
+        return g.is_replica_range(i) and (is_using_sequence_parallel() or self.use_isp) and \
+            _group_size(ParallelMode.WEIGHT if self.use_isp else ParallelMode.TENSOR) > 1
+
+    def _advance(self, g: _GroupState, final: bool):
+        while g.next < len(g.order):
+            i = g.order[g.next]
+            if not final and (g.pending[i] > 0 or self._range_is_late(g, i)):
+                return
+            self._launch_reduce(g, i)
+            self.overlap_stats["step_launches" if final else "hook_launches"] += 1
+            g.next += 1
+
+    # ---- gradient reduction of one range -----------------------------------------------------------------------------------
+    def _side(self):
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self.device)
+        return self._side_stream
+
+    def _launch_reduce(self, g: _GroupState, i: int):
+        """Average range ``i`` over the data-parallel group; afterwards this rank's sub-slice holds the reduced values (in the
+        arena for the peer-memory path, in ``g.gshard`` otherwise)."""
+        g.launched[i] = True
+        if g.dp_size <= 1:
+            return
+        lo, hi = g.ranges[i]
+        a, m, n = g.sub(i)
+        dp_group = gpc.get_group(g.dp_mode)
+        if self._fused is not None and g.gid in self._fused.groups:
+            self._fused.reduce_range(self, g, i)
+            return
+        same = g.zero_size == g.dp_size and gpc.get_ranks_in_group(g.dp_mode) == gpc.get_ranks_in_group(g.zero_mode)
+        seg = g.grad_arena[lo:hi]
+        if seg.is_cuda and same:
+            h = dist.reduce_scatter_tensor(g.grad_shard()[m: m + n], seg, op=dist.ReduceOp.AVG, group=dp_group,
+                                           async_op=True)
+            g.handles.append(h)
+        elif seg.is_cuda:
+            g.handles.append(dist.all_reduce(seg, op=dist.ReduceOp.AVG, group=dp_group, async_op=True))
+            g.copy_back.append(i)
+        else:  # gloo: no AVG, no reduce_scatter_tensor
+            dist.all_reduce(seg, group=dp_group)
+            seg.div_(g.dp_size)
+            g.copy_back.append(i)
+
+    def _finish_reduce(self, g: _GroupState):
+        """Join the reductions of this step into the compute stream; ``g.gshard`` (or the arena sub-slices on the
+        peer-memory path) is final afterwards."""
+        for h in g.handles:
+            h.wait()
+        g.handles = []
+        if self._fused is not None and g.gid in self._fused.groups:
+            self._fused.join(self)
+            return
+        if g.zero_size == 1:
+            g.copy_back = []        # grad_shard() IS the arena
+        elif g.dp_size <= 1:        # pragma: no cover - zero_size > 1 implies data parallelism
+            g.copy_back = list(range(len(g.ranges)))
+        if g.copy_back:
+            gs = g.grad_shard()
+            for i in g.copy_back:
+                a, m, n = g.sub(i)
+                gs[m: m + n].copy_(g.grad_arena[a: a + n])
+            g.copy_back = []
 
     # ------------------------------------------------------------------------------------------------------------
     def _collect_grads(self, g: _GroupState):
         """Fold autograd-produced ``.grad`` tensors into the arena; zero slots of parameters that got no gradient."""
         for p in g.params:
             if p.grad is not None:
-                if p.grad_ready:
-                    p.grad_buf.add_(p.grad)
-                else:
-                    p.grad_buf.copy_(p.grad)
-                p.grad = None
-                p.grad_ready = True
+                self._fold_autograd_grad(p)
             elif not p.grad_ready:
                 p.grad_buf.zero_()
 
@@ -261,34 +456,21 @@ class HybridZeroOptimizer:
         else:
             dist.all_reduce(rep, group=gpc.get_group(mode))
 
-    def _sync_grads(self, g: _GroupState):
-        """Average over the data-parallel group; afterwards ``g.owned_grad()`` holds this rank's reduced slice."""
-        dp_group, zero_group = gpc.get_group(g.dp_mode), gpc.get_group(g.zero_mode)
-        if g.dp_size <= 1 or dp_group is None:
-            return
-        same = g.zero_size == g.dp_size and gpc.get_ranks_in_group(g.dp_mode) == gpc.get_ranks_in_group(g.zero_mode)
-        if same and g.grad_arena.is_cuda:
-            dist.reduce_scatter_tensor(g.owned_grad(), g.grad_arena, op=dist.ReduceOp.AVG, group=dp_group)
-        else:
-            _all_reduce_avg(g.grad_arena, g.dp_mode)
-        del zero_group
-
     def _group_sumsq(self, g: _GroupState) -> torch.Tensor:
-        """Σ grad² of the owned slice with replica parameters counted only on tp/wp rank 0, reduced over the ZeRO and
+        """Σ grad² of the owned sub-slices with replica parameters counted only on tp/wp rank 0, reduced over the ZeRO and
         tensor (weight) groups (reference ``compute_norm``, ``optimizer/utils.py:265-378``).  The sum over pipeline stages
         is done for all groups at once by ``_reduce_sumsq_over_pipeline``."""
-        g.sumsq.zero_()
-        owned = g.owned_grad()
-        rep_lo = max(g.replica_start, g.lo) - g.lo
         model_mode = ParallelMode.WEIGHT if self.use_isp else ParallelMode.TENSOR
         count_replica = gpc.get_local_rank(model_mode) == 0
-        if rep_lo >= g.shard:
-            ops.sumsq_(owned, g.sumsq)
+        if self._fused is not None and g.gid in self._fused.groups:
+            self._fused.local_sumsq(self, g, count_replica)     # the reduce kernels already accumulated the squares
         else:
-            if rep_lo > 0:
-                ops.sumsq_(owned[:rep_lo], g.sumsq)
-            if count_replica:
-                ops.sumsq_(owned[rep_lo:], g.sumsq)
+            g.sumsq.zero_()
+            owned = g.grad_shard()
+            if g.replica_moff > 0:
+                ops.sumsq_(owned[: g.replica_moff], g.sumsq)
+            if count_replica and g.replica_moff < g.shard:
+                ops.sumsq_(owned[g.replica_moff:], g.sumsq)
         if g.zero_size > 1:
             dist.all_reduce(g.sumsq, group=gpc.get_group(g.zero_mode))
         if g.dp_mode is ParallelMode.EXPERT_DATA:
@@ -325,43 +507,67 @@ class HybridZeroOptimizer:
             if n in by_name:
                 by_name[n].sumsq.copy_(vec[i:i + 1])
 
-    def _update(self, g: _GroupState):
+    # ---- parameter update + redistribution, range by range --------------------------------------------------------------
+    def _hyper(self, g: _GroupState):
         cfg = g.cfg
         beta1, beta2 = cfg.get("betas", (0.9, 0.95))
-        g.step += 1
-        lp = g.param_arena[g.lo: g.hi] if g.dtype is not torch.float32 else None
-        ops.adamw_(g.master, g.exp_avg, g.exp_avg_sq, g.owned_grad(), lp, cfg["lr"], beta1, beta2, cfg.get("eps", 1e-8),
-                   cfg.get("weight_decay", 0.0), g.step, g.scalars)
-        if lp is None:
-            g.param_arena[g.lo: g.hi].copy_(g.master)
+        return cfg["lr"], beta1, beta2, cfg.get("eps", 1e-8), cfg.get("weight_decay", 0.0)
 
-    # ---- AdamW overlapped with the next forward ------------------------------------------------------------------------
-    # Without ZeRO sharding (zero group of size 1, e.g. the 1-GPU benchmark) the update is 28 bytes per parameter of pure
-    # HBM streaming (40 ms for 7.7 B parameters) during which the tensor cores idle, and nothing but the NEXT forward
-    # depends on it - layer by layer.  The update therefore runs chunk by chunk (norm weights first, then arena order =
-    # forward order) on a side stream; every module's pre-forward hook makes the compute stream wait for the chunks that
-    # hold that module's parameters only.  The backward of the next step cannot start before its forward, so the
-    # gradients an update chunk reads are never overwritten early.  Same arithmetic, same order of operations per element.
+    def _update_range(self, g: _GroupState, i: int):
+        """AdamW on this rank's sub-slice of range ``i`` and redistribution of the new low-precision values inside the ZeRO
+        group.  Runs on the current stream (the side stream when overlapped)."""
+        lr, beta1, beta2, eps, wd = self._hyper(g)
+        lo, hi = g.ranges[i]
+        a, m, n = g.sub(i)
+        if self._fused is not None and g.gid in self._fused.groups:
+            self._fused.update_range(self, g, i, (lr, beta1, beta2, eps, wd))
+            return
+        lowp = g.dtype is not torch.float32
+        lp = g.param_arena[a: a + n] if lowp else None
+        ops.adamw_(g.master[m: m + n], g.exp_avg[m: m + n], g.exp_avg_sq[m: m + n], g.grad_shard()[m: m + n], lp, lr,
+                   beta1, beta2, eps, wd, g.step, g.scalars)
+        if lp is None:
+            g.param_arena[a: a + n].copy_(g.master[m: m + n])
+        if g.zero_size > 1:
+            group = gpc.get_group(g.zero_mode)
+            seg, mine = g.param_arena[lo:hi], g.param_arena[a: a + n]
+            try:
+                dist.all_gather_into_tensor(seg, mine, group=group)
+            except RuntimeError:  # very old gloo builds
+                parts = list(seg.chunk(g.zero_size))
+                dist.all_gather(parts, mine.clone(), group=group)
+
+    # The update is 28 bytes per parameter of pure HBM streaming during which the tensor cores idle, and nothing but the NEXT
+    # forward depends on it - block by block.  It therefore runs range by range (norm weights first, then arena order =
+    # forward order) on a side stream; the pre-forward hook of every block makes the compute stream wait for the ranges that
+    # hold that block's parameters only.  The backward of the next step cannot start before its forward, so the gradients a
+    # range reads are never overwritten early.  Same arithmetic, same order of operations per element.
     def attach_model(self, model) -> None:
-        """Register the pre-forward hooks (called once by ``initialize_optimizer``)."""
+        """Register the pre-forward hooks (called once by ``initialize_optimizer``).  A transformer block waits as a whole -
+        its forward may read ``self.w13.weight`` or a gate weight without calling the sub-module that owns it - and every
+        parameter outside the blocks (embedding, final norm, head) waits on the module that owns it directly."""
         if not self._adam_overlap or self._model_attached:
             return
-        owner_of = {}
-        modules = model if isinstance(model, (list, torch.nn.ModuleList)) else [model]
+        modules = list(model) if isinstance(model, (list, torch.nn.ModuleList)) else [model]
+        waiters: Dict[int, torch.nn.Module] = {}      # id(param) -> module whose pre-forward hook guards it
         for m in modules:
             for sub in m.modules():
+                if getattr(sub, "is_zero_wait_block", False) or type(sub).__name__ == "DecoderLayer":
+                    for p in sub.parameters():
+                        waiters.setdefault(id(p), sub)
+            for sub in m.modules():
                 for p in sub.parameters(recurse=False):
-                    owner_of.setdefault(id(p), sub)
+                    waiters.setdefault(id(p), sub)
         for g in self.groups:
-            if not g.params or g.zero_size != 1:
+            if not g.params:
                 continue
-            plan = self._chunk_plan(g)
+            self._ensure_events(g)
             for p in g.params:
-                sub = owner_of.get(id(p))
-                if sub is None:      # a parameter no module owns directly: the overlap cannot be made safe
+                sub = waiters.get(id(p))
+                if sub is None:      # a parameter no module owns: the overlap cannot be made safe
                     self._adam_overlap = False
                     return
-                ev = plan["events"][self._chunk_of(plan, g.offsets[id(p)])]
+                ev = g.events[g.range_of[id(p)]]
                 lst = self._owner_events.setdefault(id(sub), [])
                 if ev not in lst:
                     lst.append(ev)
@@ -371,6 +577,11 @@ class HybridZeroOptimizer:
                     sub.register_forward_pre_hook(self._pre_forward_wait)
         self._model_attached = True
 
+    def _ensure_events(self, g: _GroupState):
+        if g.events is None:
+            g.events = [torch.cuda.Event() for _ in g.ranges]
+            g.ready_ev = torch.cuda.Event()
+
     def _pre_forward_wait(self, module, inputs):
         if self._owner_seen.get(id(module), 0) != self._update_gen:
             self._owner_seen[id(module)] = self._update_gen
@@ -378,131 +589,76 @@ class HybridZeroOptimizer:
             for ev in self._owner_events[id(module)]:
                 stream.wait_event(ev)
 
-    def _chunk_plan(self, g: _GroupState):
-        if g.plan is None:
-            ranges = []
-            if g.replica_start < g.total:
-                ranges.append((g.replica_start, g.total))          # norm weights / gates: needed by the very first layer
-            starts = sorted(g.offsets[id(p)] for p in g.ordered if g.offsets[id(p)] < g.replica_start)
-            target = max(1 << 22, g.replica_start // 48)
-            lo = 0
-            for s in starts[1:]:
-                if s - lo >= target:
-                    ranges.append((lo, s))
-                    lo = s
-            if g.replica_start > lo:
-                ranges.append((lo, g.replica_start))
-            g.plan = {"ranges": ranges, "starts": [r[0] for r in ranges],
-                      "events": [torch.cuda.Event() for _ in ranges], "ready": torch.cuda.Event()}
-        return g.plan
+    def _can_overlap_update(self, g: _GroupState) -> bool:
+        return self._adam_overlap and self._model_attached and g.master.is_cuda and g.events is not None
 
-    @staticmethod
-    def _chunk_of(plan, offset: int) -> int:
-        best = 0
-        for i, (lo, hi) in enumerate(plan["ranges"]):
-            if lo <= offset < hi:
-                best = i
-        return best
+    def _update_order(self, g: _GroupState):
+        """Replica tail (norm weights: needed by the very first block) first, then arena order = forward order."""
+        return list(range(g.n_sharded_ranges, len(g.ranges))) + list(range(g.n_sharded_ranges))
 
-    def _can_overlap(self, g: _GroupState) -> bool:
-        return (self._adam_overlap and self._model_attached and g.zero_size == 1 and g.master.is_cuda
-                and g.plan is not None)
-
-    def _update_overlapped(self, g: _GroupState):
-        cfg = g.cfg
-        beta1, beta2 = cfg.get("betas", (0.9, 0.95))
+    def _update_group(self, g: _GroupState) -> bool:
         g.step += 1
-        plan = g.plan
-        if self._opt_stream is None:
-            self._opt_stream = torch.cuda.Stream(device=g.master.device)
-        main = torch.cuda.current_stream()
-        plan["ready"].record(main)                 # gradients, clip multiplier and overflow flag are final
-        self._opt_stream.wait_event(plan["ready"])
-        lowp = g.dtype is not torch.float32
-        with torch.cuda.stream(self._opt_stream):
-            for (lo, hi), ev in zip(plan["ranges"], plan["events"]):
-                lp = g.param_arena[lo:hi] if lowp else None
-                ops.adamw_(g.master[lo:hi], g.exp_avg[lo:hi], g.exp_avg_sq[lo:hi], g.grad_arena[lo:hi], lp, cfg["lr"], beta1,
-                           beta2, cfg.get("eps", 1e-8), cfg.get("weight_decay", 0.0), g.step, g.scalars)
-                if lp is None:
-                    g.param_arena[lo:hi].copy_(g.master[lo:hi])
-                ev.record(self._opt_stream)
+        if not self._can_overlap_update(g):
+            for i in self._update_order(g):
+                self._update_range(g, i)
+            if self._fused is not None and g.gid in self._fused.groups:
+                self._fused.after_update(self, g)
+            return False
+        side, main = self._side(), torch.cuda.current_stream()
+        g.ready_ev.record(main)                 # gradients, clip multiplier and overflow flag are final
+        side.wait_event(g.ready_ev)
+        with torch.cuda.stream(side):
+            for i in self._update_order(g):
+                self._update_range(g, i)
+                g.events[i].record(side)
+        return True
 
     def flush_param_update(self) -> None:
-        """Make the current stream wait for every in-flight update chunk (checkpointing, state loading, end of a timed
+        """Make the current stream wait for every in-flight update range (checkpointing, state loading, end of a timed
         region): after this call parameters and optimizer state can be read or written in stream order as usual."""
-        if self._opt_stream is not None:
-            torch.cuda.current_stream().wait_stream(self._opt_stream)
-
-    def _sync_params(self, g: _GroupState):
-        group = gpc.get_group(g.zero_mode)
-        if g.zero_size <= 1 or group is None:
-            return
-        shard = g.param_arena[g.lo: g.hi]
-        try:
-            h = dist.all_gather_into_tensor(g.param_arena, shard, group=group, async_op=self._overlap_sync_param)
-        except RuntimeError:  # very old gloo builds
-            parts = list(g.param_arena.chunk(g.zero_size))
-            h = dist.all_gather(parts, shard.clone(), group=group, async_op=self._overlap_sync_param)
-        g.param_sync_handle = h if self._overlap_sync_param else None
+        if self._side_stream is not None:
+            torch.cuda.current_stream().wait_stream(self._side_stream)
 
     # ------------------------------------------------------------------------------------------------------------
     def step(self, closure=None):
         """→ ``(success, {group_name: grad_norm})``; a non-finite norm skips the update and backs off the loss scale."""
         assert closure is None
-        self.wait_param_sync()
         timer("sync_grad").start()
-        if self._fused is not None:
-            ok, norms = self._fused.step(self)
-            timer("sync_grad").stop()
-            return ok, norms
-        for g in self.groups:
-            if not g.params:
-                continue
+        active = [g for g in self.groups if g.params]
+        for g in active:
             self._collect_grads(g)
             self._reduce_replica_grads(g)
-            self._sync_grads(g)
+        for g in active:
+            self._advance(g, final=True)       # whatever the hooks did not launch during backward, in the same order
+        for g in active:
+            self._finish_reduce(g)
         timer("sync_grad").stop()
         timer("step").start()
         scale = self.grad_scaler.scale
-        active = [g for g in self.groups if g.params]
         for g in active:
             self._group_sumsq(g)
         self._reduce_sumsq_over_pipeline(active)
         for g in active:
             ops.clip_scalars_(g.sumsq, g.scalars, scale, self._clip_grad_norm)
         # overflow anywhere must skip every group: fold the flags (tiny device op), still no host sync
-        if len(self.groups) > 1:
-            flag = torch.stack([g.scalars[1] for g in self.groups if g.params]).max()
-            for g in self.groups:
-                if g.params:
-                    g.scalars[1] = flag
+        if len(active) > 1:
+            flag = torch.stack([g.scalars[1] for g in active]).max()
+            for g in active:
+                g.scalars[1] = flag
         overlapped = False
-        for g in self.groups:
-            if g.params:
-                if self._can_overlap(g):
-                    self._update_overlapped(g)
-                    overlapped = True
-                else:
-                    self._update(g)
-                self._sync_params(g)
+        for g in active:
+            overlapped |= self._update_group(g)
         if overlapped:
             self._update_gen += 1
         timer("step").stop()
         # single read-back for logging / loss-scale bookkeeping (everything above is already queued)
-        host = torch.stack([g.scalars for g in self.groups if g.params]).cpu() if self.has_params else torch.zeros(1, 4)
+        host = torch.stack([g.scalars for g in active]).cpu() if self.has_params else torch.zeros(1, 4)
         found_inf = bool((host[:, 1] != 0).any())
-        norms = {}
-        i = 0
-        for g in self.groups:
-            if g.params:
-                norms[g.name] = float(host[i, 2])
-                i += 1
+        norms = {g.name: float(host[i, 2]) for i, g in enumerate(active)}
         self.grad_scaler.update(found_inf)
         if found_inf:
-            for g in self.groups:
-                if g.params:
-                    g.step -= 1
+            for g in active:
+                g.step -= 1
             if gpc.is_rank_for_log():
                 logger.warning("Overflow occurs, please check it.")
             self.zero_grad()
@@ -514,18 +670,33 @@ class HybridZeroOptimizer:
     def clip_grad_norm(self, model, max_norm):
         """No-op: clipping happens inside ``step`` (reference ``hybrid_zero_optim.py:855-857``)."""
 
+    def _redistribute_params(self, g: _GroupState):
+        """Full (blocking) parameter all-gather of every range: state loading / master reload."""
+        if g.zero_size <= 1:
+            return
+        group = gpc.get_group(g.zero_mode)
+        for i, (lo, hi) in enumerate(g.ranges):
+            a, m, n = g.sub(i)
+            seg, mine = g.param_arena[lo:hi], g.param_arena[a: a + n]
+            try:
+                dist.all_gather_into_tensor(seg, mine, group=group)
+            except RuntimeError:  # very old gloo builds
+                parts = list(seg.chunk(g.zero_size))
+                dist.all_gather(parts, mine.clone(), group=group)
+
     def state_dict(self):
         self.flush_param_update()
         states = {"grad_scaler": self.grad_scaler.state_dict(), "zero_devide_optim_plan": {}, "groups": []}
         for g in self.groups:
             states["groups"].append({
-                "name": g.name, "step": g.step, "lo": g.lo, "hi": g.hi, "total": g.total,
+                "name": g.name, "step": g.step, "total": g.total, "layout": "range-interleaved",
+                "ranges": [list(r) for r in g.ranges], "zero_rank": g.zero_rank, "zero_size": g.zero_size,
                 "flat_fp32_weights": g.master.detach().cpu(), "exp_avg": g.exp_avg.detach().cpu(),
                 "exp_avg_sq": g.exp_avg_sq.detach().cpu(),
                 "hyper": {k: v for k, v in g.cfg.items() if k != "params"},
             })
             states["zero_devide_optim_plan"][g.name] = {
-                "zero_rank": g.zero_rank, "zero_size": g.zero_size,
+                "zero_rank": g.zero_rank, "zero_size": g.zero_size, "ranges": [list(r) for r in g.ranges],
                 "offsets": [(list(p.shape), g.offsets[id(p)]) for p in g.ordered],
             }
         return states
@@ -535,9 +706,11 @@ class HybridZeroOptimizer:
         self.flush_param_update()
         self.grad_scaler.load_state_dict(states["grad_scaler"])
         for g, st in zip(self.groups, states["groups"]):
-            assert st["total"] == g.total and st["lo"] == g.lo, (
-                f"optimizer checkpoint layout mismatch for group {g.name}: the parallel sizes must match the checkpoint"
-            )
+            same = (st.get("layout") == "range-interleaved" and st["total"] == g.total
+                    and [tuple(r) for r in st["ranges"]] == g.ranges and st["zero_rank"] == g.zero_rank
+                    and st["zero_size"] == g.zero_size)
+            assert same, (f"optimizer checkpoint layout mismatch for group {g.name}: parallel sizes and "
+                          f"reduce_bucket_size must match the checkpoint")
             g.step = st["step"]
             g.master.copy_(st["flat_fp32_weights"])
             g.exp_avg.copy_(st["exp_avg"])
@@ -545,15 +718,14 @@ class HybridZeroOptimizer:
             for k in ("lr", "betas", "eps", "weight_decay"):
                 if k in st.get("hyper", {}):
                     g.cfg[k] = st["hyper"][k]
-            g.param_arena[g.lo: g.hi].copy_(g.master)
-            self._sync_params(g)
-        self.wait_param_sync()
+            g.push_master()
+            self._redistribute_params(g)
 
     def reload_zero_fp32_buff(self):
         """After a model-only load: refresh the fp32 master from the (new) low-precision parameters."""
         self.flush_param_update()
         for g in self.groups:
-            g.master.copy_(g.param_arena[g.lo: g.hi])
+            g.pull_master()
 
 
 def reload_zero_fp32_buff(optimizer):

@@ -40,7 +40,17 @@ def _worker(rank, world, port, fn, args, ret):
 
 
 def run_distributed(fn, world, *args, timeout=300):
-    """Run ``fn(rank, world, *args)`` in ``world`` processes; returns the list of results, raises on any failure."""
+    """Run ``fn(rank, world, *args)`` in ``world`` processes; returns the list of results, raises on any failure.  A
+    rendezvous port that another process grabbed between ``find_free_port`` and the bind is retried on a fresh port."""
+    for attempt in range(3):
+        try:
+            return _run_distributed_once(fn, world, *args, timeout=timeout)
+        except AssertionError as e:
+            if "EADDRINUSE" not in str(e) or attempt == 2:
+                raise
+
+
+def _run_distributed_once(fn, world, *args, timeout=300):
     ctx = mp.get_context("spawn")
     mgr = ctx.Manager()
     ret = mgr.dict()

@@ -57,7 +57,11 @@ def _load_golden(model, opt, cfg):
 def _train(rank, world, kw):
     from internevo_b200.core.context import ParallelMode, global_context as gpc
 
+    kw = dict(kw)
+    overlap = kw.pop("overlap", None)
     cfg = tiny_config(**kw)
+    if overlap is not None:   # gradient reduction launched range by range from the backward hooks
+        cfg["hybrid_zero_optimizer"].update(overlap_sync_grad=True, reduce_bucket_size=int(overlap))
     trainer, opt, model, _ = build_trainer(cfg)
     _load_golden(model, opt, cfg)
     dp, dpr = gpc.get_world_size(ParallelMode.DATA), gpc.get_local_rank(ParallelMode.DATA)
@@ -85,6 +89,11 @@ def _train(rank, world, kw):
             losses.append(float(loss))
         else:
             losses.append(None)
+    if overlap is not None:
+        g = max(opt.groups, key=lambda g: g.total)
+        assert len(g.ranges) >= 4, g.ranges
+        if gpc.get_world_size(ParallelMode.PIPELINE) == 1:   # every sharded range goes out while the backward is running
+            assert opt.overlap_stats["hook_launches"] >= STEPS * g.n_sharded_ranges, (opt.overlap_stats, g.ranges)
     return losses, norms
 
 
@@ -126,6 +135,21 @@ def test_pp2_1f1b(baseline):
 
 def test_pp2_interleaved(baseline):
     _check(run_distributed(_train, 2, dict(pp=2, micro_num=MICRO_TOTAL, num_chunks=2)), baseline)
+
+
+@pytest.mark.parametrize("zero1", [-1, 1])
+def test_dp2_zero_overlapped_with_backward(baseline, zero1):
+    """``overlap_sync_grad``: ranges of 8 Ki elements reduced from the grad hooks while the backward is still running must
+    give the serial trajectory (range-interleaved ownership, fixed launch order)."""
+    _check(run_distributed(_train, 2, dict(micro_num=MICRO_TOTAL // 2, zero1=zero1, overlap=8192)), baseline)
+
+
+def test_tp2_dp2_zero2_overlapped(baseline):
+    _check(run_distributed(_train, 4, dict(tp=2, mode="msp", micro_num=MICRO_TOTAL // 2, zero1=2, overlap=4096)), baseline)
+
+
+def test_pp2_dp2_overlapped(baseline):
+    _check(run_distributed(_train, 4, dict(pp=2, micro_num=MICRO_TOTAL // 2, overlap=4096)), baseline)
 
 
 def test_tp2_dp2_zero2(baseline):
