@@ -12,6 +12,11 @@ initialize_optimizer → initialize_trainer → trainer.execute_schedule / train
   * "value": K full optimizer steps (fwd + bwd over all micro-batches + grad sync + clip + AdamW + param sync), timed
     with CUDA events between barrier+synchronize brackets, max over ranks;
   * "e2e":   the same K steps with each step's batch copied from pinned host memory and the step loss read back to the host.
+With N >= 2 (and no explicit --tp) the same process then re-initialises in the layout BASELINE.json names for the
+multi-GPU config - TP=2 + Hybrid-ZeRO over N/2 data-parallel ranks - and reports it under the "tp2" key of the SAME line
+(both arms do this, so the driver can compare them layout by layout).
+Every step sees FRESH random token ids (a pool of pinned host batches, none repeated inside a timed region), so the loss
+stays near ln(V) and the power draw does not depend on memorised data.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -48,6 +53,7 @@ def parse():
     p.add_argument("--checkpoint", type=float, default=0.0)
     p.add_argument("--attn", default=None, help="attention implementation override (b200|flash_attn|sdpa)")
     p.add_argument("--fused-comm", type=int, default=-1, help="peer-memory fused collectives (default: on when N>1)")
+    p.add_argument("--no-tp2", action="store_true", help="skip the secondary TP=2 + Hybrid-ZeRO measurement (N >= 2)")
     return p.parse_args()
 
 
@@ -134,11 +140,11 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_batches(n, micro_num, T, vocab, pin):
+def make_batches(n, micro_num, T, vocab, pin, seed=1234):
     """Synthetic packed batches in (pinned) host memory: one 4096-token segment per micro-batch row."""
     import torch
 
-    g = torch.Generator().manual_seed(1234)
+    g = torch.Generator().manual_seed(seed)
     out = []
     for _ in range(n):
         ids = torch.randint(1, vocab, (micro_num, T), generator=g, dtype=torch.long)
@@ -158,7 +164,7 @@ def batch_bytes(b):
     return sum(v.numel() * v.element_size() for v in d.values()) + l.numel() * l.element_size()
 
 
-def timed_loop(torch, dist, step_fn, batches, steps, world, sampler=None, finish=None):
+def timed_loop(torch, dist, step_fn, batches, steps, world, sampler=None, finish=None, first=0):
     """K steps between barrier + synchronize brackets, CUDA events on the compute stream, max over ranks.
     ``finish`` (optional) joins work the steps left on side streams (the overlapped optimizer update of the LAST step) into
     the compute stream before the end event is recorded, so the event pair covers all K steps completely."""
@@ -173,7 +179,7 @@ def timed_loop(torch, dist, step_fn, batches, steps, world, sampler=None, finish
     s.record()
     last = None
     for i in range(steps):
-        last = step_fn(batches[i % len(batches)])
+        last = step_fn(batches[(first + i) % len(batches)])
     if finish is not None:
         finish()
     e.record()
@@ -244,24 +250,27 @@ def run(a, ours: bool):
         launches = lambda: 0  # noqa: E731
         assert "baseline/_ref" in fw.__file__.replace(os.sep, "/"), fw.__file__
 
+    torch.cuda.reset_peak_memory_stats()
     initialize_distributed_env(config=cfg, launcher="torch", seed=1024)
     model = initialize_model()
     isp = initialize_isp_communicator(model)
     criterion = FlashGPTLMLoss(parallel_output=True, label_smoothing=0)
     optimizer, beta2_scheduler, lr_scheduler = initialize_optimizer(model, isp)
+    # the same (empty) metric hook on both arms: the reference's AccPerplex needs torch_scatter, which this image lacks
     if ours:
-        metric = AccPerplex(dataset_types=None)
-        hooks = get_scheduler_hooks(metric, optimizer, isp)
+        hooks = get_scheduler_hooks(None, optimizer, isp)
     else:
         from internlm.model.metrics import SchedulerMetricHook
 
-        hooks = [SchedulerMetricHook(metric=None, skip=True)]  # no AccPerplex: torch_scatter is not in this image
+        hooks = [SchedulerMetricHook(metric=None, skip=True)]
     trainer, _, _, _ = fw.initialize_trainer(model=model, optimizer=optimizer, criterion=criterion,
                                              lr_scheduler=lr_scheduler, beta2_scheduler=beta2_scheduler,
                                              scheduler_hooks=hooks)
     trainer.train()
     T = a.seq_len * a.micro_bsz
-    host_batches = make_batches(4, a.micro_num, T, MODEL_7B["vocab_size"], pin=True)
+    # fresh ids for every step of the run: W warm-up + K device-timed + 1 + K end-to-end steps, every rank its own stream
+    n_pool = min(96, a.warmup + 2 * a.steps + 1)
+    host_batches = make_batches(n_pool, a.micro_num, T, MODEL_7B["vocab_size"], pin=True, seed=1234 + 7919 * rank)
     dev_batches = [({k: v.cuda() for k, v in d.items()}, l.cuda()) for d, l in host_batches]
 
     skipped = [0]   # the reference arm only reports skipped steps (its loss-scale warm-up is its own business)
@@ -287,10 +296,12 @@ def run(a, ours: bool):
     l0 = launches()
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) if rank == 0 else None
     finish = getattr(optimizer, "flush_param_update", None)
-    ms, wall_ms, clocks, last = timed_loop(torch, dist, step_dev, dev_batches, a.steps, world, sampler, finish)
+    ms, wall_ms, clocks, last = timed_loop(torch, dist, step_dev, dev_batches, a.steps, world, sampler, finish,
+                                           first=a.warmup)
     n_launch = launches() - l0
-    step_e2e(host_batches[0])
-    e2e_ms, e2e_wall, _, last_e2e = timed_loop(torch, dist, step_e2e, host_batches, a.steps, world, None, finish)
+    step_e2e(host_batches[(a.warmup + a.steps) % n_pool])
+    e2e_ms, e2e_wall, _, last_e2e = timed_loop(torch, dist, step_e2e, host_batches, a.steps, world, None, finish,
+                                               first=a.warmup + a.steps + 1)
     e2e_ms = max(e2e_ms, e2e_wall)  # the host read-back is part of the region: take the host clock if it is longer
 
     tokens_per_step = T * a.micro_num * dp
@@ -312,7 +323,8 @@ def run(a, ours: bool):
             "unit": "tokens/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": round(ms / a.steps, 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": round(value / (BASELINE_TGS * world), 3) if full else None, "dtype": "bf16",
-            "data": "synthetic packed tokens (random ids, one 4096-token segment per micro-batch), random-init weights",
+            "data": "synthetic packed tokens (fresh random ids every step, one 4096-token segment per micro-batch), "
+                    "random-init weights",
             "impl": "ours" if ours else "reference",
             "tgs": round(value / world, 1), "tflops_per_gpu": round(tflops, 1),
             "config": {"model": "InternLM2-7B (h4096 L32 H32/kv8 mlp3.5 V92544)" if full else
@@ -321,19 +333,40 @@ def run(a, ours: bool):
                        "micro_bsz": a.micro_bsz, "micro_num": a.micro_num,
                        "parallelism": f"tp{tp}({a.tp_mode})-dp{dp}-zero{dp}", "act_ckpt": a.checkpoint,
                        "l2": "working set >> L2: 15.5 GB of bf16 weights + activations are streamed every step",
-                       "fused_comm": bool(cfg.get("fused_comm", False)) if ours else None},
+                       "fused_comm": bool(cfg.get("fused_comm", False)) if ours else None,
+                       "zero_overlap": (bool(getattr(optimizer, "_overlap_sync_grad", False)) if ours else None),
+                       "metric_hook": "none (both arms)"},
             "e2e": {"value": round(e2e_value, 1), "unit": "tokens/s", "h2d_bytes_per_step": batch_bytes(host_batches[0]),
                     "d2h_bytes_per_step": 4 + 16 * (len(optimizer.groups) if ours else 1),
                     "ms_per_step": round(e2e_ms / a.steps, 2)},
             "gpu_launches": int(n_launch), "clocks": clocks, "last_loss": float(last) if last is not None else None,
             "peak_mem_gib": round(mem, 1), "skipped_steps": skipped[0],
         }
-        print(json.dumps(res), flush=True)
+    else:
+        res = None
+    # tear the layout down completely (model, optimizer state, symmetric heaps, process groups): a second layout may follow
+    del trainer, optimizer, model, criterion, hooks, dev_batches, host_batches
+    import gc
+
+    gc.collect()
     gpc.destroy()
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
+
+
+def _tp2_args(a):
+    import copy
+
+    b = copy.copy(a)
+    b.tp, b.tp_mode, b.no_tp2 = 2, "mtp", True
+    return b
 
 
 def main():
     a = parse()
+    rank0 = int(os.environ.get("RANK", "0")) == 0
+    want_tp2 = a.gpus >= 2 and a.gpus % 2 == 0 and a.tp == 0 and not a.no_tp2
     if a.impl == "reference":
         ref = os.path.join(ROOT, "baseline", "_ref", "internlm")
         if not os.path.isdir(ref):
@@ -341,15 +374,48 @@ def main():
                               "(pip install --no-index --target baseline/_ref /root/reference)"}))
             return 0
         try:
-            run(a, ours=False)
+            res = run(a, ours=False)
         except BaseException as e:  # the reference's stock path may not run on sm_100 in this image
-            if int(os.environ.get("RANK", "0")) == 0:
+            if rank0:
                 msg = f"{type(e).__name__}: {str(e).splitlines()[0] if str(e) else ''}"[:300]
                 print(json.dumps({"impl": "reference", "unavailable": msg}), flush=True)
             if os.environ.get("BENCH_DEBUG"):
                 raise
-        return 0
-    run(a, ours=True)
+            return 0
+    else:
+        res = run(a, ours=True)
+    if want_tp2:
+        # second layout in the same process: TP=2 + Hybrid-ZeRO over N/2 data-parallel ranks (BASELINE.json's named layout)
+        # watchdog: if the second layout wedges (a rendezvous or collective that never returns), rank 0 still prints the main
+        # result - with the reason - and the process exits instead of hanging the driver
+        def bail():
+            if rank0 and res is not None:
+                res["tp2"] = {"unavailable": "secondary layout did not finish within 420 s"}
+                print(json.dumps(res), flush=True)
+            os._exit(0)
+
+        dog = threading.Timer(420.0, bail)
+        dog.daemon = True
+        dog.start()
+        try:
+            import gc
+
+            gc.collect()
+            sub = run(_tp2_args(a), ours=a.impl != "reference")
+            if rank0 and sub is not None:
+                keep = ("value", "unit", "ms_per_step", "tgs", "tflops_per_gpu", "e2e", "gpu_launches", "last_loss",
+                        "peak_mem_gib", "skipped_steps")
+                res["tp2"] = {k: sub[k] for k in keep if k in sub}
+                res["tp2"]["parallelism"] = sub["config"]["parallelism"]
+                res["tp2"]["global_batch"] = sub["config"]["global_batch"]
+        except BaseException as e:
+            if rank0 and res is not None:
+                res["tp2"] = {"unavailable": f"{type(e).__name__}: {str(e).splitlines()[0] if str(e) else ''}"[:300]}
+            if os.environ.get("BENCH_DEBUG"):
+                raise
+        dog.cancel()
+    if rank0 and res is not None:
+        print(json.dumps(res), flush=True)
     return 0
 
 

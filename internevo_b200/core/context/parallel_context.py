@@ -341,6 +341,14 @@ class ParallelContext:
         self.virtual_pipeline_parallel_rank = rank
 
     def destroy(self):
+        # peer-memory back-ends cache symmetric buffers / flag epochs keyed by process group: drop them with the groups so a
+        # later initialisation in the same process (another layout, another test) starts from a clean heap
+        try:
+            from internevo_b200.parallel import reset_caches
+
+            reset_caches()
+        except Exception:  # pragma: no cover - teardown must not raise
+            pass
         if self.is_distributed:
             try:
                 dist.barrier()
