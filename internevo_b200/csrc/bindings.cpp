@@ -352,7 +352,8 @@ void reduce_scatter_adam_mc(int64_t grad_mc, int64_t param_mc, int64_t grad_loca
 // [M, N] symmetric output, out_ptrs its per-rank pointer table).  stage_ptrs: per-rank symmetric staging
 // [world, M/world, N] that the peers' epilogues push their partial tiles into.
 void gemm_rs(const Tensor& a, const Tensor& b, Tensor& out, int64_t stage_ptrs, int64_t out_ptrs, int64_t flags_ptrs,
-             int64_t rank, int64_t world, int64_t epoch, bool b_mn, int64_t mode) {
+             int64_t rank, int64_t world, int64_t epoch, bool b_mn, int64_t mode, int64_t done_ptrs,
+             const optional<Tensor>& done_counter) {
     CHECK_BF16(a); CHECK_BF16(b); CHECK_BF16(out);
     c10::cuda::CUDAGuard guard(a.device());
     b200::GemmCommDesc d;
@@ -368,6 +369,11 @@ void gemm_rs(const Tensor& a, const Tensor& b, Tensor& out, int64_t stage_ptrs, 
     d.flags_ptrs = reinterpret_cast<uint32_t* const*>(flags_ptrs);
     d.rank = rank; d.world = world; d.epoch = (uint32_t)epoch; d.mode = mode;
     d.out_local = out.data_ptr(); d.ld_out = out.stride(0);
+    d.done_ptrs = reinterpret_cast<uint32_t* const*>(done_ptrs);
+    if (done_counter.has_value()) {
+        TORCH_CHECK(done_counter->is_cuda() && done_counter->scalar_type() == at::kInt, "gemm_rs: done_counter must be cuda int32");
+        d.done_counter = reinterpret_cast<uint32_t*>(done_counter->data_ptr<int>());
+    }
     CHECK_RC(b200::gemm_reduce_scatter(d, cur_stream()), "b200::gemm_rs");
 }
 
@@ -487,6 +493,6 @@ TORCH_LIBRARY(b200, m) {
     m.def("symm_allgather_small(int buf_ptrs, Tensor src, int flags_ptrs, int rank, int world, int epoch) -> ()", &symm_allgather_small);
     m.def("moe_scatter_rows(Tensor x, Tensor slot_rank, Tensor slot_row, Tensor? scale, int x_ptrs, int y_ptrs, Tensor(a!)? dw, int k) -> ()", &moe_scatter_rows);
     m.def("moe_gather_combine(Tensor(a!) out, Tensor? w, Tensor slot_rank, Tensor slot_row, int y_ptrs, int k) -> ()", &moe_gather_combine);
-    m.def("gemm_rs(Tensor a, Tensor b, Tensor(a!) out, int stage_ptrs, int out_ptrs, int flags_ptrs, int rank, int world, int epoch, bool b_mn, int mode) -> ()", &gemm_rs);
+    m.def("gemm_rs(Tensor a, Tensor b, Tensor(a!) out, int stage_ptrs, int out_ptrs, int flags_ptrs, int rank, int world, int epoch, bool b_mn, int mode, int done_ptrs, Tensor? done_counter) -> ()", &gemm_rs);
     m.def("ag_gemm(Tensor x_local, int gathered_ptrs, int flags_ptrs, int rank, int world, int epoch, Tensor b, bool b_mn, Tensor(a!) gathered, Tensor(b!) out, int flags, Tensor? h, int comm_ctas) -> ()", &ag_gemm);
 }

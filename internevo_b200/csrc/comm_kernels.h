@@ -41,7 +41,9 @@ struct GemmCommDesc {
     void* out_local = nullptr;
     int64_t ld_out = 0;
     const void* x_local = nullptr;      // ag_gemm: this rank's shard
-    int comm_ctas = 8;
+    int comm_ctas = 0;
+    uint32_t* const* done_ptrs = nullptr;   // all-reduce: per-rank completion words
+    uint32_t* done_counter = nullptr;       // all-reduce: local finished-CTA counter
 };
 int gemm_reduce_scatter(const GemmCommDesc& d, cudaStream_t s);
 int allgather_gemm(const GemmCommDesc& d, cudaStream_t s);

@@ -83,17 +83,23 @@ B200_DEVICE void item_coords(int item, const GemmKernelArgs& a, int& tm, int& tn
     n_off = slice * width;
 }
 
+// A "block" below is a 128-row slab of the output (one CTA's share of a tile): with CG == 2 the pair's tile tm covers
+// blocks 2 tm and 2 tm + 1.  Flags, ownership and staging are all per block, so the 1-CTA and the 2-CTA kernels share the
+// protocol.
+static constexpr int AG_PARTS = 16;  // an all-gather block is pushed as 16 pieces of 8 rows, each with its own flag word
+
 struct CommKernelArgs {
     int mode;
     void* const* peer_ptrs;        // AG: every rank's gathered A [M, K]; RS/AR: every rank's staging [world, m_local, N]
     uint32_t* const* flags_ptrs;   // every rank's flag words for this operation
     void* const* out_ptrs;         // AR: every rank's output [M, N]
+    uint32_t* const* done_ptrs;    // AR: every rank's `world` completion words (end-of-kernel handshake)
+    uint32_t* done_counter;        // AR: local counter of finished CTAs (wraps to 0 by atomicInc)
     int rank, world;
     uint32_t epoch;
     int m_local;          // rows per rank
     void* out_local;      // RS: reduced rows [m_local, N]
     int64_t ld_out;
-    int gemm_ctas;        // CTAs [0, gemm_ctas) run the GEMM, the rest (AG only) run the copy-engine role
     const void* x_local;  // AG: this rank's shard [m_local, K] (contiguous)
 };
 
@@ -104,23 +110,9 @@ B200_DEVICE uint4 ld_cg_v4(const void* p) {
     asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
-// 1-D bulk copies through the TMA unit (no tensor map): global -> shared with mbarrier completion, shared -> global
-// (works on peer-mapped addresses: the destination may live in another GPU's HBM behind NVLink).
-B200_DEVICE void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
+B200_DEVICE void st_v4(void* p, uint4 v) {
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-B200_DEVICE void bulk_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
-                 "r"(bytes)
-                 : "memory");
-}
-template <int N>
-B200_DEVICE void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-template <int N>
-B200_DEVICE void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Rotation of the m-tile order: AG starts on the local shard (no waiting), then the shards in the order the peers push
 // them; RS/AR starts with the rows of rank+1 (pushed to their owner first) and finishes on the rows this rank owns.
@@ -131,62 +123,38 @@ B200_DEVICE int comm_remap_m(int m, int tiles_m, const CommKernelArgs& c) {
     return (m + shift) % tiles_m;
 }
 
-// ---- all-gather copy-engine role: CTAs [gemm_ctas, gridDim.x) of the SAME kernel ------------------------------------
-// One thread per CTA drives the TMA unit: 128-row chunks of the local shard stream HBM -> shared -> every peer's
-// gathered-A buffer (posted NVLink writes, so nothing here waits on a round trip), then the chunk's flag is released on
-// that peer.  The peer's GEMM producer acquires the flag right before the first TMA load of a tile that needs the rows.
-template <int BN>
-B200_DEVICE void ag_push_role(const GemmKernelArgs& args, const CommKernelArgs& c, uint8_t* smem) {
-    constexpr int PIECE = 32 * 1024, SLOTS = 7, AHEAD = 2, PENDING = SLOTS - AHEAD - 1;
-    __shared__ __align__(8) uint64_t ld_bar[SLOTS];
-    if (threadIdx.x != 0) return;
-    const int cta = blockIdx.x - c.gemm_ctas, ncta = gridDim.x - c.gemm_ctas;
-    for (int i = 0; i < SLOTS; ++i) mbar_init(&ld_bar[i], 1);
-    fence_barrier_init();
-    const int per = args.tiles_m / c.world;
-    const int64_t row_bytes = (int64_t)args.K * 2;
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(c.x_local);
-    const int64_t dst_base = (int64_t)c.rank * c.m_local * row_bytes;
-    auto chunk_bytes = [&](int ch) { return (int64_t)min(BM, c.m_local - ch * BM) * row_bytes; };
-
-    // two cursors over this CTA's piece sequence: loads run AHEAD pieces in front of the stores
-    int ld_ch = cta, st_ch = cta;
-    int64_t ld_o = 0, st_o = 0;
-    uint32_t n_ld = 0, n_st = 0;
-    auto issue_load = [&]() {
-        const int64_t cb = chunk_bytes(ld_ch);
-        const uint32_t n = static_cast<uint32_t>(min((int64_t)PIECE, cb - ld_o));
-        const int slot = n_ld % SLOTS;
-        bulk_wait_read<PENDING>();  // the stores that last read this slot (piece n_ld - SLOTS) have drained it
-        mbar_expect_tx(&ld_bar[slot], n);
-        bulk_load_1d(smem + slot * PIECE, src + (int64_t)ld_ch * BM * row_bytes + ld_o, n, &ld_bar[slot]);
-        ++n_ld;
-        ld_o += PIECE;
-        if (ld_o >= cb) { ld_o = 0; ld_ch += ncta; }
-    };
-    for (int i = 0; i < AHEAD && ld_ch < per; ++i) issue_load();
-    while (st_ch < per) {
-        if (ld_ch < per) issue_load();
-        const int64_t cb = chunk_bytes(st_ch);
-        const uint32_t n = static_cast<uint32_t>(min((int64_t)PIECE, cb - st_o));
-        const int slot = n_st % SLOTS;
-        mbar_wait(&ld_bar[slot], (n_st / SLOTS) & 1);
-        const int64_t off = dst_base + (int64_t)st_ch * BM * row_bytes + st_o;
-        for (int p = 0; p < c.world; ++p) {
-            const int pr = (c.rank + 1 + p) % c.world;  // peers first, the local copy (kept for wgrad) last
-            bulk_store_1d(reinterpret_cast<uint8_t*>(c.peer_ptrs[pr]) + off, smem + slot * PIECE, n);
+// ---- all-gather push: the four epilogue warps of EVERY CTA, before their first tile is due --------------------------------
+// The local shard [m_local, K] goes to every peer's gathered buffer (and to the local one, which wgrad reads later) in
+// pieces of 8 rows: 128 threads move 16 bytes each per step with plain vector loads / stores - NVLink writes are posted, so
+// nothing waits for a round trip - and the piece's flag is released on every peer once the CTA's stores are ordered before
+// it.  With ~148 CTAs pushing, no single SM's store path limits the link; the accumulators are double-buffered, so the
+// tensor cores run two tiles ahead while the epilogue warps are busy here.
+B200_DEVICE void ag_push_pieces(const GemmKernelArgs& args, const CommKernelArgs& c, int t /*0..127*/) {
+    const int blocks_local = c.m_local / BM;
+    const int pieces = blocks_local * AG_PARTS;
+    const int64_t piece_bytes = (int64_t)(BM / AG_PARTS) * args.K * 2;
+    const uint8_t* src0 = reinterpret_cast<const uint8_t*>(c.x_local);
+    const int64_t dst_base = (int64_t)c.rank * c.m_local * args.K * 2;
+    for (int p = blockIdx.x; p < pieces; p += gridDim.x) {
+        const uint8_t* src = src0 + (int64_t)p * piece_bytes;
+        const int64_t doff = dst_base + (int64_t)p * piece_bytes;
+        for (int64_t o = (int64_t)t * 16; o < piece_bytes; o += 4 * 128 * 16) {
+            uint4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (o + j * 2048 < piece_bytes) v[j] = ld_nc_v4(src + o + j * 2048);
+            for (int q = 0; q < c.world; ++q) {
+                uint8_t* dst = reinterpret_cast<uint8_t*>(c.peer_ptrs[(c.rank + 1 + q) % c.world]) + doff;  // local copy last
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (o + j * 2048 < piece_bytes) st_v4(dst + o + j * 2048, v[j]);
+            }
         }
-        tma_store_commit();
-        ++n_st;
-        st_o += PIECE;
-        if (st_o >= cb) {
-            bulk_wait_all<0>();  // every write of this chunk has been performed
-            fence_proxy_async_all();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (t < c.world) {   // one thread per destination publishes the piece there
             fence_acq_rel_sys();
-            const int m = c.rank * per + st_ch;
-            for (int p = 0; p < c.world; ++p) st_release_sys(c.flags_ptrs[(c.rank + 1 + p) % c.world] + m, c.epoch);
-            st_o = 0;
-            st_ch += ncta;
+            const int b = p / AG_PARTS, j = p % AG_PARTS;
+            st_release_sys(c.flags_ptrs[(c.rank + 1 + t) % c.world] + (c.rank * blocks_local + b) * AG_PARTS + j, c.epoch);
         }
     }
 }
@@ -195,21 +163,15 @@ template <int BN, bool COMM, int CG = 1>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_bt, const GemmKernelArgs args, const CommKernelArgs comm) {
-    static_assert(CG == 1 || (!COMM && BN == 256), "2-CTA tiles: plain GEMM, BN = 256");
+    static_assert(CG == 1 || BN == 256, "2-CTA tiles: BN = 256");
     using Cfg = GemmCfg<BN, CG>;
     griddep_launch_dependents();  // PDL (launch.h): the next kernel's CTAs may take over SMs this grid's tail has left
     const int cta_rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
-    if constexpr (COMM) {
-        if (static_cast<int>(blockIdx.x) >= comm.gemm_ctas) {
-            ag_push_role<BN>(args, comm, smem);
-            return;
-        }
-    }
     // persistent schedule over work units (a unit = one CTA, or one CTA pair)
-    const int grid_ctas = (COMM ? comm.gemm_ctas : static_cast<int>(gridDim.x)) / CG;
+    const int grid_ctas = static_cast<int>(gridDim.x) / CG;
     const int unit = static_cast<int>(blockIdx.x) / CG;
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
@@ -249,9 +211,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        {
             int stage = 0;
             uint32_t phase = 0;
+            uint64_t ready = 0;  // all-gather: blocks (of the first 64) whose pieces are known to have landed
             for (int tile = unit; tile < num_items; tile += grid_ctas) {
                 int tm, tn, n_off, width;
                 item_coords<BN>(tile, args, tm, tn, n_off, width);
@@ -260,15 +223,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     tm = comm_remap_m(tm, args.tiles_m, comm);
                     if (comm.mode == GEMM_COMM_ALL_GATHER) {
                         own_rows = tm / (args.tiles_m / comm.world) == comm.rank;
-                        if (!own_rows) {
-                            // these rows are pushed into the local gathered buffer by their owner's copy CTAs
-                            const uint32_t* f = comm.flags_ptrs[comm.rank] + tm;
-                            while (static_cast<int32_t>(ld_acquire_sys(f) - comm.epoch) < 0) {
+                        const int blk = tm * CG + cta_rank;
+                        if (!own_rows && !(blk < 64 && ((ready >> blk) & 1))) {
+                            // these rows are pushed into the local gathered buffer by their owner's epilogue warps, 16 pieces per
+                            // block: lanes 0..15 each acquire one piece flag
+                            if (lane < AG_PARTS) {
+                                const uint32_t* f = comm.flags_ptrs[comm.rank] + blk * AG_PARTS + lane;
+                                while (static_cast<int32_t>(ld_acquire_sys(f) - comm.epoch) < 0) {
+                                }
                             }
+                            __syncwarp();
                             fence_proxy_async_all();
+                            if (blk < 64) ready |= 1ull << blk;
                         }
                     }
                 }
+                if (lane != 0) continue;   // lane 0 issues every TMA load of the tile
                 const int m0 = (tm * CG + cta_rank) * BM, n0 = tn * BN + n_off + cta_rank * (width / CG);
                 const int m0_own = m0 - comm.rank * comm.m_local;
                 // 2-CTA: every CTA loads its rows of A and its half of B, all bytes are counted on the leader's barrier
@@ -284,7 +254,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
                     const int k0 = kb * BK;
                     if (COMM && own_rows) {  // the local shard is read in place (tmap_bt doubles as its map)
-                        tma_load_2d(sa, &tmap_bt, &full_bar[stage], k0, m0_own);
+                        ld(sa, &tmap_bt, &full_bar[stage], k0, m0_own);
                     } else if (!args.a_mn) {
                         ld(sa, &tmap_a, &full_bar[stage], k0, m0);
                     } else {
@@ -358,47 +328,47 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const bool accumulate = args.flags & GEMM_ACCUMULATE;
         const bool swiglu = args.flags & GEMM_SWIGLU;
         const bool no_store_d = args.flags & GEMM_SKIP_D;
+        bool rs_mode = false;
+        if constexpr (COMM) {
+            rs_mode = comm.mode == GEMM_COMM_REDUCE_SCATTER || comm.mode == GEMM_COMM_ALL_REDUCE;
+            // all-gather: push the local shard to every peer first (the MMA warp runs up to two tiles ahead meanwhile)
+            if (comm.mode == GEMM_COMM_ALL_GATHER) ag_push_pieces(args, comm, static_cast<int>(threadIdx.x) - 64);
+        }
         for (int tile = unit; tile < num_items; tile += grid_ctas) {
             int tm, tn, n_off, width;
             item_coords<BN>(tile, args, tm, tn, n_off, width);
             if constexpr (COMM) tm = comm_remap_m(tm, args.tiles_m, comm);
-            const int row = (tm * CG + cta_rank) * BM + q * 32 + lane;
+            const int blk = tm * CG + cta_rank;   // 128-row block of this CTA
+            const int row = blk * BM + q * 32 + lane;
             const int n0 = tn * BN + n_off;
-            // reduce-scatter / all-reduce: rows owned by a peer are pushed straight into that peer's staging slot,
-            // rows owned by this rank are reduced with what the peers pushed and written as the final result
-            bool rs_mode = false, own = false;
-            int owner = 0, row_local = 0;
+            const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
             if constexpr (COMM) {
-                rs_mode = comm.mode == GEMM_COMM_REDUCE_SCATTER || comm.mode == GEMM_COMM_ALL_REDUCE;
                 if (rs_mode) {
-                    const int per = args.tiles_m / comm.world;
-                    owner = tm / per;
-                    own = owner == comm.rank;
-                    row_local = row - owner * comm.m_local;
+                    // ---- reduce-scatter / all-reduce -------------------------------------------------------------------
+                    // A block owned by a peer: the bf16 partial goes straight into that peer's staging slot.  A block owned
+                    // by this rank (scheduled last): add what the peers staged and write the final rows - to the local
+                    // output (RS) or to every rank's output (AR).  Either way the 32 x 128 sub-tile of a warp is transposed
+                    // through shared memory (16-byte units XOR-swizzled by row) so that 16 lanes store one contiguous
+                    // 256-byte row segment: NVLink wants whole 128-byte requests.
+                    const int per_blk = args.tiles_m * CG / comm.world;
+                    const int owner = blk / per_blk;
+                    const bool own = owner == comm.rank;
+                    const int blk_local = blk - owner * per_blk;
+                    const int row0_local = blk_local * BM + q * 32;   // first row of this warp inside the owner's shard
                     if (own) {
                         if (warp == 2 && lane < comm.world && lane != comm.rank) {
-                            const uint32_t* f = comm.flags_ptrs[comm.rank] + (int64_t)lane * per * args.tiles_n +
-                                                (tm - owner * per) * args.tiles_n + tn;
+                            const uint32_t* f = comm.flags_ptrs[comm.rank] + ((int64_t)lane * per_blk + blk_local) * args.tiles_n + tn;
                             while (static_cast<int32_t>(ld_acquire_sys(f) - comm.epoch) < 0) {
                             }
                         }
                         asm volatile("bar.sync 1, 128;" ::: "memory");
                     }
-                }
-            }
-            mbar_wait(&tmem_full[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
-            bool pushed = false;
-            if constexpr (COMM) {
-                if (rs_mode && !own) {
-                    // Push the bf16 partial tile into its owner's staging slot.  NVLink wants whole 128-byte requests:
-                    // every warp transposes 32 rows x 128 columns through shared memory (16-byte units XOR-swizzled by
-                    // row) so that 16 lanes store one contiguous 256-byte row segment.
+                    mbar_wait(&tmem_full[acc], acc_phase);
+                    tc_fence_after();
                     uint8_t* wst = smem + STAGES * Cfg::STAGE_BYTES + 256 + q * 8192;
-                    __nv_bfloat16* dbase = reinterpret_cast<__nv_bfloat16*>(comm.peer_ptrs[owner]) +
-                                           ((int64_t)comm.rank * comm.m_local + (tm * BM + q * 32 - owner * comm.m_local)) *
-                                               args.N + n0;
+                    const __nv_bfloat16* staged = reinterpret_cast<const __nv_bfloat16*>(comm.peer_ptrs[comm.rank]);
+                    int ndst = 1;
+                    if (own && comm.mode == GEMM_COMM_ALL_REDUCE) ndst = comm.world;
 #pragma unroll 1
                     for (int half = 0; half < BN / 128; ++half) {
 #pragma unroll 1
@@ -406,13 +376,33 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             uint32_t r[32];
                             tmem_ld_32x32b_x32(taddr + half * 128 + c4 * 32, r);
                             tmem_ld_wait();
+                            float v[32];
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                            const int col = n0 + half * 128 + c4 * 32;
+                            if (own && col < args.N) {
+                                for (int pr = 1; pr < comm.world; ++pr) {
+                                    const int sl = (comm.rank + pr) % comm.world;
+                                    const __nv_bfloat16* src = staged + ((int64_t)sl * comm.m_local + row0_local + lane) * args.N + col;
+#pragma unroll
+                                    for (int i = 0; i < 32; i += 8) {
+                                        if (col + i < args.N) {
+                                            const uint4 x = ld_cg_v4(src + i);
+                                            float2 a = unpack_bf16(x.x), b = unpack_bf16(x.y), cq = unpack_bf16(x.z),
+                                                   dd = unpack_bf16(x.w);
+                                            v[i] += a.x; v[i + 1] += a.y; v[i + 2] += b.x; v[i + 3] += b.y;
+                                            v[i + 4] += cq.x; v[i + 5] += cq.y; v[i + 6] += dd.x; v[i + 7] += dd.y;
+                                        }
+                                    }
+                                }
+                            }
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 uint4 o;
-                                o.x = pack_bf16(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1]));
-                                o.y = pack_bf16(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
-                                o.z = pack_bf16(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
-                                o.w = pack_bf16(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+                                o.x = pack_bf16(v[8 * j], v[8 * j + 1]);
+                                o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+                                o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+                                o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
                                 const int u = c4 * 4 + j;
                                 *reinterpret_cast<uint4*>(wst + lane * 256 + ((u ^ (lane & 7)) << 4)) = o;
                             }
@@ -420,20 +410,53 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         __syncwarp();
                         const int u = lane & 15;
                         const int col = n0 + half * 128 + u * 8;
+                        for (int d = 0; d < ndst; ++d) {
+                            __nv_bfloat16* dbase;
+                            int64_t ldd;
+                            if (!own) {            // the owner's staging slot of this rank
+                                dbase = reinterpret_cast<__nv_bfloat16*>(comm.peer_ptrs[owner]) +
+                                        ((int64_t)comm.rank * comm.m_local + row0_local) * args.N;
+                                ldd = args.N;
+                            } else if (comm.mode == GEMM_COMM_REDUCE_SCATTER) {
+                                dbase = reinterpret_cast<__nv_bfloat16*>(comm.out_local) + (int64_t)row0_local * comm.ld_out;
+                                ldd = comm.ld_out;
+                            } else {               // every rank's output, peers first
+                                dbase = reinterpret_cast<__nv_bfloat16*>(comm.out_ptrs[(comm.rank + 1 + d) % comm.world]) +
+                                        (int64_t)(blk * BM + q * 32) * comm.ld_out;
+                                ldd = comm.ld_out;
+                            }
 #pragma unroll 4
-                        for (int rr = 0; rr < 32; rr += 2) {
-                            const int rw = rr + (lane >> 4);
-                            const uint4 o = *reinterpret_cast<const uint4*>(wst + rw * 256 + ((u ^ (rw & 7)) << 4));
-                            if (col < args.N)
-                                *reinterpret_cast<uint4*>(dbase + (int64_t)rw * args.N + half * 128 + u * 8) = o;
+                            for (int rr = 0; rr < 32; rr += 2) {
+                                const int rw = rr + (lane >> 4);
+                                const uint4 o = *reinterpret_cast<const uint4*>(wst + rw * 256 + ((u ^ (rw & 7)) << 4));
+                                if (col < args.N) st_v4(dbase + (int64_t)rw * ldd + col, o);
+                            }
                         }
                         __syncwarp();
                     }
-                    pushed = true;
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if constexpr (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0);
+                        else mbar_arrive(&tmem_empty[acc]);
+                    }
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                    if (!own) {
+                        // the partial block x n-tile has been stored into its owner's staging slot: publish it there
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        if (warp == 2 && lane == 0) {
+                            fence_acq_rel_sys();
+                            st_release_sys(comm.flags_ptrs[owner] + ((int64_t)comm.rank * per_blk + blk_local) * args.tiles_n + tn,
+                                           comm.epoch);
+                        }
+                    }
+                    continue;
                 }
             }
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < width && !pushed; c += 32) {
+            for (int c = 0; c < width; c += 32) {
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(taddr + c, r);
                 tmem_ld_wait();
@@ -443,53 +466,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
                     const int ncols = min(32, args.N - col);  // multiple of 8 (host asserts N % 8 == 0)
-                    if constexpr (COMM) {
-                        if (rs_mode) {
-                            {
-                                const __nv_bfloat16* mine = reinterpret_cast<const __nv_bfloat16*>(
-                                    comm.peer_ptrs[comm.rank]);
-                                for (int p = 1; p < comm.world; ++p) {
-                                    const int sl = (comm.rank + p) % comm.world;
-                                    const __nv_bfloat16* src = mine + ((int64_t)sl * comm.m_local + row_local) * args.N + col;
-#pragma unroll
-                                    for (int i = 0; i < 32; i += 8) {
-                                        if (i < ncols) {
-                                            const uint4 x = ld_cg_v4(src + i);
-                                            float2 a = unpack_bf16(x.x), b = unpack_bf16(x.y), cq = unpack_bf16(x.z),
-                                                   dd = unpack_bf16(x.w);
-                                            v[i] += a.x; v[i + 1] += a.y; v[i + 2] += b.x; v[i + 3] += b.y;
-                                            v[i + 4] += cq.x; v[i + 5] += cq.y; v[i + 6] += dd.x; v[i + 7] += dd.y;
-                                        }
-                                    }
-                                }
-                                uint4 o[4];
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    o[i].x = pack_bf16(v[8 * i], v[8 * i + 1]);
-                                    o[i].y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
-                                    o[i].z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
-                                    o[i].w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
-                                }
-                                if (comm.mode == GEMM_COMM_REDUCE_SCATTER) {
-                                    __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(comm.out_local) +
-                                                       (int64_t)row_local * comm.ld_out + col;
-#pragma unroll
-                                    for (int i = 0; i < 4; ++i)
-                                        if (8 * i < ncols) *reinterpret_cast<uint4*>(d + 8 * i) = o[i];
-                                } else {
-                                    for (int p = 0; p < comm.world; ++p) {
-                                        __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(
-                                                               comm.out_ptrs[(comm.rank + p) % comm.world]) +
-                                                           (int64_t)row * comm.ld_out + col;
-#pragma unroll
-                                        for (int i = 0; i < 4; ++i)
-                                            if (8 * i < ncols) *reinterpret_cast<uint4*>(d + 8 * i) = o[i];
-                                    }
-                                }
-                            }
-                            continue;
-                        }
-                    }
                     if (args.bias != nullptr) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 8) {
@@ -595,19 +571,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 else mbar_arrive(&tmem_empty[acc]);
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-            if constexpr (COMM) {
-                if (rs_mode && !own) {
-                    // the partial tile has been stored into its owner's staging slot: publish it there
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (warp == 2 && lane == 0) {
-                        const int per = args.tiles_m / comm.world;
-                        fence_acq_rel_sys();
-                        st_release_sys(comm.flags_ptrs[owner] + (int64_t)comm.rank * per * args.tiles_n +
-                                           (tm - owner * per) * args.tiles_n + tn,
-                                       comm.epoch);
-                    }
-                }
-            }
         }
     }
 
@@ -617,6 +580,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
+    }
+    if constexpr (COMM) {
+        // all-reduce: the kernel must not complete before every peer has written its rows into this rank's output.  The last
+        // CTA to finish (atomicInc wraps the counter back to 0 for the next call) tells every peer that this rank is done
+        // and waits for the same word from each of them - the trailing device barrier, without a launch.
+        if (comm.mode == GEMM_COMM_ALL_REDUCE && threadIdx.x == 0) {
+            fence_acq_rel_sys();
+            if (atomicInc(comm.done_counter, gridDim.x - 1) == gridDim.x - 1) {
+                fence_acq_rel_sys();
+                for (int pr = 1; pr < comm.world; ++pr)
+                    st_release_sys(comm.done_ptrs[(comm.rank + pr) % comm.world] + comm.rank, comm.epoch);
+                for (int pr = 1; pr < comm.world; ++pr) {
+                    const uint32_t* f = comm.done_ptrs[comm.rank] + (comm.rank + pr) % comm.world;
+                    while (static_cast<int32_t>(ld_acquire_sys(f) - comm.epoch) < 0) {
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -793,19 +774,20 @@ static int launch(const GemmDesc& g, cudaStream_t stream) {
 //   / ALL_REDUCE    NVLink writes) and reduces the tiles this rank owns, which are scheduled last, with the slots the
 //                   peers filled.  No extra CTAs, no second pass over the output.
 int gemm_bf16_comm(const GemmDesc& g, const GemmCommArgs& c, cudaStream_t stream) {
-    constexpr int BN = 256;
-    using Cfg = GemmCfg<BN>;
+    constexpr int BN = 256, CG = 2;   // the CTA-pair tile (cta_group::2), same as the plain GEMM's default
+    using Cfg = GemmCfg<BN, CG>;
     if (c.world < 2 || g.a_mn_major) return -20;
-    const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
-    if (g.M % (BM * c.world) != 0) return -21;  // every rank owns whole 128-row tiles
+    const int tiles_m = (g.M + BM * CG - 1) / (BM * CG), tiles_n = (g.N + BN - 1) / BN;
+    if (g.M % (BM * CG * c.world) != 0) return -21;  // every rank owns whole 256-row tiles
     if (g.N % 8 != 0 || g.K % 8 != 0) return -22;
     const bool ag = c.mode == GEMM_COMM_ALL_GATHER;
+    if (c.mode == GEMM_COMM_ALL_REDUCE && (c.done_ptrs == nullptr || c.done_counter == nullptr)) return -23;
     CUtensorMap ta, tb, tx;
     int rc;
     // A: the gathered buffer (AG) or the local activations (RS / AR)
     rc = make_tmap_2d_bf16(&ta, ag ? c.out_local : g.A, g.K, g.M, ag ? (int64_t)g.K : g.lda, BK, BM);
     if (rc) return rc;
-    if (!g.b_mn_major) rc = make_tmap_2d_bf16(&tb, g.B, g.K, g.N, g.ldb, BK, BN);
+    if (!g.b_mn_major) rc = make_tmap_2d_bf16(&tb, g.B, g.K, g.N, g.ldb, BK, BN / CG);
     else               rc = make_tmap_2d_bf16(&tb, g.B, g.N, g.K, g.ldb, 64, BK);
     if (rc) return rc;
     tx = tb;
@@ -822,22 +804,26 @@ int gemm_bf16_comm(const GemmDesc& g, const GemmCommArgs& c, cudaStream_t stream
     a.tiles_m = tiles_m; a.tiles_n = tiles_n;
     CommKernelArgs k;
     k.mode = c.mode; k.peer_ptrs = c.peer_ptrs; k.flags_ptrs = c.flags_ptrs; k.out_ptrs = c.out_ptrs;
+    k.done_ptrs = c.done_ptrs; k.done_counter = c.done_counter;
     k.rank = c.rank; k.world = c.world; k.epoch = c.epoch; k.m_local = (int)c.m_local;
     k.out_local = c.out_local; k.ld_out = c.ld_out; k.x_local = c.x_local;
-    const int sms = num_sms();
-    const int comm_ctas = ag ? (c.comm_ctas > 0 ? c.comm_ctas : 8) : 0;
-    int gemm_ctas = sms - comm_ctas;
-    if (gemm_ctas > tiles_m * tiles_n) gemm_ctas = tiles_m * tiles_n;
-    k.gemm_ctas = gemm_ctas;
+    int units = num_sms() / CG;
+    // all-gather: every CTA also pushes a share of the local shard, so the whole machine is launched even for few tiles
+    if (!ag && units > tiles_m * tiles_n) units = tiles_m * tiles_n;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(gemm_bf16_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(gemm_bf16_kernel<BN, true, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  Cfg::SMEM_BYTES_COMM) != cudaSuccess)
             return -3;
         attr_set = true;
     }
-    gemm_bf16_kernel<BN, true><<<gemm_ctas + comm_ctas, NUM_THREADS, Cfg::SMEM_BYTES_COMM, stream>>>(ta, tb, tx, a, k);
-    return cudaGetLastError() == cudaSuccess ? 0 : -4;
+    cudaError_t e = launch_pdl(gemm_bf16_kernel<BN, true, CG>, dim3(units * CG), dim3(NUM_THREADS), Cfg::SMEM_BYTES_COMM, stream,
+                               CG, ta, tb, tx, a, k);
+    if (e != cudaSuccess) {
+        fprintf(stderr, "[b200] comm gemm launch failed: %s\n", cudaGetErrorString(e));
+        return -4;
+    }
+    return 0;
 }
 
 int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {

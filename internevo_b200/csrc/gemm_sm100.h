@@ -41,7 +41,7 @@ void set_gemm_group_m(int g);
 // ---- GEMM fused with its tensor-parallel collective (one launch, peer memory over NVLink) -------------------------
 enum GemmCommMode : int {
     GEMM_COMM_NONE = 0,
-    GEMM_COMM_ALL_GATHER = 1,      // A = all-gather of per-rank row shards, pushed by copy CTAs while early tiles compute
+    GEMM_COMM_ALL_GATHER = 1,      // A = all-gather of per-rank row shards, pushed by the epilogue warps of every CTA first
     GEMM_COMM_REDUCE_SCATTER = 2,  // epilogue pushes partial tiles to their owner; the owner's epilogue reduces
     GEMM_COMM_ALL_REDUCE = 3,      // as above, reduced rows are pushed into every peer's output
 };
@@ -49,7 +49,7 @@ enum GemmCommMode : int {
 struct GemmCommArgs {
     int mode = GEMM_COMM_NONE;
     void* const* peer_ptrs = nullptr;      // AG: per-rank gathered A [M, K]; RS/AR: per-rank staging [world, m_local, N]
-    uint32_t* const* flags_ptrs = nullptr; // per-rank flag arrays (uint32): AG tiles_m words, RS/AR tiles_m * tiles_n
+    uint32_t* const* flags_ptrs = nullptr; // per-rank flag arrays (uint32): AG 16 words per 128-row block, RS/AR blocks * tiles_n
     void* const* out_ptrs = nullptr;       // AR: per-rank final output [M, N]
     int rank = 0, world = 1;
     uint32_t epoch = 0;
@@ -57,7 +57,9 @@ struct GemmCommArgs {
     void* out_local = nullptr;             // AG: this rank's gathered A [M, K] (contiguous); RS: reduced rows [m_local, N]
     int64_t ld_out = 0;                    // RS / AR: row stride of the output
     const void* x_local = nullptr;         // AG: this rank's shard [m_local, K] (contiguous)
-    int comm_ctas = 8;                     // AG: number of copy CTAs
+    int comm_ctas = 0;                     // unused (the all-gather push runs on the epilogue warps of every CTA)
+    uint32_t* const* done_ptrs = nullptr;  // AR: per-rank `world` completion words (end-of-kernel handshake)
+    uint32_t* done_counter = nullptr;      // AR: local counter of finished CTAs
 };
 
 int gemm_bf16_comm(const GemmDesc& g, const GemmCommArgs& c, cudaStream_t stream);

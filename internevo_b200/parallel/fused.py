@@ -29,32 +29,35 @@ logger = get_logger(__file__)
 
 
 class TPFusedBackend:
-    """Symmetric scratch + launch logic for the fused TP linears of one process group.
+    """Symmetric scratch + launch logic for the fused TP linears of one process group (CTA-pair tcgen05 tile).
 
-    ``ag_gemm``  copy CTAs push this rank's activation shard into every peer's gathered buffer through the TMA unit
-                 while the GEMM CTAs of the same launch start on the local rows.
-    ``gemm_rs``  the GEMM epilogue stores partial tiles owned by a peer straight into that peer's staging slot over
-                 NVLink and reduces the tiles this rank owns (scheduled last) with what the peers pushed.
-    Scratch buffers are ping-pong pairs keyed by shape; a stream-ordered device barrier (6 us) in front of every launch
-    guarantees that the slot being overwritten on a peer is no longer in use there.
-    """
+    ``ag_gemm``  the epilogue warps of every CTA first push this rank's activation shard into every peer's gathered buffer
+                 (8-row pieces, one flag each) while the tensor cores start on the local rows; a tile of remote rows is
+                 loaded as soon as its pieces have landed.
+    ``gemm_rs``  the GEMM epilogue stores partial blocks owned by a peer straight into that peer's staging slot over
+                 NVLink and reduces the blocks this rank owns (scheduled last) with what the peers pushed; the all-reduce
+                 form writes the reduced rows into every rank's output and ends with an in-kernel completion handshake.
+    Scratch buffers are ping-pong pairs keyed by shape.  No barrier launch brackets the kernels: every call makes each rank
+    wait for data of EVERY peer, so when a rank starts call k all peers have started call k - 1 and therefore finished
+    call k - 2 - the last user of the slot call k overwrites."""
 
-    def __init__(self, group: dist.ProcessGroup, comm_ctas: int = 8):
+    def __init__(self, group: dist.ProcessGroup, comm_ctas: int = 0):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.flags = symm.flags_for(group)
-        self.comm_ctas = comm_ctas
         self._gath: Dict[Tuple[int, int], list] = {}     # (M, K) -> ping-pong gathered-activation buffers
         self._stage: Dict[Tuple[int, int], list] = {}    # (M, N) -> ping-pong [world, M/world, N] staging
         self._out: Dict[Tuple[int, int], list] = {}      # (M, N) -> ping-pong all-reduce outputs
+        self._done_counter = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
 
     def supports(self, M: int, x: torch.Tensor, weight: torch.Tensor) -> bool:
-        """bf16, whole 128-row tiles per rank, 16-byte aligned rows, flag space for every tile."""
-        return (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and M % (128 * self.world) == 0
+        """bf16, whole 256-row tiles per rank, 16-byte aligned rows, flag space for every block."""
+        return (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and M % (256 * self.world) == 0
                 and x.shape[1] % 8 == 0 and weight.shape[0] % 8 == 0 and weight.shape[1] % 8 == 0
                 and x.stride(-1) == 1 and weight.stride(1) == 1
-                and (M // 128) * ((max(weight.shape) + 255) // 256) <= symm.RS_FLAG_WORDS)
+                and (M // 128) * ((max(weight.shape) + 255) // 256) <= symm.RS_FLAG_WORDS
+                and (M // 128) * 16 <= symm.AG_FLAG_WORDS)
 
     def _pp(self, cache, key, numel):
         if key not in cache:
@@ -77,13 +80,13 @@ class TPFusedBackend:
         gb = self._pp(self._gath, (M, K), M * K)
         gathered = gb.tensor.view(M, K)
         out = torch.empty(M, N, device=x.device, dtype=x.dtype)
-        self.flags.barrier()  # the slot is free on every rank (its previous reader is stream-ordered before this)
         if symm.DEBUG:
+            self.flags.barrier()
             symm.poison(gathered)
             self.flags.barrier()
         torch.ops.b200.ag_gemm(x, gb.table_ptr(0), symm.ag_flag_table(self.flags), self.rank, self.world,
-                               self.flags.next_epoch(), weight, b_mn, gathered, out, 0, None, self.comm_ctas)
-        _bump(2)
+                               self.flags.next_epoch(), weight, b_mn, gathered, out, 0, None, 0)
+        _bump()
         if symm.DEBUG:
             symm.assert_clean(gathered, "ag_gemm gathered activations")
             symm.assert_clean(out, "ag_gemm output")
@@ -103,17 +106,17 @@ class TPFusedBackend:
         else:
             out = torch.empty(M // self.world, N, device=x.device, dtype=x.dtype)
             out_ptrs = 0
-        self.flags.barrier()  # staging / output slots are free on every rank
         if symm.DEBUG:
+            self.flags.barrier()
             symm.poison(stage.tensor)
             if all_reduce:
                 symm.poison(out)
             self.flags.barrier()
         torch.ops.b200.gemm_rs(x, weight, out, stage.table_ptr(0), out_ptrs, symm.rs_flag_table(self.flags), self.rank,
-                               self.world, self.flags.next_epoch(), b_mn, 1 if all_reduce else 0)
-        _bump(2)
+                               self.world, self.flags.next_epoch(), b_mn, 1 if all_reduce else 0,
+                               symm.done_flag_table(self.flags), self._done_counter)
+        _bump()
         if all_reduce:
-            self.flags.barrier()  # every rank has pushed its rows into everybody's output
             if symm.DEBUG:
                 symm.assert_clean(out, "gemm_rs all-reduce output")
             return out.clone()  # detach from the ping-pong slot (it is recycled two calls later)
@@ -129,14 +132,10 @@ def enable_tp(group: Optional[dist.ProcessGroup]) -> Optional[TPFusedBackend]:
     """Create (once) the fused backend for ``group`` and route the TP linears through it."""
     if group is None or dist.get_world_size(group) <= 1 or not symm.symm_available():
         return None
-    # Opt-in (B200_TP_FUSED=1).  Measured after the 2-CTA (cta_group::2) GEMM became the default for plain GEMMs
-    # (profiles/fused_comm_check_n2_r1_v3.json, profiles/bench_ours_n2_tp2_*): the fused kernels still run the 1-CTA tile, so
-    # only GEMM -> reduce-scatter of wo stays ahead of "2-CTA GEMM + NCCL" (0.095 vs 0.109 ms); all-gather -> GEMM and the
-    # all-reduce forms are behind, and a tp = 2 training step is 3 % slower with them (477.6 vs 463.2 ms).  They remain the
-    # numerically verified basis for a 2-CTA fused variant; Hybrid-ZeRO and MoE dispatch / combine (which do win) are
-    # unaffected by this switch.
-    if os.environ.get("B200_TP_FUSED", "0") != "1":
-        logger.info("fused TP linears are opt-in (B200_TP_FUSED=1); using the 2-CTA tcgen05 GEMM + NCCL")
+    # Default on: the collective runs inside the CTA-pair tcgen05 GEMM (B200_TP_FUSED=0 selects 2-CTA GEMM + NCCL, which is
+    # also the numerical oracle of tests/test_fused_comm_gpu.py).
+    if os.environ.get("B200_TP_FUSED", "1") == "0":
+        logger.info("fused TP linears disabled (B200_TP_FUSED=0); using the 2-CTA tcgen05 GEMM + NCCL")
         return None
     key = id(group)
     if key not in _tp_backends:

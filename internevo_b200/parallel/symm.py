@@ -20,6 +20,8 @@ import torch.distributed as dist
 _BARRIER_SLOTS = 1024        # [0, 1024): barrier flags (one slot per peer)
 _AG_BASE = 1024              # [1024, 8192): all-gather chunk flags (local)
 _RS_BASE = 8192              # [8192, ...): reduce-scatter tile flags, `world` blocks of tiles each
+_DONE_BASE = 512             # [512, 512 + world): end-of-kernel completion words of the fused all-reduce GEMM
+AG_FLAG_WORDS = _RS_BASE - _AG_BASE
 RS_FLAG_WORDS = 8 * 8192
 FLAG_WORDS = 8192 + RS_FLAG_WORDS
 
@@ -133,3 +135,7 @@ def ag_flag_table(flags: SymmFlags) -> int:
 
 def rs_flag_table(flags: SymmFlags) -> int:
     return flags.table_ptr(_RS_BASE)
+
+
+def done_flag_table(flags: SymmFlags) -> int:
+    return flags.table_ptr(_DONE_BASE)

@@ -17,6 +17,16 @@ from internevo_b200 import ops
 from internevo_b200.parallel import fused, symm
 
 
+# roofline denominators: sustained cuBLAS bf16 throughput from MEASURED_PEAKS.json when present (fallback: the profiling
+# recipe's 1.4 PFLOP/s) and the recipe's measured 770 GB/s per direction peer copy
+PEAK_FLOPS, LINK_BPS = 1.4e15, 770e9
+try:
+    with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) as _f:
+        PEAK_FLOPS = json.load(_f)["bf16_tflops_sustained"] * 1e12
+except Exception:
+    pass
+
+
 def timed(fn, iters=10, warm=3):
     for _ in range(warm):
         fn()
@@ -92,10 +102,14 @@ def main():
         t_f, t_n = timed(lambda: be.gemm_rs(x, w)), timed(nccl_rs)
         t_fa, t_na = timed(lambda: be.gemm_rs(x, w, all_reduce=True)), timed(nccl_ar)
         t_g = timed(lambda: ops.matmul(x, w))
+        flop_ms = 2.0 * M * N * K / PEAK_FLOPS * 1e3
+        rs_link = M * N * 2 * (world - 1) / world / LINK_BPS * 1e3       # partial blocks sent to their owners
         res[f"gemm_rs_{name}"] = {"rel_err": r, "fused_ms": round(t_f, 4), "gemm+nccl_ms": round(t_n, 4),
-                                  "gemm_only_ms": round(t_g, 4),
-                                  "nvlink_floor_ms": round(M * N * 2 * (world - 1) / world / 770e9 * 1e3, 4)}
-        res[f"gemm_ar_{name}"] = {"rel_err": r2, "fused_ms": round(t_fa, 4), "gemm+nccl_ms": round(t_na, 4)}
+                                  "gemm_only_ms": round(t_g, 4), "roofline_ms": round(max(flop_ms, rs_link), 4),
+                                  "frac_of_roofline": round(max(flop_ms, rs_link) / t_f, 3)}
+        res[f"gemm_ar_{name}"] = {"rel_err": r2, "fused_ms": round(t_fa, 4), "gemm+nccl_ms": round(t_na, 4),
+                                  "roofline_ms": round(max(flop_ms, 2 * rs_link), 4),   # partials out + reduced rows out
+                                  "frac_of_roofline": round(max(flop_ms, 2 * rs_link) / t_fa, 3)}
     # ---- AG -> GEMM (column-parallel with sequence parallel)
     for name, (N, K) in {"wqkv": (6144 // world, h), "w13": (2 * F // world, h)}.items():
         xs = torch.randn(T // world, K, device="cuda", dtype=torch.bfloat16) * 0.1
@@ -117,15 +131,14 @@ def main():
             dist.all_gather_into_tensor(g, xs)
             ops.matmul(g, w)
 
-        sweep = {}
-        for cc in (2, 4, 8, 16):
-            be.comm_ctas = cc
-            sweep[cc] = round(timed(lambda: be.ag_gemm(xs, w)), 4)
-        be.comm_ctas = 8
-        res[f"ag_gemm_{name}"] = {"rel_err": r, "fused_ms": round(timed(lambda: be.ag_gemm(xs, w)), 4),
-                                  "fused_ms_by_copy_ctas": sweep,
+        t_f = timed(lambda: be.ag_gemm(xs, w))
+        flop_ms = 2.0 * T * N * K / PEAK_FLOPS * 1e3
+        link_ms = (T // world) * K * 2 * (world - 1) / LINK_BPS * 1e3     # bytes every GPU must send
+        res[f"ag_gemm_{name}"] = {"rel_err": r, "fused_ms": round(t_f, 4),
                                   "nccl+gemm_ms": round(timed(nccl_ag), 4),
-                                  "gemm_only_ms": round(timed(lambda: ops.matmul(xg, w)), 4)}
+                                  "gemm_only_ms": round(timed(lambda: ops.matmul(xg, w)), 4),
+                                  "roofline_ms": round(max(flop_ms, link_ms), 4),
+                                  "frac_of_roofline": round(max(flop_ms, link_ms) / t_f, 3)}
     # ---- fused ZeRO kernels: reduce-scatter (mean) + sumsq, AdamW + parameter push
     n = 64 * 1024 * 1024
     gbuf = symm.SymmBuffer(n, torch.bfloat16, group)
