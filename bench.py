@@ -335,6 +335,8 @@ def run(a, ours: bool):
                        "l2": "working set >> L2: 15.5 GB of bf16 weights + activations are streamed every step",
                        "fused_comm": bool(cfg.get("fused_comm", False)) if ours else None,
                        "zero_overlap": (bool(getattr(optimizer, "_overlap_sync_grad", False)) if ours else None),
+                       "zero_ranges_reduced_in_backward_vs_step": (list(optimizer.overlap_stats.values()) if ours else None),
+                       "tp_fused": (os.environ.get("B200_TP_FUSED", "1") != "0" and tp > 1) if ours else None,
                        "metric_hook": "none (both arms)"},
             "e2e": {"value": round(e2e_value, 1), "unit": "tokens/s", "h2d_bytes_per_step": batch_bytes(host_batches[0]),
                     "d2h_bytes_per_step": 4 + 16 * (len(optimizer.groups) if ours else 1),

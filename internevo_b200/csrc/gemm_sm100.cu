@@ -53,7 +53,17 @@ struct GemmKernelArgs {
     int group_m;      // raster group height in tile rows
     int tiles_full;   // work items [0, tiles_full) are whole BM x BN tiles
     int tail_split;   // the remaining tiles are split into this many column slices (1, 2 or 4) to fill the last wave
+    // ---- grouped GEMM (MoE experts): `grp_num` problems in ONE launch, their sizes read from DEVICE memory ---------------
+    // grp_off[g] .. grp_off[g + 1] are the rows of group g in the packed activation buffer (multiples of 128, padding rows
+    // zero).  mode 1 (forward / dgrad): rows of A and D, B = weights of group g through its own tensor map b_maps[g];
+    // mode 2 (wgrad): the contraction runs over the group's rows, D = d_ptrs[g].
+    const int* grp_off;
+    int grp_num, grp_mode;
+    const CUtensorMap* b_maps;   // global memory, one map per group (mode 1)
+    void* const* d_ptrs;         // global memory, one output per group (mode 2)
 };
+
+static constexpr int MAX_GROUPS = 64;
 
 
 // Raster: groups of `GROUP_M` tile rows are swept column by column (8 rows: square-ish footprint of one wave of tiles;
@@ -159,11 +169,30 @@ B200_DEVICE void ag_push_pieces(const GemmKernelArgs& args, const CommKernelArgs
     }
 }
 
-template <int BN, bool COMM, int CG = 1>
+// item -> (group, m tile inside the group, n tile) for the grouped forms; s_off / s_start live in shared memory
+template <int CG>
+B200_DEVICE void grp_coords(int item, const GemmKernelArgs& a, const int* s_off, const int* s_start, int& g, int& tm, int& tn) {
+    if (a.grp_mode == 1) {
+        g = 0;
+        while (g + 1 < a.grp_num && item >= s_start[g + 1]) ++g;
+        const int local = item - s_start[g];
+        const int tiles_m_g = (s_off[g + 1] - s_off[g] + BM * CG - 1) / (BM * CG);
+        tm = local % tiles_m_g;   // m fastest: consecutive units share the (large) weight tile through L2
+        tn = local / tiles_m_g;
+    } else {
+        const int per = a.tiles_m * a.tiles_n;
+        g = item / per;
+        tile_coords(item - g * per, a.tiles_m, a.tiles_n, tm, tn, a.group_m);
+    }
+}
+
+template <int BN, bool COMM, int CG = 1, bool GRP = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_bt, const GemmKernelArgs args, const CommKernelArgs comm) {
     static_assert(CG == 1 || BN == 256, "2-CTA tiles: BN = 256");
+    static_assert(!(GRP && COMM), "grouped GEMM has no fused collective");
+    __shared__ int s_off[GRP ? MAX_GROUPS + 1 : 1], s_start[GRP ? MAX_GROUPS + 1 : 1];
     using Cfg = GemmCfg<BN, CG>;
     griddep_launch_dependents();  // PDL (launch.h): the next kernel's CTAs may take over SMs this grid's tail has left
     const int cta_rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
@@ -185,7 +214,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_tiles = args.tiles_m * args.tiles_n;
-    const int num_items = args.tiles_full + (num_tiles - args.tiles_full) * args.tail_split;
+    int num_items = args.tiles_full + (num_tiles - args.tiles_full) * args.tail_split;
     const int num_kb = (args.K + BK - 1) / BK;
 
     if (warp == 0 && lane == 0) {
@@ -203,11 +232,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     if (warp == 1) tmem_alloc<CG>(tmem_base_smem, Cfg::TMEM_COLS);
     griddep_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
+    if constexpr (GRP) {
+        // group table: row offsets (written by the routing kernels earlier in the stream) and first work item of each group
+        if (threadIdx.x == 64) {
+            int acc_items = 0;
+            for (int g = 0; g <= args.grp_num; ++g) {
+                s_off[g] = args.grp_off[g];
+                s_start[g] = acc_items;
+                if (g < args.grp_num && args.grp_mode == 1)
+                    acc_items += (args.grp_off[g + 1] - args.grp_off[g] + BM * CG - 1) / (BM * CG) * args.tiles_n;
+            }
+        }
+    }
     tc_fence_before();
     if constexpr (CG == 2) cluster_sync();  // the peer's barriers are initialised before anything signals them
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
+    if constexpr (GRP) num_items = args.grp_mode == 1 ? s_start[args.grp_num] : args.grp_num * num_tiles;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -216,8 +258,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             uint32_t phase = 0;
             uint64_t ready = 0;  // all-gather: blocks (of the first 64) whose pieces are known to have landed
             for (int tile = unit; tile < num_items; tile += grid_ctas) {
-                int tm, tn, n_off, width;
-                item_coords<BN>(tile, args, tm, tn, n_off, width);
+                int tm, tn, n_off, width, g = 0;
+                if constexpr (GRP) { grp_coords<CG>(tile, args, s_off, s_start, g, tm, tn); n_off = 0; width = BN; }
+                else item_coords<BN>(tile, args, tm, tn, n_off, width);
                 bool own_rows = false;
                 if constexpr (COMM) {
                     tm = comm_remap_m(tm, args.tiles_m, comm);
@@ -239,20 +282,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     }
                 }
                 if (lane != 0) continue;   // lane 0 issues every TMA load of the tile
-                const int m0 = (tm * CG + cta_rank) * BM, n0 = tn * BN + n_off + cta_rank * (width / CG);
+                int m0 = (tm * CG + cta_rank) * BM;
+                const int n0 = tn * BN + n_off + cta_rank * (width / CG);
                 const int m0_own = m0 - comm.rank * comm.m_local;
+                const CUtensorMap* map_b = &tmap_b;
+                int kb_n = num_kb, k_base = 0;
+                if constexpr (GRP) {
+                    if (args.grp_mode == 1) { m0 += s_off[g]; map_b = args.b_maps + g; }
+                    else { k_base = s_off[g]; kb_n = (s_off[g + 1] - s_off[g]) / BK; }
+                }
                 // 2-CTA: every CTA loads its rows of A and its half of B, all bytes are counted on the leader's barrier
                 auto ld = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
                     if constexpr (CG == 2) tma_load_2d_2sm(dst, map, bar, c0, c1);
                     else tma_load_2d(dst, map, bar, c0, c1);
                 };
                 const int nb64 = width / CG / 64;  // B arrives in 64-row (K-major) or 64-column (MN-major) boxes
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = 0; kb < kb_n; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES * CG + width * (BK * 2));
                     uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
                     uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
-                    const int k0 = kb * BK;
+                    const int k0 = k_base + kb * BK;
                     if (COMM && own_rows) {  // the local shard is read in place (tmap_bt doubles as its map)
                         ld(sa, &tmap_bt, &full_bar[stage], k0, m0_own);
                     } else if (!args.a_mn) {
@@ -264,11 +314,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     }
                     if (width == BN) {
                         if (!args.b_mn) {
-                            ld(sb, &tmap_b, &full_bar[stage], k0, n0);
+                            ld(sb, map_b, &full_bar[stage], k0, n0);
                         } else {
 #pragma unroll
                             for (int j = 0; j < BN / CG / 64; ++j)
-                                ld(sb + j * (BK * 128), &tmap_b, &full_bar[stage], n0 + j * 64, k0);
+                                ld(sb + j * (BK * 128), map_b, &full_bar[stage], n0 + j * 64, k0);
                         }
                     } else if (!args.b_mn) {  // tail slice: 64-row boxes of the K-major operand
                         for (int j = 0; j < nb64; ++j)
@@ -280,6 +330,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
+            __syncwarp();   // lanes 1..31 leave the loop early: reconverge before the warp-aligned teardown below
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -301,7 +352,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                int kb_n = num_kb;
+                if constexpr (GRP) {
+                    if (args.grp_mode == 2) {
+                        const int g = tile / num_tiles;
+                        kb_n = (s_off[g + 1] - s_off[g]) / BK;
+                    }
+                }
+                for (int kb = 0; kb < kb_n; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem_a + stage * Cfg::A_BYTES);
@@ -335,11 +393,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (comm.mode == GEMM_COMM_ALL_GATHER) ag_push_pieces(args, comm, static_cast<int>(threadIdx.x) - 64);
         }
         for (int tile = unit; tile < num_items; tile += grid_ctas) {
-            int tm, tn, n_off, width;
-            item_coords<BN>(tile, args, tm, tn, n_off, width);
+            int tm, tn, n_off, width, g = 0;
+            if constexpr (GRP) { grp_coords<CG>(tile, args, s_off, s_start, g, tm, tn); n_off = 0; width = BN; }
+            else item_coords<BN>(tile, args, tm, tn, n_off, width);
             if constexpr (COMM) tm = comm_remap_m(tm, args.tiles_m, comm);
             const int blk = tm * CG + cta_rank;   // 128-row block of this CTA
-            const int row = blk * BM + q * 32 + lane;
+            int row = blk * BM + q * 32 + lane;
+            int row_end = args.M;
+            void* d_base = args.D;
+            bool empty_k = false;
+            if constexpr (GRP) {
+                if (args.grp_mode == 1) { row += s_off[g]; row_end = s_off[g + 1]; }   // rows past the group belong to the next one
+                else { d_base = args.d_ptrs[g]; empty_k = s_off[g + 1] == s_off[g]; }   // no rows: the accumulator was never written
+            }
             const int n0 = tn * BN + n_off;
             const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
             if constexpr (COMM) {
@@ -461,10 +527,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 tmem_ld_32x32b_x32(taddr + c, r);
                 tmem_ld_wait();
                 const int col = n0 + c;
-                if (row < args.M && col < args.N) {
+                if (row < row_end && col < args.N) {
                     float v[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                    for (int i = 0; i < 32; ++i) v[i] = empty_k ? 0.f : __uint_as_float(r[i]);
                     const int ncols = min(32, args.N - col);  // multiple of 8 (host asserts N % 8 == 0)
                     if (args.bias != nullptr) {
 #pragma unroll
@@ -479,7 +545,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         }
                     }
                     if (out_f32) {
-                        float* d = reinterpret_cast<float*>(args.D) + static_cast<int64_t>(row) * args.ldd + col;
+                        float* d = reinterpret_cast<float*>(d_base) + static_cast<int64_t>(row) * args.ldd + col;
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
                             if (i < ncols) {
@@ -493,7 +559,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         }
                     } else {
                         __nv_bfloat16* d =
-                            reinterpret_cast<__nv_bfloat16*>(args.D) + static_cast<int64_t>(row) * args.ldd + col;
+                            reinterpret_cast<__nv_bfloat16*>(d_base) + static_cast<int64_t>(row) * args.ldd + col;
                         if (!no_store_d) {
 #pragma unroll
                             for (int i = 0; i < 32; i += 8) {

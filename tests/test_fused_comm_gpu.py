@@ -29,7 +29,7 @@ def _train(rank, world, fused, mode):
     cfg = tiny_config(tp=2, mode=mode, dtype="torch.bfloat16", num_layers=2, hidden=512, heads=4, kv_heads=2, seq_len=512,
                       micro_bsz=1, vocab=1024, micro_num=2)
     cfg["fused_comm"] = fused
-    os.environ["B200_TP_FUSED"] = "1" if fused else "0"     # the fused TP linears are opt-in
+    os.environ["B200_TP_FUSED"] = "1" if fused else "0"     # default on; "0" = 2-CTA GEMM + NCCL (the oracle)
     trainer, opt, model, _ = build_trainer(cfg)
     from internevo_b200.parallel import linear
 
