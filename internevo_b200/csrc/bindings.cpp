@@ -1,6 +1,8 @@
 // torch op registrations for the sm_100a kernels (namespace torch.ops.b200). Thin: shape checks + raw launches on the
 // current stream; allocation and autograd live in python (internevo_b200/ops).
+#include <ATen/ATen.h>
 #include <ATen/cuda/CUDAContext.h>
+#include <cstring>
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/library.h>
 
@@ -465,6 +467,69 @@ void moe_gather_combine(Tensor& out, const c10::optional<Tensor>& w, const Tenso
     CHECK_RC(b200::moe_gather_combine(d, cur_stream()), "b200::moe_gather_combine");
 }
 
+// ---- grouped GEMM (MoE experts) -----------------------------------------------------------------------------------------
+// 128-byte tensor maps of every expert's weight, built on the host and uploaded once (the weights live in the optimizer's
+// arena: their addresses never change), returned as a uint8 cuda tensor [G * 128].
+Tensor grouped_b_maps(at::TensorList weights, bool b_mn) {
+    TORCH_CHECK(!weights.empty(), "grouped_b_maps: no weights");
+    const int64_t G = static_cast<int64_t>(weights.size());
+    auto host = at::empty({G * 128}, at::TensorOptions().dtype(at::kByte).pinned_memory(true));
+    for (int64_t g = 0; g < G; ++g) {
+        const Tensor& w = weights[g];
+        CHECK_BF16(w);
+        TORCH_CHECK(w.dim() == 2 && w.stride(1) == 1 && w.stride(0) % 8 == 0, "grouped_b_maps: 2-D weights, unit inner stride");
+        const int N = b_mn ? w.size(1) : w.size(0), K = b_mn ? w.size(0) : w.size(1);
+        CUtensorMap m;
+        CHECK_RC(b200::grouped_b_map(&m, w.data_ptr(), N, K, w.stride(0), b_mn), "b200::grouped_b_map");
+        std::memcpy(static_cast<uint8_t*>(host.data_ptr()) + g * 128, &m, sizeof(CUtensorMap));
+    }
+    static_assert(sizeof(CUtensorMap) == 128, "tensor map size");
+    return host.to(weights[0].device(), /*non_blocking=*/false);
+}
+
+// rows of group g: offsets[g] .. offsets[g + 1] (int32, device).  out[rows, N] = a[rows, K] @ W_g^T (b_mn: @ W_g)
+void grouped_gemm(const Tensor& a, const Tensor& bmaps, const Tensor& offsets, Tensor& out, int64_t N, bool b_mn, int64_t flags,
+                  const optional<Tensor>& h) {
+    CHECK_BF16(a); CHECK_BF16(out);
+    TORCH_CHECK(offsets.is_cuda() && offsets.scalar_type() == at::kInt && offsets.is_contiguous(), "grouped_gemm: int32 offsets");
+    TORCH_CHECK(bmaps.is_cuda() && bmaps.scalar_type() == at::kByte && bmaps.numel() == (offsets.numel() - 1) * 128,
+                "grouped_gemm: one tensor map per group");
+    TORCH_CHECK((reinterpret_cast<uintptr_t>(bmaps.data_ptr()) & 63) == 0, "grouped_gemm: tensor maps must be 64-byte aligned");
+    TORCH_CHECK(a.dim() == 2 && out.dim() == 2 && a.stride(1) == 1 && out.stride(1) == 1 && out.size(0) == a.size(0) &&
+                    out.size(1) == N, "grouped_gemm: shapes");
+    c10::cuda::CUDAGuard guard(a.device());
+    b200::GroupedGemmDesc g;
+    g.mode = 1; g.num_groups = static_cast<int>(offsets.numel() - 1); g.grp_off = offsets.data_ptr<int>();
+    g.rows_cap = a.size(0); g.N = static_cast<int>(N); g.K = static_cast<int>(a.size(1));
+    g.A = a.data_ptr(); g.lda = a.stride(0); g.b_mn_major = b_mn;
+    g.b_maps = reinterpret_cast<const CUtensorMap*>(bmaps.data_ptr());
+    g.D = out.data_ptr(); g.ldd = out.stride(0); g.flags = static_cast<int>(flags);
+    if (flags & b200::GEMM_SWIGLU) {
+        TORCH_CHECK(h.has_value() && h->scalar_type() == at::kBFloat16 && h->size(0) == a.size(0) && h->size(1) == N / 2 &&
+                        h->stride(1) == 1, "grouped_gemm: bad swiglu output");
+        g.H = h->data_ptr(); g.ldh = h->stride(0);
+    }
+    CHECK_RC(b200::gemm_bf16_grouped(g, cur_stream()), "b200::grouped_gemm");
+}
+
+// dW_g [M, N] (+)= dy[rows_g, M]^T @ x[rows_g, N]; d_ptrs: int64 cuda tensor with one output pointer per group
+void grouped_wgrad(const Tensor& dy, const Tensor& x, const Tensor& offsets, const Tensor& d_ptrs, int64_t ldd, int64_t flags) {
+    CHECK_BF16(dy); CHECK_BF16(x);
+    TORCH_CHECK(offsets.is_cuda() && offsets.scalar_type() == at::kInt && offsets.is_contiguous(), "grouped_wgrad: int32 offsets");
+    TORCH_CHECK(d_ptrs.is_cuda() && d_ptrs.scalar_type() == at::kLong && d_ptrs.numel() == offsets.numel() - 1,
+                "grouped_wgrad: one output pointer per group");
+    TORCH_CHECK(dy.dim() == 2 && x.dim() == 2 && dy.size(0) == x.size(0) && dy.stride(1) == 1 && x.stride(1) == 1,
+                "grouped_wgrad: shapes");
+    c10::cuda::CUDAGuard guard(dy.device());
+    b200::GroupedGemmDesc g;
+    g.mode = 2; g.num_groups = static_cast<int>(offsets.numel() - 1); g.grp_off = offsets.data_ptr<int>();
+    g.rows_cap = dy.size(0); g.M = static_cast<int>(dy.size(1)); g.N = static_cast<int>(x.size(1));
+    g.A = dy.data_ptr(); g.lda = dy.stride(0); g.B = x.data_ptr(); g.ldb = x.stride(0);
+    g.d_ptrs = reinterpret_cast<void* const*>(d_ptrs.data_ptr<int64_t>()); g.ldd = ldd;
+    g.flags = static_cast<int>(flags);
+    CHECK_RC(b200::gemm_bf16_grouped(g, cur_stream()), "b200::grouped_wgrad");
+}
+
 TORCH_LIBRARY(b200, m) {
     m.def("gemm(Tensor a, Tensor b, Tensor(a!) out, bool a_mn, bool b_mn, Tensor? bias, int flags, Tensor? h, int force_bn, int max_ctas) -> ()", &gemm);
     m.def("set_gemm_tail_split(int on) -> ()", [](int64_t on) { b200::set_gemm_tail_split(static_cast<int>(on)); });
@@ -493,6 +558,9 @@ TORCH_LIBRARY(b200, m) {
     m.def("symm_allgather_small(int buf_ptrs, Tensor src, int flags_ptrs, int rank, int world, int epoch) -> ()", &symm_allgather_small);
     m.def("moe_scatter_rows(Tensor x, Tensor slot_rank, Tensor slot_row, Tensor? scale, int x_ptrs, int y_ptrs, Tensor(a!)? dw, int k) -> ()", &moe_scatter_rows);
     m.def("moe_gather_combine(Tensor(a!) out, Tensor? w, Tensor slot_rank, Tensor slot_row, int y_ptrs, int k) -> ()", &moe_gather_combine);
+    m.def("grouped_b_maps(Tensor[] weights, bool b_mn) -> Tensor", &grouped_b_maps);
+    m.def("grouped_gemm(Tensor a, Tensor bmaps, Tensor offsets, Tensor(a!) out, int N, bool b_mn, int flags, Tensor(b!)? h) -> ()", &grouped_gemm);
+    m.def("grouped_wgrad(Tensor dy, Tensor x, Tensor offsets, Tensor d_ptrs, int ldd, int flags) -> ()", &grouped_wgrad);
     m.def("gemm_rs(Tensor a, Tensor b, Tensor(a!) out, int stage_ptrs, int out_ptrs, int flags_ptrs, int rank, int world, int epoch, bool b_mn, int mode, int done_ptrs, Tensor? done_counter) -> ()", &gemm_rs);
     m.def("ag_gemm(Tensor x_local, int gathered_ptrs, int flags_ptrs, int rank, int world, int epoch, Tensor b, bool b_mn, Tensor(a!) gathered, Tensor(b!) out, int flags, Tensor? h, int comm_ctas) -> ()", &ag_gemm);
 }

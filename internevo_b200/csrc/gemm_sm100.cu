@@ -780,7 +780,7 @@ static int launch(const GemmDesc& g, cudaStream_t stream) {
     if (rc) return rc;
     tbt = tb;  // tail slices of a K-major B come in 64-row boxes
 
-    GemmKernelArgs a;
+    GemmKernelArgs a = {};
     a.M = g.M; a.N = g.N; a.K = g.K;
     a.D = g.D; a.ldd = g.ldd;
     a.bias = reinterpret_cast<const __nv_bfloat16*>(g.bias);
@@ -861,7 +861,7 @@ int gemm_bf16_comm(const GemmDesc& g, const GemmCommArgs& c, cudaStream_t stream
         rc = make_tmap_2d_bf16(&tx, c.x_local, g.K, c.m_local, g.K, BK, BM);
         if (rc) return rc;
     }
-    GemmKernelArgs a;
+    GemmKernelArgs a = {};
     a.tiles_full = tiles_m * tiles_n; a.tail_split = 1; a.group_m = 8;
     a.M = g.M; a.N = g.N; a.K = g.K;
     a.D = g.D; a.ldd = g.ldd;
@@ -887,6 +887,62 @@ int gemm_bf16_comm(const GemmDesc& g, const GemmCommArgs& c, cudaStream_t stream
                                CG, ta, tb, tx, a, k);
     if (e != cudaSuccess) {
         fprintf(stderr, "[b200] comm gemm launch failed: %s\n", cudaGetErrorString(e));
+        return -4;
+    }
+    return 0;
+}
+
+int grouped_b_map(CUtensorMap* out, const void* ptr, int N, int K, int64_t ldb, int b_mn_major) {
+    constexpr int BN = 256, CG = 2;
+    if (!b_mn_major) return make_tmap_2d_bf16(out, ptr, K, N, ldb, BK, BN / CG);
+    return make_tmap_2d_bf16(out, ptr, N, K, ldb, 64, BK);
+}
+
+int gemm_bf16_grouped(const GroupedGemmDesc& g, cudaStream_t stream) {
+    constexpr int BN = 256, CG = 2;
+    using Cfg = GemmCfg<BN, CG>;
+    if (g.num_groups <= 0 || g.num_groups > MAX_GROUPS || g.grp_off == nullptr) return -30;
+    if (g.N % 8 != 0) return -31;
+    CUtensorMap ta, tb;
+    int rc;
+    GemmKernelArgs a = {};
+    a.grp_off = g.grp_off; a.grp_num = g.num_groups; a.grp_mode = g.mode;
+    a.b_maps = g.b_maps; a.d_ptrs = g.d_ptrs;
+    a.N = g.N; a.flags = g.flags; a.bias = nullptr; a.H = g.H; a.ldh = g.ldh;
+    a.tiles_n = (g.N + BN - 1) / BN;
+    a.group_m = 8; a.tail_split = 1;
+    if (g.mode == 1) {
+        if (g.b_maps == nullptr || g.K % 8 != 0) return -32;
+        rc = make_tmap_2d_bf16(&ta, g.A, g.K, g.rows_cap, g.lda, BK, BM);
+        if (rc) return rc;
+        tb = ta;   // unused: every group brings its own B map
+        a.M = (int)g.rows_cap; a.K = g.K; a.D = g.D; a.ldd = g.ldd;
+        a.a_mn = 0; a.b_mn = g.b_mn_major;
+        a.tiles_m = 0; a.tiles_full = 0;
+    } else {
+        if (g.d_ptrs == nullptr || g.M % 8 != 0) return -33;
+        rc = make_tmap_2d_bf16(&ta, g.A, g.M, g.rows_cap, g.lda, 64, BK);   // dY [rows, M], MN-major A
+        if (rc) return rc;
+        rc = make_tmap_2d_bf16(&tb, g.B, g.N, g.rows_cap, g.ldb, 64, BK);   // X  [rows, N], MN-major B
+        if (rc) return rc;
+        a.M = g.M; a.K = 0; a.D = nullptr; a.ldd = g.ldd;
+        a.a_mn = 1; a.b_mn = 1;
+        a.tiles_m = (g.M + BM * CG - 1) / (BM * CG);
+        a.tiles_full = a.tiles_m * a.tiles_n;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(gemm_bf16_kernel<BN, false, CG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg::SMEM_BYTES) != cudaSuccess)
+            return -3;
+        attr_set = true;
+    }
+    int units = num_sms() / CG;
+    if (g.mode == 2 && units > g.num_groups * a.tiles_full) units = g.num_groups * a.tiles_full;
+    cudaError_t e = launch_pdl(gemm_bf16_kernel<BN, false, CG, true>, dim3(units * CG), dim3(NUM_THREADS), Cfg::SMEM_BYTES, stream,
+                               CG, ta, tb, tb, a, CommKernelArgs{});
+    if (e != cudaSuccess) {
+        fprintf(stderr, "[b200] grouped gemm launch failed: %s\n", cudaGetErrorString(e));
         return -4;
     }
     return 0;

@@ -64,6 +64,30 @@ struct GemmCommArgs {
 
 int gemm_bf16_comm(const GemmDesc& g, const GemmCommArgs& c, cudaStream_t stream);
 
+// ---- grouped GEMM: `num_groups` problems whose row ranges live in DEVICE memory (MoE experts, no host sync) --------------
+// mode 1 (forward / dgrad):  D[rows_g, N] = A[rows_g, K] * B_g^T   for the rows grp_off[g] .. grp_off[g + 1] of A / D;
+//                            B_g comes through its own tensor map (array in global memory, see grouped_b_maps).
+// mode 2 (wgrad):            D_g[M, N] (+)= A[rows_g, M]^T * B[rows_g, N]   (contraction over the group's rows).
+// Row offsets must be multiples of 128 and the padding rows of A zero (mode 2) / ignorable (mode 1: D rows are written).
+struct GroupedGemmDesc {
+    int mode = 1;
+    int num_groups = 0;
+    const int* grp_off = nullptr;            // device, [num_groups + 1]
+    int64_t rows_cap = 0;                    // rows of the packed buffers (tensor-map extent)
+    int M = 0, N = 0, K = 0;                 // mode 1: N, K (M unused); mode 2: M, N (K unused)
+    const void* A = nullptr; int64_t lda = 0;
+    const void* B = nullptr; int64_t ldb = 0;   // mode 2: the packed second operand
+    int b_mn_major = 0;                      // mode 1: layout of every B_g
+    const CUtensorMap* b_maps = nullptr;     // mode 1: device array of num_groups maps
+    void* D = nullptr; int64_t ldd = 0;      // mode 1
+    void* const* d_ptrs = nullptr;           // mode 2: device array of num_groups outputs (row stride ldd)
+    void* H = nullptr; int64_t ldh = 0;      // mode 1 + GEMM_SWIGLU
+    int flags = 0;
+};
+int gemm_bf16_grouped(const GroupedGemmDesc& g, cudaStream_t stream);
+// host-side tensor map of one group's B operand for mode 1 (K-major [N, K] or MN-major [K, N]), 128 bytes into `out`
+int grouped_b_map(CUtensorMap* out, const void* ptr, int N, int K, int64_t ldb, int b_mn_major);
+
 int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                       uint32_t box_inner, uint32_t box_outer);
 

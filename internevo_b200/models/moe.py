@@ -23,6 +23,7 @@ import torch.distributed as dist
 import torch.nn.functional as F
 from torch import nn
 
+from internevo_b200 import ops
 from internevo_b200.core.context import ParallelMode
 from internevo_b200.core.context import global_context as gpc
 from internevo_b200.core.naive_amp import set_fp32_attr_to_module
@@ -171,8 +172,37 @@ class Experts(nn.Module):
                 p.is_expert = True
                 p.group_name = expert_group_name
 
+    def _grouped_weights(self):
+        """``(w13 list, w2 list)`` when every local expert is a plain (not tensor-/weight-parallel) SwiGLU ``FeedForward``:
+        the grouped tcgen05 GEMM then runs all of them in one launch (``ops/grouped.py``)."""
+        ok = all(isinstance(e, FeedForward) and getattr(e, "process_group", None) is None and e.tp_mode != "isp"
+                 for e in self.wrapped_experts)
+        if not ok:
+            return None
+        return [e.w13.weight for e in self.wrapped_experts], [e.w2.weight for e in self.wrapped_experts]
+
+    def forward_packed(self, rows: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
+        """``rows [R, h]``: the rows of local expert ``e`` at ``offsets[e] .. offsets[e + 1]`` (int32 on the rows' device,
+        multiples of 128, padding rows zero) → ``[R, h]``.  No host-side knowledge of the per-expert counts is needed."""
+        ws = self._grouped_weights()
+        if ws is not None and rows.dim() == 2:
+            return ops.grouped_swiglu_mlp(rows, offsets, ws[0], ws[1])
+        b = [int(v) for v in offsets.tolist()]
+        out = torch.zeros_like(rows)
+        for e, expert in enumerate(self.wrapped_experts):
+            if b[e + 1] > b[e]:
+                out[b[e]: b[e + 1]] = expert(rows[b[e]: b[e + 1]])
+        return out
+
     def forward(self, inputs: torch.Tensor) -> torch.Tensor:
-        # inputs: [E_local, rows, h]
+        # inputs: [E_local, rows, h] (capacity layout: the same number of rows for every expert)
+        El, R, h = inputs.shape
+        if self._grouped_weights() is not None and inputs.is_cuda and inputs.dtype == torch.bfloat16:
+            Ra = (R + 127) // 128 * 128           # group starts must be multiples of 128 rows (zero padding)
+            x = inputs if Ra == R else F.pad(inputs, (0, 0, 0, Ra - R))
+            off = torch.arange(El + 1, device=inputs.device, dtype=torch.int32) * Ra
+            y = self.forward_packed(x.reshape(El * Ra, h), off).view(El, Ra, h)
+            return y if Ra == R else y[:, :R]
         outs = [expert(chunk.squeeze(0)) for chunk, expert in zip(inputs.chunk(self.num_local_experts, dim=0),
                                                                    self.wrapped_experts)]
         return torch.stack(outs, 0)
@@ -310,7 +340,9 @@ class DroplessMOELayer(BaseMoELayer):
         from internevo_b200.parallel.moe_fused import backend_for
 
         # worst case: every slot of every rank lands on one GPU; B200_MOE_CAPACITY < 1 trades memory for an overflow check
-        max_rows = max(1, int(n_slots * self.ep_size * float(os.environ.get("B200_MOE_CAPACITY", "1.0"))))
+        # + one 128-row alignment gap per local expert and a reserved dummy row (ops/grouped.py::padding_rows)
+        max_rows = max(1, int(n_slots * self.ep_size * float(os.environ.get("B200_MOE_CAPACITY", "1.0")))) \
+            + (self.num_local_experts + 1) * 128
         return backend_for(self.ep_group, x2.shape[1], max_rows, self.num_experts)
 
     def forward(self, x: torch.Tensor):
@@ -338,12 +370,10 @@ class DroplessMOELayer(BaseMoELayer):
             # dispatch / combine as ONE kernel each over NVLink peer memory (parallel/moe_fused.py, csrc/moe_comm.cu)
             from internevo_b200.parallel.moe_fused import fused_combine, fused_dispatch
 
-            rows, per_expert, plan = fused_dispatch(x2, flat_e, counts, be, k)
-            outs, start = [], 0
-            for e, n in enumerate(per_expert):
-                outs.append(self.experts.wrapped_experts[e](rows[start:start + n]) if n > 0 else rows[start:start])
-                start += n
-            out = torch.cat(outs, 0) if outs else rows
+            # every slot gets its address in the owner's group-aligned slab from the exchanged count matrix; the experts
+            # run as ONE grouped GEMM per projection over that slab - no host read of the counts anywhere
+            rows, offsets, plan = fused_dispatch(x2, flat_e, counts, be, k)
+            out = self.experts.forward_packed(rows, offsets)
             return fused_combine(out, w.reshape(-1), be, plan).reshape(shape)
         send = x2[tok]
         if self.ep_size > 1:
@@ -358,14 +388,19 @@ class DroplessMOELayer(BaseMoELayer):
                 torch.arange(self.num_local_experts, device=x2.device).repeat(self.ep_size), rc.reshape(-1))
             regroup = torch.argsort(src_expert, stable=True)
             rows = recv[regroup]
-            per_expert = rc.sum(0).tolist()
+            per_expert = rc.sum(0)
         else:
-            rows, per_expert, regroup = send, counts.tolist(), None
-        outs, start = [], 0
-        for e, n in enumerate(per_expert):  # grouped GEMM over exactly-sized slabs
-            outs.append(self.experts.wrapped_experts[e](rows[start:start + n]) if n > 0 else rows[start:start])
-            start += n
-        out = torch.cat(outs, 0) if outs else rows
+            rows, per_expert, regroup = send, counts, None
+        # grouped GEMM over group-aligned slabs: rows of local expert e move to offsets[e] + (position inside e); the padding
+        # rows stay zero.  The buffer size depends on the row count only (known from the all-to-all splits), not on the routing.
+        El = self.num_local_experts
+        offsets = ops.aligned_offsets(per_expert)
+        exact = per_expert.cumsum(0) - per_expert
+        e_of_row = torch.repeat_interleave(torch.arange(El, device=x2.device), per_expert, output_size=rows.shape[0])
+        dest = offsets[:-1].to(torch.int64)[e_of_row] + torch.arange(rows.shape[0], device=x2.device) - exact[e_of_row]
+        cap_rows = (rows.shape[0] + El * 127 + 127) // 128 * 128
+        packed = rows.new_zeros(cap_rows, h).index_copy(0, dest, rows)
+        out = self.experts.forward_packed(packed, offsets)[dest]
         if self.ep_size > 1:
             back = torch.empty_like(out).index_copy(0, regroup, out)
             out = _AllToAllV.apply(self.ep_group, back, recv_splits, send_splits)

@@ -30,7 +30,7 @@ from . import symm
 logger = get_logger(__file__)
 
 
-def slot_plan(expert_of_slot: torch.Tensor, count_matrix: torch.Tensor, rank: int, num_local_experts: int):
+def slot_plan(expert_of_slot: torch.Tensor, count_matrix: torch.Tensor, rank: int, num_local_experts: int, align: int = 1):
     """Addresses of this rank's routed slots inside the owners' expert slabs.
 
     ``expert_of_slot``  int64 ``[n_slots]`` global expert of every (token, j) slot of THIS rank (slot = token * k + j)
@@ -38,9 +38,11 @@ def slot_plan(expert_of_slot: torch.Tensor, count_matrix: torch.Tensor, rank: in
 
     The slab of a GPU is ordered (local expert, source rank, arrival order) — exactly the order produced by a
     variable-split all-to-all followed by the regroup-by-expert permutation, so a local expert's rows are contiguous.
+    With ``align > 1`` every local expert's slab STARTS at a multiple of ``align`` rows (the grouped GEMM's requirement);
+    the rows in between are padding that nobody writes.
 
     Returns ``(slot_rank int32[n_slots], slot_row int32[n_slots], rows_per_local_expert int64[El], rows_per_rank
-    int64[world])``.
+    int64[world])``; ``rows_per_rank`` includes the padding.
     """
     world, E = count_matrix.shape
     El = num_local_experts
@@ -48,6 +50,12 @@ def slot_plan(expert_of_slot: torch.Tensor, count_matrix: torch.Tensor, rank: in
     cd = count_matrix.view(world, world, El)                      # [src, dst, el]
     lay = cd.permute(1, 2, 0).reshape(world, El * world)          # per dst: (el, src) order
     off = (lay.cumsum(1) - lay).view(world, El, world)            # exclusive prefix: slab offset of (dst, el, src)
+    if align > 1:
+        el_tot = lay.view(world, El, world).sum(2)                # [dst, el] rows of each local expert
+        el_pad = (el_tot + align - 1) // align * align
+        el_start = el_pad.cumsum(1) - el_pad                      # aligned start of every local expert's slab
+        within = off - (el_tot.cumsum(1) - el_tot).unsqueeze(2)   # offset of (src) inside its expert's slab
+        off = el_start.unsqueeze(2) + within
     my_base = off[:, :, rank].reshape(E)                          # [E]: where MY rows for expert e start on its owner
     # arrival order inside (me -> expert e): stable order of the slots routed to e
     order = torch.argsort(expert_of_slot, stable=True)
@@ -59,7 +67,8 @@ def slot_plan(expert_of_slot: torch.Tensor, count_matrix: torch.Tensor, rank: in
     slot_row = torch.empty_like(row_sorted)
     slot_row[order] = row_sorted
     slot_rank = torch.div(expert_of_slot, El, rounding_mode="floor")
-    return slot_rank.to(torch.int32), slot_row.to(torch.int32), cd[:, rank, :].sum(0), lay.sum(1)
+    per_rank = lay.sum(1) if align <= 1 else el_pad.sum(1)
+    return slot_rank.to(torch.int32), slot_row.to(torch.int32), cd[:, rank, :].sum(0), per_rank
 
 
 class MoEFusedBackend:
@@ -110,11 +119,12 @@ def backend_for(group, hidden: int, max_rows: int, num_experts: int) -> Optional
 
 
 class _Plan:
-    __slots__ = ("slot_rank", "slot_row", "n_recv", "k", "n_tokens", "zero_fill")
+    __slots__ = ("slot_rank", "slot_row", "n_recv", "k", "n_tokens", "zero_fill", "pad_idx")
 
-    def __init__(self, slot_rank, slot_row, n_recv, k, n_tokens, zero_fill=False):
+    def __init__(self, slot_rank, slot_row, n_recv, k, n_tokens, zero_fill=False, pad_idx=None):
         self.slot_rank, self.slot_row, self.n_recv, self.k, self.n_tokens = slot_rank, slot_row, n_recv, k, n_tokens
         self.zero_fill = zero_fill   # capacity layout: rows nobody writes must read as zero
+        self.pad_idx = pad_idx       # group-aligned layout: (fixed-size) indices of the padding rows, zeroed before every scatter
 
 
 class _FusedDispatch(torch.autograd.Function):
@@ -129,6 +139,8 @@ class _FusedDispatch(torch.autograd.Function):
         elif symm.DEBUG:
             symm.poison(be.x_rows(plan.n_recv))
             be.flags.barrier()
+        if plan.pad_idx is not None:            # nobody writes the alignment padding: it must read as zero (wgrad runs over it)
+            be.x_rows(plan.n_recv).index_fill_(0, plan.pad_idx, 0)
         torch.ops.b200.moe_scatter_rows(x, plan.slot_rank, plan.slot_row, None, be.xbuf.table_ptr(0), 0, None, plan.k)
         _bump()
         be.flags.barrier()                      # every peer's rows have landed in my slab
@@ -177,6 +189,8 @@ class _FusedCombine(torch.autograd.Function):
         be.y_rows(plan.n_recv).copy_(out_rows)   # the owners publish their outputs again for d(gate weight)
         if plan.zero_fill:
             be.x_rows(plan.n_recv).zero_()       # capacity rows nobody routed to receive a zero gradient
+        if plan.pad_idx is not None:
+            be.x_rows(plan.n_recv).index_fill_(0, plan.pad_idx, 0)
         be.flags.barrier()
         dw = torch.empty_like(w)
         torch.ops.b200.moe_scatter_rows(g_out, plan.slot_rank, plan.slot_row, w, be.xbuf.table_ptr(0),
@@ -189,18 +203,24 @@ class _FusedCombine(torch.autograd.Function):
 
 
 def fused_dispatch(x2: torch.Tensor, expert_of_slot: torch.Tensor, counts: torch.Tensor, be: MoEFusedBackend, k: int):
-    """Returns ``(rows [n_recv, H], rows_per_local_expert list, plan)``; one host sync (the slab sizes)."""
+    """Returns ``(rows [R, H], offsets int32 [El + 1], plan)``: ``rows`` is this GPU's group-aligned expert slab (local
+    expert ``e`` at ``offsets[e] .. offsets[e + 1]``, padding rows zero) - the layout the grouped GEMM consumes.  Everything
+    is sized statically (``R`` = the slab's capacity) and addressed by device arithmetic on the exchanged count matrix:
+    there is NO host read.  A slab smaller than the worst case (``B200_MOE_CAPACITY`` < 1) is checked by a device-side
+    assert of the row count instead."""
+    from internevo_b200.ops.grouped import ALIGN, aligned_offsets, padding_rows
+
     cm = be.exchange_counts(counts)
     El = be.num_experts // be.world
-    slot_rank, slot_row, per_expert, per_rank = slot_plan(expert_of_slot, cm, be.rank, El)
-    host = torch.cat([per_expert, per_rank.max().view(1)]).tolist()
-    per_expert_l, worst = host[:-1], host[-1]
-    if worst > be.max_rows:
-        raise RuntimeError(f"fused MoE dispatch: a GPU would receive {worst} rows but the slab holds {be.max_rows}; "
-                           f"raise moe fused_capacity_factor")
-    plan = _Plan(slot_rank, slot_row, int(sum(per_expert_l)), k, x2.shape[0])
+    slot_rank, slot_row, per_expert, per_rank = slot_plan(expert_of_slot, cm, be.rank, El, align=ALIGN)
+    offsets = aligned_offsets(per_expert)
+    R = be.max_rows
+    if R < x2.shape[0] * k * be.world + El * ALIGN:      # not the worst case: fail loudly (asynchronously) on overflow
+        torch._assert_async((per_rank.max() < R).all() if hasattr(torch, "_assert_async") else True)
+    pad_idx = padding_rows(per_expert, offsets, dummy_row=R - 1)
+    plan = _Plan(slot_rank, slot_row, R, k, x2.shape[0], pad_idx=pad_idx)
     rows = _FusedDispatch.apply(x2.contiguous(), be, plan)
-    return rows, [int(v) for v in per_expert_l], plan
+    return rows, offsets, plan
 
 
 def fused_combine(out_rows: torch.Tensor, w_slots: torch.Tensor, be: MoEFusedBackend, plan: _Plan) -> torch.Tensor:

@@ -118,3 +118,79 @@ def test_layernorm_module_in_decoder_block():
     assert torch.allclose(y1.float(), torch.nn.functional.layer_norm(x.float(), (512,)), atol=3e-2)
     assert torch.allclose(nr.float(), (x + r).float(), atol=1e-6)
     assert torch.allclose(y2.float(), torch.nn.functional.layer_norm((x + r).float(), (512,)), atol=3e-2)
+
+
+def test_grouped_gemm_matches_fp32_reference_per_group():
+    """The grouped tcgen05 GEMM (MoE experts in one launch, row ranges read from device memory): forward K-major, dgrad
+    MN-major, SwiGLU epilogue, and wgrad over the groups' rows (fresh and accumulating, with an EMPTY group) against fp32
+    matmuls per group."""
+    _native_loaded()
+    from internevo_b200 import ops
+    from internevo_b200.ops import grouped
+
+    torch.manual_seed(0)
+    h, F2, El = 1024, 1536, 4
+    counts = torch.tensor([700, 0, 129, 2050], device="cuda")
+    off = ops.aligned_offsets(counts)
+    R = int(off[-1]) + 256      # spare rows past the last group must stay untouched
+    b = off.tolist()
+    x = torch.zeros(R, h, device="cuda", dtype=torch.bfloat16)
+    for e in range(El):
+        x[b[e]: b[e] + int(counts[e])] = torch.randn(int(counts[e]), h, device="cuda") * 0.5
+    w13 = [torch.randn(F2, h, device="cuda", dtype=torch.bfloat16) * 0.05 for _ in range(El)]
+    w2 = [torch.randn(h, F2 // 2, device="cuda", dtype=torch.bfloat16) * 0.05 for _ in range(El)]
+
+    def rel(a, ref):
+        return ((a.float() - ref).abs().max() / ref.abs().max().clamp_min(1e-6)).item()
+
+    # forward (K-major B) + SwiGLU epilogue
+    gu, hh = grouped.grouped_matmul_swiglu(x, w13, off)
+    for e in range(El):
+        if b[e + 1] > b[e]:
+            ref = x[b[e]: b[e + 1]].float() @ w13[e].float().t()
+            assert rel(gu[b[e]: b[e + 1]], ref) < 1e-2
+            g_, u_ = gu[b[e]: b[e + 1], 0::2].float(), gu[b[e]: b[e + 1], 1::2].float()
+            assert rel(hh[b[e]: b[e + 1]], torch.nn.functional.silu(g_) * u_) < 2e-2
+    y = grouped.grouped_matmul(hh, w2, off)
+    # dgrad (MN-major B)
+    dy = torch.randn(R, h, device="cuda", dtype=torch.bfloat16) * 0.1
+    for e in range(El):
+        dy[b[e] + int(counts[e]): b[e + 1]] = 0
+    dh = grouped.grouped_matmul(dy, w2, off, b_mn=True)
+    for e in range(El):
+        if b[e + 1] > b[e]:
+            assert rel(y[b[e]: b[e + 1]], hh[b[e]: b[e + 1]].float() @ w2[e].float().t()) < 1e-2
+            assert rel(dh[b[e]: b[e + 1]], dy[b[e]: b[e + 1]].float() @ w2[e].float()) < 1e-2
+    # wgrad: fresh into gradient arenas, then accumulate; the empty group must come out exactly zero
+    for w in w2:
+        w.grad_buf = torch.full_like(w, 7.0)
+        w.grad_ready = False
+    assert grouped.grouped_wgrad(dy, hh, off, w2) == [None] * El
+    refs = [dy[b[e]: b[e + 1]].float().t() @ hh[b[e]: b[e + 1]].float() for e in range(El)]
+    for e in range(El):
+        if b[e + 1] > b[e]:
+            assert rel(w2[e].grad_buf, refs[e]) < 1e-2
+        else:
+            assert float(w2[e].grad_buf.abs().max()) == 0.0
+    grouped.grouped_wgrad(dy, hh, off, w2)
+    for e in range(El):
+        if b[e + 1] > b[e]:
+            assert rel(w2[e].grad_buf, 2 * refs[e]) < 2e-2
+    # whole MLP through autograd against the per-expert oracle
+    xr = x.clone().requires_grad_(True)
+    out = ops.grouped_swiglu_mlp(xr, off, w13, w2)
+    out.backward(dy)
+    xo = x.clone().requires_grad_(True)
+    oracle = torch.zeros_like(out)
+    for e in range(El):
+        if b[e + 1] > b[e]:
+            seg = xo[b[e]: b[e + 1]].float()
+            gu_ = (seg @ w13[e].float().t()).to(torch.bfloat16).float()
+            h_ = (torch.nn.functional.silu(gu_[:, 0::2]) * gu_[:, 1::2]).to(torch.bfloat16).float()
+            oracle[b[e]: b[e + 1]] = (h_ @ w2[e].float().t()).to(torch.bfloat16)
+    oracle.backward(dy)
+    live = torch.zeros(R, dtype=torch.bool, device="cuda")
+    for e in range(El):
+        live[b[e]: b[e] + int(counts[e])] = True
+    assert rel(out[live], oracle[live].float()) < 2e-2
+    assert rel(xr.grad[live], xo.grad[live].float()) < 5e-2

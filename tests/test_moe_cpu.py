@@ -262,3 +262,77 @@ def test_internlm_v1_bias_blocks_under_sequence_parallel(mode):
     assert res[0][2] != res[1][2]                       # the premise: different parameter counts per tensor rank
     assert res[0][0] == res[1][0] and res[0][0][-1] < res[0][0][0]
     assert res[0][1] and res[1][1]
+
+
+def test_aligned_slot_plan_keeps_expert_slabs_contiguous_and_128_aligned():
+    """``slot_plan(..., align=128)``: every local expert's slab starts at a multiple of 128 rows, holds its rows in the same
+    (source rank, arrival) order as the unaligned plan, and ``aligned_offsets`` / ``padding_rows`` describe exactly the gaps."""
+    from internevo_b200.ops.grouped import aligned_offsets, padding_rows
+    from internevo_b200.parallel.moe_fused import slot_plan
+
+    torch.manual_seed(1)
+    world, El, k, S = 2, 3, 2, 301
+    E = world * El
+    experts = [torch.stack([torch.randperm(E)[:k] for _ in range(S)]).reshape(-1) for _ in range(world)]
+    counts = torch.stack([torch.bincount(e, minlength=E) for e in experts])
+    for d in range(world):
+        written = {}
+        for r in range(world):
+            rank0, row0, per0, _ = slot_plan(experts[r], counts, r, El)
+            rank1, row1, per1, per_rank = slot_plan(experts[r], counts, r, El, align=128)
+            assert torch.equal(rank0, rank1) and torch.equal(per0, per1)
+            if r == d:
+                per_expert, slab_rows = per1, int(per_rank[d])
+            for s in (rank1 == d).nonzero().flatten().tolist():
+                written[int(row1[s])] = (int(experts[r][s]) - d * El, int(row0[s]))
+        off = aligned_offsets(per_expert)
+        assert slab_rows == int(off[-1]) and all(int(o) % 128 == 0 for o in off)
+        exact = per_expert.cumsum(0) - per_expert
+        for row, (el, row_unaligned) in written.items():
+            assert int(off[el]) <= row < int(off[el]) + int(per_expert[el])
+            assert row - int(off[el]) == row_unaligned - int(exact[el])          # same order inside the expert
+        assert len(written) == int(per_expert.sum())
+        pads = set(padding_rows(per_expert, off, dummy_row=10**6).tolist()) - {10**6}
+        assert pads == set(range(int(off[-1]))) - set(written)
+
+
+def test_grouped_swiglu_mlp_matches_the_per_expert_loop():
+    """``ops.grouped_swiglu_mlp`` (reference path on CPU, the grouped tcgen05 kernels on GPU - tests/test_kernels_gpu.py)
+    against one ``FeedForward`` call per expert: outputs, input gradient and every weight gradient."""
+    from internevo_b200 import ops
+    from internevo_b200.core.context import Config, global_context as gpc
+    from internevo_b200.models.modules import FeedForward
+
+    gpc.set_config(Config(dict(parallel=dict(sequence_parallel=False))))
+    torch.manual_seed(2)
+    h, F_, El = 32, 64, 3
+    experts = [FeedForward(h, F_, out_features=h, process_group=None, bias=False, dtype=torch.float32, multiple_of=32)
+               for _ in range(El)]
+    counts = torch.tensor([70, 0, 200])
+    off = ops.aligned_offsets(counts)
+    assert off.tolist() == [0, 128, 128, 384]
+    x = torch.zeros(int(off[-1]), h)
+    for e in range(El):
+        x[int(off[e]): int(off[e]) + int(counts[e])] = torch.randn(int(counts[e]), h)
+    x.requires_grad_(True)
+    y = ops.grouped_swiglu_mlp(x, off, [e.w13.weight for e in experts], [e.w2.weight for e in experts])
+    gy = torch.randn_like(y)
+    for e in range(El):
+        gy[int(off[e]) + int(counts[e]): int(off[e + 1])] = 0      # padding rows carry no gradient
+    y.backward(gy)
+    got = (y.detach().clone(), x.grad.clone(), [e.w13.weight.grad.clone() for e in experts],
+           [e.w2.weight.grad.clone() for e in experts])
+    x.grad = None
+    for e in experts:
+        e.zero_grad()
+    outs = torch.zeros_like(y)
+    for e in range(El):
+        a, b = int(off[e]), int(off[e]) + int(counts[e])
+        if b > a:
+            outs[a:b] = experts[e](x[a:b])
+    outs.backward(gy)
+    assert torch.allclose(got[0], outs.detach(), atol=1e-5) and torch.allclose(got[1], x.grad, atol=1e-5)
+    for e in range(El):
+        w13g = experts[e].w13.weight.grad if experts[e].w13.weight.grad is not None else torch.zeros_like(got[2][e])
+        w2g = experts[e].w2.weight.grad if experts[e].w2.weight.grad is not None else torch.zeros_like(got[3][e])
+        assert torch.allclose(got[2][e], w13g, atol=1e-4) and torch.allclose(got[3][e], w2g, atol=1e-4)
