@@ -467,6 +467,54 @@ void moe_gather_combine(Tensor& out, const c10::optional<Tensor>& w, const Tenso
     CHECK_RC(b200::moe_gather_combine(d, cur_stream()), "b200::moe_gather_combine");
 }
 
+// out = x @ all_gather(w_shard)^T (b_mn = false: w_shard [N / W, K]) or x @ all_gather(w_shard) (b_mn = true: x is
+// [M, N_total], w_shard [N_total / W, K_in], the gathered rows are the contraction).  `gathered` is this rank's symmetric
+// [N_total, K_in] buffer: every rank's epilogue warps push their shard into it while the tensor cores start on the own shard.
+void gather_weight_gemm(const Tensor& x, const Tensor& w_shard, int64_t gathered_ptrs, Tensor& gathered, int64_t flags_ptrs,
+                        int64_t rank, int64_t world, int64_t epoch, bool b_mn, Tensor& out) {
+    CHECK_BF16(x); CHECK_BF16(w_shard); CHECK_BF16(gathered); CHECK_BF16(out);
+    TORCH_CHECK(x.dim() == 2 && w_shard.dim() == 2 && x.stride(1) == 1 && w_shard.stride(1) == 1 && out.stride(1) == 1 &&
+                    gathered.is_contiguous(), "gather_weight_gemm: 2-D operands with unit inner stride");
+    c10::cuda::CUDAGuard guard(x.device());
+    b200::GemmCommDesc d;
+    const int64_t rows = w_shard.size(0), kin = w_shard.size(1);
+    TORCH_CHECK(gathered.size(0) == rows * world && gathered.size(1) == kin, "gather_weight_gemm: gathered buffer shape");
+    d.g.M = x.size(0);
+    if (!b_mn) { d.g.K = kin; d.g.N = rows * world; TORCH_CHECK(x.size(1) == kin, "gather_weight_gemm: K mismatch"); }
+    else       { d.g.K = rows * world; d.g.N = kin; TORCH_CHECK(x.size(1) == rows * world, "gather_weight_gemm: K mismatch"); }
+    TORCH_CHECK(out.size(0) == d.g.M && out.size(1) == d.g.N, "gather_weight_gemm: out shape");
+    d.g.A = x.data_ptr(); d.g.lda = x.stride(0); d.g.a_mn_major = 0;
+    d.g.B = w_shard.data_ptr(); d.g.ldb = w_shard.stride(0); d.g.b_mn_major = b_mn;
+    d.g.D = out.data_ptr(); d.g.ldd = out.stride(0);
+    d.peer_ptrs = reinterpret_cast<void* const*>(gathered_ptrs);
+    d.flags_ptrs = reinterpret_cast<uint32_t* const*>(flags_ptrs);
+    d.rank = rank; d.world = world; d.epoch = (uint32_t)epoch;
+    d.out_local = gathered.data_ptr(); d.m_local = rows; d.x_local = w_shard.data_ptr();
+    CHECK_RC(b200::gather_weight_gemm(d, cur_stream()), "b200::gather_weight_gemm");
+}
+
+// out[N_total / W, K_in] (+)= scale * reduce_scatter(dy^T @ x) over the rows: the weight-parallel wgrad.  dy [T, N_total],
+// x [T, K_in]; stage_ptrs: per-rank symmetric staging [world, N_total / W, K_in].
+void wgrad_rs(const Tensor& dy, const Tensor& x, Tensor& out, int64_t stage_ptrs, int64_t flags_ptrs, int64_t rank,
+              int64_t world, int64_t epoch, double scale, bool accumulate) {
+    CHECK_BF16(dy); CHECK_BF16(x); CHECK_BF16(out);
+    TORCH_CHECK(dy.dim() == 2 && x.dim() == 2 && dy.size(0) == x.size(0) && dy.stride(1) == 1 && x.stride(1) == 1 &&
+                    out.stride(1) == 1, "wgrad_rs: shapes");
+    c10::cuda::CUDAGuard guard(dy.device());
+    b200::GemmCommDesc d;
+    d.g.M = dy.size(1); d.g.K = dy.size(0); d.g.N = x.size(1);
+    TORCH_CHECK(out.size(0) * world == d.g.M && out.size(1) == d.g.N, "wgrad_rs: out shape");
+    d.g.A = dy.data_ptr(); d.g.lda = dy.stride(0); d.g.a_mn_major = 1;
+    d.g.B = x.data_ptr(); d.g.ldb = x.stride(0); d.g.b_mn_major = 1;
+    d.g.D = nullptr; d.g.ldd = d.g.N;
+    d.g.flags = accumulate ? b200::GEMM_ACCUMULATE : 0;
+    d.peer_ptrs = reinterpret_cast<void* const*>(stage_ptrs);
+    d.flags_ptrs = reinterpret_cast<uint32_t* const*>(flags_ptrs);
+    d.rank = rank; d.world = world; d.epoch = (uint32_t)epoch; d.mode = 0;
+    d.out_local = out.data_ptr(); d.ld_out = out.stride(0); d.out_scale = static_cast<float>(scale);
+    CHECK_RC(b200::gemm_reduce_scatter(d, cur_stream()), "b200::wgrad_rs");
+}
+
 // ---- grouped GEMM (MoE experts) -----------------------------------------------------------------------------------------
 // 128-byte tensor maps of every expert's weight, built on the host and uploaded once (the weights live in the optimizer's
 // arena: their addresses never change), returned as a uint8 cuda tensor [G * 128].
@@ -558,6 +606,8 @@ TORCH_LIBRARY(b200, m) {
     m.def("symm_allgather_small(int buf_ptrs, Tensor src, int flags_ptrs, int rank, int world, int epoch) -> ()", &symm_allgather_small);
     m.def("moe_scatter_rows(Tensor x, Tensor slot_rank, Tensor slot_row, Tensor? scale, int x_ptrs, int y_ptrs, Tensor(a!)? dw, int k) -> ()", &moe_scatter_rows);
     m.def("moe_gather_combine(Tensor(a!) out, Tensor? w, Tensor slot_rank, Tensor slot_row, int y_ptrs, int k) -> ()", &moe_gather_combine);
+    m.def("gather_weight_gemm(Tensor x, Tensor w_shard, int gathered_ptrs, Tensor(a!) gathered, int flags_ptrs, int rank, int world, int epoch, bool b_mn, Tensor(b!) out) -> ()", &gather_weight_gemm);
+    m.def("wgrad_rs(Tensor dy, Tensor x, Tensor(a!) out, int stage_ptrs, int flags_ptrs, int rank, int world, int epoch, float scale, bool accumulate) -> ()", &wgrad_rs);
     m.def("grouped_b_maps(Tensor[] weights, bool b_mn) -> Tensor", &grouped_b_maps);
     m.def("grouped_gemm(Tensor a, Tensor bmaps, Tensor offsets, Tensor(a!) out, int N, bool b_mn, int flags, Tensor(b!)? h) -> ()", &grouped_gemm);
     m.def("grouped_wgrad(Tensor dy, Tensor x, Tensor offsets, Tensor d_ptrs, int ldd, int flags) -> ()", &grouped_wgrad);

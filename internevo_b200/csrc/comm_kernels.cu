@@ -276,7 +276,15 @@ int gemm_reduce_scatter(const GemmCommDesc& d, cudaStream_t s) {
     c.mode = d.mode == 1 ? GEMM_COMM_ALL_REDUCE : GEMM_COMM_REDUCE_SCATTER;
     c.peer_ptrs = d.peer_ptrs; c.out_ptrs = d.out_ptrs; c.flags_ptrs = d.flags_ptrs; c.rank = d.rank; c.world = d.world;
     c.epoch = d.epoch; c.out_local = d.out_local; c.ld_out = d.ld_out; c.m_local = d.g.M / d.world;
-    c.comm_ctas = d.comm_ctas; c.done_ptrs = d.done_ptrs; c.done_counter = d.done_counter;
+    c.comm_ctas = d.comm_ctas; c.done_ptrs = d.done_ptrs; c.done_counter = d.done_counter; c.out_scale = d.out_scale;
+    return gemm_bf16_comm(d.g, c, s);
+}
+
+int gather_weight_gemm(const GemmCommDesc& d, cudaStream_t s) {
+    GemmCommArgs c;
+    c.mode = GEMM_COMM_GATHER_B;
+    c.peer_ptrs = d.peer_ptrs; c.flags_ptrs = d.flags_ptrs; c.rank = d.rank; c.world = d.world; c.epoch = d.epoch;
+    c.out_local = d.out_local; c.m_local = d.m_local; c.x_local = d.x_local;
     return gemm_bf16_comm(d.g, c, s);
 }
 

@@ -44,9 +44,12 @@ struct GemmCommDesc {
     int comm_ctas = 0;
     uint32_t* const* done_ptrs = nullptr;   // all-reduce: per-rank completion words
     uint32_t* done_counter = nullptr;       // all-reduce: local finished-CTA counter
+    float out_scale = 1.f;                  // reduce-scatter: scale of the reduced rows
 };
 int gemm_reduce_scatter(const GemmCommDesc& d, cudaStream_t s);
 int allgather_gemm(const GemmCommDesc& d, cudaStream_t s);
+// weight parallelism (ISP): B = all-gather of per-rank weight shards, consumed shard by shard by the same launch
+int gather_weight_gemm(const GemmCommDesc& d, cudaStream_t s);
 
 // ---- MoE expert-parallel dispatch / combine over peer memory (moe_comm.cu)
 // all ranks push `nwords` words into slot `rank` of every peer's table and rendezvous (one launch)

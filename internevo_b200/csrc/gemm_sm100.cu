@@ -110,7 +110,8 @@ struct CommKernelArgs {
     int m_local;          // rows per rank
     void* out_local;      // RS: reduced rows [m_local, N]
     int64_t ld_out;
-    const void* x_local;  // AG: this rank's shard [m_local, K] (contiguous)
+    const void* x_local;  // AG: this rank's shard [m_local, K] (contiguous); weight gather: this rank's weight shard
+    float out_scale;      // RS: factor applied to the reduced rows (1 / W: the weight-parallel gradient is an average)
 };
 
 B200_DEVICE void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
@@ -127,49 +128,58 @@ B200_DEVICE void st_v4(void* p, uint4 v) {
 // Rotation of the m-tile order: AG starts on the local shard (no waiting), then the shards in the order the peers push
 // them; RS/AR starts with the rows of rank+1 (pushed to their owner first) and finishes on the rows this rank owns.
 B200_DEVICE int comm_remap_m(int m, int tiles_m, const CommKernelArgs& c) {
-    if (c.mode == GEMM_COMM_NONE) return m;
+    if (c.mode == GEMM_COMM_NONE || c.mode == GEMM_COMM_GATHER_B) return m;
     const int per = tiles_m / c.world;
     const int shift = (c.mode == GEMM_COMM_ALL_GATHER ? c.rank : c.rank + 1) * per;
     return (m + shift) % tiles_m;
 }
 
+// weight gather with a K-major B: the n tiles of this rank's own shard come first, then the shards in arrival order
+B200_DEVICE int comm_remap_n(int n, int tiles_n, const CommKernelArgs& c, int b_mn) {
+    if (c.mode != GEMM_COMM_GATHER_B || b_mn) return n;
+    return (n + c.rank * (tiles_n / c.world)) % tiles_n;
+}
+
 // ---- all-gather push: the four epilogue warps of EVERY CTA, before their first tile is due --------------------------------
-// The local shard [m_local, K] goes to every peer's gathered buffer (and to the local one, which wgrad reads later) in
-// pieces of 8 rows: 128 threads move 16 bytes each per step with plain vector loads / stores - NVLink writes are posted, so
-// nothing waits for a round trip - and the piece's flag is released on every peer once the CTA's stores are ordered before
-// it.  With ~148 CTAs pushing, no single SM's store path limits the link; the accumulators are double-buffered, so the
-// tensor cores run two tiles ahead while the epilogue warps are busy here.
-B200_DEVICE void ag_push_pieces(const GemmKernelArgs& args, const CommKernelArgs& c, int t /*0..127*/) {
+// The local shard [m_local rows of `row_bytes`] goes to every peer's gathered buffer in pieces of 8 rows: 128 threads move
+// 16 bytes each per step with plain vector loads / stores - NVLink writes are posted, so nothing waits for a round trip -
+// and the piece's flag is released on the destination once the CTA's stores are ordered before it.  With ~148 CTAs pushing,
+// no single SM's store path limits the link; the accumulators are double-buffered, so the tensor cores run two tiles ahead
+// while the epilogue warps are busy here.  Destinations are served one after the other, nearest consumer first: rank d
+// consumes the shards in the order d, d + 1, ..., so shard s goes to s - 1, then s - 2, ... and every destination receives
+// whole shards in exactly the order its GEMM asks for them (a ring schedule at full NVSwitch bandwidth).  `self_copy`
+// appends the local copy (activations: wgrad reads the gathered buffer later; weights are read in place instead).
+B200_DEVICE void ag_push_pieces(const CommKernelArgs& c, int64_t row_bytes, bool self_copy, int t /*0..127*/) {
     const int blocks_local = c.m_local / BM;
     const int pieces = blocks_local * AG_PARTS;
-    const int64_t piece_bytes = (int64_t)(BM / AG_PARTS) * args.K * 2;
+    const int64_t piece_bytes = (int64_t)(BM / AG_PARTS) * row_bytes;
     const uint8_t* src0 = reinterpret_cast<const uint8_t*>(c.x_local);
-    const int64_t dst_base = (int64_t)c.rank * c.m_local * args.K * 2;
-    for (int p = blockIdx.x; p < pieces; p += gridDim.x) {
-        const uint8_t* src = src0 + (int64_t)p * piece_bytes;
-        const int64_t doff = dst_base + (int64_t)p * piece_bytes;
-        for (int64_t o = (int64_t)t * 16; o < piece_bytes; o += 4 * 128 * 16) {
-            uint4 v[4];
+    const int64_t dst_base = (int64_t)c.rank * c.m_local * row_bytes;
+    const int ndst = c.world - 1 + (self_copy ? 1 : 0);
+    for (int q = 0; q < ndst; ++q) {
+        const int dest = (c.rank - 1 - q + 2 * c.world) % c.world;   // q == world - 1: this rank itself
+        uint8_t* dst0 = reinterpret_cast<uint8_t*>(c.peer_ptrs[dest]) + dst_base;
+        for (int p = blockIdx.x; p < pieces; p += gridDim.x) {
+            const uint8_t* src = src0 + (int64_t)p * piece_bytes;
+            uint8_t* dst = dst0 + (int64_t)p * piece_bytes;
+            for (int64_t o = (int64_t)t * 16; o < piece_bytes; o += 4 * 128 * 16) {
+                uint4 v[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (o + j * 2048 < piece_bytes) v[j] = ld_nc_v4(src + o + j * 2048);
-            for (int q = 0; q < c.world; ++q) {
-                uint8_t* dst = reinterpret_cast<uint8_t*>(c.peer_ptrs[(c.rank + 1 + q) % c.world]) + doff;  // local copy last
+                for (int j = 0; j < 4; ++j)
+                    if (o + j * 2048 < piece_bytes) v[j] = ld_nc_v4(src + o + j * 2048);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if (o + j * 2048 < piece_bytes) st_v4(dst + o + j * 2048, v[j]);
             }
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (t < c.world) {   // one thread per destination publishes the piece there
-            fence_acq_rel_sys();
-            const int b = p / AG_PARTS, j = p % AG_PARTS;
-            st_release_sys(c.flags_ptrs[(c.rank + 1 + t) % c.world] + (c.rank * blocks_local + b) * AG_PARTS + j, c.epoch);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (t == 0) {   // publish the piece on its destination
+                fence_acq_rel_sys();
+                st_release_sys(c.flags_ptrs[dest] + (c.rank * blocks_local) * AG_PARTS + p, c.epoch);
+            }
         }
     }
 }
 
-// item -> (group, m tile inside the group, n tile) for the grouped forms; s_off / s_start live in shared memory
 template <int CG>
 B200_DEVICE void grp_coords(int item, const GemmKernelArgs& a, const int* s_off, const int* s_start, int& g, int& tm, int& tn) {
     if (a.grp_mode == 1) {
@@ -281,12 +291,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         }
                     }
                 }
-                if (lane != 0) continue;   // lane 0 issues every TMA load of the tile
                 int m0 = (tm * CG + cta_rank) * BM;
-                const int n0 = tn * BN + n_off + cta_rank * (width / CG);
+                int n0 = tn * BN + n_off + cta_rank * (width / CG);
                 const int m0_own = m0 - comm.rank * comm.m_local;
                 const CUtensorMap* map_b = &tmap_b;
                 int kb_n = num_kb, k_base = 0;
+                bool gb_k = false;   // weight gather along the contraction (dgrad): shards are walked inside the k loop
+                if constexpr (COMM) {
+                    if (comm.mode == GEMM_COMM_GATHER_B) {
+                        if (!args.b_mn) {
+                            // forward: this CTA's half of the n tile is ONE 128-row block of the gathered weight
+                            tn = comm_remap_n(tn, args.tiles_n, comm, 0);
+                            n0 = tn * BN + cta_rank * (BN / CG);
+                            const int nblk = n0 / BM;
+                            if (nblk / (comm.m_local / BM) == comm.rank) {      // own shard: read in place
+                                map_b = &tmap_bt;
+                                n0 -= comm.rank * comm.m_local;
+                            } else if (!(nblk < 64 && ((ready >> nblk) & 1))) {
+                                if (lane < AG_PARTS) {
+                                    const uint32_t* f = comm.flags_ptrs[comm.rank] + nblk * AG_PARTS + lane;
+                                    while (static_cast<int32_t>(ld_acquire_sys(f) - comm.epoch) < 0) {
+                                    }
+                                }
+                                __syncwarp();
+                                fence_proxy_async_all();
+                                if (nblk < 64) ready |= 1ull << nblk;
+                            }
+                        } else {
+                            gb_k = true;
+                        }
+                    }
+                }
                 if constexpr (GRP) {
                     if (args.grp_mode == 1) { m0 += s_off[g]; map_b = args.b_maps + g; }
                     else { k_base = s_off[g]; kb_n = (s_off[g + 1] - s_off[g]) / BK; }
@@ -297,35 +332,62 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     else tma_load_2d(dst, map, bar, c0, c1);
                 };
                 const int nb64 = width / CG / 64;  // B arrives in 64-row (K-major) or 64-column (MN-major) boxes
+                // every lane walks the k loop (only the weight-gather dgrad has work for lanes 1..31: polling the flags of
+                // the next shard); lane 0 alone waits for free slots and issues the TMA loads
                 for (int kb = 0; kb < kb_n; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES * CG + width * (BK * 2));
-                    uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
-                    uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
-                    const int k0 = k_base + kb * BK;
-                    if (COMM && own_rows) {  // the local shard is read in place (tmap_bt doubles as its map)
-                        ld(sa, &tmap_bt, &full_bar[stage], k0, m0_own);
-                    } else if (!args.a_mn) {
-                        ld(sa, &tmap_a, &full_bar[stage], k0, m0);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < BM / 64; ++j)
-                            ld(sa + j * (BK * 128), &tmap_a, &full_bar[stage], m0 + j * 64, k0);
+                    int kk = kb, kb_off = 0;   // k block loaded for A / k offset of the B coordinate
+                    const CUtensorMap* mb = map_b;
+                    if constexpr (COMM) {
+                        if (gb_k) {
+                            const int kbs = kb_n / comm.world;           // k blocks per weight shard
+                            const int seg = kb / kbs;
+                            const int shard = (comm.rank + seg) % comm.world;
+                            kk = shard * kbs + (kb - seg * kbs);
+                            if (seg == 0) {
+                                mb = &tmap_bt;                             // own shard, read in place
+                                kb_off = -comm.rank * comm.m_local;
+                            } else if (kb == seg * kbs && !((ready >> shard) & 1)) {
+                                const int words = (comm.m_local / BM) * AG_PARTS;
+                                const uint32_t* f = comm.flags_ptrs[comm.rank] + shard * words;
+                                for (int i = lane; i < words; i += 32)
+                                    while (static_cast<int32_t>(ld_acquire_sys(f + i) - comm.epoch) < 0) {
+                                    }
+                                __syncwarp();
+                                fence_proxy_async_all();
+                                ready |= 1ull << shard;
+                            }
+                        }
                     }
-                    if (width == BN) {
-                        if (!args.b_mn) {
-                            ld(sb, map_b, &full_bar[stage], k0, n0);
+                    if (lane == 0) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES * CG + width * (BK * 2));
+                        uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
+                        uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
+                        const int k0 = k_base + kk * BK;
+                        if (COMM && own_rows) {  // the local shard is read in place (tmap_bt doubles as its map)
+                            ld(sa, &tmap_bt, &full_bar[stage], k0, m0_own);
+                        } else if (!args.a_mn) {
+                            ld(sa, &tmap_a, &full_bar[stage], k0, m0);
                         } else {
 #pragma unroll
-                            for (int j = 0; j < BN / CG / 64; ++j)
-                                ld(sb + j * (BK * 128), map_b, &full_bar[stage], n0 + j * 64, k0);
+                            for (int j = 0; j < BM / 64; ++j)
+                                ld(sa + j * (BK * 128), &tmap_a, &full_bar[stage], m0 + j * 64, k0);
                         }
-                    } else if (!args.b_mn) {  // tail slice: 64-row boxes of the K-major operand
-                        for (int j = 0; j < nb64; ++j)
-                            ld(sb + j * (64 * 128), &tmap_bt, &full_bar[stage], k0, n0 + j * 64);
-                    } else {
-                        for (int j = 0; j < nb64; ++j)
-                            ld(sb + j * (BK * 128), &tmap_b, &full_bar[stage], n0 + j * 64, k0);
+                        if (width == BN) {
+                            if (!args.b_mn) {
+                                ld(sb, mb, &full_bar[stage], k0, n0);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < BN / CG / 64; ++j)
+                                    ld(sb + j * (BK * 128), mb, &full_bar[stage], n0 + j * 64, k0 + kb_off);
+                            }
+                        } else if (!args.b_mn) {  // tail slice: 64-row boxes of the K-major operand
+                            for (int j = 0; j < nb64; ++j)
+                                ld(sb + j * (64 * 128), &tmap_bt, &full_bar[stage], k0, n0 + j * 64);
+                        } else {
+                            for (int j = 0; j < nb64; ++j)
+                                ld(sb + j * (BK * 128), &tmap_b, &full_bar[stage], n0 + j * 64, k0);
+                        }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -390,13 +452,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if constexpr (COMM) {
             rs_mode = comm.mode == GEMM_COMM_REDUCE_SCATTER || comm.mode == GEMM_COMM_ALL_REDUCE;
             // all-gather: push the local shard to every peer first (the MMA warp runs up to two tiles ahead meanwhile)
-            if (comm.mode == GEMM_COMM_ALL_GATHER) ag_push_pieces(args, comm, static_cast<int>(threadIdx.x) - 64);
+            if (comm.mode == GEMM_COMM_ALL_GATHER)
+                ag_push_pieces(comm, (int64_t)args.K * 2, true, static_cast<int>(threadIdx.x) - 64);
+            // weight gather (ISP): the local weight shard [N / W, K_in] goes to every peer's gathered-B buffer
+            if (comm.mode == GEMM_COMM_GATHER_B)
+                ag_push_pieces(comm, (int64_t)(args.b_mn ? args.N : args.K) * 2, false, static_cast<int>(threadIdx.x) - 64);
         }
         for (int tile = unit; tile < num_items; tile += grid_ctas) {
             int tm, tn, n_off, width, g = 0;
             if constexpr (GRP) { grp_coords<CG>(tile, args, s_off, s_start, g, tm, tn); n_off = 0; width = BN; }
             else item_coords<BN>(tile, args, tm, tn, n_off, width);
-            if constexpr (COMM) tm = comm_remap_m(tm, args.tiles_m, comm);
+            if constexpr (COMM) {
+                tm = comm_remap_m(tm, args.tiles_m, comm);
+                tn = comm_remap_n(tn, args.tiles_n, comm, args.b_mn);
+            }
             const int blk = tm * CG + cta_rank;   // 128-row block of this CTA
             int row = blk * BM + q * 32 + lane;
             int row_end = args.M;
@@ -454,6 +523,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                     for (int i = 0; i < 32; i += 8) {
                                         if (col + i < args.N) {
                                             const uint4 x = ld_cg_v4(src + i);
+                                            float2 a = unpack_bf16(x.x), b = unpack_bf16(x.y), cq = unpack_bf16(x.z),
+                                                   dd = unpack_bf16(x.w);
+                                            v[i] += a.x; v[i + 1] += a.y; v[i + 2] += b.x; v[i + 3] += b.y;
+                                            v[i + 4] += cq.x; v[i + 5] += cq.y; v[i + 6] += dd.x; v[i + 7] += dd.y;
+                                        }
+                                    }
+                                }
+                            }
+                            if (own && comm.mode == GEMM_COMM_REDUCE_SCATTER && col < args.N) {
+                                // weight-parallel wgrad: average over the group and (from the second micro-batch on) add
+                                // what the gradient arena already holds
+                                if (comm.out_scale != 1.f) {
+#pragma unroll
+                                    for (int i = 0; i < 32; ++i) v[i] *= comm.out_scale;
+                                }
+                                if (accumulate) {
+                                    const __nv_bfloat16* prev = reinterpret_cast<const __nv_bfloat16*>(comm.out_local) +
+                                                                (int64_t)(row0_local + lane) * comm.ld_out + col;
+#pragma unroll
+                                    for (int i = 0; i < 32; i += 8) {
+                                        if (col + i < args.N) {
+                                            const uint4 x = *reinterpret_cast<const uint4*>(prev + i);
                                             float2 a = unpack_bf16(x.x), b = unpack_bf16(x.y), cq = unpack_bf16(x.z),
                                                    dd = unpack_bf16(x.w);
                                             v[i] += a.x; v[i + 1] += a.y; v[i + 2] += b.x; v[i + 3] += b.y;
@@ -842,23 +933,39 @@ static int launch(const GemmDesc& g, cudaStream_t stream) {
 int gemm_bf16_comm(const GemmDesc& g, const GemmCommArgs& c, cudaStream_t stream) {
     constexpr int BN = 256, CG = 2;   // the CTA-pair tile (cta_group::2), same as the plain GEMM's default
     using Cfg = GemmCfg<BN, CG>;
-    if (c.world < 2 || g.a_mn_major) return -20;
+    const bool ag = c.mode == GEMM_COMM_ALL_GATHER, gb = c.mode == GEMM_COMM_GATHER_B;
+    const bool rs = c.mode == GEMM_COMM_REDUCE_SCATTER || c.mode == GEMM_COMM_ALL_REDUCE;
+    if (c.world < 2) return -20;
+    if (g.a_mn_major && c.mode != GEMM_COMM_REDUCE_SCATTER) return -20;   // MN-major A: the wgrad -> reduce-scatter form only
     const int tiles_m = (g.M + BM * CG - 1) / (BM * CG), tiles_n = (g.N + BN - 1) / BN;
-    if (g.M % (BM * CG * c.world) != 0) return -21;  // every rank owns whole 256-row tiles
-    if (g.N % 8 != 0 || g.K % 8 != 0) return -22;
-    const bool ag = c.mode == GEMM_COMM_ALL_GATHER;
+    if ((ag || rs) && g.M % (BM * CG * c.world) != 0) return -21;  // every rank owns whole 256-row tiles
+    if (g.N % 8 != 0 || (g.K % 8 != 0 && !g.a_mn_major)) return -22;
     if (c.mode == GEMM_COMM_ALL_REDUCE && (c.done_ptrs == nullptr || c.done_counter == nullptr)) return -23;
+    if (gb) {
+        // weight shards of whole 128-row blocks; K-major B: whole n tiles per rank, MN-major B: whole k blocks per rank
+        if (c.m_local % BM != 0) return -24;
+        if (!g.b_mn_major && (g.N != c.m_local * c.world || g.N % (BN * c.world) != 0)) return -25;
+        if (g.b_mn_major && (g.K != c.m_local * c.world)) return -26;
+    }
     CUtensorMap ta, tb, tx;
     int rc;
-    // A: the gathered buffer (AG) or the local activations (RS / AR)
-    rc = make_tmap_2d_bf16(&ta, ag ? c.out_local : g.A, g.K, g.M, ag ? (int64_t)g.K : g.lda, BK, BM);
+    // A: the gathered buffer (AG) or the local activations (RS / AR / weight gather)
+    if (!g.a_mn_major) rc = make_tmap_2d_bf16(&ta, ag ? c.out_local : g.A, g.K, g.M, ag ? (int64_t)g.K : g.lda, BK, BM);
+    else               rc = make_tmap_2d_bf16(&ta, g.A, g.M, g.K, g.lda, 64, BK);
     if (rc) return rc;
-    if (!g.b_mn_major) rc = make_tmap_2d_bf16(&tb, g.B, g.K, g.N, g.ldb, BK, BN / CG);
-    else               rc = make_tmap_2d_bf16(&tb, g.B, g.N, g.K, g.ldb, 64, BK);
+    const void* bptr = gb ? c.out_local : g.B;     // weight gather: B is this rank's gathered buffer
+    const int64_t ldb = gb ? (g.b_mn_major ? (int64_t)g.N : (int64_t)g.K) : g.ldb;
+    if (!g.b_mn_major) rc = make_tmap_2d_bf16(&tb, bptr, g.K, g.N, ldb, BK, BN / CG);
+    else               rc = make_tmap_2d_bf16(&tb, bptr, g.N, g.K, ldb, 64, BK);
     if (rc) return rc;
     tx = tb;
     if (ag) {  // this rank's shard, read in place
         rc = make_tmap_2d_bf16(&tx, c.x_local, g.K, c.m_local, g.K, BK, BM);
+        if (rc) return rc;
+    }
+    if (gb) {  // this rank's weight shard [m_local, K_in], read in place
+        if (!g.b_mn_major) rc = make_tmap_2d_bf16(&tx, c.x_local, g.K, c.m_local, g.ldb, BK, BN / CG);
+        else               rc = make_tmap_2d_bf16(&tx, c.x_local, g.N, c.m_local, g.ldb, 64, BK);
         if (rc) return rc;
     }
     GemmKernelArgs a = {};
@@ -866,16 +973,17 @@ int gemm_bf16_comm(const GemmDesc& g, const GemmCommArgs& c, cudaStream_t stream
     a.M = g.M; a.N = g.N; a.K = g.K;
     a.D = g.D; a.ldd = g.ldd;
     a.bias = nullptr; a.H = g.H; a.ldh = g.ldh; a.flags = g.flags;
-    a.a_mn = 0; a.b_mn = g.b_mn_major;
+    a.a_mn = g.a_mn_major; a.b_mn = g.b_mn_major;
     a.tiles_m = tiles_m; a.tiles_n = tiles_n;
     CommKernelArgs k;
     k.mode = c.mode; k.peer_ptrs = c.peer_ptrs; k.flags_ptrs = c.flags_ptrs; k.out_ptrs = c.out_ptrs;
     k.done_ptrs = c.done_ptrs; k.done_counter = c.done_counter;
     k.rank = c.rank; k.world = c.world; k.epoch = c.epoch; k.m_local = (int)c.m_local;
     k.out_local = c.out_local; k.ld_out = c.ld_out; k.x_local = c.x_local;
+    k.out_scale = c.out_scale;
     int units = num_sms() / CG;
-    // all-gather: every CTA also pushes a share of the local shard, so the whole machine is launched even for few tiles
-    if (!ag && units > tiles_m * tiles_n) units = tiles_m * tiles_n;
+    // all-gather forms: every CTA also pushes a share of the local shard, so the whole machine is launched even for few tiles
+    if (rs && units > tiles_m * tiles_n) units = tiles_m * tiles_n;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(gemm_bf16_kernel<BN, true, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -44,6 +44,9 @@ enum GemmCommMode : int {
     GEMM_COMM_ALL_GATHER = 1,      // A = all-gather of per-rank row shards, pushed by the epilogue warps of every CTA first
     GEMM_COMM_REDUCE_SCATTER = 2,  // epilogue pushes partial tiles to their owner; the owner's epilogue reduces
     GEMM_COMM_ALL_REDUCE = 3,      // as above, reduced rows are pushed into every peer's output
+    GEMM_COMM_GATHER_B = 4,        // B = all-gather of per-rank weight shards [N / W, K] (weight / ISP parallelism): pushed
+                                   // like the activations above; the GEMM walks the shards own-first (n tiles when B is
+                                   // K-major, k blocks when B is MN-major) and reads its own shard in place
 };
 
 struct GemmCommArgs {
@@ -54,12 +57,13 @@ struct GemmCommArgs {
     int rank = 0, world = 1;
     uint32_t epoch = 0;
     int64_t m_local = 0;                   // rows per rank (AG: contributed, RS: owned)
-    void* out_local = nullptr;             // AG: this rank's gathered A [M, K] (contiguous); RS: reduced rows [m_local, N]
+    void* out_local = nullptr;             // AG / weight gather: this rank's gathered buffer; RS: reduced rows [m_local, N]
     int64_t ld_out = 0;                    // RS / AR: row stride of the output
     const void* x_local = nullptr;         // AG: this rank's shard [m_local, K] (contiguous)
     int comm_ctas = 0;                     // unused (the all-gather push runs on the epilogue warps of every CTA)
     uint32_t* const* done_ptrs = nullptr;  // AR: per-rank `world` completion words (end-of-kernel handshake)
     uint32_t* done_counter = nullptr;      // AR: local counter of finished CTAs
+    float out_scale = 1.f;                 // RS: scale of the reduced rows (GEMM_ACCUMULATE in g.flags adds the previous out_local)
 };
 
 int gemm_bf16_comm(const GemmDesc& g, const GemmCommArgs& c, cudaStream_t stream);

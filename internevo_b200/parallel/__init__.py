@@ -8,6 +8,7 @@ def reset_caches() -> None:
     mods = sys.modules
     if "internevo_b200.parallel.fused" in mods:
         mods["internevo_b200.parallel.fused"]._tp_backends.clear()
+        mods["internevo_b200.parallel.fused"]._isp_backends.clear()
     if "internevo_b200.parallel.linear" in mods:
         mods["internevo_b200.parallel.linear"].set_fused_backend(None)
     if "internevo_b200.parallel.moe_fused" in mods:

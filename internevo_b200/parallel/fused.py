@@ -146,6 +146,92 @@ def enable_tp(group: Optional[dist.ProcessGroup]) -> Optional[TPFusedBackend]:
     return _tp_backends[key]
 
 
+class ISPFusedBackend:
+    """Weight-parallel (ISP) linears with the weight all-gather / gradient reduce-scatter INSIDE the tcgen05 GEMM
+    (reference sites: ``internlm/core/communication/isp.py:255-297,486-526``, ``internlm/model/utils.py:466-586``).
+
+    ``gather_gemm(x, w_shard)``          y = x @ all_gather(w_shard)^T: every rank's epilogue warps push their weight shard
+                                         into the peers' gathered buffers - destination by destination, in the order the
+                                         consumers need the shards - while the tensor cores start on the n tiles of the own
+                                         shard (read in place); a tile of a remote shard is loaded once its 8-row pieces
+                                         have landed.
+    ``gather_gemm(dy, w_shard, b_mn)``   dx = dy @ all_gather(w_shard): the gathered rows are the contraction; the k loop
+                                         walks the shards own-first and waits at shard boundaries.
+    ``wgrad_rs(dy, x, out)``             out (+)= (1 / W) reduce_scatter(dy^T @ x): partial blocks owned by a peer go straight
+                                         into that peer's staging slot from the GEMM epilogue, own blocks are reduced and
+                                         accumulated into the gradient arena shard.
+    No ``all_gather_into_tensor`` / ``reduce_scatter_tensor`` is left on this path.  Gathered buffers and staging slots are
+    ping-pong pairs keyed by shape (same recycling argument as ``TPFusedBackend``)."""
+
+    def __init__(self, group: dist.ProcessGroup):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.flags = symm.flags_for(group)
+        self._gath: Dict[Tuple[int, int], list] = {}
+        self._stage: Dict[Tuple[int, int], list] = {}
+
+    _pp = TPFusedBackend._pp
+
+    def supports(self, x: torch.Tensor, w_shard: torch.Tensor) -> bool:
+        rows, kin = w_shard.shape
+        n_total = rows * self.world
+        return (x.is_cuda and x.dtype == torch.bfloat16 and w_shard.dtype == torch.bfloat16 and x.dim() == 2
+                and rows % 256 == 0 and kin % 8 == 0 and x.stride(-1) == 1 and w_shard.stride(1) == 1
+                and w_shard.stride(0) % 8 == 0
+                and (n_total // 128) * 16 <= symm.AG_FLAG_WORDS
+                and (n_total // 128) * ((kin + 255) // 256) <= symm.RS_FLAG_WORDS)
+
+    def gather_gemm(self, x: torch.Tensor, w_shard: torch.Tensor, b_mn: bool = False) -> torch.Tensor:
+        rows, kin = w_shard.shape
+        n_total = rows * self.world
+        gb = self._pp(self._gath, (n_total, kin), n_total * kin)
+        gathered = gb.tensor.view(n_total, kin)
+        out = torch.empty(x.shape[0], kin if b_mn else n_total, device=x.device, dtype=x.dtype)
+        if symm.DEBUG:
+            self.flags.barrier()
+            symm.poison(gathered)
+            self.flags.barrier()
+        torch.ops.b200.gather_weight_gemm(x, w_shard, gb.table_ptr(0), gathered, symm.ag_flag_table(self.flags), self.rank,
+                                          self.world, self.flags.next_epoch(), b_mn, out)
+        _bump()
+        if symm.DEBUG:
+            symm.assert_clean(out, "isp gather_gemm output")
+        return out
+
+    def wgrad_rs(self, dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor, accumulate: bool) -> None:
+        """``out [N_total / W, K_in]`` (a gradient-arena view or a fresh tensor) ``(+)= mean over the group of dy^T @ x``."""
+        n_total, kin = dy.shape[1], x.shape[1]
+        stage = self._pp(self._stage, (n_total, kin), n_total * kin)
+        if symm.DEBUG:
+            self.flags.barrier()
+            symm.poison(stage.tensor)
+            self.flags.barrier()
+        torch.ops.b200.wgrad_rs(dy, x, out, stage.table_ptr(0), symm.rs_flag_table(self.flags), self.rank, self.world,
+                                self.flags.next_epoch(), 1.0 / self.world, accumulate)
+        _bump()
+
+
+_isp_backends: Dict[int, ISPFusedBackend] = {}
+
+
+def isp_backend(group: Optional[dist.ProcessGroup]) -> Optional[ISPFusedBackend]:
+    """The fused weight-parallel backend of ``group`` (created on first use); ``None`` when peer memory is unavailable, the
+    group is trivial or ``B200_ISP_FUSED=0`` (NCCL prefetch path, also the numerical oracle)."""
+    if group is None or dist.get_world_size(group) not in (2, 4, 8) or not symm.symm_available():
+        return None
+    if os.environ.get("B200_ISP_FUSED", "1") == "0":
+        return None
+    key = id(group)
+    if key not in _isp_backends:
+        try:
+            _isp_backends[key] = ISPFusedBackend(group)
+        except Exception as e:  # pragma: no cover - depends on driver / topology
+            logger.warning(f"fused ISP linears unavailable ({e}); using NCCL")
+            return None
+    return _isp_backends[key]
+
+
 class ZeroFusedBackend:
     """Peer-memory primitives of ``HybridZeroOptimizer`` for groups whose ZeRO group is the DP group: the optimizer decides
     WHEN a range is reduced / updated (during backward / ahead of the next forward), this class does it over NVLink.

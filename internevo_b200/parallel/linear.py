@@ -142,17 +142,40 @@ class _ParallelLinearFn(torch.autograd.Function):
         return dx, dw, db, None, None, None
 
 
+def _isp_fused(x2, weight, module, use_fused_comm=None):
+    """The peer-memory backend for this weight-parallel linear, or ``None`` (NCCL prefetch path)."""
+    if not (x2.is_cuda and x2.dtype == torch.bfloat16):
+        return None
+    from internevo_b200.core.context import global_context as gpc
+
+    if gpc.config is None or not gpc.config.get("fused_comm", False):
+        return None
+    from . import fused
+
+    be = fused.isp_backend(module.process_group)
+    return be if be is not None and be.supports(x2, weight) else None
+
+
 class _ISPLinearFn(torch.autograd.Function):
-    """Weight-parallel linear: all-gather(W) → GEMM; backward: all-gather(W) → dgrad, wgrad → reduce-scatter(AVG)."""
+    """Weight-parallel linear: all-gather(W) → GEMM; backward: all-gather(W) → dgrad, wgrad → reduce-scatter(AVG).
+    With a peer-memory heap the three collectives run inside the GEMM kernels (``fused.ISPFusedBackend``)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, module, communicator):
         ctx.module, ctx.comm = module, communicator
         ctx.has_bias = bias is not None
-        w_full = communicator.all_gather_weight(module, weight, is_bias=False)
-        b_full = communicator.all_gather_weight(module, bias, is_bias=True) if bias is not None else None
-        y = _mm(x, w_full, b_full)
-        communicator.release_weight(module)
+        be = _isp_fused(x, weight, module)
+        ctx.fused = be
+        if be is not None:
+            module._b200_isp_fused = True    # the communicator does not prefetch (NCCL-gather) this module's weight
+            y = be.gather_gemm(x, weight)
+            if bias is not None:
+                y = y + communicator.all_gather_weight(module, bias, is_bias=True)
+        else:
+            w_full = communicator.all_gather_weight(module, weight, is_bias=False)
+            b_full = communicator.all_gather_weight(module, bias, is_bias=True) if bias is not None else None
+            y = _mm(x, w_full, b_full)
+            communicator.release_weight(module)
         ctx.save_for_backward(x, weight, bias)
         return y
 
@@ -161,16 +184,31 @@ class _ISPLinearFn(torch.autograd.Function):
         x, weight, bias = ctx.saved_tensors
         comm, module = ctx.comm, ctx.module
         dy = dy.contiguous()
-        w_full = comm.all_gather_weight(module, weight, is_bias=False, backward=True)
-        dx = _mm_dgrad(dy, w_full) if ctx.needs_input_grad[0] else None
-        comm.release_weight(module)
+        be = ctx.fused
         dw = db = None
-        if ctx.needs_input_grad[1]:
-            if dy.is_cuda and dy.dtype == torch.bfloat16:
-                dw_full = ops.matmul(dy, x, a_mn=True, b_mn=True)
-            else:
-                dw_full = (dy.t() @ x).to(weight.dtype)
-            dw = comm.reduce_scatter_grad(module, weight, dw_full)
+        if be is not None:
+            dx = be.gather_gemm(dy, weight, b_mn=True) if ctx.needs_input_grad[0] else None
+            if ctx.needs_input_grad[1]:
+                buf = getattr(weight, "grad_buf", None)
+                if buf is not None:
+                    be.wgrad_rs(dy, x, buf, accumulate=getattr(weight, "grad_ready", False))
+                    weight.grad_ready = True
+                    hook = getattr(weight, "grad_hook", None)
+                    if hook is not None:
+                        hook(weight)
+                else:
+                    dw = torch.empty_like(weight)
+                    be.wgrad_rs(dy, x, dw, accumulate=False)
+        else:
+            w_full = comm.all_gather_weight(module, weight, is_bias=False, backward=True)
+            dx = _mm_dgrad(dy, w_full) if ctx.needs_input_grad[0] else None
+            comm.release_weight(module)
+            if ctx.needs_input_grad[1]:
+                if dy.is_cuda and dy.dtype == torch.bfloat16:
+                    dw_full = ops.matmul(dy, x, a_mn=True, b_mn=True)
+                else:
+                    dw_full = (dy.t() @ x).to(weight.dtype)
+                dw = comm.reduce_scatter_grad(module, weight, dw_full)
         if ctx.has_bias:
             db_full = dy.float().sum(0).to(dy.dtype)
             db = comm.reduce_scatter_grad(module, bias, db_full, is_bias=True)

@@ -52,3 +52,38 @@ def test_tp2_fused_linears_track_nccl(mode):
     for (l0, n0), (l1, n1) in zip(ref, got):
         assert abs(l0 - l1) < 0.02 * abs(l0) + 0.01, (ref, got)
         assert abs(n0 - n1) < 0.08 * n0 + 0.02, (ref, got)
+
+
+def _train_isp(rank, world, fused):
+    """Weight-parallel (ISP) run with sequence-parallel attention: sp = wp = 2."""
+    cfg = tiny_config(tp=2, wp=2, mode="isp", dtype="torch.bfloat16", num_layers=2, hidden=512, heads=4, kv_heads=2,
+                      seq_len=1024, micro_bsz=1, vocab=1024, micro_num=2)
+    cfg["fused_comm"] = True
+    os.environ["B200_ISP_FUSED"] = "1" if fused else "0"
+    trainer, opt, model, _ = build_trainer(cfg)
+    from internevo_b200 import ops
+
+    n0 = ops.launch_count()
+    out_l = []
+    for _ in range(4):
+        data, labels = synthetic_batch(2, 1024, 1024, seed=0)
+        trainer.zero_grad()
+        out = trainer.execute_schedule((data, labels), forward_only=False, return_loss=True, return_output_label=False)
+        ok, norms = trainer.step()
+        assert ok
+        out_l.append((float(out[2]), sorted(norms.items())))
+    from internevo_b200.parallel import fused as fmod
+
+    used = bool(fmod._isp_backends) and any(be._gath for be in fmod._isp_backends.values())
+    assert used == bool(fused), "the fused ISP path was (not) taken"
+    return out_l
+
+
+def test_isp_fused_linears_track_nccl():
+    """ISP with the weight all-gather / gradient reduce-scatter inside the GEMM kernels must follow the NCCL-prefetch run."""
+    ref = run_distributed(_train_isp, 2, False)[0]
+    got = run_distributed(_train_isp, 2, True)[0]
+    for (l0, n0), (l1, n1) in zip(ref, got):
+        assert abs(l0 - l1) < 0.02 * abs(l0) + 0.01, (ref, got)
+        for (k0, v0), (k1, v1) in zip(n0, n1):
+            assert k0 == k1 and abs(v0 - v1) < 0.08 * v0 + 0.02, (ref, got)

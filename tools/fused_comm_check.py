@@ -139,6 +139,57 @@ def main():
                                   "gemm_only_ms": round(timed(lambda: ops.matmul(xg, w)), 4),
                                   "roofline_ms": round(max(flop_ms, link_ms), 4),
                                   "frac_of_roofline": round(max(flop_ms, link_ms) / t_f, 3)}
+    # ---- weight-parallel (ISP) forms: weight gather inside the GEMM (forward and dgrad), wgrad -> reduce-scatter (AVG)
+    ib = fused.ISPFusedBackend(group)
+    Tl = 4096
+    for name, (Nt, K) in {"wqkv": (6144, h), "w2": (h, F)}.items():
+        xs = torch.randn(Tl, K, device="cuda", dtype=torch.bfloat16) * 0.1          # every rank its own tokens
+        wsh = torch.randn(Nt // world, K, device="cuda", dtype=torch.bfloat16) * 0.1
+        wfull = torch.empty(Nt, K, device="cuda", dtype=torch.bfloat16)
+        dist.all_gather_into_tensor(wfull, wsh)
+        ref = ops.matmul(xs, wfull)
+        y = ib.gather_gemm(xs, wsh)
+        r_f = rel(y, ref)
+        dy = torch.randn(Tl, Nt, device="cuda", dtype=torch.bfloat16) * 0.1
+        ref_dx = ops.matmul(dy, wfull, b_mn=True)
+        dx = ib.gather_gemm(dy, wsh, b_mn=True)
+        r_d = rel(dx, ref_dx)
+        dw_full = ops.matmul(dy, xs, a_mn=True, b_mn=True, out_dtype=torch.float32)
+        ref_dw = torch.empty(Nt // world, K, device="cuda")
+        dist.reduce_scatter_tensor(ref_dw, dw_full, op=dist.ReduceOp.AVG)
+        dw = torch.empty(Nt // world, K, device="cuda", dtype=torch.bfloat16)
+        ib.wgrad_rs(dy, xs, dw, accumulate=False)
+        r_w = rel(dw, ref_dw)
+        ib.wgrad_rs(dy, xs, dw, accumulate=True)
+        r_w2 = rel(dw, 2 * ref_dw)
+        ok &= r_f < 2e-2 and r_d < 2e-2 and r_w < 2e-2 and r_w2 < 3e-2
+        stage(f"isp {name} fwd rel={r_f} dgrad rel={r_d} wgrad rel={r_w} accumulate rel={r_w2}")
+
+        def nccl_fwd():
+            g = torch.empty(Nt, K, device="cuda", dtype=torch.bfloat16)
+            dist.all_gather_into_tensor(g, wsh)
+            ops.matmul(xs, g)
+
+        def nccl_dgrad():
+            g = torch.empty(Nt, K, device="cuda", dtype=torch.bfloat16)
+            dist.all_gather_into_tensor(g, wsh)
+            ops.matmul(dy, g, b_mn=True)
+
+        def nccl_wgrad():
+            full = ops.matmul(dy, xs, a_mn=True, b_mn=True)
+            o = torch.empty(Nt // world, K, device="cuda", dtype=torch.bfloat16)
+            dist.reduce_scatter_tensor(o, full, op=dist.ReduceOp.AVG)
+
+        t = {"fwd": (timed(lambda: ib.gather_gemm(xs, wsh)), timed(nccl_fwd)),
+             "dgrad": (timed(lambda: ib.gather_gemm(dy, wsh, b_mn=True)), timed(nccl_dgrad)),
+             "wgrad_rs": (timed(lambda: ib.wgrad_rs(dy, xs, dw, accumulate=False)), timed(nccl_wgrad))}
+        flop_ms = 2.0 * Tl * Nt * K / PEAK_FLOPS * 1e3
+        link_ms = (Nt // world) * K * 2 * (world - 1) / LINK_BPS * 1e3
+        res[f"isp_{name}"] = {"fwd_rel_err": r_f, "dgrad_rel_err": r_d, "wgrad_rel_err": r_w,
+                              **{f"{k}_fused_ms": round(v[0], 4) for k, v in t.items()},
+                              **{f"{k}_nccl+gemm_ms": round(v[1], 4) for k, v in t.items()},
+                              "roofline_ms": round(max(flop_ms, link_ms), 4),
+                              "fwd_frac_of_roofline": round(max(flop_ms, link_ms) / t["fwd"][0], 3)}
     # ---- fused ZeRO kernels: reduce-scatter (mean) + sumsq, AdamW + parameter push
     n = 64 * 1024 * 1024
     gbuf = symm.SymmBuffer(n, torch.bfloat16, group)
