@@ -53,6 +53,40 @@ struct AttnKernelArgs {
     int causal;
 };
 
+// Sequence-parallel form (SP): this rank holds the query rows [rank * t_local, (rank + 1) * t_local) of the packed token
+// stream (cu_seqlens stay GLOBAL) and the K / V rows of every rank are reachable through one tensor map per peer (the
+// peers' symmetric buffers, mapped over NVLink): the K / V producer walks the key tiles of a sequence across rank
+// boundaries inside ONE online-softmax pass - no all-to-all, no ring steps, no LSE merge, no limit on sp vs. kv heads.
+// Key tiles are aligned to GLOBAL multiples of 128 rows (t_local % 128 == 0), so a tile never straddles two peers.
+struct SpArgs {
+    int rank, world, t_local;
+};
+struct PeerMaps {
+    CUtensorMap k[8];
+    CUtensorMap v[8];
+};
+
+// SP: blockIdx -> (sequence, 256-row q block of the part of the sequence that lies in this rank's window)
+B200_DEVICE bool find_qblock_sp(const int* cu, int num_seqs, int idx, int block_rows, int w0, int w1, int& s0, int& len,
+                                int& q_row0, int& q_end, bool reverse = true) {
+    int acc = 0;
+    for (int b = 0; b < num_seqs; ++b) {
+        const int a = cu[b], e = cu[b + 1];
+        const int fa = max(a, w0), fe = min(e, w1);
+        if (fa >= fe) continue;
+        const int nb = (fe - fa + block_rows - 1) / block_rows;
+        if (idx < acc + nb) {
+            s0 = a; len = e - a;
+            const int blk = reverse ? nb - 1 - (idx - acc) : idx - acc;
+            q_row0 = fa - a + blk * block_rows;   // position of the block's first row inside the sequence
+            q_end = fe - a;                       // rows of the sequence beyond this one belong to the next rank
+            return true;
+        }
+        acc += nb;
+    }
+    return false;
+}
+
 // maps blockIdx.x -> (sequence, 256-row q block); heavy (late) blocks of each sequence first for causal balance
 B200_DEVICE bool find_qblock(const int* cu, int num_seqs, int idx, int block_rows, int& seq, int& blk, int& s0, int& len) {
     int acc = 0;
@@ -75,9 +109,11 @@ B200_DEVICE float fast_exp2(float x) {
     return y;
 }
 
+template <bool SP>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                const __grid_constant__ CUtensorMap tmap_v, const AttnKernelArgs args) {
+                const __grid_constant__ CUtensorMap tmap_v, const AttnKernelArgs args, const SpArgs sp,
+                const __grid_constant__ PeerMaps peers) {
     griddep_launch_dependents();  // PDL (launch.h)
     griddep_wait();               // cu_seqlens is read right away: no prologue to overlap here
     extern __shared__ uint8_t smem_raw[];
@@ -94,16 +130,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int seq, blk, s0, len;
+    int seq, blk, s0, len, q_row0, q_end;
     // grid = (heads, q blocks): CTAs are dispatched x-fastest, so the heaviest (latest) q blocks of ALL heads start first
-    if (!find_qblock(args.cu_seqlens, args.num_seqs, blockIdx.y, 2 * TM, seq, blk, s0, len)) return;
+    if constexpr (SP) {
+        if (!find_qblock_sp(args.cu_seqlens, args.num_seqs, blockIdx.y, 2 * TM, sp.rank * sp.t_local,
+                            (sp.rank + 1) * sp.t_local, s0, len, q_row0, q_end))
+            return;
+    } else {
+        if (!find_qblock(args.cu_seqlens, args.num_seqs, blockIdx.y, 2 * TM, seq, blk, s0, len)) return;
+        q_row0 = blk * 2 * TM;  // local row of the block inside the sequence
+        q_end = len;
+    }
     const int h = blockIdx.x;
     const int qpk = args.H / args.Hkv;
     const int hk = h / qpk;
-    const int q_row0 = blk * 2 * TM;  // local row of the block inside the sequence
-    // number of kv tiles: causal -> up to the block's last row
+    // number of kv tiles: causal -> up to the block's last row.  SP: tiles are aligned to global multiples of TN, the first
+    // one may start before the sequence does (those keys are masked)
     const int kv_limit = args.causal ? min(len, q_row0 + 2 * TM) : len;
-    const int n_kv = (kv_limit + TN - 1) / TN;
+    const int jt0 = SP ? s0 / TN : 0;                                   // first global key tile (SP)
+    const int n_kv = SP ? (s0 + kv_limit + TN - 1) / TN - jt0 : (kv_limit + TN - 1) / TN;
+    const int q_tok0 = SP ? s0 + q_row0 - sp.rank * sp.t_local : s0 + q_row0;   // row of the block in the local q / o buffers
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
@@ -129,20 +175,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             for (int t = 0; t < 2; ++t)
                 for (int c = 0; c < 2; ++c)
                     tma_load_2d(smem + FwdSmem::Q + t * TILE_BYTES + c * (TM * 128), &tmap_q, q_full, qcol + c * 64,
-                                s0 + q_row0 + t * TM);
+                                q_tok0 + t * TM);
             const int kcol = (int)((int64_t)hk * args.k_stride_h), vcol = (int)((int64_t)hk * args.v_stride_h);
             int st = 0; uint32_t ph = 0;
             for (int j = 0; j < n_kv; ++j) {
+                const CUtensorMap *mk = &tmap_k, *mv = &tmap_v;
+                int krow = s0 + j * TN;
+                if constexpr (SP) {   // the tile lives on exactly one peer: its map, its local row
+                    const int g = (jt0 + j) * TN, pr = g / sp.t_local;
+                    mk = &peers.k[pr]; mv = &peers.v[pr];
+                    krow = g - pr * sp.t_local;
+                }
                 mbar_wait(&k_empty[st], ph ^ 1);
                 mbar_expect_tx(&k_full[st], TILE_BYTES);
                 for (int c = 0; c < 2; ++c)
-                    tma_load_2d(smem + FwdSmem::K + st * TILE_BYTES + c * (TN * 128), &tmap_k, &k_full[st], kcol + c * 64,
-                                s0 + j * TN);
+                    tma_load_2d(smem + FwdSmem::K + st * TILE_BYTES + c * (TN * 128), mk, &k_full[st], kcol + c * 64, krow);
                 mbar_wait(&v_empty[st], ph ^ 1);
                 mbar_expect_tx(&v_full[st], TILE_BYTES);
                 for (int c = 0; c < 2; ++c)
-                    tma_load_2d(smem + FwdSmem::V + st * TILE_BYTES + c * (TN * 128), &tmap_v, &v_full[st], vcol + c * 64,
-                                s0 + j * TN);
+                    tma_load_2d(smem + FwdSmem::V + st * TILE_BYTES + c * (TN * 128), mv, &v_full[st], vcol + c * 64, krow);
                 if (++st == KV_STAGES) { st = 0; ph ^= 1; }
             }
         }
@@ -212,10 +263,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int j = 0; j < n_kv; ++j) {
             mbar_wait(&s_full[tile], j & 1);
             tc_fence_after();
-            const int kv0 = j * TN;
-            // the causal / length mask only matters on tiles that touch the diagonal or the sequence end
-            const bool need_mask = (kv0 + TN > len) || (args.causal && kv0 + TN - 1 > q_row0 + tile * TM);
+            // key positions relative to the sequence start; SP tiles are globally aligned, so the first one may begin at a
+            // negative position (keys of the previous sequence / rank: masked by kv_min)
+            const int kv0 = SP ? (jt0 + j) * TN - s0 : j * TN;
+            // the causal / length mask only matters on tiles that touch the diagonal or the sequence ends
+            const bool need_mask = (kv0 + TN > len) || (args.causal && kv0 + TN - 1 > q_row0 + tile * TM) || (SP && kv0 < 0);
             const int kv_max = args.causal ? min(row, len - 1) : len - 1;  // last visible kv index for this row
+            const int kv_min = 0;
             // ---- pass 1: row max
             float mx = -INFINITY;
 #pragma unroll 1
@@ -226,7 +280,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 if (need_mask) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                        if (kv0 + c + i <= kv_max) mx = fmaxf(mx, __uint_as_float(r[i]));
+                        if (kv0 + c + i <= kv_max && (!SP || kv0 + c + i >= kv_min)) mx = fmaxf(mx, __uint_as_float(r[i]));
                 } else {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
@@ -270,8 +324,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                     float p0 = fast_exp2(fmaf(__uint_as_float(r[i]), sl2, -mref));
                     float p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), sl2, -mref));
                     if (need_mask) {
-                        if (kv0 + c + i > kv_max) p0 = 0.f;
-                        if (kv0 + c + i + 1 > kv_max) p1 = 0.f;
+                        if (kv0 + c + i > kv_max || (SP && kv0 + c + i < kv_min)) p0 = 0.f;
+                        if (kv0 + c + i + 1 > kv_max || (SP && kv0 + c + i + 1 < kv_min)) p1 = 0.f;
                     }
                     rs += p0 + p1;
                     pk[i >> 1] = pack_bf16(p0, p1);
@@ -287,9 +341,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         // ---- epilogue: O / l -> global, LSE
         mbar_wait(&o_final[tile], 0);
         tc_fence_after();
-        const bool valid = row < len;
+        const bool valid = row < q_end;
         const float inv = (l > 0.f) ? 1.f / l : 0.f;
-        const int64_t tok = (int64_t)s0 + row;
+        const int64_t tok = (int64_t)q_tok0 + (row - q_row0);   // row in the (local) output
         __nv_bfloat16* op = args.o + (tok * args.H + h) * D;
 #pragma unroll 1
         for (int c = 0; c < D; c += 32) {
@@ -341,12 +395,31 @@ int attn_fwd(const AttnDesc& d, cudaStream_t stream) {
     a.scale = d.scale; a.scale_log2 = d.scale * 1.4426950408889634f; a.causal = d.causal;
     static bool attr = false;
     if (!attr) {
-        if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL) != cudaSuccess)
+        if (cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL) !=
+                cudaSuccess ||
+            cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL) !=
+                cudaSuccess)
             return -12;
         attr = true;
     }
     dim3 grid(d.H, upper_qblocks(d.T, d.num_seqs, 2 * TM));
-    launch_pdl(attn_fwd_kernel, dim3(grid), dim3(FWD_THREADS), FwdSmem::TOTAL, stream, 1, tq, tk, tv, a);
+    if (d.sp_world > 1) {
+        // sequence parallel: T is the LOCAL token count, K / V of peer p through its own map (same strides everywhere)
+        if (d.sp_world > 8 || d.T % TN != 0 || d.k_peers == nullptr || d.v_peers == nullptr) return -14;
+        PeerMaps pm;
+        for (int p = 0; p < d.sp_world; ++p) {
+            if (make_tmap_2d_bf16(&pm.k[p], d.k_peers[p], k_row, d.T, k_row, 64, TN)) return -11;
+            if (make_tmap_2d_bf16(&pm.v[p], d.v_peers[p], v_row, d.T, v_row, 64, TN)) return -11;
+        }
+        for (int p = d.sp_world; p < 8; ++p) { pm.k[p] = pm.k[0]; pm.v[p] = pm.v[0]; }
+        SpArgs spa{d.sp_rank, d.sp_world, d.T};
+        launch_pdl(attn_fwd_kernel<true>, dim3(grid), dim3(FWD_THREADS), FwdSmem::TOTAL, stream, 1, tq, tk, tv, a, spa, pm);
+    } else {
+        PeerMaps pm;
+        pm.k[0] = tk;   // unused by the single-rank instantiation
+        launch_pdl(attn_fwd_kernel<false>, dim3(grid), dim3(FWD_THREADS), FwdSmem::TOTAL, stream, 1, tq, tk, tv, a, SpArgs{0, 1, d.T},
+                   pm);
+    }
     return cudaGetLastError() == cudaSuccess ? 0 : -13;
 }
 
@@ -370,6 +443,21 @@ struct BwdSmem {
     static constexpr int LD = DQ + BQ * D * 4;           // 2 x (64 lse2 + 64 delta) floats
     static constexpr int BARS = LD + 2 * 2 * BQ * 4;
     static constexpr int TOTAL = BARS + 256 + 1024;
+};
+
+// sequence-parallel backward: the kv tile is local; the q tiles it meets (this rank's and the later ranks' rows of the same
+// sequence) are read from their owners - Q / dO through per-peer tensor maps, lse / delta through per-peer pointers - and
+// dQ is reduce-added into the owner's fp32 accumulator with a TMA reduce to peer memory.  q tiles are aligned to GLOBAL
+// multiples of 64 rows, so a tile never straddles two peers (t_local % 64 == 0).
+struct BwdPeers {
+    CUtensorMap q[8];
+    CUtensorMap dout[8];
+    CUtensorMap dq[8];
+};
+struct BwdSpArgs {
+    int rank, world, t_local;
+    const float* lse2[8];
+    const float* delta[8];
 };
 
 struct AttnBwdArgs {
@@ -422,10 +510,12 @@ __global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_b
     *reinterpret_cast<uint4*>(dq + t * st + (int64_t)(h / qpk) * sg + (int64_t)(h % qpk) * sh + c) = o;
 }
 
+template <bool SP>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
-                const __grid_constant__ CUtensorMap tmap_dq, const AttnBwdArgs args) {
+                const __grid_constant__ CUtensorMap tmap_dq, const AttnBwdArgs args, const BwdSpArgs sp,
+                const __grid_constant__ BwdPeers peers) {
     griddep_launch_dependents();  // PDL (launch.h)
     griddep_wait();
     extern __shared__ uint8_t smem_raw[];
@@ -446,17 +536,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
     const AttnKernelArgs& f = args.f;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int seq, blk, s0, len;
+    int seq, blk, s0, len, kv0, kv_end;
     // grid = (kv heads, kv tiles): x-fastest dispatch starts the heaviest kv tiles of all heads first (LPT order)
-    if (!find_qblock(f.cu_seqlens, f.num_seqs, blockIdx.y, TN, seq, blk, s0, len)) return;
-    const int nkv = (len + TN - 1) / TN;
-    blk = nkv - 1 - blk;                      // find_qblock reverses; bwd wants early (heavy) kv tiles first
+    if constexpr (SP) {
+        // kv tiles of the sequence fragments inside this rank's window, aligned to the fragment start, early tiles first
+        if (!find_qblock_sp(f.cu_seqlens, f.num_seqs, blockIdx.y, TN, sp.rank * sp.t_local, (sp.rank + 1) * sp.t_local, s0, len,
+                            kv0, kv_end, false))
+            return;
+    } else {
+        if (!find_qblock(f.cu_seqlens, f.num_seqs, blockIdx.y, TN, seq, blk, s0, len)) return;
+        const int nkv = (len + TN - 1) / TN;
+        blk = nkv - 1 - blk;                      // find_qblock reverses; bwd wants early (heavy) kv tiles first
+        kv0 = blk * TN;
+        kv_end = len;
+    }
     const int hk = blockIdx.x;
     const int qpk = f.H / f.Hkv;
-    const int kv0 = blk * TN;
-    const int mq0 = f.causal ? kv0 / BQ : 0;
-    const int nq = (len + BQ - 1) / BQ - mq0;   // q tiles per head
+    // q tiles: non-SP seq-relative index mq (rows s0 + mq * BQ); SP GLOBAL index (rows mq * BQ of the packed stream)
+    const int mq0 = SP ? (f.causal ? (s0 + kv0) / BQ : s0 / BQ) : (f.causal ? kv0 / BQ : 0);
+    const int nq = SP ? (s0 + len + BQ - 1) / BQ - mq0 : (len + BQ - 1) / BQ - mq0;   // q tiles per head
     const int n_steps = nq * qpk;
+    const int w0 = SP ? sp.rank * sp.t_local : 0;   // first global row held locally
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
@@ -483,8 +583,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             const int kcol = (int)((int64_t)hk * f.k_stride_h), vcol = (int)((int64_t)hk * f.v_stride_h);
             mbar_expect_tx(kv_full, 2 * TILE_BYTES);
             for (int c = 0; c < 2; ++c) {
-                tma_load_2d(smem + BwdSmem::K + c * (TN * 128), &tmap_k, kv_full, kcol + c * 64, s0 + kv0);
-                tma_load_2d(smem + BwdSmem::V + c * (TN * 128), &tmap_v, kv_full, vcol + c * 64, s0 + kv0);
+                tma_load_2d(smem + BwdSmem::K + c * (TN * 128), &tmap_k, kv_full, kcol + c * 64, s0 + kv0 - w0);
+                tma_load_2d(smem + BwdSmem::V + c * (TN * 128), &tmap_v, kv_full, vcol + c * 64, s0 + kv0 - w0);
             }
             for (int i = 0; i < n_steps; ++i) {
                 const int st = i % QSTAGES;
@@ -493,11 +593,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 mbar_wait(&qdo_empty[st], ((i / QSTAGES) & 1) ^ 1);
                 mbar_expect_tx(&qdo_full[st], 2 * QT_BYTES);
                 const int qcol = (int)((int64_t)hk * f.q_stride_g + (int64_t)j * f.q_stride_h);
+                const CUtensorMap *mq_map = &tmap_q, *mdo_map = &tmap_do;
+                int qrow = s0 + mq * BQ;
+                if constexpr (SP) {   // the q tile lives on exactly one peer
+                    const int pr = (mq * BQ) / sp.t_local;
+                    mq_map = &peers.q[pr]; mdo_map = &peers.dout[pr];
+                    qrow = mq * BQ - pr * sp.t_local;
+                }
                 for (int c = 0; c < 2; ++c) {
-                    tma_load_2d(smem + BwdSmem::Q + st * QT_BYTES + c * (BQ * 128), &tmap_q, &qdo_full[st], qcol + c * 64,
-                                s0 + mq * BQ);
-                    tma_load_2d(smem + BwdSmem::DO + st * QT_BYTES + c * (BQ * 128), &tmap_do, &qdo_full[st],
-                                h * D + c * 64, s0 + mq * BQ);
+                    tma_load_2d(smem + BwdSmem::Q + st * QT_BYTES + c * (BQ * 128), mq_map, &qdo_full[st], qcol + c * 64, qrow);
+                    tma_load_2d(smem + BwdSmem::DO + st * QT_BYTES + c * (BQ * 128), mdo_map, &qdo_full[st],
+                                h * D + c * 64, qrow);
                 }
             }
         }
@@ -592,9 +698,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         auto load_rowstats = [&](int step, int j, int mq) {
             if (tid < 2 * BQ && step < n_steps) {
                 const int h = hk * qpk + j;
-                const int qi = min(mq * BQ + (tid & (BQ - 1)), len - 1);
-                const float* src = (tid < BQ ? args.lse : args.delta) + (int64_t)h * f.T + s0 + qi;
-                sld[(step & 1) * 2 * BQ + tid] = __ldg(src);
+                if constexpr (SP) {
+                    // rows outside the sequence are masked later; the tile lies inside one peer's buffer, so no clamp
+                    const int pr = (mq * BQ) / sp.t_local;
+                    const int qi = mq * BQ - pr * sp.t_local + (tid & (BQ - 1));
+                    const float* src = (tid < BQ ? sp.lse2[pr] : sp.delta[pr]) + (int64_t)h * f.T + qi;
+                    sld[(step & 1) * 2 * BQ + tid] = *reinterpret_cast<const volatile float*>(src);
+                } else {
+                    const int qi = min(mq * BQ + (tid & (BQ - 1)), len - 1);
+                    const float* src = (tid < BQ ? args.lse : args.delta) + (int64_t)h * f.T + s0 + qi;
+                    sld[(step & 1) * 2 * BQ + tid] = __ldg(src);
+                }
             }
         };
         auto reduce_dq = [&](int step, int j, int mq) {
@@ -615,9 +729,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             fence_proxy_async();
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (issuer) {
+                const CUtensorMap* mdq = &tmap_dq;
+                int qrow = s0 + mq * BQ;
+                if constexpr (SP) {   // the owner's accumulator: a TMA reduce-add into peer memory over NVLink
+                    const int pr = (mq * BQ) / sp.t_local;
+                    mdq = &peers.dq[pr];
+                    qrow = mq * BQ - pr * sp.t_local;
+                }
                 asm volatile(
                     "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
-                    ::"l"(reinterpret_cast<uint64_t>(&tmap_dq)), "r"(smem_u32(stage)), "r"(h * D), "r"(s0 + mq * BQ)
+                    ::"l"(reinterpret_cast<uint64_t>(mdq)), "r"(smem_u32(stage)), "r"(h * D), "r"(qrow)
                     : "memory");
                 tma_store_commit();
             }
@@ -628,14 +749,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int i = 0; i < n_steps; ++i) {
             const int st = i & 1;
             const int mq = cm;
-            const int q0 = mq * BQ + half * 32;   // first q row handled by this warp
+            const int q0 = (SP ? mq * BQ - s0 : mq * BQ) + half * 32;   // first q row (sequence-relative) handled by this warp
             int nj = cj, nm = cm + 1;  // step i + 1
             if (nm == mq0 + nq) { nm = mq0; ++nj; }
             asm volatile("bar.sync 2, 256;" ::: "memory");  // row stats of step i are in smem
             load_rowstats(i + 1, nj, nm);
             const float* lse2 = sld + st * 2 * BQ + half * 32;
             const float* delt = lse2 + BQ;
-            const bool edge = (q0 + 32 > len) || (kv0 + TN > len) || (f.causal && q0 < kv0 + TN);
+            const bool edge = (q0 + 32 > len) || (kv0 + TN > kv_end) || (f.causal && q0 < kv0 + TN) || (SP && q0 < 0);
             uint32_t pk[16];  // P^T row (this warp's 32 q columns), bf16 pairs
             float pf[32];     // the same values in fp32, reused by phase B (no unpack)
             // ---- phase A: P^T = exp2(S^T * scale_log2 - lse2)
@@ -655,11 +776,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                     float p3 = fast_exp2(fmaf(__uint_as_float(x[e + 3]), sl2, -l4.w));
                     if (edge) {
                         const int qa = q0 + e;
-                        const bool kvok = kv < len;
-                        if (!(kvok && qa < len && (!f.causal || kv <= qa))) p0 = 0.f;
-                        if (!(kvok && qa + 1 < len && (!f.causal || kv <= qa + 1))) p1 = 0.f;
-                        if (!(kvok && qa + 2 < len && (!f.causal || kv <= qa + 2))) p2 = 0.f;
-                        if (!(kvok && qa + 3 < len && (!f.causal || kv <= qa + 3))) p3 = 0.f;
+                        const bool kvok = kv < kv_end;
+                        // unsigned compare: a q row before the sequence start (SP: globally aligned tiles) is out, too
+                        if (!(kvok && (unsigned)qa < (unsigned)len && (!f.causal || kv <= qa))) p0 = 0.f;
+                        if (!(kvok && (unsigned)(qa + 1) < (unsigned)len && (!f.causal || kv <= qa + 1))) p1 = 0.f;
+                        if (!(kvok && (unsigned)(qa + 2) < (unsigned)len && (!f.causal || kv <= qa + 2))) p2 = 0.f;
+                        if (!(kvok && (unsigned)(qa + 3) < (unsigned)len && (!f.causal || kv <= qa + 3))) p3 = 0.f;
                     }
                     pk[e >> 1] = pack_bf16(p0, p1);
                     pk[(e >> 1) + 1] = pack_bf16(p2, p3);
@@ -712,8 +834,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         // ---- epilogue: dV, dK rows of this kv tile (each warpgroup-half writes 64 of the 128 head-dim columns)
         mbar_wait(dkv_done, 0);
         tc_fence_after();
-        const bool valid = kv < len;
-        const int64_t tok = (int64_t)s0 + kv;
+        const bool valid = kv < kv_end;
+        const int64_t tok = (int64_t)s0 + kv - w0;
         for (int which = 0; which < 2; ++which) {
             const uint32_t t_src = tmem + (which == 0 ? T_DV : T_DK) + lane_off;
             const float mul = which == 0 ? 1.f : f.scale;
@@ -751,41 +873,71 @@ int attn_bwd(const AttnBwdDesc& b, cudaStream_t stream) {
     const AttnDesc& d = b.f;
     if (d.D != D) return -10;
     if (d.T == 0) return 0;
-    CUtensorMap tq, tk, tv, tdo;
-    if (make_tmap_2d_bf16(&tq, d.q, (uint64_t)d.q_stride_t, d.T, (uint64_t)d.q_stride_t, 64, BQ)) return -11;
-    if (make_tmap_2d_bf16(&tk, d.k, (uint64_t)d.k_stride_t, d.T, (uint64_t)d.k_stride_t, 64, TN)) return -11;
-    if (make_tmap_2d_bf16(&tv, d.v, (uint64_t)d.v_stride_t, d.T, (uint64_t)d.v_stride_t, 64, TN)) return -11;
-    if (make_tmap_2d_bf16(&tdo, b.dout, (uint64_t)d.H * D, d.T, (uint64_t)d.H * D, 64, BQ)) return -11;
-    CUtensorMap tdq;
-    if (make_tmap_2d_f32_noswizzle(&tdq, b.dq_acc, (uint64_t)d.H * D, d.T, (uint64_t)d.H * D, D, BQ)) return -11;
-    {
+    const bool sp = d.sp_world > 1;
+    // phases: 0 = everything (single rank); sequence parallel runs 1 (dO.O row sums + lse*log2e into the symmetric stats
+    // buffer), 2 (main kernel: reads the peers' Q / dO / stats, reduce-adds dQ into the owners' accumulators) and 3 (dQ
+    // fp32 -> bf16) with a device barrier of the sequence group between them (parallel/sp_attention.py)
+    const int phase = b.phase;
+    if (sp && (phase < 1 || phase > 3)) return -15;
+    if (phase == 0 || phase == 1) {
         const int64_t warps = (int64_t)d.T * d.H;
-        launch_pdl(attn_bwd_delta_kernel, dim3((unsigned)((warps * 32 + 255) / 256)), dim3(256), 0, stream, 1, 
+        launch_pdl(attn_bwd_delta_kernel, dim3((unsigned)((warps * 32 + 255) / 256)), dim3(256), 0, stream, 1,
             (const __nv_bfloat16*)b.dout, (const __nv_bfloat16*)d.o, d.lse, b.delta, d.T, d.H);
     }
-    AttnBwdArgs a;
-    a.f.o = (__nv_bfloat16*)d.o; a.f.lse = d.lse; a.f.cu_seqlens = d.cu_seqlens; a.f.num_seqs = d.num_seqs;
-    a.f.T = d.T; a.f.H = d.H; a.f.Hkv = d.Hkv;
-    a.f.q_stride_g = d.q_stride_g ? d.q_stride_g : d.q_stride_h * (d.H / d.Hkv);
-    a.f.q_stride_h = d.q_stride_h; a.f.k_stride_h = d.k_stride_h; a.f.v_stride_h = d.v_stride_h;
-    a.f.scale = d.scale; a.f.scale_log2 = d.scale * 1.4426950408889634f; a.f.causal = d.causal;
-    a.lse = b.delta + (int64_t)d.H * d.T;  // lse * log2e, written by the delta pre-pass
-    a.delta = b.delta; a.dq_acc = b.dq_acc;
-    a.dk = (__nv_bfloat16*)b.dk; a.dv = (__nv_bfloat16*)b.dv;
-    a.dk_stride_t = b.dk_stride_t; a.dk_stride_h = b.dk_stride_h; a.dv_stride_t = b.dv_stride_t; a.dv_stride_h = b.dv_stride_h;
-    static bool attr = false;
-    if (!attr) {
-        if (cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::TOTAL) != cudaSuccess)
-            return -12;
-        attr = true;
+    if (phase == 0 || phase == 2) {
+        CUtensorMap tq, tk, tv, tdo;
+        if (make_tmap_2d_bf16(&tq, d.q, (uint64_t)d.q_stride_t, d.T, (uint64_t)d.q_stride_t, 64, BQ)) return -11;
+        if (make_tmap_2d_bf16(&tk, d.k, (uint64_t)d.k_stride_t, d.T, (uint64_t)d.k_stride_t, 64, TN)) return -11;
+        if (make_tmap_2d_bf16(&tv, d.v, (uint64_t)d.v_stride_t, d.T, (uint64_t)d.v_stride_t, 64, TN)) return -11;
+        if (make_tmap_2d_bf16(&tdo, b.dout, (uint64_t)d.H * D, d.T, (uint64_t)d.H * D, 64, BQ)) return -11;
+        CUtensorMap tdq;
+        if (make_tmap_2d_f32_noswizzle(&tdq, b.dq_acc, (uint64_t)d.H * D, d.T, (uint64_t)d.H * D, D, BQ)) return -11;
+        AttnBwdArgs a;
+        a.f.o = (__nv_bfloat16*)d.o; a.f.lse = d.lse; a.f.cu_seqlens = d.cu_seqlens; a.f.num_seqs = d.num_seqs;
+        a.f.T = d.T; a.f.H = d.H; a.f.Hkv = d.Hkv;
+        a.f.q_stride_g = d.q_stride_g ? d.q_stride_g : d.q_stride_h * (d.H / d.Hkv);
+        a.f.q_stride_h = d.q_stride_h; a.f.k_stride_h = d.k_stride_h; a.f.v_stride_h = d.v_stride_h;
+        a.f.scale = d.scale; a.f.scale_log2 = d.scale * 1.4426950408889634f; a.f.causal = d.causal;
+        a.lse = b.delta + (int64_t)d.H * d.T;  // lse * log2e, written by the delta pre-pass
+        a.delta = b.delta; a.dq_acc = b.dq_acc;
+        a.dk = (__nv_bfloat16*)b.dk; a.dv = (__nv_bfloat16*)b.dv;
+        a.dk_stride_t = b.dk_stride_t; a.dk_stride_h = b.dk_stride_h; a.dv_stride_t = b.dv_stride_t; a.dv_stride_h = b.dv_stride_h;
+        static bool attr = false;
+        if (!attr) {
+            if (cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::TOTAL) !=
+                    cudaSuccess ||
+                cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::TOTAL) !=
+                    cudaSuccess)
+                return -12;
+            attr = true;
+        }
+        dim3 grid(d.Hkv, upper_qblocks(d.T, d.num_seqs, TN));
+        BwdPeers pm;
+        BwdSpArgs spa{d.sp_rank, d.sp_world, d.T, {}, {}};
+        if (sp) {
+            if (d.sp_world > 8 || d.T % TN != 0 || !b.q_peers || !b.dout_peers || !b.dq_acc_peers || !b.delta_peers) return -14;
+            for (int p = 0; p < 8; ++p) {
+                const int s_ = p < d.sp_world ? p : 0;
+                if (make_tmap_2d_bf16(&pm.q[p], b.q_peers[s_], (uint64_t)d.q_stride_t, d.T, (uint64_t)d.q_stride_t, 64, BQ)) return -11;
+                if (make_tmap_2d_bf16(&pm.dout[p], b.dout_peers[s_], (uint64_t)d.H * D, d.T, (uint64_t)d.H * D, 64, BQ)) return -11;
+                if (make_tmap_2d_f32_noswizzle(&pm.dq[p], b.dq_acc_peers[s_], (uint64_t)d.H * D, d.T, (uint64_t)d.H * D, D, BQ))
+                    return -11;
+                spa.delta[p] = reinterpret_cast<const float*>(b.delta_peers[s_]);
+                spa.lse2[p] = spa.delta[p] + (int64_t)d.H * d.T;
+            }
+            launch_pdl(attn_bwd_kernel<true>, dim3(grid), dim3(BWD_THREADS), BwdSmem::TOTAL, stream, 1, tq, tk, tv, tdo, tdq, a, spa,
+                       pm);
+        } else {
+            pm.q[0] = tq;   // unused by the single-rank instantiation
+            launch_pdl(attn_bwd_kernel<false>, dim3(grid), dim3(BWD_THREADS), BwdSmem::TOTAL, stream, 1, tq, tk, tv, tdo, tdq, a, spa,
+                       pm);
+        }
     }
-    dim3 grid(d.Hkv, upper_qblocks(d.T, d.num_seqs, TN));
-    launch_pdl(attn_bwd_kernel, dim3(grid), dim3(BWD_THREADS), BwdSmem::TOTAL, stream, 1, tq, tk, tv, tdo, tdq, a);
-    {
+    if (phase == 0 || phase == 3) {
         const int qpk = d.H / d.Hkv;
         const int64_t n = (int64_t)d.T * d.H * (D / 8);
         const int64_t sg = b.dq_stride_g ? b.dq_stride_g : b.dq_stride_h * qpk;
-        launch_pdl(attn_bwd_dq_convert_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, 1, 
+        launch_pdl(attn_bwd_dq_convert_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, 1,
             b.dq_acc, (__nv_bfloat16*)b.dq, d.T, d.H, qpk, b.dq_stride_t, sg, b.dq_stride_h, d.scale);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -13;

@@ -3,6 +3,7 @@
 #include <ATen/ATen.h>
 #include <ATen/cuda/CUDAContext.h>
 #include <cstring>
+#include <vector>
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/library.h>
 
@@ -304,12 +305,78 @@ void attn_bwd(const Tensor& dout, const Tensor& q, const Tensor& k, const Tensor
     CHECK_RC(b200::attn_bwd(d, cur_stream()), "b200::attn_bwd");
 }
 
+// ---- sequence-parallel attention: K / V (forward) and Q / dO / stats / dQ accumulator (backward) of every rank are read
+// (or reduce-added) in place through peer pointers of symmetric buffers; q / out / lse hold this rank's token rows, cu_seqlens
+// are global.  `k`, `v` (forward) and `q`, `dout`, `delta`, `dq_acc` (backward) must BE this rank's slices of those buffers.
+static std::vector<const void*> as_ptrs(at::IntArrayRef v) {
+    std::vector<const void*> out;
+    for (int64_t p : v) out.push_back(reinterpret_cast<const void*>(p));
+    return out;
+}
+
+void attn_fwd_sp(const Tensor& q, const Tensor& k, const Tensor& v, Tensor& out, Tensor& lse, const Tensor& cu_seqlens,
+                 int64_t max_seqlen, double scale, bool causal, int64_t sp_rank, at::IntArrayRef k_peers,
+                 at::IntArrayRef v_peers) {
+    CHECK_BF16(q); CHECK_BF16(k); CHECK_BF16(v); CHECK_BF16(out);
+    TORCH_CHECK(out.is_contiguous(), "attn: out must be contiguous [T, H, D]");
+    TORCH_CHECK(cu_seqlens.scalar_type() == at::kInt && cu_seqlens.is_contiguous(), "attn: cu_seqlens int32");
+    TORCH_CHECK(k_peers.size() == v_peers.size() && k_peers.size() >= 2 && k_peers.size() <= 8, "attn_fwd_sp: 2..8 peers");
+    c10::cuda::CUDAGuard guard(q.device());
+    b200::AttnDesc d;
+    fill_qkv(d, q, k, v);
+    d.o = out.data_ptr(); d.lse = lse.data_ptr<float>();
+    d.cu_seqlens = cu_seqlens.data_ptr<int>(); d.num_seqs = cu_seqlens.numel() - 1; d.max_seqlen = max_seqlen;
+    d.scale = (float)scale; d.causal = causal;
+    auto kp = as_ptrs(k_peers), vp = as_ptrs(v_peers);
+    d.sp_rank = (int)sp_rank; d.sp_world = (int)k_peers.size(); d.k_peers = kp.data(); d.v_peers = vp.data();
+    CHECK_RC(b200::attn_fwd(d, cur_stream()), "b200::attn_fwd_sp");
+}
+
+void attn_bwd_sp(const Tensor& dout, const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& out, const Tensor& lse,
+                 Tensor& dq, Tensor& dk, Tensor& dv, Tensor& delta, Tensor& dq_acc, const Tensor& cu_seqlens,
+                 int64_t max_seqlen, double scale, bool causal, int64_t phase, int64_t sp_rank, at::IntArrayRef q_peers,
+                 at::IntArrayRef dout_peers, at::IntArrayRef dq_acc_peers, at::IntArrayRef delta_peers) {
+    CHECK_BF16(q); CHECK_BF16(k); CHECK_BF16(v); CHECK_BF16(dout);
+    c10::cuda::CUDAGuard guard(q.device());
+    b200::AttnBwdDesc d;
+    fill_qkv(d.f, q, k, v);
+    d.f.o = const_cast<void*>(out.data_ptr());
+    d.f.lse = const_cast<float*>(lse.data_ptr<float>());
+    d.f.cu_seqlens = cu_seqlens.data_ptr<int>(); d.f.num_seqs = cu_seqlens.numel() - 1; d.f.max_seqlen = max_seqlen;
+    d.f.scale = (float)scale; d.f.causal = causal;
+    TORCH_CHECK(dout.is_contiguous() && out.is_contiguous(), "attn_bwd: dout/out contiguous");
+    TORCH_CHECK(dq.stride(-1) == 1 && dk.stride(2) == 1 && dv.stride(2) == 1, "attn_bwd: grads last dim contiguous");
+    d.dout = dout.data_ptr();
+    d.dq = dq.data_ptr(); d.dq_stride_t = dq.stride(0);
+    if (dq.dim() == 4) { d.dq_stride_g = dq.stride(1); d.dq_stride_h = dq.stride(2); }
+    else { d.dq_stride_h = dq.stride(1); d.dq_stride_g = dq.stride(1) * (d.f.H / d.f.Hkv); }
+    d.dk = dk.data_ptr(); d.dk_stride_t = dk.stride(0); d.dk_stride_h = dk.stride(1);
+    d.dv = dv.data_ptr(); d.dv_stride_t = dv.stride(0); d.dv_stride_h = dv.stride(1);
+    d.delta = delta.data_ptr<float>();
+    d.dq_acc = dq_acc.data_ptr<float>();
+    const size_t W = q_peers.size();
+    TORCH_CHECK(W >= 2 && W <= 8 && dout_peers.size() == W && dq_acc_peers.size() == W && delta_peers.size() == W,
+                "attn_bwd_sp: 2..8 peers");
+    auto qp = as_ptrs(q_peers), dop = as_ptrs(dout_peers), dlp = as_ptrs(delta_peers);
+    std::vector<void*> dqp;
+    for (int64_t p : dq_acc_peers) dqp.push_back(reinterpret_cast<void*>(p));
+    d.f.sp_rank = (int)sp_rank; d.f.sp_world = (int)W;
+    d.phase = (int)phase; d.q_peers = qp.data(); d.dout_peers = dop.data(); d.dq_acc_peers = dqp.data(); d.delta_peers = dlp.data();
+    CHECK_RC(b200::attn_bwd(d, cur_stream()), "b200::attn_bwd_sp");
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // peer-memory communication kernels (pointers come from the symmetric heap, see internevo_b200/parallel/symm.py)
 // ---------------------------------------------------------------------------------------------------------------
 void symm_barrier(int64_t flags_ptrs, int64_t rank, int64_t world, int64_t epoch) {
     CHECK_RC(b200::symm_barrier(reinterpret_cast<uint32_t* const*>(flags_ptrs), rank, world, (uint32_t)epoch, cur_stream()),
              "b200::symm_barrier");
+}
+
+void peer_copy_bench(const Tensor& src, int64_t dst_ptr, int64_t bytes, int64_t piece_bytes, int64_t unroll, int64_t ctas) {
+    c10::cuda::CUDAGuard guard(src.device());
+    CHECK_RC(b200::peer_copy_bench(src.data_ptr(), reinterpret_cast<void*>(dst_ptr), bytes, piece_bytes, (int)unroll, (int)ctas,
+                                   cur_stream()), "b200::peer_copy_bench");
 }
 
 void reduce_scatter_adam(int64_t grad_ptrs, int64_t param_ptrs, int64_t flags_ptrs, int64_t rank, int64_t world,
@@ -600,6 +667,9 @@ TORCH_LIBRARY(b200, m) {
     m.def("clip_scalars(Tensor sumsq_in, Tensor(a!) scalars, float loss_scale, float clip) -> ()", &clip_scalars);
     m.def("attn_fwd(Tensor q, Tensor k, Tensor v, Tensor(a!) out, Tensor(b!) lse, Tensor cu_seqlens, int max_seqlen, float scale, bool causal) -> ()", &attn_fwd);
     m.def("attn_bwd(Tensor dout, Tensor q, Tensor k, Tensor v, Tensor out, Tensor lse, Tensor(a!) dq, Tensor(b!) dk, Tensor(c!) dv, Tensor(d!) delta, Tensor(e!) dq_acc, Tensor cu_seqlens, int max_seqlen, float scale, bool causal) -> ()", &attn_bwd);
+    m.def("peer_copy_bench(Tensor src, int dst_ptr, int bytes, int piece_bytes, int unroll, int ctas) -> ()", &peer_copy_bench);
+    m.def("attn_fwd_sp(Tensor q, Tensor k, Tensor v, Tensor(a!) out, Tensor(b!) lse, Tensor cu_seqlens, int max_seqlen, float scale, bool causal, int sp_rank, int[] k_peers, int[] v_peers) -> ()", &attn_fwd_sp);
+    m.def("attn_bwd_sp(Tensor dout, Tensor q, Tensor k, Tensor v, Tensor out, Tensor lse, Tensor(a!) dq, Tensor(b!) dk, Tensor(c!) dv, Tensor(d!) delta, Tensor(e!) dq_acc, Tensor cu_seqlens, int max_seqlen, float scale, bool causal, int phase, int sp_rank, int[] q_peers, int[] dout_peers, int[] dq_acc_peers, int[] delta_peers) -> ()", &attn_bwd_sp);
     m.def("symm_barrier(int flags_ptrs, int rank, int world, int epoch) -> ()", &symm_barrier);
     m.def("reduce_scatter_adam(int grad_ptrs, int param_ptrs, int flags_ptrs, int rank, int world, int epoch, int shard_off, int shard_n, Tensor(a!) p, Tensor(b!) m, Tensor(c!) v, Tensor scalars, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2, float grad_div, int phase) -> ()", &reduce_scatter_adam);
     m.def("reduce_scatter_adam_mc(int grad_mc, int param_mc, int grad_local, int world, int shard_off, int shard_n, Tensor(a!) p, Tensor(b!) m, Tensor(c!) v, Tensor scalars, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2, float grad_div, int phase) -> ()", &reduce_scatter_adam_mc);

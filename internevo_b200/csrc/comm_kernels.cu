@@ -269,6 +269,46 @@ int reduce_scatter_adam(const RsAdamDesc& d, cudaStream_t s) {
 }
 
 // ----------------------------------------------------------------------------------------------------------------
+// peer-copy micro-benchmark: the inner loop of the all-gather push (gemm_sm100.cu::ag_push_pieces) in isolation, with the
+// number of 16-byte loads a thread keeps in flight as a template parameter.  Used by tools/peer_copy_bench.py to choose
+// the unroll of the production loop; not on any training path.
+// ----------------------------------------------------------------------------------------------------------------
+template <int U>
+__global__ void __launch_bounds__(128) peer_copy_kernel(const uint8_t* __restrict__ src, uint8_t* dst, int64_t bytes,
+                                                        int64_t piece_bytes) {
+    const int t = threadIdx.x;
+    const int64_t pieces = bytes / piece_bytes;
+    for (int64_t p = blockIdx.x; p < pieces; p += gridDim.x) {
+        const uint8_t* s = src + p * piece_bytes;
+        uint8_t* d = dst + p * piece_bytes;
+        for (int64_t o = (int64_t)t * 16; o < piece_bytes; o += (int64_t)U * 2048) {
+            uint4 v[U];
+#pragma unroll
+            for (int j = 0; j < U; ++j)
+                if (o + j * 2048 < piece_bytes) v[j] = ld_nc_v4(s + o + j * 2048);
+#pragma unroll
+            for (int j = 0; j < U; ++j)
+                if (o + j * 2048 < piece_bytes)
+                    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(d + o + j * 2048), "r"(v[j].x), "r"(v[j].y),
+                                 "r"(v[j].z), "r"(v[j].w)
+                                 : "memory");
+        }
+    }
+}
+
+int peer_copy_bench(const void* src, void* dst, int64_t bytes, int64_t piece_bytes, int unroll, int ctas, cudaStream_t s) {
+    const uint8_t* a = reinterpret_cast<const uint8_t*>(src);
+    uint8_t* b = reinterpret_cast<uint8_t*>(dst);
+    switch (unroll) {
+        case 4: peer_copy_kernel<4><<<ctas, 128, 0, s>>>(a, b, bytes, piece_bytes); break;
+        case 8: peer_copy_kernel<8><<<ctas, 128, 0, s>>>(a, b, bytes, piece_bytes); break;
+        case 16: peer_copy_kernel<16><<<ctas, 128, 0, s>>>(a, b, bytes, piece_bytes); break;
+        default: return -1;
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
 // GEMM + collective: thin wrappers over the comm-aware GEMM launch (gemm_sm100.cu)
 // ----------------------------------------------------------------------------------------------------------------
 int gemm_reduce_scatter(const GemmCommDesc& d, cudaStream_t s) {

@@ -10,6 +10,8 @@
 namespace b200 {
 
 int symm_barrier(uint32_t* const* flags_ptrs, int rank, int world, uint32_t epoch, cudaStream_t s);
+// micro-benchmark of the SM-driven peer copy loop (unroll = 16-byte loads in flight per thread: 4, 8 or 16)
+int peer_copy_bench(const void* src, void* dst, int64_t bytes, int64_t piece_bytes, int unroll, int ctas, cudaStream_t s);
 
 struct RsAdamDesc {
     void* const* grad_ptrs = nullptr;    // per-rank bf16 gradient arena (same layout on every rank)

@@ -162,13 +162,16 @@ B200_DEVICE void ag_push_pieces(const CommKernelArgs& c, int64_t row_bytes, bool
         for (int p = blockIdx.x; p < pieces; p += gridDim.x) {
             const uint8_t* src = src0 + (int64_t)p * piece_bytes;
             uint8_t* dst = dst0 + (int64_t)p * piece_bytes;
-            for (int64_t o = (int64_t)t * 16; o < piece_bytes; o += 4 * 128 * 16) {
-                uint4 v[4];
+            // 16 x 16-byte loads in flight per thread: next to a GEMM that saturates L2 the copy needs the depth to keep the
+            // link busy (tools/peer_copy_bench.py: 4 in flight reach 570 GB/s on an idle GPU but starve beside the GEMM)
+            constexpr int U = 16;
+            for (int64_t o = (int64_t)t * 16; o < piece_bytes; o += (int64_t)U * 128 * 16) {
+                uint4 v[U];
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < U; ++j)
                     if (o + j * 2048 < piece_bytes) v[j] = ld_nc_v4(src + o + j * 2048);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < U; ++j)
                     if (o + j * 2048 < piece_bytes) st_v4(dst + o + j * 2048, v[j]);
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");

@@ -12,6 +12,7 @@ Parity targets: ``internlm/model/modules/{embedding,mlp,multi_head_attention}.py
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -147,6 +148,18 @@ def _is_isp() -> bool:
 # ----------------------------------------------------------------------------------------------------------------
 # attention
 # ----------------------------------------------------------------------------------------------------------------
+def _sp_peer_attention_enabled() -> bool:
+    """ISP attention over the sequence group: ``B200_SP_ATTN=peer`` selects the in-kernel peer-K/V kernel, ``a2a`` the
+    Ulysses all-to-all form (reference behaviour); the default is the peer kernel when the peer-memory back-ends are on
+    (``fused_comm``)."""
+    mode = os.environ.get("B200_SP_ATTN", "")
+    if mode == "a2a":
+        return False
+    if not torch.cuda.is_available():
+        return False
+    return mode == "peer" or bool(gpc.config is not None and gpc.config.get("fused_comm", False))
+
+
 class MHA(nn.Module):
     """Causal self-attention over packed sequences with rotary embeddings.
 
@@ -250,6 +263,18 @@ class MHA(nn.Module):
             return self.wo(ctx.reshape(T, -1))
         if q.dim() == 4:  # internlm2 grouped view → [T, H, D] (copy only when a library kernel needs it)
             q = q.reshape(T, -1, D)
+        if sp_group is not None and _ws(sp_group) > 1 and drop_p == 0.0 and _sp_peer_attention_enabled():
+            # sequence-parallel attention with in-kernel peer K / V (parallel/sp_attention.py): no all-to-all at all
+            from internevo_b200.parallel.sp_attention import sp_flash_attention
+
+            cu = cu_seqlens
+            if cu is None:
+                cu = torch.tensor([0, T * _ws(sp_group)], device=x.device, dtype=torch.int32)
+                max_seqlen = T * _ws(sp_group)
+            ctx = sp_flash_attention(q, k, v, cu, max_seqlen, sp_group, causal=self.causal, scale=self.softmax_scale)
+            if ctx is not None:
+                proj = self.out_proj if self.layout == "internlm" else self.wo
+                return proj(ctx.reshape(T, -1))
         if sp_group is not None and _ws(sp_group) > 1:
             # Ulysses: heads scattered, sequence gathered (reference multi_head_attention.py:56-135)
             q = seq_all_to_all(q.contiguous(), sp_group, scatter_dim=1, gather_dim=0)

@@ -13,5 +13,7 @@ def reset_caches() -> None:
         mods["internevo_b200.parallel.linear"].set_fused_backend(None)
     if "internevo_b200.parallel.moe_fused" in mods:
         mods["internevo_b200.parallel.moe_fused"]._backends.clear()
+    if "internevo_b200.parallel.sp_attention" in mods:
+        mods["internevo_b200.parallel.sp_attention"].reset()
     if "internevo_b200.parallel.symm" in mods:
         mods["internevo_b200.parallel.symm"]._flags_cache.clear()
