@@ -96,7 +96,11 @@ B200_DEVICE void item_coords(int item, const GemmKernelArgs& a, int& tm, int& tn
 // A "block" below is a 128-row slab of the output (one CTA's share of a tile): with CG == 2 the pair's tile tm covers
 // blocks 2 tm and 2 tm + 1.  Flags, ownership and staging are all per block, so the 1-CTA and the 2-CTA kernels share the
 // protocol.
-static constexpr int AG_PARTS = 16;  // an all-gather block is pushed as 16 pieces of 8 rows, each with its own flag word
+// An all-gather block (128 rows) is pushed as 16 pieces of 8 rows by different CTAs; every piece adds 1 to the block's
+// arrival COUNTER on the destination.  Counters only grow: call number c of a buffer waits for 16 * c (`comm.epoch` carries
+// that target), so nothing is ever reset and a fast peer that is already pushing call c + 1 cannot be mistaken for call c
+// (its own call-c pieces were counted first).
+static constexpr int AG_PARTS = 16;
 
 struct CommKernelArgs {
     int mode;
@@ -175,10 +179,9 @@ B200_DEVICE void ag_push_pieces(const CommKernelArgs& c, int64_t row_bytes, bool
                     if (o + j * 2048 < piece_bytes) st_v4(dst + o + j * 2048, v[j]);
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (t == 0) {   // publish the piece on its destination
-                fence_acq_rel_sys();
-                st_release_sys(c.flags_ptrs[dest] + (c.rank * blocks_local) * AG_PARTS + p, c.epoch);
-            }
+            // publish the piece on its destination: one arrival on the counter of its 128-row block (release: the CTA's
+            // stores, ordered before this thread by the barrier, are visible before the count)
+            if (t == 0) red_add_release_sys(c.flags_ptrs[dest] + c.rank * blocks_local + p / AG_PARTS, 1u);
         }
     }
 }
@@ -270,6 +273,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             uint64_t ready = 0;  // all-gather: blocks (of the first 64) whose pieces are known to have landed
+            uint64_t ready_hi[4] = {0, 0, 0, 0};   // weight gather along k: blocks 64 .. 319 (index (blk >> 6) & 3, slot 0 unused)
             for (int tile = unit; tile < num_items; tile += grid_ctas) {
                 int tm, tn, n_off, width, g = 0;
                 if constexpr (GRP) { grp_coords<CG>(tile, args, s_off, s_start, g, tm, tn); n_off = 0; width = BN; }
@@ -281,10 +285,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         own_rows = tm / (args.tiles_m / comm.world) == comm.rank;
                         const int blk = tm * CG + cta_rank;
                         if (!own_rows && !(blk < 64 && ((ready >> blk) & 1))) {
-                            // these rows are pushed into the local gathered buffer by their owner's epilogue warps, 16 pieces per
-                            // block: lanes 0..15 each acquire one piece flag
-                            if (lane < AG_PARTS) {
-                                const uint32_t* f = comm.flags_ptrs[comm.rank] + blk * AG_PARTS + lane;
+                            // these rows are pushed into the local gathered buffer by their owner's epilogue warps: wait until
+                            // all 16 pieces of the block have been counted
+                            if (lane == 0) {
+                                const uint32_t* f = comm.flags_ptrs[comm.rank] + blk;
                                 while (static_cast<int32_t>(ld_acquire_sys(f) - comm.epoch) < 0) {
                                 }
                             }
@@ -311,8 +315,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                 map_b = &tmap_bt;
                                 n0 -= comm.rank * comm.m_local;
                             } else if (!(nblk < 64 && ((ready >> nblk) & 1))) {
-                                if (lane < AG_PARTS) {
-                                    const uint32_t* f = comm.flags_ptrs[comm.rank] + nblk * AG_PARTS + lane;
+                                if (lane == 0) {
+                                    const uint32_t* f = comm.flags_ptrs[comm.rank] + nblk;
                                     while (static_cast<int32_t>(ld_acquire_sys(f) - comm.epoch) < 0) {
                                     }
                                 }
@@ -349,15 +353,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             if (seg == 0) {
                                 mb = &tmap_bt;                             // own shard, read in place
                                 kb_off = -comm.rank * comm.m_local;
-                            } else if (kb == seg * kbs && !((ready >> shard) & 1)) {
-                                const int words = (comm.m_local / BM) * AG_PARTS;
-                                const uint32_t* f = comm.flags_ptrs[comm.rank] + shard * words;
-                                for (int i = lane; i < words; i += 32)
-                                    while (static_cast<int32_t>(ld_acquire_sys(f + i) - comm.epoch) < 0) {
+                            } else if ((kk * BK) % BM == 0) {
+                                // entering a new 128-row block of a remote shard: the peers push the blocks of a shard in this
+                                // very order, so the k loop streams behind the push instead of waiting for whole shards
+                                const int wblk = kk * BK / BM;
+                                uint64_t& rdy = wblk < 64 ? ready : ready_hi[(wblk >> 6) & 3];
+                                if (wblk >= 320 || !((rdy >> (wblk & 63)) & 1)) {
+                                    if (lane == 0) {
+                                        const uint32_t* f = comm.flags_ptrs[comm.rank] + wblk;
+                                        while (static_cast<int32_t>(ld_acquire_sys(f) - comm.epoch) < 0) {
+                                        }
                                     }
-                                __syncwarp();
-                                fence_proxy_async_all();
-                                ready |= 1ull << shard;
+                                    __syncwarp();
+                                    fence_proxy_async_all();
+                                    if (wblk < 320) rdy |= 1ull << (wblk & 63);
+                                }
                             }
                         }
                     }

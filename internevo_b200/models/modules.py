@@ -148,16 +148,18 @@ def _is_isp() -> bool:
 # ----------------------------------------------------------------------------------------------------------------
 # attention
 # ----------------------------------------------------------------------------------------------------------------
-def _sp_peer_attention_enabled() -> bool:
-    """ISP attention over the sequence group: ``B200_SP_ATTN=peer`` selects the in-kernel peer-K/V kernel, ``a2a`` the
-    Ulysses all-to-all form (reference behaviour); the default is the peer kernel when the peer-memory back-ends are on
-    (``fused_comm``)."""
+def _sp_peer_attention_enabled(max_seqlen, t_local) -> bool:
+    """ISP attention over the sequence group: ``B200_SP_ATTN=peer`` forces the in-kernel peer-K/V kernel, ``a2a`` the
+    Ulysses all-to-all form (reference behaviour); by default the peer kernel runs when the peer-memory back-ends are on
+    (``fused_comm``) and the longest sequence fits one rank's window."""
     mode = os.environ.get("B200_SP_ATTN", "")
-    if mode == "a2a":
+    if mode == "a2a" or not torch.cuda.is_available():
         return False
-    if not torch.cuda.is_available():
+    if mode == "peer":
+        return True
+    if not (gpc.config is not None and gpc.config.get("fused_comm", False)):
         return False
-    return mode == "peer" or bool(gpc.config is not None and gpc.config.get("fused_comm", False))
+    return max_seqlen is not None and max_seqlen <= t_local
 
 
 class MHA(nn.Module):
@@ -263,7 +265,11 @@ class MHA(nn.Module):
             return self.wo(ctx.reshape(T, -1))
         if q.dim() == 4:  # internlm2 grouped view → [T, H, D] (copy only when a library kernel needs it)
             q = q.reshape(T, -1, D)
-        if sp_group is not None and _ws(sp_group) > 1 and drop_p == 0.0 and _sp_peer_attention_enabled():
+        # peer kernel when no sequence is longer than one rank's window (packed SFT batches: 2.2x faster than the all-to-all
+        # form at sp = 2, profiles/sp_attn_check_n2_r2_v1.json); one long sequence re-reads the earlier ranks' K / V over
+        # NVLink once per q block and is better served by the head-scattered form
+        if sp_group is not None and _ws(sp_group) > 1 and drop_p == 0.0 and _sp_peer_attention_enabled(
+                None if max_seqlen is None else int(max_seqlen), T):
             # sequence-parallel attention with in-kernel peer K / V (parallel/sp_attention.py): no all-to-all at all
             from internevo_b200.parallel.sp_attention import sp_flash_attention
 

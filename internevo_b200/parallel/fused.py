@@ -56,8 +56,7 @@ class TPFusedBackend:
         return (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and M % (256 * self.world) == 0
                 and x.shape[1] % 8 == 0 and weight.shape[0] % 8 == 0 and weight.shape[1] % 8 == 0
                 and x.stride(-1) == 1 and weight.stride(1) == 1
-                and (M // 128) * ((max(weight.shape) + 255) // 256) <= symm.RS_FLAG_WORDS
-                and (M // 128) * 16 <= symm.AG_FLAG_WORDS)
+                and (M // 128) * ((max(weight.shape) + 255) // 256) <= symm.RS_FLAG_WORDS)
 
     def _pp(self, cache, key, numel):
         if key not in cache:
@@ -65,6 +64,19 @@ class TPFusedBackend:
         ent = cache[key]
         ent[0] ^= 1
         return ent[1 + ent[0]]
+
+    def _pp_counted(self, cache, key, numel, blocks):
+        """Ping-pong gathered buffers of one shape plus their arrival counters: one uint32 per 128-row block on every rank,
+        16 arrivals per call, never reset - the call's target count is returned (``csrc/gemm_sm100.cu::AG_PARTS``)."""
+        if key not in cache:
+            cache[key] = [0] + [symm.SymmBuffer(numel, torch.bfloat16, self.group, zero=False) for _ in range(2)] + \
+                [symm.SymmBuffer(max(64, blocks), torch.int32, self.group, zero=True), 0]
+            torch.cuda.synchronize()
+            dist.barrier(self.group)             # every rank's counters are zero before anyone pushes
+        ent = cache[key]
+        ent[0] ^= 1
+        ent[4] += 1
+        return ent[1 + ent[0]], ent[3].table_ptr(0), (16 * ent[4]) & 0xFFFFFFFF
 
     # -- all-gather -> GEMM -----------------------------------------------------------------------------------------
     def ag_gemm(self, x: torch.Tensor, weight: torch.Tensor, group=None, keep_gathered: bool = False,
@@ -77,15 +89,15 @@ class TPFusedBackend:
         m_local, K = x.shape
         N = weight.shape[1] if b_mn else weight.shape[0]
         M = m_local * self.world
-        gb = self._pp(self._gath, (M, K), M * K)
+        gb, counters, target = self._pp_counted(self._gath, (M, K), M * K, M // 128)
         gathered = gb.tensor.view(M, K)
         out = torch.empty(M, N, device=x.device, dtype=x.dtype)
         if symm.DEBUG:
             self.flags.barrier()
             symm.poison(gathered)
             self.flags.barrier()
-        torch.ops.b200.ag_gemm(x, gb.table_ptr(0), symm.ag_flag_table(self.flags), self.rank, self.world,
-                               self.flags.next_epoch(), weight, b_mn, gathered, out, 0, None, 0)
+        torch.ops.b200.ag_gemm(x, gb.table_ptr(0), counters, self.rank, self.world, target, weight, b_mn, gathered, out, 0,
+                               None, 0)
         _bump()
         if symm.DEBUG:
             symm.assert_clean(gathered, "ag_gemm gathered activations")
@@ -172,6 +184,7 @@ class ISPFusedBackend:
         self._stage: Dict[Tuple[int, int], list] = {}
 
     _pp = TPFusedBackend._pp
+    _pp_counted = TPFusedBackend._pp_counted
 
     def supports(self, x: torch.Tensor, w_shard: torch.Tensor) -> bool:
         rows, kin = w_shard.shape
@@ -179,21 +192,20 @@ class ISPFusedBackend:
         return (x.is_cuda and x.dtype == torch.bfloat16 and w_shard.dtype == torch.bfloat16 and x.dim() == 2
                 and rows % 256 == 0 and kin % 8 == 0 and x.stride(-1) == 1 and w_shard.stride(1) == 1
                 and w_shard.stride(0) % 8 == 0
-                and (n_total // 128) * 16 <= symm.AG_FLAG_WORDS
                 and (n_total // 128) * ((kin + 255) // 256) <= symm.RS_FLAG_WORDS)
 
     def gather_gemm(self, x: torch.Tensor, w_shard: torch.Tensor, b_mn: bool = False) -> torch.Tensor:
         rows, kin = w_shard.shape
         n_total = rows * self.world
-        gb = self._pp(self._gath, (n_total, kin), n_total * kin)
+        gb, counters, target = self._pp_counted(self._gath, (n_total, kin), n_total * kin, n_total // 128)
         gathered = gb.tensor.view(n_total, kin)
         out = torch.empty(x.shape[0], kin if b_mn else n_total, device=x.device, dtype=x.dtype)
         if symm.DEBUG:
             self.flags.barrier()
             symm.poison(gathered)
             self.flags.barrier()
-        torch.ops.b200.gather_weight_gemm(x, w_shard, gb.table_ptr(0), gathered, symm.ag_flag_table(self.flags), self.rank,
-                                          self.world, self.flags.next_epoch(), b_mn, out)
+        torch.ops.b200.gather_weight_gemm(x, w_shard, gb.table_ptr(0), gathered, counters, self.rank, self.world, target,
+                                          b_mn, out)
         _bump()
         if symm.DEBUG:
             symm.assert_clean(out, "isp gather_gemm output")
