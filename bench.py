@@ -54,10 +54,66 @@ def parse():
     p.add_argument("--attn", default=None, help="attention implementation override (b200|flash_attn|sdpa)")
     p.add_argument("--fused-comm", type=int, default=-1, help="peer-memory fused collectives (default: on when N>1)")
     p.add_argument("--no-tp2", action="store_true", help="skip the secondary TP=2 + Hybrid-ZeRO measurement (N >= 2)")
+    p.add_argument("--config", default=None, help="benchmark another shipped config file (configs/7B_MoE4_sft.py, "
+                   "configs/7B_isp_sft.py, configs/20B_internlm2.py): its model and parallel layout, synthetic data; the "
+                   "flags below override seq_len / micro_bsz / micro_num / sizes when given")
+    p.add_argument("--pp", type=int, default=0, help="pipeline size override (with --config)")
+    p.add_argument("--segments", type=int, default=1, help="equal-length packed sequences per micro-batch row")
     return p.parse_args()
 
 
+def _plain(x):
+    if isinstance(x, dict):
+        return {k: _plain(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return type(x)(_plain(v) for v in x)
+    return x
+
+
+def build_config_from_file(a, world):
+    """A shipped config file with synthetic data; explicit flags override its batch geometry / parallel sizes."""
+    sys.path.insert(0, ROOT)
+    from internevo_b200.core.context.config import Config
+
+    cfg = _plain(dict(Config.from_file(os.path.join(ROOT, a.config) if not os.path.isabs(a.config) else a.config)))
+    d = cfg["data"]
+    flags = {arg.split("=")[0] for arg in sys.argv[1:] if arg.startswith("--")}
+    if "--seq-len" in flags:
+        d["seq_len"] = a.seq_len
+    if "--micro-bsz" in flags:
+        d["micro_bsz"] = a.micro_bsz
+    if "--micro-num" in flags:
+        d["micro_num"] = a.micro_num
+    d.update(valid_micro_num=d["micro_num"], valid_every=0, total_steps=a.steps + a.warmup + 8, train_folder=None,
+             valid_folder=None, skip_batches="", rampup_batch_size="", empty_cache_and_diag_interval=10**9,
+             diag_outlier_ratio=1.1)
+    par = cfg["parallel"]
+    if a.tp > 0:
+        par["tensor"]["size"] = a.tp
+        if "--tp-mode" in flags:
+            par["tensor"]["mode"] = a.tp_mode
+    if "--wp" in flags:
+        par["weight"]["size"] = a.wp
+    if a.pp > 0:
+        par["pipeline"]["size"] = a.pp
+    if a.checkpoint:
+        cfg["model"]["checkpoint"] = a.checkpoint
+    if "--layers" in flags:     # debug only: fewer layers is NOT the benchmark (reported as such)
+        cfg["model"]["num_layers"] = a.layers
+    cfg["ckpt"] = dict(enable_save_ckpt=False, auto_resume=False)
+    cfg["enable_tb"] = False
+    cfg["monitor"] = dict(alert=dict(enable_feishu_alert=False, feishu_alert_address=None, light_monitor_address=None,
+                                     alert_file_path=None), tensorboard=dict(queue_max_length=10))
+    cfg["lr_scheduler"]["total_steps"] = 1000
+    a.seq_len, a.micro_bsz, a.micro_num = d["seq_len"], d["micro_bsz"], d["micro_num"]
+    a.tp_mode = par["tensor"]["mode"]
+    tp, pp = par["tensor"]["size"], par["pipeline"]["size"]
+    return cfg, tp, world // (tp * pp)
+
+
 def build_config(a, world):
+    if a.config:
+        return build_config_from_file(a, world)
     tp = a.tp if a.tp > 0 else 1
     dp = world // tp
     model = dict(
@@ -140,17 +196,19 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_batches(n, micro_num, T, vocab, pin, seed=1234):
-    """Synthetic packed batches in (pinned) host memory: one 4096-token segment per micro-batch row."""
+def make_batches(n, micro_num, T, vocab, pin, seed=1234, segments=1):
+    """Synthetic packed batches in (pinned) host memory: `segments` equal sequences per micro-batch row of T tokens."""
     import torch
 
     g = torch.Generator().manual_seed(seed)
     out = []
+    seg = T // segments
     for _ in range(n):
         ids = torch.randint(1, vocab, (micro_num, T), generator=g, dtype=torch.long)
         labels = torch.cat([ids[:, 1:], torch.full((micro_num, 1), -100, dtype=torch.long)], 1)
-        cu = torch.tensor([[0, T]] * micro_num, dtype=torch.int32)
-        idx = torch.arange(T, dtype=torch.long).repeat(micro_num, 1)
+        labels[:, seg - 1:: seg] = -100
+        cu = torch.tensor([list(range(0, T + 1, seg))] * micro_num, dtype=torch.int32)
+        idx = torch.arange(seg, dtype=torch.long).repeat(segments).repeat(micro_num, 1)
         d = {"input_ids": ids, "cu_seqlens": cu, "indexes": idx}
         if pin:
             d = {k: v.pin_memory() for k, v in d.items()}
@@ -241,7 +299,7 @@ def run(a, ours: bool):
         import torch
         import torch.distributed as dist
         import internlm as fw  # the unmodified reference package
-        from internlm.core.context import global_context as gpc
+        from internlm.core.context import ParallelMode, global_context as gpc
         from internlm.initialize import initialize_distributed_env
         from internlm.model.losses import FlashGPTLMLoss
         from internlm.model.metrics import AccPerplex
@@ -270,7 +328,10 @@ def run(a, ours: bool):
     T = a.seq_len * a.micro_bsz
     # fresh ids for every step of the run: W warm-up + K device-timed + 1 + K end-to-end steps, every rank its own stream
     n_pool = min(96, a.warmup + 2 * a.steps + 1)
-    host_batches = make_batches(n_pool, a.micro_num, T, MODEL_7B["vocab_size"], pin=True, seed=1234 + 7919 * rank)
+    mdl = cfg["model"]
+    # data-parallel replicas see different batches; the ranks of one model-parallel group (tensor / pipeline / sequence) the same
+    from_seed = 1234 + 7919 * gpc.get_local_rank(ParallelMode.DATA)
+    host_batches = make_batches(n_pool, a.micro_num, T, mdl["vocab_size"], pin=True, seed=from_seed, segments=a.segments)
     dev_batches = [({k: v.cuda() for k, v in d.items()}, l.cuda()) for d, l in host_batches]
 
     skipped = [0]   # the reference arm only reports skipped steps (its loss-scale warm-up is its own business)
@@ -289,6 +350,9 @@ def run(a, ours: bool):
 
     def step_e2e(batch):
         loss = step_dev(batch)  # engine.load_batch copies the pinned host batch to the device (non_blocking)
+        if loss is None:        # pipeline stages other than the last have no loss: read the step's grad-norm flag instead
+            torch.cuda.current_stream().synchronize()
+            return None
         return float(loss)  # device → host read of the step result
 
     for i in range(a.warmup):
@@ -307,17 +371,32 @@ def run(a, ours: bool):
     tokens_per_step = T * a.micro_num * dp
     value = tokens_per_step * a.steps / (ms / 1e3)
     e2e_value = tokens_per_step * a.steps / (e2e_ms / 1e3)
-    tflops = get_megatron_flops(ms / 1e3 / a.steps, checkpoint=bool(a.checkpoint), seq_len=a.seq_len,
-                                hidden_size=a.hidden, num_layers=a.layers, vocab_size=MODEL_7B["vocab_size"],
+    tflops = get_megatron_flops(ms / 1e3 / a.steps, checkpoint=bool(mdl.get("checkpoint", 0)), seq_len=a.seq_len,
+                                hidden_size=mdl["hidden_size"], num_layers=mdl["num_layers"], vocab_size=mdl["vocab_size"],
                                 global_batch_size=a.micro_bsz * a.micro_num * dp, global_world_size=world,
-                                mlp_ratio=MODEL_7B["mlp_ratio"])
+                                mlp_ratio=mdl["mlp_ratio"])
     mem = torch.cuda.max_memory_allocated() / 2**30
     # a step that produced a non-finite loss did not do the benchmark's work (the optimizer skips it): never report it
     for name, val in (("device-timed", last), ("e2e", last_e2e)):
         if ours and val is not None and not math.isfinite(float(val)):
             raise RuntimeError(f"bench: non-finite loss in the {name} loop ({float(val)}); the measurement is invalid")
     if rank == 0:
-        full = a.layers == MODEL_7B["num_layers"] and a.hidden == MODEL_7B["hidden_size"] and a.seq_len == 4096
+        full = (a.layers == MODEL_7B["num_layers"] and a.hidden == MODEL_7B["hidden_size"] and a.seq_len == 4096
+                and not a.config)
+        if a.config:
+            model_name = ("DEBUG (not the benchmark config) " if "--layers" in " ".join(sys.argv) else "") + (f"{os.path.basename(a.config)} (h{mdl['hidden_size']} L{mdl['num_layers']} "
+                          f"H{mdl['num_attention_heads']}/kv{mdl.get('num_kv_attention_heads', mdl['num_attention_heads'])} "
+                          f"mlp{mdl['mlp_ratio']:.3g} V{mdl['vocab_size']}"
+                          + (f" E{mdl['num_experts']}" if mdl.get('num_experts', 1) > 1 else "") + ")")
+        else:
+            model_name = "InternLM2-7B (h4096 L32 H32/kv8 mlp3.5 V92544)" if full else \
+                f"DEBUG h{a.hidden} L{a.layers} (not the benchmark config)"
+        par = cfg["parallel"]
+        layout = f"tp{tp}({a.tp_mode})-dp{dp}-zero{dp}"
+        if par["pipeline"]["size"] > 1:
+            layout += f"-pp{par['pipeline']['size']}"
+        if par.get("weight", {}).get("size", 1) > 1:
+            layout += f"-wp{par['weight']['size']}"
         res = {
             "metric": "tokens_per_second (TGS x n_gpus), InternLM2-7B pre-training step", "value": round(value, 1),
             "unit": "tokens/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -327,11 +406,10 @@ def run(a, ours: bool):
                     "random-init weights",
             "impl": "ours" if ours else "reference",
             "tgs": round(value / world, 1), "tflops_per_gpu": round(tflops, 1),
-            "config": {"model": "InternLM2-7B (h4096 L32 H32/kv8 mlp3.5 V92544)" if full else
-                       f"DEBUG h{a.hidden} L{a.layers} (not the benchmark config)",
+            "config": {"model": model_name,
                        "global_batch": a.micro_bsz * a.micro_num * dp, "seq_len": a.seq_len,
-                       "micro_bsz": a.micro_bsz, "micro_num": a.micro_num,
-                       "parallelism": f"tp{tp}({a.tp_mode})-dp{dp}-zero{dp}", "act_ckpt": a.checkpoint,
+                       "micro_bsz": a.micro_bsz, "micro_num": a.micro_num, "segments_per_row": a.segments,
+                       "parallelism": layout, "act_ckpt": mdl.get("checkpoint", 0),
                        "l2": "working set >> L2: 15.5 GB of bf16 weights + activations are streamed every step",
                        "fused_comm": bool(cfg.get("fused_comm", False)) if ours else None,
                        "zero_overlap": (bool(getattr(optimizer, "_overlap_sync_grad", False)) if ours else None),

@@ -153,37 +153,41 @@ B200_DEVICE int comm_remap_n(int n, int tiles_n, const CommKernelArgs& c, int b_
 // consumes the shards in the order d, d + 1, ..., so shard s goes to s - 1, then s - 2, ... and every destination receives
 // whole shards in exactly the order its GEMM asks for them (a ring schedule at full NVSwitch bandwidth).  `self_copy`
 // appends the local copy (activations: wgrad reads the gathered buffer later; weights are read in place instead).
-B200_DEVICE void ag_push_pieces(const CommKernelArgs& c, int64_t row_bytes, bool self_copy, int t /*0..127*/) {
+struct PushState {
+    int q, p;   // destination index, piece index of the NEXT piece this CTA pushes
+};
+B200_DEVICE bool push_done(const PushState& st, const CommKernelArgs& c, bool self_copy) {
+    return st.q >= c.world - 1 + (self_copy ? 1 : 0);
+}
+// one piece (8 rows) to one destination; all 128 epilogue threads take part (named barrier 1)
+B200_DEVICE void push_one_piece(PushState& st, const CommKernelArgs& c, int64_t row_bytes, int t /*0..127*/) {
     const int blocks_local = c.m_local / BM;
     const int pieces = blocks_local * AG_PARTS;
     const int64_t piece_bytes = (int64_t)(BM / AG_PARTS) * row_bytes;
-    const uint8_t* src0 = reinterpret_cast<const uint8_t*>(c.x_local);
-    const int64_t dst_base = (int64_t)c.rank * c.m_local * row_bytes;
-    const int ndst = c.world - 1 + (self_copy ? 1 : 0);
-    for (int q = 0; q < ndst; ++q) {
-        const int dest = (c.rank - 1 - q + 2 * c.world) % c.world;   // q == world - 1: this rank itself
-        uint8_t* dst0 = reinterpret_cast<uint8_t*>(c.peer_ptrs[dest]) + dst_base;
-        for (int p = blockIdx.x; p < pieces; p += gridDim.x) {
-            const uint8_t* src = src0 + (int64_t)p * piece_bytes;
-            uint8_t* dst = dst0 + (int64_t)p * piece_bytes;
-            // 16 x 16-byte loads in flight per thread: next to a GEMM that saturates L2 the copy needs the depth to keep the
-            // link busy (tools/peer_copy_bench.py: 4 in flight reach 570 GB/s on an idle GPU but starve beside the GEMM)
-            constexpr int U = 16;
-            for (int64_t o = (int64_t)t * 16; o < piece_bytes; o += (int64_t)U * 128 * 16) {
-                uint4 v[U];
+    if (st.p < pieces) {
+        const int dest = (c.rank - 1 - st.q + 2 * c.world) % c.world;   // q == world - 1: this rank itself
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(c.x_local) + (int64_t)st.p * piece_bytes;
+        uint8_t* dst = reinterpret_cast<uint8_t*>(c.peer_ptrs[dest]) + (int64_t)c.rank * c.m_local * row_bytes +
+                       (int64_t)st.p * piece_bytes;
+        // 16 x 16-byte loads in flight per thread: next to a GEMM that saturates L2 the copy needs the depth to keep the
+        // link busy (tools/peer_copy_bench.py: 4 in flight reach 570 GB/s on an idle GPU but starve beside the GEMM)
+        constexpr int U = 16;
+        for (int64_t o = (int64_t)t * 16; o < piece_bytes; o += (int64_t)U * 128 * 16) {
+            uint4 v[U];
 #pragma unroll
-                for (int j = 0; j < U; ++j)
-                    if (o + j * 2048 < piece_bytes) v[j] = ld_nc_v4(src + o + j * 2048);
+            for (int j = 0; j < U; ++j)
+                if (o + j * 2048 < piece_bytes) v[j] = ld_nc_v4(src + o + j * 2048);
 #pragma unroll
-                for (int j = 0; j < U; ++j)
-                    if (o + j * 2048 < piece_bytes) st_v4(dst + o + j * 2048, v[j]);
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            // publish the piece on its destination: one arrival on the counter of its 128-row block (release: the CTA's
-            // stores, ordered before this thread by the barrier, are visible before the count)
-            if (t == 0) red_add_release_sys(c.flags_ptrs[dest] + c.rank * blocks_local + p / AG_PARTS, 1u);
+            for (int j = 0; j < U; ++j)
+                if (o + j * 2048 < piece_bytes) st_v4(dst + o + j * 2048, v[j]);
         }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // publish the piece on its destination: one arrival on the counter of its 128-row block (release: the CTA's
+        // stores, ordered before this thread by the barrier, are visible before the count)
+        if (t == 0) red_add_release_sys(c.flags_ptrs[dest] + c.rank * blocks_local + st.p / AG_PARTS, 1u);
     }
+    st.p += gridDim.x;
+    if (st.p >= pieces) { st.p = blockIdx.x; ++st.q; }
 }
 
 template <int CG>
@@ -273,7 +277,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             uint64_t ready = 0;  // all-gather: blocks (of the first 64) whose pieces are known to have landed
-            uint64_t ready_hi[4] = {0, 0, 0, 0};   // weight gather along k: blocks 64 .. 319 (index (blk >> 6) & 3, slot 0 unused)
             for (int tile = unit; tile < num_items; tile += grid_ctas) {
                 int tm, tn, n_off, width, g = 0;
                 if constexpr (GRP) { grp_coords<CG>(tile, args, s_off, s_start, g, tm, tn); n_off = 0; width = BN; }
@@ -341,33 +344,38 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const int nb64 = width / CG / 64;  // B arrives in 64-row (K-major) or 64-column (MN-major) boxes
                 // every lane walks the k loop (only the weight-gather dgrad has work for lanes 1..31: polling the flags of
                 // the next shard); lane 0 alone waits for free slots and issues the TMA loads
+                // weight gather along k: the walk over the shards is tracked incrementally (the producer lane has ~500 cycles
+                // per k block next to a CTA-pair MMA: no divisions, no local-memory state in this loop)
+                int gk_seg = 0, gk_i = 0, gk_shard = 0, gk_kbs = 1;
+                if constexpr (COMM) {
+                    if (gb_k) { gk_kbs = kb_n / comm.world; gk_shard = comm.rank; }
+                }
                 for (int kb = 0; kb < kb_n; ++kb) {
                     int kk = kb, kb_off = 0;   // k block loaded for A / k offset of the B coordinate
                     const CUtensorMap* mb = map_b;
                     if constexpr (COMM) {
                         if (gb_k) {
-                            const int kbs = kb_n / comm.world;           // k blocks per weight shard
-                            const int seg = kb / kbs;
-                            const int shard = (comm.rank + seg) % comm.world;
-                            kk = shard * kbs + (kb - seg * kbs);
-                            if (seg == 0) {
+                            kk = gk_shard * gk_kbs + gk_i;
+                            if (gk_seg == 0) {
                                 mb = &tmap_bt;                             // own shard, read in place
                                 kb_off = -comm.rank * comm.m_local;
-                            } else if ((kk * BK) % BM == 0) {
-                                // entering a new 128-row block of a remote shard: the peers push the blocks of a shard in this
-                                // very order, so the k loop streams behind the push instead of waiting for whole shards
-                                const int wblk = kk * BK / BM;
-                                uint64_t& rdy = wblk < 64 ? ready : ready_hi[(wblk >> 6) & 3];
-                                if (wblk >= 320 || !((rdy >> (wblk & 63)) & 1)) {
-                                    if (lane == 0) {
-                                        const uint32_t* f = comm.flags_ptrs[comm.rank] + wblk;
-                                        while (static_cast<int32_t>(ld_acquire_sys(f) - comm.epoch) < 0) {
-                                        }
+                            } else if ((gk_i & 1) == 0 && !((ready >> gk_shard) & 1)) {
+                                // entering a new 128-row block (two k blocks) of a remote shard: the peers push the blocks of
+                                // a shard in this very order, so the k loop streams behind the push instead of waiting for
+                                // whole shards.  `ready` holds one bit per SHARD here: set once this CTA has walked it.
+                                if (lane == 0) {
+                                    const uint32_t* f = comm.flags_ptrs[comm.rank] + (kk >> 1);
+                                    while (static_cast<int32_t>(ld_acquire_sys(f) - comm.epoch) < 0) {
                                     }
-                                    __syncwarp();
-                                    fence_proxy_async_all();
-                                    if (wblk < 320) rdy |= 1ull << (wblk & 63);
                                 }
+                                __syncwarp();
+                                fence_proxy_async_all();
+                            }
+                            if (++gk_i == gk_kbs) {
+                                if (gk_seg > 0) ready |= 1ull << gk_shard;
+                                gk_i = 0;
+                                ++gk_seg;
+                                gk_shard = gk_shard + 1 == comm.world ? 0 : gk_shard + 1;
                             }
                         }
                     }
@@ -464,14 +472,31 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         bool rs_mode = false;
         if constexpr (COMM) {
             rs_mode = comm.mode == GEMM_COMM_REDUCE_SCATTER || comm.mode == GEMM_COMM_ALL_REDUCE;
-            // all-gather: push the local shard to every peer first (the MMA warp runs up to two tiles ahead meanwhile)
-            if (comm.mode == GEMM_COMM_ALL_GATHER)
-                ag_push_pieces(comm, (int64_t)args.K * 2, true, static_cast<int>(threadIdx.x) - 64);
-            // weight gather (ISP): the local weight shard [N / W, K_in] goes to every peer's gathered-B buffer
-            if (comm.mode == GEMM_COMM_GATHER_B)
-                ag_push_pieces(comm, (int64_t)(args.b_mn ? args.N : args.K) * 2, false, static_cast<int>(threadIdx.x) - 64);
         }
+        // all-gather forms: the local shard (activations, or the weight shard [N / W, K_in] under ISP) goes to every peer's
+        // gathered buffer, piece by piece, IN BETWEEN the tile epilogues: whenever no accumulator is waiting the epilogue
+        // warps push the next piece, so the tensor cores never stall behind the push and the push never waits for a tile
+        PushState push{0, static_cast<int>(blockIdx.x)};
+        bool pushing = false, push_self = false;
+        int64_t push_row_bytes = 0;
+        if constexpr (COMM) {
+            pushing = comm.mode == GEMM_COMM_ALL_GATHER || comm.mode == GEMM_COMM_GATHER_B;
+            push_self = comm.mode == GEMM_COMM_ALL_GATHER;
+            push_row_bytes = (int64_t)((comm.mode == GEMM_COMM_GATHER_B && args.b_mn) ? args.N : args.K) * 2;
+        }
+        __shared__ int s_tile_ready[2];
+        int poll_par = 0;
         for (int tile = unit; tile < num_items; tile += grid_ctas) {
+            if constexpr (COMM) {
+                while (pushing && !push_done(push, comm, push_self)) {
+                    if (threadIdx.x == 64) s_tile_ready[poll_par] = mbar_try_wait(&tmem_full[acc], acc_phase) ? 1 : 0;
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    const int rdy = s_tile_ready[poll_par];
+                    poll_par ^= 1;
+                    if (rdy) break;
+                    push_one_piece(push, comm, push_row_bytes, static_cast<int>(threadIdx.x) - 64);
+                }
+            }
             int tm, tn, n_off, width, g = 0;
             if constexpr (GRP) { grp_coords<CG>(tile, args, s_off, s_start, g, tm, tn); n_off = 0; width = BN; }
             else item_coords<BN>(tile, args, tm, tn, n_off, width);
@@ -741,6 +766,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 else mbar_arrive(&tmem_empty[acc]);
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if constexpr (COMM) {   // pieces left after the last tile (or a CTA without tiles)
+            while (pushing && !push_done(push, comm, push_self))
+                push_one_piece(push, comm, push_row_bytes, static_cast<int>(threadIdx.x) - 64);
         }
     }
 

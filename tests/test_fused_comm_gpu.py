@@ -87,3 +87,16 @@ def test_isp_fused_linears_track_nccl():
         assert abs(l0 - l1) < 0.02 * abs(l0) + 0.01, (ref, got)
         for (k0, v0), (k1, v1) in zip(n0, n1):
             assert k0 == k1 and abs(v0 - v1) < 0.08 * v0 + 0.02, (ref, got)
+
+
+def test_sequence_parallel_attention_with_peer_kv_matches_single_rank_kernel():
+    """Forward and backward of the sequence-parallel attention kernels (K / V read from the peers' symmetric buffers inside
+    the kernel, dQ reduce-added into its owner over NVLink) against the single-rank kernel on the full sequence: one long
+    sequence, ragged packed sequences crossing rank boundaries at non-aligned rows, many short sequences."""
+    n = 2
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29534", "tools/sp_attn_check.py"], cwd=ROOT,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    res = json.load(open(os.path.join(ROOT, "gpurun_out", f"sp_attn_check_n{n}.json")))
+    assert res["all_ok"], res
