@@ -262,6 +262,82 @@ class InternLM2ForCausalLM(InternLM2PreTrainedModel, GenerationMixin):
         return text, list(history) + [(query, text)]
 
 
+    def stream_chat(self, tokenizer, query: str, history=(), max_new_tokens=1024, do_sample=True, temperature=0.8, top_p=0.8,
+                    meta_instruction="You are an AI assistant whose name is InternLM.", **kwargs):
+        """Generator form of :meth:`chat`: yields ``(response_so_far, history + [(query, response_so_far)])`` every time a
+        new piece of text is available (the contract of the published checkpoints' ``stream_chat``, reference
+        ``transformers/internlm2_model/modeling_internlm2.py:1185``).  ``generate`` runs on a worker thread and hands token ids
+        to this generator through a queue; decoding is incremental, so a multi-byte character split over two tokens is held
+        back until it is complete."""
+        import queue
+        import threading
+
+        inputs = self.build_inputs(tokenizer, query, history, meta_instruction)
+        inputs = {k: v.to(self.device) for k, v in inputs.items() if torch.is_tensor(v)}
+        im_end = tokenizer.convert_tokens_to_ids("<|im_end|>")
+        eos = [tokenizer.eos_token_id] + [i for i in [im_end] if i is not None]
+        q: "queue.Queue" = queue.Queue()
+        done = object()
+
+        class _IdStreamer:   # the `streamer` protocol of generate(): put(token ids) ... end()
+            def __init__(self):
+                self.prompt_seen = False
+
+            def put(self, value):
+                if value.dim() > 1:
+                    if value.shape[0] > 1:
+                        raise ValueError("stream_chat handles one conversation at a time")
+                    value = value[0]
+                if not self.prompt_seen:      # the first call carries the prompt
+                    self.prompt_seen = True
+                    return
+                q.put(value.tolist())
+
+            def end(self):
+                q.put(done)
+
+        failure = []
+
+        def work():
+            try:
+                self.generate(**inputs, max_new_tokens=max_new_tokens, do_sample=do_sample, temperature=temperature,
+                              top_p=top_p, eos_token_id=eos, streamer=_IdStreamer(), **kwargs)
+            except BaseException as e:   # surface the error in the consumer instead of dying silently on the thread
+                failure.append(e)
+                q.put(done)
+
+        threading.Thread(target=work, daemon=True).start()
+        ids, text = [], ""
+        hist = list(history)
+        yield text, hist + [(query, text)]
+        while True:
+            item = q.get()
+            if item is done:
+                break
+            ids.extend(t for t in item if t not in eos)
+            new = tokenizer.decode(ids, skip_special_tokens=True)
+            if new.endswith("\ufffd") or new == text:      # incomplete UTF-8 sequence, or nothing visible yet
+                continue
+            text = new
+            yield text, hist + [(query, text)]
+        if failure:
+            raise failure[0]
+
+
+class InternLM2LinearScalingRotaryEmbedding(InternLM2RotaryEmbedding):
+    """Position-interpolation RoPE (positions divided by ``scaling_factor``); name of the reference / published code."""
+
+    def __init__(self, dim, max_position_embeddings=2048, base=10000, scaling_factor=1.0):
+        super().__init__(dim, max_position_embeddings, base, {"type": "linear", "factor": scaling_factor})
+
+
+class InternLM2DynamicNTKScalingRotaryEmbedding(InternLM2RotaryEmbedding):
+    """Dynamic NTK RoPE (the base grows once the sequence exceeds ``max_position_embeddings``)."""
+
+    def __init__(self, dim, max_position_embeddings=2048, base=10000, scaling_factor=1.0):
+        super().__init__(dim, max_position_embeddings, base, {"type": "dynamic", "factor": scaling_factor})
+
+
 class InternLM2ForSequenceClassification(InternLM2PreTrainedModel):
     """Reward-model style head: score of the last non-pad token (reference ``modeling_internlm2.py`` classification head)."""
 

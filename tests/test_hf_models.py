@@ -154,3 +154,43 @@ def test_convert2hf_installs_remote_code_loadable_with_auto_classes(tmp_path):
     ids = torch.tensor([[1, 5, 9, 13, 40, 41, 7]])
     with torch.no_grad():
         assert torch.allclose(hf(input_ids=ids).logits[0], _framework_logits(model, ids), atol=2e-4, rtol=1e-4)
+
+
+def test_stream_chat_yields_growing_responses_and_rope_scaling_classes():
+    """``stream_chat`` (generator over a worker-thread ``generate``) ends on the same text as ``chat`` with greedy decoding;
+    the named rope-scaling classes are the linear / dynamic-NTK configurations of the one rotary module."""
+    import torch
+    from huggingface.internlm2_model.configuration_internlm2 import InternLM2Config
+    from huggingface.internlm2_model.modeling_internlm2 import (InternLM2DynamicNTKScalingRotaryEmbedding,
+                                                                InternLM2ForCausalLM,
+                                                                InternLM2LinearScalingRotaryEmbedding,
+                                                                InternLM2RotaryEmbedding)
+
+    class Tok:   # the slice of the tokenizer API the chat helpers use: ids are code points folded into the vocabulary
+        bos_token, eos_token_id = "", 2
+
+        def __call__(self, texts, return_tensors="pt"):
+            ids = [[3 + (ord(c) % 90) for c in texts[0]][-24:]]
+            return {"input_ids": torch.tensor(ids), "attention_mask": torch.ones(1, len(ids[0]), dtype=torch.long)}
+
+        def convert_tokens_to_ids(self, t):
+            return 1
+
+        def decode(self, ids, skip_special_tokens=True):
+            return "".join(chr(97 + (int(i) % 26)) for i in ids)
+
+    torch.manual_seed(0)
+    cfg = InternLM2Config(vocab_size=96, hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=4,
+                          num_key_value_heads=2, max_position_embeddings=128, pad_token_id=0)
+    model = InternLM2ForCausalLM(cfg).float().eval()
+    final, hist = model.chat(Tok(), "hi", max_new_tokens=8, do_sample=False)
+    seen = list(model.stream_chat(Tok(), "hi", max_new_tokens=8, do_sample=False))
+    assert seen[0][0] == "" and seen[-1][0] == final and seen[-1][1] == hist
+    lens = [len(r) for r, _ in seen]
+    assert lens == sorted(lens) and len(seen) >= 3
+    pos = torch.arange(0, 300)[None]
+    base = InternLM2RotaryEmbedding(16, 128)(pos, torch.float32)[0]
+    lin = InternLM2LinearScalingRotaryEmbedding(16, 128, scaling_factor=2.0)(pos, torch.float32)[0]
+    ntk = InternLM2DynamicNTKScalingRotaryEmbedding(16, 128, scaling_factor=2.0)(pos, torch.float32)[0]
+    assert torch.allclose(lin[0, 200], base[0, 100], atol=1e-5)          # positions halved
+    assert not torch.allclose(ntk[0, 200], base[0, 200], atol=1e-3)      # base stretched beyond max_position_embeddings
