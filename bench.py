@@ -430,6 +430,16 @@ def run(a, ours: bool):
 
     gc.collect()
     gpc.destroy()
+    if not ours:
+        # the reference's destroy() leaves its RNG registry populated and a second launch in this process would trip its
+        # "Seed for ParallelMode.DATA exists" assertion: clear it with the registry's own reset() (environment handling in the
+        # harness - the reference code itself is untouched)
+        try:
+            from internlm.core.context import random as _ref_random
+
+            _ref_random._SEED_MANAGER.reset()
+        except Exception:
+            pass
     gc.collect()
     torch.cuda.empty_cache()
     return res

@@ -142,6 +142,25 @@ def _b200_available() -> bool:
 
 
 _warned_dropout = False
+_warned_shape = set()
+
+
+def _note_library_attention(q) -> None:
+    """The tcgen05 attention kernels cover bf16 with head_dim 128 (every shipped 7B / 20B config).  Other head dims or
+    dtypes run a LIBRARY kernel (flash-attn, else SDPA): said once per (dtype, head_dim) in the log, and refused outright
+    when ``B200_STRICT_NATIVE=1`` so a benchmark cannot silently measure library code."""
+    key = (str(q.dtype), int(q.shape[-1]))
+    if key in _warned_shape:
+        return
+    _warned_shape.add(key)
+    import logging
+    import os
+
+    msg = (f"attention with dtype {key[0]} / head_dim {key[1]} is outside the native tcgen05 kernels (bf16, head_dim 128): "
+           f"using the flash-attn / SDPA library kernel")
+    if os.environ.get("B200_STRICT_NATIVE", "0") == "1":
+        raise RuntimeError(msg + " (B200_STRICT_NATIVE=1)")
+    logging.getLogger(__name__).warning(msg)
 
 
 def _attention_with_dropout(q, k, v, cu_seqlens, max_seqlen, causal, scale, dropout_p):
@@ -194,6 +213,8 @@ def flash_attention_varlen(q, k, v, cu_seqlens, max_seqlen: int, causal: bool = 
         cu_seqlens = cu_seqlens.int()
     if impl == "b200" and q.dtype == torch.bfloat16 and q.shape[-1] == 128 and _b200_available():
         return _B200AttnFn.apply(q, k, v, cu_seqlens.contiguous(), int(max_seqlen), float(scale), bool(causal))
+    if impl == "b200" and q.is_cuda:
+        _note_library_attention(q)
     if impl in ("b200", "flash_attn"):
         try:
             from flash_attn import flash_attn_varlen_func
