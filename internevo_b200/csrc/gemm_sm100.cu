@@ -13,6 +13,7 @@
 #include "gemm_sm100.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -35,7 +36,7 @@ struct GemmCfg {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = (BN / CG) * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator
+    static constexpr int TMEM_COLS = 2 * BN <= 256 ? 256 : 512;  // double-buffered accumulator (allocations are powers of 2)
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
     static constexpr int SMEM_BYTES_COMM = SMEM_BYTES + 4 * 8192;  // + per-warp transpose staging of the RS push
 };
@@ -210,7 +211,7 @@ template <int BN, bool COMM, int CG = 1, bool GRP = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_bt, const GemmKernelArgs args, const CommKernelArgs comm) {
-    static_assert(CG == 1 || BN == 256, "2-CTA tiles: BN = 256");
+    static_assert(CG == 1 || BN == 256 || BN == 192, "2-CTA tiles: BN = 256, or 192 for a K-major B (wave quantisation)");
     static_assert(!(GRP && COMM), "grouped GEMM has no fused collective");
     __shared__ int s_off[GRP ? MAX_GROUPS + 1 : 1], s_start[GRP ? MAX_GROUPS + 1 : 1];
     using Cfg = GemmCfg<BN, CG>;
@@ -893,6 +894,10 @@ static int num_sms() {
     return g_num_sms;
 }
 
+static int g_bn192 = [] {
+    const char* e = std::getenv("B200_GEMM_BN192");
+    return !(e && e[0] == '0');
+}();
 static int g_tail_split = 1;
 static int g_group_m = 0;  // 0 = default (8)
 void set_gemm_tail_split(int on) { g_tail_split = on; }
@@ -1103,7 +1108,25 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     // pick the narrower tile when the 256-wide grid would leave SMs idle
     const int tiles256 = ((g.M + BM - 1) / BM) * ((g.N + 255) / 256);
     const bool use128 = g.force_bn == 128 || (g.force_bn == 0 && tiles256 < num_sms());
-    // default for large problems: 256 x 256 tile on a CTA pair (cta_group::2); force_bn 512 / 256 / 128 pin a variant
+    // default for large problems: 256 x 256 tile on a CTA pair (cta_group::2); force_bn 512 / 384 / 256 / 128 pin a variant
+    // (512 = pair x 256 columns, 384 = pair x 192 columns)
+    if (g.force_bn == 384) {
+        if (g.b_mn_major) return -5;   // MN-major B arrives in 64-column boxes: 96 columns per CTA do not tile
+        return launch<192, 2>(g, stream);
+    }
+    if (g.force_bn == 0 && !use128 && g.max_ctas == 0 && !g.b_mn_major && g_bn192) {
+        // Wave quantisation: the pair grid runs ceil(tiles / 74) rounds.  With M = 4096 (one micro-batch) a 256-wide n tile
+        // leaves e.g. wqkv (N = 6144) at 384 tiles = 5.19 rounds -> 6; 192-wide tiles make it 512 tiles = 6.92 rounds -> 7
+        // of 3/4 the work: 12 % fewer tensor cycles.  Chosen when the modelled cost is at least 3 % lower (the 256-wide
+        // tile amortises the A operand and the epilogue better, and its tail wave can be split).
+        const int units = num_sms() / 2;
+        const int tm = (g.M + 2 * BM - 1) / (2 * BM);
+        const int t256 = tm * ((g.N + 255) / 256), t192 = tm * ((g.N + 191) / 192);
+        const double r256 = (t256 % units == 0 || t256 < units) ? (double)((t256 + units - 1) / units)
+                                                                : t256 / units + 0.6;   // split tail: ~0.6 of a round
+        const double c256 = r256 * 256.0, c192 = (double)((t192 + units - 1) / units) * 192.0;
+        if (c192 < 0.97 * c256) return launch<192, 2>(g, stream);
+    }
     if (g.force_bn == 512 || (g.force_bn == 0 && !use128 && g.max_ctas == 0)) return launch<256, 2>(g, stream);
     return use128 ? launch<128>(g, stream) : launch<256>(g, stream);
 }

@@ -50,7 +50,7 @@ def check_gemm():
         a = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
         b = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
         ref = a.float() @ b.float().t()
-        for bn in (256, 128, 512):  # 512 = 256x256 tile on a CTA pair (cta_group::2)
+        for bn in (256, 128, 512, 384):  # 512 / 384 = 256x256 / 256x192 tile on a CTA pair (cta_group::2)
             out = ops.matmul(a, b, force_bn=bn)
             allok &= err_report(f"NT  {M}x{N}x{K} bn{bn}", out, ref, 1e-2)
         if M % 8 == 0:
@@ -77,7 +77,7 @@ def check_gemm():
     b = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
     bias = torch.randn(N, device=dev, dtype=torch.bfloat16)
     ref = a.float() @ b.float().t()
-    for bn in (128, 256, 512):
+    for bn in (128, 256, 512, 384):
         allok &= err_report(f"bias bn{bn}", ops.matmul(a, b, bias=bias, force_bn=bn), ref + bias.float(), 1e-2)
         allok &= err_report(f"fp32 out bn{bn}", ops.matmul(a, b, out_dtype=torch.float32, force_bn=bn), ref, 1e-3)
         acc = torch.randn(M, N, device=dev, dtype=torch.float32)
@@ -172,7 +172,9 @@ def gemm_perf():
         Bt = b if b_mn else b.t()
         row = {"case": name, "M": M, "N": N, "K": K}
         # variants are measured round-robin (3 rounds) so that clock / power drift hits all of them alike
-        variants = {"ours_2cta": (512, 1), "ours_2cta_nosplit": (512, 0), "ours_bn256": (256, 1), "ours_bn128": (128, 1)}
+        variants = {"ours_default": (0, 1), "ours_2cta": (512, 1), "ours_2cta_nosplit": (512, 0), "ours_bn256": (256, 1)}
+        if not b_mn:
+            variants["ours_2cta_bn192"] = (384, 1)
         acc = {k: [] for k in list(variants) + ["cublas"]}
         for _ in range(3):
             for key, (bn, split) in variants.items():
