@@ -8,3 +8,5 @@ timeout 300 $NCU -k regex:gemm_bf16_kernel -s 6 -c 1 -f -o gpurun_out/grouped_ge
 python tools/run_grouped_once.py 2>&1 | tail -1
 timeout 120 python tools/kernel_check.py attn 2>&1 | tail -6
 ls -la gpurun_out/*.ncu-rep
+timeout 200 python tools/kernel_check.py gemm 2>&1 | tail -4
+timeout 400 python tools/kernel_check.py gemm_perf 2>&1 | tail -12

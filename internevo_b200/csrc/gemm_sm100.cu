@@ -894,9 +894,12 @@ static int num_sms() {
     return g_num_sms;
 }
 
+// The 256 x 192 pair tile is OFF by default: measured (profiles/gemm_perf_r2_v1_bn192.json) it runs at ~70 % of the 256-wide
+// tile's rate per tile (1090 vs 1553 TFLOPS on 8192^3), which eats the wave-quantisation gain it was meant to buy (wqkv
+// forward: 1206 vs 1191 / 1240 without tail split).  B200_GEMM_BN192=1 turns the model-based choice on, force_bn = 384 pins it.
 static int g_bn192 = [] {
     const char* e = std::getenv("B200_GEMM_BN192");
-    return !(e && e[0] == '0');
+    return (e && e[0] == '1') ? 1 : 0;
 }();
 static int g_tail_split = 1;
 static int g_group_m = 0;  // 0 = default (8)
