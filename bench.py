@@ -491,6 +491,12 @@ def main():
             import gc
 
             gc.collect()
+            # a FRESH rendezvous store for the second layout: the first one's store still holds the keys of its process
+            # groups (NCCL unique ids by group name), and a re-initialisation that finds them connects to communicators
+            # that no longer exist - observed as a hang at 8 ranks.  Rank 0 therefore serves a new TCPStore on another port
+            # instead of reusing the launcher's (agent) store.
+            os.environ["MASTER_PORT"] = str(int(os.environ.get("MASTER_PORT", "29500")) + 37)
+            os.environ.pop("TORCHELASTIC_USE_AGENT_STORE", None)
             sub = run(_tp2_args(a), ours=a.impl != "reference")
             if rank0 and sub is not None:
                 keep = ("value", "unit", "ms_per_step", "tgs", "tflops_per_gpu", "e2e", "gpu_launches", "last_loss",
