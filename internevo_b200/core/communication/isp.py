@@ -107,7 +107,8 @@ class ISPCommunicator:
                 j = i - 1 if backward else i + 1
                 if 0 <= j < len(self._order):
                     nxt = self._order[j]
-                    if id(nxt) not in self._gathered and not getattr(nxt, "_b200_isp_fused", False):
+                    fused_fwd, fused_bwd = getattr(nxt, "_b200_isp_fused", (False, False))
+                    if id(nxt) not in self._gathered and not (fused_bwd if backward else fused_fwd):
                         self._gathered[id(nxt)] = self._launch_gather(nxt, nxt.weight, async_op=True)
         return out
 

@@ -196,6 +196,18 @@ class ISPFusedBackend:
                 and w_shard.stride(0) % 8 == 0
                 and (n_total // 128) * ((kin + 255) // 256) <= symm.RS_FLAG_WORDS)
 
+    def prefer(self, op: str) -> bool:
+        """Whether the in-kernel form of ``op`` ("fwd" | "dgrad" | "wgrad") is the faster one at this group size - from
+        ``profiles/fused_comm_check_n{2,8}_r2_*.json``: the forward wins at 2 and 8 ranks, the wgrad reduce-scatter at 2 (and is
+        assumed to at 4), the dgrad only ties at 2 and loses at 8 where the per-rank tiles are few.  ``B200_ISP_FUSED_BWD=1``
+        / ``0`` forces both backward forms on / off."""
+        force = os.environ.get("B200_ISP_FUSED_BWD", "")
+        if op == "fwd" or force == "1":
+            return True
+        if force == "0":
+            return False
+        return self.world <= (2 if op == "dgrad" else 4)
+
     def gather_gemm(self, x: torch.Tensor, w_shard: torch.Tensor, b_mn: bool = False) -> torch.Tensor:
         rows, kin = w_shard.shape
         n_total = rows * self.world

@@ -167,7 +167,8 @@ class _ISPLinearFn(torch.autograd.Function):
         be = _isp_fused(x, weight, module)
         ctx.fused = be
         if be is not None:
-            module._b200_isp_fused = True    # the communicator does not prefetch (NCCL-gather) this module's weight
+            # the communicator does not prefetch (NCCL-gather) this module's weight where the GEMM gathers it itself
+            module._b200_isp_fused = (True, be.prefer("dgrad"))      # (forward, backward)
             y = be.gather_gemm(x, weight)
             if bias is not None:
                 y = y + communicator.all_gather_weight(module, bias, is_bias=True)
@@ -186,9 +187,18 @@ class _ISPLinearFn(torch.autograd.Function):
         dy = dy.contiguous()
         be = ctx.fused
         dw = db = None
-        if be is not None:
-            dx = be.gather_gemm(dy, weight, b_mn=True) if ctx.needs_input_grad[0] else None
-            if ctx.needs_input_grad[1]:
+        dx = None
+        # the collective runs inside the GEMM where that form is the faster one at this group size (ISPFusedBackend.prefer);
+        # otherwise the communicator's NCCL gather (prefetched) / reduce-scatter path is taken per operation
+        if ctx.needs_input_grad[0]:
+            if be is not None and be.prefer("dgrad"):
+                dx = be.gather_gemm(dy, weight, b_mn=True)
+            else:
+                w_full = comm.all_gather_weight(module, weight, is_bias=False, backward=True)
+                dx = _mm_dgrad(dy, w_full)
+                comm.release_weight(module)
+        if ctx.needs_input_grad[1]:
+            if be is not None and be.prefer("wgrad"):
                 buf = getattr(weight, "grad_buf", None)
                 if buf is not None:
                     be.wgrad_rs(dy, x, buf, accumulate=getattr(weight, "grad_ready", False))
@@ -199,11 +209,7 @@ class _ISPLinearFn(torch.autograd.Function):
                 else:
                     dw = torch.empty_like(weight)
                     be.wgrad_rs(dy, x, dw, accumulate=False)
-        else:
-            w_full = comm.all_gather_weight(module, weight, is_bias=False, backward=True)
-            dx = _mm_dgrad(dy, w_full) if ctx.needs_input_grad[0] else None
-            comm.release_weight(module)
-            if ctx.needs_input_grad[1]:
+            else:
                 if dy.is_cuda and dy.dtype == torch.bfloat16:
                     dw_full = ops.matmul(dy, x, a_mn=True, b_mn=True)
                 else:
