@@ -480,11 +480,11 @@ def main():
         # result - with the reason - and the process exits instead of hanging the driver
         def bail():
             if rank0 and res is not None:
-                res["tp2"] = {"unavailable": "secondary layout did not finish within 420 s"}
+                res["tp2"] = {"unavailable": "secondary layout did not finish within 300 s"}
                 print(json.dumps(res), flush=True)
             os._exit(0)
 
-        dog = threading.Timer(420.0, bail)
+        dog = threading.Timer(300.0, bail)
         dog.daemon = True
         dog.start()
         try:
