@@ -97,7 +97,11 @@ def _run_layout(rank, world, folder, phase, kw, moe):
     from internevo_b200.core.context import ParallelMode, global_context as gpc
     from internevo_b200.core.trainer import TrainState
 
+    kw = dict(kw)
+    bucket = kw.pop("overlap_bucket", None)
     cfg = tiny_config(num_layers=2, micro_num=2, **kw)
+    if bucket:   # Hybrid-ZeRO with many small ranges reduced from the grad hooks: optimizer shards are range-interleaved
+        cfg["hybrid_zero_optimizer"].update(overlap_sync_grad=True, reduce_bucket_size=bucket)
     if moe:
         cfg["model"].pop("no_bias", None)
         cfg["model"].pop("num_kv_attention_heads", None)
@@ -143,6 +147,8 @@ import pytest  # noqa: E402
     ("tp2_pp2", 4, dict(tp=2, pp=2), False),
     ("isp_sp2_wp2", 2, dict(tp=2, wp=2, mode="isp"), False),
     ("moe_ep2", 2, dict(model_type="INTERNLM_MoE", num_experts=4, moe_type="MegaBlock-D"), True),  # dropless: no gate noise
+    # range-interleaved optimizer shards (many ranges, reduction overlapped with backward) must resume bit-exactly, too
+    ("dp2_zero2_overlap", 2, dict(zero1=2, overlap_bucket=4096), False),
     # MoE x pipeline: every stage numbers its blocks from 0 - the per-expert files must carry GLOBAL layer ids
     ("moe_pp2", 2, dict(pp=2, model_type="INTERNLM_MoE", num_experts=4, moe_type="MegaBlock-D"), True),
 ])
