@@ -141,3 +141,76 @@ def layout_for_rank(rank: int, s: ParallelSizes, gqa: bool = False) -> Dict[Para
             if rank in ranks:
                 res[mode] = ranks
     return res
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ``Initializer_*`` facade: user code written against the reference instantiates one class per group kind and calls
+# ``init_dist_group()`` → ``(local_rank, group_world_size, process_group, cpu_group, ranks_in_group, mode)`` (two such tuples
+# for the expert kinds).  Here every class is the SAME few lines around ``group_rank_lists``; only the mode and, for the ISP /
+# expert / GQA flavours, a detail of the sizes differ.
+# ---------------------------------------------------------------------------------------------------------------------
+class ProcessGroupInitializer:
+    MODE: ParallelMode = ParallelMode.GLOBAL
+    ISP = False
+
+    def __init__(self, rank: int, world_size: int, weight_parallel_size: int, weight_data_parallel_size: int,
+                 sequence_parallel_size: int, data_parallel_size: int, pipeline_parallel_size: int,
+                 tensor_parallel_size: int, zero1_parallel_size: int, nettest_parallel_size: int,
+                 expert_parallel_size: int):
+        assert sequence_parallel_size == tensor_parallel_size, "the sequence group is the tensor group"
+        self.rank, self.world_size = rank, world_size
+        self.weight_parallel_size, self.weight_data_parallel_size = weight_parallel_size, weight_data_parallel_size
+        self.sequence_parallel_size, self.data_parallel_size = sequence_parallel_size, data_parallel_size
+        self.pipeline_parallel_size, self.tensor_parallel_size = pipeline_parallel_size, tensor_parallel_size
+        self.zero1_parallel_size, self.nettest_parallel_size = zero1_parallel_size, nettest_parallel_size
+        self.expert_parallel_size = expert_parallel_size
+
+    def sizes(self) -> ParallelSizes:
+        return ParallelSizes(world=self.world_size, pipeline=self.pipeline_parallel_size, tensor=self.tensor_parallel_size,
+                             weight=self.weight_parallel_size, zero1=self.zero1_parallel_size,
+                             num_experts=max(1, self.expert_parallel_size), isp=self.ISP,
+                             nettest=self.nettest_parallel_size)
+
+    def _build(self, mode: ParallelMode, use_cpu: bool):
+        """Create every group of ``mode`` (all ranks must do so, in the same order) and return this rank's tuple."""
+        import torch.distributed as dist
+
+        mine = None
+        for ranks in group_rank_lists(mode, self.sizes()):
+            group = dist.new_group(ranks) if dist.is_initialized() and len(ranks) > 1 else None
+            cpu = None
+            if use_cpu and dist.is_initialized() and len(ranks) > 1:
+                cpu = dist.new_group(ranks, backend="gloo") if dist.get_backend() != "gloo" else group
+            if self.rank in ranks:
+                mine = (ranks.index(self.rank), len(ranks), group, cpu, list(ranks), mode)
+        assert mine is not None, f"rank {self.rank} is in no {mode} group"
+        return mine
+
+    def init_dist_group(self, use_cpu: bool = False):
+        return self._build(self.MODE, use_cpu)
+
+
+def _initializer(name: str, mode: ParallelMode, isp: bool = False, doc: str = ""):
+    cls = type(name, (ProcessGroupInitializer,), {"MODE": mode, "ISP": isp, "__doc__": doc})
+    return cls
+
+
+Initializer_Pipeline = _initializer("Initializer_Pipeline", ParallelMode.PIPELINE, doc="ranks with the same position in every stage")
+Initializer_Tensor = _initializer("Initializer_Tensor", ParallelMode.TENSOR, doc="contiguous ranks")
+Initializer_Weight = _initializer("Initializer_Weight", ParallelMode.WEIGHT, isp=True, doc="contiguous ranks (ISP weight shards)")
+Initializer_Data = _initializer("Initializer_Data", ParallelMode.DATA, doc="same tensor position, stride = tensor size")
+Initializer_Weight_Data = _initializer("Initializer_Weight_Data", ParallelMode.WEIGHT_DATA, isp=True,
+                                       doc="same weight position, stride = weight size")
+Initializer_Zero1 = _initializer("Initializer_Zero1", ParallelMode.ZERO1, doc="ZeRO sub-groups inside the data group")
+Initializer_Zero1_ISP = _initializer("Initializer_Zero1_ISP", ParallelMode.ZERO1, isp=True,
+                                     doc="ZeRO sub-groups inside the weight-data group")
+Initializer_Nettest = _initializer("Initializer_Nettest", ParallelMode.NETTEST, doc="blocks of `nettest` ranks")
+Initializer_Zero3_dp = _initializer("Initializer_Zero3_dp", ParallelMode.ZERO3_DP, doc="same position inside the FSDP group")
+Initializer_GQA = _initializer("Initializer_GQA", ParallelMode.GQA, doc="tensor ranks that share a kv head")
+
+
+class Initializer_Expert_Data(ProcessGroupInitializer):
+    """Expert and expert-data groups together (the reference returns both tuples from one call)."""
+
+    def init_dist_group(self, use_cpu: bool = False):
+        return [self._build(ParallelMode.EXPERT, use_cpu), self._build(ParallelMode.EXPERT_DATA, use_cpu)]

@@ -86,3 +86,28 @@ def test_seed_manager_modes_are_independent_streams():
     torch.manual_seed(1024)
     ref = torch.rand(6)
     assert torch.equal(torch.cat([a1, a2]), ref) and not torch.equal(a1, b1)
+
+
+def test_initializer_classes_are_views_of_the_layout_table():
+    """The reference's ``Initializer_*`` API (one class per group kind, ``init_dist_group()`` → tuple) on top of the layout
+    table: no process group is created without an initialised backend, the rank sets are the table's."""
+    from internevo_b200.core.context.process_groups import (Initializer_Data, Initializer_Expert_Data, Initializer_Pipeline,
+                                                            Initializer_Tensor, Initializer_Zero1, ParallelMode)
+
+    args = dict(world_size=16, weight_parallel_size=1, weight_data_parallel_size=8, sequence_parallel_size=2,
+                data_parallel_size=4, pipeline_parallel_size=2, tensor_parallel_size=2, zero1_parallel_size=2,
+                nettest_parallel_size=32, expert_parallel_size=1)
+    for rank in range(16):
+        lr, n, group, cpu, ranks, mode = Initializer_Tensor(rank, **args).init_dist_group()
+        assert mode is ParallelMode.TENSOR and ranks == [rank // 2 * 2, rank // 2 * 2 + 1] and ranks[lr] == rank and n == 2
+        assert group is None and cpu is None
+        lr, n, _, _, ranks, _ = Initializer_Pipeline(rank, **args).init_dist_group()
+        assert ranks == [rank % 8, rank % 8 + 8] and ranks[lr] == rank
+        lr, n, _, _, ranks, _ = Initializer_Data(rank, **args).init_dist_group()
+        assert n == 4 and ranks == [rank // 8 * 8 + rank % 2 + 2 * k for k in range(4)]
+        lr, n, _, _, ranks, _ = Initializer_Zero1(rank, **args).init_dist_group()
+        assert n == 2 and rank in ranks and all((r - rank) % 2 == 0 for r in ranks)
+    margs = dict(args, pipeline_parallel_size=1, tensor_parallel_size=1, sequence_parallel_size=1, data_parallel_size=16,
+                 zero1_parallel_size=16, weight_data_parallel_size=16, expert_parallel_size=4)
+    ep, edp = Initializer_Expert_Data(6, **margs).init_dist_group()
+    assert ep[4] == [4, 5, 6, 7] and edp[4] == [2, 6, 10, 14] and ep[5] is ParallelMode.EXPERT
