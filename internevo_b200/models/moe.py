@@ -279,14 +279,32 @@ class GShardMOELayer(BaseMoELayer):
         return fused_capacity_combine(out, w, be, plan)
 
 
+def _make_experts(num_local, hidden_size, mlp_ratio, device, dtype, expert_tensor_parallel):
+    """Local expert MLPs.  Default: every tensor rank holds the whole expert (replicated over the tensor group, grouped
+    GEMM path).  ``moe.expert_tensor_parallel=True`` shards every expert's hidden dimension over the tensor group the way the
+    dense MLP is sharded - column-parallel w1 / w3, row-parallel w2, the mode's collectives inside the linears - which is what
+    the reference's experts do (``moe/gshard_layer.py:423-427`` builds them on the TENSOR group; ``megablock/mlp.py:37-40``)."""
+    group, mode = None, "mtp"
+    if expert_tensor_parallel and gpc.is_initialized(ParallelMode.TENSOR) and gpc.get_world_size(ParallelMode.TENSOR) > 1:
+        mode = gpc.config.parallel["tensor"].get("mode", "mtp") if gpc.config is not None else "mtp"
+        assert mode != "isp", "expert_tensor_parallel needs a tensor mode (mtp / msp / fsp); under isp experts stay replicated"
+        group = gpc.get_group(ParallelMode.TENSOR)
+    experts = [FeedForward(hidden_size, int(hidden_size * mlp_ratio), out_features=hidden_size, process_group=group,
+                           bias=False, device=device, dtype=dtype, tp_mode=mode) for _ in range(num_local)]
+    if group is not None:
+        for e in experts:
+            for p in e.parameters():
+                p.expert_tp_sharded = True   # not a replica over the tensor group: no broadcast, no replica-grad reduction
+    return experts
+
+
 @MOE_INITIALIZER.register_module("GShard")
 def _build_gshard(hidden_size, num_experts, ep_group, ep_size, mlp_ratio, device, dtype, top_k=1, capacity_factor=1.0,
                   eval_capacity_factor=1.0, min_capacity=4, noisy_gate_policy=None, drop_tokens=True, use_rts=True,
-                  **unused):
+                  expert_tensor_parallel=False, **unused):
     assert noisy_gate_policy is None or noisy_gate_policy in ("None", "Jitter", "RSample")
     num_local = num_experts // ep_size
-    experts = [FeedForward(hidden_size, int(hidden_size * mlp_ratio), out_features=hidden_size, process_group=None,
-                           bias=False, device=device, dtype=dtype) for _ in range(num_local)]
+    experts = _make_experts(num_local, hidden_size, mlp_ratio, device, dtype, expert_tensor_parallel)
     gate = TopKGate(hidden_size, num_experts, top_k, capacity_factor, eval_capacity_factor, min_capacity,
                     noisy_gate_policy, drop_tokens, use_rts, device=device)
     return GShardMOELayer(hidden_size, gate, Experts(experts, num_local, f"moe_ep_size_{ep_size}"), ep_group, ep_size,
@@ -417,10 +435,9 @@ def _build_megablock(**kw):
 
 @MOE_INITIALIZER.register_module("MegaBlock-D")
 def _build_megablock_d(hidden_size, num_experts, ep_group, ep_size, mlp_ratio, device, dtype, top_k=1,
-                       noisy_gate_policy=None, **unused):
+                       noisy_gate_policy=None, expert_tensor_parallel=False, **unused):
     num_local = num_experts // ep_size
-    experts = [FeedForward(hidden_size, int(hidden_size * mlp_ratio), out_features=hidden_size, process_group=None,
-                           bias=False, device=device, dtype=dtype) for _ in range(num_local)]
+    experts = _make_experts(num_local, hidden_size, mlp_ratio, device, dtype, expert_tensor_parallel)
     return DroplessMOELayer(hidden_size, num_experts, ep_group, ep_size, Experts(experts, num_local, f"moe_ep_size_{ep_size}"),
                             top_k=top_k, noisy_gate_policy=noisy_gate_policy, device=device)
 

@@ -433,6 +433,8 @@ class HybridZeroOptimizer:
         if not is_using_sequence_parallel() and not self.use_isp:
             return
         mode = ParallelMode.WEIGHT if self.use_isp else ParallelMode.TENSOR
+        if g.dp_mode is ParallelMode.EXPERT_DATA and g.params and getattr(g.params[0], "expert_tp_sharded", False):
+            return   # tensor-sharded experts: the parallel linears already produce every shard's complete gradient
         if g.dp_mode is ParallelMode.EXPERT_DATA:
             # experts are replicated over the tensor (sequence) group - they are neither tensor- nor weight-sharded here; under
             # sequence parallelism each of those ranks routed a different sequence shard through them, so their gradients are
@@ -476,7 +478,9 @@ class HybridZeroOptimizer:
         if g.dp_mode is ParallelMode.EXPERT_DATA:
             if _group_size(ParallelMode.EXPERT) > 1:
                 dist.all_reduce(g.sumsq, group=gpc.get_group(ParallelMode.EXPERT))
-        replicated_experts = g.dp_mode is ParallelMode.EXPERT_DATA   # same gradient on every tensor / weight rank
+        # replicated experts: the same gradient on every tensor / weight rank (tensor-sharded experts add their shards)
+        replicated_experts = g.dp_mode is ParallelMode.EXPERT_DATA and not (
+            g.params and getattr(g.params[0], "expert_tp_sharded", False))
         if _group_size(model_mode) > 1 and not (self.use_isp and g.dp_mode is ParallelMode.DATA) and not replicated_experts:
             dist.all_reduce(g.sumsq, group=gpc.get_group(model_mode))
         return g.sumsq

@@ -78,8 +78,8 @@ def sync_model_replica_param_group(model):
     for param in model.parameters():
         if is_replica_zero_parallel_parameter(param):
             _bcast(param.data, mode)
-        elif is_expert_param(param):
-            # MoE experts are not tensor- / weight-sharded in this framework: every tensor (sequence) rank holds the same
+        elif is_expert_param(param) and not getattr(param, "expert_tp_sharded", False):
+            # replicated experts (the default; `moe.expert_tensor_parallel` shards them instead): every tensor (sequence) rank holds the same
             # copy, which must start identical (the tensor-parallel RNG stream differs per rank) and stays identical
             # (HybridZeroOptimizer._reduce_replica_grads)
             _bcast(param.data, ParallelMode.TENSOR)
