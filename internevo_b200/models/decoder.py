@@ -66,7 +66,7 @@ LLAMA_SPEC = FamilySpec("LLAMA2", "llama", "attention", "feed_forward", "attenti
 def _tp_mode() -> str:
     if gpc.config is None:
         return "mtp"
-    t = gpc.config.parallel["tensor"]
+    t = gpc.config.get("parallel", {}).get("tensor", None)   # a partial config (tools, unit tests) means plain mtp
     return t.get("mode", "mtp") if isinstance(t, dict) else "mtp"
 
 

@@ -303,7 +303,8 @@ def test_grouped_swiglu_mlp_matches_the_per_expert_loop():
     from internevo_b200.core.context import Config, global_context as gpc
     from internevo_b200.models.modules import FeedForward
 
-    gpc.set_config(Config(dict(parallel=dict(sequence_parallel=False))))
+    prev_cfg = gpc.config
+    gpc.set_config(Config(dict(parallel=dict(sequence_parallel=False, tensor=dict(size=1, mode="mtp")))))
     torch.manual_seed(2)
     h, F_, El = 32, 64, 3
     experts = [FeedForward(h, F_, out_features=h, process_group=None, bias=False, dtype=torch.float32, multiple_of=32)
@@ -336,6 +337,7 @@ def test_grouped_swiglu_mlp_matches_the_per_expert_loop():
         w13g = experts[e].w13.weight.grad if experts[e].w13.weight.grad is not None else torch.zeros_like(got[2][e])
         w2g = experts[e].w2.weight.grad if experts[e].w2.weight.grad is not None else torch.zeros_like(got[3][e])
         assert torch.allclose(got[2][e], w13g, atol=1e-4) and torch.allclose(got[3][e], w2g, atol=1e-4)
+    gpc._config = prev_cfg      # this test runs in-process: leave the global context as it was found
 
 
 def _sharded_expert_matches_dense(rank, world):
