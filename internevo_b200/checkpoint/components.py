@@ -108,12 +108,35 @@ def save_model_checkpoint(folder, model):
         topo_fn = fn.replace("model_", "topo_").replace(".pt", ".json")
         topo_path = os.path.join(folder, topo_fn)
         get_storage_manager()._client(topo_path)[0].upload_bytes(topo.encode(), try_get_storage_backend(topo_path)[1])
+    _write_expert_files(folder, experts, tp)
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+
+
+def _write_expert_files(folder, experts: dict, tp: int) -> None:
     # experts are replicated over EXPERT_DATA: rank 0 of that group writes
     if experts and (not gpc.is_initialized(ParallelMode.EXPERT_DATA) or gpc.get_local_rank(ParallelMode.EXPERT_DATA) == 0):
         for (layer, e), st in experts.items():
             llm_save(os.path.join(folder, f"model_moe_layer{layer}_expert{e}_tp{tp}.pt"), saved_obj=st)
-    if torch.cuda.is_available():
-        torch.cuda.synchronize()
+
+
+def try_save_moe_checkpoint(folder, model, tp_rank=None, pp_rank=None) -> None:  # noqa: ARG001
+    """Write ``model_moe_layer{L}_expert{E}_tp{t}.pt`` for every (global layer, global expert) this rank holds - the expert half
+    of ``save_model_checkpoint`` on its own (reference ``checkpoint/components.py:53-92``).  ``pp_rank`` is accepted for
+    signature parity: the global layer id comes from the chunk's ``start_layer_idx``, which also covers interleaved chunks."""
+    if gpc.config.model.get("num_experts", 1) <= 1 or folder is None:
+        return
+    states = {k: v.detach().clone().cpu() if torch.is_tensor(v) else v for k, v in get_shard_state_dict(model).items()}
+    _, experts = _split_expert_states(states, _chunk_layer_offsets(model))
+    _write_expert_files(folder, experts, gpc.get_local_rank(ParallelMode.TENSOR) if tp_rank is None else tp_rank)
+
+
+def try_load_moe_checkpoint(folder, model, state_dict: dict, tp_rank=None, pp_rank=None) -> dict:  # noqa: ARG001
+    """Merge this rank's expert files (this stage's layers x this rank's experts, keys back in local numbering) into
+    ``state_dict`` and return it (reference ``checkpoint/components.py:31-50``)."""
+    if gpc.config.model.get("num_experts", 1) > 1:
+        state_dict.update(_load_expert_files(folder, get_fns(folder), model))
+    return state_dict
 
 
 def _load_expert_files(folder, fns, model) -> dict:
@@ -157,8 +180,7 @@ def load_model_checkpoint(folder, model):
     assert tp_size == max_tp + 1, f"The weights are save for {max_tp + 1} parallelism, while current has {tp_size}"
     fp = os.path.join(folder, _model_fn())
     states = llm_load(fp, map_location="cpu")
-    if gpc.config.model.get("num_experts", 1) > 1:
-        states.update(_load_expert_files(folder, fns, model))
+    try_load_moe_checkpoint(folder, model, states)
     missing_k, unexpected_keys = load_shard_state_dict(model, states, strict=False)
     lost = [k for k in missing_k if _EXPERT_KEY.match(k)]
     assert not lost, f"expert weights missing from the checkpoint (they would keep their random init): {lost[:4]}..."

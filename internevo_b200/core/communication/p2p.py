@@ -65,10 +65,17 @@ def process_object_to_send(obj, scatter_gather_tensors):
     return [process_object_to_send(o, scatter_gather_tensors) for o in obj]
 
 
-def _ops_for(obj, peer, send: bool, group=None):
-    fn = dist.isend if send else dist.irecv
+def filling_ops_queue(obj, comm_op, comm_rank, ops_queue, group=None) -> None:
+    """Append one ``P2POp`` per tensor of ``obj`` (a tensor or a list of tensors) to ``ops_queue`` - the building block of
+    ``batch_isend_irecv`` exchanges (reference ``core/communication/p2p.py:79-86``)."""
     objs = obj if isinstance(obj, (list, tuple)) else [obj]
-    return [dist.P2POp(fn, o, peer, group) for o in objs]
+    ops_queue.extend(dist.P2POp(comm_op, o, comm_rank, group) for o in objs)
+
+
+def _ops_for(obj, peer, send: bool, group=None):
+    ops: list = []
+    filling_ops_queue(obj, dist.isend if send else dist.irecv, peer, ops, group)
+    return ops
 
 
 def _communicate_async(object_send_next=None, object_send_prev=None, recv_prev=False, recv_next=False,

@@ -24,6 +24,12 @@ from internevo_b200 import ops
 from internevo_b200.core.context import ParallelMode
 from internevo_b200.core.context import global_context as gpc
 from internevo_b200.ops.attention import flash_attention_packed, flash_attention_varlen
+from internevo_b200.ops.rope import (  # noqa: F401  (reference names, embedding.py:89-283)
+    ApplyRotaryEmb,
+    ApplyRotaryEmbQKV_,
+    apply_rotary_emb,
+    apply_rotary_emb_qkv_,
+)
 from internevo_b200.ops.swiglu import swiglu_interleaved_bwd
 from internevo_b200.parallel.functional import (
     gather_forward_split_backward,

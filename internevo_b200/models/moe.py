@@ -517,3 +517,43 @@ def top2gating(logits, capacity_factor, min_capacity):
 AllToAll = _AllToAll
 MegaBlockMoE = GShardMOELayer           # capacity raised to the busiest expert's load: see _build_megablock
 MegaBlockdMoE = DroplessMOELayer
+
+
+def einsum(rule: str, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """The handful of contractions of the dense GShard formulation written as broadcasts / matmuls (they map to GEMMs instead
+    of the generic einsum planner), anything else falls through to ``torch.einsum`` (reference ``gshard_layer.py:75-112``)."""
+    if rule == "s,se->se":
+        return a.reshape(-1, 1) * b
+    if rule == "se,sc->sec":
+        return a.unsqueeze(2) * b.unsqueeze(1)
+    if rule == "se,se->s":
+        return (a * b).sum(-1)
+    if rule == "sec,sm->ecm":
+        s_, e_, c_ = a.shape
+        return (a.reshape(s_, e_ * c_).t() @ b).reshape(e_, c_, b.shape[1])
+    if rule == "sec,ecm->sm":
+        return a.reshape(a.shape[0], -1) @ b.reshape(-1, b.shape[-1])
+    if rule == "ks,ksm->sm":
+        return (a.unsqueeze(-1) * b).sum(0)
+    return torch.einsum(rule, a, b)
+
+
+# MegaBlocks-style functional API (sdd / dsd over the grouped GEMM, expert MLP modules): reference ``moe/megablock/utils.py``, ``mlp.py``
+from .megablock import (  # noqa: E402,F401
+    BlockDiagonal,
+    MegaBlockFeedForward,
+    MegaBlockGroupedFeedForward,
+    TensorParallelBmm,
+    TensorParallelDsdNn,
+    TensorParallelSddNt,
+    Topology,
+    WeightParallelDsdNn,
+    WeightParallelSddNt,
+    act_fn,
+    check_megablock_installed,
+    check_stk_installed,
+    dsd_nn,
+    promote_scalar,
+    sdd_nt,
+    tensor_parallel_bmm,
+)

@@ -26,3 +26,14 @@ def get_job_name():
 
 def get_job_key():
     return f"{get_job_id()}_{get_job_name()}"
+
+
+def try_import_send_exception():
+    """The optional site-specific exception reporter: ``uniscale_monitoring.send_exception_msg`` when that (proprietary)
+    package is importable, else ``None`` and the caller falls back to the webhook alert (reference ``monitor/utils.py:37-47``)."""
+    import importlib
+
+    try:
+        return getattr(importlib.import_module("uniscale_monitoring"), "send_exception_msg", None)
+    except ImportError:
+        return None

@@ -105,3 +105,108 @@ def apply_rotary_packed(x: torch.Tensor, pos: Optional[torch.Tensor], cos: torch
     """Autograd-aware in-place RoPE on ``[T, heads, D]`` or, with ``head_dim``, on the flat ``[T, heads * D]`` projection
     output (the InternLM2 packed wqkv viewed as heads)."""
     return _RopeFn.apply(x, pos, cos, sin, group, rot_per_group, interleaved, head_dim or x.shape[-1])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# flash-attn style autograd functions kept for code written against the reference (``internlm/model/modules/embedding.py:
+# 89-170`` ``ApplyRotaryEmb``: out of place on ``[b, s, heads, d]``; ``:172-283`` ``ApplyRotaryEmbQKV_``: in place on q and k of
+# a packed ``[total, 3, heads, d]`` or padded ``[b, s, 3, heads, d]`` qkv).  Full-width rotations of bf16 CUDA tensors go
+# through ``rope_`` (one launch for q and k together); partial ``rotary_dim`` and separate key tables use the fp32 formula.
+# ---------------------------------------------------------------------------------------------------------------------
+def _rotate_prefix_(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, interleaved: bool, conj: bool) -> None:
+    """Rotate the first ``2 * cos.shape[-1]`` features of ``x [..., rows, heads, d]`` in place; ``cos`` / ``sin`` are
+    ``[rows, rd / 2]`` (broadcast over the leading dims and the heads)."""
+    rd = cos.shape[-1] * 2
+    c, s = cos.float().unsqueeze(-2), sin.float().unsqueeze(-2)
+    if conj:
+        s = -s
+    ro = x[..., :rd]
+    x1, x2 = (ro[..., 0::2], ro[..., 1::2]) if interleaved else (ro[..., : rd // 2], ro[..., rd // 2:])
+    a, b = x1.float(), x2.float()
+    o1, o2 = (a * c - b * s).to(x.dtype), (a * s + b * c).to(x.dtype)
+    x1.copy_(o1)
+    x2.copy_(o2)
+
+
+def _native_full_width(x: torch.Tensor, cos: torch.Tensor) -> bool:
+    return _lib.use_native(x) and x.dtype == torch.bfloat16 and x.is_contiguous() and cos.shape[-1] * 2 == x.shape[-1] \
+        and cos.dtype == torch.float32
+
+
+class ApplyRotaryEmb(torch.autograd.Function):
+    """``out = rope(x)`` for ``x [batch, seqlen, heads, d]`` with tables ``[>= seqlen, rotary_dim / 2]`` (positions 0..s-1)."""
+
+    @staticmethod
+    def forward(ctx, x, cos, sin, interleaved=False):
+        b, s, _, d = x.shape
+        assert cos.shape == sin.shape and cos.shape[0] >= s and cos.shape[1] * 2 <= d
+        ctx.save_for_backward(cos, sin)
+        ctx.interleaved = interleaved
+        out = x.clone(memory_format=torch.contiguous_format)
+        ApplyRotaryEmb._run(out, cos, sin, interleaved, False)
+        return out
+
+    @staticmethod
+    def _run(t, cos, sin, interleaved, conj):
+        b, s, h, d = t.shape
+        if _native_full_width(t, cos):
+            pos = torch.arange(s, device=t.device, dtype=torch.int32).repeat(b)
+            rope_(t.view(b * s, h, d), pos, cos.contiguous(), sin.contiguous(), 1, 1, conj, interleaved)
+        else:
+            _rotate_prefix_(t, cos[:s], sin[:s], interleaved, conj)
+
+    @staticmethod
+    def backward(ctx, do):
+        cos, sin = ctx.saved_tensors
+        dx = do.clone(memory_format=torch.contiguous_format)
+        ApplyRotaryEmb._run(dx, cos, sin, ctx.interleaved, True)
+        return dx, None, None, None
+
+
+class ApplyRotaryEmbQKV_(torch.autograd.Function):
+    """In-place RoPE of q and k inside ``qkv``: packed ``[total, 3, heads, d]`` with per-token tables ``[total, rd / 2]``, or
+    padded ``[b, s, 3, heads, d]`` with tables indexed by position."""
+
+    @staticmethod
+    def forward(ctx, qkv, cos, sin, cos_k=None, sin_k=None, interleaved=False):
+        packed = qkv.dim() == 4
+        assert qkv.shape[1 if packed else 2] == 3
+        ctx.save_for_backward(cos, sin, cos_k, sin_k)
+        ctx.interleaved = interleaved
+        ApplyRotaryEmbQKV_._run(qkv, cos, sin, cos_k, sin_k, interleaved, False)
+        ctx.mark_dirty(qkv)
+        return qkv
+
+    @staticmethod
+    def _run(qkv, cos, sin, cos_k, sin_k, interleaved, conj):
+        packed = qkv.dim() == 4
+        same = cos_k is None and sin_k is None
+        if packed:
+            total, _, h, d = qkv.shape
+            if same and _native_full_width(qkv, cos) and cos.shape[0] >= total:
+                # heads 0..h-1 are q, h..2h-1 are k, 2h..3h-1 are v: one launch rotates the first two thirds of every row
+                rope_(qkv.view(total, 3 * h, d), None, cos.contiguous(), sin.contiguous(), 3 * h, 2 * h, conj, interleaved)
+                return
+            _rotate_prefix_(qkv[:, 0], cos[:total], sin[:total], interleaved, conj)
+            _rotate_prefix_(qkv[:, 1], (cos if cos_k is None else cos_k)[:total], (sin if sin_k is None else sin_k)[:total],
+                            interleaved, conj)
+        else:
+            b, s, _, h, d = qkv.shape
+            if same and _native_full_width(qkv, cos):
+                pos = torch.arange(s, device=qkv.device, dtype=torch.int32).repeat(b)
+                rope_(qkv.view(b * s, 3 * h, d), pos, cos.contiguous(), sin.contiguous(), 3 * h, 2 * h, conj, interleaved)
+                return
+            _rotate_prefix_(qkv[:, :, 0], cos[:s], sin[:s], interleaved, conj)
+            _rotate_prefix_(qkv[:, :, 1], (cos if cos_k is None else cos_k)[:s], (sin if sin_k is None else sin_k)[:s],
+                            interleaved, conj)
+
+    @staticmethod
+    def backward(ctx, dqkv):
+        cos, sin, cos_k, sin_k = ctx.saved_tensors
+        dqkv = dqkv.contiguous()
+        ApplyRotaryEmbQKV_._run(dqkv, cos, sin, cos_k, sin_k, ctx.interleaved, True)
+        return dqkv, None, None, None, None, None
+
+
+apply_rotary_emb = ApplyRotaryEmb.apply
+apply_rotary_emb_qkv_ = ApplyRotaryEmbQKV_.apply

@@ -211,3 +211,18 @@ def Silu(w1_o, w2_o):
 
 def is_moe_param(param) -> bool:
     return getattr(param, "is_expert", False)
+
+
+# The functional dense API (``fused_dense_func`` & co., reference ``model/utils.py:31-69,220-660``) lives in ``parallel/dense.py``
+# which needs ``parallel/linear.py`` which imports this module: resolved on first access.
+_DENSE_NAMES = ("ReduceScatterFunc", "AllReduceFunc", "reduce_scatter", "all_reduce", "linear_bias_wgrad_torch",
+                "FusedDenseFunc", "MegatronFusedDenseFunc", "ISPFusedDenseFunc", "fused_dense_func",
+                "megatron_fused_dense_func", "isp_fused_dense_func")
+
+
+def __getattr__(name):
+    if name in _DENSE_NAMES:
+        from . import dense
+
+        return getattr(dense, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

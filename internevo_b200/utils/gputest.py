@@ -53,6 +53,33 @@ def empty_cache_and_diag(batch_count, interval=50):
         gc.collect()
 
 
+def benchmark_forward(test_fn, *inputs, repeats: int = 100, amp: bool = True, amp_dtype=torch.float16, warmup: int = 3,
+                      **kwinputs) -> float:
+    """Mean seconds per call of ``test_fn(*inputs, **kwinputs)`` (forward only, under autocast when ``amp``): CUDA events
+    around ``repeats`` back-to-back launches after ``warmup`` untimed ones; the host clock on CPU.  Same contract as the
+    reference helper built on ``torch.utils.benchmark`` (``utils/gputest.py:60-80``) without its per-call synchronisation."""
+    import time
+
+    on_gpu = torch.cuda.is_available()
+    ctx = torch.autocast(device_type="cuda" if on_gpu else "cpu", dtype=amp_dtype if on_gpu else torch.bfloat16, enabled=amp)
+    with torch.no_grad(), ctx:
+        for _ in range(warmup):
+            test_fn(*inputs, **kwinputs)
+        if on_gpu:
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            s.record()
+            for _ in range(repeats):
+                test_fn(*inputs, **kwinputs)
+            e.record()
+            e.synchronize()
+            return s.elapsed_time(e) * 1e-3 / repeats
+        t0 = time.perf_counter()
+        for _ in range(repeats):
+            test_fn(*inputs, **kwinputs)
+        return (time.perf_counter() - t0) / repeats
+
+
 def flops(batch, seqlen, headdim, nheads, time_f):
     return (4 * batch * seqlen**2 * nheads * headdim) / time_f / 1e12
 

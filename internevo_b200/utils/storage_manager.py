@@ -317,6 +317,129 @@ def check_tmp_folder_accessibility(tmp_local_folder: str, min_free_gb: float = 0
                            f"(need >= {min_free_gb} GB)")
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Parsed storage paths ("meta info").  One record type: which backend, bucket, endpoint (region for TOS), object key and - for
+# asynchronous saves - the staging file the object is serialised to first.  The four reference names (``Boto3MetaInfo``,
+# ``VolcMetaInfo``, ``AliMetaInfo``, ``LocalMetaInfo``; reference ``storage_manager.py:142-301,859-934``) are the same record
+# with the backend fixed, and ``get_*_meta`` are its parsers; ``StorageManager.get_meta`` hands them out with the client set.
+# ---------------------------------------------------------------------------------------------------------------------
+class PathMetaInfo:
+    backend = "local"
+    scheme = ""
+
+    def __init__(self, is_async: bool = False, handler: Optional[StorageClient] = None, bucket_name: Optional[str] = None,
+                 endpoint: Optional[str] = None, file_path: str = "", async_upload_fn: Optional[Callable] = None,
+                 local_nvme_path: Optional[str] = None, region: Optional[str] = None) -> None:
+        self.client = handler
+        self.bucket_name, self.endpoint, self.region = bucket_name, endpoint, region
+        self.file_path = file_path
+        self.is_async, self.local_nvme_path, self.async_upload_fn = is_async, local_nvme_path, async_upload_fn
+
+    @property
+    def url(self) -> str:
+        """The path in the form the clients of this module take."""
+        if not self.scheme:
+            return self.file_path
+        host = re.sub(r"^https?://", "", self.endpoint or "").split(":")[0]
+        return f"{self.scheme}{self.bucket_name}.{host}/{self.file_path}"
+
+    def save_args(self):
+        head = (self.client, self.bucket_name, self.file_path) if self.scheme else (self.file_path,)
+        return (*head, self.local_nvme_path) if (self.is_async and self.scheme) else head
+
+    def nosave_args(self):
+        return (self.client, self.bucket_name, self.file_path) if self.scheme else (self.file_path,)
+
+    def __str__(self) -> str:
+        return (f"backend: {self.backend}, is_async: {self.is_async}, bucket_name: {self.bucket_name}, endpoint: {self.endpoint}, "
+                f"file_path: {self.file_path}, local_nvme_path: {self.local_nvme_path}")
+
+
+class Boto3MetaInfo(PathMetaInfo):
+    backend, scheme = "boto3", "s3://"
+    unpack_boto3_save_meta = staticmethod(PathMetaInfo.save_args)
+    unpack_boto3_nosave_meta = staticmethod(PathMetaInfo.nosave_args)
+
+
+class VolcMetaInfo(PathMetaInfo):
+    backend, scheme = "volc", "vc://"
+    unpack_volc_save_meta = staticmethod(PathMetaInfo.save_args)
+    unpack_volc_nosave_meta = staticmethod(PathMetaInfo.nosave_args)
+
+
+class AliMetaInfo(PathMetaInfo):
+    backend, scheme = "oss2", "ali://"
+    unpack_ali_save_meta = staticmethod(PathMetaInfo.save_args)
+    unpack_ali_nosave_meta = staticmethod(PathMetaInfo.nosave_args)
+
+
+class LocalMetaInfo(PathMetaInfo):
+    def __init__(self, file_path: str) -> None:
+        super().__init__(file_path=file_path)
+
+    unpack_local_save_meta = staticmethod(PathMetaInfo.save_args)
+    unpack_local_nosave_meta = staticmethod(PathMetaInfo.nosave_args)
+
+
+def unpack_save_meta(meta: PathMetaInfo):
+    return meta.save_args()
+
+
+def unpack_nosave_meta(meta: PathMetaInfo):
+    return meta.nosave_args()
+
+
+def _object_meta(cls, fp: str, tmp_local_folder: Optional[str], is_async: bool, **extra) -> PathMetaInfo:
+    assert fp.startswith(cls.scheme), f"Path '{fp}' is not a {cls.backend} url ({cls.scheme}<bucket>.<endpoint>/<key>)"
+    bucket, endpoint, key = _split_bucket_url(fp, cls.scheme)
+    staging = get_tmp_file_name(tmp_local_folder, fp) if is_async else None
+    return cls(is_async=is_async, bucket_name=bucket, endpoint=endpoint, file_path=key, local_nvme_path=staging, **extra)
+
+
+def get_boto3_meta(fp: str, tmp_local_folder: str, is_async: bool) -> Boto3MetaInfo:
+    meta = _object_meta(Boto3MetaInfo, fp, tmp_local_folder, is_async)
+    meta.endpoint = f"http://{meta.endpoint}:80" if ":" not in meta.endpoint else f"http://{meta.endpoint}"
+    return meta
+
+
+def get_volc_meta(fp: str, tmp_local_folder: str, is_async: bool) -> VolcMetaInfo:
+    meta = _object_meta(VolcMetaInfo, fp, tmp_local_folder, is_async)
+    meta.region = "-".join(meta.endpoint.split(".")[0].split("-")[1:])      # tos-cn-beijing.volces.com -> cn-beijing
+    return meta
+
+
+def get_ali_meta(fp: str, tmp_local_folder: str, is_async: bool) -> AliMetaInfo:
+    return _object_meta(AliMetaInfo, fp, tmp_local_folder, is_async)
+
+
+def get_local_meta(fp: str) -> LocalMetaInfo:
+    assert not fp.startswith(("s3://", "vc://", "ali://")), f"Path '{fp}' is not a local path"
+    return LocalMetaInfo(fp)
+
+
+_META_PARSERS = {"boto3": get_boto3_meta, "volc": get_volc_meta, "oss2": get_ali_meta}
+
+
+def is_rank_for_log() -> bool:
+    """Storage messages are printed once per job (rank 0 of the launcher's numbering; no process group is needed)."""
+    return os.environ.get("RANK", "0") == "0"
+
+
+class Logger:
+    """Rank-0-only facade over the module logger, the form storage code logs through (reference ``:61-88``)."""
+
+    def info(self, mesage: str):
+        if is_rank_for_log():
+            logger.info(mesage)
+
+    def warning(self, mesage: str):
+        if is_rank_for_log():
+            logger.warning(mesage)
+
+    def error(self, mesage: str):
+        logger.error(mesage)
+
+
 def _make_client(backend: str, path: str) -> StorageClient:
     if backend == "local":
         return LocalClient()
@@ -375,6 +498,15 @@ class StorageManager:
         if backend not in self._clients:
             self._clients[backend] = _custom_backends[backend](real) if backend in _custom_backends else _make_client(backend, real)
         return self._clients[backend], backend, real
+
+    def get_meta(self, path: str, is_async: Optional[bool] = None) -> PathMetaInfo:
+        """Parsed form of ``path`` with this manager's client for its backend attached."""
+        backend, real = try_get_storage_backend(path)
+        is_async = self.async_mode if is_async is None else is_async
+        meta = get_local_meta(real) if backend == "local" else _META_PARSERS[backend](
+            real, self.tmp_local_folder, is_async and backend != "local")
+        meta.client = self._client(path)[0]
+        return meta
 
     def assert_fp_exists(self, folder) -> None:
         c, _, real = self._client(folder)

@@ -111,6 +111,36 @@ def test_simple_memory_profiler_accounts_params_grads_optimizer_and_activations(
     assert prof._stoped and prof._activation.total_mem == (5 * 16 + 5 * 16 + 5 * 4) * 4
     model(torch.randn(5, 8))                      # hooks are removed after the last profiled step
     assert prof._activation.total_mem == (5 * 16 + 5 * 16 + 5 * 4) * 4
+    # everything the forward kept alive was handed back during backward; the peak saw all three outputs at once
+    assert prof._activation.live == 0 and prof._activation.peak_live == (5 * 16 + 5 * 16 + 5 * 4) * 4
+    assert "alive at the peak" in text and os.path.exists(tmp_path / "memory.html")
+
+
+def test_memory_profiler_tracks_model_chunks_and_in_place_consumers(tmp_path):
+    """Interleaved pipeline stages: one activation tree per chunk; an in-place op on a profiled module's output (the attention
+    block rotates the wqkv projection in place) must keep working while the profiler is attached."""
+    from internevo_b200.utils.simple_memory_profiler import ActivationMemState, SimpleMemoryProfiler
+
+    class Wrapped(torch.nn.Module):          # stands for NaiveAMPModel: the chunk is ``.model``
+        def __init__(self, m):
+            super().__init__()
+            self.model = m
+
+        def forward(self, x):
+            return self.model(x)
+
+    chunks = torch.nn.ModuleList([Wrapped(torch.nn.Linear(4, 4)), Wrapped(torch.nn.Linear(4, 2))])
+    prof = SimpleMemoryProfiler(chunks, None, str(tmp_path), total_steps=1)
+    assert isinstance(prof._activation, ActivationMemState) and len(prof._activation.states) == 2
+    h = chunks[0](torch.randn(3, 4))
+    h.mul_(2.0)                              # in place on the hooked output
+    chunks[1](h).sum().backward()
+    assert prof._activation.inited == [True, True]
+    assert [s.total_mem for s in prof._activation.states] == [3 * 4 * 4, 3 * 2 * 4]
+    assert prof._activation.live == 0
+    prof.step()
+    text = open(tmp_path / "memory_1.log").read()
+    assert "activations_0" in text and "activations_1" in text and "chunk1" in text
 
 
 # ----------------------------------------------------------------------------------------------------------------- G3
