@@ -406,6 +406,11 @@ class CheckpointManager:
                         f"(+ optimizer {timer('save-optimizer').elapsed(False):.3f}s)")
         del start
 
+    def set_save_folder(self, folder, step) -> None:
+        """Tell the storage manager where the newest checkpoint lives (asynchronous uploads report against it)."""
+        sm = get_storage_manager()
+        sm.latest_save_folder, sm.latest_save_step = folder, step
+
     def try_ping_storage(self):
         if gpc.is_rank_for_log() and self.save_ckpt_folder:
             p = os.path.join(self.save_ckpt_folder, "ping.pt")

@@ -206,6 +206,11 @@ class AsynCommunicator:
         self.kw = dict(dtype=dtype, scatter_gather_tensors=scatter_gather_tensors)
         self.tensor_to_send, self.recv_shape = tensor_to_send, recv_shape
 
+    @property
+    def need_receive(self) -> bool:
+        """Does ``wait_and_receive`` hand back a tensor (a receive shape was given) or only complete the send?"""
+        return self.recv_shape is not None
+
     def start(self) -> None:
         if self.forward:  # send to next stage, receive from previous
             self._finish = _communicate_async(object_send_next=self.tensor_to_send, recv_prev=self.recv_shape is not None,

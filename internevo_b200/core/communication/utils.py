@@ -67,15 +67,30 @@ class ParamAsyncBcastHandler:
         self._optimizer = None
         modules = model if isinstance(model, torch.nn.ModuleList) else [model]
 
+        self._extra_handles: list = []
+
         def _pre_forward(module, inputs):
             if self._optimizer is not None:
                 self._optimizer.wait_param_sync()
+            while self._extra_handles:
+                _, h = self._extra_handles.pop()
+                if h is not None:
+                    h.wait()
 
         for m in modules:
             m.register_forward_pre_hook(_pre_forward)
 
     def bind(self, optimizer):
         self._optimizer = optimizer
+
+    def get_rank_by_param(self, param) -> int:
+        """Rank of the ZeRO group that owns (the start of) ``param``'s optimizer state."""
+        g = self._optimizer._state_of(param) if self._optimizer is not None else None
+        return g.owner_of(param) if g is not None else 0
+
+    def add_bcast_handle(self, rank, handle) -> None:
+        """Track an in-flight parameter redistribution started outside the optimizer; waited for before the next forward."""
+        self._extra_handles.append((rank, handle))
 
 
 def split_tensor_into_1d_equal_chunks(tensor: torch.Tensor, new_buffer: bool = False) -> torch.Tensor:

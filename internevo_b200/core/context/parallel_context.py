@@ -90,6 +90,25 @@ class ParallelContext:
     def set_config(self, config: Config):
         self._config = config
 
+    # shorthands of the data section used all over training scripts (reference ``parallel_context.py:167-181``)
+    @property
+    def micro_bsz(self) -> int:
+        return self._config.data.micro_bsz
+
+    @property
+    def micro_num(self) -> int:
+        return self._config.data.micro_num
+
+    @property
+    def grad_accum_num(self) -> int:
+        return self._config.data.get("gradient_accumulation", self._config.data.micro_num)
+
+    @property
+    def expert_parallel_group_names(self) -> list:
+        """Names of the optimizer parameter groups that hold experts (one per expert-parallel size in use)."""
+        n = self._config.model.get("num_experts", 1) if self._config is not None and "model" in self._config else 1
+        return [f"moe_ep_size_{self.expert_parallel_size}"] if n > 1 else []
+
     # ------------------------------------------------------------------ queries
     @staticmethod
     def _check_mode(mode):

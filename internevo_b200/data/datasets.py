@@ -188,6 +188,38 @@ class PackedDataset(Dataset):
     def __getitem__(self, item: int) -> Dict:
         return self.build_pack(item)
 
+    # ---- the stream arithmetic under the reference's names (``packed_dataset.py:122-131,243-282,333-340``) ---------------
+    def accu_sample_len(self, seed=None):
+        """``(shuffled sample ids, their lengths, running total of those lengths)`` for ``seed`` (default: dataset seed - 1)."""
+        idx, lens, acc = self._shuffled(self.seed - 1 if seed is None else seed)
+        return idx, lens.tolist(), acc.tolist()
+
+    def find_offset(self, offset: int):
+        """Token ``offset`` of the stream -> ``(position of its sample in the shuffled order, offset inside that sample)``."""
+        pos = int(np.searchsorted(self.acm_len_samples, offset, side="right"))
+        return pos, int(offset - (self.acm_len_samples[pos - 1] if pos > 0 else 0))
+
+    def cal_map(self, carriage_idx: int = 0) -> int:
+        """Shuffled position of the sample that holds the LAST token of pack ``carriage_idx``."""
+        assert carriage_idx >= 0
+        return int(np.searchsorted(self.acm_len_samples, (carriage_idx + 1) * self.packed_length, side="left"))
+
+    def mapping(self, pack_idx: int = 0):
+        """``(first sample position, token offset in it, last sample position, one-past-last token offset in it)`` of a pack."""
+        pre_pos, pre_tok = self.find_offset(pack_idx * self.packed_length) if pack_idx > 0 else (0, 0)
+        pos = self.cal_map(pack_idx)
+        tok = int(self.len_samples_shuffled[pos] - (self.acm_len_samples[pos] - (pack_idx + 1) * self.packed_length))
+        return pre_pos, pre_tok, pos, tok
+
+    def cal_pos_unpack(self, index: int):
+        """Sample range ``[pre_pos, pos)`` of un-packed micro-batch ``index``."""
+        mb = gpc.config.data["micro_bsz"]
+        return index * mb, (index + 1) * mb
+
+    def pdebug(self, line) -> None:
+        if getattr(self, "debug", False):
+            print(line, flush=True)
+
 
 class PackedDatasetWithCut(PackedDataset):
     """Concatenate shuffled samples into a token stream and cut it every ``packed_length`` tokens; fragments longer

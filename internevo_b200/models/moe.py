@@ -307,8 +307,8 @@ def _build_gshard(hidden_size, num_experts, ep_group, ep_size, mlp_ratio, device
     experts = _make_experts(num_local, hidden_size, mlp_ratio, device, dtype, expert_tensor_parallel)
     gate = TopKGate(hidden_size, num_experts, top_k, capacity_factor, eval_capacity_factor, min_capacity,
                     noisy_gate_policy, drop_tokens, use_rts, device=device)
-    return GShardMOELayer(hidden_size, gate, Experts(experts, num_local, f"moe_ep_size_{ep_size}"), ep_group, ep_size,
-                          num_local)
+    cls = unused.pop("_layer_cls", None) or GShardMOELayer
+    return cls(hidden_size, gate, Experts(experts, num_local, f"moe_ep_size_{ep_size}"), ep_group, ep_size, num_local)
 
 
 class _AllToAllV(torch.autograd.Function):
@@ -430,6 +430,7 @@ class DroplessMOELayer(BaseMoELayer):
 @MOE_INITIALIZER.register_module("MegaBlock")
 def _build_megablock(**kw):
     kw["drop_tokens"] = False  # capacity-padded variant: padded to the busiest expert instead of dropping
+    kw["_layer_cls"] = MegaBlockMoE
     return _build_gshard(**kw)
 
 
@@ -438,8 +439,8 @@ def _build_megablock_d(hidden_size, num_experts, ep_group, ep_size, mlp_ratio, d
                        noisy_gate_policy=None, expert_tensor_parallel=False, **unused):
     num_local = num_experts // ep_size
     experts = _make_experts(num_local, hidden_size, mlp_ratio, device, dtype, expert_tensor_parallel)
-    return DroplessMOELayer(hidden_size, num_experts, ep_group, ep_size, Experts(experts, num_local, f"moe_ep_size_{ep_size}"),
-                            top_k=top_k, noisy_gate_policy=noisy_gate_policy, device=device)
+    return MegaBlockdMoE(hidden_size, num_experts, ep_group, ep_size, Experts(experts, num_local, f"moe_ep_size_{ep_size}"),
+                         top_k=top_k, noisy_gate_policy=noisy_gate_policy, device=device)
 
 
 class MoE(nn.Module):
@@ -513,10 +514,98 @@ def top2gating(logits, capacity_factor, min_capacity):
     return _dense_routing(*_route(logits.float(), 2, capacity_factor, min_capacity, None, True, False), E)
 
 
-# reference class names (``moe/utils.py``, ``moe/megablock/megablock_{moe,dmoe}.py``)
+# ---------------------------------------------------------------------------------------------------------------------
+# Routing arithmetic in the MegaBlocks vocabulary (reference ``megablock_moe.py:73-99,253-275``, ``megablock_dmoe.py:85-182``):
+# sort-based "indices and bins", capacity, load-balancing loss, binned gather / scatter around the experts.  The layers above
+# do the same work inline (fused with their all-to-all); these are the stand-alone pieces for user code and tests.
+# ---------------------------------------------------------------------------------------------------------------------
+class _BinnedRouting:
+    blocking = 128
+
+    def _n_experts(self) -> int:
+        return self.gate.num_experts if hasattr(self, "gate") else self.num_experts
+
+    def _top_k(self) -> int:
+        return self.gate.k if hasattr(self, "gate") else self.top_k
+
+    def expert_capacity(self, tokens: int, top_k: int) -> int:
+        """Rows one expert accepts when tokens are dropped: ``capacity_factor * top_k * tokens * ep / E``."""
+        cf = getattr(getattr(self, "gate", None), "capacity_factor", 1.0)
+        return int(cf * top_k * tokens * max(1, self.ep_size) / self._n_experts())
+
+    def indices_and_bins(self, top_expert: torch.Tensor):
+        """``(indices, bin_ids, bins, tokens_per_expert)``: the stable order that groups the (token, choice) slots by expert,
+        the sorted expert ids, the inclusive running row count per expert and the row count per expert."""
+        flat = top_expert.reshape(-1).to(torch.int64)
+        bin_ids, indices = torch.sort(flat, stable=True)
+        tokens_per_expert = torch.bincount(flat, minlength=self._n_experts())
+        return indices.to(torch.int32), bin_ids.to(torch.int32), tokens_per_expert.cumsum(0).to(torch.int32), \
+            tokens_per_expert.to(torch.int32)
+
+    def indices_and_padded_bins(self, selected_experts: torch.Tensor):
+        """As ``indices_and_bins`` plus ``padded_bins``: the running count with every expert rounded up to the 128-row block of
+        the grouped GEMM (= ``ops.aligned_offsets(tokens_per_expert)[1:]``)."""
+        indices, bin_ids, bins, tpe = self.indices_and_bins(selected_experts)
+        padded = (tpe.to(torch.int64) + self.blocking - 1) // self.blocking * self.blocking
+        return indices, bin_ids, bins, padded.cumsum(0).to(torch.int32), tpe
+
+    def load_balancing_loss(self, tokens_per_expert: torch.Tensor, expert_scores: torch.Tensor) -> torch.Tensor:
+        """``E / (tokens * k) * <tokens_per_expert, mean score per expert>`` (Switch-style auxiliary loss)."""
+        assert expert_scores.dim() == 2 and tokens_per_expert.dim() == 1
+        tokens, E = expert_scores.shape
+        assert E == self._n_experts() == tokens_per_expert.numel()
+        return (E / (tokens * self._top_k())) * torch.dot(tokens_per_expert.to(expert_scores.dtype), expert_scores.mean(0))
+
+    def topology(self, x: torch.Tensor, padded_bins: torch.Tensor):
+        """Block-diagonal structure of the expert activations for a row buffer ``x`` laid out by ``padded_bins``."""
+        from .megablock import Topology
+
+        assert x.shape[0] % self.blocking == 0
+        off = torch.cat([padded_bins.new_zeros(1), padded_bins]).to(torch.int32)
+        first = self.experts.wrapped_experts[0]
+        ffn = first.w2.weight.shape[1] if hasattr(first, "w2") else next(first.parameters()).shape[0]
+        return Topology(off, ffn, rows=x.shape[0])
+
+    @staticmethod
+    def sparse_transpose(size, row_indices: torch.Tensor, column_indices: torch.Tensor, blocking: int = 128):
+        """Transpose metadata of a block-COO pattern ``(row_indices, column_indices)`` (in row-major block order):
+        ``(column_indices_t, offsets_t, block_offsets_t)`` = the block rows listed column by column, the CSC offsets, and for
+        every transposed block the position of its data in the original order."""
+        order = torch.sort(column_indices.to(torch.int64), stable=True)[1]
+        per_col = torch.bincount(column_indices.to(torch.int64), minlength=size[1] // blocking)
+        offsets_t = torch.cat([per_col.new_zeros(1), per_col.cumsum(0)]).to(torch.int32)
+        return row_indices.gather(0, order), offsets_t, order.to(torch.int32)
+
+    def permute_and_compute(self, x, indices, expert_weights, bins, expert_capacity, top_k):
+        """Binned gather -> experts on ``[E, capacity, h]`` -> weighted binned scatter: slot ``indices[j]`` (token
+        ``indices[j] // top_k``) is the ``j - bins[e - 1]``-th row of its expert ``e`` and is dropped beyond ``expert_capacity``."""
+        x = x.reshape(-1, x.shape[-1])
+        E = bins.numel()
+        idx = indices.to(torch.int64)
+        j = torch.arange(idx.numel(), device=x.device)
+        expert = torch.searchsorted(bins.to(torch.int64), j, right=True)
+        start = torch.cat([bins.new_zeros(1), bins[:-1]]).to(torch.int64)
+        slot = j - start[expert]
+        keep = slot < expert_capacity
+        rows = (expert * expert_capacity + slot)[keep]
+        toks = torch.div(idx, top_k, rounding_mode="floor")[keep]
+        buf = x.new_zeros(E * expert_capacity, x.shape[1]).index_copy(0, rows, x[toks])
+        out = self.experts(buf.view(E, expert_capacity, -1)).reshape(E * expert_capacity, -1)
+        w = expert_weights.reshape(-1)[idx][keep].to(out.dtype)
+        return x.new_zeros(x.shape).index_add(0, toks, out[rows] * w.unsqueeze(1))
+
+
+class MegaBlockMoE(_BinnedRouting, GShardMOELayer):
+    """Capacity-padded MegaBlocks layer: the GShard data path with the capacity raised to the busiest expert's load
+    (``_build_megablock``) plus the binned-routing helpers."""
+
+
+class MegaBlockdMoE(_BinnedRouting, DroplessMOELayer):
+    """Dropless MegaBlocks layer (``MegaBlock-D``)."""
+
+
+# reference class names (``moe/utils.py``)
 AllToAll = _AllToAll
-MegaBlockMoE = GShardMOELayer           # capacity raised to the busiest expert's load: see _build_megablock
-MegaBlockdMoE = DroplessMOELayer
 
 
 def einsum(rule: str, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:

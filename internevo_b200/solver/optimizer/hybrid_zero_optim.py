@@ -167,6 +167,12 @@ class _GroupState:
     def is_replica_range(self, i: int) -> bool:
         return i >= self.n_sharded_ranges
 
+    def owner_of(self, p) -> int:
+        """Rank of the ZeRO group whose sub-slice holds the first element of ``p`` (a parameter larger than a sub-slice
+        continues on the following ranks)."""
+        lo, hi = self.ranges[self.range_of[id(p)]]
+        return (self.offsets[id(p)] - lo) // ((hi - lo) // self.zero_size)
+
     def owned_views(self, arena: torch.Tensor):
         for i in range(len(self.ranges)):
             a, m, n = self.sub(i)
@@ -687,6 +693,47 @@ class HybridZeroOptimizer:
             except RuntimeError:  # very old gloo builds
                 parts = list(seg.chunk(g.zero_size))
                 dist.all_gather(parts, mine.clone(), group=group)
+
+    # ---- the reference's introspection surface (``hybrid_zero_optim.py:238-244,369-388,809-837``) on the arena layout ----
+    @property
+    def zero_local_rank(self) -> List[int]:
+        """This rank's position in the ZeRO group of every parameter group."""
+        return [g.zero_rank for g in self.groups]
+
+    @property
+    def zero_world_size(self) -> List[int]:
+        return [g.zero_size for g in self.groups]
+
+    def _state_of(self, param) -> Optional[_GroupState]:
+        for g in self.groups:
+            if id(param) in g.offsets:
+                return g
+        return None
+
+    def belongs_to_current_rank(self, param) -> bool:
+        """Does this rank hold optimizer state for (part of) ``param``?  Ranges are split evenly over the ZeRO group, so a
+        parameter may span several ranks: true for each of them."""
+        g = self._state_of(param)
+        if g is None:
+            return False
+        lo, hi = g.ranges[g.range_of[id(param)]]
+        n = (hi - lo) // g.zero_size
+        start = g.offsets[id(param)] - lo
+        return start // n <= g.zero_rank <= (start + param.numel() - 1) // n
+
+    def broadcast_params(self) -> None:
+        """Bring every rank's low-precision parameters up to date with the owners' fp32 masters (blocking).  ``step`` does this
+        range by range, overlapped; this is the explicit form (after editing the masters by hand, in tests)."""
+        self.flush_param_update()
+        for g in self.groups:
+            if g.params:
+                g.push_master()
+                self._redistribute_params(g)
+
+    def accumulate_left_grads_after_backward(self) -> None:
+        """ISP with overlap: fold the weight-gradient reduce-scatters still in flight into the gradient arena."""
+        if self._isp_communicator is not None and getattr(self._isp_communicator, "overlap", False):
+            self._isp_communicator.flush_grads()
 
     def state_dict(self):
         self.flush_param_update()

@@ -181,3 +181,99 @@ class BaseGradScaler:
 
     def update(self, overflow: bool) -> None:
         pass
+
+
+# ---- list-based global gradient norm (reference ``solver/optimizer/utils.py:25-39,225-378``).  The arena optimizer computes the
+# same quantity from its flat shard inside the reduce kernels (``HybridZeroOptimizer._group_sumsq``); this is the general form
+# for arbitrary (gradient, parameter) lists.
+def get_grad_accumulate_object(tensor):
+    """The ``AccumulateGrad`` node of a leaf parameter (hooks registered on it fire when the parameter's gradient is complete).
+    ``expand_as`` makes a temporary non-leaf whose first ``next_functions`` entry is that node."""
+    if tensor.grad_fn is not None:
+        raise RuntimeError("get_grad_accumulate_object() takes a leaf tensor; compute graphs are built from parameters")
+    acc = tensor.expand_as(tensor).grad_fn.next_functions[0][0]
+    assert acc is not None and "AccumulateGrad" in type(acc).__name__
+    return acc
+
+
+def _counts_toward_norm(p, model_mode) -> bool:
+    """Does THIS rank contribute ``p``'s gradient to the global norm?  Sharded parameters (tensor / weight / expert shards)
+    count everywhere - every rank holds a different piece; parameters replicated over the model-parallel group (norm weights,
+    gates) count on that group's rank 0 only; pipeline-shared modules on the first rank of their sharing group."""
+    from internevo_b200.utils import parallel as _par
+
+    shared = getattr(p, "pipeline_shared_module_pg", None)
+    if shared is not None:
+        return dist.get_rank(shared) == 0
+    if _par.is_replica_zero_parallel_parameter(p):
+        return not gpc.is_initialized(model_mode) or gpc.get_local_rank(model_mode) == 0
+    if (_par.is_tensor_data_parallel_parameter(p) or _par.is_tensor_zero_parallel_parameter(p)
+            or _par.is_weight_zero_parallel_parameter(p) or _par.is_tensor_expert_data_parallel_parameter(p)):
+        return True
+    # untagged parameters are treated like replicas: one copy per model-parallel group
+    return not gpc.is_initialized(model_mode) or gpc.get_local_rank(model_mode) == 0
+
+
+def _model_mode():
+    from internevo_b200.core.context import ParallelMode
+    from internevo_b200.utils.parallel import is_using_isp
+
+    return ParallelMode.WEIGHT if is_using_isp() else ParallelMode.TENSOR
+
+
+def reduce_grads(gradients, parameters, weight_parallel_mode=None):
+    """fp32 copies of the gradients this rank contributes to the global norm (see ``_counts_toward_norm``)."""
+    mode = _model_mode() if weight_parallel_mode is None else weight_parallel_mode
+    return [g.data.float() for g, p in zip(gradients, parameters) if _counts_toward_norm(p, mode)]
+
+
+def _all_reduce_scalar(t, mode, op):
+    if mode is not None and gpc.is_initialized(mode) and gpc.get_world_size(mode) > 1:
+        dist.all_reduce(t, op=op, group=gpc.get_group(mode))
+
+
+def compute_norm(gradients, parameters, norm_type=2, zero_mode=None):
+    """``norm ** norm_type`` of the gradients of ONE parameter group over the whole job (take the root before use).  The local
+    contribution is reduced over the model-parallel group the group's parameters are sharded over (tensor, or weight under
+    ISP), the pipeline stages and the ZeRO group that shards the gradients; expert groups are additionally combined over the
+    expert group, scaled by the data-parallel size.  ``-1`` stands for an infinite norm, ``-2`` for NaN (the step is skipped)."""
+    from internevo_b200.core.context import ParallelMode
+    from internevo_b200.utils import parallel as _par
+
+    zero_mode = ParallelMode.ZERO1 if zero_mode is None else zero_mode
+    gradients, parameters = list(gradients), list(parameters)
+    device = gradients[0].device
+    norm_type = float(norm_type)
+    model_mode = _model_mode()
+    first = parameters[0]
+    if _par.is_tensor_data_parallel_parameter(first):
+        # ISP embedding group: one full copy per rank of the tensor (sequence) group in this framework - nothing to add up
+        # (the reference splits it along the hidden dim and sums over TENSOR, ``optimizer/utils.py:340-342``)
+        shard_mode = None
+    elif _par.is_tensor_zero_parallel_parameter(first):
+        shard_mode = ParallelMode.TENSOR
+    else:
+        shard_mode = model_mode
+    if norm_type == _math.inf:
+        total = torch.stack([g.data.abs().max().float() for g in gradients]).max().reshape(1).to(device)
+        _all_reduce_scalar(total, shard_mode, dist.ReduceOp.MAX)
+        _all_reduce_scalar(total, ParallelMode.PIPELINE, dist.ReduceOp.MAX)
+    else:
+        mine = reduce_grads(gradients, parameters, model_mode)
+        total = torch.zeros(1, dtype=torch.float32, device=device)
+        if mine:
+            total += torch.as_tensor(get_norm(mine, norm_type, enable_cuda_kernels=device.type != "cpu"),
+                                     dtype=torch.float32, device=device).reshape(1)
+        _all_reduce_scalar(total, shard_mode, dist.ReduceOp.SUM)
+        _all_reduce_scalar(total, ParallelMode.PIPELINE, dist.ReduceOp.SUM)
+        _all_reduce_scalar(total, zero_mode, dist.ReduceOp.SUM)
+    if zero_mode == ParallelMode.EXPERT_DATA and gpc.is_initialized(ParallelMode.EXPERT):
+        # expert gradients are not synchronised over the expert group: combine the per-rank norms there
+        total = total / float(gpc.get_world_size(ParallelMode.DATA))
+        _all_reduce_scalar(total, ParallelMode.EXPERT, dist.ReduceOp.SUM)
+    value = float(total)
+    if _math.isinf(value):
+        return -1
+    if _math.isnan(value):
+        return -2
+    return value

@@ -63,6 +63,25 @@ class SimpleMemState:
             self.sub_model_stats[head] = SimpleMemState(head)
         self.sub_model_stats[head].add(rest, mem)
 
+    def delete(self, path: str) -> int:
+        """Remove the node ``path`` with everything below it; the bytes leave every ancestor's total.  Returns them."""
+        head, _, rest = path.partition(".")
+        child = self.sub_model_stats.get(head)
+        if child is None:
+            return 0
+        if rest:
+            freed = child.delete(rest)
+        else:
+            freed = child.total_mem
+            del self.sub_model_stats[head]
+        self._total_mem -= freed
+        return freed
+
+    def update_total_memory(self) -> int:
+        """Recompute the totals bottom-up (after children were edited directly)."""
+        self._total_mem = self._layer_mem + sum(c.update_total_memory() for c in self.sub_model_stats.values())
+        return self._total_mem
+
     def find_layer_state(self, path: str, create: bool = False):
         node = self
         for part in filter(None, path.split(".")):

@@ -69,6 +69,40 @@ class StorageClient:
     def delete(self, remote: str) -> None:
         raise NotImplementedError
 
+    # ---- object-level verbs (what the reference's clients expose one by one per backend, ``storage_manager.py:335-845``),
+    # written ONCE on top of the byte primitives above; ``fp`` is the path in the form this client takes
+    def sync_upload_fileobj(self, fp: str, saved_obj=None, **kwargs) -> None:
+        assert saved_obj is not None, "saved_obj is None!"
+        buf = io.BytesIO()
+        torch.save(saved_obj, buf, **kwargs)
+        self.upload_bytes(buf.getvalue(), fp)
+
+    def async_upload_fileobj(self, fp: str, local_nvme_path: str) -> str:
+        """Second half of an asynchronous save: the object already sits in the staging file; write its md5 sidecar, upload it,
+        drop the staging file.  Runs on a worker thread of the manager's pool."""
+        self.upload_bytes(compute_file_md5_by_chunk(local_nvme_path).encode(), fp + ".md5")
+        self.upload_file(local_nvme_path, fp)
+        if os.path.exists(local_nvme_path):
+            os.remove(local_nvme_path)
+        return fp
+
+    def load(self, fp: str, **kwargs):
+        kwargs.setdefault("map_location", "cpu")
+        kwargs.setdefault("weights_only", False)
+        return torch.load(io.BytesIO(self.download_bytes(fp)), **kwargs)
+
+    def is_fp_exists(self, fp: str) -> bool:
+        return self.exists(fp) or len(self.list(fp)) > 0
+
+    def assert_fp_exists(self, fp: str) -> None:
+        assert self.is_fp_exists(fp), f"'{fp}' does not exist"
+
+    def get_fns(self, fp: str) -> List[str]:
+        return self.list(fp)
+
+    def delete_obj(self, fp: str) -> None:
+        self.delete(fp)
+
 
 class LocalClient(StorageClient):
     def upload_file(self, local_path, remote):
@@ -491,7 +525,12 @@ class StorageManager:
         self.async_task_peeding = False
         if enable_save and self.async_mode:
             os.makedirs(tmp_local_folder, exist_ok=True)
-            os.chmod(tmp_local_folder, stat.S_IRWXU | stat.S_IRWXG | stat.S_IRWXO)
+            try:
+                os.chmod(tmp_local_folder, stat.S_IRWXU | stat.S_IRWXG | stat.S_IRWXO)
+            except PermissionError:      # created by another user with the right mode already: checked right below
+                pass
+            check_tmp_folder_accessibility(tmp_local_folder)
+            self.try_delete_tmpfile(tmp_local_folder)
 
     def _client(self, path: str):
         backend, real = try_get_storage_backend(path)
@@ -535,12 +574,27 @@ class StorageManager:
 
     @staticmethod
     def _upload_and_clean(client, tmp, real):
-        md5 = compute_file_md5_by_chunk(tmp)
-        client.upload_bytes(md5.encode(), real + ".md5")
-        client.upload_file(tmp, real)
-        if os.path.exists(tmp):
-            os.remove(tmp)
-        return real
+        return client.async_upload_fileobj(real, tmp)
+
+    def try_delete_tmpfile(self, tmp_dir: str) -> int:
+        """Remove staging files left behind by processes of THIS host that no longer run (a killed job's half-written
+        checkpoints fill ``/dev/shm`` otherwise); files of live processes - the other ranks share the folder - are kept.
+        Returns the number of files removed (reference ``storage_manager.py:1185-1196`` deletes every ``*.tmpfile``)."""
+        removed, host = 0, socket.gethostname() + "-"
+        if not os.path.isdir(tmp_dir):
+            return 0
+        for name in os.listdir(tmp_dir):
+            if not name.startswith(host):
+                continue
+            pid = name[len(host):].split("-", 1)[0]
+            if pid.isdigit() and int(pid) != os.getpid() and os.path.exists(f"/proc/{pid}"):
+                continue
+            try:
+                os.remove(os.path.join(tmp_dir, name))
+                removed += 1
+            except OSError:
+                pass
+        return removed
 
     def load(self, load_path: str, **kwargs) -> Any:
         c, _, real = self._client(load_path)

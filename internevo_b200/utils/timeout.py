@@ -70,6 +70,8 @@ class Timeout:
     def handle_timeout(self, signum, frame):
         raise TimeoutError(self.error_message)
 
+    timeout_handler = handle_timeout      # the reference's name for the same SIGALRM handler (``utils/timeout.py:27``)
+
     def __enter__(self):
         if self.seconds > 0 and threading.current_thread() is threading.main_thread():
             self._prev_handler = signal.signal(signal.SIGALRM, self.handle_timeout)

@@ -21,3 +21,14 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _restore_global_config():
+    """Tests that run in-process (no spawned ranks) set partial configs on the global context; give every test the config it
+    found so the outcome does not depend on which tests share an xdist worker."""
+    from internevo_b200.core.context import global_context as gpc
+
+    saved = gpc._config
+    yield
+    gpc._config = saved

@@ -404,3 +404,46 @@ def test_moe_trains_with_tensor_sharded_experts(mode):
     assert k0 == k1 and k0 > 0
     assert l0 == l1 and l0[-1] < l0[0]          # tensor ranks agree on the loss, and it goes down
     assert n0 == n1                              # ... and on every group's gradient norm (expert shards summed over TP)
+
+
+def test_binned_routing_helpers_of_the_megablock_layers():
+    """``indices_and_bins`` / ``indices_and_padded_bins`` / ``load_balancing_loss`` / ``permute_and_compute`` / ``topology`` /
+    ``sparse_transpose`` (reference ``megablock_moe.py:73-99,253-275``, ``megablock_dmoe.py:85-182``) against direct formulas."""
+    from internevo_b200.models.moe import MOE_INITIALIZER, MegaBlockdMoE, MegaBlockMoE
+
+    torch.manual_seed(0)
+    h, E, k, S = 16, 4, 2, 12
+    kw = dict(hidden_size=h, num_experts=E, ep_group=None, ep_size=1, mlp_ratio=2, device="cpu", dtype=torch.float32, top_k=k)
+    mb = MOE_INITIALIZER.get_module("MegaBlock")(**kw)
+    md = MOE_INITIALIZER.get_module("MegaBlock-D")(**kw)
+    assert isinstance(mb, MegaBlockMoE) and isinstance(md, MegaBlockdMoE)
+    scores = torch.softmax(torch.randn(S, E), -1)
+    w, top = torch.topk(scores, k, dim=-1)
+    indices, bin_ids, bins, padded_bins, tpe = md.indices_and_padded_bins(top)
+    flat = top.reshape(-1)
+    assert torch.equal(tpe.long(), torch.bincount(flat, minlength=E)) and int(bins[-1]) == S * k
+    assert torch.equal(flat[indices.long()], bin_ids.long()) and bool((bin_ids[1:] >= bin_ids[:-1]).all())
+    assert all(int(v) % 128 == 0 for v in padded_bins) and int(padded_bins[-1]) == 128 * int((tpe > 0).sum())
+    i2, b2, bins2, tpe2 = mb.indices_and_bins(top)
+    assert torch.equal(i2, indices) and torch.equal(bins2, bins) and torch.equal(tpe2, tpe) and torch.equal(b2, bin_ids)
+    lb = md.load_balancing_loss(tpe, scores)
+    want = E / (S * k) * sum(float(tpe[e]) * float(scores[:, e].mean()) for e in range(E))
+    assert abs(float(lb) - want) < 1e-5
+    assert mb.expert_capacity(S, k) == int(1.0 * k * S / E)
+    # binned gather -> experts -> weighted scatter == every token through its chosen experts
+    x = torch.randn(S, h)
+    cap = int(tpe.max())
+    out = mb.permute_and_compute(x, indices, w, bins, cap, k)
+    ref = torch.zeros(S, h)
+    for t in range(S):
+        for j in range(k):
+            ref[t] += w[t, j] * mb.experts.wrapped_experts[int(top[t, j])](x[t: t + 1])[0]
+    assert torch.allclose(out, ref, atol=1e-5)
+    dropped = mb.permute_and_compute(x, indices, w, bins, 1, k)      # capacity 1: only the first slot of every expert survives
+    assert float((dropped - ref).detach().abs().max()) > 1e-4
+    topo = md.topology(torch.zeros(int(padded_bins[-1]), h), padded_bins)
+    assert topo.num_experts == E and topo.ffn == md.experts.wrapped_experts[0].w2.weight.shape[1]
+    assert topo.offsets.tolist() == [0] + padded_bins.tolist()
+    # block COO (2 x 3 blocks): rows [0, 0, 1], cols [0, 2, 1]
+    ct, off_t, blk = md.sparse_transpose((256, 384), torch.tensor([0, 0, 1]), torch.tensor([0, 2, 1]))
+    assert ct.tolist() == [0, 1, 0] and off_t.tolist() == [0, 1, 2, 3] and blk.tolist() == [0, 2, 1]

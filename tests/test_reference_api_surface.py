@@ -12,8 +12,8 @@ import torch
 from common import ROOT, run_distributed  # noqa: F401
 
 REF = "/root/reference/internlm"
-# by design: one accelerator backend; gradients / params live in flat arenas instead of bucket stores
-NO_COUNTERPART = {"internlm.accelerator.npu_accelerator", "internlm.solver.optimizer.store"}
+# by design: one accelerator backend
+NO_COUNTERPART = {"internlm.accelerator.npu_accelerator"}
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
@@ -38,9 +38,8 @@ def test_every_reference_module_path_resolves():
                     names += 1
                     absent += not hasattr(m, node.name)
     assert not missing, missing
-    # public classes / functions reachable under their reference name (the rest are internals of designs replaced here:
-    # bucket stores, apex wrappers, block-sparse MegaBlocks kernels, per-mode duplicate classes)
-    assert names > 300 and absent / names < 0.25, (names, absent)
+    # every public class / function of the reference is reachable under its own name
+    assert names > 300 and absent == 0, (names, absent)
 
 
 def test_lr_schedulers():
