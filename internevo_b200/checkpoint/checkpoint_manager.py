@@ -113,6 +113,21 @@ def try_load_internevo_ckpt(ckpt_mm, load_info, train_state: TrainState = None):
             if ckpt_mm.lr_scheduler and train_state:
                 gpc.config.lr_scheduler.last_epoch = train_state.step_count
                 ckpt_mm.lr_scheduler.step(train_state.step_count)
+            if load_content.need_load(CheckpointLoadContent.SCHEDULAER) and ckpt_mm.optimizer is not None:
+                # schedule without optimizer states: still take the loss-scale state and the per-group learning rates from
+                # the optimizer file (reference ``only_load_lr``, ``checkpoint_manager.py:109-114``)
+                gpc.config.only_load_lr = True
+                try:
+                    load_optimizer_checkpoint(load_ckpt_folder, ckpt_mm.optimizer)
+                except (FileNotFoundError, AssertionError) as e:
+                    if gpc.is_rank_for_log():
+                        logger.warning(f"only_load_lr: no usable optimizer file in {load_ckpt_folder} ({e})")
+                finally:
+                    gpc.config.only_load_lr = False
+            if load_content.need_load(CheckpointLoadContent.MODEL) and hasattr(ckpt_mm.optimizer, "reload_zero_fp32_buff"):
+                # new weights but the old optimizer: the fp32 master must follow the weights, or the first step would write
+                # the pre-load values back
+                ckpt_mm.optimizer.reload_zero_fp32_buff()
         if load_content.need_load(CheckpointLoadContent.SAMPLER):
             if hasattr(train_state, "batch_sampler") and train_state.batch_sampler is not None:
                 load_sampler(load_ckpt_folder, ckpt_mm.train_dl.batch_sampler)

@@ -119,6 +119,13 @@ class NaiveAMPModel(nn.Module):
         def _post(model, inputs, outputs):
             return to_dtype(outputs, self.dtype)
 
+        output_tf32 = bool(gpc.config.get("output_tf32", False)) if gpc.config is not None else False
+
+        def _is_output_head(mod) -> bool:
+            from internevo_b200.parallel.linear import BaseScaleColumnParallelLinear
+
+            return module_is_output(mod) or isinstance(mod, BaseScaleColumnParallelLinear)
+
         modules = self.model if isinstance(self.model, nn.ModuleList) else [self.model]
         for m in modules:
             for sub in m.modules():
@@ -126,3 +133,10 @@ class NaiveAMPModel(nn.Module):
                     sub.to(dtype)
                     sub.register_forward_pre_hook(_pre)
                     sub.register_forward_hook(_post)
+                elif output_tf32 and _is_output_head(sub):
+                    # ``output_tf32``: the LM head keeps fp32 weights and takes fp32 inputs; its GEMM runs on the TF32 tensor
+                    # path and the logits stay fp32 for the loss (reference ``naive_amp.py:203-208``)
+                    sub.to(dtype)
+                    torch.backends.cudnn.allow_tf32 = True
+                    torch.backends.cuda.matmul.allow_tf32 = True
+                    sub.register_forward_pre_hook(_pre)

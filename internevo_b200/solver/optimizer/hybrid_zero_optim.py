@@ -756,6 +756,12 @@ class HybridZeroOptimizer:
         assert "grad_scaler" in states, "Not found grad_scaler state!"
         self.flush_param_update()
         self.grad_scaler.load_state_dict(states["grad_scaler"])
+        if gpc.config is not None and gpc.config.get("only_load_lr", False):
+            # resume of the schedule only: learning rates (and the loss scale above), no weights / moments
+            for g, st in zip(self.groups, states["groups"]):
+                if "lr" in st.get("hyper", {}):
+                    g.cfg["lr"] = st["hyper"]["lr"]
+            return
         for g, st in zip(self.groups, states["groups"]):
             same = (st.get("layout") == "range-interleaved" and st["total"] == g.total
                     and [tuple(r) for r in st["ranges"]] == g.ranges and st["zero_rank"] == g.zero_rank

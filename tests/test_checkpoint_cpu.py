@@ -172,3 +172,52 @@ def test_resume_is_exact_for_model_parallel_and_moe_layouts(tmp_path, name, worl
         assert layers == {0, 1} and len(files) == 2 * 4, files    # 2 global layers x 4 global experts, no collisions
         st = torch.load(os.path.join(str(tmp_path), "2", "model_moe_layer1_expert3_tp0.pt"), weights_only=False)
         assert st and all(".wrapped_experts.3." in k for k in st), list(st)[:3]   # keys carry the global expert id
+
+
+def _run_partial(rank, world, folder, phase):
+    """Load ``content=("model", "scheduler")`` from a finished run into a FRESH optimizer: the fp32 master must follow the
+    loaded weights (or the first step writes the init weights' update back) and the learning rate comes from the checkpoint."""
+    from internevo_b200.checkpoint import CheckpointManager
+    from internevo_b200.core.context import ParallelMode, global_context as gpc
+    from internevo_b200.core.trainer import TrainState
+
+    cfg = tiny_config(zero1=world, num_layers=2, micro_num=2)
+    cfg["ckpt"] = dict(enable_save_ckpt=(phase == "first"), save_ckpt_folder=f"local:{folder}", checkpoint_every=2,
+                       oss_snapshot_freq=0, auto_resume=False, async_upload=False)
+    if phase != "first":
+        cfg["ckpt"]["load_ckpt_info"] = dict(path=f"local:{folder}/2", content=("model", "scheduler"), ckpt_type="internevo")
+    trainer, opt, model, _ = build_trainer(cfg, seed=1024 if phase == "first" else 77)    # different init on reload
+    dpr = gpc.get_local_rank(ParallelMode.DATA)
+    ts = TrainState(gpc.config, None)
+    mm = CheckpointManager(ckpt_config=gpc.config.ckpt, model=model, optimizer=opt, lr_scheduler=trainer.engine._lr_scheduler,
+                           model_config=gpc.config.model)
+    mm.try_resume_training(ts)
+    if phase == "first":
+        for s in (1, 2):
+            ts.batch_count = s - 1
+            _step(trainer, cfg, dpr, s)
+            ts.step_count += 1
+            mm.try_save_checkpoint(ts)
+        mm.wait_async_upload_finish()
+        g = next(g for g in opt.groups if g.params)
+        return {"w": g.param_arena.clone(), "lr": g.cfg["lr"]}
+    g = next(g for g in opt.groups if g.params)
+    loaded = g.param_arena.clone()
+    # master == loaded weights on the owned sub-slices
+    for v, m, n in g.owned_views(g.param_arena):
+        assert torch.equal(g.master[m: m + n], v.float())
+    lr = g.cfg["lr"]
+    _step(trainer, cfg, dpr, 3)
+    moved = float((g.param_arena - loaded).abs().max())
+    return {"w": loaded, "lr": lr, "moved": moved, "step": ts.step_count}
+
+
+def test_partial_load_keeps_loaded_weights_and_learning_rate(tmp_path):
+    first = run_distributed(_run_partial, 2, str(tmp_path), "first")
+    again = run_distributed(_run_partial, 2, str(tmp_path), "reload")
+    for r in range(2):
+        assert torch.equal(first[r]["w"], again[r]["w"])                     # the checkpoint's weights, not the new init
+        assert abs(first[r]["lr"] - again[r]["lr"]) < 1e-12, (first[r]["lr"], again[r]["lr"])
+        assert again[r]["step"] == 2
+        # one AdamW step from the loaded weights moves them by ~lr, not by the distance to another initialisation
+        assert 0 < again[r]["moved"] < 0.02, again[r]["moved"]

@@ -186,3 +186,31 @@ def test_attention_dropout_is_applied_in_training():
     (drop, _), = run_distributed(_knobs, 1, dict(attn_drop_rate=0.5))
     assert all(l == l for l in drop)
     assert abs(drop[0] - base[0]) > 1e-4, "attn_drop_rate had no effect on the training loss"
+
+
+def test_output_tf32_keeps_the_head_in_fp32():
+    """``output_tf32 = True``: the LM head's weights stay fp32, it is fed fp32 activations and returns fp32 logits while the
+    rest of the model runs in the low-precision dtype (reference ``core/naive_amp.py:203-208``)."""
+    from internevo_b200.core.context import Config, global_context as gpc
+    from internevo_b200.core.naive_amp import NaiveAMPModel
+    from internevo_b200.parallel.linear import ScaleColumnParallelLinear
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.body = torch.nn.Linear(8, 8)
+            self.output = ScaleColumnParallelLinear(8, 16, process_group=None, bias=False)
+
+        def forward(self, x):
+            return self.output(self.body(x))
+
+    gpc.set_config(Config(dict(output_tf32=True, parallel=dict(tensor=dict(size=1, mode="mtp")))))
+    amp = NaiveAMPModel(Tiny(), output_to_fp32=False, dtype=torch.bfloat16)
+    assert amp.model.body.weight.dtype == torch.bfloat16 and amp.model.output.weight.dtype == torch.float32
+    y = amp(torch.randn(4, 8))
+    assert y.dtype == torch.float32 and y.shape == (4, 16)
+    y.sum().backward()
+    assert amp.model.output.weight.grad.dtype == torch.float32 and amp.model.body.weight.grad is not None
+    gpc.set_config(Config(dict(output_tf32=False, parallel=dict(tensor=dict(size=1, mode="mtp")))))
+    amp = NaiveAMPModel(Tiny(), output_to_fp32=False, dtype=torch.bfloat16)
+    assert amp.model.output.weight.dtype == torch.bfloat16
