@@ -372,6 +372,11 @@ class CheckpointManager:
         load_type = self.load_ckpt_info["ckpt_type"]
         load_func = self.defalut_load_type_func[load_type]
         load_content_str = load_func(self, self.load_ckpt_info, train_state)
+        # whatever loader ran (user-registered types included): after a weights-only load the optimizer's fp32 master follows
+        # the new weights (idempotent; reference ``checkpoint_manager.py:553-557``)
+        content = self.load_ckpt_info["content"]
+        if content.only_load(CheckpointLoadContent.MODEL) and hasattr(self.optimizer, "reload_zero_fp32_buff"):
+            self.optimizer.reload_zero_fp32_buff()
         if gpc.is_rank_for_log():
             logger.info(f"===========Resume training from `{load_path}` {current_time}, loaded: {load_content_str}===========")
             if train_state is not None:
