@@ -7,6 +7,7 @@ import os
 import re
 
 import torch
+import torch.distributed as dist
 
 from internevo_b200.core.context import ParallelMode
 from internevo_b200.core.context import global_context as gpc
@@ -92,9 +93,78 @@ def _expert_keys_to_local(st: dict, glob_e: int, local_e: int) -> dict:
     return out
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# ISP file layout.  In memory this framework keeps the token embedding whole on every rank of the sequence (tensor) group and
+# shards the head's vocabulary rows over the WEIGHT group; the reference splits the embedding along the hidden dimension and
+# the head's vocabulary rows over the TENSOR group (``modules/embedding.py:44-47``, ``ops/linear.py:24-83``).  Files are
+# written - and understood - in the reference's layout so ``model_tp{t}_wp{w}_pp{p}.pt`` moves between the two code bases; the
+# conversion costs one all-gather of the head per save / load.  Older files of this framework (whole embedding, weight-group
+# head rows) are recognised by their shapes and loaded as they are.
+# ---------------------------------------------------------------------------------------------------------------------
+def _isp_embed_head_keys(model, states):
+    emb, head = [], []
+    for mod in model.modules():
+        spec = getattr(mod, "spec", None)
+        if spec is not None and hasattr(spec, "embed_name") and hasattr(spec, "head_name"):
+            for k in states:
+                if k.endswith(f"{spec.embed_name}.weight") and k not in emb:
+                    emb.append(k)
+                elif k.endswith(f"{spec.head_name}.weight") and k not in head:
+                    head.append(k)
+    return emb, head
+
+
+def _gather_rows(t: torch.Tensor, mode: ParallelMode) -> torch.Tensor:
+    n = gpc.get_world_size(mode)
+    if n <= 1:
+        return t
+    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else t.device
+    src = t.detach().to(dev).contiguous()
+    out = torch.empty(n * src.shape[0], *src.shape[1:], dtype=src.dtype, device=dev)
+    dist.all_gather_into_tensor(out, src, group=gpc.get_group(mode))
+    return out
+
+
+def _my_slice(full: torch.Tensor, mode: ParallelMode, dim: int) -> torch.Tensor:
+    n, r = gpc.get_world_size(mode), gpc.get_local_rank(mode)
+    size = full.shape[dim] // n
+    return full.narrow(dim, r * size, size).contiguous()
+
+
+def _isp_states_to_file_layout(model, states: dict) -> dict:
+    """Collective over the TENSOR and WEIGHT groups (every rank of a pipeline stage holds the same keys)."""
+    emb, head = _isp_embed_head_keys(model, states)
+    vocab, hidden = gpc.config.model.vocab_size, gpc.config.model.hidden_size
+    out = dict(states)
+    for k in emb:
+        if tuple(states[k].shape) == (vocab, hidden):
+            out[k] = _my_slice(states[k].detach(), ParallelMode.TENSOR, 1)
+    for k in head:
+        if states[k].shape[0] * gpc.get_world_size(ParallelMode.WEIGHT) == vocab:
+            out[k] = _my_slice(_gather_rows(states[k], ParallelMode.WEIGHT), ParallelMode.TENSOR, 0)
+    return out
+
+
+def _isp_states_from_file_layout(model, states: dict) -> dict:
+    emb, head = _isp_embed_head_keys(model, model.state_dict())
+    vocab, hidden = gpc.config.model.vocab_size, gpc.config.model.hidden_size
+    tp, wp = gpc.get_world_size(ParallelMode.TENSOR), gpc.get_world_size(ParallelMode.WEIGHT)
+    for k in emb:
+        if k in states and tuple(states[k].shape) == (vocab, hidden // tp) and tp > 1:
+            parts = _gather_rows(states[k].t().contiguous(), ParallelMode.TENSOR)      # gather along hidden
+            states[k] = parts.t().contiguous().cpu()
+    for k in head:
+        if k in states and states[k].shape[0] == vocab // tp and not (tp == wp):
+            states[k] = _my_slice(_gather_rows(states[k], ParallelMode.TENSOR), ParallelMode.WEIGHT, 0).cpu()
+        # tp == wp: the two groups are the same ranks and the row slices coincide; vocab // wp rows: this framework's older files
+    return states
+
+
 def save_model_checkpoint(folder, model):
     """``model_tp*_pp*.pt`` + topology json (+ one file per global expert)."""
     states = get_shard_state_dict(model)
+    if is_using_isp():
+        states = _isp_states_to_file_layout(model, states)
     states = {k: v.detach().clone().cpu() if torch.is_tensor(v) else v for k, v in states.items()}
     states, experts = (_split_expert_states(states, _chunk_layer_offsets(model))
                        if gpc.config.model.get("num_experts", 1) > 1 else (states, {}))
@@ -180,6 +250,8 @@ def load_model_checkpoint(folder, model):
     assert tp_size == max_tp + 1, f"The weights are save for {max_tp + 1} parallelism, while current has {tp_size}"
     fp = os.path.join(folder, _model_fn())
     states = llm_load(fp, map_location="cpu")
+    if is_using_isp():
+        states = _isp_states_from_file_layout(model, states)
     try_load_moe_checkpoint(folder, model, states)
     missing_k, unexpected_keys = load_shard_state_dict(model, states, strict=False)
     lost = [k for k in missing_k if _EXPERT_KEY.match(k)]

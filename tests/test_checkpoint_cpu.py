@@ -146,6 +146,8 @@ import pytest  # noqa: E402
 @pytest.mark.parametrize("name,world,kw,moe", [
     ("tp2_pp2", 4, dict(tp=2, pp=2), False),
     ("isp_sp2_wp2", 2, dict(tp=2, wp=2, mode="isp"), False),
+    # weight group wider than the sequence group: the head's vocabulary rows are re-sharded between file and memory layout
+    ("isp_sp2_wp4", 4, dict(tp=2, wp=4, mode="isp"), False),
     ("moe_ep2", 2, dict(model_type="INTERNLM_MoE", num_experts=4, moe_type="MegaBlock-D"), True),  # dropless: no gate noise
     # range-interleaved optimizer shards (many ranges, reduction overlapped with backward) must resume bit-exactly, too
     ("dp2_zero2_overlap", 2, dict(zero1=2, overlap_bucket=4096), False),
@@ -163,6 +165,24 @@ def test_resume_is_exact_for_model_parallel_and_moe_layouts(tmp_path, name, worl
                 assert abs(l0 - l1) < 1e-6, (name, first[r], resumed[r])
             for (k0, v0), (k1, v1) in zip(n0, n1):
                 assert k0 == k1 and abs(v0 - v1) < 1e-5 * max(1.0, abs(v0)), (name, n0, n1)
+    if name.startswith("isp"):
+        # files carry the reference's ISP layout: embedding split along hidden, head rows split over the TENSOR group
+        cfgm = tiny_config(num_layers=2, **{k: v for k, v in kw.items() if k != "overlap_bucket"})["model"]
+        V, h, tp, wp = cfgm["vocab_size"], cfgm["hidden_size"], kw["tp"], kw["wp"]
+        for w in range(wp):
+            t = w % tp
+            st = torch.load(os.path.join(str(tmp_path), "2", f"model_tp{t}_wp{w}_pp0.pt"), weights_only=False)
+            emb = next(v for k, v in st.items() if k.endswith("tok_embeddings.weight"))
+            head = next(v for k, v in st.items() if k.endswith("output.weight"))
+            wqkv = next(v for k, v in st.items() if k.endswith("layers.0.attention.wqkv.weight"))
+            assert tuple(emb.shape) == (V, h // tp) and tuple(head.shape) == (V // tp, h), (emb.shape, head.shape)
+            assert wqkv.shape[0] * wp == (cfgm["num_attention_heads"] + 2 * cfgm["num_kv_attention_heads"]) * (
+                h // cfgm["num_attention_heads"])
+        # the tensor ranks' embedding slices are different columns of ONE matrix, the head slices different rows
+        e0 = torch.load(os.path.join(str(tmp_path), "2", "model_tp0_wp0_pp0.pt"), weights_only=False)
+        e1 = torch.load(os.path.join(str(tmp_path), "2", "model_tp1_wp1_pp0.pt"), weights_only=False)
+        k_emb = next(k for k in e0 if k.endswith("tok_embeddings.weight"))
+        assert not torch.equal(e0[k_emb], e1[k_emb])
     if moe:
         import glob
         import re as _re

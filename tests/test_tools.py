@@ -226,3 +226,31 @@ def test_openai_api_chat_completions_and_streaming(sp_model):
     assert lines[-1] == "data: [DONE]" and 1 <= len(lines) - 1 <= 6          # at most max_tokens chunks
     deltas = [json.loads(ln[6:])["choices"][0]["delta"]["content"] for ln in lines[:-1]]
     assert "".join(deltas) == r["choices"][0]["message"]["content"]           # greedy: streaming == non-streaming
+
+
+def test_ckpt_io_merges_weight_parallel_checkpoints(tmp_path):
+    """``model_tp{t}_wp{w}_pp{p}.pt`` (isp) folders merge into the same full state dict they were cut from: linears by weight rank,
+    embedding by the tensor ranks' hidden slices, head by their vocabulary rows."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import ckpt_io
+
+    torch.manual_seed(0)
+    V, h, F = 32, 16, 24
+    full = {"tok_embeddings.weight": torch.randn(V, h), "norm.weight": torch.randn(h), "output.weight": torch.randn(V, h)}
+    for i in range(2):
+        p = f"layers.{i}."
+        full[p + "attention.wqkv.weight"] = torch.randn(24, h)
+        full[p + "attention.wo.weight"] = torch.randn(h, h)
+        full[p + "attention_norm.weight"] = torch.randn(h)
+        full[p + "ffn_norm.weight"] = torch.randn(h)
+        for n, s in (("w1", (F, h)), ("w3", (F, h)), ("w2", (h, F))):
+            full[p + f"feed_forward.{n}.weight"] = torch.randn(*s)
+    for tp, wp in ((2, 2), (2, 4), (1, 4)):
+        d = str(tmp_path / f"tp{tp}wp{wp}")
+        ckpt_io.save_sharded_isp(full, d, tp, wp)
+        assert len(ckpt_io.find_isp_shards(d)) == wp
+        one = torch.load(os.path.join(d, f"model_tp{(wp - 1) % tp}_wp{wp - 1}_pp0.pt"), weights_only=False)
+        assert tuple(one["tok_embeddings.weight"].shape) == (V, h // tp) and tuple(one["output.weight"].shape) == (V // tp, h)
+        assert tuple(one["layers.0.feed_forward.w2.weight"].shape) == (h // wp, F)
+        back = ckpt_io.load_full_state(d)
+        assert set(back) == set(full) and all(torch.equal(back[k], full[k]) for k in full), (tp, wp)
