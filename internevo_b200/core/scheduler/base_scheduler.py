@@ -36,6 +36,16 @@ def model_kwargs(target, data: Dict) -> Dict:
 class BaseScheduler(ABC):
     def __init__(self, data_process_func: Callable = None):
         self.data_process_func = data_process_func
+        # labels are un-packed with the ignore index as padding when the function can take one (``data.unpack_data``)
+        self._label_pad = {}
+        if data_process_func is not None:
+            import inspect
+
+            try:
+                if "padding_v" in inspect.signature(data_process_func).parameters:
+                    self._label_pad = {"padding_v": -100}
+            except (TypeError, ValueError):
+                pass
 
     @abstractmethod
     def pre_processing(self, engine):

@@ -37,7 +37,7 @@ class NonPipelineScheduler(BaseScheduler):
         self._grad_accum_offset += self._bsz_stride
         if self.data_process_func:
             _data["input_ids"] = self.data_process_func(_data["input_ids"], _data["cu_seqlens"])
-            _label = self.data_process_func(_label, _data["cu_seqlens"])
+            _label = self.data_process_func(_label, _data["cu_seqlens"], **self._label_pad)
             _data.pop("cu_seqlens")
             _data.pop("indexes")
             _data.pop("max_seqlen", None)

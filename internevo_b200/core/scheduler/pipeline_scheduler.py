@@ -129,7 +129,7 @@ class PipelineScheduler(BaseScheduler):
         data, label = self._load_micro_batch(self.batch_data, self.batch_label, self.microbatch_offset, self.bsz_stride)
         if self.data_process_func:
             data["input_ids"] = self.data_process_func(data["input_ids"], data["cu_seqlens"])
-            label = self.data_process_func(label, data["cu_seqlens"])
+            label = self.data_process_func(label, data["cu_seqlens"], **self._label_pad)
             data.pop("cu_seqlens")
             data.pop("indexes")
             data.pop("max_seqlen", None)

@@ -369,16 +369,18 @@ def get_packed_dataset_without_short_length(folder, max_length_per_sample=2048, 
 
 
 def unpack_data(input_ids, cu_seqlens, is_type_ids: bool = False, padding_v: int = 0):
-    """packed ``[b, packed_len]`` → ``[b * num_seq, max_seq]`` rows (reference ``internlm/data/utils.py:27-55``)."""
+    """Un-packed (no flash-attention) mode: a packed row ``[b, packed_length]`` built by ``build_unpack`` holds ``micro_bsz`` whole
+    samples followed by padding up to ``packed_length``; give the samples back as rows ``[b, micro_bsz, seq_len]`` padded with
+    ``padding_v`` (the trailing padding segment is dropped).  ``b == 1`` is squeezed away unless ``is_type_ids`` (reference
+    ``internlm/data/utils.py:27-55``; labels should be unpacked with ``padding_v=-100`` so the padding never enters the loss)."""
     bsz = input_ids.shape[0]
-    outs = []
-    max_len = gpc.config.data["seq_len"]
+    n_seq, max_len = gpc.config.data["micro_bsz"], gpc.config.data["seq_len"]
+    out = torch.full((bsz, n_seq, max_len), padding_v, dtype=input_ids.dtype, device=input_ids.device)
     for i in range(bsz):
-        cu = cu_seqlens[i] if not torch.is_tensor(cu_seqlens) or cu_seqlens.dim() > 1 else cu_seqlens
-        segs = int(len(cu) - 1)
-        rows = torch.full((segs, max_len), padding_v, dtype=input_ids.dtype, device=input_ids.device)
-        for j in range(segs):
-            a, b = int(cu[j]), int(cu[j + 1])
-            rows[j, : b - a] = input_ids[i, a:b]
-        outs.append(rows)
-    return torch.cat(outs, 0)
+        cu = cu_seqlens[i] if torch.is_tensor(cu_seqlens) and cu_seqlens.dim() > 1 else (
+            cu_seqlens[i] if not torch.is_tensor(cu_seqlens) and hasattr(cu_seqlens[0], "__len__") else cu_seqlens)
+        for j in range(min(n_seq, len(cu) - 1)):
+            a0, b0 = int(cu[j]), int(cu[j + 1])
+            n = min(b0 - a0, max_len)
+            out[i, j, :n] = input_ids[i, a0: a0 + n]
+    return out.squeeze(0) if bsz == 1 and not is_type_ids else out

@@ -17,6 +17,7 @@ def switch_evaluation_no_pipeline_scheduler(trainer, grad_accum_size, metric_hoo
         prev_grad_accum_size = trainer.schedule._grad_accum_size
         prev_metric_hooks = trainer.schedule._hooks
         try:
+            trainer.schedule.data_process_func = None     # validation batches are not packed: nothing to un-pack
             trainer.schedule._grad_accum_size = grad_accum_size
             trainer.schedule._hooks = metric_hook_list
             yield
@@ -36,6 +37,7 @@ def switch_evaluation_pipeline_scheduler(trainer, num_microbatches, tensor_shape
         prev_tensor_shape = trainer.schedule.tensor_shape
         prev_metric_hooks = trainer.schedule._hooks
         try:
+            trainer.schedule.data_process_func = None
             trainer.schedule.num_microbatches = num_microbatches
             trainer.schedule.tensor_shape = tensor_shape
             trainer.schedule._hooks = metric_hook_list

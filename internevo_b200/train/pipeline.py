@@ -229,9 +229,7 @@ def load_new_batch(train_dl: DataLoader, train_iter: Iterable, train_state: Trai
     if batch[0].get("type_ids", None) is not None and not gpc.config.data.get("use_packed_dataset", True):
         from internevo_b200.data.datasets import unpack_data
 
-        t = batch[0]["type_ids"]
-        batch[0]["type_ids"] = torch.stack([unpack_data(t[i:i + 1], batch[0]["cu_seqlens"][i:i + 1], is_type_ids=True)
-                                            for i in range(t.shape[0])])
+        batch[0]["type_ids"] = unpack_data(batch[0]["type_ids"], batch[0]["cu_seqlens"], is_type_ids=True)
     attach_host_max_seqlen(batch[0])
     return batch, train_iter
 

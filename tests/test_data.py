@@ -1,7 +1,9 @@
 """Packed dataset / sampler behaviour (reference semantics: ``tests/test_data/test_batch_sampler.py`` and the
 ``PackedDatasetWithCut`` docstring example)."""
 import numpy as np
+import torch
 
+from common import run_distributed
 from internevo_b200.core.context import Config
 from internevo_b200.core.context import global_context as gpc
 from internevo_b200.data.batch_sampler import StaticBatchSampler
@@ -133,3 +135,63 @@ def test_load_new_batch_crosses_epoch_boundary():
         assert sorted(sum(seen[3 * e:3 * e + 3], [])) == list(range(12))
     assert seen[0:3] != seen[3:6]   # reshuffled between epochs
     assert state.batch_sampler.num_consumed_samples_in_epoch == 12
+
+
+# --------------------------------------------------------------------------------------------- un-packed (no flash-attention) mode
+def test_unpack_data_rows_and_ignored_padding():
+    """``build_unpack`` packs ``micro_bsz`` whole samples + padding into one row; ``unpack_data`` hands the samples back as
+    ``[micro_bsz, seq_len]`` rows: short samples, a padding segment LONGER than ``seq_len`` and label padding with -100."""
+    from internevo_b200.core.context import Config, global_context as gpc
+    from internevo_b200.data.datasets import unpack_data
+
+    gpc.set_config(Config(dict(data=dict(micro_bsz=2, seq_len=8, packed_length=16), model=dict(use_flash_attn=False))))
+    ids = torch.arange(1, 17).reshape(1, 16)
+    cu = torch.tensor([[0, 3, 5, 16]], dtype=torch.int32)            # samples of 3 and 2 tokens, then 11 padding positions
+    rows = unpack_data(ids, cu)
+    assert rows.shape == (2, 8)
+    assert rows[0].tolist() == [1, 2, 3, 0, 0, 0, 0, 0] and rows[1].tolist() == [4, 5, 0, 0, 0, 0, 0, 0]
+    lab = unpack_data(ids, cu, padding_v=-100)
+    assert lab[1].tolist() == [4, 5] + [-100] * 6
+    tids = unpack_data(torch.ones(3, 16, dtype=torch.long), cu.repeat(3, 1), is_type_ids=True)
+    assert tids.shape == (3, 2, 8) and int(tids.sum()) == 3 * (3 + 2)
+
+
+def _unpacked_vs_packed(rank, world, unpacked):
+    """One step on the same two samples: packed with ``cu_seqlens`` (flash path) or un-packed ``[micro_bsz, seq_len]`` rows."""
+    from common import build_trainer, tiny_config
+
+    cfg = tiny_config(num_layers=2, micro_num=1, micro_bsz=2, seq_len=16, use_flash_attn=not unpacked)
+    cfg["data"]["use_packed_dataset"] = not unpacked
+    trainer, opt, model, _ = build_trainer(cfg)
+    g = torch.Generator().manual_seed(5)
+    s0, s1 = torch.randint(1, 100, (9,), generator=g), torch.randint(1, 100, (12,), generator=g)
+
+    def labels_of(s):
+        return torch.cat([s[1:], torch.tensor([-100])])
+
+    if unpacked:     # what PackedDatasetWithCut.build_unpack + packed_collate_fn produce: samples, then zero padding
+        pad = 32 - 21
+        ids = torch.cat([s0, s1, torch.zeros(pad, dtype=torch.long)])[None]
+        lab = torch.cat([labels_of(s0), labels_of(s1), torch.zeros(pad, dtype=torch.long)])[None]
+        cu = torch.tensor([[0, 9, 21, 32]], dtype=torch.int32)
+        idx = torch.cat([torch.arange(9), torch.arange(12), torch.arange(pad)])[None]
+    else:            # packed row of exactly the two samples' tokens, padded by a third ignored segment
+        pad = 32 - 21
+        ids = torch.cat([s0, s1, torch.ones(pad, dtype=torch.long)])[None]
+        lab = torch.cat([labels_of(s0), labels_of(s1), torch.full((pad,), -100)])[None]
+        cu = torch.tensor([[0, 9, 21, 32]], dtype=torch.int32)
+        idx = torch.cat([torch.arange(9), torch.arange(12), torch.arange(pad)])[None]
+    data = {"input_ids": ids, "cu_seqlens": cu, "indexes": idx}
+    trainer.zero_grad()
+    out = trainer.execute_schedule((data, lab), forward_only=False, return_loss=True, return_output_label=False)
+    ok, norms = trainer.step()
+    assert ok
+    return float(out[2]), {k: float(v) for k, v in norms.items()}
+
+
+def test_unpacked_mode_matches_the_packed_loss_and_gradient_norm():
+    packed = run_distributed(_unpacked_vs_packed, 1, False)[0]
+    plain = run_distributed(_unpacked_vs_packed, 1, True)[0]
+    assert abs(packed[0] - plain[0]) < 1e-4, (packed, plain)                       # same tokens, same targets, padding ignored
+    for k in packed[1]:
+        assert abs(packed[1][k] - plain[1][k]) < 1e-3 * max(1.0, packed[1][k]), (packed, plain)
