@@ -176,7 +176,9 @@ class ParallelContext:
         return self.is_last_rank(ParallelMode.PIPELINE)
 
     def is_no_pp_or_last_stage(self) -> bool:
-        return not self.is_initialized(ParallelMode.PIPELINE) or self.is_pipeline_last_stage()
+        """Does this RANK produce the loss / logits?  Asked by code outside the schedulers (metrics, validation), after a schedule
+        has reset the virtual (chunk) rank - so the chunk is ignored: with interleaving the last pipeline rank owns the last chunk."""
+        return not self.is_initialized(ParallelMode.PIPELINE) or self.is_pipeline_last_stage(ignore_virtual=True)
 
     def get_world_size(self, mode) -> int:
         self._check_mode(mode)
@@ -359,7 +361,10 @@ class ParallelContext:
     def set_virtual_pipeline_parallel_rank(self, rank):
         self.virtual_pipeline_parallel_rank = rank
 
-    def destroy(self):
+    def destroy(self, graceful: bool = True):
+        """Tear the groups down.  ``graceful=False`` is the error path: this rank is leaving because of an exception while its
+        peers may sit in a collective that will never complete - no barrier, no collective teardown, just forget the groups
+        (the launcher kills the remaining ranks when this process exits non-zero)."""
         # peer-memory back-ends cache symmetric buffers / flag epochs keyed by process group: drop them with the groups so a
         # later initialisation in the same process (another layout, another test) starts from a clean heap
         try:
@@ -368,7 +373,7 @@ class ParallelContext:
             reset_caches()
         except Exception:  # pragma: no cover - teardown must not raise
             pass
-        if self.is_distributed:
+        if self.is_distributed and graceful:
             try:
                 dist.barrier()
             except Exception:  # pragma: no cover

@@ -98,12 +98,20 @@ def evaluate_on_val_dls(trainer, val_dls, writer, logger, step_count, update_pan
                 with torch.inference_mode():
                     total_bsz = len(batch[1])
                     assert total_bsz % data_cfg.micro_bsz == 0
-                    num_micro = total_bsz // data_cfg.micro_bsz
+                    num_micro, rows = total_bsz // data_cfg.micro_bsz, data_cfg.micro_bsz
+                    pp = gpc.get_world_size(ParallelMode.PIPELINE)
+                    if pp > 1 and getattr(trainer.schedule, "_num_chunks", 1) > 1 and num_micro % pp != 0:
+                        # the interleaved schedule runs micro-batches in groups of pp: cut the validation batch into the
+                        # smallest multiple of pp micro-batches that divides it (fewer rows per micro-batch)
+                        fits = [m for m in range(pp, total_bsz + 1, pp) if total_bsz % m == 0]
+                        assert fits, (f"interleaved pipeline (pp = {pp}) cannot split a validation batch of {total_bsz} samples: "
+                                      f"make valid_micro_num * micro_bsz a multiple of {pp}")
+                        num_micro, rows = fits[0], total_bsz // fits[0]
                     sp = gpc.get_world_size(ParallelMode.TENSOR) if gpc.config.parallel.get("sequence_parallel", False) else 1
-                    shape = (data_cfg.micro_bsz * batch[0]["input_ids"].shape[1] // sp, gpc.config.model["hidden_size"])
+                    shape = (rows * batch[0]["input_ids"].shape[1] // sp, gpc.config.model["hidden_size"])
                     if gpc.is_using_parallel_mode(ParallelMode.PIPELINE):
                         with switch_evaluation_pipeline_scheduler(trainer, num_micro, shape, [hook]):
-                            trainer.schedule.bsz_stride = data_cfg.micro_bsz
+                            trainer.schedule.bsz_stride = rows
                             out = trainer.execute_schedule(batch, forward_only=True, return_loss=True, return_output_label=False)
                     else:
                         with switch_evaluation_no_pipeline_scheduler(trainer, num_micro, [hook]):

@@ -37,11 +37,14 @@ class RotaryTables:
     def get(self, max_pos: int, device) -> tuple:
         if self.cos is None or max_pos > self.max_pos or self.cos.device != torch.device(device):
             n = max(max_pos, 2 * self.max_pos, 4096)
-            t = torch.arange(n, device=device, dtype=torch.float32)
-            if not self.ntk_max_position and self.scaling_factor != 1.0:
-                t = t / self.scaling_factor
-            freqs = torch.outer(t, self._inv_freq(n, device))
-            self.cos, self.sin, self.max_pos = freqs.cos().contiguous(), freqs.sin().contiguous(), n
+            # the tables outlive the call that builds them: a cache filled while validation runs under inference_mode() would be
+            # made of inference tensors, which a later TRAINING step cannot save for backward - build them as normal tensors
+            with torch.inference_mode(False), torch.no_grad():
+                t = torch.arange(n, device=device, dtype=torch.float32)
+                if not self.ntk_max_position and self.scaling_factor != 1.0:
+                    t = t / self.scaling_factor
+                freqs = torch.outer(t, self._inv_freq(n, device))
+                self.cos, self.sin, self.max_pos = freqs.cos().contiguous(), freqs.sin().contiguous(), n
         return self.cos, self.sin
 
 

@@ -80,3 +80,77 @@ def test_overflow_on_one_pipeline_stage_skips_the_step_everywhere():
     for ok, unchanged, ok2 in run_distributed(_overflow_on_one_stage, 2):
         assert ok is False and unchanged        # no stage applied the poisoned step
         assert ok2 is True
+
+
+# ---------------------------------------------------------------------------------------------- validation under pipeline parallel
+class _ToyValSet:
+    """Token lists below the vocabulary size of ``tiny_config`` (``RandomDataset`` emits repeat counts up to 199)."""
+
+    def __init__(self, n=6, length=24, vocab=100):
+        import torch
+
+        g = torch.Generator().manual_seed(11)
+        self.rows = [torch.randint(1, vocab, (length - i % 5,), generator=g).tolist() for i in range(n)]
+
+    def __len__(self):
+        return len(self.rows)
+
+    def __getitem__(self, i):
+        return {"tokens": self.rows[i], "type_id": 0}
+
+
+class _Log:
+    def __init__(self):
+        self.lines = []
+
+    def info(self, msg, *a, **k):
+        self.lines.append(str(msg))
+
+    warning = error = info
+
+
+def _validate(rank, world, kw):
+    """``evaluate_on_val_dls`` with a validation batch of ONE training micro-batch: fewer micro-batches than pipeline stages."""
+    from functools import partial
+
+    import torch
+
+    from common import build_trainer, tiny_config
+    from internevo_b200.core.context import global_context as gpc
+    from internevo_b200.data.batch_sampler import get_dpsampler_dataloader
+    from internevo_b200.data.collaters import jsonl_ds_collate_fn
+    from internevo_b200.eval.evaluation import evaluate_on_val_dls
+
+    cfg = tiny_config(num_layers=4, micro_num=2, **kw)
+    trainer, opt, model, _ = build_trainer(cfg)
+    dl = get_dpsampler_dataloader(_ToyValSet(), shuffle=False, drop_last=True, batch_size=cfg["data"]["micro_bsz"],
+                                  collate_fn=partial(jsonl_ds_collate_fn, max_length_per_sample=cfg["data"]["seq_len"]))
+    log = _Log()
+    evaluate_on_val_dls(trainer, {"toy": dl}, writer=None, logger=log, step_count=7)
+    line = next((ln for ln in log.lines if ln.startswith("Validation on toy")), None)
+    # training still works after the schedule was switched back
+    from common import synthetic_batch
+
+    T = cfg["data"]["seq_len"] * cfg["data"]["micro_bsz"]
+    data, labels = synthetic_batch(2, T, cfg["model"]["vocab_size"], seed=1)
+    trainer.zero_grad()
+    trainer.execute_schedule((data, labels), forward_only=False, return_loss=True, return_output_label=False)
+    ok, _ = trainer.step()
+    return gpc.is_rank_for_log(), line, ok
+
+
+@pytest.mark.parametrize("name,world,kw", [
+    ("pp2_1f1b", 2, dict(pp=2)),
+    ("pp2_interleaved", 2, dict(pp=2, num_chunks=2)),     # 1 validation micro-batch < 2 stages: the batch is cut row-wise
+    ("tp2_pp2_fsp", 4, dict(tp=2, pp=2, mode="fsp")),
+])
+def test_validation_reports_a_loss_under_pipeline_parallel(name, world, kw):
+    import math
+    import re
+
+    res = run_distributed(_validate, world, kw)
+    assert all(ok for _, _, ok in res)
+    lines = [line for is_log, line, _ in res if is_log]
+    assert lines and all(line is not None for line in lines), (name, res)     # the last pipeline rank logs, whatever chunk ran last
+    loss = float(re.search(r"val/toy_loss=([0-9.]+)", lines[0]).group(1))
+    assert math.isfinite(loss) and 3.0 < loss < 7.0, lines[0]                  # ~ ln(vocab) for an untrained model

@@ -198,11 +198,14 @@ if __name__ == "__main__":
     alert = gpc.config.monitor.alert
     with initialize_monitor_manager(job_name=gpc.config.JOB_NAME,
                                     alert_address=alert.get("feishu_alert_address") if alert.get("enable_feishu_alert") else None):
+        failed = False
         try:
             main(args)
         except Exception:
+            failed = True
             logger.error(f"Raise exception from {hostname} with rank id: {gpc.get_global_rank()}\n{traceback.format_exc()}")
             mm.monitor_exception(alert_address=alert.get("feishu_alert_address", None), excp_info=traceback.format_exc())
             raise
         finally:
-            gpc.destroy()
+            # after an exception the peers may be blocked in a collective: leave without a barrier so the job fails fast
+            gpc.destroy(graceful=not failed)
