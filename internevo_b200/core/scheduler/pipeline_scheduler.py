@@ -251,6 +251,8 @@ class PipelineScheduler(BaseScheduler):
         output, label = pack_return_tensors(return_tensors) if len(return_tensors) > 0 else (None, None)
         if gpc.config.get("model") is not None and hasattr(gpc.config.model, "num_experts"):
             dist.all_reduce(accum_moe_loss, group=gpc.get_group(ParallelMode.PIPELINE))
+            if accum_loss is not None:      # same convention as the training step: the returned loss contains the auxiliary term
+                accum_loss = accum_loss + accum_moe_loss
             return output, label, accum_loss, accum_moe_loss
         return output, label, accum_loss
 

@@ -117,8 +117,10 @@ def evaluate_on_val_dls(trainer, val_dls, writer, logger, step_count, update_pan
                         with switch_evaluation_no_pipeline_scheduler(trainer, num_micro, [hook]):
                             out = trainer.execute_schedule(batch, forward_only=True, return_loss=True, return_output_label=False)
                     loss = out[2]
+                    moe_loss = out[3] if len(out) > 3 else None
                 if gpc.is_no_pp_or_last_stage() and loss is not None:
-                    val_loss += float(loss)
+                    # language-model loss only: the schedulers add the MoE auxiliary loss to what they return (reference ``:107``)
+                    val_loss += float(loss) - (float(moe_loss) if moe_loss is not None else 0.0)
                     n += 1
             if n > 0:
                 res = val_metric.get_metric()

@@ -122,6 +122,9 @@ def _validate(rank, world, kw):
     from internevo_b200.eval.evaluation import evaluate_on_val_dls
 
     cfg = tiny_config(num_layers=4, micro_num=2, **kw)
+    if "num_experts" in kw:      # a LARGE auxiliary coefficient: the reported validation loss must not contain that term
+        cfg["moe"] = dict(top_k=2)
+        cfg["loss"]["moe_loss_coeff"] = 1.0
     trainer, opt, model, _ = build_trainer(cfg)
     dl = get_dpsampler_dataloader(_ToyValSet(), shuffle=False, drop_last=True, batch_size=cfg["data"]["micro_bsz"],
                                   collate_fn=partial(jsonl_ds_collate_fn, max_length_per_sample=cfg["data"]["seq_len"]))
@@ -143,6 +146,8 @@ def _validate(rank, world, kw):
     ("pp2_1f1b", 2, dict(pp=2)),
     ("pp2_interleaved", 2, dict(pp=2, num_chunks=2)),     # 1 validation micro-batch < 2 stages: the batch is cut row-wise
     ("tp2_pp2_fsp", 4, dict(tp=2, pp=2, mode="fsp")),
+    ("moe_ep2", 2, dict(model_type="INTERNLM_MoE", num_experts=4, moe_type="MegaBlock-D")),
+    ("moe_pp2", 2, dict(pp=2, model_type="INTERNLM_MoE", num_experts=2, moe_type="MegaBlock-D")),
 ])
 def test_validation_reports_a_loss_under_pipeline_parallel(name, world, kw):
     import math
