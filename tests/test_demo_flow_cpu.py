@@ -205,3 +205,49 @@ def test_alpaca_sft_shards_train(tmp_path):
                 "gloo"], ROOT, timeout=900, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
     losses = [float(x) for x in re.findall(r"step=\d+ loss=([0-9.]+)", log)]
     assert len(losses) >= 6 and losses[-1] < losses[0] - 0.5, losses
+
+
+def test_flow_with_weight_parallel_checkpoints(tmp_path):
+    """ISP (sequence parallel 2 x weight parallel 2): train on real shards, checkpoint in the ``model_tp{t}_wp{w}_pp{p}.pt`` layout
+    (embedding split along hidden, head rows over the tensor group), `convert2hf` merges it and the HF model has learned the corpus."""
+    import sentencepiece as spm
+
+    from common import find_free_port
+
+    words = ["alpha", "beta", "gamma", "delta", "epsilon", "zeta", "eta", "theta", "iota", "kappa"]
+    rng = np.random.RandomState(0)
+    corpus = tmp_path / "corpus.txt"
+    corpus.write_text("\n".join(" ".join(rng.choice(words, 12)) for _ in range(600)))
+    spm.SentencePieceTrainer.Train(input=str(corpus), model_prefix=str(tmp_path / "tok"), vocab_size=64, bos_id=1, eos_id=2,
+                                   unk_id=0, pad_id=-1, model_type="bpe", minloglevel=2)
+    tok_model = str(tmp_path / "tok.model")
+    for split in ("train", "valid"):
+        os.makedirs(tmp_path / "data" / split / "en")
+        _run([PY, "tools/tokenizer.py", "--text_input_path", str(corpus), "--bin_output_path",
+              str(tmp_path / "data" / split / "en" / "part0.bin"), "--tokenizer_model", tok_model], ROOT)
+    ckpt = tmp_path / "ckpts"
+    text = CONFIG.format(ckpt=ckpt, steps=8, train=tmp_path / "data" / "train", valid=tmp_path / "data" / "valid", hidden=64,
+                         dtype="torch.float32", tp=2, pp=1, model_type="INTERNLM2_PUBLIC", model_extra="", moe_section="")
+    text = text.replace('mode="mtp"', 'mode="isp"').replace("weight=dict(size=1", "weight=dict(size=2")
+    cfg = tmp_path / "cfg_isp.py"
+    cfg.write_text(text)
+    _run([PY, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port",
+          str(find_free_port()), "train.py", "--config", str(cfg), "--launcher", "torch", "--backend", "gloo"], ROOT, timeout=900,
+         env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    files = set(os.listdir(ckpt / "8"))
+    assert {"model_tp0_wp0_pp0.pt", "model_tp1_wp1_pp0.pt", "8.step"} <= files, sorted(files)
+    st = torch.load(ckpt / "8" / "model_tp1_wp1_pp0.pt", weights_only=False)
+    emb = next(v for k, v in st.items() if k.endswith("tok_embeddings.weight"))
+    head = next(v for k, v in st.items() if k.endswith("output.weight"))
+    assert tuple(emb.shape) == (64, 32) and tuple(head.shape) == (32, 64), (emb.shape, head.shape)
+    hf = tmp_path / "hf"
+    _run([PY, "tools/convert2hf.py", "--src", str(ckpt / "8"), "--tgt", str(hf), "--dtype", "float32", "--tokenizer", tok_model,
+          "--max_pos", "128"], ROOT)
+    from transformers import AutoModelForCausalLM, AutoTokenizer
+
+    model = AutoModelForCausalLM.from_pretrained(str(hf), trust_remote_code=True, dtype=torch.float32).eval()
+    tok = AutoTokenizer.from_pretrained(str(hf), trust_remote_code=True)
+    line = tok(corpus.read_text().split("\n")[0], return_tensors="pt")["input_ids"]
+    with torch.no_grad():
+        loss = float(model(input_ids=line, labels=line).loss)
+    assert loss < 3.9, loss        # ln(64) = 4.16 untrained
