@@ -51,8 +51,27 @@ def _run(cmd):
     return r.stdout + r.stderr
 
 
+DATAIO_SO = os.path.join(PKG, "_dataio.so")
+
+
+def build_dataio(force: bool = False) -> str:
+    """Host-only helper library of the data pipeline (``dataio.cpp``: corpus scan, token-line parser; plain C ABI, loaded with
+    ctypes) -> ``internevo_b200/_dataio.so``."""
+    src = os.path.join(HERE, "dataio.cpp")
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    tag = os.path.join(BUILD_DIR, "dataio." + _digest([src]))
+    if force or not os.path.exists(DATAIO_SO) or not os.path.exists(tag):
+        _run(["g++", "-O3", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", DATAIO_SO, src])
+        for f in os.listdir(BUILD_DIR):
+            if f.startswith("dataio."):
+                os.remove(os.path.join(BUILD_DIR, f))
+        open(tag, "w").close()
+    return DATAIO_SO
+
+
 def build(verbose: bool = False, force: bool = False) -> str:
     """Compile everything that is out of date and link ``_C.so``; returns its path."""
+    build_dataio(force)
     import torch
     from torch.utils import cpp_extension
 

@@ -75,6 +75,11 @@ class JsonlDataset(Dataset):
 
     @staticmethod
     def _build_meta(path):
+        from . import _native
+
+        table = _native.scan_jsonl(path)          # one native pass over the file; None: no library / unusual lines
+        if table is not None:
+            return table
         offs, pos = [], 0
         with open(path, "rb") as f:
             for line in f:
@@ -85,7 +90,13 @@ class JsonlDataset(Dataset):
     def __getitem__(self, idx):
         f = self._get_mmap()
         f.seek(int(self.offsets[idx][0]))
-        item = f.readline().decode("utf-8")
+        raw = f.readline()
+        from . import _native
+
+        toks = _native.parse_tokens(raw)          # plain {"tokens": [...]} lines never reach the JSON decoder
+        if toks is not None:
+            return {"tokens": toks.tolist(), "length": int(toks.shape[0]), "type_id": self.type_id}
+        item = raw.decode("utf-8")
         try:
             item = json.loads(item)
             item["length"] = len(item["tokens"])

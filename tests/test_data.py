@@ -195,3 +195,44 @@ def test_unpacked_mode_matches_the_packed_loss_and_gradient_norm():
     assert abs(packed[0] - plain[0]) < 1e-4, (packed, plain)                       # same tokens, same targets, padding ignored
     for k in packed[1]:
         assert abs(packed[1][k] - plain[1][k]) < 1e-3 * max(1.0, packed[1][k]), (packed, plain)
+
+
+# --------------------------------------------------------------------------------------------- native corpus scan / token parser
+def test_native_dataio_matches_the_json_decoder(tmp_path):
+    """``csrc/dataio.cpp`` through ctypes: the .meta table of a shard and every sample are what ``json`` gives; lines in another form
+    (extra keys, floats, empty) are handed back to the JSON decoder instead of being mis-parsed."""
+    import json
+
+    from internevo_b200.data import _native
+    from internevo_b200.data.datasets import JsonlDataset
+
+    assert _native.lib() is not None, "internevo_b200/_dataio.so is built by csrc/build.py (g++ only)"
+    rng = np.random.RandomState(0)
+    rows = [rng.randint(-50000, 90000, size=int(n)).tolist() for n in rng.randint(0, 300, size=200)]
+    rows[3] = []
+    path = tmp_path / "part0.bin"
+    with open(path, "wb") as f:
+        for i, r in enumerate(rows):
+            sep = (", ", ",", " , ")[i % 3]
+            f.write(("{" + '"tokens": [' + sep.join(map(str, r)) + "]}" + ("\n" if i != len(rows) - 1 else "")).encode())
+    table = _native.scan_jsonl(str(path))
+    assert table.shape == (200, 2) and table[:, 1].tolist() == [len(r) for r in rows] and int(table[0, 0]) == 0
+    raw = open(path, "rb").read()
+    for i in (0, 3, 57, 199):
+        end = raw.find(b"\n", int(table[i, 0]))
+        line = raw[int(table[i, 0]): end if end >= 0 else len(raw)]
+        assert json.loads(line)["tokens"] == rows[i] and _native.parse_tokens(line).tolist() == rows[i]
+    ds = JsonlDataset(str(path), dataset_type_id=2, min_length=0)            # no .meta file: built by the native scan
+    assert len(ds) == 200 and ds.num_tokens == sum(len(r) for r in rows)
+    item = ds[57]
+    assert item["tokens"] == rows[57] and item["length"] == len(rows[57]) and item["type_id"] == 2
+    # other shapes fall back to json (parse) / to the Python scan (meta)
+    for odd in (b'{"tokens": [1, 2], "type_id": 5}', b'{"tokens": [1.5]}', b'{"text": "x"}', b'', b'{"tokens": [1,]}',
+                b'{"tokens": [12345678901234567890]}'):
+        assert _native.parse_tokens(odd) is None, odd
+    assert _native.parse_tokens(b' { "tokens" : [ -7 , 8 ] } \n').tolist() == [-7, 8]
+    mixed = tmp_path / "mixed.bin"
+    mixed.write_bytes(b'{"tokens": [1, 2, 3]}\n{"tokens": [4], "note": "extra key"}\n')
+    assert _native.scan_jsonl(str(mixed)) is None
+    ds2 = JsonlDataset(str(mixed), min_length=0)
+    assert ds2.offsets[:, 1].tolist() == [3, 1] and ds2[1]["tokens"] == [4] and ds2[1]["note"] == "extra key"
