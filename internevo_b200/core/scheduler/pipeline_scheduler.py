@@ -48,15 +48,15 @@ def switch_optimizer_grad_sync_skip_mode(optimizer, skip: bool = True):
 
 def get_tensor_shape():
     """Activation shape crossing a stage boundary: ``[tokens (/sp), hidden]`` (reference ``:31-69``)."""
+    if gpc.config is not None and gpc.config.get("TENSOR_SHAPE", None) is not None:
+        return tuple(gpc.config.TENSOR_SHAPE)      # explicit override for user models whose boundary tensor is not [tokens, hidden]
     if not gpc.is_initialized(ParallelMode.PIPELINE) or gpc.config is None:
         return None
     data, model = gpc.config.get("data", None), gpc.config.get("model", None)
     if not data or not model or "hidden_size" not in model:
         return None
-    if gpc.is_evaluating and not data.get("use_packed_dataset", True):
-        tokens = data["micro_bsz"] * data["seq_len"]
-    else:
-        tokens = data["micro_bsz"] * data["seq_len"]
+    # packed or not, one micro-batch carries micro_bsz * seq_len tokens; the stages exchange them flattened
+    tokens = data["micro_bsz"] * data["seq_len"]
     sp = gpc.get_world_size(ParallelMode.TENSOR) if gpc.config.parallel.get("sequence_parallel", False) else 1
     return (tokens // sp, model["hidden_size"])
 

@@ -14,6 +14,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PY = sys.executable
+TRAIN_PY = os.path.join(ROOT, "train.py")      # launched from the test's tmp dir: logs / traces / tensorboards land there
 
 CONFIG = '''
 JOB_NAME = "demo_flow"
@@ -90,8 +91,8 @@ def run_flow(tmp_path, gpu: bool, tp: int = 1, pp: int = 1, moe: bool = False):
         cfg.write_text(text + ("fused_comm = True\n" if gpu else ""))
         env = dict(os.environ) if gpu else dict(os.environ, CUDA_VISIBLE_DEVICES="")
         return _run([PY, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-                     "--master-port", str(port), "train.py", "--config", str(cfg), "--launcher", "torch", "--backend",
-                     "nccl" if gpu else "gloo"], ROOT, timeout=900, env=env)
+                     "--master-port", str(port), TRAIN_PY, "--config", str(cfg), "--launcher", "torch", "--backend",
+                     "nccl" if gpu else "gloo"], str(tmp_path), timeout=900, env=env)
 
     from common import find_free_port
 
@@ -150,8 +151,8 @@ def run_flow(tmp_path, gpu: bool, tp: int = 1, pp: int = 1, moe: bool = False):
     cfg = tmp_path / "cfg_sft.py"
     cfg.write_text(text)
     log = _run([PY, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                "--master-port", str(find_free_port()), "train.py", "--config", str(cfg), "--launcher", "torch", "--backend",
-                "gloo"], ROOT, timeout=900, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+                "--master-port", str(find_free_port()), TRAIN_PY, "--config", str(cfg), "--launcher", "torch", "--backend",
+                "gloo"], str(tmp_path), timeout=900, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
     import re
 
     first = re.search(r"step=0 loss=([0-9.]+)", log)
@@ -201,8 +202,8 @@ def test_alpaca_sft_shards_train(tmp_path):
     cfg = tmp_path / "cfg.py"
     cfg.write_text(text)
     log = _run([PY, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                "--master-port", str(find_free_port()), "train.py", "--config", str(cfg), "--launcher", "torch", "--backend",
-                "gloo"], ROOT, timeout=900, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+                "--master-port", str(find_free_port()), TRAIN_PY, "--config", str(cfg), "--launcher", "torch", "--backend",
+                "gloo"], str(tmp_path), timeout=900, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
     losses = [float(x) for x in re.findall(r"step=\d+ loss=([0-9.]+)", log)]
     assert len(losses) >= 6 and losses[-1] < losses[0] - 0.5, losses
 
@@ -232,7 +233,7 @@ def test_flow_with_weight_parallel_checkpoints(tmp_path):
     cfg = tmp_path / "cfg_isp.py"
     cfg.write_text(text)
     _run([PY, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port",
-          str(find_free_port()), "train.py", "--config", str(cfg), "--launcher", "torch", "--backend", "gloo"], ROOT, timeout=900,
+          str(find_free_port()), TRAIN_PY, "--config", str(cfg), "--launcher", "torch", "--backend", "gloo"], str(tmp_path), timeout=900,
          env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
     files = set(os.listdir(ckpt / "8"))
     assert {"model_tp0_wp0_pp0.pt", "model_tp1_wp1_pp0.pt", "8.step"} <= files, sorted(files)
