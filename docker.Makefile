@@ -2,6 +2,7 @@
 #   make -f docker.Makefile devel-ubuntu     full image: toolchain + built extension + test deps
 #   make -f docker.Makefile runtime-ubuntu   slim image: python package + _C.so only
 #   make -f docker.Makefile devel-rocky      same on a RHEL-family base
+#   make -f docker.Makefile experiment       next-toolchain test image (experiment/README.md)
 DOCKER_REGISTRY ?= docker.io
 DOCKER_ORG      ?= internevo-b200
 DOCKER_IMAGE    ?= internevo_b200
@@ -12,7 +13,7 @@ TAG             ?= $(VERSION)-cuda$(CUDA_VERSION)
 BUILD           ?= docker build --progress=plain
 NAME             = $(DOCKER_REGISTRY)/$(DOCKER_ORG)/$(DOCKER_IMAGE)
 
-.PHONY: all devel-ubuntu runtime-ubuntu devel-rocky push clean
+.PHONY: all devel-ubuntu runtime-ubuntu devel-rocky experiment push clean
 all: devel-ubuntu
 
 devel-ubuntu:
@@ -23,6 +24,9 @@ runtime-ubuntu:
 
 devel-rocky:
 	$(BUILD) --build-arg CUDA_VERSION=$(CUDA_VERSION) -t $(NAME):$(TAG)-devel-rocky -f docker/Dockerfile-rocky .
+
+experiment:
+	$(BUILD) --build-arg BASE=$(TORCH_IMAGE) -t $(NAME):$(VERSION)-experiment -f experiment/Dockerfile-next .
 
 push:
 	docker push $(NAME):$(TAG)-devel-ubuntu

@@ -254,3 +254,38 @@ def test_ckpt_io_merges_weight_parallel_checkpoints(tmp_path):
         assert tuple(one["layers.0.feed_forward.w2.weight"].shape) == (h // wp, F)
         back = ckpt_io.load_full_state(d)
         assert set(back) == set(full) and all(torch.equal(back[k], full[k]) for k in full), (tp, wp)
+
+
+def test_ci_flow_driver_runs_the_user_journey_on_two_cpu_ranks(tmp_path):
+    """``ci_scripts/flow.py all``: shards -> train.py (case merged over configs/demo.py, checkpoint file set checked) -> HF
+    conversion -> Auto* load -> resumed second launch; plus the pieces on their own (case merge, expected file sets)."""
+    import subprocess
+
+    import numpy as np
+    import sentencepiece as spm
+
+    sys.path.insert(0, os.path.join(ROOT, "ci_scripts"))
+    import flow
+
+    assert flow.deep_merge({"a": {"b": 1, "c": 2}, "d": 3}, {"a": {"b": 5}, "e": 6}) == {"a": {"b": 5, "c": 2}, "d": 3, "e": 6}
+    cfg = flow.write_case_config("tp2_dp4", str(tmp_path / "tp2.py"))
+    assert cfg["parallel"]["tensor"]["size"] == 2 and cfg["lr_scheduler"]["total_steps"] == cfg["data"]["total_steps"] == 10
+    want = flow.expected_checkpoint_files(cfg, 8, 10)
+    assert {"model_tp0_pp0.pt", "model_tp1_pp0.pt", "optimizer_tp1_pp0_zo3.pt", "10.step"} <= want and len(want) == 5 + 2 + 8
+    from internevo_b200.core.context import Config
+
+    assert Config.from_file(str(tmp_path / "tp2.py")).model["num_layers"] == 8          # the generated file is a loadable config
+
+    words = ["alpha", "beta", "gamma", "delta", "epsilon", "zeta", "eta", "theta", "iota", "kappa"]
+    rng = np.random.RandomState(0)
+    corpus = tmp_path / "corpus.txt"
+    corpus.write_text("\n".join(" ".join(rng.choice(words, 12)) for _ in range(400)))
+    spm.SentencePieceTrainer.Train(input=str(corpus), model_prefix=str(tmp_path / "tok"), vocab_size=64, bos_id=1, eos_id=2,
+                                   unk_id=0, pad_id=-1, model_type="bpe", minloglevel=2)
+    from common import find_free_port
+
+    r = subprocess.run([sys.executable, "ci_scripts/flow.py", "all", "--corpus", str(corpus), "--tokenizer",
+                        str(tmp_path / "tok.model"), "--work", str(tmp_path / "work"), "--case", "cpu_smoke", "--cpu", "--nproc", "2",
+                        "--port", str(find_free_port())], cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "flow ok" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    assert sorted(d for d in os.listdir(tmp_path / "work" / "llm_ckpts") if d.isdigit()) == ["12", "6"]
