@@ -28,27 +28,39 @@ LAYOUTS = {
     "7B_isp_sft_sp8_wp8": ("h8kv8", dict(tp=8, wp=8, mode="isp", micro_num=4)),
     "20B_internlm2_tp4_pp2": ("h8kv4", dict(tp=4, pp=2, micro_num=4)),
     "20B_internlm2_tp4_pp2_msp_interleaved": ("h8kv4", dict(tp=4, pp=2, mode="msp", micro_num=4, num_chunks=2)),
+    # the reference's three-way marks (``16GPU_4DP2TP2PP_{MTP,MSP,FSP}``) with data parallel 2: DP x TP x PP + Hybrid-ZeRO
+    "dp2_tp2_pp2_mtp": ("h4kv2", dict(tp=2, pp=2, mode="mtp", micro_num=2)),
+    "dp2_tp2_pp2_msp": ("h4kv2", dict(tp=2, pp=2, mode="msp", micro_num=2)),
+    "dp2_tp2_pp2_fsp_interleaved": ("h4kv2", dict(tp=2, pp=2, mode="fsp", micro_num=2, num_chunks=2)),
+    "dp2_isp_sp2_wp4_pp2": ("h4kv2", dict(tp=2, wp=4, pp=2, mode="isp", micro_num=2)),
 }
 _baselines = {}
 
 
-def _baseline(shape):
-    if shape not in _baselines:
-        _baselines[shape] = run_distributed(T._train, 1, dict(micro_num=T.MICRO_TOTAL, **SHAPES[shape]))[0]
-    return _baselines[shape]
+def _baseline(shape, isp=False):
+    """Single-process trajectory.  ISP layouts are compared with a single-process run in ISP mode: ISP keeps the embedding and the
+    head in a parameter group of their own and gradient clipping is per GROUP (reference ``hybrid_zero_optim.py:863-876``), so from
+    the second update on its trajectory differs (deterministically, ~2e-4) from the one-group trajectory of the other modes."""
+    if (shape, isp) not in _baselines:
+        kw = dict(micro_num=T.MICRO_TOTAL, **SHAPES[shape])
+        if isp:
+            kw["mode"] = "isp"
+        _baselines[shape, isp] = run_distributed(T._train, 1, kw)[0]
+    return _baselines[shape, isp]
 
 
 @pytest.mark.parametrize("name", list(LAYOUTS))
 def test_baseline_layout_at_8_ranks_matches_single_process(name):
     shape, kw = LAYOUTS[name]
+    isp = kw.get("mode") == "isp"
     res = run_distributed(T._train, WORLD, dict(kw, **SHAPES[shape]), timeout=900)
-    if kw.get("mode") != "isp":
-        _check_union(res, _baseline(shape), 2e-4)
+    if not isp or kw["tp"] <= 2:          # sp = 2: both sequence shards hold the same number of valid labels
+        _check_union(res, _baseline(shape, isp), 2e-4)
         return
     # ISP reports (and back-propagates) the mean over each sequence shard's OWN valid tokens, like the reference: with 8 shards
     # of 8 tokens and the ignored labels at the segment ends the shards weigh their tokens 8/7 : 1, so the trajectory follows the
-    # single-process one closely but not to rounding (with no ignored label the step-0 norm agrees to 1e-7)
-    ref_losses, ref_norms = _baseline(shape)
+    # single-process one closely but not to rounding (with no ignored label it agrees like every other layout)
+    ref_losses, ref_norms = _baseline(shape, isp)
     for losses, _ in res:
         for a, b in zip(losses, ref_losses):
             assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (losses, ref_losses)
