@@ -189,3 +189,43 @@ def _train8(rank, world, kw):
 
     me.MICRO_TOTAL = 8
     return _train(rank, world, kw)
+
+
+def _train_swapped(rank, world, kw):
+    """The SAME token stream cut into ``micro_num`` micro-batches of ``micro_bsz`` packed sequences each."""
+    from internevo_b200.core.context import global_context as gpc  # noqa: F401  (initialised by build_trainer)
+
+    micro_num, micro_bsz, seq_len, total_rows = kw["micro_num"], kw["micro_bsz"], 32, 4
+    cfg = tiny_config(micro_num=micro_num, micro_bsz=micro_bsz, seq_len=seq_len)
+    trainer, opt, model, _ = build_trainer(cfg)
+    _load_golden(model, opt, cfg)
+    losses, norms = [], None
+    for step in range(STEPS):
+        # four sequences of seq_len tokens; a micro-batch packs micro_bsz of them into one row
+        data, labels = synthetic_batch(total_rows, seq_len, cfg["model"]["vocab_size"], seed=step, segments=1)
+        rows = total_rows // micro_bsz
+        ids = data["input_ids"].reshape(rows, micro_bsz * seq_len)
+        cu = torch.arange(0, micro_bsz * seq_len + 1, seq_len, dtype=torch.int32).repeat(rows, 1)
+        idx = torch.arange(seq_len).repeat(rows, micro_bsz)
+        assert rows == micro_num
+        trainer.zero_grad()
+        out = trainer.execute_schedule(({"input_ids": ids, "cu_seqlens": cu, "indexes": idx},
+                                        labels.reshape(rows, micro_bsz * seq_len)),
+                                       forward_only=False, return_loss=True, return_output_label=False)
+        ok, norms = trainer.step()
+        assert ok
+        losses.append(float(out[2]))
+    return losses, norms
+
+
+def test_swapping_micro_num_and_micro_bsz_keeps_loss_and_grad_norm():
+    """Counterpart of the reference's ``tests/test_training/test_swap_nb_loss_and_gradnorm.py``: 4 micro-batches of one sequence,
+    2 of two and 1 of four see the same tokens with the same per-token weights, so loss and gradient norm agree step by step."""
+    runs = {mn: run_distributed(_train_swapped, 1, dict(micro_num=mn, micro_bsz=4 // mn))[0] for mn in (4, 2, 1)}
+    ref_losses, ref_norms = runs[4]
+    for mn in (2, 1):
+        losses, norms = runs[mn]
+        for a, b in zip(losses, ref_losses):
+            assert abs(a - b) < 2e-5 * max(1.0, abs(b)), (mn, losses, ref_losses)
+        for k, v in ref_norms.items():
+            assert abs(norms[k] - v) < 1e-4 * max(1.0, v), (mn, norms, ref_norms)
