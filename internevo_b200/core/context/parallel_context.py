@@ -233,6 +233,10 @@ class ParallelContext:
                     if ":" in host else f"tcp://{host}:{port}", timeout=LLM_NCCL_TIMEOUT,
                 )
             group = dist.group.WORLD
+            # which ranks share this rank's node: the peer-memory (NVLink) back-ends only serve groups that stay inside one
+            from internevo_b200.parallel import symm
+
+            symm.exchange_node_ids()
         else:
             group = None  # single process: no communicator at all
         self._global_ranks[ParallelMode.GLOBAL] = rank

@@ -17,3 +17,5 @@ def reset_caches() -> None:
         mods["internevo_b200.parallel.sp_attention"].reset()
     if "internevo_b200.parallel.symm" in mods:
         mods["internevo_b200.parallel.symm"]._flags_cache.clear()
+        mods["internevo_b200.parallel.symm"]._intra_cache.clear()
+        mods["internevo_b200.parallel.symm"]._node_ids = None

@@ -144,7 +144,7 @@ _tp_backends: Dict[int, TPFusedBackend] = {}
 
 def enable_tp(group: Optional[dist.ProcessGroup]) -> Optional[TPFusedBackend]:
     """Create (once) the fused backend for ``group`` and route the TP linears through it."""
-    if group is None or dist.get_world_size(group) <= 1 or not symm.symm_available():
+    if group is None or dist.get_world_size(group) <= 1 or not symm.peer_addressable(group):
         return None
     # Default on: the collective runs inside the CTA-pair tcgen05 GEMM (B200_TP_FUSED=0 selects 2-CTA GEMM + NCCL, which is
     # also the numerical oracle of tests/test_fused_comm_gpu.py).
@@ -244,7 +244,7 @@ _isp_backends: Dict[int, ISPFusedBackend] = {}
 def isp_backend(group: Optional[dist.ProcessGroup]) -> Optional[ISPFusedBackend]:
     """The fused weight-parallel backend of ``group`` (created on first use); ``None`` when peer memory is unavailable, the
     group is trivial or ``B200_ISP_FUSED=0`` (NCCL prefetch path, also the numerical oracle)."""
-    if group is None or dist.get_world_size(group) not in (2, 4, 8) or not symm.symm_available():
+    if group is None or dist.get_world_size(group) not in (2, 4, 8) or not symm.peer_addressable(group):
         return None
     if os.environ.get("B200_ISP_FUSED", "1") == "0":
         return None
@@ -282,6 +282,8 @@ class ZeroFusedBackend:
             if not same or g.zero_size not in (2, 4, 8):
                 continue
             group = gpc.get_group(g.zero_mode)
+            if not symm.group_is_intra_node(group):
+                continue        # the ZeRO group leaves the node: its reduce-scatter / all-gather stay on NCCL
             # move both arenas into symmetric memory (parameters and grad_buf views are re-pointed)
             pbuf = symm.SymmBuffer(g.total, torch.bfloat16, group, zero=False)
             gbuf = symm.SymmBuffer(g.total, torch.bfloat16, group, zero=True)

@@ -104,7 +104,7 @@ _backends: Dict[Tuple[int, int, int, int], MoEFusedBackend] = {}
 def backend_for(group, hidden: int, max_rows: int, num_experts: int) -> Optional[MoEFusedBackend]:
     """One backend per (group, hidden): the slabs are shared by all MoE layers of the model (they are used strictly one
     layer at a time, every use bracketed by device barriers)."""
-    if not symm.symm_available() or dist.get_world_size(group) not in (2, 4, 8):
+    if dist.get_world_size(group) not in (2, 4, 8) or not symm.peer_addressable(group):
         return None
     key = (id(group), hidden, num_experts, 0)
     be = _backends.get(key)

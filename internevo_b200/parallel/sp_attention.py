@@ -57,7 +57,7 @@ _backends: Dict[Tuple, SPAttentionBackend] = {}
 
 
 def backend_for(group, t_local: int, H: int, Hkv: int, D: int) -> Optional[SPAttentionBackend]:
-    if group is None or dist.get_world_size(group) not in (2, 4, 8) or not symm.symm_available():
+    if group is None or dist.get_world_size(group) not in (2, 4, 8) or not symm.peer_addressable(group):
         return None
     key = (id(group), t_local, H, Hkv, D)
     be = _backends.get(key)

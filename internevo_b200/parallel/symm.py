@@ -12,7 +12,8 @@ value ``>=`` the epoch of the operation, so flags never need to be cleared betwe
 from __future__ import annotations
 
 import os
-from typing import Dict, List
+import socket
+from typing import Dict, List, Optional
 
 import torch
 import torch.distributed as dist
@@ -53,6 +54,74 @@ def symm_available() -> bool:
         return True
     except Exception:
         return False
+
+
+# ---- which groups are peer-addressable -------------------------------------------------------------------------------------
+# Peer loads / stores reach the GPUs of ONE NVLink domain - one node here.  A process group that spans nodes (data parallel over
+# two 8-GPU boxes, a pipeline across nodes) keeps its collectives on NCCL; groups inside a node (tensor, weight, expert, a ZeRO
+# sub-group) get the peer-memory kernels.  Every rank publishes an identity of its node in the rendezvous store once, right
+# after ``init_process_group`` (host-side key / value traffic only - no communicator is created for it), and a group is
+# peer-addressable when all its members published the same identity.
+_node_ids: Optional[List[str]] = None
+
+
+def this_node() -> str:
+    """Identity of the machine (and container) this rank runs on.  ``B200_NODE_ID`` overrides it (tests simulate several nodes
+    on one box with it; a site whose containers share one IPC namespace can give them one id)."""
+    forced = os.environ.get("B200_NODE_ID")
+    if forced:
+        return forced
+    try:
+        with open("/proc/sys/kernel/random/boot_id") as f:
+            boot = f.read().strip()
+    except OSError:
+        boot = ""
+    return f"{socket.gethostname()}/{boot}"
+
+
+def exchange_node_ids() -> Optional[List[str]]:
+    """Publish this rank's node identity and read everybody's (called by ``ParallelContext.init_global_dist``)."""
+    global _node_ids
+    _node_ids = None
+    if not dist.is_initialized():
+        return None
+    rank, world = dist.get_rank(), dist.get_world_size()
+    try:
+        store = dist.distributed_c10d._get_default_store()
+        store.set(f"b200/node_id/{rank}", this_node())
+        _node_ids = [store.get(f"b200/node_id/{r}").decode() for r in range(world)]
+    except Exception:  # pragma: no cover - a launcher without a key / value store: fall back to the launcher's own statement
+        local = int(os.environ.get("LOCAL_WORLD_SIZE", "0") or 0)
+        _node_ids = ["node0"] * world if local == world else None
+    return _node_ids
+
+
+def node_ids() -> Optional[List[str]]:
+    return _node_ids
+
+
+def group_is_intra_node(group: Optional[dist.ProcessGroup]) -> bool:
+    """True when every rank of ``group`` runs on this rank's node.  Pure table look-up after ``exchange_node_ids``; a process
+    that never exchanged (the groups were made outside ``gpc``) asks the group itself once."""
+    if group is None or not dist.is_initialized():
+        return True
+    if _node_ids is not None:
+        ranks = dist.get_process_group_ranks(group)
+        return len({_node_ids[r] for r in ranks}) == 1
+    key = id(group)
+    if key not in _intra_cache:
+        seen = [None] * dist.get_world_size(group)
+        dist.all_gather_object(seen, this_node(), group=group)
+        _intra_cache[key] = len(set(seen)) == 1
+    return _intra_cache[key]
+
+
+_intra_cache: Dict[int, bool] = {}
+
+
+def peer_addressable(group: Optional[dist.ProcessGroup]) -> bool:
+    """Can the peer-memory kernels serve ``group``: symmetric memory is there and the group does not leave the node."""
+    return symm_available() and group_is_intra_node(group)
 
 
 class SymmBuffer:

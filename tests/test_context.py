@@ -111,3 +111,39 @@ def test_initializer_classes_are_views_of_the_layout_table():
                  zero1_parallel_size=16, weight_data_parallel_size=16, expert_parallel_size=4)
     ep, edp = Initializer_Expert_Data(6, **margs).init_dist_group()
     assert ep[4] == [4, 5, 6, 7] and edp[4] == [2, 6, 10, 14] and ep[5] is ParallelMode.EXPERT
+
+
+def _node_locality(rank, world, kw):
+    import os
+
+    os.environ["B200_NODE_ID"] = f"node{rank // 2}"      # two "nodes" of two ranks each on this box
+    from common import tiny_config
+
+    from internevo_b200.core.context import ParallelMode, global_context as gpc
+    from internevo_b200.initialize import initialize_distributed_env
+    from internevo_b200.parallel import fused, moe_fused, sp_attention, symm
+
+    initialize_distributed_env(config=tiny_config(tp=2), launcher="torch", seed=1)
+    assert symm.node_ids() == ["node0", "node0", "node1", "node1"], symm.node_ids()
+    tensor, data = gpc.get_group(ParallelMode.TENSOR), gpc.get_group(ParallelMode.DATA)
+    intra = (symm.group_is_intra_node(tensor), symm.group_is_intra_node(data), symm.group_is_intra_node(None))
+    # with symmetric memory "present" the back-ends still refuse the group that leaves the node (and never touch CUDA for it)
+    symm.symm_available = lambda: True
+    refused = (symm.peer_addressable(data), fused.enable_tp(data), fused.isp_backend(data),
+               moe_fused.backend_for(data, 64, 128, 4), sp_attention.backend_for(data, 64, 4, 2, 16))
+    tensor_ok = symm.peer_addressable(tensor)
+    # groups made outside gpc (no table): the group itself is asked once
+    symm._node_ids = None
+    asked = (symm.group_is_intra_node(tensor), symm.group_is_intra_node(data))
+    return intra, refused, tensor_ok, asked
+
+
+def test_peer_memory_backends_only_serve_groups_inside_one_node():
+    """Multi-node jobs: tensor groups (ranks {0,1}, {2,3}) stay inside a node and may use peer memory; the data-parallel groups
+    ({0,2}, {1,3}) cross nodes, so every peer-memory back-end declines them and their collectives stay on NCCL."""
+    from common import run_distributed
+
+    for intra, refused, tensor_ok, asked in run_distributed(_node_locality, 4, {}):
+        assert intra == (True, False, True) and asked == (True, False)
+        assert refused == (False, None, None, None, None)
+        assert tensor_ok is True
