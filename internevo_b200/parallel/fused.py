@@ -153,7 +153,11 @@ def enable_tp(group: Optional[dist.ProcessGroup]) -> Optional[TPFusedBackend]:
         return None
     key = id(group)
     if key not in _tp_backends:
-        _tp_backends[key] = TPFusedBackend(group)
+        try:
+            _tp_backends[key] = TPFusedBackend(group)
+        except Exception as e:  # pragma: no cover - depends on driver / topology (no P2P between the group's GPUs)
+            logger.warning(f"fused TP linears unavailable ({e}); using the 2-CTA tcgen05 GEMM + NCCL")
+            return None
     from . import linear
 
     linear.set_fused_backend(_tp_backends[key])

@@ -28,8 +28,11 @@ import torch
 import torch.distributed as dist
 
 from internevo_b200.ops.gemm import _bump
+from internevo_b200.utils.logger import get_logger
 
 from . import symm
+
+logger = get_logger(__file__)
 
 
 class SPAttentionBackend:
@@ -60,11 +63,13 @@ def backend_for(group, t_local: int, H: int, Hkv: int, D: int) -> Optional[SPAtt
     if group is None or dist.get_world_size(group) not in (2, 4, 8) or not symm.peer_addressable(group):
         return None
     key = (id(group), t_local, H, Hkv, D)
-    be = _backends.get(key)
-    if be is None:
-        be = SPAttentionBackend(group, t_local, H, Hkv, D)
-        _backends[key] = be
-    return be
+    if key not in _backends:
+        try:
+            _backends[key] = SPAttentionBackend(group, t_local, H, Hkv, D)
+        except Exception as e:  # pragma: no cover - depends on driver / topology (no P2P between the group's GPUs)
+            logger.warning(f"peer-K/V attention unavailable ({e}); using the all-to-all (Ulysses) form")
+            _backends[key] = None
+    return _backends[key]
 
 
 def reset() -> None:
