@@ -273,12 +273,75 @@ def _optimizer_fn():
     return f"optimizer_tp{tp}_pp{pp}_zo{gpc.get_local_rank(ParallelMode.ZERO1)}.pt"
 
 
+def _optimizer_format() -> str:
+    ck = gpc.config.get("ckpt", None) if gpc.config is not None else None
+    fmt = ck.get("optimizer_ckpt_format", "internevo_b200") if ck is not None else "internevo_b200"
+    assert fmt in ("internevo_b200", "reference"), f"ckpt.optimizer_ckpt_format: 'internevo_b200' or 'reference', got {fmt!r}"
+    return fmt
+
+
+def _convertible(optim) -> bool:
+    """The layout converters need the arena optimizer with its model bound, outside ISP (whose optimizer files are per (tp, wp,
+    pp, dp) coordinate and whose embedding / head change their sharding between memory and file)."""
+    return hasattr(optim, "groups") and getattr(optim, "_model", None) is not None and not is_using_isp()
+
+
+def _gather_named(optim) -> dict:
+    """Per-parameter optimizer state of this (tp, pp) coordinate, assembled over the ZeRO group (every rank gets all of it;
+    gathered range by range so the transient buffer is one range, not the arena)."""
+    from collections import OrderedDict
+
+    import torch.distributed as dist
+
+    from .optimizer_interchange import _FILE_KEY, KINDS
+
+    optim.flush_param_update()
+    named = {"grad_scaler": optim.grad_scaler.state_dict(), "groups": OrderedDict()}
+    for g in optim.groups:
+        compact = {"master": g.master, "exp_avg": g.exp_avg, "exp_avg_sq": g.exp_avg_sq}
+        full = {}
+        for k in KINDS:
+            if g.zero_size == 1:
+                full[k] = compact[k].detach().float().cpu()
+                continue
+            out, group = torch.empty(g.total, dtype=torch.float32), gpc.get_group(g.zero_mode)
+            for lo, hi in g.ranges:
+                n = (hi - lo) // g.zero_size
+                mine = compact[k][lo // g.zero_size: lo // g.zero_size + n].contiguous()
+                parts = [torch.empty_like(mine) for _ in range(g.zero_size)]
+                dist.all_gather(parts, mine, group=group)
+                out[lo:hi] = torch.cat(parts).float().cpu()
+            full[k] = out
+        params = OrderedDict()
+        for p in g.ordered:
+            o = g.offsets[id(p)]
+            params[optim.param_name(p)] = {k: full[k][o: o + p.numel()].view(p.shape).clone() for k in KINDS}
+        named["groups"][g.name] = {"step": g.step, "hyper": {k: v for k, v in g.cfg.items() if k != "params"}, "params": params}
+    assert set(_FILE_KEY) == set(KINDS)
+    return named
+
+
 def save_optimizer_checkpoint(optim, state_path):
-    """One file per (tp, pp, zero) coordinate; ranks beyond the first ZeRO replica hold identical shards and skip."""
+    """One file per (tp, pp, zero) coordinate; ranks beyond the first ZeRO replica hold identical shards and skip.
+    ``ckpt.optimizer_ckpt_format = "reference"`` writes the files in the reference's layout (whole parameters per ZeRO rank, one
+    flat buffer per group; ``checkpoint/optimizer_interchange.py``) so that the reference can resume from them."""
     if optim is None or state_path is None:
         return
     zero_size = gpc.get_world_size(ParallelMode.ZERO1)
     dp_rank = gpc.get_local_rank(ParallelMode.WEIGHT_DATA if is_using_isp() else ParallelMode.DATA)
+    if _optimizer_format() == "reference":
+        assert _convertible(optim), "ckpt.optimizer_ckpt_format='reference' needs HybridZeroOptimizer (not FSDP) and no ISP"
+        from .optimizer_interchange import reference_file_from_named
+
+        named = _gather_named(optim)            # collective over the ZeRO groups: every rank takes part before anyone returns
+        if dp_rank >= zero_size:
+            return
+        moe = gpc.expert_parallel_group_names[0] if gpc.expert_parallel_group_names else None
+        layout = {g.name: (g.zero_size, g.zero_rank) for g in optim.groups}
+        layout.setdefault("default", (zero_size, gpc.get_local_rank(ParallelMode.ZERO1)))
+        mine = reference_file_from_named(named, optim._model, gpc.config.model.get("dtype", torch.float32), layout, moe_group=moe)
+        llm_save(os.path.join(state_path, _optimizer_fn()), saved_obj=mine)
+        return
     if dp_rank >= zero_size and not is_using_isp():
         return
     states = optim.state_dict()
@@ -287,7 +350,18 @@ def save_optimizer_checkpoint(optim, state_path):
         llm_save(os.path.join(state_path, optim.rank_unique_id), saved_obj=states["zero_devide_optim_plan"])
 
 
+def _same_arena_layout(optim, states) -> bool:
+    if not hasattr(optim, "groups") or "groups" not in states or len(states["groups"]) != len(optim.groups):
+        return False
+    return all(st.get("layout") == "range-interleaved" and st["total"] == g.total and st["zero_size"] == g.zero_size
+               and st["zero_rank"] == g.zero_rank and [tuple(r) for r in st["ranges"]] == g.ranges
+               for g, st in zip(optim.groups, states["groups"]))
+
+
 def load_optimizer_checkpoint(folder, optim):
+    """Loads this rank's optimizer shard.  Files written with the current layout are read directly; files of ANOTHER layout -
+    a different ZeRO / data-parallel size or bucket size, or the reference's own parameter-wise files - are converted through
+    the per-parameter form (every rank reads the ZeRO shards of its (tp, pp) coordinate; ``optimizer_interchange.py``)."""
     fns = get_fns(folder)
     max_tp = max_pp = max_zo = 0
     for fn in fns:
@@ -297,15 +371,75 @@ def load_optimizer_checkpoint(folder, optim):
             _, tp, pp, zo = os.path.splitext(fn)[0].split("_")
             max_zo, max_tp, max_pp = max(max_zo, int(zo[2:])), max(max_tp, int(tp[2:])), max(max_pp, int(pp[2:]))
     if not is_using_isp():
-        assert gpc.get_world_size(ParallelMode.ZERO1) == max_zo + 1, (
-            f"The optimizer states are save for {max_zo + 1} zero parallel, while current has "
-            f"{gpc.get_world_size(ParallelMode.ZERO1)} zero broadcast range.")
         assert gpc.get_world_size(ParallelMode.PIPELINE) == max_pp + 1 and gpc.get_world_size(ParallelMode.TENSOR) == max_tp + 1
-    states = llm_load(os.path.join(folder, _optimizer_fn()), map_location="cpu")
+    mine = _optimizer_fn()
+    probe = mine if mine in fns or is_using_isp() else mine[: mine.rindex("_zo")] + "_zo0.pt"
+    states = llm_load(os.path.join(folder, probe), map_location="cpu")
+    reference_format = "base_optim_states" in states
+    if reference_format or (not is_using_isp() and not _same_arena_layout(optim, states)
+                            and not gpc.config.get("only_load_lr", False)):
+        assert _convertible(optim), (
+            f"The optimizer states are saved for {max_zo + 1} zero parallel in another layout, while current has "
+            f"{gpc.get_world_size(ParallelMode.ZERO1)} zero broadcast range, and this optimizer cannot convert them")
+        from .optimizer_interchange import arena_states_from_named, named_from_arena_files, named_from_reference
+
+        prefix, cache = mine[: mine.rindex("_zo")], {probe: states}
+
+        def zo_file(z):
+            fn = f"{prefix}_zo{z}.pt"
+            if fn not in cache:
+                cache[fn] = llm_load(os.path.join(folder, fn), map_location="cpu")
+            return cache[fn]
+
+        if reference_format:
+            if gpc.config.get("only_load_lr", False):
+                optim.grad_scaler.load_state_dict(states["grad_scaler"])
+                lrs = {pg.get("name"): pg["lr"] for pg in states["base_optim_states"]["param_groups"] if "lr" in pg}
+                for g in optim.groups:
+                    if g.name in lrs:
+                        g.cfg["lr"] = lrs[g.name]
+                return
+            model_keys = llm_load(os.path.join(folder, _model_fn()), map_location="cpu")
+            moe = gpc.expert_parallel_group_names[0] if gpc.expert_parallel_group_names else None
+            if moe is not None:      # the reference keeps expert weights in per-expert files: put them back in key order
+                model_keys = _with_expert_keys(folder, fns, optim._model, model_keys)
+
+            def files_of_group(name):
+                if name == moe and gpc.is_initialized(ParallelMode.EXPERT_DATA):
+                    # the replicas of this rank's experts: their files are named by their rank in the ZERO1 group
+                    zero_ranks = gpc.get_ranks_in_group(ParallelMode.ZERO1)
+                    return [zo_file(zero_ranks.index(r)) for r in gpc.get_ranks_in_group(ParallelMode.EXPERT_DATA)]
+                return [zo_file(z) for z in range(max_zo + 1)]
+
+            named = named_from_reference(files_of_group, model_keys, optim._model, optim,
+                                         gpc.config.model.get("dtype", torch.float32), moe_group=moe)
+            what = "the reference's parameter-wise layout"
+        else:
+            named = named_from_arena_files([zo_file(z) for z in range(max_zo + 1)])
+            what = f"a {max_zo + 1}-way ZeRO layout"
+        if gpc.is_rank_for_log():
+            logger.info(f"optimizer checkpoint {folder}: converting from {what} to the current "
+                        f"{gpc.get_world_size(ParallelMode.ZERO1)}-way arena layout")
+        states = arena_states_from_named(named, optim)
+        del cache, named
     optim.load_state_dict(states)
     del states
     if torch.cuda.is_available():
         torch.cuda.empty_cache()
+
+
+def _with_expert_keys(folder, fns, model, model_keys: dict) -> dict:
+    """The reference's model state dict (its key order untouched) followed by this rank's expert tensors in registration order
+    (local numbering).  Experts form an optimizer group of their own, so only the order AMONG them matters."""
+    from collections import OrderedDict
+
+    from .optimizer_interchange import _reference_order
+
+    experts = _load_expert_files(folder, fns, model)
+    merged = OrderedDict(model_keys)
+    for k in _reference_order([k for k in get_shard_state_dict(model).keys() if k in experts]):
+        merged[k] = experts[k]
+    return merged
 
 
 def load_sampler(ckpt_path: str, sampler):

@@ -263,6 +263,7 @@ class HybridZeroOptimizer:
         self._owner_seen: Dict[int, int] = {}        # id(module) -> update generation it has already waited for
         self._update_gen = 0
         self._model_attached = False
+        self._model, self._param_names = None, {}       # bind_model(): names for the checkpoint plan / the state converters
         self._pp_group_names = None   # union of parameter-group names over the pipeline group (agreed at the first step)
         self._group_of: Dict[int, _GroupState] = {}
         self.overlap_stats = {"hook_launches": 0, "step_launches": 0}   # ranges reduced during backward / inside step()
@@ -552,6 +553,19 @@ class HybridZeroOptimizer:
     # forward order) on a side stream; the pre-forward hook of every block makes the compute stream wait for the ranges that
     # hold that block's parameters only.  The backward of the next step cannot start before its forward, so the gradients a
     # range reads are never overwritten early.  Same arithmetic, same order of operations per element.
+    def bind_model(self, model) -> None:
+        """Remember the model: parameter names go into the checkpoint's plan, and the checkpoint converters translate optimizer
+        state through the model's state-dict hooks (``checkpoint/optimizer_interchange.py``)."""
+        # the object the checkpoint manager saves: the AMP wrapper is looked through, a list of pipeline chunks is kept
+        inner = model.model if hasattr(model, "model") and not isinstance(model, torch.nn.ModuleList) else model
+        self._model = inner
+        self._param_names = {id(p): n for n, p in inner.named_parameters()}
+
+    def param_name(self, p) -> str:
+        name = self._param_names.get(id(p))
+        assert name is not None, "HybridZeroOptimizer.bind_model(model) has not been called: parameter names are unknown"
+        return name
+
     def attach_model(self, model) -> None:
         """Register the pre-forward hooks (called once by ``initialize_optimizer``).  A transformer block waits as a whole -
         its forward may read ``self.w13.weight`` or a gate weight without calling the sub-module that owns it - and every
@@ -749,6 +763,8 @@ class HybridZeroOptimizer:
             states["zero_devide_optim_plan"][g.name] = {
                 "zero_rank": g.zero_rank, "zero_size": g.zero_size, "ranges": [list(r) for r in g.ranges],
                 "offsets": [(list(p.shape), g.offsets[id(p)]) for p in g.ordered],
+                # parameter names make the file layout-free: it can be re-sharded / converted (checkpoint/optimizer_interchange.py)
+                "names": [self._param_names.get(id(p)) for p in g.ordered],
             }
         return states
 

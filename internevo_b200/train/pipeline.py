@@ -182,6 +182,8 @@ def initialize_optimizer(model: Union[nn.Module, nn.ModuleList], isp_communicato
     else:
         optimizer = HybridZeroOptimizer(naive, grad_scal_cfg=gpc.config.grad_scaler, zero_cfg=zero_cfg,
                                         isp_communicator=isp_communicator)
+    if hasattr(optimizer, "bind_model"):
+        optimizer.bind_model(model)
     if hasattr(optimizer, "attach_model"):
         optimizer.attach_model(model)   # pre-forward hooks of the update / forward overlap (unsharded groups on CUDA)
     beta2_scheduler = Beta2Scheduler(optimizer=naive, **gpc.config.beta2_scheduler)

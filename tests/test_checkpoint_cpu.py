@@ -99,7 +99,10 @@ def _run_layout(rank, world, folder, phase, kw, moe):
 
     kw = dict(kw)
     bucket = kw.pop("overlap_bucket", None)
+    ckpt_extra = kw.pop("ckpt_extra", {})
+    top_level = kw.pop("top_level", {})
     cfg = tiny_config(num_layers=2, micro_num=2, **kw)
+    cfg.update(top_level)
     if bucket:   # Hybrid-ZeRO with many small ranges reduced from the grad hooks: optimizer shards are range-interleaved
         cfg["hybrid_zero_optimizer"].update(overlap_sync_grad=True, reduce_bucket_size=bucket)
     if moe:
@@ -109,6 +112,8 @@ def _run_layout(rank, world, folder, phase, kw, moe):
         cfg["loss"]["moe_loss_coeff"] = 0.1
     cfg["ckpt"] = dict(enable_save_ckpt=True, save_ckpt_folder=f"local:{folder}", checkpoint_every=2, oss_snapshot_freq=0,
                        auto_resume=(phase == "resume"), async_upload=False)
+    if phase == "first":
+        cfg["ckpt"].update(ckpt_extra)
     trainer, opt, model, _ = build_trainer(cfg)
     dpr = gpc.get_local_rank(ParallelMode.DATA)
     ts = TrainState(gpc.config, None)
