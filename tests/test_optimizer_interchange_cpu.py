@@ -174,3 +174,60 @@ def test_reference_format_round_trip_for_families_and_layouts(tmp_path, name, wo
                 assert abs(la - lb) < 1e-6 * max(1.0, abs(la)), (name, first[r], resumed[r])
             for (ka, va), (kb, vb) in zip(na, nb):
                 assert ka == kb and abs(va - vb) < 1e-5 * max(1.0, abs(va)), (name, na, nb)
+
+
+_REFERENCE_LOADER = r'''
+import json, sys, types, torch
+ref, folder, world, keys = sys.argv[1], sys.argv[2], int(sys.argv[3]), json.loads(sys.argv[4])
+sys.path.insert(0, ref)
+from internlm.core.context import global_context as gpc
+from internlm.core.context.parallel_context import Config
+from internlm.solver.optimizer.hybrid_zero_optim import HybridZeroOptimizer
+gpc._config = Config(dict(only_load_lr=False))
+gpc.is_rank_for_log = lambda: False
+model = torch.load(f"{folder}/model_tp0_pp0.pt", weights_only=False)
+params = [torch.nn.Parameter(model[k].float()) for k in keys]          # the reference's model.parameters(), in ITS order
+part = types.SimpleNamespace(_zero_world_size=[world], params_per_rank_id_dict=[], _overlap_sync_param=False)
+per_rank, _ = HybridZeroOptimizer._partition_param_list(part, 0, {"params": params})
+class Scaler:
+    def load_state_dict(self, st): self.st = st
+for z in range(world):
+    weights = torch.cat([p.detach().reshape(-1) for p in per_rank[z]])
+    flat = torch.zeros_like(weights).requires_grad_()                   # the rank's fp32 master buffer, to be filled by the load
+    low = torch.zeros_like(weights)
+    optim = torch.optim.AdamW([dict(params=[flat], name="default"), dict(params=[], name="fp32")], lr=1.0)
+    me = types.SimpleNamespace(
+        grad_scaler=Scaler(), optim=optim, _fp32_flat_param_groups_of_current_rank={0: flat}, _zero_local_rank=[z, z],
+        param_group_no_params_ranks=[set(), set(range(world))], _fp16_param_groups=[per_rank[z], []],
+        _param_store=types.SimpleNamespace(get_flat_fp16_param_by_rank_group=lambda rank, group_id: low),
+        params_per_rank_id_dict=None)
+    HybridZeroOptimizer.load_state_dict(me, torch.load(f"{folder}/optimizer_tp0_pp0_zo{z}.pt", weights_only=False))
+    # an fp32 run: the master weights ARE the weights - the reference now holds, parameter by parameter, what its model file says
+    assert torch.equal(flat.detach(), weights) and torch.equal(low, weights), z
+    st = optim.state_dict()["state"][0]
+    assert st["exp_avg"].shape == weights.shape and float(st["exp_avg"].abs().sum()) > 0 and float(st["step"]) == 2.0
+    assert optim.param_groups[0]["lr"] != 1.0 and me.params_per_rank_id_dict is not None and "_scale" in me.grad_scaler.st
+print("REFERENCE_LOADED_OK")
+'''
+
+
+def test_the_references_own_loader_accepts_the_exported_files(tmp_path):
+    """Files written with ``optimizer_ckpt_format="reference"`` go through the REFERENCE's ``HybridZeroOptimizer.load_state_dict``
+    (run unbound on a stub that carries what its ``__init__`` would have built: the parameter partition from its own
+    ``_partition_param_list``, one flat fp32 buffer + ``torch.optim.AdamW`` per rank).  torch validates the AdamW state dict, the
+    reference its buffer shapes, and afterwards its master buffer equals the weights of its model file parameter by parameter -
+    which pins the parameter order and the ``w13`` → ``w1`` / ``w3`` translation."""
+    import json
+    import subprocess
+
+    from internevo_b200.checkpoint.optimizer_interchange import _reference_order
+
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "internlm")):
+        pytest.skip("baseline/_ref is not installed")
+    run_distributed(_run, 2, str(tmp_path), "first", 2, "reference")
+    folder = os.path.join(str(tmp_path), "2")
+    keys = _reference_order(list(torch.load(os.path.join(folder, "model_tp0_pp0.pt"), weights_only=False).keys()))
+    r = subprocess.run([sys.executable, "-c", _REFERENCE_LOADER, ref, folder, "2", json.dumps(keys)], capture_output=True,
+                       text=True, timeout=600, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert r.returncode == 0 and "REFERENCE_LOADED_OK" in r.stdout, r.stderr[-3000:]
