@@ -150,11 +150,20 @@ class PipelineScheduler(BaseScheduler):
 
     @staticmethod
     def _prep_stage_input(input_obj, data: dict) -> dict:
-        """non-first stages consume the received activation instead of ``input_ids``"""
+        """Non-first stages consume the received activation instead of ``input_ids``.  The activation crosses the stage boundary
+        flattened to ``[tokens, hidden]``; for an UN-packed batch (validation, ``use_packed_dataset=False``: ``input_ids`` is
+        ``[rows, seq]`` and there is no ``cu_seqlens``) the row structure would be lost with it - the later stage would attend
+        across rows and count positions through them - so it is handed over as uniform segments, exactly what the first
+        stage derives from ``input_ids`` itself."""
         if input_obj is not None:
             data = dict(data)
             data["hidden_states"] = input_obj
-            data.pop("input_ids", None)
+            ids = data.pop("input_ids", None)
+            if torch.is_tensor(ids) and ids.dim() == 2 and data.get("cu_seqlens", None) is None:
+                rows, seq = ids.shape
+                data["cu_seqlens"] = torch.arange(0, (rows + 1) * seq, seq, device=input_obj.device, dtype=torch.int32)
+                data["indexes"] = torch.arange(seq, device=input_obj.device).repeat(rows)
+                data["max_seqlen"] = seq
         return data
 
     def _call_engine(self, engine, data):  # pylint: disable=W0237

@@ -159,3 +159,44 @@ def test_validation_reports_a_loss_under_pipeline_parallel(name, world, kw):
     assert lines and all(line is not None for line in lines), (name, res)     # the last pipeline rank logs, whatever chunk ran last
     loss = float(re.search(r"val/toy_loss=([0-9.]+)", lines[0]).group(1))
     assert math.isfinite(loss) and 3.0 < loss < 7.0, lines[0]                  # ~ ln(vocab) for an untrained model
+
+
+def _validate_golden(rank, world, kw):
+    """Validation loss / accuracy of the SAME weights (``test_parallel_cpu._golden_state``) on the toy validation set."""
+    import re
+    from functools import partial
+
+    from common import build_trainer, tiny_config
+    from internevo_b200.core.context import global_context as gpc
+    from internevo_b200.data.batch_sampler import get_dpsampler_dataloader
+    from internevo_b200.data.collaters import jsonl_ds_collate_fn
+    from internevo_b200.eval.evaluation import evaluate_on_val_dls
+    from test_parallel_cpu import _load_golden
+
+    cfg = tiny_config(num_layers=4, micro_num=2, **kw)
+    trainer, opt, model, _ = build_trainer(cfg)
+    _load_golden(model, opt, cfg)
+    dl = get_dpsampler_dataloader(_ToyValSet(), shuffle=False, drop_last=True, batch_size=2 * cfg["data"]["micro_bsz"],
+                                  collate_fn=partial(jsonl_ds_collate_fn, max_length_per_sample=cfg["data"]["seq_len"]))
+    log = _Log()
+    evaluate_on_val_dls(trainer, {"toy": dl}, writer=None, logger=log, step_count=1)
+    line = next((ln for ln in log.lines if ln.startswith("Validation on toy")), None)
+    if not gpc.is_rank_for_log() or line is None:
+        return None
+    return tuple(float(re.search(rf"val/toy_{k}=([0-9.]+)", line).group(1)) for k in ("loss", "acc"))
+
+
+@pytest.mark.parametrize("name,world,kw", [
+    ("pp2_1f1b", 2, dict(pp=2)),
+    ("pp2_interleaved", 2, dict(pp=2, num_chunks=2)),
+    ("tp2_pp2_msp", 4, dict(tp=2, pp=2, mode="msp")),
+])
+def test_validation_under_pipeline_parallel_equals_the_single_process_value(name, world, kw):
+    """Validation batches are un-packed ``[rows, seq]``: the activation crosses a stage boundary flattened, and a later stage must
+    still see the rows as separate sequences (it used to attend across the rows of a micro-batch and count RoPE positions
+    through them, which moved the reported loss in the fifth digit and the accuracy in the third)."""
+    want = [r for r in run_distributed(_validate_golden, 1, {}) if r is not None][0]
+    got = [r for r in run_distributed(_validate_golden, world, kw) if r is not None]
+    assert got, name
+    for loss, acc in got:
+        assert abs(loss - want[0]) < 2e-6 * max(1.0, want[0]) and abs(acc - want[1]) < 1e-6, (name, got, want)

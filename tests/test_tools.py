@@ -289,3 +289,26 @@ def test_ci_flow_driver_runs_the_user_journey_on_two_cpu_ranks(tmp_path):
                         "--port", str(find_free_port())], cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "flow ok" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
     assert sorted(d for d in os.listdir(tmp_path / "work" / "llm_ckpts") if d.isdigit()) == ["12", "6"]
+
+
+@pytest.mark.parametrize("src_layout,tgt_layout", [((1, 1), (2, 2)), ((2, 2), (4, 1)), ((2, 1), (1, 4))])
+def test_reshard_ckpt_between_tensor_and_pipeline_layouts(tmp_path, src_layout, tgt_layout):
+    """``tools/reshard_ckpt.py``: files of one tp x pp layout → another; merging the result gives the same full model, every
+    stage numbers its layers from 0 and only the first / last stage carry embedding / head."""
+    import ckpt_io
+    import reshard_ckpt
+
+    full, cfg = _fake_internlm2(L=5)        # 5 layers over 2 / 4 stages: uneven stages, later ones larger
+    src, tgt = str(tmp_path / "src"), str(tmp_path / "tgt")
+    ckpt_io.save_sharded(full, src, tp_size=src_layout[0], embed_split_hidden=True, pp_size=src_layout[1])
+    torch.save(dict(cfg, embed_split_hidden=True), os.path.join(src, "model_config.pt"))
+    assert reshard_ckpt.main(["--src", src, "--tgt", tgt, "--tp", str(tgt_layout[0]), "--pp", str(tgt_layout[1])]) == 0
+    assert ckpt_io.find_shards(tgt) == tgt_layout and os.path.exists(os.path.join(tgt, "model_config.pt"))
+    back = ckpt_io.load_full_state(tgt, True)
+    assert set(back) == set(full) and all(torch.equal(back[k], full[k]) for k in full)
+    last = torch.load(os.path.join(tgt, f"model_tp0_pp{tgt_layout[1] - 1}.pt"), weights_only=False)
+    first = torch.load(os.path.join(tgt, "model_tp0_pp0.pt"), weights_only=False)
+    assert "tok_embeddings.weight" in first and "output.weight" in last and "layers.0.attention.wqkv.weight" in last
+    if tgt_layout[1] > 1:
+        assert "output.weight" not in first and "tok_embeddings.weight" not in last
+        assert first["layers.0.attention.wqkv.weight"].shape[0] * tgt_layout[0] == full["layers.0.attention.wqkv.weight"].shape[0]

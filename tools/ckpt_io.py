@@ -104,11 +104,34 @@ def load_full_state(folder: str, embed_split_hidden: bool = True) -> Dict[str, t
     return {k: unshard_tensors(k, [s[k] for s in per_tp], embed_split_hidden) for k in per_tp[0]}
 
 
-def save_sharded(full: Dict[str, torch.Tensor], folder: str, tp_size: int, embed_split_hidden: bool = True):
+def _names_of(full: Dict[str, torch.Tensor]) -> dict:
+    """Layer-list / embedding / final-norm / head names of the family the keys belong to (InternLM v1 and MoE use ``blocks``)."""
+    if any(k.startswith("blocks.") for k in full):
+        return dict(layers_name="blocks", embed_name="embedding", final_norm="norm", head="head")
+    return dict(layers_name="layers", embed_name="tok_embeddings", final_norm="norm", head="output")
+
+
+def pipeline_stages(full: Dict[str, torch.Tensor], pp_size: int) -> List[Dict[str, torch.Tensor]]:
+    """Cut a full state dict (global layer indices) into ``pp_size`` stages the way the trainer does (``partition_uniform``):
+    local layer numbering per stage, embedding on the first stage, final norm + head on the last."""
+    from internevo_b200.models.sharding import pipeline_slice
+    from internevo_b200.solver.pipeline_utils import partition_uniform
+
+    names = _names_of(full)
+    n_layers = 1 + max(int(m.group(2)) for m in (_LAYER.match(k) for k in full) if m)
+    parts = partition_uniform(n_layers, pp_size, 1)
+    return [pipeline_slice(full, parts[p][0][0], parts[p][0][1], first=p == 0, last=p == pp_size - 1, **names)
+            for p in range(pp_size)]
+
+
+def save_sharded(full: Dict[str, torch.Tensor], folder: str, tp_size: int, embed_split_hidden: bool = True, pp_size: int = 1):
+    """Write ``full`` as ``model_tp{t}_pp{p}.pt`` files of a ``tp_size`` x ``pp_size`` layout."""
     os.makedirs(folder, exist_ok=True)
-    for t in range(tp_size):
-        sd = {k: v.clone() for k, v in shard_state_dict(full, t, tp_size, embed_split_hidden).items()}
-        torch.save(sd, os.path.join(folder, f"model_tp{t}_pp0.pt"))
+    stages = pipeline_stages(full, pp_size) if pp_size > 1 else [full]
+    for p, stage in enumerate(stages):
+        for t in range(tp_size):
+            sd = {k: v.clone() for k, v in shard_state_dict(stage, t, tp_size, embed_split_hidden).items()}
+            torch.save(sd, os.path.join(folder, f"model_tp{t}_pp{p}.pt"))
 
 
 def load_model_config(folder: str) -> dict:
