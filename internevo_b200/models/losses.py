@@ -3,6 +3,8 @@ pipeline; with ``parallel_output`` the logits are a vocabulary shard and the los
 (max, sum-exp, target) statistics over the tensor group."""
 from __future__ import annotations
 
+import torch
+import torch.distributed as dist
 from torch import nn
 
 from internevo_b200 import ops
@@ -29,9 +31,11 @@ class FlashGPTLMLoss(nn.Module):
             raise RuntimeError(f"The number of criterion inputs are:{len(args)}")
         shift_logits = logits.reshape(-1, logits.size(-1))
         shift_labels = labels.reshape(-1)
-        if is_using_isp() and gpc.get_world_size(ParallelMode.TENSOR) > 1:
+        isp = is_using_isp() and gpc.get_world_size(ParallelMode.TENSOR) > 1
+        if isp:
             # ISP keeps activations sequence-sharded through the head: take the matching label slice
             n, r = gpc.get_world_size(ParallelMode.TENSOR), gpc.get_local_rank(ParallelMode.TENSOR)
+            valid_in_micro_batch = (shift_labels != -100).sum().clamp_min(1)      # every rank holds the full labels
             shift_labels = shift_labels.chunk(n)[r]
             group = None
         else:
@@ -43,7 +47,17 @@ class FlashGPTLMLoss(nn.Module):
         self.last_labels = shift_labels
         valid = (shift_labels != -100).sum().clamp_min(1)
         loss = per_tok.sum() / valid
-        if is_using_isp() and gpc.get_world_size(ParallelMode.TENSOR) > 1:
-            # each sequence shard normalises by its own token count; gradients are averaged over all ranks later
-            pass
+        if isp:
+            # The reference gathers the sequence in front of the head and takes the mean over ALL valid tokens of the micro-batch
+            # (``ops/linear.py:65-82``, ``model/utils.py:258-269``).  Here the head works on this rank's token shard, so the rank
+            # contributes its share ``n * S_r / N`` (S_r: its summed token losses, N: valid tokens of the whole micro-batch): the
+            # gradient reduction over the sequence group is a mean, and the mean of the shares is the reference's ``S / N`` -
+            # shards with fewer valid labels no longer weigh their tokens higher.  The VALUE handed back is that global mean
+            # (one scalar all-reduce), the gradient is the share's.
+            loss = per_tok.sum() * (n / valid_in_micro_batch)
+            with torch.no_grad():
+                mean = loss.detach().clone()
+                dist.all_reduce(mean, group=gpc.get_group(ParallelMode.TENSOR))
+                mean /= n
+            loss = loss + (mean - loss.detach())
         return loss

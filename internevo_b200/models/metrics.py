@@ -18,9 +18,19 @@ from internevo_b200.utils.common import SchedulerHook, get_current_device
 from internevo_b200.utils.megatron_timers import megatron_timer as timer
 
 
+def _isp_shards() -> int:
+    """Under ISP every rank of the tensor (sequence) group scores its own token shard; 1 otherwise."""
+    from internevo_b200.utils.parallel import is_using_isp
+
+    return gpc.get_world_size(ParallelMode.TENSOR) if gpc.config is not None and is_using_isp() else 1
+
+
 def _dp_sum(t: torch.Tensor):
+    """Sum the counters over every rank that saw DIFFERENT tokens: the data-parallel group, and under ISP the sequence shards."""
     if gpc.is_initialized(ParallelMode.DATA) and gpc.get_world_size(ParallelMode.DATA) > 1:
         dist.all_reduce(t, group=gpc.get_group(ParallelMode.DATA))
+    if _isp_shards() > 1:
+        dist.all_reduce(t, group=gpc.get_group(ParallelMode.TENSOR))
     return t
 
 
@@ -73,7 +83,10 @@ class AccPerplex:
             self.total_log_probs += (per_token_loss * mask).sum()
             tids = type_ids if type_ids is not None else self.type_ids
             if self.total_type_count > 0 and tids is not None:
-                tids = tids.reshape(-1)[: labels.numel()].long().clamp_(0, self.total_type_count - 1)
+                tids = tids.reshape(-1)
+                if _isp_shards() > 1 and tids.numel() == labels.numel() * _isp_shards():
+                    tids = tids.chunk(_isp_shards())[gpc.get_local_rank(ParallelMode.TENSOR)]    # this rank's token shard
+                tids = tids[: labels.numel()].long().clamp_(0, self.total_type_count - 1)
                 self.ds_right.index_add_(0, tids, (correct & mask).double())
                 self.ds_tokens.index_add_(0, tids, mask.double())
                 self.ds_loss.index_add_(0, tids, (per_token_loss * mask).double())
@@ -117,9 +130,13 @@ class LossWithTypeId:
 
         with torch.no_grad():
             labels = labels.reshape(-1)
-            loss = ops.cross_entropy(logits.reshape(-1, logits.shape[-1]).detach().clone(), labels,
-                                     process_group=gpc.get_group(ParallelMode.TENSOR)
-                                     if gpc.config.model.get("parallel_output", True) else None)
+            group = gpc.get_group(ParallelMode.TENSOR) if gpc.config.model.get("parallel_output", True) else None
+            if _isp_shards() > 1:       # full-vocabulary logits of this rank's token shard
+                r, group = gpc.get_local_rank(ParallelMode.TENSOR), None
+                if labels.numel() == logits.reshape(-1, logits.shape[-1]).shape[0] * _isp_shards():
+                    labels = labels.chunk(_isp_shards())[r]
+                    type_ids = type_ids.reshape(-1).chunk(_isp_shards())[r] if type_ids is not None else None
+            loss = ops.cross_entropy(logits.reshape(-1, logits.shape[-1]).detach().clone(), labels, process_group=group)
             mask = labels != -100
             self.loss += (loss * mask).sum()
             self.token_num += mask.sum()

@@ -80,9 +80,10 @@ class Embedding1D(nn.Module):
         out = F.embedding(input_, self.weight, self.padding_idx)
         group = gpc.get_group(ParallelMode.TENSOR)
         if _is_isp():
-            # ISP: weights are replicated over the sequence group, activations sequence-sharded.  Every rank's loss is the
-            # mean over ITS shard and the objective is the mean of those, so the gathered gradient (one block per shard)
-            # carries a factor 1 / tp: without it the embedding would be updated with tp x the true gradient.
+            # ISP: weights are replicated over the sequence group, activations sequence-sharded.  Every rank's loss is ITS
+            # shard's share of the micro-batch loss (``losses.py``) and the objective is the mean of the shares, so the
+            # gathered gradient (one block per shard) carries a factor 1 / tp: without it the embedding would be updated
+            # with tp x the true gradient.
             if _ws(group) <= 1:
                 return out
             return _scale_grad(split_forward_gather_backward(out, group, dim=0), 1.0 / _ws(group))

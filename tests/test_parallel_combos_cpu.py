@@ -190,6 +190,9 @@ def _validate_golden(rank, world, kw):
     ("pp2_1f1b", 2, dict(pp=2)),
     ("pp2_interleaved", 2, dict(pp=2, num_chunks=2)),
     ("tp2_pp2_msp", 4, dict(tp=2, pp=2, mode="msp")),
+    # ISP: every sequence shard scores its own tokens - loss and accuracy are those of ALL tokens, not of the log rank's shard
+    ("isp_sp2_wp2", 2, dict(tp=2, wp=2, mode="isp")),
+    ("isp_sp2_wp2_pp2", 4, dict(tp=2, wp=2, pp=2, mode="isp")),
 ])
 def test_validation_under_pipeline_parallel_equals_the_single_process_value(name, world, kw):
     """Validation batches are un-packed ``[rows, seq]``: the activation crosses a stage boundary flattened, and a later stage must
