@@ -171,8 +171,11 @@ class PackedDataset(Dataset):
         lens = self.lengths[idx]
         return idx, lens, np.cumsum(lens)
 
-    def _gather(self, start: int, end: int):
-        """tokens / labels / type_ids / per-token (sample ordinal, offset in sample) of stream range [start, end)."""
+    def _gather(self, start: int, end: int, label_across_cut: bool = True):
+        """tokens / labels / type_ids / per-token (sample ordinal, offset in sample) of stream range [start, end).  The last token
+        of a fragment whose sample goes on in the next pack is labelled with its true successor (``PackedDatasetWithCut``,
+        reference ``packed_dataset.py:318``) or, ``label_across_cut=False``, ignored like a sample end
+        (``PackedDatasetWithoutCuSeqlen``, reference ``:190-196``)."""
         first = int(np.searchsorted(self.acm_len_samples, start, side="right"))
         last = int(np.searchsorted(self.acm_len_samples, end, side="left"))
         last = min(last, len(self.sample_indices) - 1)
@@ -188,7 +191,7 @@ class PackedDataset(Dataset):
             chunk = t[lo:hi]
             nxt = np.empty_like(chunk)
             nxt[:-1] = chunk[1:]
-            nxt[-1] = t[hi] if hi < len(t) else -100
+            nxt[-1] = t[hi] if hi < len(t) and label_across_cut else -100
             toks.append(chunk)
             labs.append(nxt)
             tids.append(np.full(len(chunk), sample.get("type_id", 0), dtype=np.int64))
@@ -312,7 +315,7 @@ class PackedDatasetWithoutCuSeqlen(PackedDataset):
 
     def build_pack(self, item: int):
         start, end = item * self.packed_length, (item + 1) * self.packed_length
-        toks, labs, tids, _, _ = self._gather(start, end)
+        toks, labs, tids, _, _ = self._gather(start, end, label_across_cut=False)
         return {"tokens": np.concatenate(toks).tolist(), "cu_seqlens": list(self.cu_seqlens),
                 "indexes": list(self.indexes), "labels": np.concatenate(labs).tolist(),
                 "type_ids": np.concatenate(tids).tolist()}
