@@ -77,10 +77,12 @@ def build_train_loader_with_data_type():
     assert data_cfg.type == "tokenized", f"unsupported data type {data_cfg.type}"
     train_ds, train_sampler, train_collate_fn = get_tokenized_train_loader_items(data_cfg)
     dataset_types = list(["en", "cn", "code"])
+    # ``data.num_worker`` loader processes pack the next batches while the GPU runs the current step: 4 unless configured, as in
+    # the reference (``data/build_dataloader.py:107-110``); a CPU-only host (plumbing / demo runs) loads in the main process
+    workers = data_cfg.get("num_worker", 4 if torch.cuda.is_available() else 0)
     train_dl = DataLoader(
-        dataset=train_ds, batch_sampler=train_sampler, num_workers=data_cfg.get("num_worker", 0),
-        pin_memory=torch.cuda.is_available(), collate_fn=train_collate_fn,
-        persistent_workers=data_cfg.get("num_worker", 0) > 0,
+        dataset=train_ds, batch_sampler=train_sampler, num_workers=workers, pin_memory=torch.cuda.is_available(),
+        collate_fn=train_collate_fn, persistent_workers=workers > 0,
     )
     return train_dl, dataset_types
 

@@ -101,7 +101,7 @@ def args_sanity_check():
     for k, v in dict(min_length=0, train_folder=None, valid_folder=None, valid_micro_num=data.micro_num, valid_every=0,
                      empty_cache_and_diag_interval=50, diag_outlier_ratio=1.1, use_packed_dataset=True,
                      fixed_random_dataset_seqlen=False, pack_sample_into_one=False, rampup_batch_size=None,
-                     total_steps=0, skip_batches="", num_worker=0).items():
+                     total_steps=0, skip_batches="").items():
         _d(data, k, v)
     data.diag_outlier_ratio = max(1, data.diag_outlier_ratio)
 

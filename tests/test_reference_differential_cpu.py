@@ -100,3 +100,33 @@ def test_learning_rate_schedule(both, key, total, init, ratio, eta):
     assert _same(ref[key][:warm], ours[key][:warm], tol=1e-12)
     excess = 2 / (1 + math.cos(math.pi / T)) - 1
     assert max(abs(a - b) for a, b in zip(ref[key][:total], ours[key][:total])) <= excess * base * 1.01
+
+
+@pytest.mark.parametrize("config", ["7B_sft", "7B_internlm2", "7B_isp_sft", "7B_MoE4_sft", "7B_llama2"])
+def test_args_sanity_check_fills_a_reference_config_like_the_reference(tmp_path, config):
+    """A config file SHIPPED BY THE REFERENCE goes through ``args_sanity_check`` on both sides: every default it fills in, every
+    derived key (``sequence_parallel``, ``packed_length``, checkpoint sub-keys, monitor section, MoE / ISP switches ...) comes
+    out identical - the configuration a reference user brings along means the same thing here."""
+    ref = _reference_root()
+    src = next((p for p in (os.path.join("/root/reference/configs", config + ".py"),
+                            os.path.join(ref or "", "..", "..", "configs", config + ".py")) if os.path.exists(p)), None)
+    if ref is None or src is None:
+        pytest.skip("the reference (and its configs folder) is not available")
+    out = {}
+    for side, root in (("reference", ref), ("ours", ROOT)):
+        dst = str(tmp_path / f"{side}.json")
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "differential_config_probe.py"), root, src, dst],
+                           capture_output=True, text=True, timeout=600, cwd=str(tmp_path),
+                           env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+        assert r.returncode == 0 and "PROBE_OK" in r.stdout, f"{side}: {r.stderr[-3000:]}"
+        out[side] = json.load(open(dst))
+
+    def flat(d, prefix=""):
+        res = {}
+        for k, v in d.items():
+            res.update(flat(v, prefix + k + ".") if isinstance(v, dict) else {prefix + k: v})
+        return res
+
+    a, b = flat(out["reference"]), flat(out["ours"])
+    diff = {k: (a.get(k, "<absent>"), b.get(k, "<absent>")) for k in sorted(set(a) | set(b)) if a.get(k, "<absent>") != b.get(k, "<absent>")}
+    assert not diff, diff
