@@ -144,5 +144,21 @@ try:
 except Exception as e:   # noqa: BLE001
     out["unpack"] = "error: " + type(e).__name__
 
+# ---- skip_batches ranges, GShard gating ------------------------------------------------------------------------------------------
+from internlm.model.moe.gshard_layer import top1gating, top2gating  # noqa: E402
+from internlm.utils.common import BatchSkipper  # noqa: E402
+
+skip = BatchSkipper("2-4,7,10-11")
+out["skipper"] = [bool(skip(i)) for i in range(14)]
+torch.manual_seed(0)
+logits = torch.randn(32, 4)
+for name, fn, kw in [("top2", top2gating, dict(capacity_factor=1.0, min_capacity=2)),
+                     ("top2_drop", top2gating, dict(capacity_factor=0.5, min_capacity=1)),
+                     ("top1", top1gating, dict(capacity_factor=1.0, min_capacity=2, use_rts=False)),
+                     ("top1_drop", top1gating, dict(capacity_factor=0.5, min_capacity=1, use_rts=False))]:
+    l_aux, combine, dispatch, counts = fn(logits, **kw)
+    out["gate_" + name] = dict(l_aux=float(l_aux), combine=tl(combine.float()), dispatch=tl(dispatch.int()), counts=tl(counts))
+out["gate_probs"] = tl(torch.softmax(logits, dim=1))
+
 json.dump(out, open(dst, "w"))
 print("PROBE_OK")

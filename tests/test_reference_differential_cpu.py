@@ -130,3 +130,33 @@ def test_args_sanity_check_fills_a_reference_config_like_the_reference(tmp_path,
     a, b = flat(out["reference"]), flat(out["ours"])
     diff = {k: (a.get(k, "<absent>"), b.get(k, "<absent>")) for k in sorted(set(a) | set(b)) if a.get(k, "<absent>") != b.get(k, "<absent>")}
     assert not diff, diff
+
+
+def test_skip_batches_and_top2_gating_equal_the_references(both):
+    """``top2gating`` (capacity, second-expert masking, renormalised weights, drops, l_aux) agrees entry by entry of the
+    ``[token, expert, slot]`` combine tensor, with and without token dropping."""
+    ref, ours = both
+    assert ref["skipper"] == ours["skipper"]
+    for key in ("gate_top2", "gate_top2_drop"):
+        assert _same(ref[key], ours[key], tol=1e-6), key
+
+
+@pytest.mark.parametrize("key", ["gate_top1", "gate_top1_drop"])
+def test_top1_gating_without_random_token_selection(both, key):
+    """Same auxiliary loss, expert counts and capacity, every kept token weighted with its gate probability at a slot of its own.
+    WHICH tokens of an over-subscribed expert are kept is not compared: without random token selection the reference takes
+    ``torch.topk`` of a 0 / 1 mask, i.e. whatever order topk gives equal elements; this framework keeps the earliest tokens."""
+    import torch
+
+    ref, ours = both
+    assert abs(ref[key]["l_aux"] - ours[key]["l_aux"]) < 1e-6 and ref[key]["counts"] == ours[key]["counts"]
+    probs = torch.tensor(ours["gate_probs"])
+    kept = []
+    for side in (ref, ours):
+        combine = torch.tensor(side[key]["combine"])
+        assert combine.shape == torch.tensor(ref[key]["combine"]).shape            # same capacity
+        tok, exp, slot = combine.nonzero(as_tuple=True)
+        assert torch.allclose(combine[tok, exp, slot], probs[tok, exp], atol=1e-6)
+        assert (exp == probs.argmax(1)[tok]).all() and len(set(zip(exp.tolist(), slot.tolist()))) == len(tok)
+        kept.append(torch.bincount(exp, minlength=4).tolist())
+    assert kept[0] == kept[1] == [min(c, torch.tensor(ref[key]["combine"]).shape[2]) for c in ref[key]["counts"]]
