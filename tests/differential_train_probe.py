@@ -1,0 +1,98 @@
+"""Eight optimizer steps of the UNMODIFIED reference on CPU: its ``initialize_model`` / ``initialize_optimizer`` (HybridZeroOptimizer
+over ``torch.optim.AdamW``) / ``initialize_trainer`` / non-pipeline scheduler / ``FlashGPTLMLoss`` (torch cross entropy) on a small
+fp32 InternLM2 with the torch attention path.  Saves the initial weights, the batches, per-step loss and gradient norm and the
+final weights (see ``test_reference_differential_cpu.py``).  The reference has no CPU mode: the accelerator's RNG / stream hooks
+are pointed at no-ops and a one-rank gloo group stands in for every parallel mode; its training code is untouched.
+
+    python differential_train_probe.py <reference root> <output .pt>
+"""
+import os, sys, contextlib
+root, dst = sys.argv[1], sys.argv[2]
+sys.path.insert(0, root)
+import torch, torch.distributed as dist
+import internlm
+import internlm.utils.common as common
+from internlm.accelerator import get_accelerator
+from internlm.core.context import ParallelMode, global_context as gpc
+from internlm.core.context.parallel_context import Config
+cpu, orig = torch.device("cpu"), common.get_current_device
+for mod in list(sys.modules.values()):
+    if mod is not None and getattr(mod, "get_current_device", None) is orig:
+        setattr(mod, "get_current_device", lambda: cpu)
+acc = get_accelerator()
+class _S:
+    def wait_stream(self, *a): pass
+    def synchronize(self): pass
+    def wait_event(self, *a): pass
+    def record_event(self, *a): return _E()
+class _E:
+    def record(self, *a): pass
+    def wait(self, *a): pass
+    def synchronize(self): pass
+    def query(self): return True
+acc.get_rng_state = lambda *a, **k: torch.get_rng_state()
+acc.set_rng_state = lambda st, *a, **k: torch.set_rng_state(st)
+acc.manual_seed = acc.manual_seed_all = lambda s: torch.manual_seed(s)
+acc.synchronize = acc.empty_cache = lambda *a, **k: None
+acc.current_device = lambda: 0
+acc.is_available = lambda: True
+type(acc).Stream = property(lambda self: (lambda *a, **k: _S()))
+type(acc).Event = property(lambda self: (lambda *a, **k: _E()))
+acc.current_stream = lambda *a, **k: _S()
+acc.default_stream = lambda *a, **k: _S()
+acc.stream = lambda s: contextlib.nullcontext()
+acc.memory_allocated = acc.max_memory_allocated = acc.memory_reserved = acc.max_memory_reserved = lambda *a, **k: 0
+acc.reset_peak_memory_stats = lambda *a, **k: None
+dist.init_process_group("gloo", rank=0, world_size=1, init_method="tcp://127.0.0.1:%d" % (20000 + os.getpid() % 20000))
+for mode in ParallelMode:
+    gpc._world_sizes[mode], gpc._local_ranks[mode], gpc._global_ranks[mode] = 1, 0, 0
+    gpc._groups[mode], gpc._ranks_in_group[mode] = dist.group.WORLD, [0]
+S, MB, MN = 16, 2, 2
+cfg = dict(
+    JOB_NAME="diff", model_type="INTERNLM2_PUBLIC", use_fp32_norm=False,
+    model=dict(checkpoint=False, num_chunks=1, num_attention_heads=4, embed_split_hidden=True, vocab_size=64, embed_grad_scale=1,
+               parallel_output=False, hidden_size=32, num_layers=2, no_bias=True, mlp_ratio=2, apply_post_layer_norm=False,
+               dtype=torch.float32, norm_type="rmsnorm", layer_norm_epsilon=1e-5, num_kv_attention_heads=2, use_flash_attn=False),
+    data=dict(seq_len=S, micro_bsz=MB, micro_num=MN, use_packed_dataset=False, gradient_accumulation=MN, total_steps=10, valid_every=0, type="tokenized"),
+    parallel=dict(zero1=dict(size=1, fsdp=False), tensor=dict(size=1, mode="mtp"), pipeline=dict(size=1, interleaved_overlap=False),
+                  weight=dict(size=1, overlap=False, memory_pool=False), sequence_parallel=False),
+    grad_scaler=dict(fp16=dict(initial_scale=2**16, min_scale=1, growth_interval=1000), growth_factor=2, backoff_factor=0.5, max_scale=2**24, hysteresis=2),
+    hybrid_zero_optimizer=dict(overlap_sync_grad=False, overlap_sync_param=False, reduce_bucket_size=512*1024*1024, clip_grad_norm=100.0),
+    loss=dict(label_smoothing=0.0),
+    adam=dict(lr=3e-3, adam_beta1=0.9, adam_beta2=0.95, adam_beta2_c=0, adam_eps=1e-8, weight_decay=0.01),
+    lr_scheduler=dict(total_steps=2000, init_steps=0, warmup_ratio=0.001, eta_min=1e-4, last_epoch=-1),
+    beta2_scheduler=dict(init_beta2=0.95, c=0, cur_iter=-1),
+    ckpt=dict(enable_save_ckpt=False), monitor=dict(alert=dict(enable_feishu_alert=False)),
+)
+gpc._config = Config(cfg)
+gpc.expert_parallel_size = 1
+gpc.zero1_parallel_size = 1; gpc.data_parallel_size = 1; gpc.tensor_parallel_size = 1; gpc.pipeline_parallel_size = 1; gpc.weight_parallel_size=1
+gpc.set_seed(1024)
+from internlm.train import initialize_model, initialize_optimizer, get_scheduler_hooks
+from internlm.model.losses import FlashGPTLMLoss
+from internlm.data.utils import unpack_data
+torch.manual_seed(0)
+model = initialize_model()
+state = {k: v.clone() for k, v in model.model.state_dict().items()}
+optimizer, beta2_scheduler, lr_scheduler = initialize_optimizer(model)
+criterion = FlashGPTLMLoss(parallel_output=False, label_smoothing=0.0)
+trainer, _, _, _ = internlm.initialize_trainer(model=model, optimizer=optimizer, criterion=criterion, lr_scheduler=lr_scheduler, beta2_scheduler=beta2_scheduler,
+                                               scheduler_hooks=get_scheduler_hooks(None, optimizer, None))
+trainer.train()
+g = torch.Generator().manual_seed(7)
+batches, losses, norms = [], [], []
+for step in range(8):
+    ids = torch.randint(1, 64, (MN, MB * S), generator=g)
+    labels = torch.cat([ids[:, 1:], torch.full((MN, 1), -100)], 1)
+    labels[:, S - 1::S] = -100
+    cu = torch.arange(0, MB * S + 1, S, dtype=torch.int32).repeat(MN, 1)
+    idx = torch.arange(S).repeat(MN, MB)
+    batch = ({"input_ids": ids.clone(), "cu_seqlens": cu.clone(), "indexes": idx.clone()}, labels.clone())
+    batches.append((ids, labels))
+    trainer.zero_grad()
+    _, _, loss = trainer.execute_schedule(batch, forward_only=False, return_loss=True, return_output_label=False)
+    ok, gn = trainer.step()
+    losses.append(float(loss)); norms.append({k: float(v) for k, v in gn.items()} if isinstance(gn, dict) else float(gn))
+torch.save({"state": state, "batches": batches, "losses": losses, "norms": norms, "final": {k: v.clone() for k, v in model.model.state_dict().items()}}, dst)
+print("PROBE_OK", flush=True)
+os._exit(0)
