@@ -4,10 +4,11 @@ fp32 InternLM2 with the torch attention path.  Saves the initial weights, the ba
 final weights (see ``test_reference_differential_cpu.py``).  The reference has no CPU mode: the accelerator's RNG / stream hooks
 are pointed at no-ops and a one-rank gloo group stands in for every parallel mode; its training code is untouched.
 
-    python differential_train_probe.py <reference root> <output .pt>
+    python differential_train_probe.py <reference root> <output .pt> [model type]
 """
 import os, sys, contextlib
 root, dst = sys.argv[1], sys.argv[2]
+family = sys.argv[3] if len(sys.argv) > 3 else "INTERNLM2_PUBLIC"
 sys.path.insert(0, root)
 import torch, torch.distributed as dist
 import internlm
@@ -49,7 +50,7 @@ for mode in ParallelMode:
     gpc._groups[mode], gpc._ranks_in_group[mode] = dist.group.WORLD, [0]
 S, MB, MN = 16, 2, 2
 cfg = dict(
-    JOB_NAME="diff", model_type="INTERNLM2_PUBLIC", use_fp32_norm=False,
+    JOB_NAME="diff", model_type=family, use_fp32_norm=False,
     model=dict(checkpoint=False, num_chunks=1, num_attention_heads=4, embed_split_hidden=True, vocab_size=64, embed_grad_scale=1,
                parallel_output=False, hidden_size=32, num_layers=2, no_bias=True, mlp_ratio=2, apply_post_layer_norm=False,
                dtype=torch.float32, norm_type="rmsnorm", layer_norm_epsilon=1e-5, num_kv_attention_heads=2, use_flash_attn=False),
@@ -59,11 +60,17 @@ cfg = dict(
     grad_scaler=dict(fp16=dict(initial_scale=2**16, min_scale=1, growth_interval=1000), growth_factor=2, backoff_factor=0.5, max_scale=2**24, hysteresis=2),
     hybrid_zero_optimizer=dict(overlap_sync_grad=False, overlap_sync_param=False, reduce_bucket_size=512*1024*1024, clip_grad_norm=100.0),
     loss=dict(label_smoothing=0.0),
-    adam=dict(lr=3e-3, adam_beta1=0.9, adam_beta2=0.95, adam_beta2_c=0, adam_eps=1e-8, weight_decay=0.01),
+    adam=dict(lr=3e-3, adam_beta1=0.9, adam_beta2=0.95, adam_beta2_c=0, adam_eps=1e-4, weight_decay=0.01),
     lr_scheduler=dict(total_steps=2000, init_steps=0, warmup_ratio=0.001, eta_min=1e-4, last_epoch=-1),
     beta2_scheduler=dict(init_beta2=0.95, c=0, cur_iter=-1),
     ckpt=dict(enable_save_ckpt=False), monitor=dict(alert=dict(enable_feishu_alert=False)),
 )
+if family in ("INTERNLM", "INTERNLM_MoE"):
+    cfg["model"].pop("no_bias"); cfg["model"].pop("num_kv_attention_heads")
+if family == "INTERNLM_MoE":
+    cfg["model"].update(num_experts=4, moe_use_residual=False, moe_type="GShard")
+    cfg["moe"] = dict(top_k=1, capacity_factor=4.0, eval_capacity_factor=4.0, min_capacity=4, noisy_gate_policy=None, drop_tokens=True, use_rts=False)
+    cfg["loss"]["moe_loss_coeff"] = 0.1
 gpc._config = Config(cfg)
 gpc.expert_parallel_size = 1
 gpc.zero1_parallel_size = 1; gpc.data_parallel_size = 1; gpc.tensor_parallel_size = 1; gpc.pipeline_parallel_size = 1; gpc.weight_parallel_size=1
@@ -81,7 +88,7 @@ trainer, _, _, _ = internlm.initialize_trainer(model=model, optimizer=optimizer,
 trainer.train()
 g = torch.Generator().manual_seed(7)
 batches, losses, norms = [], [], []
-for step in range(8):
+for step in range(int(os.environ.get("DIFF_STEPS", "8"))):
     ids = torch.randint(1, 64, (MN, MB * S), generator=g)
     labels = torch.cat([ids[:, 1:], torch.full((MN, 1), -100)], 1)
     labels[:, S - 1::S] = -100
@@ -90,7 +97,7 @@ for step in range(8):
     batch = ({"input_ids": ids.clone(), "cu_seqlens": cu.clone(), "indexes": idx.clone()}, labels.clone())
     batches.append((ids, labels))
     trainer.zero_grad()
-    _, _, loss = trainer.execute_schedule(batch, forward_only=False, return_loss=True, return_output_label=False)
+    loss = trainer.execute_schedule(batch, forward_only=False, return_loss=True, return_output_label=False)[2]
     ok, gn = trainer.step()
     losses.append(float(loss)); norms.append({k: float(v) for k, v in gn.items()} if isinstance(gn, dict) else float(gn))
 torch.save({"state": state, "batches": batches, "losses": losses, "norms": norms, "final": {k: v.clone() for k, v in model.model.state_dict().items()}}, dst)
