@@ -185,7 +185,7 @@ def _reference_group_of(key: str, tensor: torch.Tensor, model_dtype, isp: bool, 
     """Which optimizer group the reference puts a parameter in (``internlm/train/utils.py:31-79``)."""
     if isp and re.search(r"(^|\.)(tok_embeddings|embedding|output|head)\.", key):
         return "embed_head"
-    if tensor.dtype == torch.float32 and model_dtype != torch.float32:
+    if tensor.dtype == torch.float32:       # whatever the model dtype: an fp32 MODEL has all its parameters in this group
         return "fp32"
     if moe_group is not None and _EXPERT.search(key):
         return moe_group
@@ -243,7 +243,10 @@ def named_from_reference(files_of_group, model_keys: "OrderedDict[str, torch.Ten
     per_kind = {k: params_from_file_layout(model, flat[k]) for k in KINDS}
     named = {"grad_scaler": first["grad_scaler"], "groups": OrderedDict()}
     for g in optim.groups:
-        src = meta.get(g.name)
+        # step count and hyper-parameters are those of the reference group of the same name; where the two sides file a parameter
+        # under different groups (an fp32 model: "fp32" there, "default" here) any group's will do - the reference steps and
+        # schedules all its groups together
+        src = meta.get(g.name) or (next(iter(meta.values())) if meta else None)
         assert src is not None or not g.params, f"parameter group '{g.name}' has no counterpart in the reference checkpoint"
         params = OrderedDict((optim.param_name(p), {k: per_kind[k][optim.param_name(p)] for k in KINDS}) for p in g.ordered)
         named["groups"][g.name] = {"step": src["step"] if src else 0, "hyper": src["hyper"] if src else {}, "params": params}
@@ -279,7 +282,7 @@ def reference_file_from_named(named: dict, model, model_dtype, layout: Dict[str,
         world, rank = layout.get(gname, layout["default"])
         shapes = [tuple(per_kind["master"][k].shape) for k in keys]
         idx, ids = reference_partition(shapes, world)
-        src = named["groups"].get(gname, {"step": 0, "hyper": {}})
+        src = named["groups"].get(gname) or next(iter(named["groups"].values()), {"step": 0, "hyper": {}})
         out["zero_devide_optim_plan"].append([list(x) for x in ids])
         pg = {"name": gname, "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
               "differentiable": False, "fused": True, "params": [packed] if keys else []}

@@ -4,11 +4,12 @@ fp32 InternLM2 with the torch attention path.  Saves the initial weights, the ba
 final weights (see ``test_reference_differential_cpu.py``).  The reference has no CPU mode: the accelerator's RNG / stream hooks
 are pointed at no-ops and a one-rank gloo group stands in for every parallel mode; its training code is untouched.
 
-    python differential_train_probe.py <reference root> <output .pt> [model type]
+    python differential_train_probe.py <reference root> <output .pt> [model type [checkpoint folder]]
 """
 import os, sys, contextlib
 root, dst = sys.argv[1], sys.argv[2]
 family = sys.argv[3] if len(sys.argv) > 3 else "INTERNLM2_PUBLIC"
+ckpt_folder = sys.argv[4] if len(sys.argv) > 4 else None        # given: the reference's CheckpointManager saves after step 4
 sys.path.insert(0, root)
 import torch, torch.distributed as dist
 import internlm
@@ -63,7 +64,10 @@ cfg = dict(
     adam=dict(lr=3e-3, adam_beta1=0.9, adam_beta2=0.95, adam_beta2_c=0, adam_eps=1e-4, weight_decay=0.01),
     lr_scheduler=dict(total_steps=2000, init_steps=0, warmup_ratio=0.001, eta_min=1e-4, last_epoch=-1),
     beta2_scheduler=dict(init_beta2=0.95, c=0, cur_iter=-1),
-    ckpt=dict(enable_save_ckpt=False), monitor=dict(alert=dict(enable_feishu_alert=False)),
+    ckpt=dict(enable_save_ckpt=ckpt_folder is not None, save_ckpt_folder=f"local:{ckpt_folder}", checkpoint_every=4, oss_snapshot_freq=0,
+              async_upload=False, async_upload_tmp_folder=None, auto_resume=False, stop_file_path=None, load_ckpt_info=None,
+              snapshot_ckpt_folder=f"local:{ckpt_folder}/snapshot", is_async_upload=False),
+    monitor=dict(alert=dict(enable_feishu_alert=False)), resume_tb_folder=None, tensorboard_folder=None,
 )
 if family in ("INTERNLM", "INTERNLM_MoE"):
     cfg["model"].pop("no_bias"); cfg["model"].pop("num_kv_attention_heads")
@@ -86,6 +90,13 @@ criterion = FlashGPTLMLoss(parallel_output=False, label_smoothing=0.0)
 trainer, _, _, _ = internlm.initialize_trainer(model=model, optimizer=optimizer, criterion=criterion, lr_scheduler=lr_scheduler, beta2_scheduler=beta2_scheduler,
                                                scheduler_hooks=get_scheduler_hooks(None, optimizer, None))
 trainer.train()
+manager = train_state = None
+if ckpt_folder is not None:
+    from internlm.checkpoint import CheckpointManager
+    from internlm.core.trainer import TrainState
+    manager = CheckpointManager(ckpt_config=gpc.config.ckpt, model=model, optimizer=optimizer, lr_scheduler=lr_scheduler,
+                                model_config=gpc.config.model)
+    train_state = TrainState(gpc.config, None)
 g = torch.Generator().manual_seed(7)
 batches, losses, norms = [], [], []
 for step in range(int(os.environ.get("DIFF_STEPS", "8"))):
@@ -99,6 +110,10 @@ for step in range(int(os.environ.get("DIFF_STEPS", "8"))):
     trainer.zero_grad()
     loss = trainer.execute_schedule(batch, forward_only=False, return_loss=True, return_output_label=False)[2]
     ok, gn = trainer.step()
+    if manager is not None:
+        train_state.batch_count = step
+        train_state.step_count += 1
+        manager.try_save_checkpoint(train_state)
     losses.append(float(loss)); norms.append({k: float(v) for k, v in gn.items()} if isinstance(gn, dict) else float(gn))
 torch.save({"state": state, "batches": batches, "losses": losses, "norms": norms, "final": {k: v.clone() for k, v in model.model.state_dict().items()}}, dst)
 print("PROBE_OK", flush=True)

@@ -79,11 +79,13 @@ def _check_reference_files(folder, world):
         st = torch.load(os.path.join(folder, "2", f"optimizer_tp0_pp0_zo{z}.pt"), weights_only=False)
         assert {"grad_scaler", "base_optim_states", "flat_fp32_weights", "zero_devide_optim_plan"} <= set(st)
         groups = st["base_optim_states"]["param_groups"]
-        assert [g["name"] for g in groups] == ["default", "fp32"] and groups[0]["params"] == [0] and groups[1]["params"] == []
-        assert {"lr", "betas", "eps", "weight_decay"} <= set(groups[0])
-        plan = st["zero_devide_optim_plan"][0]
+        # an fp32 model: the reference files every fp32 parameter under its "fp32" group (id 1), "default" stays empty
+        assert [g["name"] for g in groups] == ["default", "fp32"] and groups[0]["params"] == [] and groups[1]["params"] == [0]
+        assert {"lr", "betas", "eps", "weight_decay"} <= set(groups[1])
+        assert st["zero_devide_optim_plan"][0] == [[] for _ in range(world)]
+        plan = st["zero_devide_optim_plan"][1]
         assert len(plan) == world
-        flat, state = st["flat_fp32_weights"][0], st["base_optim_states"]["state"][0]
+        flat, state = st["flat_fp32_weights"][1], st["base_optim_states"]["state"][0]
         want = sum(int(torch.Size([int(d) for d in pid.split("_")[1:]]).numel()) for pid in plan[z])
         assert flat.dtype == torch.float32 and flat.numel() == want == state["exp_avg"].numel() == state["exp_avg_sq"].numel()
         assert float(state["step"]) == 2.0
@@ -93,7 +95,7 @@ def _check_reference_files(folder, world):
     sizes = sorted(numel.values(), reverse=True)
     for z in range(world):
         for pid in torch.load(os.path.join(folder, "2", f"optimizer_tp0_pp0_zo{z}.pt"), weights_only=False)[
-                "zero_devide_optim_plan"][0][z]:
+                "zero_devide_optim_plan"][1][z]:
             pos, dims = int(pid.split("_")[0]), [int(d) for d in pid.split("_")[1:]]
             assert int(torch.Size(dims).numel()) == sizes[pos]
 
@@ -155,7 +157,8 @@ REFERENCE_FORMAT = dict(ckpt_extra=dict(optimizer_ckpt_format="reference"))
     ("llama2", 2, dict(model_type="LLAMA2"), False),                     # wq / wk / wv in the files, one wqkv in memory
     ("internlm_v1", 2, dict(model_type="INTERNLM"), False),              # biases, Wqkv / out_proj / w1 w2 w3 naming
     ("bf16_fp32_norm", 2, dict(dtype="torch.bfloat16", top_level=dict(use_fp32_norm=True)), False),   # the "fp32" group
-    ("moe_ep2", 2, dict(model_type="INTERNLM_MoE", num_experts=4, moe_type="MegaBlock-D"), True),     # expert group
+    # expert group (bf16: in an fp32 model the reference files the experts under "fp32" as well, before it looks for experts)
+    ("moe_ep2", 2, dict(model_type="INTERNLM_MoE", num_experts=4, moe_type="MegaBlock-D", dtype="torch.bfloat16"), True),
 ])
 def test_reference_format_round_trip_for_families_and_layouts(tmp_path, name, world, kw, moe):
     """Save in the reference's optimizer layout, resume from it: the trajectory equals the uninterrupted run for every model
@@ -187,18 +190,18 @@ gpc._config = Config(dict(only_load_lr=False))
 gpc.is_rank_for_log = lambda: False
 model = torch.load(f"{folder}/model_tp0_pp0.pt", weights_only=False)
 params = [torch.nn.Parameter(model[k].float()) for k in keys]          # the reference's model.parameters(), in ITS order
-part = types.SimpleNamespace(_zero_world_size=[world], params_per_rank_id_dict=[], _overlap_sync_param=False)
-per_rank, _ = HybridZeroOptimizer._partition_param_list(part, 0, {"params": params})
+part = types.SimpleNamespace(_zero_world_size=[world, world], params_per_rank_id_dict=[[]], _overlap_sync_param=False)
+per_rank, _ = HybridZeroOptimizer._partition_param_list(part, 1, {"params": params})      # fp32 model: everything is in group 1
 class Scaler:
     def load_state_dict(self, st): self.st = st
 for z in range(world):
     weights = torch.cat([p.detach().reshape(-1) for p in per_rank[z]])
     flat = torch.zeros_like(weights).requires_grad_()                   # the rank's fp32 master buffer, to be filled by the load
     low = torch.zeros_like(weights)
-    optim = torch.optim.AdamW([dict(params=[flat], name="default"), dict(params=[], name="fp32")], lr=1.0)
+    optim = torch.optim.AdamW([dict(params=[], name="default"), dict(params=[flat], name="fp32")], lr=1.0)
     me = types.SimpleNamespace(
-        grad_scaler=Scaler(), optim=optim, _fp32_flat_param_groups_of_current_rank={0: flat}, _zero_local_rank=[z, z],
-        param_group_no_params_ranks=[set(), set(range(world))], _fp16_param_groups=[per_rank[z], []],
+        grad_scaler=Scaler(), optim=optim, _fp32_flat_param_groups_of_current_rank={1: flat}, _zero_local_rank=[z, z],
+        param_group_no_params_ranks=[set(range(world)), set()], _fp16_param_groups=[[], per_rank[z]],
         _param_store=types.SimpleNamespace(get_flat_fp16_param_by_rank_group=lambda rank, group_id: low),
         params_per_rank_id_dict=None)
     HybridZeroOptimizer.load_state_dict(me, torch.load(f"{folder}/optimizer_tp0_pp0_zo{z}.pt", weights_only=False))
@@ -206,7 +209,7 @@ for z in range(world):
     assert torch.equal(flat.detach(), weights) and torch.equal(low, weights), z
     st = optim.state_dict()["state"][0]
     assert st["exp_avg"].shape == weights.shape and float(st["exp_avg"].abs().sum()) > 0 and float(st["step"]) == 2.0
-    assert optim.param_groups[0]["lr"] != 1.0 and me.params_per_rank_id_dict is not None and "_scale" in me.grad_scaler.st
+    assert optim.param_groups[1]["lr"] != 1.0 and me.params_per_rank_id_dict is not None and "_scale" in me.grad_scaler.st
 print("REFERENCE_LOADED_OK")
 '''
 

@@ -298,3 +298,77 @@ def test_eight_training_steps_follow_the_reference(tmp_path, family):
     # the learning rate; ``adam_eps = 1e-4`` keeps entries whose gradient is pure rounding noise, like the key bias of the
     # InternLM-v1 attention whose true gradient is zero, from random-walking by +-lr per step on either side.)
     assert moved > 5e-3 and drift < 0.03 * moved, (drift, moved)
+
+
+def _resume_reference_checkpoint(rank, world, ref_file, folder):
+    import torch
+
+    import internevo_b200 as fw
+    from common import tiny_config
+    from internevo_b200.checkpoint import CheckpointManager
+    from internevo_b200.core.context import global_context as gpc
+    from internevo_b200.core.trainer import TrainState
+    from internevo_b200.initialize import initialize_distributed_env
+    from internevo_b200.models.losses import FlashGPTLMLoss
+    from internevo_b200.train import get_scheduler_hooks, initialize_model, initialize_optimizer
+
+    ref = torch.load(ref_file, weights_only=False)
+    S, MB, MN = 16, 2, 2
+    cfg = tiny_config(num_layers=2, hidden=32, heads=4, kv_heads=2, vocab=64, seq_len=S, micro_bsz=MB, micro_num=MN)
+    cfg["model"].update(parallel_output=False, use_flash_attn=False)
+    cfg["data"].update(use_packed_dataset=False, total_steps=10)
+    cfg["adam"].update(lr=3e-3, adam_eps=1e-4, weight_decay=0.01)
+    cfg["lr_scheduler"].update(total_steps=2000, warmup_ratio=0.001, eta_min=1e-4)
+    cfg["grad_scaler"]["fp16"]["initial_scale"] = 2**16
+    cfg["hybrid_zero_optimizer"]["clip_grad_norm"] = 100.0
+    cfg["ckpt"] = dict(enable_save_ckpt=False, auto_resume=False,
+                       load_ckpt_info=dict(path=f"local:{folder}/4", content=("model", "optimizer", "scheduler"),
+                                           ckpt_type="internevo"))
+    initialize_distributed_env(config=cfg, launcher="torch", seed=77)       # another seed: every weight must come from the files
+    model = initialize_model()
+    opt, b2, lrs = initialize_optimizer(model)
+    crit = FlashGPTLMLoss(parallel_output=False, label_smoothing=0)
+    trainer, _, _, _ = fw.initialize_trainer(model=model, optimizer=opt, criterion=crit, lr_scheduler=lrs, beta2_scheduler=b2,
+                                             scheduler_hooks=get_scheduler_hooks(None, opt, None))
+    trainer.train()
+    ts = TrainState(gpc.config, None)
+    CheckpointManager(ckpt_config=gpc.config.ckpt, model=model, optimizer=opt, lr_scheduler=lrs,
+                      model_config=gpc.config.model).try_resume_training(ts)
+    assert ts.step_count == 4, ts.step_count
+    losses = []
+    for ids, labels in ref["batches"][4:]:
+        cu = torch.arange(0, MB * S + 1, S, dtype=torch.int32).repeat(MN, 1)
+        idx = torch.arange(S).repeat(MN, MB)
+        trainer.zero_grad()
+        out = trainer.execute_schedule(({"input_ids": ids.clone(), "cu_seqlens": cu, "indexes": idx}, labels.clone()),
+                                       forward_only=False, return_loss=True, return_output_label=False)
+        ok, _ = trainer.step()
+        assert ok
+        losses.append(float(out[2]))
+    final = model.model.state_dict()
+    drift = max(float((final[k] - ref["final"][k]).abs().max()) for k in ref["final"])
+    moved = max(float((ref["final"][k] - ref["state"][k]).abs().max()) for k in ref["final"])
+    return losses, ref["losses"][4:], drift, moved
+
+
+def test_a_checkpoint_written_by_the_reference_resumes_here(tmp_path):
+    """The reference trains 4 steps on CPU and ITS ``CheckpointManager`` writes a checkpoint (``model_tp0_pp0.pt``,
+    ``optimizer_tp0_pp0_zo0.pt`` in its parameter-wise flat layout, ``schedulder.pt``, ``context.pt``), then trains 4 more steps.
+    This framework - initialised with another seed - loads model, optimizer and scheduler state from those files and its next 4
+    steps reproduce the reference's: weights, fp32 master copy, Adam moments and step count, loss scale and the position in the
+    learning-rate schedule all arrive through the files (``checkpoint/optimizer_interchange.py``)."""
+    from common import run_distributed
+
+    ref = _reference_root()
+    if ref is None:
+        pytest.skip("the reference is not installed (baseline/_ref)")
+    dst, folder = str(tmp_path / "train.pt"), str(tmp_path / "ref_ckpt")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "differential_train_probe.py"), ref, dst, "INTERNLM2_PUBLIC", folder],
+                       capture_output=True, text=True, timeout=900, cwd=str(tmp_path), env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert r.returncode == 0 and "PROBE_OK" in r.stdout, r.stderr[-3000:]
+    assert {"model_tp0_pp0.pt", "optimizer_tp0_pp0_zo0.pt", "schedulder.pt", "context.pt", "4.step"} <= set(os.listdir(f"{folder}/4"))
+    losses, ref_losses, drift, moved = run_distributed(_resume_reference_checkpoint, 1, dst, folder)[0]
+    assert len(losses) == 4
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) < 2e-6 * max(1.0, abs(b)), (losses, ref_losses)
+    assert moved > 5e-3 and drift < 0.03 * moved, (drift, moved)
