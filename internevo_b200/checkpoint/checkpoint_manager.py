@@ -404,7 +404,16 @@ class CheckpointManager:
                      saved_obj=train_state.data_state_dict)
         if gpc.is_rank_for_log():
             if scheduler:
-                llm_save(os.path.join(folder, "schedulder.pt"), saved_obj=scheduler.state_dict())
+                states = scheduler.state_dict()
+                if gpc.config.get("ckpt", {}).get("optimizer_ckpt_format", "internevo_b200") == "reference":
+                    from internevo_b200.utils.parallel import is_using_isp
+
+                    from .optimizer_interchange import reference_scheduler_state
+
+                    # the reference keeps its empty groups: default, [embed_head], fp32, [experts]
+                    n_groups = 2 + int(is_using_isp()) + len(gpc.expert_parallel_group_names)
+                    states = reference_scheduler_state(scheduler, n_groups)
+                llm_save(os.path.join(folder, "schedulder.pt"), saved_obj=states)
             if hasattr(train_state, "batch_sampler") and train_state.batch_sampler is not None:
                 llm_save(os.path.join(folder, "sampler.pt"), saved_obj=train_state.batch_sampler.state_dict())
             llm_save(os.path.join(folder, "context.pt"), saved_obj=train_state.state_dict())

@@ -284,9 +284,17 @@ def reference_file_from_named(named: dict, model, model_dtype, layout: Dict[str,
         idx, ids = reference_partition(shapes, world)
         src = named["groups"].get(gname) or next(iter(named["groups"].values()), {"step": 0, "hyper": {}})
         out["zero_devide_optim_plan"].append([list(x) for x in ids])
+        # torch's ``load_state_dict`` REPLACES the live group dicts by the saved ones, so every key the reference reads after its
+        # constructor has to be here: ``name``, ``dtype`` (of the group's model parameters; ``None`` for an empty group,
+        # ``hybrid_zero_optim.py:155,604``), ``moe``.  ``optimizer_mode`` (an enum of the reference's own module) is only read
+        # while the optimizer is built and is left out.
         pg = {"name": gname, "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
-              "differentiable": False, "fused": True, "params": [packed] if keys else []}
-        pg.update({k: v for k, v in src.get("hyper", {}).items() if k in ("lr", "betas", "eps", "weight_decay")})
+              "differentiable": False, "fused": True, "decoupled_weight_decay": True,
+              "dtype": live[keys[0]].dtype if keys else None, "params": [packed] if keys else []}
+        if moe_group is not None and gname == moe_group:
+            pg["moe"] = True
+        pg.update({k: v for k, v in src.get("hyper", {}).items() if k in ("lr", "betas", "eps", "weight_decay", "initial_lr")})
+        pg.setdefault("initial_lr", pg.get("lr"))
         out["base_optim_states"]["param_groups"].append(pg)
         if idx[rank]:
             cat = {k: torch.cat([per_kind[k][keys[i]].reshape(-1) for i in idx[rank]]) for k in KINDS}
@@ -313,4 +321,27 @@ def _reference_order(keys: List[str]) -> List[str]:
         block = keys[i:j]
         out.extend(sorted(block, key=lambda k: (rank[re.match(r"^.*\.(w[123])\.(weight|bias)$", k).group(1)], block.index(k))))
         i = j
+    return out
+
+
+def reference_scheduler_state(scheduler, n_groups: int) -> dict:
+    """``schedulder.pt`` the way the reference's ``FineTuneCosineAnnealingWarmupLR.state_dict()`` writes it
+    (``solver/schedulers/lr_scheduler.py:28-36``): the warm-up wrapper's fields plus the wrapped torch ``CosineAnnealingLR``'s, with
+    one ``base_lr`` per REFERENCE parameter group (it keeps its empty groups).  The wrapper's ``last_epoch`` stops at the end of
+    the warm-up, from there on the cosine scheduler counts."""
+    st = scheduler.state_dict()
+    warm, epoch = scheduler.warmup_epochs, scheduler.last_epoch
+    finished = epoch >= warm
+    base, last = [scheduler.base_lrs[0]] * n_groups, [scheduler.get_last_lr()[0]] * n_groups
+    torch_fields = {"_is_initial": False, "_get_lr_called_within_step": False}
+    after_epoch = epoch - warm if finished else 0
+    out = dict(st)
+    out.update(torch_fields)
+    out.update({
+        "_init_steps": scheduler._init_steps, "_warmup_steps": scheduler._warmup_steps, "warmup_epochs": warm,
+        "finished": finished, "base_lrs": base, "last_epoch": min(epoch, warm), "_step_count": min(epoch, warm) + 1,
+        "_last_lr": last, "after_scheduler_type": "CosineAnnealingLR",
+        "after_scheduler_dict": dict(torch_fields, T_max=scheduler.total_steps - warm, eta_min=scheduler.eta_min, base_lrs=list(base),
+                                     last_epoch=after_epoch, _step_count=after_epoch + 1, _last_lr=list(last)),
+    })
     return out

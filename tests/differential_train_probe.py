@@ -4,12 +4,13 @@ fp32 InternLM2 with the torch attention path.  Saves the initial weights, the ba
 final weights (see ``test_reference_differential_cpu.py``).  The reference has no CPU mode: the accelerator's RNG / stream hooks
 are pointed at no-ops and a one-rank gloo group stands in for every parallel mode; its training code is untouched.
 
-    python differential_train_probe.py <reference root> <output .pt> [model type [checkpoint folder]]
+    python differential_train_probe.py <reference root> <output .pt> [model type [checkpoint folder ["resume"]]]
 """
 import os, sys, contextlib
 root, dst = sys.argv[1], sys.argv[2]
 family = sys.argv[3] if len(sys.argv) > 3 else "INTERNLM2_PUBLIC"
 ckpt_folder = sys.argv[4] if len(sys.argv) > 4 else None        # given: the reference's CheckpointManager saves after step 4
+resume = len(sys.argv) > 5 and sys.argv[5] == "resume"          # ... or loads <folder>/4 (written by this framework) first
 sys.path.insert(0, root)
 import torch, torch.distributed as dist
 import internlm
@@ -65,7 +66,9 @@ cfg = dict(
     lr_scheduler=dict(total_steps=2000, init_steps=0, warmup_ratio=0.001, eta_min=1e-4, last_epoch=-1),
     beta2_scheduler=dict(init_beta2=0.95, c=0, cur_iter=-1),
     ckpt=dict(enable_save_ckpt=ckpt_folder is not None, save_ckpt_folder=f"local:{ckpt_folder}", checkpoint_every=4, oss_snapshot_freq=0,
-              async_upload=False, async_upload_tmp_folder=None, auto_resume=False, stop_file_path=None, load_ckpt_info=None,
+              async_upload=False, async_upload_tmp_folder=None, auto_resume=False, stop_file_path=None,
+              load_ckpt_info=dict(path=f"local:{ckpt_folder}/4", content=("model", "optimizer", "scheduler"),
+                                  ckpt_type="internevo") if resume else None,
               snapshot_ckpt_folder=f"local:{ckpt_folder}/snapshot", is_async_upload=False),
     monitor=dict(alert=dict(enable_feishu_alert=False)), resume_tb_folder=None, tensorboard_folder=None,
 )
@@ -97,6 +100,9 @@ if ckpt_folder is not None:
     manager = CheckpointManager(ckpt_config=gpc.config.ckpt, model=model, optimizer=optimizer, lr_scheduler=lr_scheduler,
                                 model_config=gpc.config.model)
     train_state = TrainState(gpc.config, None)
+    if resume:
+        manager.try_resume_training(train_state)
+        assert train_state.step_count == 4, train_state.step_count
 g = torch.Generator().manual_seed(7)
 batches, losses, norms = [], [], []
 for step in range(int(os.environ.get("DIFF_STEPS", "8"))):
@@ -107,10 +113,12 @@ for step in range(int(os.environ.get("DIFF_STEPS", "8"))):
     idx = torch.arange(S).repeat(MN, MB)
     batch = ({"input_ids": ids.clone(), "cu_seqlens": cu.clone(), "indexes": idx.clone()}, labels.clone())
     batches.append((ids, labels))
+    if resume and step < 4:
+        continue
     trainer.zero_grad()
     loss = trainer.execute_schedule(batch, forward_only=False, return_loss=True, return_output_label=False)[2]
     ok, gn = trainer.step()
-    if manager is not None:
+    if manager is not None and not resume:
         train_state.batch_count = step
         train_state.step_count += 1
         manager.try_save_checkpoint(train_state)

@@ -372,3 +372,81 @@ def test_a_checkpoint_written_by_the_reference_resumes_here(tmp_path):
     for a, b in zip(losses, ref_losses):
         assert abs(a - b) < 2e-6 * max(1.0, abs(b)), (losses, ref_losses)
     assert moved > 5e-3 and drift < 0.03 * moved, (drift, moved)
+
+
+def _train_and_save_for_the_reference(rank, world, folder):
+    import torch
+
+    import internevo_b200 as fw
+    from common import tiny_config
+    from internevo_b200.checkpoint import CheckpointManager
+    from internevo_b200.core.context import global_context as gpc
+    from internevo_b200.core.trainer import TrainState
+    from internevo_b200.initialize import initialize_distributed_env
+    from internevo_b200.models.losses import FlashGPTLMLoss
+    from internevo_b200.train import get_scheduler_hooks, initialize_model, initialize_optimizer
+
+    S, MB, MN = 16, 2, 2
+    cfg = tiny_config(num_layers=2, hidden=32, heads=4, kv_heads=2, vocab=64, seq_len=S, micro_bsz=MB, micro_num=MN)
+    cfg["model"].update(parallel_output=False, use_flash_attn=False)
+    cfg["data"].update(use_packed_dataset=False, total_steps=10)
+    cfg["adam"].update(lr=3e-3, adam_eps=1e-4, weight_decay=0.01)
+    cfg["lr_scheduler"].update(total_steps=2000, warmup_ratio=0.001, eta_min=1e-4)
+    cfg["grad_scaler"]["fp16"]["initial_scale"] = 2**16
+    cfg["hybrid_zero_optimizer"]["clip_grad_norm"] = 100.0
+    cfg["ckpt"] = dict(enable_save_ckpt=True, save_ckpt_folder=f"local:{folder}", checkpoint_every=4, oss_snapshot_freq=0,
+                       auto_resume=False, async_upload=False, optimizer_ckpt_format="reference")
+    initialize_distributed_env(config=cfg, launcher="torch", seed=5)
+    model = initialize_model()
+    opt, b2, lrs = initialize_optimizer(model)
+    crit = FlashGPTLMLoss(parallel_output=False, label_smoothing=0)
+    trainer, _, _, _ = fw.initialize_trainer(model=model, optimizer=opt, criterion=crit, lr_scheduler=lrs, beta2_scheduler=b2,
+                                             scheduler_hooks=get_scheduler_hooks(None, opt, None))
+    trainer.train()
+    ts = TrainState(gpc.config, None)
+    mm = CheckpointManager(ckpt_config=gpc.config.ckpt, model=model, optimizer=opt, lr_scheduler=lrs, model_config=gpc.config.model)
+    g = torch.Generator().manual_seed(7)        # the batch stream of differential_train_probe.py
+    losses = []
+    for step in range(8):
+        ids = torch.randint(1, 64, (MN, MB * S), generator=g)
+        labels = torch.cat([ids[:, 1:], torch.full((MN, 1), -100)], 1)
+        labels[:, S - 1::S] = -100
+        cu = torch.arange(0, MB * S + 1, S, dtype=torch.int32).repeat(MN, 1)
+        idx = torch.arange(S).repeat(MN, MB)
+        trainer.zero_grad()
+        out = trainer.execute_schedule(({"input_ids": ids, "cu_seqlens": cu, "indexes": idx}, labels), forward_only=False,
+                                       return_loss=True, return_output_label=False)
+        ok, _ = trainer.step()
+        assert ok
+        losses.append(float(out[2]))
+        if step < 4:
+            ts.batch_count, ts.step_count = step, ts.step_count + 1
+            mm.try_save_checkpoint(ts)
+    mm.wait_async_upload_finish()
+    return losses, {k: v.clone() for k, v in model.model.state_dict().items()}
+
+
+def test_the_reference_resumes_a_checkpoint_written_here(tmp_path):
+    """The other direction with the reference's real code: this framework trains 4 steps and saves with
+    ``optimizer_ckpt_format="reference"``; the reference's ``CheckpointManager.try_resume_training`` loads model, optimizer
+    (``HybridZeroOptimizer.load_state_dict`` + ``torch.optim.AdamW.load_state_dict``) and scheduler from that folder on CPU and its
+    next 4 steps reproduce the 4 steps this framework went on to take."""
+    import torch
+
+    from common import run_distributed
+
+    ref = _reference_root()
+    if ref is None:
+        pytest.skip("the reference is not installed (baseline/_ref)")
+    folder, dst = str(tmp_path / "our_ckpt"), str(tmp_path / "resumed.pt")
+    losses, final = run_distributed(_train_and_save_for_the_reference, 1, folder)[0]
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "differential_train_probe.py"), ref, dst, "INTERNLM2_PUBLIC", folder,
+                        "resume"], capture_output=True, text=True, timeout=900, cwd=str(tmp_path),
+                       env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert r.returncode == 0 and "PROBE_OK" in r.stdout, r.stderr[-3000:]
+    theirs = torch.load(dst, weights_only=False)
+    assert len(theirs["losses"]) == 4
+    for a, b in zip(theirs["losses"], losses[4:]):
+        assert abs(a - b) < 2e-6 * max(1.0, abs(b)), (theirs["losses"], losses[4:])
+    drift = max(float((final[k] - theirs["final"][k]).abs().max()) for k in final)
+    assert drift < 2e-4, drift
