@@ -50,6 +50,10 @@ class FineTuneCosineAnnealingWarmupLR:
         for k in ("last_epoch", "base_lrs", "_last_lr"):
             if k in state:
                 setattr(self, k, state[k])
+        if state.get("finished") and "after_scheduler_dict" in state:
+            # the reference's layout (its file, or one written here for it): the warm-up wrapper stops counting at the end of the
+            # warm-up and the wrapped cosine scheduler counts from there (``lr_scheduler.py:62-72``)
+            self.last_epoch = int(state["last_epoch"]) + int(state["after_scheduler_dict"]["last_epoch"])
         for g, lr in zip(self.optimizer.param_groups, self._last_lr):
             g["lr"] = lr
 

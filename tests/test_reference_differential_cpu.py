@@ -335,6 +335,10 @@ def _resume_reference_checkpoint(rank, world, ref_file, folder):
     CheckpointManager(ckpt_config=gpc.config.ckpt, model=model, optimizer=opt, lr_scheduler=lrs,
                       model_config=gpc.config.model).try_resume_training(ts)
     assert ts.step_count == 4, ts.step_count
+    # the position in the schedule: the reference's warm-up wrapper stopped counting at 2, its cosine scheduler counted 2 more
+    their_sched = torch.load(f"{folder}/4/schedulder.pt", weights_only=False)
+    assert (their_sched["last_epoch"], their_sched["after_scheduler_dict"]["last_epoch"]) == (2, 2) and lrs.last_epoch == 4
+    assert abs(opt.param_groups[0]["lr"] - their_sched["_last_lr"][0]) < 1e-9 * their_sched["_last_lr"][0]
     losses = []
     for ids, labels in ref["batches"][4:]:
         cu = torch.arange(0, MB * S + 1, S, dtype=torch.int32).repeat(MN, 1)
