@@ -338,7 +338,8 @@ def _resume_reference_checkpoint(rank, world, ref_file, folder):
     # the position in the schedule: the reference's warm-up wrapper stopped counting at 2, its cosine scheduler counted 2 more
     their_sched = torch.load(f"{folder}/4/schedulder.pt", weights_only=False)
     assert (their_sched["last_epoch"], their_sched["after_scheduler_dict"]["last_epoch"]) == (2, 2) and lrs.last_epoch == 4
-    assert abs(opt.param_groups[0]["lr"] - their_sched["_last_lr"][0]) < 1e-9 * their_sched["_last_lr"][0]
+    # (equal up to the factor 2 / (1 + cos(pi / T)) = 1 + 6e-7 of the reference's recursive cosine, see test_learning_rate_schedule)
+    assert abs(opt.param_groups[0]["lr"] - their_sched["_last_lr"][0]) < 2e-6 * their_sched["_last_lr"][0]
     losses = []
     for ids, labels in ref["batches"][4:]:
         cu = torch.arange(0, MB * S + 1, S, dtype=torch.int32).repeat(MN, 1)
