@@ -14,6 +14,7 @@ from internevo_b200.utils.parallel import is_using_isp
 from .batch_sampler import StaticBatchSampler, get_dpsampler_dataloader
 from .collaters import jsonl_ds_collate_fn, packed_collate_fn
 from .datasets import (
+    get_dataset_type_ids_map,
     JsonlDataset,
     PackedDatasetWithCut,
     PackedDatasetWithoutCuSeqlen,
@@ -53,7 +54,7 @@ def get_tokenized_train_loader_items(data_cfg):
     train_sampler = StaticBatchSampler(
         train_ds.datasets if isinstance(train_ds, ConcatDataset) else [train_ds],
         batch_size=data_cfg.micro_num, rampup_batch_size=data_cfg.rampup_batch_size, micro_bsz=data_cfg.micro_bsz,
-        seed=1024, drop_last=True, data_rank=rank, data_world_size=size,
+        seed=data_cfg.get("seed", 1024), drop_last=True, data_rank=rank, data_world_size=size,
     )
     train_collate_fn = partial(packed_collate_fn, packed_length=data_cfg.packed_length)
     return train_ds, train_sampler, train_collate_fn
@@ -65,7 +66,9 @@ def get_tokenized_valid_loader_items(data_cfg):
         valid_ds = RandomDataset(num_samples=gpc.get_world_size(ParallelMode.DATA) * 500, max_len=data_cfg.seq_len,
                                  fixed_seqlen=data_cfg.get("fixed_random_dataset_seqlen", False))
     else:
-        valid_ds = get_dataset_dict(folder=data_cfg.valid_folder, split="")
+        # samples shorter than ``data.valid_min_length`` tokens are left out; 50 unless configured, as in the reference
+        # (its ``JsonlDataset`` default, ``tokenized/dataset.py:9-56``)
+        valid_ds = get_dataset_dict(folder=data_cfg.valid_folder, split="", min_length=data_cfg.get("valid_min_length", 50))
     if not isinstance(valid_ds, dict):
         valid_ds = {"val": valid_ds}
     return valid_ds, partial(jsonl_ds_collate_fn, max_length_per_sample=data_cfg.seq_len)
@@ -76,7 +79,9 @@ def build_train_loader_with_data_type():
     data_cfg = gpc.config.data
     assert data_cfg.type == "tokenized", f"unsupported data type {data_cfg.type}"
     train_ds, train_sampler, train_collate_fn = get_tokenized_train_loader_items(data_cfg)
-    dataset_types = list(["en", "cn", "code"])
+    # names of the per-type training metrics: the sub-folders of the training folder in sorted order, the order of their type ids
+    train_folder = data_cfg.get("train_folder", None)
+    dataset_types = list(get_dataset_type_ids_map(train_folder).keys()) if train_folder else ["en", "cn", "code"]
     # ``data.num_worker`` loader processes pack the next batches while the GPU runs the current step: 4 unless configured, as in
     # the reference (``data/build_dataloader.py:107-110``); a CPU-only host (plumbing / demo runs) loads in the main process
     workers = data_cfg.get("num_worker", 4 if torch.cuda.is_available() else 0)

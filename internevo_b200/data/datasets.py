@@ -324,7 +324,7 @@ class PackedDatasetWithoutCuSeqlen(PackedDataset):
 DATASET_TYPE_IDS_MAP = {"en": 0, "cn": 1, "code": 2}
 
 
-def get_dataset_dict(folder, split="valid") -> Dict[str, Dataset]:
+def get_dataset_dict(folder, split="valid", min_length: int = 50) -> Dict[str, Dataset]:
     """``{sub-folder name: ConcatDataset of its *.bin files whose name contains `split`}`` — one validation set per data
     source, walked in sorted order so every rank builds the same dict (reference ``data/tokenized/dataset.py:9-56``)."""
     assert os.path.exists(folder), f"folder `{folder}` not exists"
@@ -335,7 +335,7 @@ def get_dataset_dict(folder, split="valid") -> Dict[str, Dataset]:
         dirs.sort()
         bins = [os.path.join(root, f) for f in sorted(files) if f.endswith(".bin") and split in f]
         if bins:
-            out[os.path.basename(os.path.normpath(root))] = ConcatDataset([JsonlDataset(b, min_length=0) for b in bins])
+            out[os.path.basename(os.path.normpath(root))] = ConcatDataset([JsonlDataset(b, min_length=min_length) for b in bins])
     return out
 
 
@@ -345,32 +345,53 @@ def get_dataset_type_ids_map(path):
 
 
 def get_dataset_type_id(dataset_type_ids_map, path):
-    matches = [v for k, v in dataset_type_ids_map.items() if f"/{k}/" in path or path.startswith(f"{k}/")]
+    import re
+
+    matches = [v for k, v in dataset_type_ids_map.items()
+               if re.search(rf"/[z_]*{re.escape(k)}/", path) or path.startswith(f"{k}/")]
     assert len(matches) == 1, f"{path} should match exactly one of {list(dataset_type_ids_map)}"
     return matches[0]
 
 
+def _walk_like_rank0(folder):
+    """``os.walk`` of the training folder as RANK 0 sees it, handed to every rank (reference ``packed_dataset.py:427-432``): the
+    datasets are concatenated in that order, and the order is part of the data stream a checkpointed sampler position refers to.
+    The reference materialises the walk before it sorts the sub-folders, so its order is the file system's; it is kept (a run
+    that moves over from the reference, or back, sees the same stream on the same storage), files inside a folder are sorted."""
+    import torch.distributed as dist
+
+    triples = [list(os.walk(folder, followlinks=True))] if gpc.get_global_rank() == 0 else [None]
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast_object_list(triples, src=0)
+    if triples[0] is None:       # single process that is not "rank 0" (tools, tests)
+        triples = [list(os.walk(folder, followlinks=True))]
+    return triples[0]
+
+
 def get_packed_dataset_without_short_length(folder, max_length_per_sample=2048, packed_length=4096, show_progress=False,
                                             min_length=50, min_length_dict=None, pack_sample_into_one=False):
-    """Walk ``folder`` for ``*.bin`` files, pack each, concatenate (reference ``packed_dataset.py:392-480``)."""
+    """Every ``*.bin`` file under ``folder`` becomes one packed dataset (short samples filtered: ``min_length``, or the value of
+    the ``min_length_dict`` key that occurs in the file's path), all concatenated; a token's type id is the position of its
+    top-level sub-folder in the sorted folder listing (reference ``packed_dataset.py:392-480``, ``data/utils.py:11-24``)."""
     assert os.path.exists(folder), f"{folder} does not exist."
     datasets = []
-    for root, dirs, files in os.walk(folder, followlinks=True):
-        dirs.sort()
+    type_ids_map = get_dataset_type_ids_map(folder)
+    for root, _, files in _walk_like_rank0(folder):
         for fn in sorted(files):
             if not fn.endswith(".bin"):
                 continue
             fp = os.path.join(root, fn)
-            catalog = root.replace(folder, "").lstrip("/")
-            type_id = 0
-            if catalog:
-                try:
-                    type_id = get_dataset_type_id(DATASET_TYPE_IDS_MAP, catalog + "/")
-                except AssertionError:
-                    type_id = 0
-            ml = (min_length_dict or {}).get(catalog.split("/")[0] if catalog else "", min_length)
+            hits = [k for k in (min_length_dict or {}) if k in fp]
+            assert len(hits) < 2, f"The file name `{fp}` matched the following resample keys:{hits}"
+            ml = min_length_dict[hits[0]] if hits else min_length
+            try:
+                type_id = get_dataset_type_id(type_ids_map, fp)
+            except AssertionError:      # a .bin directly under `folder`: no sub-folder names it
+                type_id = 0
             ds = JsonlDataset(fp, type_id, min_length=ml)
             if len(ds) == 0:
+                if gpc.is_rank_for_log():
+                    logger.info(f"None of the data in `{fp}` is longer than {ml}")
                 continue
             if ds.num_tokens < packed_length:
                 if gpc.is_rank_for_log():

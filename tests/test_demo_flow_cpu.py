@@ -23,7 +23,7 @@ ckpt = dict(enable_save_ckpt=True, save_ckpt_folder="local:{ckpt}", checkpoint_e
             async_upload=False, oss_snapshot_freq=0)
 data = dict(seq_len=64, micro_num=2, micro_bsz=2, valid_micro_num=1, valid_every=4, pack_sample_into_one=False,
             total_steps={steps}, skip_batches="", rampup_batch_size="", min_length=4, train_folder="{train}",
-            valid_folder="{valid}", empty_cache_and_diag_interval=200, diag_outlier_ratio=1.1)
+            valid_folder="{valid}", valid_min_length=0, empty_cache_and_diag_interval=200, diag_outlier_ratio=1.1)
 grad_scaler = dict(fp16=dict(initial_scale=2**16, min_scale=1, growth_interval=1000), growth_factor=2, backoff_factor=0.5,
                    max_scale=2**24, hysteresis=2)
 hybrid_zero_optimizer = dict(overlap_sync_grad=False, overlap_sync_param=False, reduce_bucket_size=512 * 1024 * 1024,

@@ -185,9 +185,11 @@ def test_validation_sets_per_subfolder(tmp_path):
         _write_bin(str(tmp_path / name / "valid.bin"), n, seed=n)
     _write_bin(str(tmp_path / "zhihu" / "valid2.bin"), 3, seed=1)
     _write_bin(str(tmp_path / "zhihu" / "train.bin"), 7, seed=2)
-    d = get_dataset_dict(str(tmp_path), split="valid")
+    d = get_dataset_dict(str(tmp_path), split="valid", min_length=0)
     assert list(d) == ["baike", "zhihu"] and len(d["zhihu"]) == 12 and len(d["baike"]) == 5
-    assert len(get_dataset_dict(str(tmp_path), split="")["zhihu"]) == 19
+    assert len(get_dataset_dict(str(tmp_path), split="", min_length=0)["zhihu"]) == 19
+    assert not get_dataset_dict(str(tmp_path), split="valid") or \
+        len(get_dataset_dict(str(tmp_path), split="valid")["zhihu"]) < 12      # default: samples under 50 tokens are left out
     assert get_dataset_type_ids_map(str(tmp_path)) == {"baike": 0, "zhihu": 1}
 
 
@@ -200,7 +202,7 @@ def _valid_loader_worker(rank, world, folder):
     from internevo_b200.initialize import initialize_distributed_env
 
     cfg = tiny_config(micro_bsz=2, micro_num=2)
-    cfg["data"].update(valid_folder=folder, valid_micro_num=2)
+    cfg["data"].update(valid_folder=folder, valid_micro_num=2, valid_min_length=0)
     initialize_distributed_env(config=cfg, launcher="torch", seed=5)
     dls = build_valid_loader_with_data_type()
     # zhihu: 12 samples / dp 2 = 6 per rank -> batch min(4, 6) = 4; baike: 5 // 2 = 2 -> batch 2; tiny: 1 // 2 = 0 -> skipped

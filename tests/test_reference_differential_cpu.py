@@ -455,3 +455,49 @@ def test_the_reference_resumes_a_checkpoint_written_here(tmp_path):
         assert abs(a - b) < 2e-6 * max(1.0, abs(b)), (theirs["losses"], losses[4:])
     drift = max(float((final[k] - theirs["final"][k]).abs().max()) for k in final)
     assert drift < 2e-4, drift
+
+
+@pytest.fixture(scope="module")
+def data_folder(tmp_path_factory):
+    import sentencepiece as spm
+
+    work = tmp_path_factory.mktemp("loader")
+    rng = np.random.RandomState(3)
+    words = ["alpha", "beta", "gamma", "delta", "epsilon", "zeta", "eta", "theta", "iota", "kappa"]
+    (work / "corpus.txt").write_text("\n".join(" ".join(rng.choice(words, 12)) for _ in range(300)))
+    spm.SentencePieceTrainer.Train(input=str(work / "corpus.txt"), model_prefix=str(work / "tok"), vocab_size=64, bos_id=1,
+                                   eos_id=2, unk_id=0, pad_id=-1, model_type="bpe", minloglevel=2)
+    for split, lo, hi, n in (("train", 1, 30, 60), ("valid", 25, 60, 40)):      # validation lines long enough for min_length 50
+        for lang, files in (("en", 2), ("cn", 1), ("code", 1)):
+            os.makedirs(work / "data" / split / lang)
+            for i in range(files):
+                (work / "c.txt").write_text("\n".join(" ".join(rng.choice(words, rng.randint(lo, hi))) for _ in range(n)))
+                subprocess.run([sys.executable, os.path.join(ROOT, "tools", "tokenizer.py"), "--text_input_path", str(work / "c.txt"),
+                                "--bin_output_path", str(work / "data" / split / lang / f"part{i}.bin"), "--tokenizer_model",
+                                str(work / "tok.model")], check=True, capture_output=True)
+    return work
+
+
+@pytest.mark.parametrize("dp_rank,pack", [(0, "cut"), (1, "cut"), (0, "one")])
+def test_train_and_validation_loaders_yield_the_references_batches(data_folder, dp_rank, pack):
+    """The data stream of a run: which files form which dataset in which order (the reference concatenates them in the order
+    rank 0's ``os.walk`` finds the folders), the type id of every token (position of its sub-folder in the sorted listing), short-
+    sample filtering (``min_length`` for training, 50 tokens for validation), packing, the sampler's order and the collated batch -
+    the first six training batches and the first two batches of every validation set are identical, tensor by tensor, on both
+    data-parallel ranks and in both packing modes."""
+    ref = _reference_root()
+    if ref is None:
+        pytest.skip("the reference is not installed (baseline/_ref)")
+    out = {}
+    for side, root in (("reference", ref), ("ours", ROOT)):
+        dst = str(data_folder / f"{side}_{dp_rank}_{pack}.json")
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "differential_loader_probe.py"), root,
+                            str(data_folder / "data"), dst] + (["one"] if pack == "one" else []), capture_output=True, text=True,
+                           timeout=600, cwd=str(data_folder), env=dict(os.environ, CUDA_VISIBLE_DEVICES="", PROBE_DP_RANK=str(dp_rank)))
+        assert r.returncode == 0 and "PROBE_OK" in r.stdout, f"{side}: {r.stderr[-3000:]}"
+        out[side] = json.load(open(dst))
+    a, b = out["reference"], out["ours"]
+    assert a["types"] == b["types"] == ["cn", "code", "en"] and a["len"] == b["len"] > 6
+    for i, (x, y) in enumerate(zip(a["batches"], b["batches"])):
+        assert x == y, f"training batch {i} differs"
+    assert sorted(a["valid"]) == sorted(b["valid"]) == ["cn", "code", "en"] and a["valid"] == b["valid"]
