@@ -98,7 +98,8 @@ class AccPerplex:
         right, total, logp = stats[0].item(), stats[1].item(), stats[2].item()
         acc = right / max(total, 1)
         loss = logp / max(total, 1)
-        res = {"acc": round(acc, 4), "perplexity": round(float(torch.exp(torch.tensor(min(loss, 20.0)))), 4)}
+        res = {"acc": round(acc, 4), "perplexity": round(float(torch.exp(torch.tensor(min(loss, 20.0)))), 4),
+               "loss_from_metric": round(loss, 4)}      # the reference's AccPerplex carries its LossWithTypeId result along
         if self.total_type_count > 0:
             dr, dt, dl = stats[3:3 + n], stats[3 + n:3 + 2 * n], stats[3 + 2 * n:3 + 3 * n]
             for i, name in enumerate(self.dataset_types):

@@ -501,3 +501,24 @@ def test_train_and_validation_loaders_yield_the_references_batches(data_folder, 
     for i, (x, y) in enumerate(zip(a["batches"], b["batches"])):
         assert x == y, f"training batch {i} differs"
     assert sorted(a["valid"]) == sorted(b["valid"]) == ["cn", "code", "en"] and a["valid"] == b["valid"]
+
+
+def test_metrics_report_the_references_keys_and_values(tmp_path):
+    """Accuracy, perplexity, ``loss_from_metric`` and the per-type ``acc/`` ``tokens/`` ``loss/`` entries of the step log: every key
+    the reference's ``AccPerplex`` / ``LossWithTypeId`` return is returned here with the same value (this framework adds
+    ``perplexity/<type>``)."""
+    ref = _reference_root()
+    if ref is None:
+        pytest.skip("the reference is not installed (baseline/_ref)")
+    out = {}
+    for side, root in (("reference", ref), ("ours", ROOT)):
+        dst = str(tmp_path / f"{side}.json")
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "differential_metric_probe.py"), root, dst], capture_output=True,
+                           text=True, timeout=600, cwd=str(tmp_path), env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+        assert r.returncode == 0 and "PROBE_OK" in r.stdout, f"{side}: {r.stderr[-3000:]}"
+        out[side] = json.load(open(dst))
+    for part in ("acc", "loss"):
+        theirs, ours = out["reference"][part], out["ours"][part]
+        assert set(theirs) <= set(ours), (part, sorted(set(theirs) - set(ours)))
+        for k, v in theirs.items():
+            assert abs(v - ours[k]) < 1e-4 * max(1.0, abs(v)), (k, v, ours[k])
