@@ -522,3 +522,26 @@ def test_metrics_report_the_references_keys_and_values(tmp_path):
         assert set(theirs) <= set(ours), (part, sorted(set(theirs) - set(ours)))
         for k, v in theirs.items():
             assert abs(v - ours[k]) < 1e-4 * max(1.0, abs(v)), (k, v, ours[k])
+
+
+def test_tokenizer_tool_writes_the_references_bytes(tmp_path):
+    """``tools/tokenizer.py`` of both code bases on the same text with the reference's own SentencePiece model: the ``.bin`` files
+    are byte-identical and the ``.meta`` offsets / lengths equal (kept int64 here - the reference's int32 wraps beyond 2 GiB)."""
+    ref_tool, model = "/root/reference/tools/tokenizer.py", "/root/reference/tools/tokenizer_internlm.model"
+    if not (os.path.exists(ref_tool) and os.path.exists(model)):
+        pytest.skip("the reference's tools folder is not available")
+    rng = np.random.RandomState(5)
+    words = ["alpha", "beta", "gamma", "delta", "epsilon", "zeta", "eta", "theta", "iota", "kappa", "训练", "模型", "数据"]
+    text = tmp_path / "corpus.txt"
+    text.write_text("\n".join(" ".join(rng.choice(words, rng.randint(1, 40))) for _ in range(200)))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, ref_tool, "--text_input_path", str(text), "--bin_output_path", str(tmp_path / "ref.bin")],
+                       capture_output=True, text=True, timeout=600, cwd="/root/reference", env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "tokenizer.py"), "--text_input_path", str(text),
+                        "--bin_output_path", str(tmp_path / "ours.bin"), "--tokenizer_model", model], capture_output=True, text=True,
+                       timeout=600, cwd=str(tmp_path), env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert open(tmp_path / "ref.bin", "rb").read() == open(tmp_path / "ours.bin", "rb").read()
+    a, b = np.load(tmp_path / "ref.bin.meta", allow_pickle=True), np.load(tmp_path / "ours.bin.meta", allow_pickle=True)
+    assert a.shape == b.shape and (a == b).all()
