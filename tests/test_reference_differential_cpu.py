@@ -545,3 +545,62 @@ def test_tokenizer_tool_writes_the_references_bytes(tmp_path):
     assert open(tmp_path / "ref.bin", "rb").read() == open(tmp_path / "ours.bin", "rb").read()
     a, b = np.load(tmp_path / "ref.bin.meta", allow_pickle=True), np.load(tmp_path / "ours.bin.meta", allow_pickle=True)
     assert a.shape == b.shape and (a == b).all()
+
+
+def _our_evaluation(rank, world, ref_file, data):
+    import torch
+
+    import internevo_b200 as fw
+    from common import tiny_config
+    from internevo_b200.data import build_valid_loader_with_data_type
+    from internevo_b200.eval.evaluation import evaluate_on_val_dls
+    from internevo_b200.initialize import initialize_distributed_env
+    from internevo_b200.models.losses import FlashGPTLMLoss
+    from internevo_b200.train import get_scheduler_hooks, initialize_model, initialize_optimizer
+
+    ref = torch.load(ref_file, weights_only=False)
+    cfg = tiny_config(num_layers=2, hidden=32, heads=4, kv_heads=2, vocab=64, seq_len=16, micro_bsz=2, micro_num=2)
+    cfg["model"].update(parallel_output=False, use_flash_attn=False)
+    cfg["data"].update(use_packed_dataset=False, total_steps=10, valid_every=1, valid_micro_num=2, valid_folder=os.path.join(data, "valid"))
+    initialize_distributed_env(config=cfg, launcher="torch", seed=3)
+    model = initialize_model()
+    model.model.load_state_dict(ref["state"], strict=True)
+    opt, b2, lrs = initialize_optimizer(model)
+    crit = FlashGPTLMLoss(parallel_output=False, label_smoothing=0)
+    trainer, _, _, _ = fw.initialize_trainer(model=model, optimizer=opt, criterion=crit, lr_scheduler=lrs, beta2_scheduler=b2,
+                                             scheduler_hooks=get_scheduler_hooks(None, opt, None))
+    scalars = {}
+
+    class Writer:
+        def add_scalar(self, key, value, step):
+            scalars[key] = float(value)
+
+    class Logger:
+        def info(self, *a, **k):
+            pass
+
+        warning = error = info
+
+    val_dls = build_valid_loader_with_data_type()
+    evaluate_on_val_dls(trainer, val_dls, Writer(), Logger(), step_count=3)
+    return scalars, {k: len(v) for k, v in val_dls.items()}, ref["scalars"], ref["sizes"]
+
+
+def test_validation_reports_the_references_numbers(data_folder, tmp_path):
+    """``evaluate_on_val_dls`` of both code bases on the same weights and the same validation folder (three sub-folders): the same
+    validation sets with the same number of batches, and per set the same ``val/<name>_loss`` / ``_acc`` / ``_plex`` scalars."""
+    from common import run_distributed
+
+    ref = _reference_root()
+    if ref is None:
+        pytest.skip("the reference is not installed (baseline/_ref)")
+    dst = str(tmp_path / "eval.pt")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "differential_eval_probe.py"), ref, dst, str(data_folder / "data")],
+                       capture_output=True, text=True, timeout=900, cwd=str(tmp_path), env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert r.returncode == 0 and "PROBE_OK" in r.stdout, r.stderr[-3000:]
+    ours, sizes, theirs, their_sizes = run_distributed(_our_evaluation, 1, dst, str(data_folder / "data"))[0]
+    assert sizes == their_sizes and sorted(sizes) == ["cn", "code", "en"]
+    keys = {k for k in theirs if k != "step"}
+    assert keys == {k for k in ours if k != "step"} and len(keys) == 9
+    for k in keys:
+        assert abs(ours[k] - theirs[k]) < 2e-6 * max(1.0, abs(theirs[k])), (k, ours[k], theirs[k])
