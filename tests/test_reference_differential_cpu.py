@@ -604,3 +604,31 @@ def test_validation_reports_the_references_numbers(data_folder, tmp_path):
     assert keys == {k for k in ours if k != "step"} and len(keys) == 9
     for k in keys:
         assert abs(ours[k] - theirs[k]) < 2e-6 * max(1.0, abs(theirs[k])), (k, ours[k], theirs[k])
+
+
+@pytest.mark.parametrize("family", ["internlm2", "internlm"])
+def test_hf_remote_code_equals_the_references(tmp_path, family):
+    """The Hugging Face model code shipped next to converted weights (``huggingface/<family>_model``) against the reference's
+    (``transformers/<family>_model``, the code on the hub): a model created by the reference's class saves its ``state_dict``, ours
+    loads it without a missing or unexpected key and computes the same logits."""
+    import torch
+
+    theirs = f"/root/reference/transformers/{family}_model"
+    if not os.path.isdir(theirs):
+        pytest.skip("the reference's transformers folder is not available")
+    prefix = str(tmp_path / family)
+    # ours the way ``tools/convert2hf.py::install_remote_code`` puts it next to converted weights: one flat folder (the v1 files
+    # import the shared helpers from the InternLM2 files)
+    flat = tmp_path / "remote_code"
+    os.makedirs(flat)
+    for sub in ("internlm2_model", f"{family}_model"):
+        for fn in os.listdir(os.path.join(ROOT, "huggingface", sub)):
+            if fn.endswith(".py") and fn != "__init__.py":
+                src = open(os.path.join(ROOT, "huggingface", sub, fn)).read().replace("from ..internlm2_model.", "from .")
+                (flat / fn).write_text(src)
+    for which, base in (("ref", theirs), ("ours", str(flat))):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "differential_hf_probe.py"), which, base, family, prefix],
+                           capture_output=True, text=True, timeout=600, cwd=str(tmp_path), env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+        assert r.returncode == 0 and "PROBE_OK" in r.stdout, f"{which}: {r.stderr[-3000:]}"
+    a, b = torch.load(prefix + ".ref.logits"), torch.load(prefix + ".ours.logits")
+    assert a.shape == b.shape and float((a - b).abs().max()) < 2e-6 * max(1.0, float(a.abs().max()))
