@@ -632,3 +632,43 @@ def test_hf_remote_code_equals_the_references(tmp_path, family):
         assert r.returncode == 0 and "PROBE_OK" in r.stdout, f"{which}: {r.stderr[-3000:]}"
     a, b = torch.load(prefix + ".ref.logits"), torch.load(prefix + ".ours.logits")
     assert a.shape == b.shape and float((a - b).abs().max()) < 2e-6 * max(1.0, float(a.abs().max()))
+
+
+def test_converted_checkpoint_scores_like_the_training_model_in_the_references_hf_class(tmp_path):
+    """End to end across both code bases: the reference's TRAINING model (CPU, torch attention) produces weights and logits;
+    ``tools/convert2hf.py`` of this repository converts the checkpoint folder; the reference's HF class
+    (``transformers/internlm2_model``) loads the result and returns the training model's logits - the converter (GQA ``wqkv``
+    un-interleaving, rotary row permutation, names) is right with respect to both ends of the reference."""
+    import torch
+    from safetensors.torch import load_file
+
+    ref, hf_code = _reference_root(), "/root/reference/transformers/internlm2_model"
+    if ref is None or not os.path.isdir(hf_code):
+        pytest.skip("the reference (and its transformers folder) is not available")
+    dst = str(tmp_path / "train_model.pt")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "differential_model_probe.py"), ref, "INTERNLM2_PUBLIC", dst],
+                       capture_output=True, text=True, timeout=600, cwd=str(tmp_path), env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert r.returncode == 0 and "PROBE_OK" in r.stdout, r.stderr[-3000:]
+    probe = torch.load(dst, weights_only=False)
+    ckpt = tmp_path / "ckpt"
+    os.makedirs(ckpt)
+    torch.save(probe["state"], ckpt / "model_tp0_pp0.pt")
+    torch.save(dict(hidden_size=32, num_layers=2, num_attention_heads=4, num_kv_attention_heads=2, vocab_size=64, mlp_ratio=2,
+                    layer_norm_epsilon=1e-5, no_bias=True, embed_split_hidden=True, norm_type="rmsnorm", dtype=torch.float32),
+               ckpt / "model_config.pt")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "convert2hf.py"), "--src", str(ckpt), "--tgt", str(tmp_path / "hf"),
+                        "--dtype", "float32"], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-3000:]
+    weights = {}
+    for fn in os.listdir(tmp_path / "hf"):
+        if fn.endswith(".safetensors"):
+            weights.update(load_file(str(tmp_path / "hf" / fn)))
+    prefix = str(tmp_path / "conv")
+    torch.save(weights, prefix + ".hf_weights")
+    torch.save(probe["ids"], prefix + ".ids")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "differential_hf_probe.py"), "load", hf_code, "internlm2", prefix],
+                       capture_output=True, text=True, timeout=600, cwd=str(tmp_path), env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert r.returncode == 0 and "PROBE_OK" in r.stdout, r.stderr[-3000:]
+    hf_logits, train_logits = torch.load(prefix + ".load.logits"), probe["logits"]
+    assert hf_logits.shape == train_logits.shape
+    assert float((hf_logits - train_logits).abs().max()) < 2e-6 * max(1.0, float(train_logits.abs().max()))
