@@ -30,7 +30,7 @@ def load(name):
 
 cfg_mod, model_mod = load(f"configuration_{family}"), load(f"modeling_{family}")
 name = "InternLM2" if family == "internlm2" else "InternLM"
-kw = dict(vocab_size=64, hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=4,
+kw = dict(vocab_size=64, hidden_size=32, intermediate_size=int(os.environ.get("PROBE_INTERMEDIATE", "64")), num_hidden_layers=2, num_attention_heads=4,
           max_position_embeddings=64, rms_norm_eps=1e-5, attn_implementation="eager")
 if family == "internlm2":
     kw.update(num_key_value_heads=2, bias=False, rope_theta=10000)

@@ -3,7 +3,7 @@
 has no CPU mode: the accelerator's RNG / device hooks are pointed at the CPU generator, a one-rank gloo group stands in for
 every parallel mode, nothing in its model or op code is touched.
 
-    python differential_model_probe.py <reference root> <model type> <output .pt>
+    python differential_model_probe.py <reference root> <model type> <output .pt> [<.pt with "state" and "ids" to use instead>]
 """
 import os
 import sys
@@ -38,7 +38,8 @@ for mode in ParallelMode:
     gpc._groups[mode], gpc._ranks_in_group[mode] = dist.group.WORLD, [0]
 
 model_cfg = dict(checkpoint=False, num_chunks=1, num_attention_heads=4, embed_split_hidden=True, vocab_size=64, embed_grad_scale=1,
-                 parallel_output=False, hidden_size=32, num_layers=2, mlp_ratio=2, apply_post_layer_norm=False,
+                 parallel_output=False, hidden_size=32, num_layers=2, mlp_ratio=float(os.environ.get("PROBE_MLP_RATIO", "2")),
+                 apply_post_layer_norm=False,
                  dtype=torch.float32, norm_type="rmsnorm", layer_norm_epsilon=1e-5, use_flash_attn=False)
 extra = {}
 if family in ("INTERNLM2_PUBLIC", "LLAMA2"):
@@ -64,9 +65,13 @@ model = MODEL_INITIALIZER.get_module(module_name=family)(**model_cfg).float().ev
 for p in model.parameters():            # biases / norm weights start at 0 / 1: give every parameter a value that matters
     if p.dim() == 1:
         p.data.add_(0.1 * torch.randn_like(p))
+given = torch.load(sys.argv[4], weights_only=False) if len(sys.argv) > 4 else None
+if given is not None:       # weights that came from somewhere else (a reverted HF model): they must fit key for key
+    missing, unexpected = model.load_state_dict(given["state"], strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
 state = {k: v.clone() for k, v in model.state_dict().items()}
 torch.manual_seed(1)
-ids = torch.randint(1, 64, (2, 16))
+ids = given["ids"] if given is not None else torch.randint(1, 64, (2, 16))
 with torch.no_grad():
     out = model(input_ids=ids)
 moe_losses = None

@@ -672,3 +672,39 @@ def test_converted_checkpoint_scores_like_the_training_model_in_the_references_h
     hf_logits, train_logits = torch.load(prefix + ".load.logits"), probe["logits"]
     assert hf_logits.shape == train_logits.shape
     assert float((hf_logits - train_logits).abs().max()) < 2e-6 * max(1.0, float(train_logits.abs().max()))
+
+
+def test_reverted_hf_model_scores_alike_in_the_references_training_model(tmp_path):
+    """The way back: a model of the reference's HF class -> ``tools/revert_hf.py`` -> the reference's TRAINING model loads the
+    resulting ``model_tp0_pp0.pt`` key for key and returns the HF model's logits."""
+    import torch
+    from safetensors.torch import save_file
+
+    ref, hf_code = _reference_root(), "/root/reference/transformers/internlm2_model"
+    if ref is None or not os.path.isdir(hf_code):
+        pytest.skip("the reference (and its transformers folder) is not available")
+    prefix, env = str(tmp_path / "hf"), dict(os.environ, CUDA_VISIBLE_DEVICES="", PROBE_INTERMEDIATE="256", PROBE_MLP_RATIO="8")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "differential_hf_probe.py"), "ref", hf_code, "internlm2", prefix],
+                       capture_output=True, text=True, timeout=600, cwd=str(tmp_path), env=env)
+    assert r.returncode == 0 and "PROBE_OK" in r.stdout, r.stderr[-3000:]
+    hf_dir = tmp_path / "hf_model"
+    os.makedirs(hf_dir)
+    weights = {k: v.contiguous() for k, v in torch.load(prefix + ".weights").items() if "inv_freq" not in k}
+    save_file(weights, str(hf_dir / "model.safetensors"))
+    json.dump(dict(hidden_size=32, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, vocab_size=64,
+                   intermediate_size=256, rms_norm_eps=1e-5, rope_theta=10000, bias=False, model_type="internlm2",
+                   architectures=["InternLM2ForCausalLM"]), open(hf_dir / "config.json", "w"))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "revert_hf.py"), "--src", str(hf_dir), "--tgt", str(tmp_path / "ckpt"),
+                        "--tp_size", "1", "--embed_split"], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-3000:]
+    torch.manual_seed(1)
+    ids = torch.randint(1, 64, (2, 12))          # the ids differential_hf_probe.py scored
+    given = str(tmp_path / "given.pt")
+    torch.save({"state": torch.load(tmp_path / "ckpt" / "model_tp0_pp0.pt", weights_only=False), "ids": ids}, given)
+    dst = str(tmp_path / "train_model.pt")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "differential_model_probe.py"), ref, "INTERNLM2_PUBLIC", dst, given],
+                       capture_output=True, text=True, timeout=600, cwd=str(tmp_path), env=env)
+    assert r.returncode == 0 and "PROBE_OK" in r.stdout, r.stderr[-3000:]
+    train_logits, hf_logits = torch.load(dst, weights_only=False)["logits"], torch.load(prefix + ".ref.logits")
+    assert train_logits.shape == hf_logits.shape
+    assert float((train_logits - hf_logits).abs().max()) < 2e-6 * max(1.0, float(hf_logits.abs().max()))

@@ -35,7 +35,8 @@ def from_hf(hf, cfg, interleaved_rope: bool):
     H, Hkv = cfg["num_attention_heads"], cfg.get("num_key_value_heads", cfg["num_attention_heads"])
     d = cfg["hidden_size"] // H
     full = {}
-    if cfg.get("model_type") == "internlm2":
+    # InternLM2 by its config, or - a config.json without ``model_type`` - by its fused ``wqkv`` projections
+    if cfg.get("model_type") == "internlm2" or any(".attention.wqkv." in k for k in hf):
         for k, v in hf.items():
             k = k[6:] if k.startswith("model.") else k
             if k.endswith("attention.wqkv.weight") and interleaved_rope:
