@@ -708,3 +708,25 @@ def test_reverted_hf_model_scores_alike_in_the_references_training_model(tmp_pat
     train_logits, hf_logits = torch.load(dst, weights_only=False)["logits"], torch.load(prefix + ".ref.logits")
     assert train_logits.shape == hf_logits.shape
     assert float((train_logits - hf_logits).abs().max()) < 2e-6 * max(1.0, float(hf_logits.abs().max()))
+
+
+def test_alpaca_tokenizer_writes_the_references_bytes(tmp_path):
+    """``tools/alpaca_tokenizer.py`` of both code bases on the same instruction data: chat template, negated prompt tokens, end-of-
+    turn ids, truncation and the train / validation split give byte-identical ``dataset.bin`` files."""
+    ref_tool, model = "/root/reference/tools/alpaca_tokenizer.py", "/root/reference/tools/tokenizer_internlm.model"
+    if not (os.path.exists(ref_tool) and os.path.exists(model)):
+        pytest.skip("the reference's tools folder is not available")
+    rng = np.random.RandomState(0)
+    words = ["alpha", "beta", "gamma", "delta", "epsilon", "zeta", "数据", "模型"]
+    data = [{"instruction": " ".join(rng.choice(words, 5)), "input": " ".join(rng.choice(words, 3)) if i % 2 else "",
+             "output": " ".join(rng.choice(words, rng.randint(3, 2500 if i == 7 else 12)))} for i in range(60)]   # one over-long answer
+    json.dump(data, open(tmp_path / "alpaca.json", "w"))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for tool, out, cwd in ((ref_tool, "ref", "/root/reference"), (os.path.join(ROOT, "tools", "alpaca_tokenizer.py"), "ours", str(tmp_path))):
+        r = subprocess.run([sys.executable, tool, str(tmp_path / "alpaca.json"), str(tmp_path / out), model, "--split_ratio", "0.1"],
+                           capture_output=True, text=True, timeout=600, cwd=cwd, env=env)
+        assert r.returncode == 0, r.stderr[-2000:]
+    for split in ("train", "valid"):
+        a = open(tmp_path / "ref" / split / "en" / "dataset.bin", "rb").read()
+        b = open(tmp_path / "ours" / split / "en" / "dataset.bin", "rb").read()
+        assert a == b and len(a) > 0, split

@@ -37,15 +37,28 @@ def main():
     p.add_argument("--eoa_id", type=int, default=103166)
     p.add_argument("--nl_id", type=int, default=13)
     p.add_argument("--max_len", type=int, default=2048)
-    p.add_argument("--seed", type=int, default=1024)
+    p.add_argument("--shuffle_seed", type=int, default=None,
+                   help="shuffle the samples with this seed and cut the first split_ratio off as validation set; default: the "
+                        "reference's split (below)")
     a = p.parse_args()
     sp = load_sp(a.tokenizer_path)
     data = json.load(open(a.dataset_path, encoding="utf-8"))
     samples = [tokenize_sample(d, sp, a.eoh_id, a.eoa_id, a.nl_id, a.max_len) for d in data]
-    random.Random(a.seed).shuffle(samples)
-    n_valid = int(len(samples) * a.split_ratio)
-    n_tr = write_bin_and_meta(samples[n_valid:], os.path.join(a.output_path, "train", "en", "dataset.bin"))
-    n_va = write_bin_and_meta(samples[:n_valid], os.path.join(a.output_path, "valid", "en", "dataset.bin"))
+    if a.shuffle_seed is not None:
+        random.Random(a.shuffle_seed).shuffle(samples)
+        n_valid = int(len(samples) * a.split_ratio)
+        train, valid = samples[n_valid:], samples[:n_valid]
+    else:
+        # the reference's split (``tools/alpaca_tokenizer.py:123-139``): file order is kept, the validation samples are the indices
+        # numpy draws WITH replacement under seed 0 - same files byte for byte, duplicates in the draw make the set a bit smaller
+        import numpy as np
+
+        np.random.seed(0)
+        picked = set(np.random.choice(range(len(samples)), int(len(samples) * a.split_ratio)).tolist())
+        train = [s for i, s in enumerate(samples) if i not in picked]
+        valid = [s for i, s in enumerate(samples) if i in picked]
+    n_tr = write_bin_and_meta(train, os.path.join(a.output_path, "train", "en", "dataset.bin"))
+    n_va = write_bin_and_meta(valid, os.path.join(a.output_path, "valid", "en", "dataset.bin"))
     print(f"train samples: {n_tr}  valid samples: {n_va}")
 
 
