@@ -124,7 +124,7 @@ def evaluate_on_val_dls(trainer, val_dls, writer, logger, step_count, update_pan
                     n += 1
             if n > 0:
                 res = val_metric.get_metric()
-                val_loss = val_loss / n
+                val_loss = val_loss / (n + 1e-6)      # the reference's divisor (``eval/evaluation.py:115``)
                 if gpc.is_rank_for_log():
                     infos = {"step": step_count, f"val/{val_name}_loss": val_loss, f"val/{val_name}_acc": res["acc"],
                              f"val/{val_name}_plex": res["perplexity"]}
