@@ -603,7 +603,9 @@ def test_validation_reports_the_references_numbers(data_folder, tmp_path):
     keys = {k for k in theirs if k != "step"}
     assert keys == {k for k in ours if k != "step"} and len(keys) == 9
     for k in keys:
-        assert abs(ours[k] - theirs[k]) < 1e-6 * max(1.0, abs(theirs[k])), (k, ours[k], theirs[k])
+        # accuracy / perplexity are reported rounded to 4 decimals: a value on a rounding boundary may land one step apart
+        tol = 1.01e-4 if k.endswith(("_acc", "_plex")) else 1e-6 * max(1.0, abs(theirs[k]))
+        assert abs(ours[k] - theirs[k]) <= tol, (k, ours[k], theirs[k])
 
 
 @pytest.mark.parametrize("family", ["internlm2", "internlm"])
